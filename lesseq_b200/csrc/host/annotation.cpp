@@ -1,0 +1,309 @@
+// Host front end: LH_GENE_TXT + UCSC_GENE2ISOFORM -> event model.
+//
+// What the reference does at count/count.cpp:136-258 (and identically solve/solve.cpp:152-412
+// for these two formats), restated over flat vectors:
+//   * forms file: one form per '\n'-terminated line (an unterminated last line is ignored, as
+//     the reference's `getline && !eof` loops do); whitespace separated
+//     name chrom strand txStart txEnd exonCount exonStarts exonEnds.
+//   * map file: `event_id form_name` per line; events are the distinct event ids in bytewise
+//     lexicographic order and [begin,end) selects by that rank (count.cpp:204-215).
+//   * per event: atomic segments (splicing_graph.h:88-169), per-form segment lists
+//     (:318-361), span = [min exon start, max exon end] (count.cpp:246,374-375), chromosome and
+//     strand of the first form (:239-242); per chromosome the merged exon union of ALL
+//     selected events (count.cpp:244) -- the read load filter.
+#include "annotation.hpp"
+
+#include <algorithm>
+#include <climits>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <set>
+
+namespace lsqh {
+
+uint32_t Dictionary::intern(const std::string &s) {
+    auto it = index.find(s);
+    if (it != index.end()) return it->second;
+    uint32_t id = (uint32_t)names.size();
+    names.push_back(s);
+    index.emplace(s, id);
+    return id;
+}
+
+std::vector<const char *> Dictionary::c_ptrs() const {
+    std::vector<const char *> p;
+    for (auto &n : names) p.push_back(n.c_str());
+    return p;
+}
+
+// interval_list.hpp:462-503.  Every boundary inside [s,e) disappears; s becomes a start unless
+// it sits in (start,end] of an existing interval, e becomes an end under the same test.
+void IntervalSet::add(long s, long e) {
+    if (!(s < e)) return;
+    auto rank = [](const std::vector<long> &v, long x) {
+        return (long)(std::lower_bound(v.begin(), v.end(), x) - v.begin());
+    };
+    long starts_lt_s = rank(starts, s), ends_lt_s = rank(ends, s);
+    long starts_lt_e = rank(starts, e), ends_lt_e = rank(ends, e);
+    bool s_inside = (starts_lt_s - ends_lt_s) == 1;
+    bool e_inside = (starts_lt_e - ends_lt_e) == 1;
+    starts.erase(starts.begin() + starts_lt_s, starts.begin() + starts_lt_e);
+    ends.erase(ends.begin() + ends_lt_s, ends.begin() + ends_lt_e);
+    if (!s_inside) starts.insert(starts.begin() + starts_lt_s, s);
+    if (!e_inside) ends.insert(ends.begin() + ends_lt_s, e);
+}
+
+bool IntervalSet::contains(long s, long e) const {  // interval_list.hpp:396-422
+    if (!(s < e)) return true;
+    long i = (long)(std::upper_bound(starts.begin(), starts.end(), s) - starts.begin()) - 1;
+    return i >= 0 && ends[i] >= e;
+}
+
+namespace {
+
+typedef std::pair<long, long> Seg;
+
+// Cut the segment that strictly contains p.
+void split_at(std::vector<Seg> &v, long p) {
+    for (size_t i = 0; i < v.size(); ++i) {
+        if (v[i].first < p && p < v[i].second) {
+            Seg right(p, v[i].second);
+            v[i].second = p;
+            v.insert(v.begin() + i + 1, right);
+            return;
+        }
+        if (v[i].first >= p) return;
+    }
+}
+
+// ExonSet::insert (splicing_graph.h:88-169) as an arrangement update: existing segments are
+// cut at the exon's end points and the parts of the exon not yet covered become new segments.
+// A zero-length exon only cuts the segment it falls strictly inside (if one exists already).
+void insert_exon(std::vector<Seg> &v, long s, long e) {
+    split_at(v, s);
+    if (e != s) split_at(v, e);
+    if (!(s < e)) return;
+    std::vector<Seg> gaps;
+    long cur = s;
+    for (size_t i = 0; i < v.size() && v[i].first < e; ++i) {
+        if (v[i].second <= s) continue;
+        if (v[i].first > cur) gaps.push_back(Seg(cur, v[i].first));
+        cur = std::max(cur, v[i].second);
+    }
+    if (cur < e) gaps.push_back(Seg(cur, e));
+    for (auto &g : gaps) v.insert(std::upper_bound(v.begin(), v.end(), g), g);
+}
+
+struct FileLines {  // '\n'-terminated lines only
+    std::string buf;
+    bool ok = false;
+    explicit FileLines(const char *path) {
+        FILE *f = fopen(path, "rb");
+        if (!f) return;
+        char tmp[1 << 16];
+        size_t n;
+        while ((n = fread(tmp, 1, sizeof tmp, f)) > 0) buf.append(tmp, n);
+        fclose(f);
+        ok = true;
+    }
+    template <class F>
+    void each(F fn) const {
+        size_t i = 0;
+        while (i < buf.size()) {
+            size_t j = buf.find('\n', i);
+            if (j == std::string::npos) break;  // unterminated last line: dropped
+            fn(buf.data() + i, j - i);
+            i = j + 1;
+        }
+    }
+};
+
+inline bool is_ws(char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\v' || c == '\f' || c == '\n'; }
+
+// istream >> string tokenisation
+struct Tokens {
+    const char *p, *end;
+    Tokens(const char *s, size_t n) : p(s), end(s + n) {}
+    bool next(std::string &out) {
+        while (p < end && is_ws(*p)) ++p;
+        if (p == end) return false;
+        const char *b = p;
+        while (p < end && !is_ws(*p)) ++p;
+        out.assign(b, p - b);
+        return true;
+    }
+};
+
+bool parse_long_token(const std::string &t, long &v) {
+    if (t.empty()) return false;
+    char *endp = nullptr;
+    v = strtol(t.c_str(), &endp, 10);
+    return endp != t.c_str() && *endp == '\0';
+}
+
+void split_exon_list(const std::string &s, std::vector<long> &out) {  // count.cpp:154-168
+    size_t i = 0;
+    while (i < s.size()) {
+        size_t j = s.find(',', i);
+        if (j == std::string::npos) j = s.size();
+        if (j > i) out.push_back(atol(s.substr(i, j - i).c_str()));
+        i = j + 1;
+    }
+}
+
+bool fits_i32(long v) { return v >= INT32_MIN && v <= INT32_MAX; }
+
+}  // namespace
+
+int load_annotation(const char *forms_path, const char *map_path, uint64_t begin, uint64_t end,
+                    uint64_t shard_begin, uint64_t shard_end, lsqh_annotation &A) {
+    FileLines ff(forms_path);
+    if (!ff.ok || ff.buf.empty()) {
+        set_error(std::string("cannot read forms file ") + forms_path);
+        return LSQ_ERR_IO;
+    }
+    std::vector<FormRow> rows;
+    ff.each([&](const char *s, size_t n) {
+        Tokens tk(s, n);
+        FormRow r;
+        std::string tx0, tx1, cnt, es, ee;
+        bool ok = tk.next(r.name) && tk.next(r.chrom) && tk.next(r.strand);
+        long v;
+        ok = ok && tk.next(tx0) && parse_long_token(tx0, v);
+        ok = ok && tk.next(tx1) && parse_long_token(tx1, v);
+        if (ok && tk.next(cnt) && parse_long_token(cnt, v) && v >= 0) {
+            r.exon_count = (uint64_t)v;
+            if (tk.next(es)) split_exon_list(es, r.starts);
+            if (tk.next(ee)) split_exon_list(ee, r.ends);
+        }
+        rows.push_back(std::move(r));
+    });
+    std::unordered_map<std::string, size_t> name2row;  // later duplicates win (count.cpp:176-179)
+    for (size_t i = 0; i < rows.size(); ++i) name2row[rows[i].name] = i;
+
+    FileLines mf(map_path);
+    if (!mf.ok || mf.buf.empty()) {
+        set_error(std::string("cannot read map file ") + map_path);
+        return LSQ_ERR_IO;
+    }
+    std::map<std::string, std::vector<long> > ev2rows;  // std::map: bytewise lexicographic order
+    mf.each([&](const char *s, size_t n) {
+        Tokens tk(s, n);
+        std::string g, f;
+        tk.next(g);
+        tk.next(f);
+        auto it = name2row.find(f);
+        ev2rows[g].push_back(it == name2row.end() ? -1 : (long)it->second);
+    });
+
+    std::vector<const std::pair<const std::string, std::vector<long> > *> selected;
+    {
+        uint64_t rank = 0;
+        for (auto &kv : ev2rows) {
+            if (rank >= begin && rank < end) selected.push_back(&kv);
+            ++rank;
+        }
+    }
+    A.n_selected = selected.size();
+    shard_end = std::min<uint64_t>(shard_end, selected.size());
+    shard_begin = std::min(shard_begin, shard_end);
+
+    std::vector<IntervalSet> covered;  // by chromosome id
+    A.ev_seg_off.push_back(0);
+    A.ev_form_off.push_back(0);
+    A.ev_name_off.push_back(0);
+    A.form_seg_off.push_back(0);
+    for (uint64_t g = 0; g < selected.size(); ++g) {
+        const std::string &gname = selected[g]->first;
+        const std::vector<long> &fr = selected[g]->second;
+        const bool in_shard = g >= shard_begin && g < shard_end;
+        std::vector<Seg> segs;
+        long gs = LONG_MAX, ge = LONG_MIN;
+        for (long ri : fr) {
+            if (ri < 0) {
+                set_error("map file names a form that is not in the forms file (event " + gname + ")");
+                return LSQ_ERR_ARG;
+            }
+            const FormRow &r = rows[ri];
+            if (r.exon_count > r.starts.size() || r.exon_count > r.ends.size()) {
+                set_error("form " + r.name + ": exonCount exceeds the exon lists");
+                return LSQ_ERR_ARG;
+            }
+            uint32_t cid = A.chroms.intern(r.chrom);
+            if (covered.size() <= cid) covered.resize(cid + 1);
+            for (uint64_t i = 0; i < r.exon_count; ++i) {
+                long s = r.starts[i], e = r.ends[i];
+                if (s > e) {
+                    set_error("form " + r.name + ": exon start > end (reference: assertion failure)");
+                    return LSQ_ERR_ARG;
+                }
+                if (!fits_i32(s) || !fits_i32(e)) {
+                    set_error("form " + r.name + ": coordinate outside int32");
+                    return LSQ_ERR_RANGE;
+                }
+                covered[cid].add(s, e);
+                if (in_shard) insert_exon(segs, s, e);
+                if (s < e) {
+                    gs = std::min(gs, s);
+                    ge = std::max(ge, e);
+                }
+            }
+        }
+        if (!in_shard) continue;
+        if (fr.empty() || gs == LONG_MAX) {
+            set_error("event " + gname + " has no exon (reference: undefined behaviour)");
+            return LSQ_ERR_ARG;
+        }
+        if (fr.size() > LSQ_MAX_FORMS_PER_EVENT) {
+            set_error("event " + gname + " has more than 64 forms");
+            return LSQ_ERR_RANGE;
+        }
+        const FormRow &first = rows[fr[0]];
+        A.ev_name.push_back(gname);
+        A.ev_names_pool += gname;
+        A.ev_name_off.push_back((uint32_t)A.ev_names_pool.size());
+        A.ev_chrom.push_back(A.chroms.intern(first.chrom));
+        A.ev_strand.push_back(A.strands.intern(first.strand));
+        A.ev_gs.push_back((int32_t)gs);
+        A.ev_ge.push_back((int32_t)ge);
+        for (auto &sg : segs) {
+            A.seg_start.push_back((int32_t)sg.first);
+            A.seg_end.push_back((int32_t)sg.second);
+        }
+        A.ev_seg_off.push_back((uint32_t)A.seg_start.size());
+        for (long ri : fr) {  // build_isoform_array, splicing_graph.h:322-360
+            const FormRow &r = rows[ri];
+            uint64_t cursor = 0, len = 0;
+            for (size_t si = 0; si < segs.size(); ++si) {
+                for (uint64_t i = cursor; i < r.exon_count; ++i) {
+                    if (r.starts[i] <= segs[si].first && segs[si].second <= r.ends[i]) {
+                        A.form_seg_idx.push_back((uint32_t)si);
+                        len += (uint64_t)(segs[si].second - segs[si].first);
+                        cursor = i;
+                        break;
+                    }
+                }
+            }
+            A.form_seg_off.push_back((uint32_t)A.form_seg_idx.size());
+            A.form_name.push_back(r.name);
+            A.form_len.push_back(len);
+        }
+        A.ev_form_off.push_back((uint32_t)A.form_name.size());
+    }
+    if (covered.size() < A.chroms.names.size()) covered.resize(A.chroms.names.size());
+    A.cov_off.push_back(0);
+    for (auto &c : covered) {
+        for (size_t i = 0; i < c.starts.size(); ++i) {
+            A.cov_start.push_back((int32_t)c.starts[i]);
+            A.cov_end.push_back((int32_t)c.ends[i]);
+        }
+        A.cov_off.push_back((uint32_t)A.cov_start.size());
+    }
+    A.chrom_ptrs = A.chroms.c_ptrs();
+    A.strand_ptrs = A.strands.c_ptrs();
+    return LSQ_OK;
+}
+
+}  // namespace lsqh

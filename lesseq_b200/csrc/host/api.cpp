@@ -1,0 +1,390 @@
+// Host front end entry points (lsqh_* of include/lesseq_b200.h) and the drop-in bodies of the
+// reference's two programs: same positional arguments, same stdout tables, same exit codes
+// (count/count.cpp:88-501, solve/solve.cpp:102-856; only the LH_GENE_TXT / UCSC_GENE2ISOFORM /
+// MRF_SINGLE branches).  All counting and estimation is done by the lsq_* device path.
+#include <cerrno>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <string>
+#include <vector>
+
+#include "annotation.hpp"
+#include "mrf.hpp"
+
+extern "C" {
+
+int lsqh_annotation_load(const char *forms_path, const char *map_path, uint64_t begin, uint64_t end,
+                         uint64_t shard_begin, uint64_t shard_end, lsqh_annotation **out) {
+    if (!forms_path || !map_path || !out) {
+        lsqh::set_error("lsqh_annotation_load: null argument");
+        return LSQ_ERR_ARG;
+    }
+    lsqh_annotation *a = new lsqh_annotation();
+    int rc = lsqh::load_annotation(forms_path, map_path, begin, end, shard_begin, shard_end, *a);
+    if (rc) {
+        delete a;
+        return rc;
+    }
+    *out = a;
+    return LSQ_OK;
+}
+
+void lsqh_annotation_free(lsqh_annotation *a) { delete a; }
+
+int lsqh_annotation_tables(const lsqh_annotation *a, lsq_event_tables *t) {
+    if (!a || !t) {
+        lsqh::set_error("lsqh_annotation_tables: null argument");
+        return LSQ_ERR_ARG;
+    }
+    memset(t, 0, sizeof *t);
+    t->n_events = (uint32_t)a->ev_chrom.size();
+    t->n_forms = (uint32_t)a->form_name.size();
+    t->n_segments = (uint32_t)a->seg_start.size();
+    t->n_chroms = (uint32_t)a->chroms.names.size();
+    t->n_strands = (uint32_t)a->strands.names.size();
+    t->ev_chrom = a->ev_chrom.data();
+    t->ev_strand = a->ev_strand.data();
+    t->ev_gs = a->ev_gs.data();
+    t->ev_ge = a->ev_ge.data();
+    t->ev_seg_off = a->ev_seg_off.data();
+    t->ev_form_off = a->ev_form_off.data();
+    t->ev_name_off = a->ev_name_off.data();
+    t->ev_names = a->ev_names_pool.data();
+    t->seg_start = a->seg_start.data();
+    t->seg_end = a->seg_end.data();
+    t->form_seg_off = a->form_seg_off.data();
+    t->form_seg_idx = a->form_seg_idx.data();
+    t->cov_off = a->cov_off.data();
+    t->cov_start = a->cov_start.data();
+    t->cov_end = a->cov_end.data();
+    t->chrom_names = a->chrom_ptrs.data();
+    t->strand_names = a->strand_ptrs.data();
+    return LSQ_OK;
+}
+
+const char *lsqh_event_name(const lsqh_annotation *a, uint32_t e) {
+    return (a && e < a->ev_name.size()) ? a->ev_name[e].c_str() : "";
+}
+const char *lsqh_form_name(const lsqh_annotation *a, uint32_t f) {
+    return (a && f < a->form_name.size()) ? a->form_name[f].c_str() : "";
+}
+uint64_t lsqh_form_length(const lsqh_annotation *a, uint32_t f) {
+    return (a && f < a->form_len.size()) ? a->form_len[f] : 0;
+}
+
+int lsqh_mrf_parse(const char *path, lsqh_reads **out) {
+    if (!path || !out) {
+        lsqh::set_error("lsqh_mrf_parse: null argument");
+        return LSQ_ERR_ARG;
+    }
+    lsqh_reads *r = new lsqh_reads();
+    int rc = lsqh::parse_mrf(path, *r);
+    if (rc) {
+        delete r;
+        return rc;
+    }
+    *out = r;
+    return LSQ_OK;
+}
+
+void lsqh_reads_free(lsqh_reads *r) { delete r; }
+
+int lsqh_reads_view(const lsqh_reads *r, lsq_packed_reads *v) {
+    if (!r || !v) {
+        lsqh::set_error("lsqh_reads_view: null argument");
+        return LSQ_ERR_ARG;
+    }
+    memset(v, 0, sizeof *v);
+    v->n_reads = r->read_cs.size();
+    v->n_blocks = r->blk_cs.size();
+    v->blk_off = r->blk_off.data();
+    v->blk = r->blk.data();
+    v->read_cs = r->read_cs.data();
+    v->blk_cs = r->any_mixed ? r->blk_cs.data() : nullptr;
+    v->line_num = r->line_num.data();
+    v->n_chrom_names = (uint32_t)r->chroms.names.size();
+    v->n_strand_names = (uint32_t)r->strands.names.size();
+    v->chrom_names = r->chrom_ptrs.data();
+    v->strand_names = r->strand_ptrs.data();
+    v->on_device = 0;
+    return LSQ_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// Command line programs
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+long g_log_level = 2;  // LogLevel::info (jsc/util/log.hpp:22-36)
+const char *LEVELS[] = {"ERROR", "WARNING", "INFO", "DEBUG"};
+
+void logf(int level, const char *fmt, ...) {  // log.hpp:58-79 line format, stderr
+    if (level > g_log_level) return;
+    time_t raw;
+    time(&raw);
+    struct tm *ti = localtime(&raw);
+    char msg[2048];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(msg, sizeof msg, fmt, ap);
+    va_end(ap);
+    fprintf(stderr, "[LOG %d-%02d-%02d %02d:%02d:%02d %s] %s\n", ti->tm_year + 1900, ti->tm_mon + 1, ti->tm_mday,
+            ti->tm_hour, ti->tm_min, ti->tm_sec, LEVELS[level], msg);
+    fflush(stderr);
+}
+
+bool lex_ulong(const char *s, unsigned long &out) {  // boost::lexical_cast<unsigned long>
+    if (!s || !*s) return false;
+    const char *p = s;
+    if (*p == '+') ++p;
+    if (!*p) return false;
+    for (const char *q = p; *q; ++q)
+        if (*q < '0' || *q > '9') return false;
+    errno = 0;
+    out = strtoul(p, nullptr, 10);
+    return errno == 0;
+}
+
+bool lex_long(const char *s, long &out) {
+    if (!s || !*s) return false;
+    const char *p = s;
+    if (*p == '+' || *p == '-') ++p;
+    if (!*p) return false;
+    for (const char *q = p; *q; ++q)
+        if (*q < '0' || *q > '9') return false;
+    errno = 0;
+    out = strtol(s, nullptr, 10);
+    return errno == 0;
+}
+
+bool lex_double(const char *s, double &out) {  // boost::lexical_cast<double>
+    if (!s || !*s || *s == ' ' || *s == '\t') return false;
+    char *endp = nullptr;
+    out = strtod(s, &endp);
+    return endp != s && *endp == '\0';
+}
+
+const char *USAGE_COUNT =
+    "Usage:\ncount\n\tlog_level(0,1,2,...) proj_name out_prefix\n\tisoform_format isoforms_path g2i_format g2i_path "
+    "gene_begin_idx gene_end_idx\n  (read_format read_type expected_read_length reads_path )+";
+const char *USAGE_SOLVE =
+    "Usage:\nsolve\n\tlog_level(0,1,2,...) proj_name out_prefix\n\tisoform_format isoforms_path g2i_format g2i_path "
+    "gene_begin_idx gene_end_idx\n  (read_format read_type expected_read_length reads_path total_read_bases)+";
+
+struct ReadArg {
+    std::string format, type, path;
+    unsigned long length = 0;
+    double total_bases = 0;
+};
+
+bool file_openable(const std::string &p) {  // assert(ifs.is_open() && !ifs.eof()), count.cpp:139
+    FILE *f = fopen(p.c_str(), "rb");
+    if (!f) return false;
+    fclose(f);
+    return true;
+}
+
+void print_g(std::string &out, double v, int prec) {
+    char b[64];
+    snprintf(b, sizeof b, "%.*g", prec, v);  // std::ostream << double with precision(prec)
+    out += b;
+}
+
+int run_program(bool solve, int argc, char **argv) {
+    const int group = solve ? 5 : 4;
+    if (argc < 10 + group) {
+        logf(0, "%s", solve ? USAGE_SOLVE : USAGE_COUNT);
+        return 1;
+    }
+    int argi = 1;
+    if (!lex_long(argv[argi++], g_log_level)) {
+        fprintf(stderr, "terminate called after throwing an instance of 'bad_lexical_cast'\n");
+        return 134;  // the reference aborts on an uncaught bad_lexical_cast (count.cpp:99)
+    }
+    argi += 2;  // proj_name, out_prefix: parsed but unused by count/solve
+    std::string form_format = argv[argi++], form_path = argv[argi++];
+    std::string map_format = argv[argi++], map_path = argv[argi++];
+    unsigned long begin = 0, end = 0;
+    std::vector<ReadArg> sets;
+    bool cast_ok = lex_ulong(argv[argi++], begin) && lex_ulong(argv[argi++], end);
+    while (cast_ok && argi < argc) {
+        if (argc - argi < group) {
+            logf(0, "%s", solve ? USAGE_SOLVE : USAGE_COUNT);
+            return 1;
+        }
+        ReadArg ra;
+        ra.format = argv[argi++];
+        ra.type = argv[argi++];
+        cast_ok = lex_ulong(argv[argi++], ra.length);
+        ra.path = argv[argi++];
+        if (solve && cast_ok) cast_ok = lex_double(argv[argi++], ra.total_bases);
+        sets.push_back(ra);
+    }
+    if (!cast_ok) {
+        logf(0, "Lexical_cast error when converting arguments to numeric values");
+        return 1;
+    }
+    if (sets.size() > LSQ_MAX_METHODS) {
+        logf(0, "more than %u read sets are not supported", LSQ_MAX_METHODS);
+        return 1;
+    }
+    int prec = 6;
+    if (const char *p = getenv("LSQ_PRECISION")) prec = atoi(p);
+
+    logf(2, "Loading isoforms...");
+    if (!file_openable(form_path)) {
+        fprintf(stderr, "Assertion `ifs.is_open() && !ifs.eof()' failed (%s).\n", form_path.c_str());
+        return 134;
+    }
+    if (form_format != "LH_GENE_TXT") {
+        logf(0, "Unknown file format error: %s", form_format.c_str());
+        return 1;
+    }
+    logf(2, "Loading gene->isoform mappings ...");
+    if (!file_openable(map_path)) {
+        fprintf(stderr, "Assertion `ifs.is_open() && !ifs.eof()' failed (%s).\n", map_path.c_str());
+        return 134;
+    }
+    if (map_format != "UCSC_GENE2ISOFORM") {
+        logf(0, "Unknown file format error: %s", map_format.c_str());
+        return 1;
+    }
+    lsqh_annotation *ann = nullptr;
+    int rc = lsqh_annotation_load(form_path.c_str(), map_path.c_str(), begin, end, 0, UINT64_MAX, &ann);
+    if (rc == LSQ_ERR_IO) {
+        fprintf(stderr, "Assertion `ifs.is_open() && !ifs.eof()' failed: %s\n", lsq_last_error());
+        return 134;
+    }
+    if (rc) {
+        logf(0, "%s", lsq_last_error());
+        return 1;
+    }
+    lsq_event_tables tables;
+    lsqh_annotation_tables(ann, &tables);
+    logf(2, "Selected %llu gene(s)", (unsigned long long)ann->n_selected);
+
+    const uint32_t M = (uint32_t)sets.size();
+    logf(2, "Loading the reads from %u sampling method(s)", M);
+    std::vector<lsqh_reads *> reads(M, nullptr);
+    auto cleanup = [&]() {
+        for (auto r : reads) lsqh_reads_free(r);
+        lsqh_annotation_free(ann);
+    };
+    for (uint32_t m = 0; m < M; ++m) {
+        logf(2, "Loading the reads from sampling method #%u", m);
+        if (!file_openable(sets[m].path)) {
+            fprintf(stderr, "Assertion `ifs.is_open() && !ifs.eof()' failed (%s).\n", sets[m].path.c_str());
+            cleanup();
+            return 134;
+        }
+        if (sets[m].format != "MRF_SINGLE") {
+            logf(0, "Unknown file format error: %s", sets[m].format.c_str());
+            cleanup();
+            return 1;
+        }
+        rc = lsqh_mrf_parse(sets[m].path.c_str(), &reads[m]);
+        if (rc == LSQ_ERR_IO) {
+            fprintf(stderr, "Assertion `ifs.is_open() && !ifs.eof()' failed: %s\n", lsq_last_error());
+            cleanup();
+            return 134;
+        }
+        if (rc) {
+            logf(0, "%s", lsq_last_error());
+            cleanup();
+            return 1;
+        }
+    }
+    if (tables.n_events == 0) {  // nothing selected: the per-gene loop never runs
+        logf(2, "Processed 0 genes... Done");
+        cleanup();
+        return 0;
+    }
+    std::vector<uint32_t> types(M);
+    for (uint32_t m = 0; m < M; ++m) {
+        if (sets[m].type == "MEDIUM_READ") types[m] = LSQ_READ_MEDIUM;
+        else if (sets[m].type == "SHORT_READ") types[m] = LSQ_READ_SHORT;
+        else {  // detected inside the gene loop before anything is printed (count.cpp:417-419)
+            logf(0, "Unknown read type error: %s", sets[m].type.c_str());
+            cleanup();
+            return 1;
+        }
+    }
+
+    int device = 0;
+    if (const char *d = getenv("LSQ_DEVICE")) device = atoi(d);
+    lsq_ctx *ctx = nullptr;
+    auto gpu_fail = [&]() {
+        logf(0, "lesseq_b200 device path failed: %s", lsq_last_error());
+        if (ctx) lsq_ctx_destroy(ctx);
+        cleanup();
+        return 70;  // no CPU fallback
+    };
+    if (lsq_ctx_create(device, &ctx)) return gpu_fail();
+    if (lsq_upload_events(ctx, &tables)) return gpu_fail();
+    for (uint32_t m = 0; m < M; ++m) {
+        lsq_packed_reads view;
+        lsqh_reads_view(reads[m], &view);
+        if (lsq_set_reads(ctx, m, types[m], sets[m].length, &view)) return gpu_fail();
+    }
+    logf(2, "Processing reads info for genes");
+    if (lsq_count(ctx)) return gpu_fail();
+    const uint32_t E = tables.n_events, F = tables.n_forms;
+    std::vector<uint64_t> n_valid((size_t)M * E), bases((size_t)M * E), iso(F);
+    lsq_count_out co{n_valid.data(), bases.data(), iso.data()};
+    if (lsq_get_count(ctx, &co)) return gpu_fail();
+    std::vector<double> theta(F), rpkm(F), ll(E), llpr(E);
+    std::vector<uint32_t> iters(E);
+    if (solve) {
+        std::vector<double> trb(M);
+        for (uint32_t m = 0; m < M; ++m) trb[m] = sets[m].total_bases;
+        if (lsq_solve(ctx, trb.data(), M)) return gpu_fail();
+        lsq_solve_out so{theta.data(), rpkm.data(), ll.data(), llpr.data(), iters.data(), nullptr};
+        if (lsq_get_solve(ctx, &so)) return gpu_fail();
+        // the reference warns once per read when a compatible form has no accessible start
+        // (read.h:334-337); one summary line is logged here instead
+    }
+    std::string out;
+    out.reserve((size_t)F * 64);
+    for (uint32_t e = 0; e < E; ++e) {
+        for (uint32_t f = tables.ev_form_off[e]; f < tables.ev_form_off[e + 1]; ++f) {
+            out += ann->ev_name[e];
+            out += '\t';
+            for (uint32_t m = 0; m < M; ++m) {
+                print_g(out, (double)n_valid[(size_t)m * E + e], prec);
+                out += '\t';
+            }
+            out += ann->form_name[f];
+            out += '\t';
+            if (!solve) {
+                print_g(out, (double)iso[f], prec);
+            } else {
+                print_g(out, theta[f], prec);
+                out += '\t';
+                print_g(out, rpkm[f], prec);
+                out += '\t';
+                print_g(out, llpr[e], prec);
+            }
+            out += '\n';
+        }
+        if (out.size() > (1u << 20)) {
+            fwrite(out.data(), 1, out.size(), stdout);
+            out.clear();
+        }
+    }
+    fwrite(out.data(), 1, out.size(), stdout);
+    fflush(stdout);
+    logf(2, "Processed %u genes... Done", E);
+    lsq_ctx_destroy(ctx);
+    cleanup();
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int lsqh_count_main(int argc, char **argv) { return run_program(false, argc, argv); }
+extern "C" int lsqh_solve_main(int argc, char **argv) { return run_program(true, argc, argv); }

@@ -1,0 +1,19 @@
+// Host front end: packed MRF_SINGLE reads (owner of the arrays an lsq_packed_reads views).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "annotation.hpp"
+
+struct lsqh_reads {
+    lsqh::Dictionary chroms, strands;
+    std::vector<uint32_t> blk_off, read_cs, blk_cs, line_num;
+    std::vector<int32_t> blk;
+    bool any_mixed = false;
+    std::vector<const char *> chrom_ptrs, strand_ptrs;
+};
+
+namespace lsqh {
+int parse_mrf(const char *path, lsqh_reads &out);
+}

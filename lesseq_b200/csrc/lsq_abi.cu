@@ -1,0 +1,667 @@
+// C ABI of the device path (include/lesseq_b200.h, lsq_* entry points): context, table upload,
+// read-set upload, and the filter -> index -> count -> finalize -> solve pipeline.
+//
+// No CPU fallback: every compute entry point needs a CUDA device and fails with LSQ_ERR_CUDA
+// otherwise.  Host code here only lays tables out and orchestrates launches.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include "../../include/lesseq_b200.h"
+#include "lsq_kernels.cuh"
+#include "lsq_tables_host.hpp"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+
+#define LSQ_CUDA(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t e_ = (expr);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(LSQ_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));    \
+    } while (0)
+
+struct DevBuf {  // grow-only device allocation
+    void *p = nullptr;
+    size_t cap = 0;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        release();
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        else p = nullptr;
+        return e;
+    }
+    template <class T>
+    T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+template <class T>
+cudaError_t upload(DevBuf &b, const std::vector<T> &v, cudaStream_t s) {
+    cudaError_t e = b.ensure(std::max<size_t>(v.size(), 1) * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (v.empty()) return cudaSuccess;
+    return cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+}
+
+struct ReadSet {
+    bool declared = false, injected = false, borrowed = false;
+    uint32_t type = 0;
+    uint64_t read_length = 0;
+    uint64_t n_reads = 0, n_blocks = 0;
+    uint32_t n_file_strands = 0;
+    // inputs (owned copies or borrowed device pointers)
+    DevBuf d_blk_off, d_blk, d_read_cs, d_blk_cs, d_line_num;
+    const uint32_t *blk_off = nullptr, *read_cs = nullptr, *blk_cs = nullptr, *line_num = nullptr;
+    const int2 *blk = nullptr;
+    DevBuf d_chrom_remap, d_strand_tbl;
+    // injected classes (output order CSR)
+    DevBuf d_inj_off, d_inj_mask, d_inj_cnt;
+    std::vector<uint64_t> h_inj_off;
+};
+
+}  // namespace
+
+struct lsq_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int n_sms = 0;
+    // tables
+    bool have_tables = false;
+    lsq::Tables T{};
+    uint32_t E = 0, F = 0;
+    lsq::HostTables H;  // host mirror (internal order): headers, permutation, form segment lengths
+    std::map<std::string, uint32_t> chrom_id;
+    std::vector<std::string> strand_names;
+    DevBuf d_hdr, d_seg, d_fmask, d_pfx, d_tie, d_bp_chrom_off, d_bp_pos, d_stab_off, d_stab_ev, d_cov_off,
+        d_cov_start, d_cov_end, d_form_len;
+    // read sets
+    ReadSet sets[LSQ_MAX_METHODS];
+    uint32_t M = 0;  // highest declared index + 1
+    // per-run state
+    DevBuf d_slot_cnt, d_slot_mask, d_bases, d_G, d_counters;
+    DevBuf d_rkey, d_rec, d_work, d_ext, d_skey, d_srec, d_cub;
+    DevBuf d_n_valid, d_bases_out, d_iso, d_theta, d_rpkm, d_se, d_ll, d_llpr, d_iters;
+    bool counted = false, finalized = false, solved = false;
+    uint32_t solved_M = 0;
+    // timing
+    cudaEvent_t ev[16] = {};
+    lsq_timings tm{};
+    std::vector<unsigned long long> h_counters;
+};
+
+namespace {
+
+uint32_t bits_for(uint32_t v) {  // bits needed to represent values 0..v
+    uint32_t b = 1;
+    while (b < 32 && (v >> b)) ++b;
+    return b;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *lsq_last_error(void) { return g_err.c_str(); }
+const char *lsq_version(void) { return "lesseq_b200 0.1 (sm_100a)"; }
+
+uint64_t lsq_ars_length(uint32_t read_type, uint64_t R, const uint64_t *len, uint32_t n) {
+    return lsq::ars_length(read_type, R, len, n);
+}
+
+int lsq_ctx_create(int device, lsq_ctx **out) {
+    if (!out) return fail(LSQ_ERR_ARG, "lsq_ctx_create: out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(LSQ_ERR_CUDA, std::string("no CUDA device available (lesseq_b200 has no CPU fallback): ") +
+                                      cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(LSQ_ERR_ARG, "lsq_ctx_create: bad device index");
+    LSQ_CUDA(cudaSetDevice(device));
+    lsq_ctx *c = new lsq_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    LSQ_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->n_sms = prop.multiProcessorCount;
+    LSQ_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+    for (auto &ev : c->ev) LSQ_CUDA(cudaEventCreate(&ev));
+    *out = c;
+    return LSQ_OK;
+}
+
+int lsq_ctx_destroy(lsq_ctx *c) {
+    if (!c) return LSQ_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto &ev : c->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return LSQ_OK;
+}
+
+int lsq_ctx_set_stream(lsq_ctx *c, void *s) {
+    if (!c) return fail(LSQ_ERR_ARG, "null context");
+    LSQ_CUDA(cudaSetDevice(c->device));
+    LSQ_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    if (s) {
+        c->stream = (cudaStream_t)s;
+        c->own_stream = false;
+    } else {
+        LSQ_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    return LSQ_OK;
+}
+
+int lsq_ctx_sync(lsq_ctx *c) {
+    if (!c) return fail(LSQ_ERR_ARG, "null context");
+    LSQ_CUDA(cudaSetDevice(c->device));
+    LSQ_CUDA(cudaStreamSynchronize(c->stream));
+    return LSQ_OK;
+}
+
+int lsq_upload_events(lsq_ctx *c, const lsq_event_tables *t) {
+    if (!c || !t) return fail(LSQ_ERR_ARG, "lsq_upload_events: null argument");
+    LSQ_CUDA(cudaSetDevice(c->device));
+    lsq::HostTables &H = c->H;
+    std::string err;
+    int rc = lsq::build_host_tables(t, H, err);
+    if (rc) return fail(rc, err);
+    cudaStream_t s = c->stream;
+    LSQ_CUDA(upload(c->d_hdr, H.hdr, s));
+    LSQ_CUDA(upload(c->d_seg, H.seg, s));
+    LSQ_CUDA(upload(c->d_fmask, H.fmask, s));
+    LSQ_CUDA(upload(c->d_pfx, H.pfx, s));
+    LSQ_CUDA(upload(c->d_tie, H.tie, s));
+    LSQ_CUDA(upload(c->d_bp_chrom_off, H.bp_chrom_off, s));
+    LSQ_CUDA(upload(c->d_bp_pos, H.bp_pos, s));
+    LSQ_CUDA(upload(c->d_stab_off, H.stab_off, s));
+    LSQ_CUDA(upload(c->d_stab_ev, H.stab_ev, s));
+    LSQ_CUDA(upload(c->d_cov_off, H.cov_off, s));
+    LSQ_CUDA(upload(c->d_cov_start, H.cov_start, s));
+    LSQ_CUDA(upload(c->d_cov_end, H.cov_end, s));
+    LSQ_CUDA(upload(c->d_form_len, H.form_len, s));
+    LSQ_CUDA(cudaStreamSynchronize(s));
+
+    lsq::Tables &T = c->T;
+    T = H.host_view();  // sizes; pointers are replaced by the device copies below
+    T.hdr = c->d_hdr.as<lsq::EvHdr>();
+    T.seg = c->d_seg.as<int2>();
+    T.fmask = c->d_fmask.as<uint64_t>();
+    T.pfx = c->d_pfx.as<uint32_t>();
+    T.tie_pool = c->d_tie.as<char>();
+    T.bp_chrom_off = c->d_bp_chrom_off.as<uint32_t>();
+    T.bp_pos = c->d_bp_pos.as<int32_t>();
+    T.stab_off = c->d_stab_off.as<uint32_t>();
+    T.stab_ev = c->d_stab_ev.as<uint32_t>();
+    T.cov_off = c->d_cov_off.as<uint32_t>();
+    T.cov_start = c->d_cov_start.as<int32_t>();
+    T.cov_end = c->d_cov_end.as<int32_t>();
+    c->E = H.E;
+    c->F = H.F;
+    c->chrom_id.clear();
+    for (uint32_t i = 0; i < t->n_chroms; ++i) c->chrom_id[t->chrom_names[i]] = i;
+    c->strand_names.clear();
+    for (uint32_t i = 0; i < t->n_strands; ++i) c->strand_names.push_back(t->strand_names[i]);
+    c->have_tables = true;
+    c->counted = c->finalized = c->solved = false;
+    for (auto &rs : c->sets) rs.declared = false;
+    c->M = 0;
+    return LSQ_OK;
+}
+
+static int upload_G(lsq_ctx *c, uint32_t m, uint32_t read_type, uint64_t read_length) {
+    std::vector<double> G;
+    lsq::form_weights(c->H, read_type, read_length, G);
+    LSQ_CUDA(c->d_G.ensure((size_t)LSQ_MAX_METHODS * std::max<uint32_t>(c->F, 1) * sizeof(double)));
+    if (c->F)
+        LSQ_CUDA(cudaMemcpyAsync(c->d_G.as<double>() + (size_t)m * c->F, G.data(), c->F * sizeof(double),
+                                 cudaMemcpyHostToDevice, c->stream));
+    LSQ_CUDA(cudaStreamSynchronize(c->stream));
+    return LSQ_OK;
+}
+
+int lsq_set_reads(lsq_ctx *c, uint32_t m, uint32_t read_type, uint64_t read_length, const lsq_packed_reads *r) {
+    if (!c || !r) return fail(LSQ_ERR_ARG, "lsq_set_reads: null argument");
+    if (!c->have_tables) return fail(LSQ_ERR_STATE, "lsq_set_reads before lsq_upload_events");
+    if (m >= LSQ_MAX_METHODS) return fail(LSQ_ERR_RANGE, "read set index >= LSQ_MAX_METHODS");
+    if (read_type != LSQ_READ_MEDIUM && read_type != LSQ_READ_SHORT)
+        return fail(LSQ_ERR_FORMAT, "unknown read type");
+    if (r->n_blocks > 0xFFFFFFFFull || r->n_reads > 0xFFFFFFF0ull)
+        return fail(LSQ_ERR_RANGE, "read set exceeds 2^32 reads or blocks");
+    if (r->n_strand_names > 256 || r->n_chrom_names > 65536)
+        return fail(LSQ_ERR_RANGE, "read dictionaries too large");
+    LSQ_CUDA(cudaSetDevice(c->device));
+    ReadSet &rs = c->sets[m];
+    cudaStream_t s = c->stream;
+    rs.declared = true;
+    rs.injected = false;
+    rs.type = read_type;
+    rs.read_length = read_length;
+    rs.n_reads = r->n_reads;
+    rs.n_blocks = r->n_blocks;
+    rs.n_file_strands = r->n_strand_names;
+    rs.borrowed = r->on_device != 0;
+    if (rs.borrowed) {
+        rs.blk_off = r->blk_off;
+        rs.blk = reinterpret_cast<const int2 *>(r->blk);
+        rs.read_cs = r->read_cs;
+        rs.blk_cs = r->blk_cs;
+        rs.line_num = r->line_num;
+    } else {
+        const size_t n = r->n_reads, nb = r->n_blocks;
+        LSQ_CUDA(rs.d_blk_off.ensure((n + 1) * 4));
+        LSQ_CUDA(rs.d_blk.ensure(std::max<size_t>(nb, 1) * 8));
+        LSQ_CUDA(rs.d_read_cs.ensure(std::max<size_t>(n, 1) * 4));
+        LSQ_CUDA(rs.d_line_num.ensure(std::max<size_t>(n, 1) * 4));
+        LSQ_CUDA(cudaMemcpyAsync(rs.d_blk_off.p, r->blk_off, (n + 1) * 4, cudaMemcpyHostToDevice, s));
+        if (nb) LSQ_CUDA(cudaMemcpyAsync(rs.d_blk.p, r->blk, nb * 8, cudaMemcpyHostToDevice, s));
+        if (n) LSQ_CUDA(cudaMemcpyAsync(rs.d_read_cs.p, r->read_cs, n * 4, cudaMemcpyHostToDevice, s));
+        if (n) LSQ_CUDA(cudaMemcpyAsync(rs.d_line_num.p, r->line_num, n * 4, cudaMemcpyHostToDevice, s));
+        rs.blk_cs = nullptr;
+        if (r->blk_cs) {
+            bool any_mixed = false;
+            for (size_t i = 0; i < n && !any_mixed; ++i) any_mixed = (r->read_cs[i] & LSQ_READ_MIXED) != 0;
+            if (any_mixed) {
+                LSQ_CUDA(rs.d_blk_cs.ensure(std::max<size_t>(nb, 1) * 4));
+                LSQ_CUDA(cudaMemcpyAsync(rs.d_blk_cs.p, r->blk_cs, nb * 4, cudaMemcpyHostToDevice, s));
+                rs.blk_cs = rs.d_blk_cs.as<uint32_t>();
+            }
+        }
+        rs.blk_off = rs.d_blk_off.as<uint32_t>();
+        rs.blk = rs.d_blk.as<int2>();
+        rs.read_cs = rs.d_read_cs.as<uint32_t>();
+        rs.line_num = rs.d_line_num.as<uint32_t>();
+    }
+    // dictionaries: file chromosome ids -> annotation ids; strand order table
+    std::vector<uint32_t> remap(std::max<uint32_t>(r->n_chrom_names, 1), 0xFFFFFFFFu);
+    for (uint32_t i = 0; i < r->n_chrom_names; ++i) {
+        auto it = c->chrom_id.find(r->chrom_names[i]);
+        if (it != c->chrom_id.end()) remap[i] = it->second;
+    }
+    std::vector<uint8_t> tbl;
+    lsq::strand_table(r->strand_names, r->n_strand_names, c->strand_names, tbl);
+    LSQ_CUDA(upload(rs.d_chrom_remap, remap, s));
+    LSQ_CUDA(upload(rs.d_strand_tbl, tbl, s));
+    LSQ_CUDA(cudaStreamSynchronize(s));
+    c->M = std::max(c->M, m + 1);
+    c->counted = c->finalized = c->solved = false;
+    return upload_G(c, m, read_type, read_length);
+}
+
+int lsq_set_classes(lsq_ctx *c, uint32_t m, uint32_t read_type, uint64_t read_length, const uint64_t *cls_off,
+                    const uint64_t *cls_mask, const uint64_t *cls_cnt, const uint64_t *bases) {
+    if (!c || !cls_off || !bases) return fail(LSQ_ERR_ARG, "lsq_set_classes: null argument");
+    if (!c->have_tables) return fail(LSQ_ERR_STATE, "lsq_set_classes before lsq_upload_events");
+    if (m >= LSQ_MAX_METHODS) return fail(LSQ_ERR_RANGE, "read set index >= LSQ_MAX_METHODS");
+    if (read_type != LSQ_READ_MEDIUM && read_type != LSQ_READ_SHORT)
+        return fail(LSQ_ERR_FORMAT, "unknown read type");
+    LSQ_CUDA(cudaSetDevice(c->device));
+    ReadSet &rs = c->sets[m];
+    cudaStream_t s = c->stream;
+    const uint32_t E = c->E;
+    const uint64_t nc = cls_off[E];
+    if (nc && (!cls_mask || !cls_cnt)) return fail(LSQ_ERR_ARG, "lsq_set_classes: null class arrays");
+    rs.declared = true;
+    rs.injected = true;
+    rs.type = read_type;
+    rs.read_length = read_length;
+    rs.h_inj_off.assign(cls_off, cls_off + E + 1);
+    LSQ_CUDA(rs.d_inj_off.ensure((E + 1) * 8));
+    LSQ_CUDA(rs.d_inj_mask.ensure(std::max<uint64_t>(nc, 1) * 8));
+    LSQ_CUDA(rs.d_inj_cnt.ensure(std::max<uint64_t>(nc, 1) * 8));
+    LSQ_CUDA(cudaMemcpyAsync(rs.d_inj_off.p, cls_off, (E + 1) * 8, cudaMemcpyHostToDevice, s));
+    if (nc) {
+        LSQ_CUDA(cudaMemcpyAsync(rs.d_inj_mask.p, cls_mask, nc * 8, cudaMemcpyHostToDevice, s));
+        LSQ_CUDA(cudaMemcpyAsync(rs.d_inj_cnt.p, cls_cnt, nc * 8, cudaMemcpyHostToDevice, s));
+    }
+    // bases arrive in output order; the device keeps them in internal order
+    std::vector<unsigned long long> b(std::max<uint32_t>(E, 1));
+    for (uint32_t ie = 0; ie < E; ++ie) b[ie] = bases[c->H.order[ie]];
+    LSQ_CUDA(c->d_bases.ensure((size_t)LSQ_MAX_METHODS * std::max<uint32_t>(E, 1) * 8));
+    LSQ_CUDA(cudaMemcpyAsync(c->d_bases.as<unsigned long long>() + (size_t)m * E, b.data(), (size_t)E * 8,
+                             cudaMemcpyHostToDevice, s));
+    LSQ_CUDA(cudaStreamSynchronize(s));
+    c->M = std::max(c->M, m + 1);
+    c->finalized = c->solved = false;
+    return upload_G(c, m, read_type, read_length);
+}
+
+static int ensure_run_buffers(lsq_ctx *c) {
+    const size_t E = std::max<uint32_t>(c->E, 1), F = std::max<uint32_t>(c->F, 1);
+    const size_t slots = std::max<uint64_t>(c->T.total_slots, 1);
+    LSQ_CUDA(c->d_slot_cnt.ensure((size_t)LSQ_MAX_METHODS * slots * 8));
+    LSQ_CUDA(c->d_slot_mask.ensure((size_t)LSQ_MAX_METHODS * slots * 8));
+    LSQ_CUDA(c->d_bases.ensure((size_t)LSQ_MAX_METHODS * E * 8));
+    LSQ_CUDA(c->d_counters.ensure(64 * 8));
+    LSQ_CUDA(c->d_n_valid.ensure((size_t)LSQ_MAX_METHODS * E * 8));
+    LSQ_CUDA(c->d_bases_out.ensure((size_t)LSQ_MAX_METHODS * E * 8));
+    LSQ_CUDA(c->d_iso.ensure(F * 8));
+    LSQ_CUDA(c->d_theta.ensure(F * 8));
+    LSQ_CUDA(c->d_rpkm.ensure(F * 8));
+    LSQ_CUDA(c->d_se.ensure(F * 8));
+    LSQ_CUDA(c->d_ll.ensure(E * 8));
+    LSQ_CUDA(c->d_llpr.ensure(E * 8));
+    LSQ_CUDA(c->d_iters.ensure(E * 4));
+    return LSQ_OK;
+}
+
+static void fill_solve_params(lsq_ctx *c, lsq::SolveParams &P) {
+    memset(&P, 0, sizeof P);
+    P.T = c->T;
+    P.M = c->M;
+    P.slot_cnt = c->d_slot_cnt.as<unsigned long long>();
+    P.slot_mask = c->d_slot_mask.as<unsigned long long>();
+    P.bases = c->d_bases.as<unsigned long long>();
+    P.G = c->d_G.as<double>();
+    P.form_len = c->d_form_len.as<uint64_t>();
+    for (uint32_t m = 0; m < c->M; ++m) {
+        if (c->sets[m].injected) {
+            P.inj_off[m] = c->sets[m].d_inj_off.as<uint64_t>();
+            P.inj_mask[m] = c->sets[m].d_inj_mask.as<uint64_t>();
+            P.inj_cnt[m] = c->sets[m].d_inj_cnt.as<uint64_t>();
+        }
+    }
+    P.n_valid = c->d_n_valid.as<unsigned long long>();
+    P.bases_out = c->d_bases_out.as<unsigned long long>();
+    P.iso_count = c->d_iso.as<unsigned long long>();
+    P.theta = c->d_theta.as<double>();
+    P.rpkm = c->d_rpkm.as<double>();
+    P.se = c->d_se.as<double>();
+    P.loglik = c->d_ll.as<double>();
+    P.ll_per_read = c->d_llpr.as<double>();
+    P.iters = c->d_iters.as<uint32_t>();
+    P.max_iters = 10000000u;
+}
+
+static int run_finalize(lsq_ctx *c) {
+    if (c->finalized) return LSQ_OK;
+    lsq::SolveParams P;
+    fill_solve_params(c, P);
+    if (c->E) {
+        lsq::lsq_finalize_kernel<<<(c->E + 127) / 128, 128, 0, c->stream>>>(P);
+        LSQ_CUDA(cudaGetLastError());
+        c->tm.launches++;
+    }
+    c->finalized = true;
+    return LSQ_OK;
+}
+
+int lsq_count(lsq_ctx *c) {
+    if (!c) return fail(LSQ_ERR_ARG, "null context");
+    if (!c->have_tables) return fail(LSQ_ERR_STATE, "lsq_count before lsq_upload_events");
+    if (c->M == 0) return fail(LSQ_ERR_STATE, "lsq_count without read sets");
+    for (uint32_t m = 0; m < c->M; ++m)
+        if (!c->sets[m].declared) return fail(LSQ_ERR_STATE, "read set indices must be contiguous from 0");
+    LSQ_CUDA(cudaSetDevice(c->device));
+    int rc = ensure_run_buffers(c);
+    if (rc) return rc;
+    cudaStream_t s = c->stream;
+    const lsq::Tables &T = c->T;
+    lsq_timings &tm = c->tm;
+    memset(&tm, 0, sizeof tm);
+    const uint32_t E = c->E;
+    float acc[5] = {0, 0, 0, 0, 0};
+    c->h_counters.assign((size_t)LSQ_MAX_METHODS * 4, 0);
+    for (uint32_t m = 0; m < c->M; ++m) {
+        ReadSet &rs = c->sets[m];
+        if (rs.injected) continue;
+        const size_t n = rs.n_reads, nb = rs.n_blocks;
+        unsigned long long *slot_cnt = c->d_slot_cnt.as<unsigned long long>() + (size_t)m * T.total_slots;
+        unsigned long long *slot_mask = c->d_slot_mask.as<unsigned long long>() + (size_t)m * T.total_slots;
+        unsigned long long *bases = c->d_bases.as<unsigned long long>() + (size_t)m * E;
+        unsigned long long *counters = c->d_counters.as<unsigned long long>() + (size_t)m * 4;
+        LSQ_CUDA(c->d_rkey.ensure(std::max<size_t>(n, 1) * 4));
+        LSQ_CUDA(c->d_skey.ensure(std::max<size_t>(n, 1) * 4));
+        LSQ_CUDA(c->d_rec.ensure(std::max<size_t>(n, 1) * 16));
+        LSQ_CUDA(c->d_srec.ensure(std::max<size_t>(n, 1) * 16));
+        LSQ_CUDA(c->d_work.ensure(std::max<size_t>(nb, 1) * 8));
+        LSQ_CUDA(c->d_ext.ensure(std::max<size_t>(nb, 1) * 8));
+        size_t cub_bytes = 0;
+        const int end_bit = (int)bits_for(T.n_pieces);
+        cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, c->d_rkey.as<uint32_t>(), c->d_skey.as<uint32_t>(),
+                                        c->d_rec.as<lsq::ReadRec>(), c->d_srec.as<lsq::ReadRec>(), (int64_t)n, 0,
+                                        end_bit, s);
+        LSQ_CUDA(c->d_cub.ensure(std::max<size_t>(cub_bytes, 1)));
+
+        LSQ_CUDA(cudaEventRecord(c->ev[0], s));
+        LSQ_CUDA(cudaMemsetAsync(slot_cnt, 0, std::max<uint64_t>(T.total_slots, 1) * 8, s));
+        LSQ_CUDA(cudaMemsetAsync(slot_mask, 0, std::max<uint64_t>(T.total_slots, 1) * 8, s));
+        LSQ_CUDA(cudaMemsetAsync(bases, 0, std::max<uint32_t>(E, 1) * 8, s));
+        LSQ_CUDA(cudaMemsetAsync(counters, 0, 4 * 8, s));
+        if (n) {
+            lsq::FilterParams FP;
+            FP.T = T;
+            FP.n_reads = n;
+            FP.blk_off = rs.blk_off;
+            FP.blk = rs.blk;
+            FP.read_cs = rs.read_cs;
+            FP.blk_cs = rs.blk_cs;
+            FP.chrom_remap = rs.d_chrom_remap.as<uint32_t>();
+            FP.ext = c->d_ext.as<int2>();
+            FP.rkey = c->d_rkey.as<uint32_t>();
+            FP.rec = c->d_rec.as<lsq::ReadRec>();
+            FP.counters = counters;
+            lsq::lsq_filter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(FP, c->d_work.as<int2>());
+            LSQ_CUDA(cudaGetLastError());
+            tm.launches++;
+        }
+        LSQ_CUDA(cudaEventRecord(c->ev[1], s));
+        if (n) {
+            LSQ_CUDA(cub::DeviceRadixSort::SortPairs(c->d_cub.p, cub_bytes, c->d_rkey.as<uint32_t>(),
+                                                     c->d_skey.as<uint32_t>(), c->d_rec.as<lsq::ReadRec>(),
+                                                     c->d_srec.as<lsq::ReadRec>(), (int64_t)n, 0, end_bit, s));
+        }
+        LSQ_CUDA(cudaEventRecord(c->ev[2], s));
+        if (n) {
+            lsq::CountParams CP;
+            CP.T = T;
+            CP.counters = counters;
+            CP.g_key = c->d_skey.as<uint32_t>();
+            CP.g_rec = c->d_srec.as<lsq::ReadRec>();
+            CP.ext = c->d_ext.as<int2>();
+            CP.line_num = rs.line_num;
+            CP.strand_tbl = rs.d_strand_tbl.as<uint8_t>();
+            CP.slot_cnt = slot_cnt;
+            CP.slot_mask = slot_mask;
+            CP.bases = bases;
+            CP.stats = counters + 2;
+            unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)c->n_sms * 8);
+            lsq::lsq_count_kernel<<<grid, 256, 0, s>>>(CP);
+            LSQ_CUDA(cudaGetLastError());
+            tm.launches++;
+            tm.count_launches++;
+        }
+        LSQ_CUDA(cudaEventRecord(c->ev[3], s));
+        LSQ_CUDA(cudaMemcpyAsync(c->h_counters.data() + (size_t)m * 4, counters, 4 * 8, cudaMemcpyDeviceToHost, s));
+        LSQ_CUDA(cudaStreamSynchronize(s));
+        float f;
+        LSQ_CUDA(cudaEventElapsedTime(&f, c->ev[0], c->ev[1]));
+        acc[0] += f;
+        LSQ_CUDA(cudaEventElapsedTime(&f, c->ev[1], c->ev[2]));
+        acc[1] += f;
+        LSQ_CUDA(cudaEventElapsedTime(&f, c->ev[2], c->ev[3]));
+        acc[3] += f;
+        tm.reads_in += n;
+        tm.reads_kept += c->h_counters[(size_t)m * 4 + 0];
+        tm.pairs_valid += c->h_counters[(size_t)m * 4 + 2];
+        // algorithmic bytes of the count kernel: key (4) + record (16) per kept read, plus one
+        // 8-byte entry header and 8 bytes per further block of multi-block reads
+        tm.count_bytes += c->h_counters[(size_t)m * 4 + 0] * 20ull + c->h_counters[(size_t)m * 4 + 1] * 8ull;
+    }
+    c->counted = true;
+    c->finalized = false;
+    c->solved = false;
+    LSQ_CUDA(cudaEventRecord(c->ev[4], s));
+    rc = run_finalize(c);
+    if (rc) return rc;
+    LSQ_CUDA(cudaEventRecord(c->ev[5], s));
+    LSQ_CUDA(cudaStreamSynchronize(s));
+    float f;
+    LSQ_CUDA(cudaEventElapsedTime(&f, c->ev[4], c->ev[5]));
+    tm.filter_ms = acc[0];
+    tm.index_ms = acc[1];
+    tm.gather_ms = 0;
+    tm.count_ms = acc[3];
+    tm.count_kernel_ms = acc[3];
+    tm.finalize_ms = f;
+    return LSQ_OK;
+}
+
+int lsq_get_count(lsq_ctx *c, lsq_count_out *o) {
+    if (!c || !o) return fail(LSQ_ERR_ARG, "lsq_get_count: null argument");
+    bool any_inj = false, all_ready = true;
+    for (uint32_t m = 0; m < c->M; ++m) {
+        any_inj |= c->sets[m].injected;
+        all_ready &= c->sets[m].injected || c->counted;
+    }
+    (void)any_inj;
+    if (!all_ready || c->M == 0) return fail(LSQ_ERR_STATE, "lsq_get_count before lsq_count");
+    LSQ_CUDA(cudaSetDevice(c->device));
+    int rc = ensure_run_buffers(c);
+    if (rc) return rc;
+    rc = run_finalize(c);
+    if (rc) return rc;
+    cudaStream_t s = c->stream;
+    const size_t E = c->E, F = c->F, M = c->M;
+    if (o->n_valid && E) LSQ_CUDA(cudaMemcpyAsync(o->n_valid, c->d_n_valid.p, M * E * 8, cudaMemcpyDeviceToHost, s));
+    if (o->bases && E) LSQ_CUDA(cudaMemcpyAsync(o->bases, c->d_bases_out.p, M * E * 8, cudaMemcpyDeviceToHost, s));
+    if (o->iso_count && F) LSQ_CUDA(cudaMemcpyAsync(o->iso_count, c->d_iso.p, F * 8, cudaMemcpyDeviceToHost, s));
+    LSQ_CUDA(cudaStreamSynchronize(s));
+    return LSQ_OK;
+}
+
+int lsq_get_classes(lsq_ctx *c, uint32_t m, uint64_t *cls_off, uint64_t *cls_mask, uint64_t *cls_cnt) {
+    if (!c || !cls_off) return fail(LSQ_ERR_ARG, "lsq_get_classes: null argument");
+    if (m >= c->M || !c->sets[m].declared) return fail(LSQ_ERR_ARG, "lsq_get_classes: unknown read set");
+    LSQ_CUDA(cudaSetDevice(c->device));
+    const uint32_t E = c->E;
+    ReadSet &rs = c->sets[m];
+    if (rs.injected) {
+        std::copy(rs.h_inj_off.begin(), rs.h_inj_off.end(), cls_off);
+        if (cls_mask && cls_cnt && cls_off[E]) {
+            LSQ_CUDA(cudaMemcpy(cls_mask, rs.d_inj_mask.p, cls_off[E] * 8, cudaMemcpyDeviceToHost));
+            LSQ_CUDA(cudaMemcpy(cls_cnt, rs.d_inj_cnt.p, cls_off[E] * 8, cudaMemcpyDeviceToHost));
+        }
+        return LSQ_OK;
+    }
+    if (!c->counted) return fail(LSQ_ERR_STATE, "lsq_get_classes before lsq_count");
+    const size_t slots = c->T.total_slots;
+    std::vector<unsigned long long> cnt(std::max<size_t>(slots, 1)), msk(std::max<size_t>(slots, 1));
+    LSQ_CUDA(cudaStreamSynchronize(c->stream));
+    if (slots) {
+        LSQ_CUDA(cudaMemcpy(cnt.data(), c->d_slot_cnt.as<unsigned long long>() + (size_t)m * slots, slots * 8,
+                            cudaMemcpyDeviceToHost));
+        LSQ_CUDA(cudaMemcpy(msk.data(), c->d_slot_mask.as<unsigned long long>() + (size_t)m * slots, slots * 8,
+                            cudaMemcpyDeviceToHost));
+    }
+    // output order: event e is internal event inv[e]
+    std::vector<uint32_t> inv(E);
+    for (uint32_t ie = 0; ie < E; ++ie) inv[c->H.order[ie]] = ie;
+    uint64_t tot = 0;
+    for (uint32_t e = 0; e < E; ++e) {
+        cls_off[e] = tot;
+        const lsq::EvHdr &h = c->H.hdr[inv[e]];
+        std::vector<std::pair<uint64_t, uint64_t> > cl;
+        for (uint32_t i = 0; i < h.slot_cap; ++i) {
+            uint64_t n = cnt[h.slot_off + i];
+            if (!n) continue;
+            uint64_t mk = (h.flags & lsq::EV_HASH) ? msk[h.slot_off + i] : (uint64_t)(i + 1);
+            cl.push_back(std::make_pair(mk, n));
+        }
+        std::sort(cl.begin(), cl.end());
+        if (cls_mask && cls_cnt)
+            for (size_t i = 0; i < cl.size(); ++i) {
+                cls_mask[tot + i] = cl[i].first;
+                cls_cnt[tot + i] = cl[i].second;
+            }
+        tot += cl.size();
+    }
+    cls_off[E] = tot;
+    return LSQ_OK;
+}
+
+int lsq_solve(lsq_ctx *c, const double *total_read_bases, uint32_t n_methods) {
+    if (!c || !total_read_bases) return fail(LSQ_ERR_ARG, "lsq_solve: null argument");
+    if (!c->have_tables || c->M == 0) return fail(LSQ_ERR_STATE, "lsq_solve without tables / read sets");
+    if (n_methods != c->M) return fail(LSQ_ERR_ARG, "lsq_solve: n_methods differs from the declared read sets");
+    for (uint32_t m = 0; m < c->M; ++m) {
+        if (!c->sets[m].declared) return fail(LSQ_ERR_STATE, "read set indices must be contiguous from 0");
+        if (!c->sets[m].injected && !c->counted) return fail(LSQ_ERR_STATE, "lsq_solve before lsq_count");
+    }
+    LSQ_CUDA(cudaSetDevice(c->device));
+    int rc = ensure_run_buffers(c);
+    if (rc) return rc;
+    cudaStream_t s = c->stream;
+    rc = run_finalize(c);
+    if (rc) return rc;
+    lsq::SolveParams P;
+    fill_solve_params(c, P);
+    double mb = 0.0;  // solve.cpp:810-812
+    for (uint32_t m = 0; m < c->M; ++m) mb += total_read_bases[m] / 1.0E6;
+    P.total_read_mbases = mb;
+    LSQ_CUDA(cudaEventRecord(c->ev[6], s));
+    if (c->E) {
+        constexpr int WARPS = 8;
+        unsigned grid = std::min<unsigned>((c->E + WARPS - 1) / WARPS, (unsigned)c->n_sms * 8u);
+        lsq::lsq_solve_kernel<WARPS><<<grid, WARPS * 32, 0, s>>>(P);
+        LSQ_CUDA(cudaGetLastError());
+        c->tm.launches++;
+    }
+    LSQ_CUDA(cudaEventRecord(c->ev[7], s));
+    LSQ_CUDA(cudaStreamSynchronize(s));
+    LSQ_CUDA(cudaEventElapsedTime(&c->tm.solve_ms, c->ev[6], c->ev[7]));
+    c->solved = true;
+    c->solved_M = c->M;
+    return LSQ_OK;
+}
+
+int lsq_get_solve(lsq_ctx *c, lsq_solve_out *o) {
+    if (!c || !o) return fail(LSQ_ERR_ARG, "lsq_get_solve: null argument");
+    if (!c->solved) return fail(LSQ_ERR_STATE, "lsq_get_solve before lsq_solve");
+    LSQ_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const size_t E = c->E, F = c->F;
+    if (o->theta && F) LSQ_CUDA(cudaMemcpyAsync(o->theta, c->d_theta.p, F * 8, cudaMemcpyDeviceToHost, s));
+    if (o->rpkm && F) LSQ_CUDA(cudaMemcpyAsync(o->rpkm, c->d_rpkm.p, F * 8, cudaMemcpyDeviceToHost, s));
+    if (o->loglik && E) LSQ_CUDA(cudaMemcpyAsync(o->loglik, c->d_ll.p, E * 8, cudaMemcpyDeviceToHost, s));
+    if (o->ll_per_read && E) LSQ_CUDA(cudaMemcpyAsync(o->ll_per_read, c->d_llpr.p, E * 8, cudaMemcpyDeviceToHost, s));
+    if (o->iters && E) LSQ_CUDA(cudaMemcpyAsync(o->iters, c->d_iters.p, E * 4, cudaMemcpyDeviceToHost, s));
+    if (o->se) return fail(LSQ_ERR_ARG, "standard errors are not available in this build");
+    LSQ_CUDA(cudaStreamSynchronize(s));
+    return LSQ_OK;
+}
+
+int lsq_get_timings(lsq_ctx *c, lsq_timings *o) {
+    if (!c || !o) return fail(LSQ_ERR_ARG, "lsq_get_timings: null argument");
+    *o = c->tm;
+    return LSQ_OK;
+}
+
+}  // extern "C"
+
+namespace lsqh {
+void set_error(const std::string &msg) { g_err = msg; }
+}  // namespace lsqh

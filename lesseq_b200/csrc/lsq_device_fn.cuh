@@ -1,0 +1,364 @@
+// Per-read / per-pair device functions of the count path (no warp intrinsics here).
+//
+// Everything in this header is written against LSQ_HD so that tests/emul/ can compile the very
+// same logic with g++ and replay it sequentially on the CPU against the oracle while no GPU is
+// attached to the development container.  That harness is test infrastructure: the product
+// only ever runs these functions inside the CUDA kernels of lsq_kernels.cuh.
+#pragma once
+#include "lsq_types.cuh"
+
+#ifdef __CUDACC__
+#define LSQ_HD __device__ __forceinline__
+#define LSQ_LD(p) __ldg(p)
+#else
+#define LSQ_HD inline
+#define LSQ_LD(p) (*(p))
+#endif
+
+namespace lsq {
+
+LSQ_HD int lsq_clz64(uint64_t v) {
+#ifdef __CUDA_ARCH__
+    return __clzll((long long)v);
+#else
+    return __builtin_clzll(v);
+#endif
+}
+LSQ_HD double lsq_div(double a, double b) {  // IEEE division, never contracted or approximated
+#ifdef __CUDA_ARCH__
+    return __ddiv_rn(a, b);
+#else
+    return a / b;
+#endif
+}
+LSQ_HD int32_t lsq_max(int32_t a, int32_t b) { return a > b ? a : b; }
+LSQ_HD int32_t lsq_min(int32_t a, int32_t b) { return a < b ? a : b; }
+
+// ---------------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------------
+// number of elements < x in sorted a[lo,hi)
+LSQ_HD uint32_t lower_bound_i32(const int32_t *__restrict__ a, uint32_t lo, uint32_t hi,
+                                                    int32_t x) {
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (LSQ_LD(a + mid) < x) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+// number of elements <= x in sorted a[lo,hi)
+LSQ_HD uint32_t upper_bound_i32(const int32_t *__restrict__ a, uint32_t lo, uint32_t hi,
+                                                    int32_t x) {
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (LSQ_LD(a + mid) <= x) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// contains_interval on the merged covered regions of one chromosome (interval_list.hpp:396-422):
+// the last interval starting at or before s must reach e.
+LSQ_HD bool covered_contains(const Tables &T, uint32_t chrom, int32_t s, int32_t e) {
+    uint32_t lo = LSQ_LD(T.cov_off + chrom), hi = LSQ_LD(T.cov_off + chrom + 1);
+    uint32_t i = upper_bound_i32(T.cov_start, lo, hi, s);
+    return i > lo && LSQ_LD(T.cov_end + i - 1) >= e;
+}
+
+// In-place "erase [b,e) then optionally insert v at b" on one component (.x or .y) of an int2 list.
+LSQ_HD void erase_insert(int32_t *comp /* stride 2 */, uint32_t n, uint32_t b, uint32_t e,
+                                    bool ins, int32_t v) {
+    int shift = (ins ? 1 : 0) - (int)(e - b);
+    if (shift < 0) {
+        for (uint32_t i = e; i < n; ++i) comp[2 * (i + shift)] = comp[2 * i];
+    } else if (shift > 0) {
+        for (uint32_t i = n; i > e; --i) comp[2 * (i - 1 + shift)] = comp[2 * (i - 1)];
+    }
+    if (ins) comp[2 * b] = v;
+}
+
+// interval_list::add_interval on a list of n intervals stored in L[0..n) (capacity >= n+1).
+// Returns the new length.  General (order dependent) semantics; the caller handles the
+// common append/extend case without calling this.
+LSQ_HD uint32_t list_add(int2 *L, uint32_t n, int32_t s, int32_t e) {
+    uint32_t ss = 0, se = 0, es = 0, ee = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        int2 v = L[i];
+        ss += v.x < s;
+        se += v.y < s;
+        es += v.x < e;
+        ee += v.y < e;
+    }
+    bool s_in = (ss - se) == 1u, e_in = (es - ee) == 1u;
+    int32_t *base = reinterpret_cast<int32_t *>(L);
+    erase_insert(base, n, ss, es, !s_in, s);
+    erase_insert(base + 1, n, se, ee, !e_in, e);
+    return ss + (s_in ? 0u : 1u) + (n - es);
+}
+
+
+// Result of the per-read load filter.
+struct FilteredRead {
+    uint32_t n;       // kept intervals (0: read dropped)
+    uint32_t key;     // stab piece, or T.n_pieces when the read is not a candidate of any event
+    int2 first;       // first kept interval
+    uint32_t strand;  // file strand id of the last registered block
+};
+
+// count.cpp:297-327 for one read: every block is tested against the covered regions of its
+// chromosome; kept blocks are merged into the read's interval list (work[0..n), used only when
+// the read has more than one raw block); the read's chromosome/strand are those of the last
+// registered block; the stab piece is looked up for the first kept start.
+LSQ_HD FilteredRead filter_read(const FilterParams &P, uint64_t r, int2 *work) {
+    const Tables &T = P.T;
+    FilteredRead out;
+    out.n = 0;
+    out.key = T.n_pieces;
+    out.first = make_int2(0, 0);
+    out.strand = 0;
+    const uint32_t base = LSQ_LD(P.blk_off + r);
+    const uint32_t nraw = LSQ_LD(P.blk_off + r + 1) - base;
+    const uint32_t cs0 = LSQ_LD(P.read_cs + r);
+    const bool mixed = (cs0 & 0x80000000u) != 0;
+    uint32_t chrom = 0xFFFFFFFFu;  // annotation id of the last registered block
+    bool registered = false;
+    int32_t last_end = 0;
+    uint32_t n = 0;
+    int2 first = make_int2(0, 0);
+    work += base;
+    for (uint32_t j = 0; j < nraw; ++j) {
+        int2 b = LSQ_LD(P.blk + base + j);
+        uint32_t cs = mixed ? LSQ_LD(P.blk_cs + base + j) : cs0;
+        uint32_t c = LSQ_LD(P.chrom_remap + (cs & 0xFFFFu));
+        bool keep;
+        if (!(b.x < b.y)) keep = true;  // a nil block is "contained" (interval_list.hpp:398-401)
+        else keep = (c != 0xFFFFFFFFu) && covered_contains(T, c, b.x, b.y);
+        if (!keep) continue;
+        registered = true;
+        chrom = c;
+        out.strand = (cs >> 16) & 0xFFu;
+        if (!(b.x < b.y)) continue;  // add_interval ignores nil intervals
+        if (n == 0) {
+            first = b;
+            last_end = b.y;
+            n = 1;
+            if (nraw > 1) work[0] = b;
+        } else if (b.x >= last_end) {
+            if (b.x == last_end) {  // starts where the last interval ends: the two fuse
+                last_end = b.y;
+                if (n == 1) first.y = b.y;
+                work[n - 1].y = b.y;
+            } else {
+                work[n] = b;
+                last_end = b.y;
+                ++n;
+            }
+        } else {  // out of order or overlapping: general list update
+            n = list_add(work, n, b.x, b.y);
+            first = work[0];
+            last_end = work[n - 1].y;
+        }
+    }
+    out.n = n;
+    out.first = first;
+    if (registered && n > 0 && chrom != 0xFFFFFFFFu) {
+        uint32_t lo = LSQ_LD(T.bp_chrom_off + chrom), hi = LSQ_LD(T.bp_chrom_off + chrom + 1);
+        uint32_t p = upper_bound_i32(T.bp_pos, lo, hi, first.x);
+        if (p > lo) {
+            --p;
+            if (LSQ_LD(T.stab_off + p + 1) > LSQ_LD(T.stab_off + p)) out.key = p;
+        }
+    }
+    return out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per (read, event) pair
+// ---------------------------------------------------------------------------------------------
+struct ReadView {
+    int2 b0;          // first kept block
+    uint32_t n;       // kept blocks
+    uint32_t z;       // n == 1: read index; else offset of the ext entry
+    const int2 *ext;  // ext entry when n > 1: ext[0] = {read index, n}, ext[j] = block j
+    LSQ_HD int2 block(uint32_t j) const { return j == 0 ? b0 : LSQ_LD(ext + j); }
+    LSQ_HD int32_t last_end() const { return n == 1 ? b0.y : LSQ_LD(ext + n - 1).y; }
+    LSQ_HD uint32_t read_index() const { return n == 1 ? z : (uint32_t)LSQ_LD(ext).x; }
+};
+
+// "read-<N>" < name for tie mode 2: the name is "read-" + suffix, so compare the decimal digits
+// of N with the suffix bytewise (std::string operator<).
+LSQ_HD bool digits_less(uint32_t N, const char *__restrict__ sfx, uint32_t len) {
+    char d[10];
+    int nd = 0;
+    do {
+        d[nd++] = (char)('0' + N % 10u);
+        N /= 10u;
+    } while (N);
+    for (int i = 0; i < nd; ++i) {
+        if ((uint32_t)i >= len) return false;  // suffix is a proper prefix of the digits
+        unsigned char a = (unsigned char)d[nd - 1 - i], b = (unsigned char)sfx[i];
+        if (a != b) return a < b;
+    }
+    return (uint32_t)nd < len;  // digits are a proper prefix of the suffix
+}
+
+// Read_single::build (common/read.h:204-274) for S <= 64: segment bit mask + matched length.
+// `seg` may point to shared or global memory.
+LSQ_HD void walk_mask(const ReadView &rv, const int2 *seg, uint32_t S, uint64_t &mask,
+                                          uint32_t &matched) {
+    uint32_t it = 0, b = 0;
+    int32_t cont = 0;  // the reference's cur_exon_start
+    bool found = false;
+    uint64_t m = 0;
+    uint32_t ml = 0;
+    while (b < rv.n) {
+        int2 blk = rv.block(b);
+        int32_t cs = blk.x;
+        const int32_t ce = blk.y;
+        bool consumed = false;
+        while (it < S) {
+            int2 sg = seg[it];
+            if (!(sg.x < ce)) break;
+            cont = lsq_max(cont, sg.x);
+            if (cs >= cont && cs < sg.y) {
+                if (!found) found = true;
+                else if (cs > cont) break;
+                m |= 1ull << it;
+                cont = lsq_min(sg.y, ce);
+                ml += (uint32_t)(cont - cs);
+                if (ce < sg.y) {  // block ends inside this segment: the cursor stays on it
+                    consumed = true;
+                    break;
+                } else if (ce == sg.y) {
+                    consumed = true;
+                    cs = ce;
+                } else {
+                    cs = sg.y;  // only an abutting next segment can continue the block
+                }
+            } else if (cont > sg.x && cont < sg.y) {
+                break;
+            }
+            ++it;
+        }
+        if (!consumed) break;  // block not fully matched: the read is truncated here
+        ++b;
+    }
+    mask = m;
+    matched = ml;
+}
+
+// Wide events (S > 64): the same walk, checking one form on the fly with its prefix counts
+// pf[s] = number of form segments with index < s.  The read's index list must be a contiguous
+// run of the form's list (common/read.h:44-79).
+LSQ_HD bool walk_wide(const ReadView &rv, const int2 *seg, uint32_t S,
+                                 const uint32_t *__restrict__ pf, uint32_t &matched) {
+    uint32_t it = 0, b = 0;
+    int32_t cont = 0;
+    bool found = false, ok = true;
+    uint32_t ml = 0;
+    uint32_t last_added = 0xFFFFFFFFu, last_rank = 0;
+    while (b < rv.n) {
+        int2 blk = rv.block(b);
+        int32_t cs = blk.x;
+        const int32_t ce = blk.y;
+        bool consumed = false;
+        while (it < S) {
+            int2 sg = seg[it];
+            if (!(sg.x < ce)) break;
+            cont = lsq_max(cont, sg.x);
+            if (cs >= cont && cs < sg.y) {
+                if (!found) found = true;
+                else if (cs > cont) break;
+                if (it != last_added) {
+                    uint32_t rk = LSQ_LD(pf + it);
+                    bool member = LSQ_LD(pf + it + 1) != rk;
+                    if (!member || (last_added != 0xFFFFFFFFu && rk != last_rank + 1)) ok = false;
+                    last_added = it;
+                    last_rank = rk;
+                }
+                cont = lsq_min(sg.y, ce);
+                ml += (uint32_t)(cont - cs);
+                if (ce < sg.y) {
+                    consumed = true;
+                    break;
+                } else if (ce == sg.y) {
+                    consumed = true;
+                    cs = ce;
+                } else {
+                    cs = sg.y;
+                }
+            } else if (cont > sg.x && cont < sg.y) {
+                break;
+            }
+            ++it;
+        }
+        if (!consumed) break;
+        ++b;
+    }
+    matched = ml;
+    return ok && last_added != 0xFFFFFFFFu;
+}
+
+LSQ_HD uint32_t hash_mask(uint64_t m) {
+    m ^= m >> 33;
+    m *= 0xff51afd7ed558ccdULL;
+    m ^= m >> 33;
+    return (uint32_t)m;
+}
+
+// The lower_bound skip of count.cpp:429-432: a read starting exactly at the event start is
+// passed over when its key (start, end, strand, name) sorts before the probe
+// (gs, ge, event strand, event name) under the comparator of count.cpp:64-85.
+LSQ_HD bool tie_skipped(const CountParams &P, const EvHdr &h, const ReadView &rv,
+                                            uint32_t strand) {
+    if (rv.b0.x != h.gs) return false;
+    int32_t r_end = rv.last_end();
+    if (r_end < h.ge) return true;
+    if (r_end > h.ge) return false;
+    uint8_t t = LSQ_LD(P.strand_tbl + strand * P.T.n_ann_strands + h.strand);
+    if (t & 1u) return true;
+    if (!(t & 2u)) return false;
+    uint32_t mode = h.flags & EV_TIE_MASK;
+    if (mode == 0u) return false;
+    if (mode == 1u) return true;
+    uint32_t ln = LSQ_LD(P.line_num + rv.read_index());
+    return digits_less(ln, P.T.tie_pool + h.tie_off, h.tie_len);
+}
+
+// One (read, event) pair -> form compatibility mask of a VALID read (0 otherwise) and matched bases.
+// Validity (count.cpp:438-448): compatible with some form and matched/total > 0.98 as IEEE doubles.
+LSQ_HD uint64_t eval_pair(const CountParams &P, const EvHdr &h, const int2 *seg,
+                                              const uint64_t *fm, const ReadView &rv, uint32_t strand,
+                                              uint32_t total_len, uint32_t &matched) {
+    matched = 0;
+    if (tie_skipped(P, h, rv, strand)) return 0;
+    uint64_t cm = 0;
+    uint32_t ml = 0;
+    if (!(h.flags & EV_WIDE)) {
+        uint64_t rmask;
+        walk_mask(rv, seg, h.S, rmask, ml);
+        if (rmask == 0) return 0;
+        // contiguous-run test (read.h:44-79) as a bit identity: within the span of the read's
+        // segments the form must contain exactly the read's segments.
+        uint32_t hi = 63u - (uint32_t)lsq_clz64(rmask);
+        uint64_t low = rmask & (0ull - rmask);
+        uint64_t span = ((2ull << hi) - 1ull) & ~(low - 1ull);
+        for (uint32_t k = 0; k < h.K; ++k) cm |= (uint64_t)((fm[k] & span) == rmask) << k;
+    } else {
+        const uint32_t *pf = P.T.pfx + h.pfx_off;
+        for (uint32_t k = 0; k < h.K; ++k) {
+            uint32_t mk;
+            bool ok = walk_wide(rv, seg, h.S, pf + (size_t)k * (h.S + 1u), mk);
+            ml = mk;
+            cm |= (uint64_t)ok << k;
+        }
+    }
+    if (cm == 0) return 0;
+    if (!(lsq_div((double)ml, (double)total_len) > 0.98)) return 0;
+    matched = ml;
+    return cm;
+}
+
+
+}  // namespace lsq

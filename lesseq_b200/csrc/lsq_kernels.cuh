@@ -1,0 +1,331 @@
+// Hand-written sm_100a kernels of the count + solve hot path.
+//
+//   lsq_filter_kernel  per-block covered-region filter + per-read interval list + stab piece key
+//                      (count/count.cpp:319-324; jsc/util/interval_list.hpp:396-422, 462-503;
+//                       index key of count.cpp:346-364)
+//   lsq_count_kernel   candidate scan, Read_single::build walk, compatibility, validity, class
+//                      histogram (count.cpp:421-482; common/read.h:44-79, 204-274)
+//   lsq_finalize_kernel per-event n_valid and per-form tallies from the class histogram
+//                      (count.cpp:467-482)
+//   lsq_solve_kernel   EM on the class histogram + RPKM + log-likelihood, FP64 without FMA
+//                      contraction (common/read.h:592-660; solve/solve.cpp:796-826)
+#pragma once
+#include "lsq_device_fn.cuh"
+
+namespace lsq {
+
+// ---------------------------------------------------------------------------------------------
+// Filter kernel: one thread per read.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+
+__global__ void __launch_bounds__(256) lsq_filter_kernel(FilterParams P, int2 *__restrict__ work) {
+    const Tables &T = P.T;
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in_range = r < P.n_reads;
+    FilteredRead fr;
+    fr.n = 0;
+    fr.key = T.n_pieces;
+    fr.first = make_int2(0, 0);
+    fr.strand = 0;
+    if (in_range) fr = filter_read(P, r, work);
+    const bool kept = fr.key != T.n_pieces;
+    // warp-aggregated allocation of ext entries (n slots for reads with n >= 2 kept blocks)
+    const uint32_t need = (kept && fr.n >= 2) ? fr.n : 0u;
+    uint32_t incl = need;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane_id() >= (uint32_t)d) incl += v;
+    }
+    const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    unsigned long long ext_base = 0;
+    if (lane_id() == 31 && total) ext_base = atomicAdd(P.counters + 1, (unsigned long long)total);
+    ext_base = __shfl_sync(0xFFFFFFFFu, ext_base, 31);
+    const unsigned kept_mask = __ballot_sync(0xFFFFFFFFu, kept);
+    if (lane_id() == 0 && kept_mask) atomicAdd(P.counters + 0, (unsigned long long)__popc(kept_mask));
+    if (!in_range) return;
+    ReadRec rec;
+    rec.x = (uint32_t)fr.first.x;
+    rec.y = (uint32_t)fr.first.y;
+    rec.w = (fr.strand << 24) | (fr.n & 0xFFFFFFu);
+    if (need) {
+        const uint32_t off = (uint32_t)(ext_base + incl - need);
+        const uint32_t base = __ldg(P.blk_off + r);
+        P.ext[off] = make_int2((int32_t)(uint32_t)r, (int32_t)fr.n);
+        for (uint32_t i = 1; i < fr.n; ++i) P.ext[off + i] = work[base + i];
+        rec.z = off;
+    } else {
+        rec.z = (uint32_t)r;
+    }
+    P.rkey[r] = fr.key;
+    P.rec[r] = rec;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Count kernel
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bump_class(const CountParams &P, const EvHdr &h, uint64_t cm) {
+    if (!(h.flags & EV_HASH)) {
+        atomicAdd(P.slot_cnt + h.slot_off + (uint32_t)(cm - 1ull), 1ull);
+        return;
+    }
+    uint32_t capm = h.slot_cap - 1u;
+    uint32_t i = hash_mask(cm) & capm;
+    while (true) {
+        unsigned long long *kp = P.slot_mask + h.slot_off + i;
+        unsigned long long cur = *((volatile unsigned long long *)kp);
+        if (cur == 0ull) cur = atomicCAS(kp, 0ull, (unsigned long long)cm);
+        if (cur == 0ull || cur == cm) {
+            atomicAdd(P.slot_cnt + h.slot_off + i, 1ull);
+            return;
+        }
+        i = (i + 1u) & capm;
+    }
+}
+
+// Reads arrive sorted by stab piece, so the 32 reads of a warp nearly always share one piece
+// and therefore one list of candidate events: the event loop is warp-uniform, per-class counts
+// are formed with __ballot_sync/__popc and one lane issues the global reduction.
+__global__ void __launch_bounds__(256) lsq_count_kernel(CountParams P) {
+    const Tables &T = P.T;
+    const unsigned long long n_kept = P.counters[0];
+    const uint32_t lane = lane_id();
+    const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    unsigned long long my_valid = 0;
+    for (uint64_t base = warp0 * 32ull; base < n_kept; base += n_warps * 32ull) {
+        const uint64_t i = base + lane;
+        const bool act = i < n_kept;
+        uint32_t key = T.n_pieces;
+        ReadView rv;
+        rv.b0 = make_int2(0, 0);
+        rv.n = 1;
+        rv.z = 0;
+        rv.ext = nullptr;
+        uint32_t strand = 0, total_len = 0;
+        if (act) {
+            key = __ldg(P.g_key + i);
+            ReadRec rec = __ldg(P.g_rec + i);
+            rv.b0 = make_int2((int32_t)rec.x, (int32_t)rec.y);
+            rv.n = rec.w & 0xFFFFFFu;
+            rv.z = rec.z;
+            strand = rec.w >> 24;
+            total_len = (uint32_t)(rv.b0.y - rv.b0.x);
+            if (rv.n > 1) {
+                rv.ext = P.ext + rec.z;
+                for (uint32_t j = 1; j < rv.n; ++j) {
+                    int2 b = __ldg(rv.ext + j);
+                    total_len += (uint32_t)(b.y - b.x);
+                }
+            }
+        }
+        unsigned todo = __ballot_sync(0xFFFFFFFFu, act);
+        while (todo) {
+            const int leader = __ffs(todo) - 1;
+            const uint32_t k0 = __shfl_sync(0xFFFFFFFFu, key, leader);
+            const bool mine = act && key == k0;
+            todo &= ~__ballot_sync(0xFFFFFFFFu, mine);
+            const uint32_t so = __ldg(T.stab_off + k0), se = __ldg(T.stab_off + k0 + 1);
+            for (uint32_t q = so; q < se; ++q) {
+                const uint32_t x = __ldg(T.stab_ev + q);
+                const EvHdr h = T.hdr[x];
+                uint64_t cm = 0;
+                uint32_t ml = 0;
+                if (mine) cm = eval_pair(P, h, T.seg + h.seg_off, T.fmask + h.form_off, rv, strand, total_len, ml);
+                const unsigned vmask = __ballot_sync(0xFFFFFFFFu, cm != 0);
+                if (vmask == 0) continue;
+                if (h.K <= 2) {
+                    const uint32_t ncls = (1u << h.K) - 1u;
+                    for (uint32_t c = 1; c <= ncls; ++c) {
+                        unsigned bm = __ballot_sync(0xFFFFFFFFu, cm == c);
+                        if (lane == 0 && bm)
+                            atomicAdd(P.slot_cnt + h.slot_off + c - 1u, (unsigned long long)__popc(bm));
+                    }
+                } else if (cm != 0) {
+                    bump_class(P, h, cm);
+                }
+                uint32_t sum = __reduce_add_sync(0xFFFFFFFFu, ml);
+                if (lane == 0) atomicAdd(P.bases + x, (unsigned long long)sum);
+                my_valid += (cm != 0);
+            }
+        }
+    }
+    my_valid = __reduce_add_sync(0xFFFFFFFFu, (unsigned)my_valid);
+    if (lane == 0 && my_valid) atomicAdd(P.stats, my_valid);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Class iteration shared by finalize and solve: visits (mask, count) of event h in read set m.
+// ---------------------------------------------------------------------------------------------
+struct ClassRange {
+    const unsigned long long *cnt;
+    const unsigned long long *mask;  // null: dense table, mask = index + 1
+    uint32_t n;
+};
+
+__device__ __forceinline__ ClassRange class_range(const SolveParams &P, const EvHdr &h, uint32_t m) {
+    ClassRange r;
+    if (P.inj_off[m]) {
+        uint64_t a = P.inj_off[m][h.out_ev], b = P.inj_off[m][h.out_ev + 1];
+        r.cnt = (const unsigned long long *)P.inj_cnt[m] + a;
+        r.mask = (const unsigned long long *)P.inj_mask[m] + a;
+        r.n = (uint32_t)(b - a);
+    } else {
+        size_t o = (size_t)m * P.T.total_slots + h.slot_off;
+        r.cnt = P.slot_cnt + o;
+        r.mask = (h.flags & EV_HASH) ? P.slot_mask + o : nullptr;
+        r.n = h.slot_cap;
+    }
+    return r;
+}
+
+// One thread per event: n_valid[m], bases[m] and per-form tallies in the caller's order.
+__global__ void __launch_bounds__(128) lsq_finalize_kernel(SolveParams P) {
+    uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= P.T.E) return;
+    const EvHdr h = P.T.hdr[x];
+    unsigned long long iso[LSQ_MAX_FORMS_PER_EVENT_DEV];
+    for (uint32_t k = 0; k < h.K; ++k) iso[k] = 0;
+    for (uint32_t m = 0; m < P.M; ++m) {
+        ClassRange cr = class_range(P, h, m);
+        unsigned long long nv = 0;
+        for (uint32_t i = 0; i < cr.n; ++i) {
+            unsigned long long c = cr.cnt[i];
+            if (!c) continue;
+            unsigned long long mk = cr.mask ? cr.mask[i] : (unsigned long long)(i + 1u);
+            nv += c;
+            for (uint32_t k = 0; k < h.K; ++k)
+                if ((mk >> k) & 1ull) iso[k] += c;
+        }
+        P.n_valid[(size_t)m * P.T.E + h.out_ev] = nv;
+        P.bases_out[(size_t)m * P.T.E + h.out_ev] = P.bases[(size_t)m * P.T.E + x];
+    }
+    for (uint32_t k = 0; k < h.K; ++k) P.iso_count[h.out_form + k] = iso[k];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Solve kernel: one warp per event, lanes over compatibility classes.
+// All floating point goes through __dmul_rn/__dadd_rn/__ddiv_rn so that nvcc cannot contract
+// multiply-add pairs into FMAs: per class the arithmetic is bit-identical to the reference's
+// per-read arithmetic (read.h:604-613, 628-632); only the order of the sum over reads differs.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xFFFFFFFFu, v, d));
+    return v;
+}
+
+// s = sum_k theta[k] * M(i,k) over the forms of the mask in ascending k (zero terms add nothing)
+__device__ __forceinline__ double class_prob(uint64_t mk, const double *theta, const double *G) {
+    double s = 0.0;
+    while (mk) {
+        int k = __ffsll((long long)mk) - 1;
+        mk &= mk - 1ull;
+        s = __dadd_rn(s, __dmul_rn(theta[k], G[k]));
+    }
+    return s;
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) lsq_solve_kernel(SolveParams P) {
+    __shared__ double s_theta[WARPS][2][LSQ_MAX_FORMS_PER_EVENT_DEV];
+    const uint32_t lane = lane_id();
+    const uint32_t w = threadIdx.x >> 5;
+    const uint32_t E = P.T.E;
+    for (uint32_t x = blockIdx.x * WARPS + w; x < E; x += gridDim.x * WARPS) {
+        const EvHdr h = P.T.hdr[x];
+        const uint32_t K = h.K;
+        double *th_old = s_theta[w][0], *th_new = s_theta[w][1];
+        // N = total number of valid reads (read.h:599-602), sum of supports (solve.cpp:826)
+        double n_total = 0.0, sum_supports = 0.0;
+        bool any = false;
+        for (uint32_t m = 0; m < P.M; ++m) {
+            unsigned long long nv = P.n_valid[(size_t)m * E + h.out_ev];
+            if (nv) {
+                any = true;
+                n_total = __dadd_rn(n_total, (double)nv);
+            }
+            sum_supports = __dadd_rn(sum_supports, (double)nv);
+        }
+        __syncwarp();
+        for (uint32_t k = lane; k < K; k += 32) th_new[k] = __ddiv_rn(1.0, (double)K);
+        __syncwarp();
+        uint32_t iters = 0;
+        double ll = 0.0;
+        auto loglik = [&](const double *th) {  // read.h:620-636
+            double part = 0.0;
+            for (uint32_t m = 0; m < P.M; ++m) {
+                ClassRange cr = class_range(P, h, m);
+                const double *G = P.G + (size_t)m * P.T.F + h.form_off;
+                for (uint32_t i = lane; i < cr.n; i += 32) {
+                    unsigned long long c = cr.cnt[i];
+                    if (!c) continue;
+                    uint64_t mk = cr.mask ? cr.mask[i] : (uint64_t)(i + 1u);
+                    part = __dadd_rn(part, __dmul_rn((double)c, log(class_prob(mk, th, G))));
+                }
+            }
+            return warp_sum(part);
+        };
+        if (!any) {
+            // no valid read in any read set: uniform theta, log-likelihood 0 (solve.cpp:798-800)
+        } else if (K == 1) {
+            if (lane == 0) th_new[0] = 1.0;  // solve.cpp:801-802
+            __syncwarp();
+            ll = loglik(th_new);
+        } else {
+            double ll_old = loglik(th_new);
+            while (true) {  // read.h:647-659
+                __syncwarp();
+                for (uint32_t k = lane; k < K; k += 32) th_old[k] = th_new[k];
+                __syncwarp();
+                for (uint32_t k = 0; k < K; ++k) {  // read.h:597-617
+                    double part = 0.0;
+                    for (uint32_t m = 0; m < P.M; ++m) {
+                        ClassRange cr = class_range(P, h, m);
+                        const double *G = P.G + (size_t)m * P.T.F + h.form_off;
+                        for (uint32_t i = lane; i < cr.n; i += 32) {
+                            unsigned long long c = cr.cnt[i];
+                            if (!c) continue;
+                            uint64_t mk = cr.mask ? cr.mask[i] : (uint64_t)(i + 1u);
+                            if (!((mk >> k) & 1ull)) continue;
+                            double s = class_prob(mk, th_old, G);
+                            if (s > 0.0) {
+                                double lp = __dmul_rn(th_old[k], G[k]);
+                                if (lp > 0.0) part = __dadd_rn(part, __dmul_rn((double)c, __ddiv_rn(lp, s)));
+                            }
+                        }
+                    }
+                    double z = warp_sum(part);
+                    if (lane == 0) th_new[k] = __ddiv_rn(z, n_total);
+                }
+                __syncwarp();
+                ll = loglik(th_new);
+                ++iters;
+                double ratio = __ddiv_rn(ll_old, ll);
+                if (!(fabs(__dsub_rn(1.0, ratio)) > 1E-6) || iters >= P.max_iters) break;
+                ll_old = ll;  // the next iteration's old_ll is this very value (same theta, same order)
+            }
+        }
+        __syncwarp();
+        // RPKM (solve.cpp:809-821) and outputs
+        for (uint32_t k = lane; k < K; k += 32) {
+            double th = th_new[k];
+            double r = 0.0;
+            for (uint32_t m = 0; m < P.M; ++m)
+                r = __dadd_rn(r, __dmul_rn((double)P.bases[(size_t)m * E + x], th));
+            r = __ddiv_rn(r, __ddiv_rn((double)P.form_len[h.form_off + k], 1.0E3));
+            r = __ddiv_rn(r, P.total_read_mbases);
+            P.theta[h.out_form + k] = th;
+            P.rpkm[h.out_form + k] = r;
+        }
+        if (lane == 0) {
+            P.loglik[h.out_ev] = ll;
+            P.ll_per_read[h.out_ev] = (sum_supports > 1E-5) ? __ddiv_rn(ll, sum_supports) : 0.0;
+            P.iters[h.out_ev] = iters;
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace lsq

@@ -1,0 +1,276 @@
+// Host-side layout of the device tables (pure C++, shared by lsq_abi.cu and the CPU replay
+// harness under tests/emul/).  Turns the caller's event model (lsq_event_tables, output order)
+// into the sorted internal arrays the kernels read: event headers, segments, form masks /
+// prefix counts, tie-break data, class-slot layout and the stab arrangement.
+#pragma once
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/lesseq_b200.h"
+#include "lsq_types.cuh"
+
+namespace lsq {
+
+struct HostTables {
+    uint32_t E = 0, F = 0, n_chroms = 0, n_strands = 0;
+    uint64_t slot_total = 0;
+    std::vector<uint32_t> order;  // internal -> output event index
+    std::vector<EvHdr> hdr;       // internal order + sentinel
+    std::vector<int2> seg;
+    std::vector<uint64_t> fmask, form_len, form_seg_len;
+    std::vector<uint32_t> pfx, form_seg_off;
+    std::vector<char> tie;
+    std::vector<uint32_t> bp_chrom_off, stab_off, stab_ev, cov_off;
+    std::vector<int32_t> bp_pos, cov_start, cov_end;
+
+    // Table view over the HOST arrays (CPU replay harness only).
+    Tables host_view() const {
+        Tables T{};
+        T.E = E;
+        T.F = F;
+        T.n_pieces = (uint32_t)bp_pos.size();
+        T.n_chroms = n_chroms;
+        T.n_ann_strands = n_strands;
+        T.total_slots = slot_total;
+        T.hdr = hdr.data();
+        T.seg = seg.data();
+        T.fmask = fmask.data();
+        T.pfx = pfx.data();
+        T.tie_pool = tie.data();
+        T.bp_chrom_off = bp_chrom_off.data();
+        T.bp_pos = bp_pos.data();
+        T.stab_off = stab_off.data();
+        T.stab_ev = stab_ev.data();
+        T.cov_off = cov_off.data();
+        T.cov_start = cov_start.data();
+        T.cov_end = cov_end.data();
+        return T;
+    }
+};
+
+inline int tfail(std::string &err, int code, const std::string &msg) {
+    err = msg;
+    return code;
+}
+
+// "read-<N>" < name ?  0: never, 1: always, 2: decided by comparing the digits of N with the
+// suffix of the name after "read-" (count.cpp:64-85 with read names of count.cpp:293-295).
+inline uint8_t tie_mode(const std::string &name) {
+    static const char P[] = "read-";
+    size_t n = std::min<size_t>(5, name.size());
+    for (size_t i = 0; i < n; ++i) {
+        unsigned char a = (unsigned char)P[i], b = (unsigned char)name[i];
+        if (a != b) return a < b ? 1 : 0;
+    }
+    if (name.size() <= 5) return 0;  // the name is a prefix of every read name
+    return 2;
+}
+
+// ARS length of one form: closed form of accessible_read_starts.h:48-89 (MEDIUM) and :221-274
+// (SHORT, min_partial 0): segments before the first one from which a read of length R no
+// longer fits contribute l (MEDIUM) or l+1 (SHORT) starts; that segment contributes
+// max(l + 1 - overshoot, 0).
+inline uint64_t ars_length(uint32_t read_type, uint64_t R, const uint64_t *len, uint32_t n) {
+    uint64_t T = 0;
+    for (uint32_t i = 0; i < n; ++i) T += len[i];
+    uint64_t total = 0, c = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        c += len[i];
+        if (c + R > T) {
+            long long tail = (long long)len[i] + 1 - (long long)(c + R - T);
+            return total + (tail > 0 ? (uint64_t)tail : 0);
+        }
+        total += len[i] + (read_type == LSQ_READ_SHORT ? 1 : 0);
+    }
+    return total;
+}
+
+// G_k = 1 / ARS_k, or 0 when no read of this length fits (read.h:331-340); internal form order.
+inline void form_weights(const HostTables &H, uint32_t read_type, uint64_t read_length, std::vector<double> &G) {
+    G.assign(H.F, 0.0);
+    for (uint32_t f = 0; f < H.F; ++f) {
+        uint32_t a = H.form_seg_off[f], b = H.form_seg_off[f + 1];
+        uint64_t ars = ars_length(read_type, read_length, H.form_seg_len.data() + a, b - a);
+        double nd = (double)ars;
+        G[f] = (nd <= 0) ? 0.0 : 1.0 / nd;
+    }
+}
+
+// strand order table: bit0 = read strand string < event strand string, bit1 = equal
+inline void strand_table(const char *const *file_strands, uint32_t nf, const std::vector<std::string> &ann,
+                         std::vector<uint8_t> &tbl) {
+    tbl.assign(std::max<size_t>((size_t)nf * ann.size(), 1), 0);
+    for (uint32_t i = 0; i < nf; ++i)
+        for (size_t j = 0; j < ann.size(); ++j) {
+            std::string a = file_strands[i];
+            tbl[(size_t)i * ann.size() + j] = (uint8_t)((a < ann[j] ? 1 : 0) | (a == ann[j] ? 2 : 0));
+        }
+}
+
+inline int build_host_tables(const lsq_event_tables *t, HostTables &H, std::string &err) {
+    const uint32_t E = t->n_events;
+    if (t->n_chroms > 0xFFFF) return tfail(err, LSQ_ERR_RANGE, "more than 65535 chromosomes");
+    if (t->n_strands > 0xFF) return tfail(err, LSQ_ERR_RANGE, "more than 255 strand strings");
+    // internal order: (chromosome, gs, ge, output index)
+    std::vector<uint32_t> &order = H.order;
+    order.assign(E, 0);
+    for (uint32_t i = 0; i < E; ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+        if (t->ev_chrom[a] != t->ev_chrom[b]) return t->ev_chrom[a] < t->ev_chrom[b];
+        if (t->ev_gs[a] != t->ev_gs[b]) return t->ev_gs[a] < t->ev_gs[b];
+        if (t->ev_ge[a] != t->ev_ge[b]) return t->ev_ge[a] < t->ev_ge[b];
+        return a < b;
+    });
+    std::vector<lsq::EvHdr> &hdr = H.hdr;
+    hdr.assign(E + 1, lsq::EvHdr());
+    std::vector<int2> &seg = H.seg;
+    std::vector<uint64_t> &fmask = H.fmask, &form_len = H.form_len, &form_seg_len = H.form_seg_len;
+    std::vector<uint32_t> &pfx = H.pfx, &form_seg_off = H.form_seg_off;
+    seg.clear(); fmask.clear(); form_len.clear(); form_seg_len.clear(); pfx.clear();
+    form_seg_off.assign(1, 0);
+    std::string tie_pool;
+    uint64_t slot_total = 0;
+    for (uint32_t ie = 0; ie < E; ++ie) {
+        const uint32_t e = order[ie];
+        lsq::EvHdr &h = hdr[ie];
+        h = lsq::EvHdr();
+        const uint32_t s0 = t->ev_seg_off[e], S = t->ev_seg_off[e + 1] - s0;
+        const uint32_t f0 = t->ev_form_off[e], K = t->ev_form_off[e + 1] - f0;
+        if (K == 0 || K > LSQ_MAX_FORMS_PER_EVENT)
+            return tfail(err, LSQ_ERR_RANGE, "event with 0 or more than 64 forms");
+        if (S > 0xFFFF) return tfail(err, LSQ_ERR_RANGE, "event with more than 65535 segments");
+        if (t->ev_chrom[e] >= t->n_chroms || t->ev_strand[e] >= t->n_strands)
+            return tfail(err, LSQ_ERR_ARG, "event chromosome/strand id out of range");
+        if (t->ev_ge[e] == INT32_MAX) return tfail(err, LSQ_ERR_RANGE, "event end at INT32_MAX");
+        h.gs = t->ev_gs[e];
+        h.ge = t->ev_ge[e];
+        h.seg_off = (uint32_t)seg.size();
+        h.form_off = (uint32_t)fmask.size();
+        h.S = (uint16_t)S;
+        h.K = (uint16_t)K;
+        h.strand = (uint8_t)t->ev_strand[e];
+        h.out_ev = e;
+        h.out_form = f0;
+        for (uint32_t s = 0; s < S; ++s) {
+            if (s && t->seg_start[s0 + s] < t->seg_end[s0 + s - 1])
+                return tfail(err, LSQ_ERR_ARG, "segments of an event must be disjoint and ascending");
+            seg.push_back(make_int2(t->seg_start[s0 + s], t->seg_end[s0 + s]));
+        }
+        std::string name(t->ev_names + t->ev_name_off[e], t->ev_names + t->ev_name_off[e + 1]);
+        uint8_t mode = tie_mode(name);
+        h.flags = mode;
+        if (mode == 2) {
+            h.tie_off = (uint32_t)tie_pool.size();
+            h.tie_len = (uint16_t)std::min<size_t>(name.size() - 5, 0xFFFF);
+            tie_pool.append(name, 5, h.tie_len);
+        }
+        const bool wide = S > 64;
+        if (wide) {
+            h.flags |= lsq::EV_WIDE;
+            h.pfx_off = (uint32_t)pfx.size();
+        }
+        uint64_t runs_bound = 0;
+        for (uint32_t k = 0; k < K; ++k) {
+            const uint32_t a = t->form_seg_off[f0 + k], b = t->form_seg_off[f0 + k + 1];
+            uint64_t mask = 0, len = 0;
+            std::vector<uint32_t> member(S + 1, 0);
+            uint32_t prev = 0;
+            for (uint32_t q = a; q < b; ++q) {
+                uint32_t si = t->form_seg_idx[q];
+                if (si >= S || (q > a && si <= prev))
+                    return tfail(err, LSQ_ERR_ARG, "form segment indices must be ascending and < S");
+                prev = si;
+                if (si < 64) mask |= 1ull << si;
+                member[si] = 1;
+                uint64_t l = (uint64_t)((int64_t)t->seg_end[s0 + si] - (int64_t)t->seg_start[s0 + si]);
+                len += l;
+                form_seg_len.push_back(l);
+            }
+            form_seg_off.push_back((uint32_t)form_seg_len.size());
+            fmask.push_back(wide ? 0ull : mask);
+            form_len.push_back(len);
+            uint64_t nk = b - a;
+            runs_bound += nk * (nk + 1) / 2;
+            if (wide) {
+                uint32_t acc = 0;
+                for (uint32_t s = 0; s <= S; ++s) {
+                    pfx.push_back(acc);
+                    if (s < S) acc += member[s];
+                }
+            }
+        }
+        h.slot_off = (uint32_t)slot_total;
+        if (K <= (uint32_t)lsq::DENSE_MAX_FORMS) {
+            h.slot_cap = (1u << K) - 1u;
+        } else {
+            // distinct classes <= distinct valid segment runs <= sum_k n_k (n_k + 1) / 2
+            uint64_t want = 2 * runs_bound + 2;
+            uint64_t cap = 16;
+            while (cap < want) cap <<= 1;
+            if (cap > (1ull << 30)) return tfail(err, LSQ_ERR_RANGE, "class table of one event exceeds 2^30 slots");
+            h.slot_cap = (uint32_t)cap;
+            h.flags |= lsq::EV_HASH;
+        }
+        slot_total += h.slot_cap;
+        if (slot_total > 0xFFFFFFFFull) return tfail(err, LSQ_ERR_RANGE, "class tables exceed 2^32 slots");
+    }
+    hdr[E].seg_off = (uint32_t)seg.size();
+    hdr[E].form_off = (uint32_t)fmask.size();
+
+    // stab arrangement: per chromosome the event spans [gs, ge] cut the axis into pieces;
+    // every read start falls into one piece and the piece lists the events it is a candidate for.
+    std::vector<uint32_t> &bp_chrom_off = H.bp_chrom_off, &stab_off = H.stab_off, &stab_ev = H.stab_ev;
+    std::vector<int32_t> &bp_pos = H.bp_pos;
+    bp_chrom_off.assign(t->n_chroms + 1, 0);
+    stab_off.assign(1, 0);
+    stab_ev.clear();
+    bp_pos.clear();
+    {
+        uint32_t ie = 0;
+        for (uint32_t ch = 0; ch < t->n_chroms; ++ch) {
+            bp_chrom_off[ch] = (uint32_t)bp_pos.size();
+            uint32_t first = ie;
+            while (ie < E && t->ev_chrom[order[ie]] == ch) ++ie;
+            if (ie == first) continue;
+            std::vector<int32_t> bps;
+            for (uint32_t q = first; q < ie; ++q) {
+                bps.push_back(hdr[q].gs);
+                bps.push_back(hdr[q].ge + 1);
+            }
+            std::sort(bps.begin(), bps.end());
+            bps.erase(std::unique(bps.begin(), bps.end()), bps.end());
+            std::vector<std::vector<uint32_t> > lists(bps.size());
+            uint64_t total = 0;
+            for (uint32_t q = first; q < ie; ++q) {
+                size_t a = std::lower_bound(bps.begin(), bps.end(), hdr[q].gs) - bps.begin();
+                size_t b = std::lower_bound(bps.begin(), bps.end(), hdr[q].ge + 1) - bps.begin();
+                for (size_t p = a; p < b; ++p) lists[p].push_back(q);
+                total += b - a;
+                if (stab_ev.size() + total > 0x7FFFFFFFull)
+                    return tfail(err, LSQ_ERR_RANGE, "stab lists exceed 2^31 entries (too many nested events)");
+            }
+            for (size_t p = 0; p < bps.size(); ++p) {
+                bp_pos.push_back(bps[p]);
+                stab_ev.insert(stab_ev.end(), lists[p].begin(), lists[p].end());
+                stab_off.push_back((uint32_t)stab_ev.size());
+            }
+        }
+        bp_chrom_off[t->n_chroms] = (uint32_t)bp_pos.size();
+        if (ie != E) return tfail(err, LSQ_ERR_ARG, "event chromosome ids must be < n_chroms");
+    }
+    H.cov_off.assign(t->cov_off, t->cov_off + t->n_chroms + 1);
+    H.cov_start.assign(t->cov_start, t->cov_start + H.cov_off.back());
+    H.cov_end.assign(t->cov_end, t->cov_end + H.cov_off.back());
+    H.tie.assign(tie_pool.begin(), tie_pool.end());
+    H.slot_total = slot_total;
+    H.E = E;
+    H.F = (uint32_t)fmask.size();
+    H.n_chroms = t->n_chroms;
+    H.n_strands = t->n_strands;
+    return LSQ_OK;
+
+}
+
+}  // namespace lsq

@@ -1,0 +1,110 @@
+// Device-side table layouts shared by the kernels and the host orchestration (lsq_abi.cu).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace lsq {
+
+constexpr uint32_t KEY_NONE_BITS = 0xFFFFFFFFu;
+constexpr int DENSE_MAX_FORMS = 8;  // events with K <= 8 use a direct-indexed class table
+constexpr int LSQ_MAX_FORMS_PER_EVENT_DEV = 64;
+
+// Event header, 48 bytes, events sorted by (chromosome, gs, ge).  hdr[E] is a sentinel whose
+// seg_off / form_off close the last event's ranges.
+struct __align__(16) EvHdr {
+    int32_t gs, ge;        // candidate reads have gs <= start <= ge (count.cpp:431-432)
+    uint32_t seg_off;      // into seg[]
+    uint32_t form_off;     // into fmask[] / G[] (internal form order)
+    uint16_t S, K;         // segments, forms
+    uint8_t strand;        // annotation strand id of the first form
+    uint8_t flags;         // EV_* below
+    uint16_t tie_len;      // length of the name suffix for tie mode 2
+    uint32_t slot_off;     // first class slot of this event (per read set: + m * total_slots)
+    uint32_t slot_cap;     // dense: 2^K-1 slots indexed by mask-1; hash: power of two
+    uint32_t tie_off;      // into tie_pool
+    uint32_t pfx_off;      // into pfx[] when EV_WIDE (K rows of S+1 prefix counts)
+    uint32_t out_ev;       // index of the event in the caller's (output) order
+    uint32_t out_form;     // index of the event's first form in the caller's order
+};
+static_assert(sizeof(EvHdr) == 48, "EvHdr layout");
+
+constexpr uint8_t EV_TIE_MASK = 0x3;   // 0: "read-N" never < name, 1: always, 2: compare digits with suffix
+constexpr uint8_t EV_WIDE = 0x4;       // S > 64: prefix-count compatibility test
+constexpr uint8_t EV_HASH = 0x8;       // class table is an open-addressed hash (K > DENSE_MAX_FORMS)
+
+// Sorted read record (16 bytes), value type of the radix sort keyed by stab piece.
+//   x,y : first kept block [start,end)
+//   z   : n == 1 ? original read index : offset of the read's entry in ext[]
+//   w   : (file strand id << 24) | n   (n = number of kept blocks)
+// ext entry of a multi-block read: ext[z] = {read index, n}, ext[z+1 .. z+n-1] = blocks 1..n-1.
+typedef uint4 ReadRec;
+
+struct Tables {
+    uint32_t E, F, n_pieces, n_chroms, n_ann_strands;
+    uint64_t total_slots;
+    const EvHdr *hdr;
+    const int2 *seg;
+    const uint64_t *fmask;
+    const uint32_t *pfx;
+    const char *tie_pool;
+    const uint32_t *bp_chrom_off;  // [n_chroms+1] piece range per chromosome
+    const int32_t *bp_pos;         // [n_pieces] first position of each stab piece
+    const uint32_t *stab_off;      // [n_pieces+1]
+    const uint32_t *stab_ev;       // events (internal ids) whose span covers the piece
+    const uint32_t *cov_off;       // [n_chroms+1]
+    const int32_t *cov_start, *cov_end;
+};
+
+struct FilterParams {
+    Tables T;
+    uint64_t n_reads;
+    const uint32_t *blk_off;
+    const int2 *blk;
+    const uint32_t *read_cs;
+    const uint32_t *blk_cs;       // may be null
+    const uint32_t *chrom_remap;  // file chromosome id -> annotation id or 0xFFFFFFFF
+    int2 *ext;                    // [n_blocks + n_reads] worst case
+    uint32_t *rkey;               // [n_reads] stab piece or n_pieces (= dropped)
+    ReadRec *rec;                 // [n_reads]
+    unsigned long long *counters; // [0] kept reads, [1] ext cursor, [2] valid pairs
+};
+
+struct CountParams {
+    Tables T;
+    const unsigned long long *counters;
+    const uint32_t *g_key;
+    const ReadRec *g_rec;
+    const int2 *ext;
+    const uint32_t *line_num;
+    const uint8_t *strand_tbl;   // [file strands x annotation strands] bit0: read < event, bit1: equal
+    unsigned long long *slot_cnt;   // this read set's class counters
+    unsigned long long *slot_mask;  // hash keys (EV_HASH events)
+    unsigned long long *bases;      // [E] internal order
+    unsigned long long *stats;      // [0] valid pairs
+};
+
+struct SolveParams {
+    Tables T;
+    uint32_t M;
+    const unsigned long long *slot_cnt;   // [M * total_slots]
+    const unsigned long long *slot_mask;  // [M * total_slots]
+    const unsigned long long *bases;      // [M * E] internal order
+    const double *G;                      // [M * F] internal form order, 1/ARS or 0
+    const uint64_t *form_len;             // [F] internal form order
+    // injected class tables (output-order CSR), per read set; null when counted on the device
+    const uint64_t *inj_off[16];
+    const uint64_t *inj_mask[16];
+    const uint64_t *inj_cnt[16];
+    double total_read_mbases;
+    // outputs, caller (output) order
+    unsigned long long *n_valid;    // [M * E]
+    unsigned long long *bases_out;  // [M * E]
+    unsigned long long *iso_count;  // [F]
+    double *theta, *rpkm, *se;      // [F]
+    double *loglik, *ll_per_read;   // [E]
+    uint32_t *iters;                // [E]
+    uint32_t max_iters;
+    int with_se;
+};
+
+}  // namespace lsq

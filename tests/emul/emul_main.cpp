@@ -1,0 +1,281 @@
+// CPU replay harness -- TEST INFRASTRUCTURE ONLY (never built into or loaded by lesseq_b200).
+//
+// The development container has no GPU, so kernel logic bugs would otherwise surface only on
+// gpurun calls.  This program compiles the product's own per-read / per-pair device functions
+// (lesseq_b200/csrc/lsq_device_fn.cuh, via the LSQ_HD switch) and the product's host table
+// layout (lsq_tables_host.hpp) with g++ and replays the filter -> index -> count pipeline
+// sequentially; the EM is restated over the class histogram with the same per-class
+// arithmetic as lsq_solve_kernel.  tests/test_emul_vs_oracle.py compares its output with the
+// oracle.  It takes the same positional arguments as the reference programs.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../lesseq_b200/csrc/host/annotation.hpp"
+#include "../../lesseq_b200/csrc/host/mrf.hpp"
+#include "../../lesseq_b200/csrc/lsq_device_fn.cuh"
+#include "../../lesseq_b200/csrc/lsq_tables_host.hpp"
+
+static std::string g_err;
+namespace lsqh {
+void set_error(const std::string &m) { g_err = m; }
+}  // namespace lsqh
+extern "C" const char *lsq_last_error(void) { return g_err.c_str(); }
+
+using namespace lsq;
+
+static double class_prob_h(uint64_t mk, const double *theta, const double *G) {
+    double s = 0.0;
+    for (int k = 0; k < 64; ++k)
+        if ((mk >> k) & 1ull) s = s + theta[k] * G[k];
+    return s;
+}
+
+int main(int argc, char **argv) {
+    if (argc < 2) return 2;
+    const bool solve = std::string(argv[1]) == "solve";
+    argv += 1;
+    argc -= 1;
+    const int group = solve ? 5 : 4;
+    if (argc < 10 + group) return 1;
+    int argi = 4;
+    std::string form_path = argv[argi + 1], map_path = argv[argi + 3];
+    unsigned long begin = strtoul(argv[8], nullptr, 10), end = strtoul(argv[9], nullptr, 10);
+    argi = 10;
+    struct RA {
+        std::string type, path;
+        unsigned long len;
+        double trb;
+    };
+    std::vector<RA> sets;
+    while (argi < argc) {
+        RA r;
+        argi++;
+        r.type = argv[argi++];
+        r.len = strtoul(argv[argi++], nullptr, 10);
+        r.path = argv[argi++];
+        r.trb = solve ? atof(argv[argi++]) : 0;
+        sets.push_back(r);
+    }
+    lsqh_annotation ann;
+    int rc = lsqh::load_annotation(form_path.c_str(), map_path.c_str(), begin, end, 0, UINT64_MAX, ann);
+    if (rc) {
+        fprintf(stderr, "emul: %s\n", g_err.c_str());
+        return 1;
+    }
+    lsq_event_tables t{};
+    t.n_events = (uint32_t)ann.ev_chrom.size();
+    t.n_forms = (uint32_t)ann.form_name.size();
+    t.n_segments = (uint32_t)ann.seg_start.size();
+    t.n_chroms = (uint32_t)ann.chroms.names.size();
+    t.n_strands = (uint32_t)ann.strands.names.size();
+    t.ev_chrom = ann.ev_chrom.data();
+    t.ev_strand = ann.ev_strand.data();
+    t.ev_gs = ann.ev_gs.data();
+    t.ev_ge = ann.ev_ge.data();
+    t.ev_seg_off = ann.ev_seg_off.data();
+    t.ev_form_off = ann.ev_form_off.data();
+    t.ev_name_off = ann.ev_name_off.data();
+    t.ev_names = ann.ev_names_pool.data();
+    t.seg_start = ann.seg_start.data();
+    t.seg_end = ann.seg_end.data();
+    t.form_seg_off = ann.form_seg_off.data();
+    t.form_seg_idx = ann.form_seg_idx.data();
+    t.cov_off = ann.cov_off.data();
+    t.cov_start = ann.cov_start.data();
+    t.cov_end = ann.cov_end.data();
+    t.chrom_names = ann.chrom_ptrs.data();
+    t.strand_names = ann.strand_ptrs.data();
+    HostTables H;
+    std::string err;
+    rc = build_host_tables(&t, H, err);
+    if (rc) {
+        fprintf(stderr, "emul: %s\n", err.c_str());
+        return 1;
+    }
+    const Tables T = H.host_view();
+    const uint32_t E = H.E, M = (uint32_t)sets.size();
+    if (E == 0) return 0;
+    std::map<std::string, uint32_t> chrom_id;
+    for (uint32_t i = 0; i < t.n_chroms; ++i) chrom_id[t.chrom_names[i]] = i;
+    std::vector<std::string> ann_strands(ann.strands.names);
+
+    // class histogram per (m, internal event): mask -> count
+    std::vector<std::vector<std::map<uint64_t, uint64_t> > > hist(M, std::vector<std::map<uint64_t, uint64_t> >(E));
+    std::vector<std::vector<uint64_t> > bases(M, std::vector<uint64_t>(E, 0));
+    std::vector<std::vector<double> > Gm(M);
+    for (uint32_t m = 0; m < M; ++m) {
+        uint32_t type;
+        if (sets[m].type == "MEDIUM_READ") type = LSQ_READ_MEDIUM;
+        else if (sets[m].type == "SHORT_READ") type = LSQ_READ_SHORT;
+        else return 1;
+        form_weights(H, type, sets[m].len, Gm[m]);
+        lsqh_reads R;
+        rc = lsqh::parse_mrf(sets[m].path.c_str(), R);
+        if (rc) {
+            fprintf(stderr, "emul: %s\n", g_err.c_str());
+            return 1;
+        }
+        const size_t n = R.read_cs.size(), nb = R.blk_cs.size();
+        std::vector<uint32_t> remap(std::max<size_t>(R.chroms.names.size(), 1), 0xFFFFFFFFu);
+        for (size_t i = 0; i < R.chroms.names.size(); ++i) {
+            auto it = chrom_id.find(R.chroms.names[i]);
+            if (it != chrom_id.end()) remap[i] = it->second;
+        }
+        std::vector<uint8_t> stbl;
+        strand_table(R.strand_ptrs.data(), (uint32_t)R.strand_ptrs.size(), ann_strands, stbl);
+        std::vector<int2> work(std::max<size_t>(nb, 1)), ext(std::max<size_t>(nb, 1));
+        std::vector<uint32_t> rkey(n);
+        std::vector<ReadRec> rec(n);
+        unsigned long long counters[4] = {0, 0, 0, 0};
+        FilterParams FP{};
+        FP.T = T;
+        FP.n_reads = n;
+        FP.blk_off = R.blk_off.data();
+        FP.blk = reinterpret_cast<const int2 *>(R.blk.data());
+        FP.read_cs = R.read_cs.data();
+        FP.blk_cs = R.any_mixed ? R.blk_cs.data() : nullptr;
+        FP.chrom_remap = remap.data();
+        FP.ext = ext.data();
+        FP.rkey = rkey.data();
+        FP.rec = rec.data();
+        FP.counters = counters;
+        for (size_t r = 0; r < n; ++r) {  // lsq_filter_kernel, one "thread" at a time
+            FilteredRead fr = filter_read(FP, r, work.data());
+            ReadRec q;
+            q.x = (uint32_t)fr.first.x;
+            q.y = (uint32_t)fr.first.y;
+            q.w = (fr.strand << 24) | (fr.n & 0xFFFFFFu);
+            if (fr.key != T.n_pieces && fr.n >= 2) {
+                uint32_t off = (uint32_t)counters[1];
+                counters[1] += fr.n;
+                ext[off] = make_int2((int32_t)r, (int32_t)fr.n);
+                for (uint32_t i = 1; i < fr.n; ++i) ext[off + i] = work[R.blk_off[r] + i];
+                q.z = off;
+            } else {
+                q.z = (uint32_t)r;
+            }
+            rkey[r] = fr.key;
+            rec[r] = q;
+        }
+        std::vector<uint32_t> perm(n);
+        for (size_t i = 0; i < n; ++i) perm[i] = (uint32_t)i;
+        std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) { return rkey[a] < rkey[b]; });
+        CountParams CP{};
+        CP.T = T;
+        CP.ext = ext.data();
+        CP.line_num = R.line_num.data();
+        CP.strand_tbl = stbl.data();
+        for (size_t i = 0; i < n; ++i) {  // lsq_count_kernel, one read at a time
+            uint32_t r = perm[i];
+            uint32_t key = rkey[r];
+            if (key == T.n_pieces) break;
+            ReadRec q = rec[r];
+            ReadView rv;
+            rv.b0 = make_int2((int32_t)q.x, (int32_t)q.y);
+            rv.n = q.w & 0xFFFFFFu;
+            rv.z = q.z;
+            rv.ext = rv.n > 1 ? ext.data() + q.z : nullptr;
+            uint32_t strand = q.w >> 24;
+            uint32_t total = (uint32_t)(rv.b0.y - rv.b0.x);
+            for (uint32_t j = 1; j < rv.n; ++j) total += (uint32_t)(rv.ext[j].y - rv.ext[j].x);
+            for (uint32_t s = T.stab_off[key]; s < T.stab_off[key + 1]; ++s) {
+                uint32_t x = T.stab_ev[s];
+                const EvHdr &h = T.hdr[x];
+                uint32_t ml;
+                uint64_t cm = eval_pair(CP, h, T.seg + h.seg_off, T.fmask + h.form_off, rv, strand, total, ml);
+                if (cm) {
+                    hist[m][x][cm]++;
+                    bases[m][x] += ml;
+                }
+            }
+        }
+    }
+    // outputs in the caller's order
+    std::vector<uint32_t> inv(E);
+    for (uint32_t ie = 0; ie < E; ++ie) inv[H.order[ie]] = ie;
+    int prec = 6;
+    if (const char *p = getenv("LSQ_PRECISION")) prec = atoi(p);
+    for (uint32_t e = 0; e < E; ++e) {
+        const uint32_t x = inv[e];
+        const EvHdr &h = H.hdr[x];
+        const uint32_t K = h.K;
+        std::vector<uint64_t> nv(M, 0), iso(K, 0);
+        for (uint32_t m = 0; m < M; ++m)
+            for (auto &kv : hist[m][x]) {
+                nv[m] += kv.second;
+                for (uint32_t k = 0; k < K; ++k)
+                    if ((kv.first >> k) & 1ull) iso[k] += kv.second;
+            }
+        std::vector<double> theta(K, 1.0 / (double)K), rpkm(K, 0.0);
+        double ll = 0.0, sum_supports = 0.0, n_total = 0.0;
+        bool any = false;
+        for (uint32_t m = 0; m < M; ++m) {
+            if (nv[m]) {
+                any = true;
+                n_total += (double)nv[m];
+            }
+            sum_supports += (double)nv[m];
+        }
+        if (solve) {
+            auto loglik = [&](const std::vector<double> &th) {
+                double s = 0.0;
+                for (uint32_t m = 0; m < M; ++m)
+                    for (auto &kv : hist[m][x])
+                        s += (double)kv.second * log(class_prob_h(kv.first, th.data(), Gm[m].data() + h.form_off));
+                return s;
+            };
+            if (!any) {
+            } else if (K == 1) {
+                theta[0] = 1.0;
+                ll = loglik(theta);
+            } else {
+                double ll_old = loglik(theta);
+                while (true) {
+                    std::vector<double> old_t = theta;
+                    for (uint32_t k = 0; k < K; ++k) {
+                        double z = 0.0;
+                        for (uint32_t m = 0; m < M; ++m) {
+                            const double *G = Gm[m].data() + h.form_off;
+                            for (auto &kv : hist[m][x]) {
+                                if (!((kv.first >> k) & 1ull)) continue;
+                                double s = class_prob_h(kv.first, old_t.data(), G);
+                                if (s > 0.0) {
+                                    double lp = old_t[k] * G[k];
+                                    if (lp > 0.0) z += (double)kv.second * (lp / s);
+                                }
+                            }
+                        }
+                        theta[k] = z / n_total;
+                    }
+                    ll = loglik(theta);
+                    if (!(fabs(1.0 - ll_old / ll) > 1E-6)) break;
+                    ll_old = ll;
+                }
+            }
+            double mb = 0.0;
+            for (uint32_t m = 0; m < M; ++m) mb += sets[m].trb / 1.0E6;
+            for (uint32_t k = 0; k < K; ++k) {
+                double r = 0.0;
+                for (uint32_t m = 0; m < M; ++m) r += (double)bases[m][x] * theta[k];
+                r /= ((double)H.form_len[h.form_off + k] / 1.0E3);
+                r /= mb;
+                rpkm[k] = r;
+            }
+        }
+        for (uint32_t k = 0; k < K; ++k) {
+            printf("%s\t", ann.ev_name[e].c_str());
+            for (uint32_t m = 0; m < M; ++m) printf("%.*g\t", prec, (double)nv[m]);
+            printf("%s\t", ann.form_name[h.out_form + k].c_str());
+            if (!solve) printf("%.*g\n", prec, (double)iso[k]);
+            else
+                printf("%.*g\t%.*g\t%.*g\n", prec, theta[k], prec, rpkm[k], prec,
+                       sum_supports > 1E-5 ? ll / sum_supports : 0.0);
+        }
+    }
+    return 0;
+}
