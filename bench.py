@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the count + solve hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload C2|C1|C4] [--reads R] [--genes G]
+
+A "step" is one full pass of the device pipeline over one batch of synthetic packed reads:
+load filter -> index (radix sort by stab piece) -> count -> finalize -> EM solve.
+  value : reads/s of that pass, inputs already resident in HBM, CUDA-event timed, max over ranks
+  e2e   : the same through the C ABI with HOST (pinned) buffers: lsq_set_reads (H2D) + lsq_count +
+          lsq_solve + lsq_get_count/lsq_get_solve (D2H) inside the timed region
+  roofline : the count kernel's algorithmic bytes / its CUDA-event duration vs the measured HBM copy peak
+  cpu_baseline : the reference's own count + solve binaries (oracle/_ref) on a bounded text sample
+`--impl reference` times the reference binaries on all host cores (its own scale-out recipe:
+one process per disjoint gene range, each reading the whole read file).
+Multi-GPU: one process per GPU (torchrun), events sharded by gene rank, reads bucketed per shard,
+no collective inside the loop, one gather of results to rank 0 per step; scaling is weak.
+"""
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "reads_per_sec_counted_and_solved"
+UNIT = "reads/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C4"])
+    ap.add_argument("--reads", type=int, default=None, help="reads per GPU (default: the workload's)")
+    ap.add_argument("--genes", type=int, default=None)
+    ap.add_argument("--sample-reads", type=int, default=300000, help="reads of the CPU reference sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args, world):
+    from lesseq_b200 import synth
+    kw, R, n = synth.CONFIGS[args.workload]
+    n = args.reads or n
+    genes = args.genes or kw["n_genes"]
+    desc = {"C1": "C1: single chromosome, SE events only, 50bp MRF_SINGLE reads",
+            "C2": "C2: 24 chromosomes, all 8 event types (SE/RI/A5SS/A3SS/MXE/AFE/ALE/T3), 75bp reads",
+            "C4": "C4: junction-heavy 100bp reads over short exons, 2% junction overhangs"}[args.workload]
+    cfg = {"workload": desc, "genes": genes, "reads_per_gpu": n, "read_length": R, "read_type": "SHORT_READ",
+           "sharding": "gene-rank ranges x%d, covered regions of the whole range" % world,
+           "l2_policy": "inputs (%.1f GB packed reads per GPU) far exceed the 126 MB L2; no flush needed" % (n * 22e-9)}
+    return cfg, R, n, genes
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].startswith("Active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def write_sample(args, tmp):
+    """Annotation text + a bounded MRF text sample of the same workload for the CPU reference."""
+    from lesseq_b200 import synth
+    A, R, _ = synth.make_config(args.workload, n_genes=args.genes)
+    fp, mp, rp = os.path.join(tmp, "ev.interval"), os.path.join(tmp, "ev.map"), os.path.join(tmp, "sample.mrf")
+    A.write(fp, mp)
+    reads = synth.make_reads(A, args.sample_reads, R, 1234, device="cpu")
+    synth.reads_to_mrf(reads, rp)
+    return A, R, fp, mp, rp, reads["total_read_bases"]
+
+
+def ref_args(fp, mp, b, e, R, rp, trb=None):
+    a = ["0", "bench", "o_", "LH_GENE_TXT", fp, "UCSC_GENE2ISOFORM", mp, str(b), str(e), "MRF_SINGLE", "SHORT_READ",
+         str(R), rp]
+    return a + ([repr(trb)] if trb is not None else [])
+
+
+def cpu_reference_once(fp, mp, R, rp, trb, n_events, procs):
+    """count then solve with `procs` concurrent reference processes over disjoint gene ranges.
+    Returns wall seconds and the kind of CPU implementation used."""
+    from oracle import runner
+    if runner.ref_available() or runner.build_ref():
+        def launch(prog, args):
+            env = dict(os.environ)
+            env["LD_LIBRARY_PATH"] = os.path.join(runner.REF_DIR, "lib")
+            return subprocess.Popen([os.path.join(runner.REF_DIR, prog)] + args, env=env,
+                                    stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        kind = "reference"
+    else:
+        runner.build_oracle()
+
+        def launch(prog, args):
+            return subprocess.Popen([runner.ORACLE_BIN, prog] + args, stdout=subprocess.DEVNULL,
+                                    stderr=subprocess.DEVNULL)
+        kind = "port"
+    t0 = time.time()
+    for prog in ("count", "solve"):
+        ps = []
+        for p in range(procs):
+            b, e = (n_events * p) // procs, (n_events * (p + 1)) // procs
+            ps.append(launch(prog, ref_args(fp, mp, b, e, R, rp, trb if prog == "solve" else None)))
+        for p in ps:
+            if p.wait() != 0:
+                raise RuntimeError("CPU reference process failed")
+    return time.time() - t0, kind
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    cfg, R, n, genes = workload_config(args, world)
+    tmp = tempfile.mkdtemp(prefix="lsq_ref_")
+    try:
+        A, R, fp, mp, rp, trb = write_sample(args, tmp)
+        procs = os.cpu_count() or 1
+        n_events = len(A.ev_gene)
+        times = []
+        kind = "reference"
+        for i in range(args.warmup + args.steps):
+            dt, kind = cpu_reference_once(fp, mp, R, rp, trb, n_events, procs)
+            if i >= args.warmup:
+                times.append(dt)
+        ms = 1000.0 * sum(times) / len(times)
+        value = args.sample_reads / (ms / 1000.0)
+        sample = ("%d-read MRF text sample of the workload + the full %d-event annotation per step; count then solve, "
+                  "%d concurrent reference processes over disjoint gene ranges, each reading the whole file"
+                  % (args.sample_reads, n_events, procs))
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "i64+f64", "data": "synthetic", "config": cfg,
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": kind, "sample": sample},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "events_per_sec": n_events / (ms / 1000.0), "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from lesseq_b200 import build
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- lesseq_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if rank == 0:
+        build.build()
+    if world > 1:
+        dist.barrier()
+    from lesseq_b200 import api, synth
+    from lesseq_b200 import dist as lsd
+
+    cfg, R, n, genes = workload_config(args, world)
+    tmp = tempfile.mkdtemp(prefix="lsq_bench_")
+    A, _, _ = synth.make_config(args.workload, n_genes=args.genes)
+    fp, mp = os.path.join(tmp, "ev.interval"), os.path.join(tmp, "ev.map")
+    A.write(fp, mp)
+    # gene-rank order = bytewise lexicographic order of the event ids (count.cpp:204-215)
+    ids = [A.map_rows[2 * i][0] for i in range(len(A.ev_gene))]
+    order = sorted(range(len(ids)), key=lambda i: ids[i].encode())
+    sb, se = lsd.shard_range(len(ids), rank, world)
+    ann = api.Annotation(fp, mp, 0, api.UINT64_MAX, shard=(sb, se))
+    assert ann.n_events == se - sb
+    reads = synth.make_reads(A, n, R, 100 + rank, device="cuda", events=np.array(order[sb:se]))
+    dev_reads = api.Reads.from_torch(reads["blk_off"], reads["blk"], reads["read_cs"], reads["line_num"],
+                                     reads["chrom_names"], reads["strand_names"])
+    trb = [reads["total_read_bases"]]
+    stream = torch.cuda.current_stream()
+    ctx = api.Context(local, stream=stream.cuda_stream)
+    ctx.upload_events(ann)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def gather(cnt, sol):
+        return lsd.gather_results(cnt, sol) if world > 1 else None
+
+    # ---- device-resident pass ---------------------------------------------------------------
+    ctx.set_reads(0, "SHORT_READ", R, dev_reads)
+
+    def step_resident():
+        ctx.count()
+        ctx.solve(trb)
+        if world > 1:
+            gather(ctx.get_count(), ctx.get_solve())
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    phases = {k: 0.0 for k in ("filter_ms", "index_ms", "count_kernel_ms", "finalize_ms", "solve_ms")}
+    launches = 0
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step_resident()
+        t = ctx.timings()
+        for k in phases:
+            phases[k] += t[k]
+        launches += t["launches"]
+    ev1.record(stream)
+    barrier()
+    ms_local = ev0.elapsed_time(ev1) / args.steps
+    tsum = ctx.timings()
+    cnt, sol = ctx.get_count(), ctx.get_solve()
+
+    # ---- end to end through the C ABI with host buffers ---------------------------------------
+    pinned = {k: reads[k].cpu().pin_memory() for k in ("blk_off", "blk", "read_cs", "line_num")}
+    host_reads = api.Reads.from_torch(pinned["blk_off"], pinned["blk"], pinned["read_cs"], pinned["line_num"],
+                                      reads["chrom_names"], reads["strand_names"])
+
+    def step_e2e():
+        ctx.set_reads(0, "SHORT_READ", R, host_reads)
+        ctx.count()
+        ctx.solve(trb)
+        c, s = ctx.get_count(), ctx.get_solve()
+        if world > 1:
+            gather(c, s)
+        return c, s
+
+    for _ in range(min(args.warmup, 2)):
+        step_e2e()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        c2, s2 = step_e2e()
+    e1.record(stream)
+    barrier()
+    e2e_ms_local = e0.elapsed_time(e1) / args.steps
+    clocks = sampler.stop() if sampler else None
+    assert np.array_equal(c2["iso_count"], cnt["iso_count"]) and np.array_equal(s2["theta"], sol["theta"])
+
+    red = torch.tensor([ms_local, e2e_ms_local], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(red[0]), float(red[1])
+    total_reads = n * world
+    n_events_total = len(ids)
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        ck_ms = phases["count_kernel_ms"] / args.steps
+        achieved = tsum["count_bytes"] / (ck_ms * 1e-3) / 1e9 if ck_ms > 0 else 0.0
+        d2h = int(sum(v.nbytes for v in cnt.values()) + sum(v.nbytes for v in sol.values()))
+        line = {
+            "metric": METRIC, "value": total_reads / (ms / 1000.0), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "i32+f64", "data": "synthetic", "config": cfg,
+            "clocks": clocks,
+            "e2e": {"value": total_reads / (e2e_ms / 1000.0), "unit": UNIT,
+                    "h2d_bytes_per_step": int(host_reads.host_bytes()), "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "lsq_count_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "bytes_per_launch": int(tsum["count_bytes"]), "ms_per_launch": ck_ms},
+            "events_per_sec": n_events_total / (ms / 1000.0),
+            "events": n_events_total,
+            "phases_ms_per_step_rank0": {k: v / args.steps for k, v in phases.items()},
+            "reads_kept_rank0": int(tsum["reads_kept"]), "valid_pairs_rank0": int(tsum["pairs_valid"]),
+            "em_iters_mean_rank0": float(sol["iters"].mean()),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                A2, R2, fp2, mp2, rp2, trb2 = write_sample(args, tmp)
+                dt, kind = cpu_reference_once(fp2, mp2, R2, rp2, trb2, len(A2.ev_gene), 1)
+                line["cpu_baseline"] = {
+                    "value": args.sample_reads / dt, "unit": UNIT, "cores": 1, "kind": kind,
+                    "sample": "%d-read MRF text sample of the workload + the full %d-event annotation: reference "
+                              "count then solve, one single-threaded process each, %.1f s wall"
+                              % (args.sample_reads, len(A2.ev_gene), dt)}
+            except Exception as ex:  # the oracle always exists; report why it could not run
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %s" % ex}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    shutil.rmtree(tmp, ignore_errors=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

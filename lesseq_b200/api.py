@@ -1,0 +1,279 @@
+"""Python mirror of the drop-in boundary (include/lesseq_b200.h).
+
+The reference has no library API -- only two programs (count/count.cpp, solve/solve.cpp).  The
+classes below wrap the C ABI one-to-one; ``count_main`` / ``solve_main`` take the reference's
+positional argument lists.  numpy holds host buffers, torch (if given CUDA tensors) device ones.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from . import _lib
+from ._lib import LsqError, READ_TYPES, check  # noqa: F401
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+UINT64_MAX = 2 ** 64 - 1
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Annotation:
+    """Event model built from LH_GENE_TXT + UCSC_GENE2ISOFORM files (count/count.cpp:136-258)."""
+
+    def __init__(self, forms_path, map_path, begin=0, end=UINT64_MAX, shard=(0, UINT64_MAX)):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        check(self._lib.lsqh_annotation_load(str(forms_path).encode(), str(map_path).encode(), begin, end,
+                                             shard[0], shard[1], C.byref(self._h)))
+        self.tables = _lib.EventTables()
+        check(self._lib.lsqh_annotation_tables(self._h, C.byref(self.tables)))
+        self.n_events = self.tables.n_events
+        self.n_forms = self.tables.n_forms
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._lib.lsqh_annotation_free(self._h)
+            self._h = None
+
+    def event_names(self):
+        return [self._lib.lsqh_event_name(self._h, e).decode() for e in range(self.n_events)]
+
+    def form_names(self):
+        return [self._lib.lsqh_form_name(self._h, f).decode() for f in range(self.n_forms)]
+
+    def form_lengths(self):
+        return np.array([self._lib.lsqh_form_length(self._h, f) for f in range(self.n_forms)], dtype=np.uint64)
+
+    def form_offsets(self):
+        return np.ctypeslib.as_array(self.tables.ev_form_off, shape=(self.n_events + 1,)).copy()
+
+    def array(self, name, n):
+        return np.ctypeslib.as_array(getattr(self.tables, name), shape=(n,)).copy()
+
+
+class ArrayAnnotation:
+    """Event model given directly as arrays (no text front end); same `tables` attribute as
+    Annotation.  Used for solve-only workloads (BASELINE config 5) and tests."""
+
+    def __init__(self, ev_chrom, ev_strand, ev_gs, ev_ge, ev_seg_off, ev_form_off, seg_start, seg_end,
+                 form_seg_off, form_seg_idx, cov_off, cov_start, cov_end, chrom_names, strand_names, ev_names=None):
+        u32 = lambda a: np.ascontiguousarray(a, dtype=np.uint32)  # noqa: E731
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)  # noqa: E731
+        E = len(ev_gs)
+        if ev_names is None:
+            ev_names = ["e%d" % i for i in range(E)]
+        pool = "".join(ev_names).encode()
+        name_off = np.zeros(E + 1, dtype=np.uint32)
+        name_off[1:] = np.cumsum([len(n.encode()) for n in ev_names])
+        self._a = dict(ev_chrom=u32(ev_chrom), ev_strand=u32(ev_strand), ev_gs=i32(ev_gs), ev_ge=i32(ev_ge),
+                       ev_seg_off=u32(ev_seg_off), ev_form_off=u32(ev_form_off), ev_name_off=name_off,
+                       seg_start=i32(seg_start), seg_end=i32(seg_end), form_seg_off=u32(form_seg_off),
+                       form_seg_idx=u32(form_seg_idx), cov_off=u32(cov_off), cov_start=i32(cov_start),
+                       cov_end=i32(cov_end))
+        self._pool = C.create_string_buffer(pool, max(len(pool), 1))
+        self._cn = (C.c_char_p * max(len(chrom_names), 1))(*[s.encode() for s in chrom_names])
+        self._sn = (C.c_char_p * max(len(strand_names), 1))(*[s.encode() for s in strand_names])
+        t = _lib.EventTables()
+        t.n_events, t.n_forms, t.n_segments = E, len(form_seg_off) - 1, len(seg_start)
+        t.n_chroms, t.n_strands = len(chrom_names), len(strand_names)
+        for k, a in self._a.items():
+            setattr(t, k, a.ctypes.data_as(dict(_lib.EventTables._fields_)[k]))
+        t.ev_names = C.cast(self._pool, C.c_void_p)
+        t.chrom_names = C.cast(self._cn, _lib.c_strp)
+        t.strand_names = C.cast(self._sn, _lib.c_strp)
+        self.tables = t
+        self.n_events, self.n_forms = E, t.n_forms
+        self.names = ev_names
+
+    def form_offsets(self):
+        return self._a["ev_form_off"].copy()
+
+
+class Reads:
+    """Packed MRF_SINGLE reads (lsq_packed_reads).  Build with ``from_mrf``, ``from_numpy`` or
+    ``from_torch`` (CUDA tensors are passed by device pointer without a copy)."""
+
+    def __init__(self):
+        self.view = _lib.PackedReads()
+        self._keep = []
+        self._h = None
+        self._lib = _lib.load()
+
+    @classmethod
+    def from_mrf(cls, path):
+        self = cls()
+        self._h = C.c_void_p()
+        check(self._lib.lsqh_mrf_parse(str(path).encode(), C.byref(self._h)))
+        check(self._lib.lsqh_reads_view(self._h, C.byref(self.view)))
+        return self
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._lib.lsqh_reads_free(self._h)
+            self._h = None
+
+    def _names(self, chrom_names, strand_names):
+        cn = (C.c_char_p * len(chrom_names))(*[s.encode() for s in chrom_names])
+        sn = (C.c_char_p * len(strand_names))(*[s.encode() for s in strand_names])
+        self._keep += [cn, sn]
+        self.view.n_chrom_names = len(chrom_names)
+        self.view.n_strand_names = len(strand_names)
+        self.view.chrom_names = C.cast(cn, _lib.c_strp)
+        self.view.strand_names = C.cast(sn, _lib.c_strp)
+
+    @classmethod
+    def from_numpy(cls, blk_off, blk, read_cs, line_num, chrom_names, strand_names, blk_cs=None):
+        self = cls()
+        blk_off = np.ascontiguousarray(blk_off, dtype=np.uint32)
+        blk = np.ascontiguousarray(blk, dtype=np.int32).reshape(-1)
+        read_cs = np.ascontiguousarray(read_cs, dtype=np.uint32)
+        line_num = np.ascontiguousarray(line_num, dtype=np.uint32)
+        self._keep += [blk_off, blk, read_cs, line_num]
+        v = self.view
+        v.n_reads = len(read_cs)
+        v.n_blocks = len(blk) // 2
+        v.blk_off, v.blk, v.read_cs, v.line_num = _ptr(blk_off), _ptr(blk), _ptr(read_cs), _ptr(line_num)
+        if blk_cs is not None:
+            blk_cs = np.ascontiguousarray(blk_cs, dtype=np.uint32)
+            self._keep.append(blk_cs)
+            v.blk_cs = _ptr(blk_cs)
+        v.on_device = 0
+        self._names(chrom_names, strand_names)
+        return self
+
+    @classmethod
+    def from_torch(cls, blk_off, blk, read_cs, line_num, chrom_names, strand_names, blk_cs=None):
+        """Tensors must be contiguous int32 (bit patterns of the uint32 fields); CUDA tensors are
+        borrowed (on_device=1), CPU tensors (pinned or not) are host buffers."""
+        self = cls()
+        ts = [blk_off, blk, read_cs, line_num] + ([blk_cs] if blk_cs is not None else [])
+        dev = blk_off.is_cuda
+        for t in ts:
+            assert t.is_contiguous() and t.element_size() == 4 and t.is_cuda == dev
+        self._keep += ts
+        v = self.view
+        v.n_reads = read_cs.numel()
+        v.n_blocks = blk.numel() // 2
+        v.blk_off, v.blk, v.read_cs, v.line_num = (blk_off.data_ptr(), blk.data_ptr(), read_cs.data_ptr(),
+                                                   line_num.data_ptr())
+        if blk_cs is not None:
+            v.blk_cs = blk_cs.data_ptr()
+        v.on_device = 1 if dev else 0
+        self._names(chrom_names, strand_names)
+        return self
+
+    @property
+    def n_reads(self):
+        return int(self.view.n_reads)
+
+    @property
+    def n_blocks(self):
+        return int(self.view.n_blocks)
+
+    def host_bytes(self):
+        """Bytes lsq_set_reads copies host->device for this read set."""
+        n, nb = self.n_reads, self.n_blocks
+        return (n + 1) * 4 + nb * 8 + n * 4 + n * 4
+
+
+class Context:
+    """One device context (lsq_ctx).  Call order: upload_events -> set_reads* -> count -> solve."""
+
+    def __init__(self, device=0, stream=None):
+        self._lib = _lib.load()
+        self._c = C.c_void_p()
+        check(self._lib.lsq_ctx_create(device, C.byref(self._c)))
+        self.E = self.F = self.M = 0
+        if stream is not None:
+            check(self._lib.lsq_ctx_set_stream(self._c, C.c_void_p(stream)))
+
+    def close(self):
+        if getattr(self, "_c", None):
+            self._lib.lsq_ctx_destroy(self._c)
+            self._c = None
+
+    __del__ = close
+
+    def upload_events(self, ann):
+        t = ann.tables if isinstance(ann, Annotation) else ann
+        check(self._lib.lsq_upload_events(self._c, C.byref(t)))
+        self.E, self.F, self.M = t.n_events, t.n_forms, 0
+        self._ann = ann
+
+    def set_reads(self, m, read_type, read_length, reads):
+        rt = READ_TYPES[read_type] if isinstance(read_type, str) else read_type
+        check(self._lib.lsq_set_reads(self._c, m, rt, read_length, C.byref(reads.view)))
+        self.M = max(self.M, m + 1)
+        self._reads = getattr(self, "_reads", {})
+        self._reads[m] = reads
+
+    def set_classes(self, m, read_type, read_length, cls_off, cls_mask, cls_cnt, bases):
+        rt = READ_TYPES[read_type] if isinstance(read_type, str) else read_type
+        a = [np.ascontiguousarray(x, dtype=np.uint64) for x in (cls_off, cls_mask, cls_cnt, bases)]
+        check(self._lib.lsq_set_classes(self._c, m, rt, read_length, _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(a[3])))
+        self.M = max(self.M, m + 1)
+
+    def count(self):
+        check(self._lib.lsq_count(self._c))
+
+    def get_count(self):
+        nv = np.zeros((self.M, self.E), dtype=np.uint64)
+        bs = np.zeros((self.M, self.E), dtype=np.uint64)
+        iso = np.zeros(self.F, dtype=np.uint64)
+        out = _lib.CountOut(_ptr(nv), _ptr(bs), _ptr(iso))
+        check(self._lib.lsq_get_count(self._c, C.byref(out)))
+        return {"n_valid": nv, "bases": bs, "iso_count": iso}
+
+    def get_classes(self, m):
+        off = np.zeros(self.E + 1, dtype=np.uint64)
+        check(self._lib.lsq_get_classes(self._c, m, _ptr(off), None, None))
+        n = int(off[-1])
+        mask = np.zeros(max(n, 1), dtype=np.uint64)
+        cnt = np.zeros(max(n, 1), dtype=np.uint64)
+        check(self._lib.lsq_get_classes(self._c, m, _ptr(off), _ptr(mask), _ptr(cnt)))
+        return off, mask[:n], cnt[:n]
+
+    def solve(self, total_read_bases):
+        trb = np.ascontiguousarray(total_read_bases, dtype=np.float64)
+        check(self._lib.lsq_solve(self._c, trb.ctypes.data_as(_lib.c_f64p), len(trb)))
+
+    def get_solve(self):
+        th = np.zeros(self.F)
+        rp = np.zeros(self.F)
+        ll = np.zeros(self.E)
+        lp = np.zeros(self.E)
+        it = np.zeros(self.E, dtype=np.uint32)
+        out = _lib.SolveOut(_ptr(th), _ptr(rp), _ptr(ll), _ptr(lp), _ptr(it), None)
+        check(self._lib.lsq_get_solve(self._c, C.byref(out)))
+        return {"theta": th, "rpkm": rp, "loglik": ll, "ll_per_read": lp, "iters": it}
+
+    def sync(self):
+        check(self._lib.lsq_ctx_sync(self._c))
+
+    def timings(self):
+        t = _lib.Timings()
+        check(self._lib.lsq_get_timings(self._c, C.byref(t)))
+        return {k: getattr(t, k) for k, _ in _lib.Timings._fields_}
+
+
+def ars_length(read_type, read_length, seg_len):
+    rt = READ_TYPES[read_type] if isinstance(read_type, str) else read_type
+    a = np.ascontiguousarray(seg_len, dtype=np.uint64)
+    return int(_lib.load().lsq_ars_length(rt, read_length, a.ctypes.data_as(_lib.c_u64p), len(a)))
+
+
+def run_program(prog, args, precision=None, timeout=None):
+    """Run the drop-in `count` / `solve` executable (lesseq_b200/bin) with the reference's
+    positional arguments; returns (returncode, stdout, stderr)."""
+    exe = os.path.join(PKG, "bin", prog)
+    if not os.path.exists(exe):
+        raise ImportError("lesseq_b200: %s not built -- run `python -m lesseq_b200.build`" % exe)
+    env = dict(os.environ)
+    if precision is not None:
+        env["LSQ_PRECISION"] = str(precision)
+    p = subprocess.run([exe] + [str(a) for a in args], env=env, capture_output=True, text=True, timeout=timeout)
+    return p.returncode, p.stdout, p.stderr

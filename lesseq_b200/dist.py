@@ -1,0 +1,63 @@
+"""Gene-range sharding over torch.distributed (one process per GPU).
+
+The reference's only parallelism is "run N processes with different gene_begin_idx/gene_end_idx
+and concatenate the outputs" (count/count.cpp:113-114, 202-215).  Here rank r of P takes the
+contiguous slice [b + r*n/P, b + (r+1)*n/P) of the selected gene ranks; every rank filters reads
+with the covered regions of the WHOLE selection so results do not depend on P.
+No collective runs inside the loop; per-event results are gathered to rank 0 once at the end
+(NCCL for CUDA tensors, gloo for CPU tensors in the tests).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n, rank, world):
+    """Slice of n gene ranks owned by `rank` (the reference's begin/end mechanism, end exclusive)."""
+    return (n * rank) // world, (n * (rank + 1)) // world
+
+
+def gather_rows(local, root=0):
+    """Concatenate per-rank 1-D/2-D numpy arrays (rows = events or forms, rank order = gene-rank
+    order) on `root`.  Returns the concatenation on root, None elsewhere.  Variable lengths are
+    handled by a size exchange followed by one padded all_gather per array."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return local
+    world, rank = dist.get_world_size(), dist.get_rank()
+    use_cuda = dist.get_backend() == "nccl"
+    dev = torch.device("cuda", torch.cuda.current_device()) if use_cuda else torch.device("cpu")
+    a = np.ascontiguousarray(local)
+    flat = a.reshape(a.shape[0], -1) if a.ndim > 1 else a.reshape(-1, 1)
+    width = flat.shape[1]
+    sizes = torch.zeros(world, dtype=torch.int64, device=dev)
+    sizes[rank] = flat.shape[0]
+    dist.all_reduce(sizes)
+    maxn = int(sizes.max().item())
+    raw = torch.from_numpy(flat.view(np.uint8).reshape(flat.shape[0], -1).copy())
+    pad = torch.zeros((maxn, raw.shape[1]), dtype=torch.uint8)
+    pad[: raw.shape[0]] = raw
+    pad = pad.to(dev)
+    out = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad)
+    if rank != root:
+        return None
+    parts = [o[: int(sizes[r].item())].cpu().numpy() for r, o in enumerate(out)]
+    cat = np.concatenate(parts, axis=0).view(a.dtype).reshape(-1, width)
+    if a.ndim == 1:
+        return cat.reshape(-1)
+    return cat.reshape((-1,) + a.shape[1:])
+
+
+def gather_results(count, solve, root=0):
+    """Gather the dicts returned by Context.get_count / get_solve.  n_valid and bases are
+    [M, E_local]: they are gathered along the event axis."""
+    out = {}
+    for k, v in count.items():
+        if v.ndim == 2:
+            g = gather_rows(np.ascontiguousarray(v.T), root)
+            out[k] = None if g is None else np.ascontiguousarray(g.T)
+        else:
+            out[k] = gather_rows(v, root)
+    for k, v in (solve or {}).items():
+        out[k] = gather_rows(v, root)
+    return out

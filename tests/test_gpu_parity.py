@@ -1,0 +1,200 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI
+(liblesseq_b200.so) -- either via the drop-in count/solve executables or via the ctypes
+mirror -- and is compared with (a) the golden outputs of the reference's own binaries and
+(b) the CPU oracle on the same seeded inputs."""
+import os
+
+import numpy as np
+import pytest
+
+import fuzzgen
+import golden_util
+from parity_util import num_close, tables_match
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def api():
+    from lesseq_b200 import build
+    build.build()
+    from lesseq_b200 import api as _api
+    return _api
+
+
+GOLDEN = golden_util.all_cases()
+
+
+@pytest.mark.parametrize("case", GOLDEN, ids=[c["name"] for c in GOLDEN])
+def test_cli_matches_reference_golden(case, api, tmp_path):
+    ca, sa = golden_util.materialise(case, str(tmp_path))
+    exp = case["expect"]
+    for prog, args in (("count", ca), ("solve", sa)):
+        for prec in (17, 6):
+            rc, out, err = api.run_program(prog, args, precision=prec)
+            assert rc == exp["%s_rc" % prog], err
+            bad = tables_match(exp["%s%d" % (prog, prec)], out, prog == "solve", rel6=(prec == 6))
+            assert bad is None, "%s %s prec=%d: %s" % (case["name"], prog, prec, bad)
+
+
+def _oracle_dump(oracle_bin, prog, args, path):
+    rc, out, err = oracle_bin.run_oracle(prog, args, dump=path)
+    assert rc == 0, err
+    classes, bases, iters = {}, {}, {}
+    for line in open(path):
+        f = line.rstrip("\n").split("\t")
+        if f[0] == "C":
+            classes.setdefault((f[1], int(f[2])), {})[int(f[3])] = int(f[4])
+        elif f[0] == "B":
+            bases[(f[1], int(f[2]))] = (int(float(f[3])), int(float(f[4])))
+        elif f[0] == "E":
+            iters[f[1]] = int(f[3])
+    return out, classes, bases, iters
+
+
+def test_abi_matches_oracle_on_fuzz(api, oracle_bin, tmp_path):
+    """Per-event n_valid, bases, class histogram (bit-exact), EM iteration count, theta, rpkm and
+    log-likelihood (1e-9) through the ctypes mirror of the C ABI, one context reused."""
+    ctx = api.Context(0)
+    checked = 0
+    for seed in range(9000, 9150):
+        case = fuzzgen.make_case(seed)
+        d = tmp_path / ("s%d" % seed)
+        d.mkdir()
+        ca, sa = fuzzgen.write_case(case, str(d))
+        rc, _, _ = oracle_bin.run_oracle("count", ca)
+        if rc != 0:
+            continue
+        out, classes, bases, iters = _oracle_dump(oracle_bin, "solve", sa, str(d / "dump.txt"))
+        ann = api.Annotation(ca[4], ca[6], case["begin"], case["end"])
+        if ann.n_events == 0:
+            continue
+        ctx.upload_events(ann)
+        M = len(case["sets"])
+        for m, s in enumerate(case["sets"]):
+            ctx.set_reads(m, s["type"], s["read_length"], api.Reads.from_mrf(d / ("r%d.mrf" % m)))
+        ctx.count()
+        cnt = ctx.get_count()
+        ctx.solve([s["total_read_bases"] for s in case["sets"]])
+        sol = ctx.get_solve()
+        names = ann.event_names()
+        foff = ann.form_offsets()
+        rows = [r for r in out.splitlines()]
+        for m in range(M):
+            off, mask, c = ctx.get_classes(m)
+            for e, g in enumerate(names):
+                got = {int(mask[i]): int(c[i]) for i in range(int(off[e]), int(off[e + 1]))}
+                assert got == classes.get((g, m), {}), (seed, g, m)
+                assert (int(cnt["n_valid"][m, e]), int(cnt["bases"][m, e])) == bases[(g, m)], (seed, g, m)
+        for e, g in enumerate(names):
+            assert int(sol["iters"][e]) == iters[g], (seed, g)
+            for f in range(int(foff[e]), int(foff[e + 1])):
+                cols = rows[f].split("\t")
+                assert num_close(float(cols[-3]), float(sol["theta"][f])), (seed, g, cols, sol["theta"][f])
+                assert num_close(float(cols[-2]), float(sol["rpkm"][f])), (seed, g)
+                assert num_close(float(cols[-1]), float(sol["ll_per_read"][e])), (seed, g)
+        checked += 1
+    ctx.close()
+    assert checked > 100
+
+
+def _synth_case(api, tmp_path, name, n_genes, n_reads, seed, **kw):
+    from lesseq_b200 import synth
+    A, R, _ = synth.make_config(name, n_genes=n_genes)
+    fp, mp, rp = str(tmp_path / "ev.interval"), str(tmp_path / "ev.map"), str(tmp_path / "r.mrf")
+    A.write(fp, mp)
+    reads = synth.make_reads(A, n_reads, R, seed, device="cpu", **kw)
+    synth.reads_to_mrf(reads, rp)
+    head = ["0", "p", str(tmp_path / "o_"), "LH_GENE_TXT", fp, "UCSC_GENE2ISOFORM", mp, "0", "100000000"]
+    return A, R, reads, head, rp
+
+
+@pytest.mark.parametrize("name,n_genes,n_reads,kw", [
+    ("C1", 500, 200000, {}),
+    ("C2", 400, 200000, {}),
+    ("C4", 400, 200000, {"overhang_frac": 0.02}),
+])
+def test_synthetic_configs_match_oracle(api, oracle_bin, tmp_path, name, n_genes, n_reads, kw):
+    """BASELINE-shaped inputs at a size the oracle finishes in seconds, through the drop-in
+    executables (text in, table out), 17 digits."""
+    A, R, reads, head, rp = _synth_case(api, tmp_path, name, n_genes, n_reads, 11, **kw)
+    ca = head + ["MRF_SINGLE", "SHORT_READ", str(R), rp]
+    sa = ca + [repr(reads["total_read_bases"])]
+    for prog, args in (("count", ca), ("solve", sa)):
+        rc1, o1, e1 = oracle_bin.run_oracle(prog, args)
+        rc2, o2, e2 = api.run_program(prog, args, precision=17)
+        assert rc1 == 0 and rc2 == 0, e2
+        assert len(o1.splitlines()) == 2 * len(A.ev_gene)
+        bad = tables_match(o1, o2, prog == "solve")
+        assert bad is None, "%s %s: %s" % (name, prog, bad)
+
+
+def test_device_resident_reads_and_properties(api, tmp_path):
+    """Size-independent properties on a larger device-generated input: classes sum to n_valid,
+    per-form tallies follow from the classes, shuffling the reads changes nothing, counting twice
+    is idempotent, and a two-shard run over the same covered regions concatenates to the full run."""
+    import torch
+    from lesseq_b200 import synth
+    A, R, _ = synth.make_config("C2", n_genes=2000)
+    fp, mp = str(tmp_path / "ev.interval"), str(tmp_path / "ev.map")
+    A.write(fp, mp)
+    n = 4_000_000
+    reads = synth.make_reads(A, n, R, 5, device="cuda")
+
+    def run(ann, rd):
+        ctx = api.Context(0)
+        ctx.upload_events(ann)
+        ctx.set_reads(0, "SHORT_READ", R, api.Reads.from_torch(rd["blk_off"], rd["blk"], rd["read_cs"],
+                                                               rd["line_num"], rd["chrom_names"], rd["strand_names"]))
+        ctx.count()
+        c1 = ctx.get_count()
+        ctx.count()
+        c2 = ctx.get_count()
+        for k in c1:
+            assert np.array_equal(c1[k], c2[k]), "count is not idempotent (%s)" % k
+        off, mask, cnt = ctx.get_classes(0)
+        ctx.solve([rd["total_read_bases"]])
+        sol = ctx.get_solve()
+        t = ctx.timings()
+        ctx.close()
+        return c1, (off, mask, cnt), sol, t
+
+    ann = api.Annotation(fp, mp)
+    c, (off, mask, cnt), sol, t = run(ann, reads)
+    assert t["reads_in"] == n and 0 < t["reads_kept"] <= n
+    foff = ann.form_offsets()
+    for e in range(ann.n_events):
+        sl = slice(int(off[e]), int(off[e + 1]))
+        assert int(cnt[sl].sum()) == int(c["n_valid"][0, e])
+        for k in range(int(foff[e + 1] - foff[e])):
+            assert int(cnt[sl][(mask[sl] >> np.uint64(k)) & np.uint64(1) == 1].sum()) == int(c["iso_count"][foff[e] + k])
+    assert int(c["n_valid"].sum()) > n // 2
+    th = sol["theta"]
+    for e in range(ann.n_events):
+        assert abs(th[foff[e]:foff[e + 1]].sum() - 1.0) < 1e-9
+    # permutation invariance (host-side shuffle of the packed reads)
+    perm = torch.randperm(n, device="cuda")
+    nblk = (reads["blk_off"][1:] - reads["blk_off"][:-1]).to(torch.int64)
+    off2 = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
+    off2[1:] = torch.cumsum(nblk[perm], 0)
+    idx = torch.repeat_interleave(reads["blk_off"][:-1].to(torch.int64)[perm] - off2[:-1], nblk[perm]) + \
+        torch.arange(int(off2[-1]), device="cuda")
+    shuffled = dict(reads)
+    shuffled["blk_off"] = off2.to(torch.int32).contiguous()
+    shuffled["blk"] = reads["blk"].view(-1, 2)[idx].contiguous().view(-1)
+    shuffled["read_cs"] = reads["read_cs"][perm].contiguous()
+    shuffled["line_num"] = reads["line_num"][perm].contiguous()
+    c3, cl3, _, _ = run(ann, shuffled)
+    for k in c:
+        assert np.array_equal(c[k], c3[k]), "shuffling reads changed %s" % k
+    # shards: covered regions of the whole range, events of each half
+    half = ann.n_events // 2
+    parts = []
+    for sh in ((0, half), (half, ann.n_events)):
+        a2 = api.Annotation(fp, mp, shard=sh)
+        parts.append(run(a2, reads)[0])
+    for k in ("n_valid", "bases"):
+        assert np.array_equal(np.concatenate([p[k] for p in parts], axis=1), c[k]), k
+    assert np.array_equal(np.concatenate([p["iso_count"] for p in parts]), c["iso_count"])

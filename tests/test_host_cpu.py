@@ -1,0 +1,193 @@
+"""CPU-side tests of the product: the C-ABI library loads and exports every declared symbol,
+fails loudly without a GPU, and the host front end + device functions (replayed on the CPU by
+tests/emul) agree with the oracle."""
+import ctypes as C
+import math
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import fuzzgen
+import golden_util
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMUL = os.path.join(ROOT, "tests", "emul", "_build", "emul")
+
+
+@pytest.fixture(scope="session")
+def built_lib():
+    from lesseq_b200 import build, _lib
+    build.build()
+    return _lib.load()
+
+
+@pytest.fixture(scope="session")
+def emul_bin():
+    subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "emul"), "-s"], check=True)
+    return EMUL
+
+
+def test_library_exports_every_header_symbol(built_lib):
+    hdr = open(os.path.join(ROOT, "include", "lesseq_b200.h")).read()
+    declared = set(re.findall(r"\b(lsqh?_[a-z_0-9]+)\s*\(", hdr))
+    from lesseq_b200 import _lib
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    for name in declared:
+        assert hasattr(built_lib, name), name
+
+
+def test_no_cpu_fallback(built_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    ctx = C.c_void_p()
+    rc = built_lib.lsq_ctx_create(0, C.byref(ctx))
+    assert rc == -2
+    assert b"no CPU fallback" in built_lib.lsq_last_error()
+    from lesseq_b200 import api
+    with pytest.raises(api.LsqError):
+        api.Context(0)
+
+
+def test_ars_closed_form_against_enumeration(built_lib):
+    """ARS length (accessible_read_starts.h:48-89, 221-274) against a direct enumeration of the
+    reference's per-segment interval arithmetic."""
+    from lesseq_b200 import api
+    rng = np.random.default_rng(0)
+
+    def brute(short, R, lens):
+        T = sum(lens)
+        total, c = 0, 0
+        for L in lens:
+            c += L
+            if c + R > T:
+                return total + max(L + 1 - (c + R - T), 0)
+            if short:
+                pts = set(range(0, max(L - R + 1, 0))) | (set(range(max(L - R, 0), L + 1)) if L > 0 else set())
+                total += len(pts)
+            else:
+                total += L
+        return total
+
+    for _ in range(500):
+        n = int(rng.integers(1, 6))
+        lens = [int(x) for x in rng.integers(1, 120, n)]
+        R = int(rng.integers(0, 200))
+        assert api.ars_length("SHORT_READ", R, lens) == brute(True, R, lens)
+        assert api.ars_length("MEDIUM_READ", R, lens) == brute(False, R, lens)
+    assert api.ars_length("SHORT_READ", 50, [100, 100, 100]) == 253
+    assert api.ars_length("MEDIUM_READ", 50, [100, 100, 100]) == 251
+
+
+def test_annotation_front_end_a1(built_lib, tmp_path):
+    from lesseq_b200 import api
+    case = [c for c in golden_util.load("seed.json") if c["name"] == "A1_se_basics"][0]
+    ca, _ = golden_util.materialise(case, str(tmp_path))
+    ann = api.Annotation(ca[4], ca[6], 0, 100)
+    assert ann.n_events == 1 and ann.n_forms == 2
+    assert ann.event_names() == ["1"] and ann.form_names() == ["E1|2|1", "E1|2|2"]
+    assert list(ann.array("seg_start", 3)) == [100, 300, 600]
+    assert list(ann.array("seg_end", 3)) == [200, 400, 700]
+    assert list(ann.form_lengths()) == [300, 200]
+    assert list(ann.array("cov_start", 3)) == [100, 300, 600]
+
+
+def test_mrf_parser_errors_and_packing(built_lib, tmp_path):
+    from lesseq_b200 import api
+    p = tmp_path / "bad.mrf"
+    p.write_text("AlignmentBlocks\nchr1:+:10:x20:1:11\n")
+    with pytest.raises(api.LsqError) as ei:
+        api.Reads.from_mrf(p)
+    assert ei.value.code == -6
+    p.write_text("AlignmentBlocks\n# c\nchr1:+:10:20:1:11,chr2:-:5:9:12:16\nAlignmentBlocks\nchr1:+:1:5\nchr1:+:7:9")
+    r = api.Reads.from_mrf(p)
+    assert r.n_reads == 2 and r.n_blocks == 3  # the unterminated last line is dropped
+    ln = np.ctypeslib.as_array(C.cast(r.view.line_num, C.POINTER(C.c_uint32)), shape=(2,))
+    assert list(ln) == [2, 4]  # comment and header lines advance the read number
+    cs = np.ctypeslib.as_array(C.cast(r.view.read_cs, C.POINTER(C.c_uint32)), shape=(2,))
+    assert cs[0] & 0x80000000 and not (cs[1] & 0x80000000)
+
+
+def _close(a, b, solve):
+    la, lb = a.splitlines(), b.splitlines()
+    if len(la) != len(lb):
+        return False
+    for x, y in zip(la, lb):
+        fx, fy = x.split("\t"), y.split("\t")
+        if len(fx) != len(fy):
+            return False
+        for u, v in zip(fx, fy):
+            if u == v:
+                continue
+            if not solve:
+                return False
+            du, dv = float(u), float(v)
+            if math.isnan(du) and math.isnan(dv):
+                continue
+            if abs(du - dv) > 1e-9 * max(abs(du), abs(dv)):
+                return False
+    return True
+
+
+def _run_emul(emul, prog, args):
+    env = dict(os.environ)
+    env["LSQ_PRECISION"] = "17"
+    p = subprocess.run([emul, prog] + [str(a) for a in args], env=env, capture_output=True, text=True)
+    return p.returncode, p.stdout
+
+
+def test_device_functions_replayed_on_cpu_match_golden(emul_bin, tmp_path):
+    """Host front end + table layout + per-read/per-pair device functions vs the reference
+    binaries' golden outputs: counts bit-exact, solve columns within 1e-9 relative."""
+    n = 0
+    for case in golden_util.all_cases():
+        if case["name"].startswith("A6"):
+            continue
+        d = tmp_path / case["name"]
+        d.mkdir()
+        ca, sa = golden_util.materialise(case, str(d))
+        exp = case["expect"]
+        for prog, args in (("count", ca), ("solve", sa)):
+            if exp["%s_rc" % prog] != 0:
+                continue
+            rc, out = _run_emul(emul_bin, prog, args)
+            assert rc == 0
+            assert _close(exp["%s17" % prog], out, prog == "solve"), (case["name"], prog)
+            n += 1
+    assert n > 150
+
+
+def test_device_functions_replayed_on_cpu_match_oracle_fuzz(emul_bin, oracle_bin, tmp_path):
+    for seed in range(7000, 7120):
+        case = fuzzgen.make_case(seed)
+        d = tmp_path / ("s%d" % seed)
+        d.mkdir()
+        ca, sa = fuzzgen.write_case(case, str(d))
+        for prog, args in (("count", ca), ("solve", sa)):
+            rc1, o1, _ = oracle_bin.run_oracle(prog, args)
+            rc2, o2 = _run_emul(emul_bin, prog, args)
+            assert rc1 == rc2 and _close(o1, o2, prog == "solve"), (seed, prog)
+
+
+def test_cli_argument_errors(built_lib, tmp_path):
+    """Exit codes of the drop-in programs for malformed command lines (count.cpp:20-38, 95-129)."""
+    from lesseq_b200 import api
+    rc, out, err = api.run_program("count", ["0", "p", "o"])
+    assert rc == 1 and out == "" and "Usage" in err
+    case = golden_util.load("seed.json")[0]
+    ca, sa = golden_util.materialise(case, str(tmp_path))
+    bad = list(ca)
+    bad[7] = "x"
+    assert api.run_program("count", bad)[0] == 1
+    bad = list(ca)
+    bad[3] = "UCSC_GFF"
+    rc, out, err = api.run_program("count", bad)
+    assert rc == 1 and "Unknown file format error: UCSC_GFF" in err
+    bad = list(ca)
+    bad[4] = str(tmp_path / "missing")
+    assert api.run_program("count", bad)[0] == 134
+    rc, out, err = api.run_program("solve", sa[:-1])
+    assert rc == 1 and "Usage" in err
