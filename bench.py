@@ -317,7 +317,8 @@ def run_ours(args):
             "events": n_events_total,
             "phases_ms_per_step_rank0": {k: v / args.steps for k, v in phases.items()},
             "reads_kept_rank0": int(tsum["reads_kept"]), "valid_pairs_rank0": int(tsum["pairs_valid"]),
-            "em_iters_mean_rank0": float(sol["iters"].mean()),
+            "em_iters_mean_rank0": float(sol["iters"].mean()), "em_iters_max_rank0": int(sol["iters"].max()),
+            "em_iters_p99_rank0": float(np.percentile(sol["iters"], 99)),
         }
         if world == 1 and not args.no_cpu_baseline:
             try:

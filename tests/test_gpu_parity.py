@@ -24,11 +24,13 @@ def api():
     return _api
 
 
-GOLDEN = golden_util.all_cases()
+SEED_CASES = golden_util.load("seed.json")
+FUZZ_CASES = golden_util.load("fuzz.json")
 
 
-@pytest.mark.parametrize("case", GOLDEN, ids=[c["name"] for c in GOLDEN])
+@pytest.mark.parametrize("case", SEED_CASES, ids=[c["name"] for c in SEED_CASES])
 def test_cli_matches_reference_golden(case, api, tmp_path):
+    """Drop-in executables (text in, table out) against the reference binaries' outputs."""
     ca, sa = golden_util.materialise(case, str(tmp_path))
     exp = case["expect"]
     for prog, args in (("count", ca), ("solve", sa)):
@@ -37,6 +39,51 @@ def test_cli_matches_reference_golden(case, api, tmp_path):
             assert rc == exp["%s_rc" % prog], err
             bad = tables_match(exp["%s%d" % (prog, prec)], out, prog == "solve", rel6=(prec == 6))
             assert bad is None, "%s %s prec=%d: %s" % (case["name"], prog, prec, bad)
+
+
+def format_tables(api, ann, M, cnt, sol, prec):
+    """The two stdout tables (count.cpp:486-492, solve.cpp:836-846) from C-ABI results."""
+    g = lambda v: "%.*g" % (prec, v)  # noqa: E731
+    names, forms, foff = ann.event_names(), ann.form_names(), ann.form_offsets()
+    ct, st = [], []
+    for e, name in enumerate(names):
+        sup = "".join(g(float(cnt["n_valid"][m, e])) + "\t" for m in range(M))
+        for f in range(int(foff[e]), int(foff[e + 1])):
+            ct.append("%s\t%s%s\t%s\n" % (name, sup, forms[f], g(float(cnt["iso_count"][f]))))
+            st.append("%s\t%s%s\t%s\t%s\t%s\n" % (name, sup, forms[f], g(sol["theta"][f]), g(sol["rpkm"][f]),
+                                                  g(sol["ll_per_read"][e])))
+    return "".join(ct), "".join(st)
+
+
+def test_abi_matches_reference_golden_fuzz(api, tmp_path):
+    """The 80 fuzz fixtures (reference binary outputs) through the ctypes mirror of the C ABI in
+    one process: count tables identical, solve tables within tolerance."""
+    ctx = api.Context(0)
+    for case in FUZZ_CASES:
+        d = tmp_path / case["name"]
+        d.mkdir()
+        ca, sa = golden_util.materialise(case, str(d))
+        exp = case["expect"]
+        if exp["count_rc"] != 0:
+            continue
+        ann = api.Annotation(ca[4], ca[6], case["begin"], case["end"])
+        if ann.n_events == 0:
+            assert exp["count17"] == ""
+            continue
+        ctx.upload_events(ann)
+        M = len(case["sets"])
+        for m, s in enumerate(case["sets"]):
+            ctx.set_reads(m, s["type"], s["read_length"], api.Reads.from_mrf(d / ("r%d.mrf" % m)))
+        ctx.count()
+        cnt = ctx.get_count()
+        ctx.solve([s["total_read_bases"] for s in case["sets"]])
+        sol = ctx.get_solve()
+        for prec in (17, 6):
+            ct, st = format_tables(api, ann, M, cnt, sol, prec)
+            assert tables_match(exp["count%d" % prec], ct, False) is None, (case["name"], prec)
+            bad = tables_match(exp["solve%d" % prec], st, True, rel6=(prec == 6))
+            assert bad is None, (case["name"], prec, bad)
+    ctx.close()
 
 
 def _oracle_dump(oracle_bin, prog, args, path):
