@@ -92,7 +92,7 @@ struct lsq_ctx {
     lsq::HostTables H;  // host mirror (internal order): headers, permutation, form segment lengths
     std::map<std::string, uint32_t> chrom_id;
     std::vector<std::string> strand_names;
-    DevBuf d_hdr, d_seg, d_fmask, d_pfx, d_tie, d_bp_chrom_off, d_bp_pos, d_stab_off, d_stab_ev, d_cov_off,
+    DevBuf d_hdr, d_seg, d_fmask, d_pfx, d_tie, d_bp_chrom_off, d_bp_pos, d_stab_off, d_stab, d_cov_off, d_bp_bkt_off, d_bp_bkt, d_cov_bkt_off, d_cov_bkt,
         d_cov_start, d_cov_end, d_form_len;
     // read sets
     ReadSet sets[LSQ_MAX_METHODS];
@@ -197,8 +197,17 @@ int lsq_upload_events(lsq_ctx *c, const lsq_event_tables *t) {
     LSQ_CUDA(upload(c->d_tie, H.tie, s));
     LSQ_CUDA(upload(c->d_bp_chrom_off, H.bp_chrom_off, s));
     LSQ_CUDA(upload(c->d_bp_pos, H.bp_pos, s));
-    LSQ_CUDA(upload(c->d_stab_off, H.stab_off, s));
-    LSQ_CUDA(upload(c->d_stab_ev, H.stab_ev, s));
+    {
+        std::vector<uint32_t> padded(H.stab_off);  // slack so 16-byte aligned bulk copies stay in bounds
+        padded.resize(padded.size() + 8, padded.back());
+        LSQ_CUDA(upload(c->d_stab_off, padded, s));
+        LSQ_CUDA(cudaStreamSynchronize(s));
+    }
+    LSQ_CUDA(upload(c->d_stab, H.stab, s));
+    LSQ_CUDA(upload(c->d_bp_bkt_off, H.bp_bkt_off, s));
+    LSQ_CUDA(upload(c->d_bp_bkt, H.bp_bkt, s));
+    LSQ_CUDA(upload(c->d_cov_bkt_off, H.cov_bkt_off, s));
+    LSQ_CUDA(upload(c->d_cov_bkt, H.cov_bkt, s));
     LSQ_CUDA(upload(c->d_cov_off, H.cov_off, s));
     LSQ_CUDA(upload(c->d_cov_start, H.cov_start, s));
     LSQ_CUDA(upload(c->d_cov_end, H.cov_end, s));
@@ -215,7 +224,11 @@ int lsq_upload_events(lsq_ctx *c, const lsq_event_tables *t) {
     T.bp_chrom_off = c->d_bp_chrom_off.as<uint32_t>();
     T.bp_pos = c->d_bp_pos.as<int32_t>();
     T.stab_off = c->d_stab_off.as<uint32_t>();
-    T.stab_ev = c->d_stab_ev.as<uint32_t>();
+    T.stab = c->d_stab.as<lsq::StabEntry>();
+    T.bp_bkt_off = c->d_bp_bkt_off.as<uint32_t>();
+    T.bp_bkt = c->d_bp_bkt.as<uint32_t>();
+    T.cov_bkt_off = c->d_cov_bkt_off.as<uint32_t>();
+    T.cov_bkt = c->d_cov_bkt.as<uint32_t>();
     T.cov_off = c->d_cov_off.as<uint32_t>();
     T.cov_start = c->d_cov_start.as<int32_t>();
     T.cov_end = c->d_cov_end.as<int32_t>();
@@ -355,7 +368,7 @@ static int ensure_run_buffers(lsq_ctx *c) {
     LSQ_CUDA(c->d_slot_cnt.ensure((size_t)LSQ_MAX_METHODS * slots * 8));
     LSQ_CUDA(c->d_slot_mask.ensure((size_t)LSQ_MAX_METHODS * slots * 8));
     LSQ_CUDA(c->d_bases.ensure((size_t)LSQ_MAX_METHODS * E * 8));
-    LSQ_CUDA(c->d_counters.ensure(64 * 8));
+    LSQ_CUDA(c->d_counters.ensure(128 * 8));
     LSQ_CUDA(c->d_n_valid.ensure((size_t)LSQ_MAX_METHODS * E * 8));
     LSQ_CUDA(c->d_bases_out.ensure((size_t)LSQ_MAX_METHODS * E * 8));
     LSQ_CUDA(c->d_iso.ensure(F * 8));
@@ -440,7 +453,7 @@ int lsq_count(lsq_ctx *c) {
         LSQ_CUDA(c->d_work.ensure(std::max<size_t>(nb, 1) * 8));
         LSQ_CUDA(c->d_ext.ensure(std::max<size_t>(nb, 1) * 8));
         size_t cub_bytes = 0;
-        const int end_bit = (int)bits_for(T.n_pieces);
+        const int end_bit = (int)bits_for(T.n_pieces << 1);  // keys 0 .. 2 * n_pieces (= dropped)
         cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, c->d_rkey.as<uint32_t>(), c->d_skey.as<uint32_t>(),
                                         c->d_rec.as<lsq::ReadRec>(), c->d_srec.as<lsq::ReadRec>(), (int64_t)n, 0,
                                         end_bit, s);
@@ -488,8 +501,8 @@ int lsq_count(lsq_ctx *c) {
             CP.slot_mask = slot_mask;
             CP.bases = bases;
             CP.stats = counters + 2;
-            unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)c->n_sms * 8);
-            lsq::lsq_count_kernel<<<grid, 256, 0, s>>>(CP);
+            unsigned grid = (unsigned)std::min<size_t>((n + lsq::COUNT_CHUNK - 1) / lsq::COUNT_CHUNK, (size_t)c->n_sms * 6);
+            lsq::lsq_count_kernel<<<grid, lsq::COUNT_BLOCK, 0, s>>>(CP);
             LSQ_CUDA(cudaGetLastError());
             tm.launches++;
             tm.count_launches++;
@@ -622,8 +635,20 @@ int lsq_solve(lsq_ctx *c, const double *total_read_bases, uint32_t n_methods) {
     double mb = 0.0;  // solve.cpp:810-812
     for (uint32_t m = 0; m < c->M; ++m) mb += total_read_bases[m] / 1.0E6;
     P.total_read_mbases = mb;
+    bool small = c->M <= 2;
+    for (uint32_t m = 0; m < c->M; ++m) small = small && !c->sets[m].injected;
+    P.small_enabled = small ? 1 : 0;
+    P.work_counter = reinterpret_cast<unsigned int *>(c->d_counters.as<unsigned long long>() + 100);
     LSQ_CUDA(cudaEventRecord(c->ev[6], s));
-    if (c->E) {
+    if (c->E && small) {
+        LSQ_CUDA(cudaMemsetAsync(P.work_counter, 0, sizeof(unsigned int), s));
+        unsigned grid = std::min<unsigned>((c->E + 127) / 128, (unsigned)c->n_sms * 8u);
+        if (c->M == 1) lsq::lsq_solve_small_kernel<1><<<grid, 128, 0, s>>>(P);
+        else lsq::lsq_solve_small_kernel<2><<<grid, 128, 0, s>>>(P);
+        LSQ_CUDA(cudaGetLastError());
+        c->tm.launches++;
+    }
+    if (c->E && (!small || c->H.max_forms > 2)) {
         constexpr int WARPS = 8;
         unsigned grid = std::min<unsigned>((c->E + WARPS - 1) / WARPS, (unsigned)c->n_sms * 8u);
         lsq::lsq_solve_kernel<WARPS><<<grid, WARPS * 32, 0, s>>>(P);

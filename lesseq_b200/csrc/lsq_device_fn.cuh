@@ -58,11 +58,24 @@ LSQ_HD uint32_t upper_bound_i32(const int32_t *__restrict__ a, uint32_t lo, uint
     return lo;
 }
 
+// Number of elements <= x among arr[off[c], off[c+1]) through the bucket index (see
+// lsq_tables_host.hpp): one load of two adjacent bucket ranks, then a search inside one bucket.
+LSQ_HD uint32_t bucket_upper_bound(const int32_t *__restrict__ arr, const uint32_t *__restrict__ off,
+                                   const uint32_t *__restrict__ bkt_off, const uint32_t *__restrict__ bkt,
+                                   uint32_t shift, uint32_t c, int32_t x) {
+    const uint32_t lo = LSQ_LD(off + c), hi = LSQ_LD(off + c + 1);
+    if (x < 0) return upper_bound_i32(arr, lo, hi, x);
+    const uint32_t b0 = LSQ_LD(bkt_off + c), nb = LSQ_LD(bkt_off + c + 1) - b0 - 1u;
+    const uint32_t b = (uint32_t)x >> shift;
+    if (b >= nb) return hi;
+    return upper_bound_i32(arr, LSQ_LD(bkt + b0 + b), LSQ_LD(bkt + b0 + b + 1), x);
+}
+
 // contains_interval on the merged covered regions of one chromosome (interval_list.hpp:396-422):
 // the last interval starting at or before s must reach e.
 LSQ_HD bool covered_contains(const Tables &T, uint32_t chrom, int32_t s, int32_t e) {
-    uint32_t lo = LSQ_LD(T.cov_off + chrom), hi = LSQ_LD(T.cov_off + chrom + 1);
-    uint32_t i = upper_bound_i32(T.cov_start, lo, hi, s);
+    uint32_t lo = LSQ_LD(T.cov_off + chrom);
+    uint32_t i = bucket_upper_bound(T.cov_start, T.cov_off, T.cov_bkt_off, T.cov_bkt, T.cov_shift, chrom, s);
     return i > lo && LSQ_LD(T.cov_end + i - 1) >= e;
 }
 
@@ -98,12 +111,24 @@ LSQ_HD uint32_t list_add(int2 *L, uint32_t n, int32_t s, int32_t e) {
 }
 
 
+// ReadRec::w packing: bits 0-22 kept blocks, bit 23 "start is the first position of its piece",
+// bits 24-31 file strand id.
+constexpr uint32_t REC_N_MASK = 0x7FFFFFu;
+constexpr uint32_t REC_AT_PIECE_START = 1u << 23;
+LSQ_HD uint32_t pack_rec_w(const uint32_t n, const uint32_t at_start, const uint32_t strand) {
+    return (strand << 24) | (at_start ? REC_AT_PIECE_START : 0u) | (n & REC_N_MASK);
+}
+
+// Sort key of a read that is a candidate of no event: one past the largest real key.
+LSQ_HD uint32_t KEY_DROPPED(const Tables &T) { return T.n_pieces << 1; }
+
 // Result of the per-read load filter.
 struct FilteredRead {
     uint32_t n;       // kept intervals (0: read dropped)
-    uint32_t key;     // stab piece, or T.n_pieces when the read is not a candidate of any event
+    uint32_t key;     // (stab piece << 1) | (n > 1), or KEY_DROPPED when the read is no candidate
     int2 first;       // first kept interval
     uint32_t strand;  // file strand id of the last registered block
+    uint32_t at_piece_start;  // 1 when the first kept start is the first position of its piece
 };
 
 // count.cpp:297-327 for one read: every block is tested against the covered regions of its
@@ -114,9 +139,10 @@ LSQ_HD FilteredRead filter_read(const FilterParams &P, uint64_t r, int2 *work) {
     const Tables &T = P.T;
     FilteredRead out;
     out.n = 0;
-    out.key = T.n_pieces;
+    out.key = KEY_DROPPED(T);
     out.first = make_int2(0, 0);
     out.strand = 0;
+    out.at_piece_start = 0;
     const uint32_t base = LSQ_LD(P.blk_off + r);
     const uint32_t nraw = LSQ_LD(P.blk_off + r + 1) - base;
     const uint32_t cs0 = LSQ_LD(P.read_cs + r);
@@ -163,11 +189,14 @@ LSQ_HD FilteredRead filter_read(const FilterParams &P, uint64_t r, int2 *work) {
     out.n = n;
     out.first = first;
     if (registered && n > 0 && chrom != 0xFFFFFFFFu) {
-        uint32_t lo = LSQ_LD(T.bp_chrom_off + chrom), hi = LSQ_LD(T.bp_chrom_off + chrom + 1);
-        uint32_t p = upper_bound_i32(T.bp_pos, lo, hi, first.x);
+        uint32_t lo = LSQ_LD(T.bp_chrom_off + chrom);
+        uint32_t p = bucket_upper_bound(T.bp_pos, T.bp_chrom_off, T.bp_bkt_off, T.bp_bkt, T.bp_shift, chrom, first.x);
         if (p > lo) {
             --p;
-            if (LSQ_LD(T.stab_off + p + 1) > LSQ_LD(T.stab_off + p)) out.key = p;
+            if (LSQ_LD(T.stab_off + p + 1) > LSQ_LD(T.stab_off + p)) {
+                out.key = (p << 1) | (n > 1 ? 1u : 0u);
+                out.at_piece_start = LSQ_LD(T.bp_pos + p) == first.x ? 1u : 0u;
+            }
         }
     }
     return out;
@@ -298,6 +327,39 @@ LSQ_HD bool walk_wide(const ReadView &rv, const int2 *seg, uint32_t S,
     }
     matched = ml;
     return ok && last_added != 0xFFFFFFFFu;
+}
+
+// Table-driven evaluation of a SINGLE-BLOCK read [s,e) against a FAST stab entry: the block
+// starts inside chain segment 0; it is matched up to min(e, end of the chain) and covers chain
+// segments 0..i where c[i] is the first chain end >= e.  Same result as walk_mask + the
+// compatibility test + the validity rule of eval_pair, without touching the event tables.
+// Returns the form mask of a valid read (0 otherwise); `tie` tells the caller that the start
+// equals the event start and the end reaches the event end, i.e. the rare lower_bound tie-break
+// must be resolved with the full event header.
+LSQ_HD uint32_t eval_fast(const StabEntry &en, bool at_piece_start, int32_t s, int32_t e, uint32_t &matched,
+                          bool &tie) {
+    tie = false;
+    matched = 0;
+    if ((en.meta & SE_AT_GS) && at_piece_start) {
+        if (e < en.ge) return 0;  // key (start, end) sorts before the probe (gs, ge): skipped
+        tie = true;
+        return 0;
+    }
+    const uint32_t nchain = (en.meta >> 16) & 3u;
+    const int32_t cend = en.c[nchain - 1];
+    uint32_t cm;
+    if (e <= en.c[0]) cm = en.cmask[0];
+    else if (e <= en.c[1]) cm = en.cmask[1];
+    else cm = en.cmask[2];
+    if (cm == 0) return 0;
+    const uint32_t total = (uint32_t)(e - s);
+    uint32_t ml = total;
+    if (e > cend) {  // the block overhangs the chain: truncated match, IEEE rule of count.cpp:441-442
+        ml = (uint32_t)(cend - s);
+        if (!(lsq_div((double)ml, (double)total) > 0.98)) return 0;
+    }
+    matched = ml;
+    return cm;
 }
 
 LSQ_HD uint32_t hash_mask(uint64_t m) {

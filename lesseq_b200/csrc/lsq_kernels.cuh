@@ -11,6 +11,7 @@
 //                      contraction (common/read.h:592-660; solve/solve.cpp:796-826)
 #pragma once
 #include "lsq_device_fn.cuh"
+#include "lsq_tma.cuh"
 
 namespace lsq {
 
@@ -25,11 +26,12 @@ __global__ void __launch_bounds__(256) lsq_filter_kernel(FilterParams P, int2 *_
     const bool in_range = r < P.n_reads;
     FilteredRead fr;
     fr.n = 0;
-    fr.key = T.n_pieces;
+    fr.key = KEY_DROPPED(T);
     fr.first = make_int2(0, 0);
     fr.strand = 0;
+    fr.at_piece_start = 0;
     if (in_range) fr = filter_read(P, r, work);
-    const bool kept = fr.key != T.n_pieces;
+    const bool kept = fr.key != KEY_DROPPED(T);
     // warp-aggregated allocation of ext entries (n slots for reads with n >= 2 kept blocks)
     const uint32_t need = (kept && fr.n >= 2) ? fr.n : 0u;
     uint32_t incl = need;
@@ -48,7 +50,7 @@ __global__ void __launch_bounds__(256) lsq_filter_kernel(FilterParams P, int2 *_
     ReadRec rec;
     rec.x = (uint32_t)fr.first.x;
     rec.y = (uint32_t)fr.first.y;
-    rec.w = (fr.strand << 24) | (fr.n & 0xFFFFFFu);
+    rec.w = pack_rec_w(fr.n, fr.at_piece_start, fr.strand);
     if (need) {
         const uint32_t off = (uint32_t)(ext_base + incl - need);
         const uint32_t base = __ldg(P.blk_off + r);
@@ -84,75 +86,133 @@ __device__ __forceinline__ void bump_class(const CountParams &P, const EvHdr &h,
     }
 }
 
-// Reads arrive sorted by stab piece, so the 32 reads of a warp nearly always share one piece
-// and therefore one list of candidate events: the event loop is warp-uniform, per-class counts
-// are formed with __ballot_sync/__popc and one lane issues the global reduction.
-__global__ void __launch_bounds__(256) lsq_count_kernel(CountParams P) {
+// Count kernel.  Reads arrive sorted by (stab piece, multi-block flag), so the 32 reads of a warp
+// nearly always share one piece and therefore one list of stab entries: the entry loop is
+// warp-uniform, per-class counts are formed with __ballot_sync/__popc and one lane issues the
+// global reduction.  A CTA works on chunks of COUNT_CHUNK consecutive reads; the stab entries and
+// offsets of the chunk's piece range are contiguous in memory and are staged in shared memory
+// with two bulk async copies (TMA, mbarrier completion) when they fit, else read through L1/L2.
+constexpr int COUNT_BLOCK = 256;
+constexpr int COUNT_ITEMS = 8;
+constexpr int COUNT_CHUNK = COUNT_BLOCK * COUNT_ITEMS;
+constexpr int COUNT_MAX_ENT = 512;      // staged stab entries (16 KB)
+constexpr int COUNT_MAX_PIECES = 1016;  // staged offsets (+8 slack words for 16-byte alignment)
+
+__global__ void __launch_bounds__(COUNT_BLOCK) lsq_count_kernel(CountParams P) {
+    __shared__ __align__(128) StabEntry s_ent[COUNT_MAX_ENT];
+    __shared__ __align__(16) uint32_t s_off[COUNT_MAX_PIECES + 8];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_info[4];  // staged?, first entry, first (aligned) piece
     const Tables &T = P.T;
     const unsigned long long n_kept = P.counters[0];
-    const uint32_t lane = lane_id();
-    const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    uint32_t phase = 0;
     unsigned long long my_valid = 0;
-    for (uint64_t base = warp0 * 32ull; base < n_kept; base += n_warps * 32ull) {
-        const uint64_t i = base + lane;
-        const bool act = i < n_kept;
-        uint32_t key = T.n_pieces;
-        ReadView rv;
-        rv.b0 = make_int2(0, 0);
-        rv.n = 1;
-        rv.z = 0;
-        rv.ext = nullptr;
-        uint32_t strand = 0, total_len = 0;
-        if (act) {
-            key = __ldg(P.g_key + i);
-            ReadRec rec = __ldg(P.g_rec + i);
-            rv.b0 = make_int2((int32_t)rec.x, (int32_t)rec.y);
-            rv.n = rec.w & 0xFFFFFFu;
-            rv.z = rec.z;
-            strand = rec.w >> 24;
-            total_len = (uint32_t)(rv.b0.y - rv.b0.x);
-            if (rv.n > 1) {
-                rv.ext = P.ext + rec.z;
-                for (uint32_t j = 1; j < rv.n; ++j) {
-                    int2 b = __ldg(rv.ext + j);
-                    total_len += (uint32_t)(b.y - b.x);
-                }
+    const unsigned long long n_chunks = (n_kept + COUNT_CHUNK - 1) / COUNT_CHUNK;
+    for (unsigned long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        const unsigned long long base = chunk * COUNT_CHUNK;
+        const unsigned long long end = min(base + (unsigned long long)COUNT_CHUNK, n_kept);
+        if (threadIdx.x == 0) {
+            const uint32_t pf = __ldg(P.g_key + base) >> 1, pl = __ldg(P.g_key + end - 1) >> 1;
+            const uint32_t e0 = __ldg(T.stab_off + pf), e1 = __ldg(T.stab_off + pl + 1);
+            const uint32_t pa = pf & ~3u;  // 16-byte aligned start of the offset slice
+            const uint32_t noff = ((pl + 2 - pa) + 3u) & ~3u;
+            const bool staged = (e1 - e0) <= (uint32_t)COUNT_MAX_ENT && noff <= (uint32_t)(COUNT_MAX_PIECES + 8) && e1 > e0;
+            s_info[0] = staged;
+            s_info[1] = e0;
+            s_info[2] = pa;
+            if (staged) {
+                const uint32_t ebytes = (e1 - e0) * (uint32_t)sizeof(StabEntry), obytes = noff * 4u;
+                mbar_expect_tx(&s_bar, ebytes + obytes);
+                bulk_g2s(s_ent, T.stab + e0, ebytes, &s_bar);
+                bulk_g2s(s_off, T.stab_off + pa, obytes, &s_bar);
             }
         }
-        unsigned todo = __ballot_sync(0xFFFFFFFFu, act);
-        while (todo) {
-            const int leader = __ffs(todo) - 1;
-            const uint32_t k0 = __shfl_sync(0xFFFFFFFFu, key, leader);
-            const bool mine = act && key == k0;
-            todo &= ~__ballot_sync(0xFFFFFFFFu, mine);
-            const uint32_t so = __ldg(T.stab_off + k0), se = __ldg(T.stab_off + k0 + 1);
-            for (uint32_t q = so; q < se; ++q) {
-                const uint32_t x = __ldg(T.stab_ev + q);
-                const EvHdr h = T.hdr[x];
-                uint64_t cm = 0;
-                uint32_t ml = 0;
-                if (mine) cm = eval_pair(P, h, T.seg + h.seg_off, T.fmask + h.form_off, rv, strand, total_len, ml);
-                const unsigned vmask = __ballot_sync(0xFFFFFFFFu, cm != 0);
-                if (vmask == 0) continue;
-                if (h.K <= 2) {
-                    const uint32_t ncls = (1u << h.K) - 1u;
-                    for (uint32_t c = 1; c <= ncls; ++c) {
-                        unsigned bm = __ballot_sync(0xFFFFFFFFu, cm == c);
-                        if (lane == 0 && bm)
-                            atomicAdd(P.slot_cnt + h.slot_off + c - 1u, (unsigned long long)__popc(bm));
+        __syncthreads();
+        const bool staged = s_info[0] != 0;
+        const StabEntry *ent = T.stab;
+        const uint32_t *off = T.stab_off;
+        if (staged) {
+            mbar_wait(&s_bar, phase);
+            phase ^= 1u;
+            ent = s_ent - s_info[1];
+            off = s_off - s_info[2];
+        }
+        for (int it = 0; it < COUNT_ITEMS; ++it) {
+            const unsigned long long i = base + (unsigned long long)((warp * COUNT_ITEMS + it) * 32u + lane);
+            if (base + (unsigned long long)((warp * COUNT_ITEMS + it) * 32u) >= end) break;  // warp-uniform
+            const bool act = i < end;
+            uint32_t key = 0xFFFFFFFFu;
+            ReadView rv;
+            rv.b0 = make_int2(0, 0);
+            rv.n = 1;
+            rv.z = 0;
+            rv.ext = nullptr;
+            uint32_t strand = 0;
+            bool at_start = false;
+            if (act) {
+                key = __ldg(P.g_key + i);
+                const ReadRec rec = __ldg(P.g_rec + i);
+                rv.b0 = make_int2((int32_t)rec.x, (int32_t)rec.y);
+                rv.n = rec.w & REC_N_MASK;
+                rv.z = rec.z;
+                strand = rec.w >> 24;
+                at_start = (rec.w & REC_AT_PIECE_START) != 0;
+                if (rv.n > 1) rv.ext = P.ext + rec.z;
+            }
+            unsigned todo = __ballot_sync(0xFFFFFFFFu, act);
+            while (todo) {
+                const int leader = __ffs(todo) - 1;
+                const uint32_t k0 = __shfl_sync(0xFFFFFFFFu, key, leader);
+                const bool mine = act && key == k0;
+                todo &= ~__ballot_sync(0xFFFFFFFFu, mine);
+                const uint32_t piece = k0 >> 1;
+                const uint32_t so = off[piece], se = off[piece + 1];
+                for (uint32_t q = so; q < se; ++q) {
+                    const StabEntry en = ent[q];
+                    uint32_t cm32 = 0, ml = 0;
+                    uint64_t cm = 0;
+                    bool general = mine;
+                    if (mine && rv.n == 1 && (en.meta & SE_FAST)) {
+                        bool tie;
+                        cm32 = eval_fast(en, at_start, rv.b0.x, rv.b0.y, ml, tie);
+                        cm = cm32;
+                        general = tie;
                     }
-                } else if (cm != 0) {
-                    bump_class(P, h, cm);
+                    if (general) {  // multi-block reads, wide / many-form events, long chains, tie-breaks
+                        const EvHdr h = T.hdr[en.x];
+                        uint32_t total_len = (uint32_t)(rv.b0.y - rv.b0.x);
+                        for (uint32_t j = 1; j < rv.n; ++j) {
+                            const int2 b = __ldg(rv.ext + j);
+                            total_len += (uint32_t)(b.y - b.x);
+                        }
+                        cm = eval_pair(P, h, T.seg + h.seg_off, T.fmask + h.form_off, rv, strand, total_len, ml);
+                    }
+                    const unsigned vmask = __ballot_sync(0xFFFFFFFFu, cm != 0);
+                    if (vmask == 0) continue;
+                    if (en.K <= 2) {
+                        const uint32_t ncls = (1u << en.K) - 1u;
+                        for (uint32_t c = 1; c <= ncls; ++c) {
+                            const unsigned bm = __ballot_sync(0xFFFFFFFFu, cm == c);
+                            if (lane == 0 && bm)
+                                atomicAdd(P.slot_cnt + en.slot_off + c - 1u, (unsigned long long)__popc(bm));
+                        }
+                    } else if (cm != 0) {
+                        const EvHdr h = T.hdr[en.x];
+                        bump_class(P, h, cm);
+                    }
+                    const uint32_t sum = __reduce_add_sync(0xFFFFFFFFu, ml);
+                    if (lane == 0) atomicAdd(P.bases + en.x, (unsigned long long)sum);
+                    my_valid += (cm != 0);
                 }
-                uint32_t sum = __reduce_add_sync(0xFFFFFFFFu, ml);
-                if (lane == 0) atomicAdd(P.bases + x, (unsigned long long)sum);
-                my_valid += (cm != 0);
             }
         }
+        __syncthreads();  // every warp is done with the staged tables before the next chunk overwrites them
     }
-    my_valid = __reduce_add_sync(0xFFFFFFFFu, (unsigned)my_valid);
-    if (lane == 0 && my_valid) atomicAdd(P.stats, my_valid);
+    const unsigned v = __reduce_add_sync(0xFFFFFFFFu, (unsigned)my_valid);
+    if (lane == 0 && v) atomicAdd(P.stats, (unsigned long long)v);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -236,6 +296,7 @@ __global__ void __launch_bounds__(WARPS * 32) lsq_solve_kernel(SolveParams P) {
     for (uint32_t x = blockIdx.x * WARPS + w; x < E; x += gridDim.x * WARPS) {
         const EvHdr h = P.T.hdr[x];
         const uint32_t K = h.K;
+        if (P.small_enabled && K <= 2) continue;  // solved by lsq_solve_small_kernel
         double *th_old = s_theta[w][0], *th_new = s_theta[w][1];
         // N = total number of valid reads (read.h:599-602), sum of supports (solve.cpp:826)
         double n_total = 0.0, sum_supports = 0.0;
@@ -325,6 +386,103 @@ __global__ void __launch_bounds__(WARPS * 32) lsq_solve_kernel(SolveParams P) {
             P.iters[h.out_ev] = iters;
         }
         __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Solve kernel for the common small events (K <= 2 forms, M <= 2 counted read sets): one THREAD
+// per event, the whole EM state in registers, and lanes fetch a new event as soon as theirs has
+// converged, so iteration-count skew between events does not idle a warp.  Arithmetic per class
+// is the same as in lsq_solve_kernel (and the reference's per-read arithmetic); only the order
+// of the sums over classes differs.
+// ---------------------------------------------------------------------------------------------
+template <int M>
+__global__ void __launch_bounds__(128) lsq_solve_small_kernel(SolveParams P) {
+    const uint32_t E = P.T.E;
+    while (true) {
+        const uint32_t x = atomicAdd(P.work_counter, 1u);
+        if (x >= E) return;
+        const EvHdr h = P.T.hdr[x];
+        const uint32_t K = h.K;
+        if (K > 2) continue;
+        double cnt[M][3], G[M][2];
+        double n_total = 0.0, sum_supports = 0.0;
+        bool any = false;
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            const unsigned long long *sc = P.slot_cnt + (size_t)m * P.T.total_slots + h.slot_off;
+            cnt[m][0] = (double)sc[0];
+            cnt[m][1] = K == 2 ? (double)sc[1] : 0.0;
+            cnt[m][2] = K == 2 ? (double)sc[2] : 0.0;
+            const double *g = P.G + (size_t)m * P.T.F + h.form_off;
+            G[m][0] = g[0];
+            G[m][1] = K == 2 ? g[1] : 0.0;
+            const unsigned long long nv = P.n_valid[(size_t)m * E + h.out_ev];
+            if (nv) {
+                any = true;
+                n_total = __dadd_rn(n_total, (double)nv);
+            }
+            sum_supports = __dadd_rn(sum_supports, (double)nv);
+        }
+        double th0 = __ddiv_rn(1.0, (double)K), th1 = th0;
+        // log-likelihood at (t0, t1): sum over classes of count * log(sum_k theta_k G_k)
+        auto loglik = [&](double t0, double t1) {
+            double ll = 0.0;
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                const double p0 = __dmul_rn(t0, G[m][0]), p1 = __dmul_rn(t1, G[m][1]);
+                if (cnt[m][0] != 0.0) ll = __dadd_rn(ll, __dmul_rn(cnt[m][0], log(p0)));
+                if (cnt[m][1] != 0.0) ll = __dadd_rn(ll, __dmul_rn(cnt[m][1], log(p1)));
+                if (cnt[m][2] != 0.0) ll = __dadd_rn(ll, __dmul_rn(cnt[m][2], log(__dadd_rn(p0, p1))));
+            }
+            return ll;
+        };
+        uint32_t iters = 0;
+        double ll = 0.0;
+        if (!any) {
+        } else if (K == 1) {
+            th0 = 1.0;
+            ll = loglik(1.0, 0.0);
+        } else {
+            double ll_old = loglik(th0, th1);
+            while (true) {
+                double z0 = 0.0, z1 = 0.0;
+#pragma unroll
+                for (int m = 0; m < M; ++m) {
+                    const double p0 = __dmul_rn(th0, G[m][0]), p1 = __dmul_rn(th1, G[m][1]);
+                    const double s3 = __dadd_rn(p0, p1);
+                    // form 0: classes {0} and {0,1}; form 1: classes {1} and {0,1}
+                    if (p0 > 0.0) {
+                        if (cnt[m][0] != 0.0) z0 = __dadd_rn(z0, __dmul_rn(cnt[m][0], __ddiv_rn(p0, p0)));
+                        if (cnt[m][2] != 0.0 && s3 > 0.0) z0 = __dadd_rn(z0, __dmul_rn(cnt[m][2], __ddiv_rn(p0, s3)));
+                    }
+                    if (p1 > 0.0) {
+                        if (cnt[m][1] != 0.0) z1 = __dadd_rn(z1, __dmul_rn(cnt[m][1], __ddiv_rn(p1, p1)));
+                        if (cnt[m][2] != 0.0 && s3 > 0.0) z1 = __dadd_rn(z1, __dmul_rn(cnt[m][2], __ddiv_rn(p1, s3)));
+                    }
+                }
+                th0 = __ddiv_rn(z0, n_total);
+                th1 = __ddiv_rn(z1, n_total);
+                ll = loglik(th0, th1);
+                ++iters;
+                const double ratio = __ddiv_rn(ll_old, ll);
+                if (!(fabs(__dsub_rn(1.0, ratio)) > 1E-6) || iters >= P.max_iters) break;
+                ll_old = ll;
+            }
+        }
+        for (uint32_t k = 0; k < K; ++k) {
+            const double th = k == 0 ? th0 : th1;
+            double r = 0.0;
+#pragma unroll
+            for (int m = 0; m < M; ++m) r = __dadd_rn(r, __dmul_rn((double)P.bases[(size_t)m * E + x], th));
+            r = __ddiv_rn(r, __ddiv_rn((double)P.form_len[h.form_off + k], 1.0E3));
+            r = __ddiv_rn(r, P.total_read_mbases);
+            P.theta[h.out_form + k] = th;
+            P.rpkm[h.out_form + k] = r;
+        }
+        P.loglik[h.out_ev] = ll;
+        P.ll_per_read[h.out_ev] = (sum_supports > 1E-5) ? __ddiv_rn(ll, sum_supports) : 0.0;
+        P.iters[h.out_ev] = iters;
     }
 }
 

@@ -16,14 +16,18 @@ namespace lsq {
 struct HostTables {
     uint32_t E = 0, F = 0, n_chroms = 0, n_strands = 0;
     uint64_t slot_total = 0;
+    uint32_t max_forms = 0;
     std::vector<uint32_t> order;  // internal -> output event index
     std::vector<EvHdr> hdr;       // internal order + sentinel
     std::vector<int2> seg;
     std::vector<uint64_t> fmask, form_len, form_seg_len;
     std::vector<uint32_t> pfx, form_seg_off;
     std::vector<char> tie;
-    std::vector<uint32_t> bp_chrom_off, stab_off, stab_ev, cov_off;
+    std::vector<uint32_t> bp_chrom_off, stab_off, cov_off;
+    std::vector<StabEntry> stab;
     std::vector<int32_t> bp_pos, cov_start, cov_end;
+    uint32_t bp_shift = 0, cov_shift = 0;
+    std::vector<uint32_t> bp_bkt_off, bp_bkt, cov_bkt_off, cov_bkt;
 
     // Table view over the HOST arrays (CPU replay harness only).
     Tables host_view() const {
@@ -42,13 +46,48 @@ struct HostTables {
         T.bp_chrom_off = bp_chrom_off.data();
         T.bp_pos = bp_pos.data();
         T.stab_off = stab_off.data();
-        T.stab_ev = stab_ev.data();
+        T.stab = stab.data();
+        T.bp_shift = bp_shift;
+        T.cov_shift = cov_shift;
+        T.bp_bkt_off = bp_bkt_off.data();
+        T.bp_bkt = bp_bkt.data();
+        T.cov_bkt_off = cov_bkt_off.data();
+        T.cov_bkt = cov_bkt.data();
         T.cov_off = cov_off.data();
         T.cov_start = cov_start.data();
         T.cov_end = cov_end.data();
         return T;
     }
 };
+
+// Bucket index over per-chromosome sorted coordinate arrays (CSR `off`): bucket b of a
+// chromosome covers positions [b << shift, (b+1) << shift) and stores the rank (global index)
+// of the first element >= b << shift; one extra bucket per chromosome closes the last range.
+// The shift is chosen so that there are about as many buckets as elements (at most 2^24).
+inline void build_bucket_index(const std::vector<int32_t> &arr, const std::vector<uint32_t> &off, uint32_t &shift,
+                               std::vector<uint32_t> &bkt_off, std::vector<uint32_t> &bkt) {
+    const size_t nch = off.size() - 1;
+    uint64_t span = 0;
+    for (size_t c = 0; c < nch; ++c)
+        if (off[c + 1] > off[c]) span += (uint64_t)std::max<int32_t>(arr[off[c + 1] - 1], 0) + 1;
+    uint64_t want = std::min<uint64_t>(std::max<uint64_t>(arr.size(), 1), 1ull << 24);
+    shift = 0;
+    while ((span >> shift) > want && shift < 30) ++shift;
+    bkt_off.assign(nch + 1, 0);
+    bkt.clear();
+    for (size_t c = 0; c < nch; ++c) {
+        bkt_off[c] = (uint32_t)bkt.size();
+        uint32_t lo = off[c], hi = off[c + 1];
+        uint32_t nb = hi > lo ? (uint32_t)(((uint64_t)std::max<int32_t>(arr[hi - 1], 0) >> shift) + 1) : 0;
+        uint32_t i = lo;
+        for (uint32_t b = 0; b <= nb; ++b) {  // nb + 1 entries: the last one is `hi`
+            int64_t start = (int64_t)b << shift;
+            while (i < hi && (int64_t)arr[i] < start) ++i;
+            bkt.push_back(b == nb ? hi : i);
+        }
+    }
+    bkt_off[nch] = (uint32_t)bkt.size();
+}
 
 inline int tfail(std::string &err, int code, const std::string &msg) {
     err = msg;
@@ -125,6 +164,7 @@ inline int build_host_tables(const lsq_event_tables *t, HostTables &H, std::stri
     });
     std::vector<lsq::EvHdr> &hdr = H.hdr;
     hdr.assign(E + 1, lsq::EvHdr());
+    H.max_forms = 0;
     std::vector<int2> &seg = H.seg;
     std::vector<uint64_t> &fmask = H.fmask, &form_len = H.form_len, &form_seg_len = H.form_seg_len;
     std::vector<uint32_t> &pfx = H.pfx, &form_seg_off = H.form_seg_off;
@@ -150,6 +190,7 @@ inline int build_host_tables(const lsq_event_tables *t, HostTables &H, std::stri
         h.form_off = (uint32_t)fmask.size();
         h.S = (uint16_t)S;
         h.K = (uint16_t)K;
+        H.max_forms = std::max(H.max_forms, K);
         h.strand = (uint8_t)t->ev_strand[e];
         h.out_ev = e;
         h.out_form = f0;
@@ -219,13 +260,17 @@ inline int build_host_tables(const lsq_event_tables *t, HostTables &H, std::stri
     hdr[E].seg_off = (uint32_t)seg.size();
     hdr[E].form_off = (uint32_t)fmask.size();
 
-    // stab arrangement: per chromosome the event spans [gs, ge] cut the axis into pieces;
-    // every read start falls into one piece and the piece lists the events it is a candidate for.
-    std::vector<uint32_t> &bp_chrom_off = H.bp_chrom_off, &stab_off = H.stab_off, &stab_ev = H.stab_ev;
+    // stab arrangement: per chromosome, every segment boundary and span end of its events cuts
+    // the axis into pieces.  A read is keyed by the piece holding the start of its first kept
+    // block; the piece lists the events for which that start lies inside a segment (a start
+    // outside every segment of an event can never be matched by the walk of read.h:226-262, so
+    // such pairs are not candidates at all).
+    std::vector<uint32_t> &bp_chrom_off = H.bp_chrom_off, &stab_off = H.stab_off;
+    std::vector<StabEntry> &stab = H.stab;
     std::vector<int32_t> &bp_pos = H.bp_pos;
     bp_chrom_off.assign(t->n_chroms + 1, 0);
     stab_off.assign(1, 0);
-    stab_ev.clear();
+    stab.clear();
     bp_pos.clear();
     {
         uint32_t ie = 0;
@@ -238,23 +283,61 @@ inline int build_host_tables(const lsq_event_tables *t, HostTables &H, std::stri
             for (uint32_t q = first; q < ie; ++q) {
                 bps.push_back(hdr[q].gs);
                 bps.push_back(hdr[q].ge + 1);
+                for (uint32_t j = 0; j < hdr[q].S; ++j) {
+                    bps.push_back(seg[hdr[q].seg_off + j].x);
+                    bps.push_back(seg[hdr[q].seg_off + j].y);
+                }
             }
             std::sort(bps.begin(), bps.end());
             bps.erase(std::unique(bps.begin(), bps.end()), bps.end());
-            std::vector<std::vector<uint32_t> > lists(bps.size());
+            std::vector<std::vector<StabEntry> > lists(bps.size());
             uint64_t total = 0;
             for (uint32_t q = first; q < ie; ++q) {
-                size_t a = std::lower_bound(bps.begin(), bps.end(), hdr[q].gs) - bps.begin();
-                size_t b = std::lower_bound(bps.begin(), bps.end(), hdr[q].ge + 1) - bps.begin();
-                for (size_t p = a; p < b; ++p) lists[p].push_back(q);
-                total += b - a;
-                if (stab_ev.size() + total > 0x7FFFFFFFull)
-                    return tfail(err, LSQ_ERR_RANGE, "stab lists exceed 2^31 entries (too many nested events)");
+                const EvHdr &h = hdr[q];
+                const int2 *sg = seg.data() + h.seg_off;
+                const bool plain = !(h.flags & (EV_WIDE | EV_HASH));
+                for (uint32_t j = 0; j < h.S; ++j) {
+                    if (!(sg[j].x < sg[j].y)) continue;
+                    StabEntry en;
+                    memset(&en, 0, sizeof en);
+                    en.x = q;
+                    en.slot_off = h.slot_off;
+                    en.ge = h.ge;
+                    en.K = (uint8_t)h.K;
+                    // chain of abutting segments a single block starting in segment j runs through
+                    uint32_t nchain = 1;
+                    while (j + nchain < h.S && sg[j + nchain].x == sg[j + nchain - 1].y) ++nchain;
+                    bool fast = plain && nchain <= 3 && sg[j].x >= 0;
+                    if (fast) {
+                        for (uint32_t i = 0; i < 3; ++i) {
+                            uint32_t ii = std::min(i, nchain - 1);
+                            en.c[i] = sg[j + ii].y;
+                            uint64_t rmask = ((2ull << (j + ii)) - 1ull) & ~((1ull << j) - 1ull);
+                            uint8_t cm = 0;
+                            for (uint32_t k = 0; k < h.K; ++k)
+                                // a block covering consecutive segments j..j+ii is its own span, so
+                                // the contiguous-run test (read.h:44-79) is plain containment
+                                if ((fmask[h.form_off + k] & rmask) == rmask) cm |= (uint8_t)(1u << k);
+                            en.cmask[i] = cm;
+                        }
+                    }
+                    en.meta = (j & 0xFFFFu) | ((fast ? nchain : 0u) << 16) | (fast ? SE_FAST : 0u);
+                    size_t a = std::lower_bound(bps.begin(), bps.end(), sg[j].x) - bps.begin();
+                    size_t b = std::lower_bound(bps.begin(), bps.end(), sg[j].y) - bps.begin();
+                    for (size_t p = a; p < b; ++p) {
+                        StabEntry e2 = en;
+                        if (bps[p] == h.gs) e2.meta |= SE_AT_GS;
+                        lists[p].push_back(e2);
+                    }
+                    total += b - a;
+                    if (stab.size() + total > 0x3FFFFFFFull)
+                        return tfail(err, LSQ_ERR_RANGE, "stab lists exceed 2^30 entries (too many nested events)");
+                }
             }
             for (size_t p = 0; p < bps.size(); ++p) {
                 bp_pos.push_back(bps[p]);
-                stab_ev.insert(stab_ev.end(), lists[p].begin(), lists[p].end());
-                stab_off.push_back((uint32_t)stab_ev.size());
+                stab.insert(stab.end(), lists[p].begin(), lists[p].end());
+                stab_off.push_back((uint32_t)stab.size());
             }
         }
         bp_chrom_off[t->n_chroms] = (uint32_t)bp_pos.size();
@@ -264,6 +347,8 @@ inline int build_host_tables(const lsq_event_tables *t, HostTables &H, std::stri
     H.cov_start.assign(t->cov_start, t->cov_start + H.cov_off.back());
     H.cov_end.assign(t->cov_end, t->cov_end + H.cov_off.back());
     H.tie.assign(tie_pool.begin(), tie_pool.end());
+    build_bucket_index(H.bp_pos, H.bp_chrom_off, H.bp_shift, H.bp_bkt_off, H.bp_bkt);
+    build_bucket_index(H.cov_start, H.cov_off, H.cov_shift, H.cov_bkt_off, H.cov_bkt);
     H.slot_total = slot_total;
     H.E = E;
     H.F = (uint32_t)fmask.size();

@@ -32,6 +32,26 @@ constexpr uint8_t EV_TIE_MASK = 0x3;   // 0: "read-N" never < name, 1: always, 2
 constexpr uint8_t EV_WIDE = 0x4;       // S > 64: prefix-count compatibility test
 constexpr uint8_t EV_HASH = 0x8;       // class table is an open-addressed hash (K > DENSE_MAX_FORMS)
 
+// Stab entry, 32 bytes: one (piece, event) pair of the stab arrangement.  Pieces are the
+// elementary intervals cut by every segment boundary and span end of the events of a chromosome,
+// so for a read whose first block starts in the piece, the segment j0 of event x that contains
+// the start is known in advance, and so is the chain of abutting segments a single block can run
+// through (common/read.h:226-262).  FAST entries carry the chain ends c[i] and the form
+// compatibility mask cmask[i] of a read covering chain segments 0..i, which decides a
+// single-block read with a few compares; everything else takes the general walk.
+struct __align__(16) StabEntry {
+    uint32_t x;         // internal event id
+    uint32_t slot_off;  // class slots of x (copy of EvHdr::slot_off)
+    int32_t ge;         // event end, first test of the lower_bound tie-break
+    uint32_t meta;      // bits 0-15 j0 | bits 16-17 chain length (1..3) | SE_* flags
+    int32_t c[3];       // chain segment ends, ascending
+    uint8_t cmask[3];   // form mask (K <= 8) when the block ends within chain segment i
+    uint8_t K;          // forms of x
+};
+static_assert(sizeof(StabEntry) == 32, "StabEntry layout");
+constexpr uint32_t SE_FAST = 1u << 24;   // table-driven single-block evaluation is valid
+constexpr uint32_t SE_AT_GS = 1u << 25;  // the piece starts at the event start (tie-break possible)
+
 // Sorted read record (16 bytes), value type of the radix sort keyed by stab piece.
 //   x,y : first kept block [start,end)
 //   z   : n == 1 ? original read index : offset of the read's entry in ext[]
@@ -50,9 +70,16 @@ struct Tables {
     const uint32_t *bp_chrom_off;  // [n_chroms+1] piece range per chromosome
     const int32_t *bp_pos;         // [n_pieces] first position of each stab piece
     const uint32_t *stab_off;      // [n_pieces+1]
-    const uint32_t *stab_ev;       // events (internal ids) whose span covers the piece
+    const StabEntry *stab;         // candidate events of each piece
     const uint32_t *cov_off;       // [n_chroms+1]
     const int32_t *cov_start, *cov_end;
+    // bucket indexes: position >> shift -> rank of the bucket start in the sorted array, so a
+    // lookup is one table load plus a short forward scan instead of a full binary search
+    uint32_t bp_shift, cov_shift;
+    const uint32_t *bp_bkt_off;    // [n_chroms+1] first bucket of each chromosome
+    const uint32_t *bp_bkt;        // [buckets + n_chroms] rank within bp_pos
+    const uint32_t *cov_bkt_off;
+    const uint32_t *cov_bkt;       // rank within cov_start
 };
 
 struct FilterParams {
@@ -105,6 +132,8 @@ struct SolveParams {
     uint32_t *iters;                // [E]
     uint32_t max_iters;
     int with_se;
+    int small_enabled;             // events with K <= 2 are solved by lsq_solve_small_kernel
+    unsigned int *work_counter;    // dynamic event fetch of lsq_solve_small_kernel
 };
 
 }  // namespace lsq

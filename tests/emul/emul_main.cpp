@@ -149,8 +149,8 @@ int main(int argc, char **argv) {
             ReadRec q;
             q.x = (uint32_t)fr.first.x;
             q.y = (uint32_t)fr.first.y;
-            q.w = (fr.strand << 24) | (fr.n & 0xFFFFFFu);
-            if (fr.key != T.n_pieces && fr.n >= 2) {
+            q.w = pack_rec_w(fr.n, fr.at_piece_start, fr.strand);
+            if (fr.key != KEY_DROPPED(T) && fr.n >= 2) {
                 uint32_t off = (uint32_t)counters[1];
                 counters[1] += fr.n;
                 ext[off] = make_int2((int32_t)r, (int32_t)fr.n);
@@ -173,21 +173,31 @@ int main(int argc, char **argv) {
         for (size_t i = 0; i < n; ++i) {  // lsq_count_kernel, one read at a time
             uint32_t r = perm[i];
             uint32_t key = rkey[r];
-            if (key == T.n_pieces) break;
+            if (key == KEY_DROPPED(T)) break;
             ReadRec q = rec[r];
             ReadView rv;
             rv.b0 = make_int2((int32_t)q.x, (int32_t)q.y);
-            rv.n = q.w & 0xFFFFFFu;
+            rv.n = q.w & REC_N_MASK;
+            const bool at_start = (q.w & REC_AT_PIECE_START) != 0;
             rv.z = q.z;
             rv.ext = rv.n > 1 ? ext.data() + q.z : nullptr;
             uint32_t strand = q.w >> 24;
             uint32_t total = (uint32_t)(rv.b0.y - rv.b0.x);
             for (uint32_t j = 1; j < rv.n; ++j) total += (uint32_t)(rv.ext[j].y - rv.ext[j].x);
-            for (uint32_t s = T.stab_off[key]; s < T.stab_off[key + 1]; ++s) {
-                uint32_t x = T.stab_ev[s];
+            const uint32_t piece = key >> 1;
+            for (uint32_t s = T.stab_off[piece]; s < T.stab_off[piece + 1]; ++s) {
+                const StabEntry &en = T.stab[s];
+                uint32_t x = en.x;
                 const EvHdr &h = T.hdr[x];
-                uint32_t ml;
-                uint64_t cm = eval_pair(CP, h, T.seg + h.seg_off, T.fmask + h.form_off, rv, strand, total, ml);
+                uint32_t ml = 0;
+                uint64_t cm = 0;
+                bool general = true;
+                if (rv.n == 1 && (en.meta & SE_FAST)) {
+                    bool tie;
+                    cm = eval_fast(en, at_start, rv.b0.x, rv.b0.y, ml, tie);
+                    general = tie;
+                }
+                if (general) cm = eval_pair(CP, h, T.seg + h.seg_off, T.fmask + h.form_off, rv, strand, total, ml);
                 if (cm) {
                     hist[m][x][cm]++;
                     bases[m][x] += ml;
