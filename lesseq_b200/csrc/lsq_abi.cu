@@ -92,7 +92,7 @@ struct lsq_ctx {
     lsq::HostTables H;  // host mirror (internal order): headers, permutation, form segment lengths
     std::map<std::string, uint32_t> chrom_id;
     std::vector<std::string> strand_names;
-    DevBuf d_hdr, d_seg, d_fmask, d_pfx, d_tie, d_bp_chrom_off, d_bp_pos, d_stab_off, d_stab, d_cov_off, d_bp_bkt_off, d_bp_bkt, d_cov_bkt_off, d_cov_bkt,
+    DevBuf d_hdr, d_seg, d_fmask, d_pfx, d_tie, d_bp_chrom_off, d_bp_pos, d_stab_off, d_stab, d_cov_off, d_bp_bkt_off, d_bp_bkt, d_pinfo,
         d_cov_start, d_cov_end, d_form_len;
     // read sets
     ReadSet sets[LSQ_MAX_METHODS];
@@ -196,7 +196,7 @@ int lsq_upload_events(lsq_ctx *c, const lsq_event_tables *t) {
     LSQ_CUDA(upload(c->d_pfx, H.pfx, s));
     LSQ_CUDA(upload(c->d_tie, H.tie, s));
     LSQ_CUDA(upload(c->d_bp_chrom_off, H.bp_chrom_off, s));
-    LSQ_CUDA(upload(c->d_bp_pos, H.bp_pos, s));
+    LSQ_CUDA(upload(c->d_pinfo, H.pinfo, s));
     {
         std::vector<uint32_t> padded(H.stab_off);  // slack so 16-byte aligned bulk copies stay in bounds
         padded.resize(padded.size() + 8, padded.back());
@@ -206,8 +206,6 @@ int lsq_upload_events(lsq_ctx *c, const lsq_event_tables *t) {
     LSQ_CUDA(upload(c->d_stab, H.stab, s));
     LSQ_CUDA(upload(c->d_bp_bkt_off, H.bp_bkt_off, s));
     LSQ_CUDA(upload(c->d_bp_bkt, H.bp_bkt, s));
-    LSQ_CUDA(upload(c->d_cov_bkt_off, H.cov_bkt_off, s));
-    LSQ_CUDA(upload(c->d_cov_bkt, H.cov_bkt, s));
     LSQ_CUDA(upload(c->d_cov_off, H.cov_off, s));
     LSQ_CUDA(upload(c->d_cov_start, H.cov_start, s));
     LSQ_CUDA(upload(c->d_cov_end, H.cov_end, s));
@@ -222,13 +220,11 @@ int lsq_upload_events(lsq_ctx *c, const lsq_event_tables *t) {
     T.pfx = c->d_pfx.as<uint32_t>();
     T.tie_pool = c->d_tie.as<char>();
     T.bp_chrom_off = c->d_bp_chrom_off.as<uint32_t>();
-    T.bp_pos = c->d_bp_pos.as<int32_t>();
+    T.pinfo = c->d_pinfo.as<lsq::PieceInfo>();
     T.stab_off = c->d_stab_off.as<uint32_t>();
     T.stab = c->d_stab.as<lsq::StabEntry>();
     T.bp_bkt_off = c->d_bp_bkt_off.as<uint32_t>();
     T.bp_bkt = c->d_bp_bkt.as<uint32_t>();
-    T.cov_bkt_off = c->d_cov_bkt_off.as<uint32_t>();
-    T.cov_bkt = c->d_cov_bkt.as<uint32_t>();
     T.cov_off = c->d_cov_off.as<uint32_t>();
     T.cov_start = c->d_cov_start.as<int32_t>();
     T.cov_end = c->d_cov_end.as<int32_t>();

@@ -58,25 +58,39 @@ LSQ_HD uint32_t upper_bound_i32(const int32_t *__restrict__ a, uint32_t lo, uint
     return lo;
 }
 
-// Number of elements <= x among arr[off[c], off[c+1]) through the bucket index (see
-// lsq_tables_host.hpp): one load of two adjacent bucket ranks, then a search inside one bucket.
-LSQ_HD uint32_t bucket_upper_bound(const int32_t *__restrict__ arr, const uint32_t *__restrict__ off,
-                                   const uint32_t *__restrict__ bkt_off, const uint32_t *__restrict__ bkt,
-                                   uint32_t shift, uint32_t c, int32_t x) {
-    const uint32_t lo = LSQ_LD(off + c), hi = LSQ_LD(off + c + 1);
-    if (x < 0) return upper_bound_i32(arr, lo, hi, x);
-    const uint32_t b0 = LSQ_LD(bkt_off + c), nb = LSQ_LD(bkt_off + c + 1) - b0 - 1u;
-    const uint32_t b = (uint32_t)x >> shift;
-    if (b >= nb) return hi;
-    return upper_bound_i32(arr, LSQ_LD(bkt + b0 + b), LSQ_LD(bkt + b0 + b + 1), x);
-}
-
-// contains_interval on the merged covered regions of one chromosome (interval_list.hpp:396-422):
-// the last interval starting at or before s must reach e.
-LSQ_HD bool covered_contains(const Tables &T, uint32_t chrom, int32_t s, int32_t e) {
-    uint32_t lo = LSQ_LD(T.cov_off + chrom);
-    uint32_t i = bucket_upper_bound(T.cov_start, T.cov_off, T.cov_bkt_off, T.cov_bkt, T.cov_shift, chrom, s);
-    return i > lo && LSQ_LD(T.cov_end + i - 1) >= e;
+// Piece containing position x on chromosome c (index into T.pinfo), or 0xFFFFFFFF when x lies
+// before the first piece.  One load of two adjacent bucket ranks, then a short scan over
+// consecutive 16-byte PieceInfo records (a binary search when a bucket is unusually crowded).
+LSQ_HD uint32_t find_piece(const Tables &T, uint32_t c, int32_t x, PieceInfo &out) {
+    const uint32_t lo = LSQ_LD(T.bp_chrom_off + c), hi = LSQ_LD(T.bp_chrom_off + c + 1);
+    uint32_t i = lo, j = hi;
+    if (x >= 0) {
+        const uint32_t b0 = LSQ_LD(T.bp_bkt_off + c), nb = LSQ_LD(T.bp_bkt_off + c + 1) - b0 - 1u;
+        const uint32_t b = (uint32_t)x >> T.bp_shift;
+        if (b >= nb) {
+            i = j = hi;
+        } else {
+            i = LSQ_LD(T.bp_bkt + b0 + b);
+            j = LSQ_LD(T.bp_bkt + b0 + b + 1);
+        }
+    }
+    // number of pieces with pos <= x, searched in [i, j)
+    if (j - i > 8u) {
+        while (i < j) {
+            const uint32_t mid = (i + j) >> 1;
+            if (LSQ_LD(&T.pinfo[mid].pos) <= x) i = mid + 1;
+            else j = mid;
+        }
+    } else {
+        while (i < j && LSQ_LD(&T.pinfo[i].pos) <= x) ++i;
+    }
+    if (i == lo) return 0xFFFFFFFFu;
+    const uint4 raw = LSQ_LD(reinterpret_cast<const uint4 *>(T.pinfo + (i - 1)));
+    out.pos = (int32_t)raw.x;
+    out.cov_end = (int32_t)raw.y;
+    out.stab_off = raw.z;
+    out.stab_n = raw.w;
+    return i - 1;
 }
 
 // In-place "erase [b,e) then optionally insert v at b" on one component (.x or .y) of an int2 list.
@@ -153,13 +167,31 @@ LSQ_HD FilteredRead filter_read(const FilterParams &P, uint64_t r, int2 *work) {
     uint32_t n = 0;
     int2 first = make_int2(0, 0);
     work += base;
+    uint32_t first_piece = 0xFFFFFFFFu;  // piece of `first` when it was found while filtering
+    PieceInfo first_pi;
+    first_pi.pos = 0;
+    first_pi.cov_end = 0;
+    first_pi.stab_off = 0;
+    first_pi.stab_n = 0;
+    bool first_valid = false;
     for (uint32_t j = 0; j < nraw; ++j) {
         int2 b = LSQ_LD(P.blk + base + j);
         uint32_t cs = mixed ? LSQ_LD(P.blk_cs + base + j) : cs0;
         uint32_t c = LSQ_LD(P.chrom_remap + (cs & 0xFFFFu));
         bool keep;
-        if (!(b.x < b.y)) keep = true;  // a nil block is "contained" (interval_list.hpp:398-401)
-        else keep = (c != 0xFFFFFFFFu) && covered_contains(T, c, b.x, b.y);
+        PieceInfo pi;
+        uint32_t pidx = 0xFFFFFFFFu;
+        if (!(b.x < b.y)) {
+            keep = true;  // a nil block is "contained" (interval_list.hpp:398-401)
+        } else {
+            // contains_interval (interval_list.hpp:396-422): the covered region holding the block
+            // start must reach the block end
+            keep = false;
+            if (c != 0xFFFFFFFFu) {
+                pidx = find_piece(T, c, b.x, pi);
+                keep = pidx != 0xFFFFFFFFu && pi.cov_end >= b.y;
+            }
+        }
         if (!keep) continue;
         registered = true;
         chrom = c;
@@ -169,6 +201,9 @@ LSQ_HD FilteredRead filter_read(const FilterParams &P, uint64_t r, int2 *work) {
             first = b;
             last_end = b.y;
             n = 1;
+            first_piece = pidx;
+            first_pi = pi;
+            first_valid = true;
             if (nraw > 1) work[0] = b;
         } else if (b.x >= last_end) {
             if (b.x == last_end) {  // starts where the last interval ends: the two fuse
@@ -182,6 +217,7 @@ LSQ_HD FilteredRead filter_read(const FilterParams &P, uint64_t r, int2 *work) {
             }
         } else {  // out of order or overlapping: general list update
             n = list_add(work, n, b.x, b.y);
+            first_valid = first_valid && work[0].x == first.x;
             first = work[0];
             last_end = work[n - 1].y;
         }
@@ -189,14 +225,15 @@ LSQ_HD FilteredRead filter_read(const FilterParams &P, uint64_t r, int2 *work) {
     out.n = n;
     out.first = first;
     if (registered && n > 0 && chrom != 0xFFFFFFFFu) {
-        uint32_t lo = LSQ_LD(T.bp_chrom_off + chrom);
-        uint32_t p = bucket_upper_bound(T.bp_pos, T.bp_chrom_off, T.bp_bkt_off, T.bp_bkt, T.bp_shift, chrom, first.x);
-        if (p > lo) {
-            --p;
-            if (LSQ_LD(T.stab_off + p + 1) > LSQ_LD(T.stab_off + p)) {
-                out.key = (p << 1) | (n > 1 ? 1u : 0u);
-                out.at_piece_start = LSQ_LD(T.bp_pos + p) == first.x ? 1u : 0u;
-            }
+        // the read's chromosome is that of the LAST registered block; the piece found while
+        // filtering is reused when it was looked up on that chromosome for this very start
+        uint32_t p = first_piece;
+        PieceInfo pi = first_pi;
+        const uint32_t c_first = LSQ_LD(P.chrom_remap + ((mixed ? LSQ_LD(P.blk_cs + base) : cs0) & 0xFFFFu));
+        if (!first_valid || mixed || c_first != chrom) p = find_piece(T, chrom, first.x, pi);
+        if (p != 0xFFFFFFFFu && pi.stab_n > 0) {
+            out.key = (p << 1) | (n > 1 ? 1u : 0u);
+            out.at_piece_start = pi.pos == first.x ? 1u : 0u;
         }
     }
     return out;

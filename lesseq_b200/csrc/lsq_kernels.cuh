@@ -21,9 +21,12 @@ namespace lsq {
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
 __global__ void __launch_bounds__(256) lsq_filter_kernel(FilterParams P, int2 *__restrict__ work) {
+    __shared__ uint32_t s_need[8], s_kept[8];
+    __shared__ unsigned long long s_base;
     const Tables &T = P.T;
     const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool in_range = r < P.n_reads;
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
     FilteredRead fr;
     fr.n = 0;
     fr.key = KEY_DROPPED(T);
@@ -32,27 +35,38 @@ __global__ void __launch_bounds__(256) lsq_filter_kernel(FilterParams P, int2 *_
     fr.at_piece_start = 0;
     if (in_range) fr = filter_read(P, r, work);
     const bool kept = fr.key != KEY_DROPPED(T);
-    // warp-aggregated allocation of ext entries (n slots for reads with n >= 2 kept blocks)
+    // allocation of ext entries (n slots for reads with n >= 2 kept blocks): warp scan, block scan
+    // over the 8 warp totals, ONE global atomic per block for the cursor and one for the kept count
     const uint32_t need = (kept && fr.n >= 2) ? fr.n : 0u;
     uint32_t incl = need;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-        if (lane_id() >= (uint32_t)d) incl += v;
+        const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= (uint32_t)d) incl += v;
     }
-    const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-    unsigned long long ext_base = 0;
-    if (lane_id() == 31 && total) ext_base = atomicAdd(P.counters + 1, (unsigned long long)total);
-    ext_base = __shfl_sync(0xFFFFFFFFu, ext_base, 31);
     const unsigned kept_mask = __ballot_sync(0xFFFFFFFFu, kept);
-    if (lane_id() == 0 && kept_mask) atomicAdd(P.counters + 0, (unsigned long long)__popc(kept_mask));
+    if (lane == 31) s_need[warp] = incl;
+    if (lane == 0) s_kept[warp] = (uint32_t)__popc(kept_mask);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0, k = 0;
+        for (int w = 0; w < 8; ++w) {
+            const uint32_t t = s_need[w];
+            s_need[w] = tot;
+            tot += t;
+            k += s_kept[w];
+        }
+        s_base = tot ? atomicAdd(P.counters + 1, (unsigned long long)tot) : 0ull;
+        if (k) atomicAdd(P.counters + 0, (unsigned long long)k);
+    }
+    __syncthreads();
     if (!in_range) return;
     ReadRec rec;
     rec.x = (uint32_t)fr.first.x;
     rec.y = (uint32_t)fr.first.y;
     rec.w = pack_rec_w(fr.n, fr.at_piece_start, fr.strand);
     if (need) {
-        const uint32_t off = (uint32_t)(ext_base + incl - need);
+        const uint32_t off = (uint32_t)(s_base + s_need[warp] + incl - need);
         const uint32_t base = __ldg(P.blk_off + r);
         P.ext[off] = make_int2((int32_t)(uint32_t)r, (int32_t)fr.n);
         for (uint32_t i = 1; i < fr.n; ++i) P.ext[off + i] = work[base + i];
@@ -86,63 +100,90 @@ __device__ __forceinline__ void bump_class(const CountParams &P, const EvHdr &h,
     }
 }
 
-// Count kernel.  Reads arrive sorted by (stab piece, multi-block flag), so the 32 reads of a warp
-// nearly always share one piece and therefore one list of stab entries: the entry loop is
-// warp-uniform, per-class counts are formed with __ballot_sync/__popc and one lane issues the
-// global reduction.  A CTA works on chunks of COUNT_CHUNK consecutive reads; the stab entries and
-// offsets of the chunk's piece range are contiguous in memory and are staged in shared memory
-// with two bulk async copies (TMA, mbarrier completion) when they fit, else read through L1/L2.
+// Count kernel.  Reads arrive sorted by (stab piece, multi-block flag): a warp holds a few RUNS of
+// reads with the same key.  Every lane evaluates its own read against the j-th stab entry of its
+// own piece (lanes of a run share the entry, so the loads broadcast); per-class counts of a run
+// are formed with __ballot_sync/__popc restricted to the run's lane mask, the matched bases with a
+// segmented shuffle reduction, and the run's head lane issues the global reductions.
+//
+// A CTA works on chunks of COUNT_CHUNK consecutive reads.  The stab entries and offsets of a
+// chunk's piece range are contiguous in memory and are staged in shared memory by bulk async
+// copies (TMA) one chunk ahead: full[stage] completes when the bytes have landed, empty[stage]
+// when all warps have released the stage.  Chunks whose tables do not fit are read through L1/L2.
 constexpr int COUNT_BLOCK = 256;
+constexpr int COUNT_WARPS = COUNT_BLOCK / 32;
 constexpr int COUNT_ITEMS = 8;
 constexpr int COUNT_CHUNK = COUNT_BLOCK * COUNT_ITEMS;
-constexpr int COUNT_MAX_ENT = 512;      // staged stab entries (16 KB)
-constexpr int COUNT_MAX_PIECES = 1016;  // staged offsets (+8 slack words for 16-byte alignment)
+constexpr int COUNT_MAX_ENT = 384;     // staged stab entries per stage (12 KB)
+constexpr int COUNT_MAX_OFF = 1024;    // staged offsets per stage (4 KB)
+
+struct ChunkTables {
+    uint32_t e0, e1;   // stab entry range
+    uint32_t pa, noff; // 16-byte aligned offset slice
+    bool staged;
+};
+
+__device__ __forceinline__ ChunkTables chunk_tables(const CountParams &P, unsigned long long base,
+                                                    unsigned long long end) {
+    ChunkTables c;
+    const uint32_t pf = __ldg(P.g_key + base) >> 1, pl = __ldg(P.g_key + end - 1) >> 1;
+    c.e0 = __ldg(P.T.stab_off + pf);
+    c.e1 = __ldg(P.T.stab_off + pl + 1);
+    c.pa = pf & ~3u;
+    c.noff = ((pl + 2 - c.pa) + 3u) & ~3u;
+    c.staged = (c.e1 - c.e0) <= (uint32_t)COUNT_MAX_ENT && c.noff <= (uint32_t)COUNT_MAX_OFF && c.e1 > c.e0;
+    return c;
+}
 
 __global__ void __launch_bounds__(COUNT_BLOCK) lsq_count_kernel(CountParams P) {
-    __shared__ __align__(128) StabEntry s_ent[COUNT_MAX_ENT];
-    __shared__ __align__(16) uint32_t s_off[COUNT_MAX_PIECES + 8];
-    __shared__ __align__(8) uint64_t s_bar;
-    __shared__ uint32_t s_info[4];  // staged?, first entry, first (aligned) piece
+    __shared__ __align__(128) StabEntry s_ent[2][COUNT_MAX_ENT];
+    __shared__ __align__(16) uint32_t s_off[2][COUNT_MAX_OFF];
+    __shared__ __align__(8) uint64_t s_full[2], s_empty[2];
     const Tables &T = P.T;
     const unsigned long long n_kept = P.counters[0];
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+    const bool producer = threadIdx.x == 0;
+    if (producer) {
+        mbar_init(&s_full[0], 1);
+        mbar_init(&s_full[1], 1);
+        mbar_init(&s_empty[0], COUNT_WARPS);
+        mbar_init(&s_empty[1], COUNT_WARPS);
+    }
     __syncthreads();
-    uint32_t phase = 0;
-    unsigned long long my_valid = 0;
     const unsigned long long n_chunks = (n_kept + COUNT_CHUNK - 1) / COUNT_CHUNK;
-    for (unsigned long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    auto issue = [&](unsigned long long chunk, uint32_t stage) {  // producer only
         const unsigned long long base = chunk * COUNT_CHUNK;
         const unsigned long long end = min(base + (unsigned long long)COUNT_CHUNK, n_kept);
-        if (threadIdx.x == 0) {
-            const uint32_t pf = __ldg(P.g_key + base) >> 1, pl = __ldg(P.g_key + end - 1) >> 1;
-            const uint32_t e0 = __ldg(T.stab_off + pf), e1 = __ldg(T.stab_off + pl + 1);
-            const uint32_t pa = pf & ~3u;  // 16-byte aligned start of the offset slice
-            const uint32_t noff = ((pl + 2 - pa) + 3u) & ~3u;
-            const bool staged = (e1 - e0) <= (uint32_t)COUNT_MAX_ENT && noff <= (uint32_t)(COUNT_MAX_PIECES + 8) && e1 > e0;
-            s_info[0] = staged;
-            s_info[1] = e0;
-            s_info[2] = pa;
-            if (staged) {
-                const uint32_t ebytes = (e1 - e0) * (uint32_t)sizeof(StabEntry), obytes = noff * 4u;
-                mbar_expect_tx(&s_bar, ebytes + obytes);
-                bulk_g2s(s_ent, T.stab + e0, ebytes, &s_bar);
-                bulk_g2s(s_off, T.stab_off + pa, obytes, &s_bar);
-            }
+        const ChunkTables c = chunk_tables(P, base, end);
+        if (c.staged) {
+            const uint32_t ebytes = (c.e1 - c.e0) * (uint32_t)sizeof(StabEntry), obytes = c.noff * 4u;
+            mbar_expect_tx(&s_full[stage], ebytes + obytes);
+            bulk_g2s(s_ent[stage], T.stab + c.e0, ebytes, &s_full[stage]);
+            bulk_g2s(s_off[stage], T.stab_off + c.pa, obytes, &s_full[stage]);
+        } else {
+            mbar_arrive(&s_full[stage]);
         }
-        __syncthreads();
-        const bool staged = s_info[0] != 0;
-        const StabEntry *ent = T.stab;
-        const uint32_t *off = T.stab_off;
-        if (staged) {
-            mbar_wait(&s_bar, phase);
-            phase ^= 1u;
-            ent = s_ent - s_info[1];
-            off = s_off - s_info[2];
+    };
+    if (producer && blockIdx.x < n_chunks) issue(blockIdx.x, 0);
+    unsigned long long my_valid = 0;
+    uint32_t j = 0;
+    for (unsigned long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x, ++j) {
+        const uint32_t stage = j & 1u;
+        if (producer && chunk + gridDim.x < n_chunks) {
+            const uint32_t ns = (j + 1u) & 1u;
+            if (j + 1u >= 2u) mbar_wait(&s_empty[ns], (((j + 1u) >> 1) - 1u) & 1u);
+            issue(chunk + gridDim.x, ns);
         }
+        const unsigned long long base = chunk * COUNT_CHUNK;
+        const unsigned long long end = min(base + (unsigned long long)COUNT_CHUNK, n_kept);
+        const ChunkTables ct = chunk_tables(P, base, end);
+        mbar_wait(&s_full[stage], (j >> 1) & 1u);
+        const StabEntry *ent = ct.staged ? s_ent[stage] - ct.e0 : T.stab;
+        const uint32_t *off = ct.staged ? s_off[stage] - ct.pa : T.stab_off;
         for (int it = 0; it < COUNT_ITEMS; ++it) {
-            const unsigned long long i = base + (unsigned long long)((warp * COUNT_ITEMS + it) * 32u + lane);
-            if (base + (unsigned long long)((warp * COUNT_ITEMS + it) * 32u) >= end) break;  // warp-uniform
+            const unsigned long long w0 = base + (unsigned long long)((warp * COUNT_ITEMS + it) * 32u);
+            if (w0 >= end) break;  // warp-uniform
+            const unsigned long long i = w0 + lane;
             const bool act = i < end;
             uint32_t key = 0xFFFFFFFFu;
             ReadView rv;
@@ -150,7 +191,7 @@ __global__ void __launch_bounds__(COUNT_BLOCK) lsq_count_kernel(CountParams P) {
             rv.n = 1;
             rv.z = 0;
             rv.ext = nullptr;
-            uint32_t strand = 0;
+            uint32_t strand = 0, so = 0, nent = 0;
             bool at_start = false;
             if (act) {
                 key = __ldg(P.g_key + i);
@@ -161,58 +202,74 @@ __global__ void __launch_bounds__(COUNT_BLOCK) lsq_count_kernel(CountParams P) {
                 strand = rec.w >> 24;
                 at_start = (rec.w & REC_AT_PIECE_START) != 0;
                 if (rv.n > 1) rv.ext = P.ext + rec.z;
+                so = off[key >> 1];
+                nent = off[(key >> 1) + 1] - so;
             }
-            unsigned todo = __ballot_sync(0xFFFFFFFFu, act);
-            while (todo) {
-                const int leader = __ffs(todo) - 1;
-                const uint32_t k0 = __shfl_sync(0xFFFFFFFFu, key, leader);
-                const bool mine = act && key == k0;
-                todo &= ~__ballot_sync(0xFFFFFFFFu, mine);
-                const uint32_t piece = k0 >> 1;
-                const uint32_t so = off[piece], se = off[piece + 1];
-                for (uint32_t q = so; q < se; ++q) {
-                    const StabEntry en = ent[q];
-                    uint32_t cm32 = 0, ml = 0;
-                    uint64_t cm = 0;
-                    bool general = mine;
-                    if (mine && rv.n == 1 && (en.meta & SE_FAST)) {
+            // runs of equal keys: head lane, lane mask and end of the run
+            const uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, key, 1);
+            const bool head = lane == 0 || key != prev;
+            const unsigned heads = __ballot_sync(0xFFFFFFFFu, head);
+            const unsigned above = lane == 31 ? 0u : (heads >> (lane + 1));
+            const uint32_t run_end = above ? lane + (uint32_t)__ffs(above) : 32u;  // first lane of the next run
+            const unsigned run_mask = (run_end == 32u ? 0xFFFFFFFFu : ((1u << run_end) - 1u)) & ~((1u << lane) - 1u);
+            const uint32_t max_ent = __reduce_max_sync(0xFFFFFFFFu, nent);
+            for (uint32_t q = 0; q < max_ent; ++q) {
+                const bool has = q < nent;
+                uint64_t cm = 0;
+                uint32_t ml = 0, K = 0, slot_off = 0, x = 0;
+                if (has) {
+                    const StabEntry en = ent[so + q];
+                    K = en.K;
+                    slot_off = en.slot_off;
+                    x = en.x;
+                    bool general = true;
+                    if (rv.n == 1 && (en.meta & SE_FAST)) {
                         bool tie;
-                        cm32 = eval_fast(en, at_start, rv.b0.x, rv.b0.y, ml, tie);
-                        cm = cm32;
+                        cm = eval_fast(en, at_start, rv.b0.x, rv.b0.y, ml, tie);
                         general = tie;
                     }
                     if (general) {  // multi-block reads, wide / many-form events, long chains, tie-breaks
-                        const EvHdr h = T.hdr[en.x];
+                        const EvHdr h = T.hdr[x];
                         uint32_t total_len = (uint32_t)(rv.b0.y - rv.b0.x);
-                        for (uint32_t j = 1; j < rv.n; ++j) {
-                            const int2 b = __ldg(rv.ext + j);
-                            total_len += (uint32_t)(b.y - b.x);
+                        for (uint32_t b = 1; b < rv.n; ++b) {
+                            const int2 blk = __ldg(rv.ext + b);
+                            total_len += (uint32_t)(blk.y - blk.x);
                         }
                         cm = eval_pair(P, h, T.seg + h.seg_off, T.fmask + h.form_off, rv, strand, total_len, ml);
-                    }
-                    const unsigned vmask = __ballot_sync(0xFFFFFFFFu, cm != 0);
-                    if (vmask == 0) continue;
-                    if (en.K <= 2) {
-                        const uint32_t ncls = (1u << en.K) - 1u;
-                        for (uint32_t c = 1; c <= ncls; ++c) {
-                            const unsigned bm = __ballot_sync(0xFFFFFFFFu, cm == c);
-                            if (lane == 0 && bm)
-                                atomicAdd(P.slot_cnt + en.slot_off + c - 1u, (unsigned long long)__popc(bm));
+                        if (cm != 0 && K > 2) {  // rare: per-lane update of a large class table
+                            bump_class(P, h, cm);
+                            cm = 0x8000000000000000ull;  // counted; still contributes bases below
                         }
-                    } else if (cm != 0) {
-                        const EvHdr h = T.hdr[en.x];
-                        bump_class(P, h, cm);
+                    } else if (cm != 0 && K > 2) {
+                        atomicAdd(P.slot_cnt + slot_off + (uint32_t)(cm - 1ull), 1ull);
+                        cm = 0x8000000000000000ull;
                     }
-                    const uint32_t sum = __reduce_add_sync(0xFFFFFFFFu, ml);
-                    if (lane == 0) atomicAdd(P.bases + en.x, (unsigned long long)sum);
-                    my_valid += (cm != 0);
                 }
+                const unsigned b1 = __ballot_sync(0xFFFFFFFFu, cm == 1ull);
+                const unsigned b2 = __ballot_sync(0xFFFFFFFFu, cm == 2ull);
+                const unsigned b3 = __ballot_sync(0xFFFFFFFFu, cm == 3ull);
+                // matched bases of the run: segmented reduction towards the head lane
+                uint32_t v = ml;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t t = __shfl_down_sync(0xFFFFFFFFu, v, d);
+                    if (lane + (uint32_t)d < run_end) v += t;
+                }
+                if (head && has) {
+                    const uint32_t c1 = __popc(b1 & run_mask), c2 = __popc(b2 & run_mask), c3 = __popc(b3 & run_mask);
+                    if (c1) atomicAdd(P.slot_cnt + slot_off, (unsigned long long)c1);
+                    if (c2) atomicAdd(P.slot_cnt + slot_off + 1u, (unsigned long long)c2);
+                    if (c3) atomicAdd(P.slot_cnt + slot_off + 2u, (unsigned long long)c3);
+                    if (v) atomicAdd(P.bases + x, (unsigned long long)v);
+                }
+                my_valid += (cm != 0);
             }
         }
-        __syncthreads();  // every warp is done with the staged tables before the next chunk overwrites them
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[stage]);  // this warp no longer reads the stage
     }
-    const unsigned v = __reduce_add_sync(0xFFFFFFFFu, (unsigned)my_valid);
-    if (lane == 0 && v) atomicAdd(P.stats, (unsigned long long)v);
+    const unsigned vsum = __reduce_add_sync(0xFFFFFFFFu, (unsigned)my_valid);
+    if (lane == 0 && vsum) atomicAdd(P.stats, (unsigned long long)vsum);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -26,8 +26,9 @@ struct HostTables {
     std::vector<uint32_t> bp_chrom_off, stab_off, cov_off;
     std::vector<StabEntry> stab;
     std::vector<int32_t> bp_pos, cov_start, cov_end;
-    uint32_t bp_shift = 0, cov_shift = 0;
-    std::vector<uint32_t> bp_bkt_off, bp_bkt, cov_bkt_off, cov_bkt;
+    std::vector<PieceInfo> pinfo;
+    uint32_t bp_shift = 0;
+    std::vector<uint32_t> bp_bkt_off, bp_bkt;
 
     // Table view over the HOST arrays (CPU replay harness only).
     Tables host_view() const {
@@ -44,15 +45,12 @@ struct HostTables {
         T.pfx = pfx.data();
         T.tie_pool = tie.data();
         T.bp_chrom_off = bp_chrom_off.data();
-        T.bp_pos = bp_pos.data();
+        T.pinfo = pinfo.data();
         T.stab_off = stab_off.data();
         T.stab = stab.data();
         T.bp_shift = bp_shift;
-        T.cov_shift = cov_shift;
         T.bp_bkt_off = bp_bkt_off.data();
         T.bp_bkt = bp_bkt.data();
-        T.cov_bkt_off = cov_bkt_off.data();
-        T.cov_bkt = cov_bkt.data();
         T.cov_off = cov_off.data();
         T.cov_start = cov_start.data();
         T.cov_end = cov_end.data();
@@ -63,14 +61,14 @@ struct HostTables {
 // Bucket index over per-chromosome sorted coordinate arrays (CSR `off`): bucket b of a
 // chromosome covers positions [b << shift, (b+1) << shift) and stores the rank (global index)
 // of the first element >= b << shift; one extra bucket per chromosome closes the last range.
-// The shift is chosen so that there are about as many buckets as elements (at most 2^24).
+// The shift is chosen so that there are about four buckets per element (at most 2^25).
 inline void build_bucket_index(const std::vector<int32_t> &arr, const std::vector<uint32_t> &off, uint32_t &shift,
                                std::vector<uint32_t> &bkt_off, std::vector<uint32_t> &bkt) {
     const size_t nch = off.size() - 1;
     uint64_t span = 0;
     for (size_t c = 0; c < nch; ++c)
         if (off[c + 1] > off[c]) span += (uint64_t)std::max<int32_t>(arr[off[c + 1] - 1], 0) + 1;
-    uint64_t want = std::min<uint64_t>(std::max<uint64_t>(arr.size(), 1), 1ull << 24);
+    uint64_t want = std::min<uint64_t>(std::max<uint64_t>(4 * arr.size(), 1), 1ull << 25);
     shift = 0;
     while ((span >> shift) > want && shift < 30) ++shift;
     bkt_off.assign(nch + 1, 0);
@@ -278,8 +276,11 @@ inline int build_host_tables(const lsq_event_tables *t, HostTables &H, std::stri
             bp_chrom_off[ch] = (uint32_t)bp_pos.size();
             uint32_t first = ie;
             while (ie < E && t->ev_chrom[order[ie]] == ch) ++ie;
-            if (ie == first) continue;
             std::vector<int32_t> bps;
+            for (uint32_t q = t->cov_off[ch]; q < t->cov_off[ch + 1]; ++q) {
+                bps.push_back(t->cov_start[q]);
+                bps.push_back(t->cov_end[q]);
+            }
             for (uint32_t q = first; q < ie; ++q) {
                 bps.push_back(hdr[q].gs);
                 bps.push_back(hdr[q].ge + 1);
@@ -348,7 +349,19 @@ inline int build_host_tables(const lsq_event_tables *t, HostTables &H, std::stri
     H.cov_end.assign(t->cov_end, t->cov_end + H.cov_off.back());
     H.tie.assign(tie_pool.begin(), tie_pool.end());
     build_bucket_index(H.bp_pos, H.bp_chrom_off, H.bp_shift, H.bp_bkt_off, H.bp_bkt);
-    build_bucket_index(H.cov_start, H.cov_off, H.cov_shift, H.cov_bkt_off, H.cov_bkt);
+    H.pinfo.resize(H.bp_pos.size());
+    for (uint32_t ch = 0; ch < t->n_chroms; ++ch) {
+        const int32_t *cs = H.cov_start.data() + H.cov_off[ch], *ce = H.cov_end.data() + H.cov_off[ch];
+        const size_t nc = H.cov_off[ch + 1] - H.cov_off[ch];
+        for (uint32_t p = H.bp_chrom_off[ch]; p < H.bp_chrom_off[ch + 1]; ++p) {
+            PieceInfo &pi = H.pinfo[p];
+            pi.pos = H.bp_pos[p];
+            pi.stab_off = H.stab_off[p];
+            pi.stab_n = H.stab_off[p + 1] - H.stab_off[p];
+            size_t i = std::upper_bound(cs, cs + nc, pi.pos) - cs;
+            pi.cov_end = (i > 0 && ce[i - 1] > pi.pos) ? ce[i - 1] : INT32_MIN;
+        }
+    }
     H.slot_total = slot_total;
     H.E = E;
     H.F = (uint32_t)fmask.size();

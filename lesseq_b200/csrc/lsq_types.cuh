@@ -52,6 +52,17 @@ static_assert(sizeof(StabEntry) == 32, "StabEntry layout");
 constexpr uint32_t SE_FAST = 1u << 24;   // table-driven single-block evaluation is valid
 constexpr uint32_t SE_AT_GS = 1u << 25;  // the piece starts at the event start (tie-break possible)
 
+// Per-piece record read by the load filter: one 16-byte load answers "is this block start inside
+// a covered region, and up to where" as well as "which stab list does a read starting here get".
+// Pieces are cut by the covered-region boundaries too, so a piece is covered entirely or not.
+struct __align__(16) PieceInfo {
+    int32_t pos;        // first position of the piece
+    int32_t cov_end;    // end of the covered region containing the piece, INT32_MIN if uncovered
+    uint32_t stab_off;  // first stab entry
+    uint32_t stab_n;    // number of stab entries (0: reads starting here are no candidates)
+};
+static_assert(sizeof(PieceInfo) == 16, "PieceInfo layout");
+
 // Sorted read record (16 bytes), value type of the radix sort keyed by stab piece.
 //   x,y : first kept block [start,end)
 //   z   : n == 1 ? original read index : offset of the read's entry in ext[]
@@ -68,18 +79,16 @@ struct Tables {
     const uint32_t *pfx;
     const char *tie_pool;
     const uint32_t *bp_chrom_off;  // [n_chroms+1] piece range per chromosome
-    const int32_t *bp_pos;         // [n_pieces] first position of each stab piece
+    const PieceInfo *pinfo;        // [n_pieces] sorted by position within a chromosome
     const uint32_t *stab_off;      // [n_pieces+1]
     const StabEntry *stab;         // candidate events of each piece
     const uint32_t *cov_off;       // [n_chroms+1]
     const int32_t *cov_start, *cov_end;
     // bucket indexes: position >> shift -> rank of the bucket start in the sorted array, so a
     // lookup is one table load plus a short forward scan instead of a full binary search
-    uint32_t bp_shift, cov_shift;
+    uint32_t bp_shift;
     const uint32_t *bp_bkt_off;    // [n_chroms+1] first bucket of each chromosome
-    const uint32_t *bp_bkt;        // [buckets + n_chroms] rank within bp_pos
-    const uint32_t *cov_bkt_off;
-    const uint32_t *cov_bkt;       // rank within cov_start
+    const uint32_t *bp_bkt;        // [buckets + n_chroms] rank of the first piece starting in or after the bucket
 };
 
 struct FilterParams {
