@@ -444,12 +444,12 @@ int lsq_count(lsq_ctx *c) {
         unsigned long long *counters = c->d_counters.as<unsigned long long>() + (size_t)m * 4;
         LSQ_CUDA(c->d_rkey.ensure(std::max<size_t>(n, 1) * 4));
         LSQ_CUDA(c->d_skey.ensure(std::max<size_t>(n, 1) * 4));
-        LSQ_CUDA(c->d_rec.ensure(std::max<size_t>(n, 1) * 16));
-        LSQ_CUDA(c->d_srec.ensure(std::max<size_t>(n, 1) * 16));
+        LSQ_CUDA(c->d_rec.ensure(std::max<size_t>(n, 1) * sizeof(lsq::ReadRec)));
+        LSQ_CUDA(c->d_srec.ensure(std::max<size_t>(n, 1) * sizeof(lsq::ReadRec)));
         LSQ_CUDA(c->d_work.ensure(std::max<size_t>(nb, 1) * 8));
-        LSQ_CUDA(c->d_ext.ensure(std::max<size_t>(nb, 1) * 8));
+        LSQ_CUDA(c->d_ext.ensure(std::max<size_t>(nb + n, 1) * 8));
         size_t cub_bytes = 0;
-        const int end_bit = (int)bits_for(T.n_pieces << 1);  // keys 0 .. 2 * n_pieces (= dropped)
+        const int end_bit = (int)bits_for(T.n_pieces * 2u);  // keys 0 .. 2 * n_pieces (= dropped)
         cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, c->d_rkey.as<uint32_t>(), c->d_skey.as<uint32_t>(),
                                         c->d_rec.as<lsq::ReadRec>(), c->d_srec.as<lsq::ReadRec>(), (int64_t)n, 0,
                                         end_bit, s);
@@ -516,9 +516,9 @@ int lsq_count(lsq_ctx *c) {
         tm.reads_in += n;
         tm.reads_kept += c->h_counters[(size_t)m * 4 + 0];
         tm.pairs_valid += c->h_counters[(size_t)m * 4 + 2];
-        // algorithmic bytes of the count kernel: key (4) + record (16) per kept read, plus one
-        // 8-byte entry header and 8 bytes per further block of multi-block reads
-        tm.count_bytes += c->h_counters[(size_t)m * 4 + 0] * 20ull + c->h_counters[(size_t)m * 4 + 1] * 8ull;
+        // algorithmic bytes of the count kernel: key (4) + record (8) per kept read, plus the ext
+        // entry (8-byte header + 8 bytes per kept block) of every GENERAL-class read
+        tm.count_bytes += c->h_counters[(size_t)m * 4 + 0] * 12ull + c->h_counters[(size_t)m * 4 + 1] * 8ull;
     }
     c->counted = true;
     c->finalized = false;

@@ -125,21 +125,21 @@ LSQ_HD uint32_t list_add(int2 *L, uint32_t n, int32_t s, int32_t e) {
 }
 
 
-// ReadRec::w packing: bits 0-22 kept blocks, bit 23 "start is the first position of its piece",
-// bits 24-31 file strand id.
-constexpr uint32_t REC_N_MASK = 0x7FFFFFu;
-constexpr uint32_t REC_AT_PIECE_START = 1u << 23;
-LSQ_HD uint32_t pack_rec_w(const uint32_t n, const uint32_t at_start, const uint32_t strand) {
-    return (strand << 24) | (at_start ? REC_AT_PIECE_START : 0u) | (n & REC_N_MASK);
+// Read classes (see ReadRec): the table-driven evaluator handles FAST reads, everything else
+// (several kept blocks, a start on the first position of a piece -- the only place the
+// lower_bound tie-break can apply --, or an over-long block) goes through the general walk.
+constexpr uint32_t FAST_MAX_LEN = 0xFFFFu;
+LSQ_HD bool is_fast_read(uint32_t n, uint32_t at_piece_start, int2 first) {
+    return n == 1u && !at_piece_start && (uint32_t)(first.y - first.x) <= FAST_MAX_LEN;
 }
 
 // Sort key of a read that is a candidate of no event: one past the largest real key.
-LSQ_HD uint32_t KEY_DROPPED(const Tables &T) { return T.n_pieces << 1; }
+LSQ_HD uint32_t KEY_DROPPED(const Tables &T) { return T.n_pieces * 2u; }
 
 // Result of the per-read load filter.
 struct FilteredRead {
     uint32_t n;       // kept intervals (0: read dropped)
-    uint32_t key;     // (stab piece << 1) | (n > 1), or KEY_DROPPED when the read is no candidate
+    uint32_t key;     // piece (FAST class), n_pieces + piece (GENERAL), KEY_DROPPED when no candidate
     int2 first;       // first kept interval
     uint32_t strand;  // file strand id of the last registered block
     uint32_t at_piece_start;  // 1 when the first kept start is the first position of its piece
@@ -232,8 +232,8 @@ LSQ_HD FilteredRead filter_read(const FilterParams &P, uint64_t r, int2 *work) {
         const uint32_t c_first = LSQ_LD(P.chrom_remap + ((mixed ? LSQ_LD(P.blk_cs + base) : cs0) & 0xFFFFu));
         if (!first_valid || mixed || c_first != chrom) p = find_piece(T, chrom, first.x, pi);
         if (p != 0xFFFFFFFFu && pi.stab_n > 0) {
-            out.key = (p << 1) | (n > 1 ? 1u : 0u);
             out.at_piece_start = pi.pos == first.x ? 1u : 0u;
+            out.key = is_fast_read(n, out.at_piece_start, first) ? p : T.n_pieces + p;
         }
     }
     return out;
@@ -245,11 +245,11 @@ LSQ_HD FilteredRead filter_read(const FilterParams &P, uint64_t r, int2 *work) {
 struct ReadView {
     int2 b0;          // first kept block
     uint32_t n;       // kept blocks
-    uint32_t z;       // n == 1: read index; else offset of the ext entry
-    const int2 *ext;  // ext entry when n > 1: ext[0] = {read index, n}, ext[j] = block j
-    LSQ_HD int2 block(uint32_t j) const { return j == 0 ? b0 : LSQ_LD(ext + j); }
-    LSQ_HD int32_t last_end() const { return n == 1 ? b0.y : LSQ_LD(ext + n - 1).y; }
-    LSQ_HD uint32_t read_index() const { return n == 1 ? z : (uint32_t)LSQ_LD(ext).x; }
+    uint32_t ridx;    // original read index (names the read: "read-<line_num[ridx]>")
+    const int2 *blk;  // kept blocks 0..n-1 (GENERAL class: inside the ext entry)
+    LSQ_HD int2 block(uint32_t j) const { return j == 0 ? b0 : LSQ_LD(blk + j); }
+    LSQ_HD int32_t last_end() const { return n == 1 ? b0.y : LSQ_LD(blk + n - 1).y; }
+    LSQ_HD uint32_t read_index() const { return ridx; }
 };
 
 // "read-<N>" < name for tie mode 2: the name is "read-" + suffix, so compare the decimal digits
@@ -366,22 +366,13 @@ LSQ_HD bool walk_wide(const ReadView &rv, const int2 *seg, uint32_t S,
     return ok && last_added != 0xFFFFFFFFu;
 }
 
-// Table-driven evaluation of a SINGLE-BLOCK read [s,e) against a FAST stab entry: the block
-// starts inside chain segment 0; it is matched up to min(e, end of the chain) and covers chain
-// segments 0..i where c[i] is the first chain end >= e.  Same result as walk_mask + the
-// compatibility test + the validity rule of eval_pair, without touching the event tables.
-// Returns the form mask of a valid read (0 otherwise); `tie` tells the caller that the start
-// equals the event start and the end reaches the event end, i.e. the rare lower_bound tie-break
-// must be resolved with the full event header.
-LSQ_HD uint32_t eval_fast(const StabEntry &en, bool at_piece_start, int32_t s, int32_t e, uint32_t &matched,
-                          bool &tie) {
-    tie = false;
+// Table-driven evaluation of a FAST-class read [s,e) against a FAST stab entry: the block starts
+// inside chain segment 0 (not on the event start, so no tie-break applies); it is matched up to
+// min(e, end of the chain) and covers chain segments 0..i where c[i] is the first chain end >= e.
+// Same result as walk_mask + the compatibility test + the validity rule of eval_pair, without
+// touching the event tables.  Returns the form mask of a valid read (0 otherwise).
+LSQ_HD uint32_t eval_fast(const StabEntry &en, int32_t s, int32_t e, uint32_t &matched) {
     matched = 0;
-    if ((en.meta & SE_AT_GS) && at_piece_start) {
-        if (e < en.ge) return 0;  // key (start, end) sorts before the probe (gs, ge): skipped
-        tie = true;
-        return 0;
-    }
     const uint32_t nchain = (en.meta >> 16) & 3u;
     const int32_t cend = en.c[nchain - 1];
     uint32_t cm;

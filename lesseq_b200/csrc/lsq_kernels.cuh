@@ -35,9 +35,10 @@ __global__ void __launch_bounds__(256) lsq_filter_kernel(FilterParams P, int2 *_
     fr.at_piece_start = 0;
     if (in_range) fr = filter_read(P, r, work);
     const bool kept = fr.key != KEY_DROPPED(T);
-    // allocation of ext entries (n slots for reads with n >= 2 kept blocks): warp scan, block scan
-    // over the 8 warp totals, ONE global atomic per block for the cursor and one for the kept count
-    const uint32_t need = (kept && fr.n >= 2) ? fr.n : 0u;
+    const bool general = kept && fr.key >= T.n_pieces;
+    // allocation of ext entries (1 + n slots per GENERAL read): warp scan, block scan over the 8
+    // warp totals, ONE global atomic per block for the cursor and one for the kept count
+    const uint32_t need = general ? fr.n + 1u : 0u;
     uint32_t incl = need;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -45,34 +46,40 @@ __global__ void __launch_bounds__(256) lsq_filter_kernel(FilterParams P, int2 *_
         if (lane >= (uint32_t)d) incl += v;
     }
     const unsigned kept_mask = __ballot_sync(0xFFFFFFFFu, kept);
+    const unsigned gen_mask = __ballot_sync(0xFFFFFFFFu, general);
     if (lane == 31) s_need[warp] = incl;
-    if (lane == 0) s_kept[warp] = (uint32_t)__popc(kept_mask);
+    if (lane == 0) s_kept[warp] = (uint32_t)__popc(kept_mask) | ((uint32_t)__popc(gen_mask) << 16);
     __syncthreads();
     if (threadIdx.x == 0) {
-        uint32_t tot = 0, k = 0;
+        uint32_t tot = 0, k = 0, g = 0;
         for (int w = 0; w < 8; ++w) {
             const uint32_t t = s_need[w];
             s_need[w] = tot;
             tot += t;
-            k += s_kept[w];
+            k += s_kept[w] & 0xFFFFu;
+            g += s_kept[w] >> 16;
         }
         s_base = tot ? atomicAdd(P.counters + 1, (unsigned long long)tot) : 0ull;
         if (k) atomicAdd(P.counters + 0, (unsigned long long)k);
+        if (g) atomicAdd(P.counters + 3, (unsigned long long)g);
     }
     __syncthreads();
     if (!in_range) return;
     ReadRec rec;
-    rec.x = (uint32_t)fr.first.x;
-    rec.y = (uint32_t)fr.first.y;
-    rec.w = pack_rec_w(fr.n, fr.at_piece_start, fr.strand);
-    if (need) {
+    if (general) {
         const uint32_t off = (uint32_t)(s_base + s_need[warp] + incl - need);
-        const uint32_t base = __ldg(P.blk_off + r);
-        P.ext[off] = make_int2((int32_t)(uint32_t)r, (int32_t)fr.n);
-        for (uint32_t i = 1; i < fr.n; ++i) P.ext[off + i] = work[base + i];
-        rec.z = off;
+        P.ext[off] = make_int2((int32_t)(uint32_t)r, (int32_t)((fr.strand << 24) | (fr.n & 0xFFFFFFu)));
+        if (fr.n == 1) {
+            P.ext[off + 1] = fr.first;
+        } else {
+            const uint32_t base = __ldg(P.blk_off + r);
+            for (uint32_t i = 0; i < fr.n; ++i) P.ext[off + 1 + i] = work[base + i];
+        }
+        rec.x = off;
+        rec.y = 0;
     } else {
-        rec.z = (uint32_t)r;
+        rec.x = (uint32_t)fr.first.x;
+        rec.y = (uint32_t)(fr.first.y - fr.first.x) | (fr.strand << 16);
     }
     P.rkey[r] = fr.key;
     P.rec[r] = rec;
@@ -126,13 +133,44 @@ struct ChunkTables {
 __device__ __forceinline__ ChunkTables chunk_tables(const CountParams &P, unsigned long long base,
                                                     unsigned long long end) {
     ChunkTables c;
-    const uint32_t pf = __ldg(P.g_key + base) >> 1, pl = __ldg(P.g_key + end - 1) >> 1;
+    // a chunk that straddles the FAST / GENERAL class boundary wraps around in piece space and
+    // is simply not staged (pl < pf makes the sizes below huge)
+    const uint32_t kf = __ldg(P.g_key + base), kl = __ldg(P.g_key + end - 1), np = P.T.n_pieces;
+    const uint32_t pf = kf >= np ? kf - np : kf, pl = kl >= np ? kl - np : kl;
     c.e0 = __ldg(P.T.stab_off + pf);
     c.e1 = __ldg(P.T.stab_off + pl + 1);
     c.pa = pf & ~3u;
     c.noff = ((pl + 2 - c.pa) + 3u) & ~3u;
-    c.staged = (c.e1 - c.e0) <= (uint32_t)COUNT_MAX_ENT && c.noff <= (uint32_t)COUNT_MAX_OFF && c.e1 > c.e0;
+    c.staged = pl >= pf && (c.e1 - c.e0) <= (uint32_t)COUNT_MAX_ENT && c.noff <= (uint32_t)COUNT_MAX_OFF && c.e1 > c.e0;
     return c;
+}
+
+// One q-step of the run aggregation: per-class counts of each run via ballots restricted to the
+// run's lane mask, matched bases via a segmented shuffle reduction, reductions by the head lane.
+__device__ __forceinline__ void aggregate_runs(const CountParams &P, uint32_t lane, bool head_has, unsigned run_mask,
+                                               uint32_t run_end, bool single_run, uint32_t cm, uint32_t ml,
+                                               uint32_t slot_off, uint32_t x) {
+    const unsigned b1 = __ballot_sync(0xFFFFFFFFu, cm == 1u);
+    const unsigned b2 = __ballot_sync(0xFFFFFFFFu, cm == 2u);
+    const unsigned b3 = __ballot_sync(0xFFFFFFFFu, cm == 3u);
+    uint32_t v;
+    if (single_run) {  // warp-uniform: the whole warp is one run
+        v = __reduce_add_sync(0xFFFFFFFFu, ml);
+    } else {
+        v = ml;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_down_sync(0xFFFFFFFFu, v, d);
+            if (lane + (uint32_t)d < run_end) v += t;
+        }
+    }
+    if (head_has) {
+        const uint32_t c1 = __popc(b1 & run_mask), c2 = __popc(b2 & run_mask), c3 = __popc(b3 & run_mask);
+        if (c1) atomicAdd(P.slot_cnt + slot_off, (unsigned long long)c1);
+        if (c2) atomicAdd(P.slot_cnt + slot_off + 1u, (unsigned long long)c2);
+        if (c3) atomicAdd(P.slot_cnt + slot_off + 2u, (unsigned long long)c3);
+        if (v) atomicAdd(P.bases + x, (unsigned long long)v);
+    }
 }
 
 __global__ void __launch_bounds__(COUNT_BLOCK) lsq_count_kernel(CountParams P) {
@@ -177,7 +215,8 @@ __global__ void __launch_bounds__(COUNT_BLOCK) lsq_count_kernel(CountParams P) {
         const unsigned long long base = chunk * COUNT_CHUNK;
         const unsigned long long end = min(base + (unsigned long long)COUNT_CHUNK, n_kept);
         const ChunkTables ct = chunk_tables(P, base, end);
-        mbar_wait(&s_full[stage], (j >> 1) & 1u);
+        if (lane == 0) mbar_wait(&s_full[stage], (j >> 1) & 1u);  // one poller per warp
+        __syncwarp();
         const StabEntry *ent = ct.staged ? s_ent[stage] - ct.e0 : T.stab;
         const uint32_t *off = ct.staged ? s_off[stage] - ct.pa : T.stab_off;
         for (int it = 0; it < COUNT_ITEMS; ++it) {
@@ -185,84 +224,103 @@ __global__ void __launch_bounds__(COUNT_BLOCK) lsq_count_kernel(CountParams P) {
             if (w0 >= end) break;  // warp-uniform
             const unsigned long long i = w0 + lane;
             const bool act = i < end;
-            uint32_t key = 0xFFFFFFFFu;
-            ReadView rv;
-            rv.b0 = make_int2(0, 0);
-            rv.n = 1;
-            rv.z = 0;
-            rv.ext = nullptr;
-            uint32_t strand = 0, so = 0, nent = 0;
-            bool at_start = false;
+            uint32_t key = 0xFFFFFFFFu, so = 0, nent = 0;
+            ReadRec rec = make_uint2(0u, 0u);
             if (act) {
                 key = __ldg(P.g_key + i);
-                const ReadRec rec = __ldg(P.g_rec + i);
-                rv.b0 = make_int2((int32_t)rec.x, (int32_t)rec.y);
-                rv.n = rec.w & REC_N_MASK;
-                rv.z = rec.z;
-                strand = rec.w >> 24;
-                at_start = (rec.w & REC_AT_PIECE_START) != 0;
-                if (rv.n > 1) rv.ext = P.ext + rec.z;
-                so = off[key >> 1];
-                nent = off[(key >> 1) + 1] - so;
+                rec = __ldg(P.g_rec + i);
+                const uint32_t piece = key >= T.n_pieces ? key - T.n_pieces : key;
+                so = off[piece];
+                nent = off[piece + 1] - so;
             }
             // runs of equal keys: head lane, lane mask and end of the run
             const uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, key, 1);
             const bool head = lane == 0 || key != prev;
             const unsigned heads = __ballot_sync(0xFFFFFFFFu, head);
+            const bool single_run = heads == 1u;
             const unsigned above = lane == 31 ? 0u : (heads >> (lane + 1));
             const uint32_t run_end = above ? lane + (uint32_t)__ffs(above) : 32u;  // first lane of the next run
             const unsigned run_mask = (run_end == 32u ? 0xFFFFFFFFu : ((1u << run_end) - 1u)) & ~((1u << lane) - 1u);
             const uint32_t max_ent = __reduce_max_sync(0xFFFFFFFFu, nent);
-            for (uint32_t q = 0; q < max_ent; ++q) {
-                const bool has = q < nent;
-                uint64_t cm = 0;
-                uint32_t ml = 0, K = 0, slot_off = 0, x = 0;
-                if (has) {
-                    const StabEntry en = ent[so + q];
-                    K = en.K;
-                    slot_off = en.slot_off;
-                    x = en.x;
-                    bool general = true;
-                    if (rv.n == 1 && (en.meta & SE_FAST)) {
-                        bool tie;
-                        cm = eval_fast(en, at_start, rv.b0.x, rv.b0.y, ml, tie);
-                        general = tie;
+            // the chunk is sorted by key, so FAST-class reads (key < n_pieces) precede GENERAL ones
+            // and a warp is of one class except at the single class boundary
+            const bool any_general = __any_sync(0xFFFFFFFFu, act && key >= T.n_pieces);
+            if (!any_general) {
+                const int32_t s0 = (int32_t)rec.x, e0 = s0 + (int32_t)(rec.y & 0xFFFFu);
+                for (uint32_t q = 0; q < max_ent; ++q) {
+                    const bool has = q < nent;
+                    uint32_t cm = 0, ml = 0, slot_off = 0, x = 0;
+                    if (has) {
+                        const StabEntry en = ent[so + q];
+                        slot_off = en.slot_off;
+                        x = en.x;
+                        if (en.meta & SE_FAST) {
+                            cm = eval_fast(en, s0, e0, ml);
+                        } else {  // wide / many-form event or long chain: general walk of one block
+                            const EvHdr h = T.hdr[x];
+                            ReadView rv;
+                            rv.b0 = make_int2(s0, e0);
+                            rv.n = 1;
+                            rv.ridx = 0;
+                            rv.blk = nullptr;
+                            const uint64_t c64 = eval_pair(P, h, T.seg + h.seg_off, T.fmask + h.form_off, rv,
+                                                           (rec.y >> 16) & 0xFFu, (uint32_t)(e0 - s0), ml);
+                            cm = (uint32_t)c64;
+                            if (c64 != 0 && en.K > 2) {
+                                bump_class(P, h, c64);
+                                cm = 0x80000000u;
+                            }
+                        }
+                        if (cm != 0 && cm != 0x80000000u && en.K > 2) {  // dense table with more than 3 classes
+                            atomicAdd(P.slot_cnt + slot_off + (cm - 1u), 1ull);
+                            cm = 0x80000000u;
+                        }
                     }
-                    if (general) {  // multi-block reads, wide / many-form events, long chains, tie-breaks
+                    aggregate_runs(P, lane, head && has, run_mask, run_end, single_run, cm, ml, slot_off, x);
+                    my_valid += (cm != 0);
+                }
+            } else {
+                // GENERAL class (and the one mixed warp at the class boundary)
+                const bool gen = act && key >= T.n_pieces;
+                ReadView rv;
+                rv.b0 = make_int2((int32_t)rec.x, (int32_t)rec.x + (int32_t)(rec.y & 0xFFFFu));
+                rv.n = 1;
+                rv.ridx = 0;
+                rv.blk = nullptr;
+                uint32_t strand = (rec.y >> 16) & 0xFFu, total_len = rec.y & 0xFFFFu;
+                if (gen) {
+                    const int2 *entry = P.ext + rec.x;
+                    const int2 hd = __ldg(entry);
+                    rv.ridx = (uint32_t)hd.x;
+                    rv.n = (uint32_t)hd.y & 0xFFFFFFu;
+                    strand = (uint32_t)hd.y >> 24;
+                    rv.blk = entry + 1;
+                    rv.b0 = __ldg(entry + 1);
+                    total_len = (uint32_t)(rv.b0.y - rv.b0.x);
+                    for (uint32_t b = 1; b < rv.n; ++b) {
+                        const int2 blk = __ldg(rv.blk + b);
+                        total_len += (uint32_t)(blk.y - blk.x);
+                    }
+                }
+                for (uint32_t q = 0; q < max_ent; ++q) {
+                    const bool has = q < nent;
+                    uint32_t cm = 0, ml = 0, slot_off = 0, x = 0;
+                    if (has) {
+                        const StabEntry en = ent[so + q];
+                        slot_off = en.slot_off;
+                        x = en.x;
                         const EvHdr h = T.hdr[x];
-                        uint32_t total_len = (uint32_t)(rv.b0.y - rv.b0.x);
-                        for (uint32_t b = 1; b < rv.n; ++b) {
-                            const int2 blk = __ldg(rv.ext + b);
-                            total_len += (uint32_t)(blk.y - blk.x);
+                        const uint64_t c64 = eval_pair(P, h, T.seg + h.seg_off, T.fmask + h.form_off, rv, strand,
+                                                       total_len, ml);
+                        cm = (uint32_t)c64;
+                        if (c64 != 0 && en.K > 2) {
+                            bump_class(P, h, c64);
+                            cm = 0x80000000u;
                         }
-                        cm = eval_pair(P, h, T.seg + h.seg_off, T.fmask + h.form_off, rv, strand, total_len, ml);
-                        if (cm != 0 && K > 2) {  // rare: per-lane update of a large class table
-                            bump_class(P, h, cm);
-                            cm = 0x8000000000000000ull;  // counted; still contributes bases below
-                        }
-                    } else if (cm != 0 && K > 2) {
-                        atomicAdd(P.slot_cnt + slot_off + (uint32_t)(cm - 1ull), 1ull);
-                        cm = 0x8000000000000000ull;
                     }
+                    aggregate_runs(P, lane, head && has, run_mask, run_end, single_run, cm, ml, slot_off, x);
+                    my_valid += (cm != 0);
                 }
-                const unsigned b1 = __ballot_sync(0xFFFFFFFFu, cm == 1ull);
-                const unsigned b2 = __ballot_sync(0xFFFFFFFFu, cm == 2ull);
-                const unsigned b3 = __ballot_sync(0xFFFFFFFFu, cm == 3ull);
-                // matched bases of the run: segmented reduction towards the head lane
-                uint32_t v = ml;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t t = __shfl_down_sync(0xFFFFFFFFu, v, d);
-                    if (lane + (uint32_t)d < run_end) v += t;
-                }
-                if (head && has) {
-                    const uint32_t c1 = __popc(b1 & run_mask), c2 = __popc(b2 & run_mask), c3 = __popc(b3 & run_mask);
-                    if (c1) atomicAdd(P.slot_cnt + slot_off, (unsigned long long)c1);
-                    if (c2) atomicAdd(P.slot_cnt + slot_off + 1u, (unsigned long long)c2);
-                    if (c3) atomicAdd(P.slot_cnt + slot_off + 2u, (unsigned long long)c3);
-                    if (v) atomicAdd(P.bases + x, (unsigned long long)v);
-                }
-                my_valid += (cm != 0);
             }
         }
         __syncwarp();

@@ -63,12 +63,13 @@ struct __align__(16) PieceInfo {
 };
 static_assert(sizeof(PieceInfo) == 16, "PieceInfo layout");
 
-// Sorted read record (16 bytes), value type of the radix sort keyed by stab piece.
-//   x,y : first kept block [start,end)
-//   z   : n == 1 ? original read index : offset of the read's entry in ext[]
-//   w   : (file strand id << 24) | n   (n = number of kept blocks)
-// ext entry of a multi-block read: ext[z] = {read index, n}, ext[z+1 .. z+n-1] = blocks 1..n-1.
-typedef uint4 ReadRec;
+// Sorted read record (8 bytes), value type of the radix sort.  Keys: piece p for FAST-class reads
+// (one kept block, shorter than 64 Ki, not starting on the first position of its piece),
+// n_pieces + p for GENERAL-class reads, 2 * n_pieces for reads that are no candidates.
+//   fast   : x = start of the block, y = length (bits 0-15) | file strand id (bits 16-23)
+//   general: x = offset of the read's entry in ext[]:
+//            ext[x] = {original read index, (strand << 24) | n}, ext[x+1 .. x+n] = kept blocks
+typedef uint2 ReadRec;
 
 struct Tables {
     uint32_t E, F, n_pieces, n_chroms, n_ann_strands;
@@ -99,7 +100,7 @@ struct FilterParams {
     const uint32_t *read_cs;
     const uint32_t *blk_cs;       // may be null
     const uint32_t *chrom_remap;  // file chromosome id -> annotation id or 0xFFFFFFFF
-    int2 *ext;                    // [n_blocks + n_reads] worst case
+    int2 *ext;                    // [n_blocks + n_reads] worst case (header + blocks per general read)
     uint32_t *rkey;               // [n_reads] stab piece or n_pieces (= dropped)
     ReadRec *rec;                 // [n_reads]
     unsigned long long *counters; // [0] kept reads, [1] ext cursor, [2] valid pairs

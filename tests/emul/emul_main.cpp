@@ -144,20 +144,22 @@ int main(int argc, char **argv) {
         FP.rkey = rkey.data();
         FP.rec = rec.data();
         FP.counters = counters;
+        std::vector<int2> ext2(std::max<size_t>(nb + n, 1));
         for (size_t r = 0; r < n; ++r) {  // lsq_filter_kernel, one "thread" at a time
             FilteredRead fr = filter_read(FP, r, work.data());
             ReadRec q;
-            q.x = (uint32_t)fr.first.x;
-            q.y = (uint32_t)fr.first.y;
-            q.w = pack_rec_w(fr.n, fr.at_piece_start, fr.strand);
-            if (fr.key != KEY_DROPPED(T) && fr.n >= 2) {
+            if (fr.key != KEY_DROPPED(T) && fr.key >= T.n_pieces) {
                 uint32_t off = (uint32_t)counters[1];
-                counters[1] += fr.n;
-                ext[off] = make_int2((int32_t)r, (int32_t)fr.n);
-                for (uint32_t i = 1; i < fr.n; ++i) ext[off + i] = work[R.blk_off[r] + i];
-                q.z = off;
+                counters[1] += fr.n + 1;
+                ext2[off] = make_int2((int32_t)r, (int32_t)((fr.strand << 24) | (fr.n & 0xFFFFFFu)));
+                if (fr.n == 1) ext2[off + 1] = fr.first;
+                else
+                    for (uint32_t i = 0; i < fr.n; ++i) ext2[off + 1 + i] = work[R.blk_off[r] + i];
+                q.x = off;
+                q.y = 0;
             } else {
-                q.z = (uint32_t)r;
+                q.x = (uint32_t)fr.first.x;
+                q.y = (uint32_t)(fr.first.y - fr.first.x) | (fr.strand << 16);
             }
             rkey[r] = fr.key;
             rec[r] = q;
@@ -167,7 +169,7 @@ int main(int argc, char **argv) {
         std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) { return rkey[a] < rkey[b]; });
         CountParams CP{};
         CP.T = T;
-        CP.ext = ext.data();
+        CP.ext = ext2.data();
         CP.line_num = R.line_num.data();
         CP.strand_tbl = stbl.data();
         for (size_t i = 0; i < n; ++i) {  // lsq_count_kernel, one read at a time
@@ -175,29 +177,35 @@ int main(int argc, char **argv) {
             uint32_t key = rkey[r];
             if (key == KEY_DROPPED(T)) break;
             ReadRec q = rec[r];
+            const bool gen = key >= T.n_pieces;
+            const uint32_t piece = gen ? key - T.n_pieces : key;
             ReadView rv;
-            rv.b0 = make_int2((int32_t)q.x, (int32_t)q.y);
-            rv.n = q.w & REC_N_MASK;
-            const bool at_start = (q.w & REC_AT_PIECE_START) != 0;
-            rv.z = q.z;
-            rv.ext = rv.n > 1 ? ext.data() + q.z : nullptr;
-            uint32_t strand = q.w >> 24;
-            uint32_t total = (uint32_t)(rv.b0.y - rv.b0.x);
-            for (uint32_t j = 1; j < rv.n; ++j) total += (uint32_t)(rv.ext[j].y - rv.ext[j].x);
-            const uint32_t piece = key >> 1;
+            uint32_t strand, total;
+            if (gen) {
+                const int2 *entry = ext2.data() + q.x;
+                rv.ridx = (uint32_t)entry[0].x;
+                rv.n = (uint32_t)entry[0].y & 0xFFFFFFu;
+                strand = (uint32_t)entry[0].y >> 24;
+                rv.blk = entry + 1;
+                rv.b0 = entry[1];
+                total = 0;
+                for (uint32_t b = 0; b < rv.n; ++b) total += (uint32_t)(rv.blk[b].y - rv.blk[b].x);
+            } else {
+                rv.b0 = make_int2((int32_t)q.x, (int32_t)q.x + (int32_t)(q.y & 0xFFFFu));
+                rv.n = 1;
+                rv.ridx = 0;
+                rv.blk = nullptr;
+                strand = (q.y >> 16) & 0xFFu;
+                total = q.y & 0xFFFFu;
+            }
             for (uint32_t s = T.stab_off[piece]; s < T.stab_off[piece + 1]; ++s) {
                 const StabEntry &en = T.stab[s];
                 uint32_t x = en.x;
                 const EvHdr &h = T.hdr[x];
                 uint32_t ml = 0;
                 uint64_t cm = 0;
-                bool general = true;
-                if (rv.n == 1 && (en.meta & SE_FAST)) {
-                    bool tie;
-                    cm = eval_fast(en, at_start, rv.b0.x, rv.b0.y, ml, tie);
-                    general = tie;
-                }
-                if (general) cm = eval_pair(CP, h, T.seg + h.seg_off, T.fmask + h.form_off, rv, strand, total, ml);
+                if (!gen && (en.meta & SE_FAST)) cm = eval_fast(en, rv.b0.x, rv.b0.y, ml);
+                else cm = eval_pair(CP, h, T.seg + h.seg_off, T.fmask + h.form_off, rv, strand, total, ml);
                 if (cm) {
                     hist[m][x][cm]++;
                     bases[m][x] += ml;
