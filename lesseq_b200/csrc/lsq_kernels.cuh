@@ -133,15 +133,15 @@ struct ChunkTables {
 __device__ __forceinline__ ChunkTables chunk_tables(const CountParams &P, unsigned long long base,
                                                     unsigned long long end) {
     ChunkTables c;
-    // a chunk that straddles the FAST / GENERAL class boundary wraps around in piece space and
-    // is simply not staged (pl < pf makes the sizes below huge)
+    // the one chunk that straddles the FAST / GENERAL class boundary wraps around in piece space
+    // and is not staged
     const uint32_t kf = __ldg(P.g_key + base), kl = __ldg(P.g_key + end - 1), np = P.T.n_pieces;
     const uint32_t pf = kf >= np ? kf - np : kf, pl = kl >= np ? kl - np : kl;
     c.e0 = __ldg(P.T.stab_off + pf);
     c.e1 = __ldg(P.T.stab_off + pl + 1);
     c.pa = pf & ~3u;
     c.noff = ((pl + 2 - c.pa) + 3u) & ~3u;
-    c.staged = pl >= pf && (c.e1 - c.e0) <= (uint32_t)COUNT_MAX_ENT && c.noff <= (uint32_t)COUNT_MAX_OFF && c.e1 > c.e0;
+    c.staged = (kf >= np) == (kl >= np) && pl >= pf && (c.e1 - c.e0) <= (uint32_t)COUNT_MAX_ENT && c.noff <= (uint32_t)COUNT_MAX_OFF && c.e1 > c.e0;
     return c;
 }
 
