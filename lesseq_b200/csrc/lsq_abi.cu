@@ -497,11 +497,17 @@ int lsq_count(lsq_ctx *c) {
             CP.slot_mask = slot_mask;
             CP.bases = bases;
             CP.stats = counters + 2;
-            unsigned grid = (unsigned)std::min<size_t>((n + lsq::COUNT_CHUNK - 1) / lsq::COUNT_CHUNK, (size_t)c->n_sms * 6);
-            lsq::lsq_count_kernel<<<grid, lsq::COUNT_BLOCK, 0, s>>>(CP);
+            // the class sizes are only known on the device: both instantiations get a grid that
+            // covers the whole read set and walk their own range of the sorted arrays
+            const size_t chunks = (n + lsq::COUNT_CHUNK - 1) / lsq::COUNT_CHUNK;
+            unsigned grid_f = (unsigned)std::min<size_t>(chunks, (size_t)c->n_sms * 5);
+            unsigned grid_g = (unsigned)std::min<size_t>(chunks, (size_t)c->n_sms * 3);
+            lsq::lsq_count_kernel<false><<<grid_f, lsq::COUNT_BLOCK, 0, s>>>(CP);
             LSQ_CUDA(cudaGetLastError());
-            tm.launches++;
-            tm.count_launches++;
+            lsq::lsq_count_kernel<true><<<grid_g, lsq::COUNT_BLOCK, 0, s>>>(CP);
+            LSQ_CUDA(cudaGetLastError());
+            tm.launches += 2;
+            tm.count_launches += 2;
         }
         LSQ_CUDA(cudaEventRecord(c->ev[3], s));
         LSQ_CUDA(cudaMemcpyAsync(c->h_counters.data() + (size_t)m * 4, counters, 4 * 8, cudaMemcpyDeviceToHost, s));

@@ -129,8 +129,9 @@ LSQ_HD uint32_t list_add(int2 *L, uint32_t n, int32_t s, int32_t e) {
 // (several kept blocks, a start on the first position of a piece -- the only place the
 // lower_bound tie-break can apply --, or an over-long block) goes through the general walk.
 constexpr uint32_t FAST_MAX_LEN = 0xFFFFu;
-LSQ_HD bool is_fast_read(uint32_t n, uint32_t at_piece_start, int2 first) {
-    return n == 1u && !at_piece_start && (uint32_t)(first.y - first.x) <= FAST_MAX_LEN;
+LSQ_HD bool is_fast_read(uint32_t n, uint32_t at_piece_start, int2 first, uint32_t piece_stab_n) {
+    return n == 1u && !at_piece_start && (uint32_t)(first.y - first.x) <= FAST_MAX_LEN &&
+           (piece_stab_n & PIECE_ALL_FAST) != 0;
 }
 
 // Sort key of a read that is a candidate of no event: one past the largest real key.
@@ -231,9 +232,9 @@ LSQ_HD FilteredRead filter_read(const FilterParams &P, uint64_t r, int2 *work) {
         PieceInfo pi = first_pi;
         const uint32_t c_first = LSQ_LD(P.chrom_remap + ((mixed ? LSQ_LD(P.blk_cs + base) : cs0) & 0xFFFFu));
         if (!first_valid || mixed || c_first != chrom) p = find_piece(T, chrom, first.x, pi);
-        if (p != 0xFFFFFFFFu && pi.stab_n > 0) {
+        if (p != 0xFFFFFFFFu && (pi.stab_n & ~PIECE_ALL_FAST) > 0) {
             out.at_piece_start = pi.pos == first.x ? 1u : 0u;
-            out.key = is_fast_read(n, out.at_piece_start, first) ? p : T.n_pieces + p;
+            out.key = is_fast_read(n, out.at_piece_start, first, pi.stab_n) ? p : T.n_pieces + p;
         }
     }
     return out;
@@ -373,8 +374,7 @@ LSQ_HD bool walk_wide(const ReadView &rv, const int2 *seg, uint32_t S,
 // touching the event tables.  Returns the form mask of a valid read (0 otherwise).
 LSQ_HD uint32_t eval_fast(const StabEntry &en, int32_t s, int32_t e, uint32_t &matched) {
     matched = 0;
-    const uint32_t nchain = (en.meta >> 16) & 3u;
-    const int32_t cend = en.c[nchain - 1];
+    const int32_t cend = en.c[2];  // c[] is padded with the last chain end
     uint32_t cm;
     if (e <= en.c[0]) cm = en.cmask[0];
     else if (e <= en.c[1]) cm = en.cmask[1];
@@ -445,7 +445,8 @@ LSQ_HD uint64_t eval_pair(const CountParams &P, const EvHdr &h, const int2 *seg,
         }
     }
     if (cm == 0) return 0;
-    if (!(lsq_div((double)ml, (double)total_len) > 0.98)) return 0;
+    // count.cpp:441-442 as an IEEE double division; a fully matched read has ratio exactly 1
+    if (ml != total_len && !(lsq_div((double)ml, (double)total_len) > 0.98)) return 0;
     matched = ml;
     return cm;
 }

@@ -121,8 +121,8 @@ constexpr int COUNT_BLOCK = 256;
 constexpr int COUNT_WARPS = COUNT_BLOCK / 32;
 constexpr int COUNT_ITEMS = 8;
 constexpr int COUNT_CHUNK = COUNT_BLOCK * COUNT_ITEMS;
-constexpr int COUNT_MAX_ENT = 384;     // staged stab entries per stage (12 KB)
-constexpr int COUNT_MAX_OFF = 1024;    // staged offsets per stage (4 KB)
+constexpr int COUNT_MAX_ENT = 256;     // staged stab entries per stage (8 KB)
+constexpr int COUNT_MAX_OFF = 512;     // staged offsets per stage (2 KB)
 
 struct ChunkTables {
     uint32_t e0, e1;   // stab entry range
@@ -131,17 +131,14 @@ struct ChunkTables {
 };
 
 __device__ __forceinline__ ChunkTables chunk_tables(const CountParams &P, unsigned long long base,
-                                                    unsigned long long end) {
+                                                    unsigned long long end, uint32_t key_bias) {
     ChunkTables c;
-    // the one chunk that straddles the FAST / GENERAL class boundary wraps around in piece space
-    // and is not staged
-    const uint32_t kf = __ldg(P.g_key + base), kl = __ldg(P.g_key + end - 1), np = P.T.n_pieces;
-    const uint32_t pf = kf >= np ? kf - np : kf, pl = kl >= np ? kl - np : kl;
+    const uint32_t pf = __ldg(P.g_key + base) - key_bias, pl = __ldg(P.g_key + end - 1) - key_bias;
     c.e0 = __ldg(P.T.stab_off + pf);
     c.e1 = __ldg(P.T.stab_off + pl + 1);
     c.pa = pf & ~3u;
     c.noff = ((pl + 2 - c.pa) + 3u) & ~3u;
-    c.staged = (kf >= np) == (kl >= np) && pl >= pf && (c.e1 - c.e0) <= (uint32_t)COUNT_MAX_ENT && c.noff <= (uint32_t)COUNT_MAX_OFF && c.e1 > c.e0;
+    c.staged = (c.e1 - c.e0) <= (uint32_t)COUNT_MAX_ENT && c.noff <= (uint32_t)COUNT_MAX_OFF && c.e1 > c.e0;
     return c;
 }
 
@@ -173,12 +170,19 @@ __device__ __forceinline__ void aggregate_runs(const CountParams &P, uint32_t la
     }
 }
 
-__global__ void __launch_bounds__(COUNT_BLOCK) lsq_count_kernel(CountParams P) {
+// GENERAL = false: FAST-class reads, positions [0, n_fast) of the sorted arrays -- purely table
+// driven.  GENERAL = true: positions [n_fast, n_kept) -- the general walk over the ext entries.
+// Two instantiations keep the lean kernel's register count (and so its occupancy) independent
+// of the walk's.
+template <bool GENERAL>
+__global__ void __launch_bounds__(COUNT_BLOCK, GENERAL ? 3 : 5) lsq_count_kernel(CountParams P) {
     __shared__ __align__(128) StabEntry s_ent[2][COUNT_MAX_ENT];
     __shared__ __align__(16) uint32_t s_off[2][COUNT_MAX_OFF];
     __shared__ __align__(8) uint64_t s_full[2], s_empty[2];
     const Tables &T = P.T;
-    const unsigned long long n_kept = P.counters[0];
+    const unsigned long long n_fast = P.counters[0] - P.counters[3];
+    const unsigned long long r_begin = GENERAL ? n_fast : 0ull, r_end = GENERAL ? P.counters[0] : n_fast;
+    const uint32_t key_bias = GENERAL ? T.n_pieces : 0u;
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
     const bool producer = threadIdx.x == 0;
     if (producer) {
@@ -188,11 +192,11 @@ __global__ void __launch_bounds__(COUNT_BLOCK) lsq_count_kernel(CountParams P) {
         mbar_init(&s_empty[1], COUNT_WARPS);
     }
     __syncthreads();
-    const unsigned long long n_chunks = (n_kept + COUNT_CHUNK - 1) / COUNT_CHUNK;
+    const unsigned long long n_chunks = (r_end - r_begin + COUNT_CHUNK - 1) / COUNT_CHUNK;
     auto issue = [&](unsigned long long chunk, uint32_t stage) {  // producer only
-        const unsigned long long base = chunk * COUNT_CHUNK;
-        const unsigned long long end = min(base + (unsigned long long)COUNT_CHUNK, n_kept);
-        const ChunkTables c = chunk_tables(P, base, end);
+        const unsigned long long base = r_begin + chunk * COUNT_CHUNK;
+        const unsigned long long end = min(base + (unsigned long long)COUNT_CHUNK, r_end);
+        const ChunkTables c = chunk_tables(P, base, end, key_bias);
         if (c.staged) {
             const uint32_t ebytes = (c.e1 - c.e0) * (uint32_t)sizeof(StabEntry), obytes = c.noff * 4u;
             mbar_expect_tx(&s_full[stage], ebytes + obytes);
@@ -212,24 +216,34 @@ __global__ void __launch_bounds__(COUNT_BLOCK) lsq_count_kernel(CountParams P) {
             if (j + 1u >= 2u) mbar_wait(&s_empty[ns], (((j + 1u) >> 1) - 1u) & 1u);
             issue(chunk + gridDim.x, ns);
         }
-        const unsigned long long base = chunk * COUNT_CHUNK;
-        const unsigned long long end = min(base + (unsigned long long)COUNT_CHUNK, n_kept);
-        const ChunkTables ct = chunk_tables(P, base, end);
+        const unsigned long long base = r_begin + chunk * COUNT_CHUNK;
+        const unsigned long long end = min(base + (unsigned long long)COUNT_CHUNK, r_end);
+        const ChunkTables ct = chunk_tables(P, base, end, key_bias);
         if (lane == 0) mbar_wait(&s_full[stage], (j >> 1) & 1u);  // one poller per warp
         __syncwarp();
         const StabEntry *ent = ct.staged ? s_ent[stage] - ct.e0 : T.stab;
         const uint32_t *off = ct.staged ? s_off[stage] - ct.pa : T.stab_off;
-        for (int it = 0; it < COUNT_ITEMS; ++it) {
-            const unsigned long long w0 = base + (unsigned long long)((warp * COUNT_ITEMS + it) * 32u);
-            if (w0 >= end) break;  // warp-uniform
-            const unsigned long long i = w0 + lane;
+        // software pipeline: the next iteration's key and record are loaded before this one is used
+        unsigned long long i = base + (unsigned long long)(warp * COUNT_ITEMS * 32u) + lane;
+        uint32_t key_n = 0xFFFFFFFFu;
+        ReadRec rec_n = make_uint2(0u, 0u);
+        if (i < end) {
+            key_n = __ldg(P.g_key + i);
+            rec_n = __ldg(P.g_rec + i);
+        }
+        for (int it = 0; it < COUNT_ITEMS; ++it, i += 32u) {
+            if (i - lane >= end) break;  // warp-uniform
             const bool act = i < end;
-            uint32_t key = 0xFFFFFFFFu, so = 0, nent = 0;
-            ReadRec rec = make_uint2(0u, 0u);
+            const uint32_t key = key_n;
+            const ReadRec rec = rec_n;
+            key_n = 0xFFFFFFFFu;
+            if (it + 1 < COUNT_ITEMS && i + 32u < end) {
+                key_n = __ldg(P.g_key + i + 32u);
+                rec_n = __ldg(P.g_rec + i + 32u);
+            }
+            uint32_t so = 0, nent = 0;
             if (act) {
-                key = __ldg(P.g_key + i);
-                rec = __ldg(P.g_rec + i);
-                const uint32_t piece = key >= T.n_pieces ? key - T.n_pieces : key;
+                const uint32_t piece = key - key_bias;
                 so = off[piece];
                 nent = off[piece + 1] - so;
             }
@@ -242,36 +256,17 @@ __global__ void __launch_bounds__(COUNT_BLOCK) lsq_count_kernel(CountParams P) {
             const uint32_t run_end = above ? lane + (uint32_t)__ffs(above) : 32u;  // first lane of the next run
             const unsigned run_mask = (run_end == 32u ? 0xFFFFFFFFu : ((1u << run_end) - 1u)) & ~((1u << lane) - 1u);
             const uint32_t max_ent = __reduce_max_sync(0xFFFFFFFFu, nent);
-            // the chunk is sorted by key, so FAST-class reads (key < n_pieces) precede GENERAL ones
-            // and a warp is of one class except at the single class boundary
-            const bool any_general = __any_sync(0xFFFFFFFFu, act && key >= T.n_pieces);
-            if (!any_general) {
+            if (!GENERAL) {
                 const int32_t s0 = (int32_t)rec.x, e0 = s0 + (int32_t)(rec.y & 0xFFFFu);
                 for (uint32_t q = 0; q < max_ent; ++q) {
                     const bool has = q < nent;
                     uint32_t cm = 0, ml = 0, slot_off = 0, x = 0;
                     if (has) {
-                        const StabEntry en = ent[so + q];
+                        const StabEntry en = ent[so + q];  // SE_FAST by construction of the class
                         slot_off = en.slot_off;
                         x = en.x;
-                        if (en.meta & SE_FAST) {
-                            cm = eval_fast(en, s0, e0, ml);
-                        } else {  // wide / many-form event or long chain: general walk of one block
-                            const EvHdr h = T.hdr[x];
-                            ReadView rv;
-                            rv.b0 = make_int2(s0, e0);
-                            rv.n = 1;
-                            rv.ridx = 0;
-                            rv.blk = nullptr;
-                            const uint64_t c64 = eval_pair(P, h, T.seg + h.seg_off, T.fmask + h.form_off, rv,
-                                                           (rec.y >> 16) & 0xFFu, (uint32_t)(e0 - s0), ml);
-                            cm = (uint32_t)c64;
-                            if (c64 != 0 && en.K > 2) {
-                                bump_class(P, h, c64);
-                                cm = 0x80000000u;
-                            }
-                        }
-                        if (cm != 0 && cm != 0x80000000u && en.K > 2) {  // dense table with more than 3 classes
+                        cm = eval_fast(en, s0, e0, ml);
+                        if (cm != 0 && en.K > 2) {  // dense class table with more than 3 classes
                             atomicAdd(P.slot_cnt + slot_off + (cm - 1u), 1ull);
                             cm = 0x80000000u;
                         }
@@ -280,15 +275,13 @@ __global__ void __launch_bounds__(COUNT_BLOCK) lsq_count_kernel(CountParams P) {
                     my_valid += (cm != 0);
                 }
             } else {
-                // GENERAL class (and the one mixed warp at the class boundary)
-                const bool gen = act && key >= T.n_pieces;
                 ReadView rv;
-                rv.b0 = make_int2((int32_t)rec.x, (int32_t)rec.x + (int32_t)(rec.y & 0xFFFFu));
+                rv.b0 = make_int2(0, 0);
                 rv.n = 1;
                 rv.ridx = 0;
                 rv.blk = nullptr;
-                uint32_t strand = (rec.y >> 16) & 0xFFu, total_len = rec.y & 0xFFFFu;
-                if (gen) {
+                uint32_t strand = 0, total_len = 0;
+                if (act) {
                     const int2 *entry = P.ext + rec.x;
                     const int2 hd = __ldg(entry);
                     rv.ridx = (uint32_t)hd.x;

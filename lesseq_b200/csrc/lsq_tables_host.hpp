@@ -358,6 +358,9 @@ inline int build_host_tables(const lsq_event_tables *t, HostTables &H, std::stri
             pi.pos = H.bp_pos[p];
             pi.stab_off = H.stab_off[p];
             pi.stab_n = H.stab_off[p + 1] - H.stab_off[p];
+            bool all_fast = pi.stab_n > 0;
+            for (uint32_t q = H.stab_off[p]; q < H.stab_off[p + 1]; ++q) all_fast = all_fast && (H.stab[q].meta & SE_FAST);
+            if (all_fast) pi.stab_n |= PIECE_ALL_FAST;
             size_t i = std::upper_bound(cs, cs + nc, pi.pos) - cs;
             pi.cov_end = (i > 0 && ce[i - 1] > pi.pos) ? ce[i - 1] : INT32_MIN;
         }

@@ -59,8 +59,10 @@ struct __align__(16) PieceInfo {
     int32_t pos;        // first position of the piece
     int32_t cov_end;    // end of the covered region containing the piece, INT32_MIN if uncovered
     uint32_t stab_off;  // first stab entry
-    uint32_t stab_n;    // number of stab entries (0: reads starting here are no candidates)
+    uint32_t stab_n;    // number of stab entries (0: reads starting here are no candidates);
+                        // bit 31 (PIECE_ALL_FAST): every entry is table-driven (SE_FAST)
 };
+constexpr uint32_t PIECE_ALL_FAST = 0x80000000u;
 static_assert(sizeof(PieceInfo) == 16, "PieceInfo layout");
 
 // Sorted read record (8 bytes), value type of the radix sort.  Keys: piece p for FAST-class reads

@@ -204,7 +204,11 @@ int main(int argc, char **argv) {
                 const EvHdr &h = T.hdr[x];
                 uint32_t ml = 0;
                 uint64_t cm = 0;
-                if (!gen && (en.meta & SE_FAST)) cm = eval_fast(en, rv.b0.x, rv.b0.y, ml);
+                if (!gen && !(en.meta & SE_FAST)) {
+                    fprintf(stderr, "emul: FAST-class read met a non-FAST entry\n");
+                    return 3;
+                }
+                if (!gen) cm = eval_fast(en, rv.b0.x, rv.b0.y, ml);
                 else cm = eval_pair(CP, h, T.seg + h.seg_off, T.fmask + h.form_off, rv, strand, total, ml);
                 if (cm) {
                     hist[m][x][cm]++;
