@@ -9,10 +9,14 @@
 
 #ifdef __CUDACC__
 #define LSQ_HD __device__ __forceinline__
+#define LSQ_COLD __device__ __noinline__  /* rare paths: kept out of line so the hot loop stays I-cache resident */
 #define LSQ_LD(p) __ldg(p)
+#define LSQ_NO_UNROLL _Pragma("unroll 1")
 #else
 #define LSQ_HD inline
+#define LSQ_COLD inline
 #define LSQ_LD(p) (*(p))
+#define LSQ_NO_UNROLL
 #endif
 
 namespace lsq {
@@ -255,7 +259,7 @@ struct ReadView {
 
 // "read-<N>" < name for tie mode 2: the name is "read-" + suffix, so compare the decimal digits
 // of N with the suffix bytewise (std::string operator<).
-LSQ_HD bool digits_less(uint32_t N, const char *__restrict__ sfx, uint32_t len) {
+LSQ_COLD bool digits_less(uint32_t N, const char *__restrict__ sfx, uint32_t len) {
     char d[10];
     int nd = 0;
     do {
@@ -279,11 +283,13 @@ LSQ_HD void walk_mask(const ReadView &rv, const int2 *seg, uint32_t S, uint64_t 
     bool found = false;
     uint64_t m = 0;
     uint32_t ml = 0;
+    LSQ_NO_UNROLL
     while (b < rv.n) {
         int2 blk = rv.block(b);
         int32_t cs = blk.x;
         const int32_t ce = blk.y;
         bool consumed = false;
+        LSQ_NO_UNROLL
         while (it < S) {
             int2 sg = seg[it];
             if (!(sg.x < ce)) break;
@@ -318,7 +324,7 @@ LSQ_HD void walk_mask(const ReadView &rv, const int2 *seg, uint32_t S, uint64_t 
 // Wide events (S > 64): the same walk, checking one form on the fly with its prefix counts
 // pf[s] = number of form segments with index < s.  The read's index list must be a contiguous
 // run of the form's list (common/read.h:44-79).
-LSQ_HD bool walk_wide(const ReadView &rv, const int2 *seg, uint32_t S,
+LSQ_COLD bool walk_wide(const ReadView &rv, const int2 *seg, uint32_t S,
                                  const uint32_t *__restrict__ pf, uint32_t &matched) {
     uint32_t it = 0, b = 0;
     int32_t cont = 0;
@@ -400,12 +406,7 @@ LSQ_HD uint32_t hash_mask(uint64_t m) {
 // The lower_bound skip of count.cpp:429-432: a read starting exactly at the event start is
 // passed over when its key (start, end, strand, name) sorts before the probe
 // (gs, ge, event strand, event name) under the comparator of count.cpp:64-85.
-LSQ_HD bool tie_skipped(const CountParams &P, const EvHdr &h, const ReadView &rv,
-                                            uint32_t strand) {
-    if (rv.b0.x != h.gs) return false;
-    int32_t r_end = rv.last_end();
-    if (r_end < h.ge) return true;
-    if (r_end > h.ge) return false;
+LSQ_COLD bool tie_resolve(const CountParams &P, const EvHdr &h, const ReadView &rv, uint32_t strand) {
     uint8_t t = LSQ_LD(P.strand_tbl + strand * P.T.n_ann_strands + h.strand);
     if (t & 1u) return true;
     if (!(t & 2u)) return false;
@@ -414,6 +415,14 @@ LSQ_HD bool tie_skipped(const CountParams &P, const EvHdr &h, const ReadView &rv
     if (mode == 1u) return true;
     uint32_t ln = LSQ_LD(P.line_num + rv.read_index());
     return digits_less(ln, P.T.tie_pool + h.tie_off, h.tie_len);
+}
+
+LSQ_HD bool tie_skipped(const CountParams &P, const EvHdr &h, const ReadView &rv, uint32_t strand) {
+    if (rv.b0.x != h.gs) return false;
+    int32_t r_end = rv.last_end();
+    if (r_end < h.ge) return true;
+    if (r_end > h.ge) return false;
+    return tie_resolve(P, h, rv, strand);
 }
 
 // One (read, event) pair -> form compatibility mask of a VALID read (0 otherwise) and matched bases.
@@ -434,9 +443,11 @@ LSQ_HD uint64_t eval_pair(const CountParams &P, const EvHdr &h, const int2 *seg,
         uint32_t hi = 63u - (uint32_t)lsq_clz64(rmask);
         uint64_t low = rmask & (0ull - rmask);
         uint64_t span = ((2ull << hi) - 1ull) & ~(low - 1ull);
+        LSQ_NO_UNROLL
         for (uint32_t k = 0; k < h.K; ++k) cm |= (uint64_t)((fm[k] & span) == rmask) << k;
     } else {
         const uint32_t *pf = P.T.pfx + h.pfx_off;
+        LSQ_NO_UNROLL
         for (uint32_t k = 0; k < h.K; ++k) {
             uint32_t mk;
             bool ok = walk_wide(rv, seg, h.S, pf + (size_t)k * (h.S + 1u), mk);

@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256) lsq_filter_kernel(FilterParams P, int2 *_
 // ---------------------------------------------------------------------------------------------
 // Count kernel
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void bump_class(const CountParams &P, const EvHdr &h, uint64_t cm) {
+__device__ __noinline__ void bump_class(const CountParams &P, const EvHdr &h, uint64_t cm) {
     if (!(h.flags & EV_HASH)) {
         atomicAdd(P.slot_cnt + h.slot_off + (uint32_t)(cm - 1ull), 1ull);
         return;
