@@ -245,3 +245,157 @@ def test_device_resident_reads_and_properties(api, tmp_path):
     for k in ("n_valid", "bases"):
         assert np.array_equal(np.concatenate([p[k] for p in parts], axis=1), c[k]), k
     assert np.array_equal(np.concatenate([p["iso_count"] for p in parts]), c["iso_count"])
+
+
+def _walk_reads(rng, forms, L, n):
+    """Reads of length <= L walking along randomly chosen forms (blocks cut at exon ends)."""
+    lines = []
+    for _ in range(n):
+        ex = forms[rng.randrange(len(forms))]
+        tot = sum(e - s for s, e in ex)
+        off = rng.randrange(0, max(1, tot - 1))
+        need = L
+        acc = 0
+        parts = []
+        q = 1
+        for (s, e) in ex:
+            if off >= acc + (e - s):
+                acc += e - s
+                continue
+            bs = s + max(0, off - acc)
+            take = min(e - bs, need)
+            if parts and parts[-1][1] == bs:  # abutting exons give one block
+                parts[-1][1] = bs + take
+            else:
+                parts.append([bs, bs + take])
+            need -= take
+            acc += e - s
+            off = acc
+            if need <= 0:
+                break
+        st = "+" if rng.random() < 0.5 else "-"
+        lines.append(",".join("chr1:%s:%d:%d:%d:%d" % (st, a + 1, b, 1, b - a) for a, b in parts))
+    return lines
+
+
+def test_wide_and_many_form_events_match_oracle(api, oracle_bin, tmp_path):
+    """Events outside the common shape: > 64 segments (prefix-count compatibility test) and > 8
+    forms (hashed class table), plus a plain event sharing the region."""
+    import random
+    rng = random.Random(17)
+    pos, exons = 1000, []
+    for _ in range(80):
+        ln = rng.randint(20, 90)
+        exons.append((pos, pos + ln))
+        pos += ln + (0 if rng.random() < 0.15 else rng.randint(30, 200))
+    forms, fl, ml = [], [], []
+
+    def add(ev, name, ex):
+        fl.append("%s\tchr1\t+\t%d\t%d\t%d\t%s\t%s\n" % (name, ex[0][0], ex[-1][1], len(ex),
+                                                     ",".join(str(s) for s, _ in ex), ",".join(str(e) for _, e in ex)))
+        ml.append("%s\t%s\n" % (ev, name))
+        forms.append(ex)
+
+    add("WIDE", "W|1", exons)
+    add("WIDE", "W|2", [x for i, x in enumerate(exons) if i % 7 != 3])
+    add("WIDE", "W|3", [x for i, x in enumerate(exons) if i % 5 != 1 or i < 10])
+    sub = exons[20:34]
+    for k in range(11):
+        keep = [x for i, x in enumerate(sub) if i in (0, len(sub) - 1) or rng.random() < 0.7]
+        add("MANY", "M|%d" % (k + 1), keep)
+    add("PLAIN", "P|1", exons[40:43])
+    add("PLAIN", "P|2", [exons[40], exons[42]])
+    fp, mp, rp = tmp_path / "ev.interval", tmp_path / "ev.map", tmp_path / "r.mrf"
+    fp.write_text("".join(fl))
+    mp.write_text("".join(ml))
+    lines = _walk_reads(rng, forms, 100, 30000)
+    rp.write_text("AlignmentBlocks\n" + "\n".join(lines) + "\n")
+    args = ["0", "p", str(tmp_path / "o_"), "LH_GENE_TXT", str(fp), "UCSC_GENE2ISOFORM", str(mp), "0", "100",
+            "MRF_SINGLE", "SHORT_READ", "100", str(rp)]
+    for prog, a in (("count", args), ("solve", args + ["3000000"])):
+        rc1, o1, e1 = oracle_bin.run_oracle(prog, a)
+        rc2, o2, e2 = api.run_program(prog, a, precision=17)
+        assert rc1 == 0 and rc2 == 0, e2
+        assert sum(float(r.split("\t")[1]) for r in o1.splitlines()) > 10000
+        bad = tables_match(o1, o2, prog == "solve")
+        assert bad is None, "%s: %s" % (prog, bad)
+
+
+def _numpy_em(K, G, classes, n_total):
+    """EM of common/read.h:592-660 over (mask, count) classes, sequential double arithmetic."""
+    theta = np.full(K, 1.0 / K)
+
+    def ll(th):
+        s = 0.0
+        for mk, c in classes:
+            p = 0.0
+            for k in range(K):
+                if (mk >> k) & 1:
+                    p = p + th[k] * G[k]
+            s += c * np.log(p) if p > 0 else -np.inf
+        return s
+
+    old = ll(theta)
+    it = 0
+    while True:
+        new = np.zeros(K)
+        for k in range(K):
+            z = 0.0
+            for mk, c in classes:
+                if not (mk >> k) & 1:
+                    continue
+                p = 0.0
+                for j in range(K):
+                    if (mk >> j) & 1:
+                        p = p + theta[j] * G[j]
+                lp = theta[k] * G[k]
+                if p > 0 and lp > 0:
+                    z += c * (lp / p)
+            new[k] = z / n_total
+        theta = new
+        cur = ll(theta)
+        it += 1
+        with np.errstate(invalid="ignore", divide="ignore"):
+            if not (abs(1.0 - old / cur) > 1e-6):
+                break
+        old = cur
+    return theta, cur, it
+
+
+def test_solve_stress_injected_classes(api):
+    """BASELINE config 5 shape at test size: events with 2-16 forms, class tables injected through
+    lsq_set_classes, warp-per-event EM against a numpy restatement of read.h:592-660."""
+    from lesseq_b200 import synth
+    E = 3000
+    S = synth.make_solve_stress(E, 5)
+    ann = api.ArrayAnnotation(
+        ev_chrom=np.zeros(E), ev_strand=np.zeros(E), ev_gs=S["ev_gs"], ev_ge=S["ev_ge"], ev_seg_off=S["seg_off"],
+        ev_form_off=S["form_off"], seg_start=S["seg_start"], seg_end=S["seg_end"], form_seg_off=S["form_seg_off"],
+        form_seg_idx=S["form_seg_idx"], cov_off=[0, 1], cov_start=[0], cov_end=[int(S["ev_ge"][-1]) + 10],
+        chrom_names=["chr1"], strand_names=["+"])
+    ctx = api.Context(0)
+    ctx.upload_events(ann)
+    ctx.set_classes(0, "SHORT_READ", 75, S["cls_off"], S["cls_mask"], S["cls_cnt"], S["bases"])
+    ctx.solve([1e9])
+    sol = ctx.get_solve()
+    cnt = ctx.get_count()
+    ctx.close()
+    foff, coff = S["form_off"], S["cls_off"]
+    rng = np.random.default_rng(0)
+    for e in rng.choice(E, 150, replace=False):
+        K = int(S["K"][e])
+        classes = [(int(S["cls_mask"][i]), int(S["cls_cnt"][i])) for i in range(int(coff[e]), int(coff[e + 1]))]
+        n_total = float(sum(c for _, c in classes))
+        assert int(cnt["n_valid"][0, e]) == int(n_total)
+        G = []
+        for k in range(K):
+            f = int(foff[e]) + k
+            idx = S["form_seg_idx"][int(S["form_seg_off"][f]):int(S["form_seg_off"][f + 1])]
+            lens = (S["seg_end"] - S["seg_start"])[int(S["seg_off"][e]) + idx]
+            ars = api.ars_length("SHORT_READ", 75, lens)
+            G.append(1.0 / ars if ars > 0 else 0.0)
+        th, ll, it = _numpy_em(K, G, classes, n_total)
+        assert int(sol["iters"][e]) == it, (e, K, sol["iters"][e], it)
+        for k in range(K):
+            assert num_close(float(sol["theta"][int(foff[e]) + k]), float(th[k])), (e, k)
+        assert num_close(float(sol["loglik"][e]), float(ll)), e
