@@ -264,9 +264,12 @@ def run_ours(args):
     cnt, sol = ctx.get_count(), ctx.get_solve()
 
     # ---- end to end through the C ABI with host buffers ---------------------------------------
-    pinned = {k: reads[k].cpu().pin_memory() for k in ("blk_off", "blk", "read_cs", "line_num")}
-    host_reads = api.Reads.from_torch(pinned["blk_off"], pinned["blk"], pinned["read_cs"], pinned["line_num"],
-                                      reads["chrom_names"], reads["strand_names"])
+    # compact wire format: blocks per read (u8) instead of CSR offsets, implicit line numbers
+    blk_cnt = (reads["blk_off"][1:] - reads["blk_off"][:-1]).to(torch.uint8)
+    pinned = {"blk": reads["blk"].cpu().pin_memory(), "read_cs": reads["read_cs"].cpu().pin_memory(),
+              "blk_cnt": blk_cnt.cpu().pin_memory()}
+    host_reads = api.Reads.from_torch(None, pinned["blk"], pinned["read_cs"], None, reads["chrom_names"],
+                                      reads["strand_names"], blk_cnt=pinned["blk_cnt"])
 
     def step_e2e():
         ctx.set_reads(0, "SHORT_READ", R, host_reads)

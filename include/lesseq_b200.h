@@ -107,18 +107,20 @@ typedef struct lsq_event_tables {
 typedef struct lsq_packed_reads {
     uint64_t n_reads;
     uint64_t n_blocks;       /* < 2^32 */
-    const uint32_t *blk_off; /* [n_reads+1] CSR into blk / blk_cs */
+    const uint32_t *blk_off; /* [n_reads+1] CSR into blk / blk_cs; may be NULL when blk_cnt is given */
     const int32_t *blk;      /* [2*n_blocks] interleaved (start0, end) */
     const uint32_t *read_cs; /* [n_reads] bits 0-15 chromosome id, 16-23 strand id (file dictionaries),
                                 bit 31 LSQ_READ_MIXED: per-block values are in blk_cs */
     const uint32_t *blk_cs;  /* [n_blocks] same encoding per block; may be NULL if no read is MIXED */
-    const uint32_t *line_num; /* [n_reads] */
+    const uint32_t *line_num; /* [n_reads]; NULL = no comment/header lines in the file: line_num[i] = i + 1 */
     uint32_t n_chrom_names;
     uint32_t n_strand_names;
     const char *const *chrom_names;  /* always host memory */
     const char *const *strand_names; /* always host memory */
     uint32_t on_device;
     uint32_t reserved0;
+    const uint8_t *blk_cnt;  /* [n_reads] blocks per read (< 256); alternative to blk_off that costs a
+                                quarter of the host->device bytes (offsets are rebuilt by a device scan) */
 } lsq_packed_reads;
 
 /* Results of the counted path (count.cpp:421-492, solve.cpp:719-793), caller-owned host buffers. */

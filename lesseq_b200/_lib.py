@@ -44,6 +44,7 @@ class PackedReads(C.Structure):
         ("n_chrom_names", C.c_uint32), ("n_strand_names", C.c_uint32),
         ("chrom_names", c_strp), ("strand_names", c_strp),
         ("on_device", C.c_uint32), ("reserved0", C.c_uint32),
+        ("blk_cnt", C.c_void_p),
     ]
 
 

@@ -146,20 +146,28 @@ class Reads:
         return self
 
     @classmethod
-    def from_torch(cls, blk_off, blk, read_cs, line_num, chrom_names, strand_names, blk_cs=None):
-        """Tensors must be contiguous int32 (bit patterns of the uint32 fields); CUDA tensors are
-        borrowed (on_device=1), CPU tensors (pinned or not) are host buffers."""
+    def from_torch(cls, blk_off, blk, read_cs, line_num, chrom_names, strand_names, blk_cs=None, blk_cnt=None):
+        """Tensors must be contiguous int32 (bit patterns of the uint32 fields; blk_cnt uint8); CUDA
+        tensors are borrowed (on_device=1), CPU tensors (pinned or not) are host buffers.  Compact
+        wire format: pass blk_off=None with blk_cnt (blocks per read) and/or line_num=None (implicit
+        1..n)."""
         self = cls()
-        ts = [blk_off, blk, read_cs, line_num] + ([blk_cs] if blk_cs is not None else [])
-        dev = blk_off.is_cuda
+        ts = [t for t in (blk_off, blk, read_cs, line_num, blk_cs) if t is not None]
+        dev = blk.is_cuda
         for t in ts:
             assert t.is_contiguous() and t.element_size() == 4 and t.is_cuda == dev
+        if blk_cnt is not None:
+            assert blk_cnt.is_contiguous() and blk_cnt.element_size() == 1 and blk_cnt.is_cuda == dev
+            ts.append(blk_cnt)
+            self.view.blk_cnt = blk_cnt.data_ptr()
+        assert blk_off is not None or blk_cnt is not None
         self._keep += ts
         v = self.view
         v.n_reads = read_cs.numel()
         v.n_blocks = blk.numel() // 2
-        v.blk_off, v.blk, v.read_cs, v.line_num = (blk_off.data_ptr(), blk.data_ptr(), read_cs.data_ptr(),
-                                                   line_num.data_ptr())
+        v.blk, v.read_cs = blk.data_ptr(), read_cs.data_ptr()
+        v.blk_off = blk_off.data_ptr() if blk_off is not None else None
+        v.line_num = line_num.data_ptr() if line_num is not None else None
         if blk_cs is not None:
             v.blk_cs = blk_cs.data_ptr()
         v.on_device = 1 if dev else 0
@@ -177,7 +185,8 @@ class Reads:
     def host_bytes(self):
         """Bytes lsq_set_reads copies host->device for this read set."""
         n, nb = self.n_reads, self.n_blocks
-        return (n + 1) * 4 + nb * 8 + n * 4 + n * 4
+        v = self.view
+        return ((n + 1) * 4 if v.blk_off else n) + nb * 8 + n * 4 + (n * 4 if v.line_num else 0)
 
 
 class Context:

@@ -110,6 +110,7 @@ int lsqh_reads_view(const lsqh_reads *r, lsq_packed_reads *v) {
     v->chrom_names = r->chrom_ptrs.data();
     v->strand_names = r->strand_ptrs.data();
     v->on_device = 0;
+    v->blk_cnt = nullptr;
     return LSQ_OK;
 }
 

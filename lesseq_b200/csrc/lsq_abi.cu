@@ -11,6 +11,8 @@
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
 
 #include "../../include/lesseq_b200.h"
 #include "lsq_kernels.cuh"
@@ -62,6 +64,10 @@ cudaError_t upload(DevBuf &b, const std::vector<T> &v, cudaStream_t s) {
     return cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
 }
 
+struct U8ToU32 {
+    __host__ __device__ uint32_t operator()(uint8_t v) const { return (uint32_t)v; }
+};
+
 struct ReadSet {
     bool declared = false, injected = false, borrowed = false;
     uint32_t type = 0;
@@ -69,7 +75,7 @@ struct ReadSet {
     uint64_t n_reads = 0, n_blocks = 0;
     uint32_t n_file_strands = 0;
     // inputs (owned copies or borrowed device pointers)
-    DevBuf d_blk_off, d_blk, d_read_cs, d_blk_cs, d_line_num;
+    DevBuf d_blk_off, d_blk, d_read_cs, d_blk_cs, d_line_num, d_blk_cnt, d_scan_tmp;
     const uint32_t *blk_off = nullptr, *read_cs = nullptr, *blk_cs = nullptr, *line_num = nullptr;
     const int2 *blk = nullptr;
     DevBuf d_chrom_remap, d_strand_tbl;
@@ -273,36 +279,65 @@ int lsq_set_reads(lsq_ctx *c, uint32_t m, uint32_t read_type, uint64_t read_leng
     rs.n_blocks = r->n_blocks;
     rs.n_file_strands = r->n_strand_names;
     rs.borrowed = r->on_device != 0;
-    if (rs.borrowed) {
-        rs.blk_off = r->blk_off;
-        rs.blk = reinterpret_cast<const int2 *>(r->blk);
-        rs.read_cs = r->read_cs;
-        rs.blk_cs = r->blk_cs;
-        rs.line_num = r->line_num;
-    } else {
+    if (!r->blk_off && !r->blk_cnt) return fail(LSQ_ERR_ARG, "lsq_set_reads: blk_off or blk_cnt is required");
+    {
         const size_t n = r->n_reads, nb = r->n_blocks;
-        LSQ_CUDA(rs.d_blk_off.ensure((n + 1) * 4));
-        LSQ_CUDA(rs.d_blk.ensure(std::max<size_t>(nb, 1) * 8));
-        LSQ_CUDA(rs.d_read_cs.ensure(std::max<size_t>(n, 1) * 4));
-        LSQ_CUDA(rs.d_line_num.ensure(std::max<size_t>(n, 1) * 4));
-        LSQ_CUDA(cudaMemcpyAsync(rs.d_blk_off.p, r->blk_off, (n + 1) * 4, cudaMemcpyHostToDevice, s));
-        if (nb) LSQ_CUDA(cudaMemcpyAsync(rs.d_blk.p, r->blk, nb * 8, cudaMemcpyHostToDevice, s));
-        if (n) LSQ_CUDA(cudaMemcpyAsync(rs.d_read_cs.p, r->read_cs, n * 4, cudaMemcpyHostToDevice, s));
-        if (n) LSQ_CUDA(cudaMemcpyAsync(rs.d_line_num.p, r->line_num, n * 4, cudaMemcpyHostToDevice, s));
-        rs.blk_cs = nullptr;
-        if (r->blk_cs) {
-            bool any_mixed = false;
-            for (size_t i = 0; i < n && !any_mixed; ++i) any_mixed = (r->read_cs[i] & LSQ_READ_MIXED) != 0;
-            if (any_mixed) {
-                LSQ_CUDA(rs.d_blk_cs.ensure(std::max<size_t>(nb, 1) * 4));
-                LSQ_CUDA(cudaMemcpyAsync(rs.d_blk_cs.p, r->blk_cs, nb * 4, cudaMemcpyHostToDevice, s));
-                rs.blk_cs = rs.d_blk_cs.as<uint32_t>();
+        const cudaMemcpyKind kind = rs.borrowed ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        if (rs.borrowed) {
+            rs.blk = reinterpret_cast<const int2 *>(r->blk);
+            rs.read_cs = r->read_cs;
+            rs.blk_cs = r->blk_cs;
+            rs.line_num = r->line_num;
+            rs.blk_off = r->blk_off;
+        } else {
+            LSQ_CUDA(rs.d_blk.ensure(std::max<size_t>(nb, 1) * 8));
+            LSQ_CUDA(rs.d_read_cs.ensure(std::max<size_t>(n, 1) * 4));
+            if (nb) LSQ_CUDA(cudaMemcpyAsync(rs.d_blk.p, r->blk, nb * 8, kind, s));
+            if (n) LSQ_CUDA(cudaMemcpyAsync(rs.d_read_cs.p, r->read_cs, n * 4, kind, s));
+            rs.line_num = nullptr;
+            if (r->line_num) {
+                LSQ_CUDA(rs.d_line_num.ensure(std::max<size_t>(n, 1) * 4));
+                if (n) LSQ_CUDA(cudaMemcpyAsync(rs.d_line_num.p, r->line_num, n * 4, kind, s));
+                rs.line_num = rs.d_line_num.as<uint32_t>();
+            }
+            rs.blk_cs = nullptr;
+            if (r->blk_cs) {
+                bool any_mixed = false;
+                for (size_t i = 0; i < n && !any_mixed; ++i) any_mixed = (r->read_cs[i] & LSQ_READ_MIXED) != 0;
+                if (any_mixed) {
+                    LSQ_CUDA(rs.d_blk_cs.ensure(std::max<size_t>(nb, 1) * 4));
+                    LSQ_CUDA(cudaMemcpyAsync(rs.d_blk_cs.p, r->blk_cs, nb * 4, kind, s));
+                    rs.blk_cs = rs.d_blk_cs.as<uint32_t>();
+                }
+            }
+            rs.blk = rs.d_blk.as<int2>();
+            rs.read_cs = rs.d_read_cs.as<uint32_t>();
+            rs.blk_off = nullptr;
+            if (r->blk_off) {
+                LSQ_CUDA(rs.d_blk_off.ensure((n + 1) * 4));
+                LSQ_CUDA(cudaMemcpyAsync(rs.d_blk_off.p, r->blk_off, (n + 1) * 4, kind, s));
+                rs.blk_off = rs.d_blk_off.as<uint32_t>();
             }
         }
-        rs.blk_off = rs.d_blk_off.as<uint32_t>();
-        rs.blk = rs.d_blk.as<int2>();
-        rs.read_cs = rs.d_read_cs.as<uint32_t>();
-        rs.line_num = rs.d_line_num.as<uint32_t>();
+        if (!rs.blk_off) {  // rebuild the CSR offsets from the per-read block counts on the device
+            const uint8_t *cnt = r->blk_cnt;
+            if (!rs.borrowed) {
+                LSQ_CUDA(rs.d_blk_cnt.ensure(std::max<size_t>(n, 1)));
+                if (n) LSQ_CUDA(cudaMemcpyAsync(rs.d_blk_cnt.p, r->blk_cnt, n, kind, s));
+                cnt = rs.d_blk_cnt.as<uint8_t>();
+            }
+            LSQ_CUDA(rs.d_blk_off.ensure((n + 1) * 4));
+            LSQ_CUDA(cudaMemsetAsync(rs.d_blk_off.p, 0, 4, s));
+            if (n) {
+                cub::TransformInputIterator<uint32_t, U8ToU32, const uint8_t *> it(cnt, U8ToU32());
+                size_t tmp = 0;
+                cub::DeviceScan::InclusiveSum(nullptr, tmp, it, rs.d_blk_off.as<uint32_t>() + 1, (int64_t)n, s);
+                LSQ_CUDA(rs.d_scan_tmp.ensure(std::max<size_t>(tmp, 1)));
+                LSQ_CUDA(cub::DeviceScan::InclusiveSum(rs.d_scan_tmp.p, tmp, it, rs.d_blk_off.as<uint32_t>() + 1,
+                                                       (int64_t)n, s));
+            }
+            rs.blk_off = rs.d_blk_off.as<uint32_t>();
+        }
     }
     // dictionaries: file chromosome ids -> annotation ids; strand order table
     std::vector<uint32_t> remap(std::max<uint32_t>(r->n_chrom_names, 1), 0xFFFFFFFFu);

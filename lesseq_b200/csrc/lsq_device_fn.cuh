@@ -413,7 +413,8 @@ LSQ_COLD bool tie_resolve(const CountParams &P, const EvHdr &h, const ReadView &
     uint32_t mode = h.flags & EV_TIE_MASK;
     if (mode == 0u) return false;
     if (mode == 1u) return true;
-    uint32_t ln = LSQ_LD(P.line_num + rv.read_index());
+    // a read set without comment/header lines carries no line numbers: read i is "read-<i+1>"
+    uint32_t ln = P.line_num ? LSQ_LD(P.line_num + rv.read_index()) : rv.read_index() + 1u;
     return digits_less(ln, P.T.tie_pool + h.tie_off, h.tie_len);
 }
 
