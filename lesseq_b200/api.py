@@ -208,7 +208,7 @@ class Context:
     __del__ = close
 
     def upload_events(self, ann):
-        t = ann.tables if isinstance(ann, Annotation) else ann
+        t = ann.tables if hasattr(ann, "tables") else ann
         check(self._lib.lsq_upload_events(self._c, C.byref(t)))
         self.E, self.F, self.M = t.n_events, t.n_forms, 0
         self._ann = ann
