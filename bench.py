@@ -231,17 +231,15 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def gather(cnt, sol):
-        return lsd.gather_results(cnt, sol) if world > 1 else None
+    ctx.set_reads(0, "SHORT_READ", R, dev_reads)
+    gatherer = lsd.DeviceGather(ann.n_events, ann.n_forms, 1) if world > 1 else None
 
     # ---- device-resident pass ---------------------------------------------------------------
-    ctx.set_reads(0, "SHORT_READ", R, dev_reads)
-
     def step_resident():
         ctx.count()
         ctx.solve(trb)
         if world > 1:
-            gather(ctx.get_count(), ctx.get_solve())
+            gatherer.gather(ctx)  # one NCCL all_gather of the result rows, device to device
 
     for _ in range(args.warmup):
         step_resident()
@@ -275,10 +273,12 @@ def run_ours(args):
         ctx.set_reads(0, "SHORT_READ", R, host_reads)
         ctx.count()
         ctx.solve(trb)
-        c, s = ctx.get_count(), ctx.get_solve()
         if world > 1:
-            gather(c, s)
-        return c, s
+            gatherer.gather(ctx)
+            g = gatherer.unpack() if rank == 0 else None  # rank 0 reads the whole job's results
+            torch.cuda.synchronize()
+            return ctx.get_count(), ctx.get_solve(), g
+        return ctx.get_count(), ctx.get_solve(), None
 
     for _ in range(min(args.warmup, 2)):
         step_e2e()
@@ -286,12 +286,15 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
-        c2, s2 = step_e2e()
+        c2, s2, gathered = step_e2e()
     e1.record(stream)
     barrier()
     e2e_ms_local = e0.elapsed_time(e1) / args.steps
     clocks = sampler.stop() if sampler else None
     assert np.array_equal(c2["iso_count"], cnt["iso_count"]) and np.array_equal(s2["theta"], sol["theta"])
+    if gathered is not None:  # rank 0's own shard comes first in gene-rank order
+        assert np.array_equal(gathered["theta"][:ann.n_forms], sol["theta"])
+        assert gathered["iters"].shape[0] == len(ids)
 
     red = torch.tensor([ms_local, e2e_ms_local], dtype=torch.float64, device="cuda")
     if world > 1:

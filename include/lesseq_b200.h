@@ -188,6 +188,16 @@ int lsq_set_classes(lsq_ctx *ctx, uint32_t m, uint32_t read_type, uint64_t read_
 int lsq_solve(lsq_ctx *ctx, const double *total_read_bases, uint32_t n_methods);
 int lsq_get_solve(lsq_ctx *ctx, lsq_solve_out *out);
 
+/* Device pointers of the result arrays (valid until the next lsq_upload_events), for callers that
+ * move results between GPUs without a host round trip (NCCL gather of gene-range shards). */
+typedef struct lsq_device_results {
+    const uint64_t *n_valid, *bases, *iso_count; /* [M*E], [M*E], [n_forms] */
+    const double *theta, *rpkm;                  /* [n_forms] */
+    const double *loglik, *ll_per_read;          /* [E] */
+    const uint32_t *iters;                       /* [E] */
+} lsq_device_results;
+int lsq_get_device_results(lsq_ctx *ctx, lsq_device_results *out);
+
 int lsq_get_timings(lsq_ctx *ctx, lsq_timings *out);
 
 /* ARS length of one form (accessible_read_starts.h:48-89, 184-189, 221-274), host helper. */

@@ -67,6 +67,11 @@ class Timings(C.Structure):
     ]
 
 
+class DeviceResults(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("n_valid", "bases", "iso_count", "theta", "rpkm", "loglik", "ll_per_read",
+                                           "iters")]
+
+
 class LsqError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("lesseq_b200 error %d: %s" % (code, msg))
@@ -91,6 +96,7 @@ SYMBOLS = {
     "lsq_solve": (C.c_int, [C.c_void_p, c_f64p, C.c_uint32]),
     "lsq_get_solve": (C.c_int, [C.c_void_p, C.POINTER(SolveOut)]),
     "lsq_get_timings": (C.c_int, [C.c_void_p, C.POINTER(Timings)]),
+    "lsq_get_device_results": (C.c_int, [C.c_void_p, C.POINTER(DeviceResults)]),
     "lsq_ars_length": (C.c_uint64, [C.c_uint32, C.c_uint64, c_u64p, C.c_uint32]),
     "lsqh_annotation_load": (C.c_int, [C.c_char_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
                                        C.POINTER(C.c_void_p)]),

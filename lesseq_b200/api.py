@@ -260,6 +260,26 @@ class Context:
         check(self._lib.lsq_get_solve(self._c, C.byref(out)))
         return {"theta": th, "rpkm": rp, "loglik": ll, "ll_per_read": lp, "iters": it}
 
+    def device_results(self):
+        """Zero-copy torch views (CUDA) of the result arrays; uint64 arrays are viewed as int64."""
+        import torch
+        r = _lib.DeviceResults()
+        check(self._lib.lsq_get_device_results(self._c, C.byref(r)))
+        E, F, M = self.E, self.F, self.M
+
+        class _Cai:  # __cuda_array_interface__ carrier
+            def __init__(self, ptr, n, typestr):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (int(ptr), False),
+                                                 "version": 2}
+
+        def view(ptr, n, typestr):
+            return torch.as_tensor(_Cai(ptr, n, typestr), device="cuda") if n else torch.empty(0, device="cuda")
+
+        return {"n_valid": view(r.n_valid, M * E, "<i8"), "bases": view(r.bases, M * E, "<i8"),
+                "iso_count": view(r.iso_count, F, "<i8"), "theta": view(r.theta, F, "<f8"),
+                "rpkm": view(r.rpkm, F, "<f8"), "loglik": view(r.loglik, E, "<f8"),
+                "ll_per_read": view(r.ll_per_read, E, "<f8"), "iters": view(r.iters, E, "<i4")}
+
     def sync(self):
         check(self._lib.lsq_ctx_sync(self._c))
 

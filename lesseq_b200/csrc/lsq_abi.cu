@@ -264,8 +264,8 @@ int lsq_set_reads(lsq_ctx *c, uint32_t m, uint32_t read_type, uint64_t read_leng
     if (m >= LSQ_MAX_METHODS) return fail(LSQ_ERR_RANGE, "read set index >= LSQ_MAX_METHODS");
     if (read_type != LSQ_READ_MEDIUM && read_type != LSQ_READ_SHORT)
         return fail(LSQ_ERR_FORMAT, "unknown read type");
-    if (r->n_blocks > 0xFFFFFFFFull || r->n_reads > 0xFFFFFFF0ull)
-        return fail(LSQ_ERR_RANGE, "read set exceeds 2^32 reads or blocks");
+    if (r->n_blocks + r->n_reads > 0xFFFFFFF0ull)
+        return fail(LSQ_ERR_RANGE, "read set exceeds 2^32 reads + blocks");
     if (r->n_strand_names > 256 || r->n_chrom_names > 65536)
         return fail(LSQ_ERR_RANGE, "read dictionaries too large");
     LSQ_CUDA(cudaSetDevice(c->device));
@@ -438,6 +438,7 @@ static void fill_solve_params(lsq_ctx *c, lsq::SolveParams &P) {
     P.ll_per_read = c->d_llpr.as<double>();
     P.iters = c->d_iters.as<uint32_t>();
     P.max_iters = 10000000u;
+    P.pairs_valid = c->d_counters.as<unsigned long long>() + 110;
 }
 
 static int run_finalize(lsq_ctx *c) {
@@ -445,6 +446,7 @@ static int run_finalize(lsq_ctx *c) {
     lsq::SolveParams P;
     fill_solve_params(c, P);
     if (c->E) {
+        cudaMemsetAsync(P.pairs_valid, 0, 8, c->stream);
         lsq::lsq_finalize_kernel<<<(c->E + 127) / 128, 128, 0, c->stream>>>(P);
         LSQ_CUDA(cudaGetLastError());
         c->tm.launches++;
@@ -556,7 +558,6 @@ int lsq_count(lsq_ctx *c) {
         acc[3] += f;
         tm.reads_in += n;
         tm.reads_kept += c->h_counters[(size_t)m * 4 + 0];
-        tm.pairs_valid += c->h_counters[(size_t)m * 4 + 2];
         // algorithmic bytes of the count kernel: key (4) + record (8) per kept read, plus the ext
         // entry (8-byte header + 8 bytes per kept block) of every GENERAL-class read
         tm.count_bytes += c->h_counters[(size_t)m * 4 + 0] * 12ull + c->h_counters[(size_t)m * 4 + 1] * 8ull;
@@ -568,7 +569,10 @@ int lsq_count(lsq_ctx *c) {
     rc = run_finalize(c);
     if (rc) return rc;
     LSQ_CUDA(cudaEventRecord(c->ev[5], s));
+    unsigned long long pv = 0;
+    LSQ_CUDA(cudaMemcpyAsync(&pv, c->d_counters.as<unsigned long long>() + 110, 8, cudaMemcpyDeviceToHost, s));
     LSQ_CUDA(cudaStreamSynchronize(s));
+    tm.pairs_valid = pv;
     float f;
     LSQ_CUDA(cudaEventElapsedTime(&f, c->ev[4], c->ev[5]));
     tm.filter_ms = acc[0];
@@ -713,6 +717,20 @@ int lsq_get_solve(lsq_ctx *c, lsq_solve_out *o) {
     if (o->iters && E) LSQ_CUDA(cudaMemcpyAsync(o->iters, c->d_iters.p, E * 4, cudaMemcpyDeviceToHost, s));
     if (o->se) return fail(LSQ_ERR_ARG, "standard errors are not available in this build");
     LSQ_CUDA(cudaStreamSynchronize(s));
+    return LSQ_OK;
+}
+
+int lsq_get_device_results(lsq_ctx *c, lsq_device_results *o) {
+    if (!c || !o) return fail(LSQ_ERR_ARG, "lsq_get_device_results: null argument");
+    if (!c->finalized) return fail(LSQ_ERR_STATE, "lsq_get_device_results before lsq_count");
+    o->n_valid = c->d_n_valid.as<uint64_t>();
+    o->bases = c->d_bases_out.as<uint64_t>();
+    o->iso_count = c->d_iso.as<uint64_t>();
+    o->theta = c->d_theta.as<double>();
+    o->rpkm = c->d_rpkm.as<double>();
+    o->loglik = c->d_ll.as<double>();
+    o->ll_per_read = c->d_llpr.as<double>();
+    o->iters = c->d_iters.as<uint32_t>();
     return LSQ_OK;
 }
 

@@ -78,23 +78,37 @@ LSQ_HD uint32_t find_piece(const Tables &T, uint32_t c, int32_t x, PieceInfo &ou
             j = LSQ_LD(T.bp_bkt + b0 + b + 1);
         }
     }
-    // number of pieces with pos <= x, searched in [i, j)
-    if (j - i > 8u) {
-        while (i < j) {
-            const uint32_t mid = (i + j) >> 1;
-            if (LSQ_LD(&T.pinfo[mid].pos) <= x) i = mid + 1;
-            else j = mid;
-        }
+    // pieces [i, j) start inside the bucket of x; piece i-1 (if any) starts before it.  The three
+    // candidates i-1, i, i+1 are fetched with independent 16-byte loads; only a bucket holding more
+    // than two piece starts at or below x needs the search loop.
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    const uint4 r0 = i > lo ? LSQ_LD(reinterpret_cast<const uint4 *>(T.pinfo + (i - 1))) : z;
+    const uint4 r1 = i < j ? LSQ_LD(reinterpret_cast<const uint4 *>(T.pinfo + i)) : z;
+    const uint4 r2 = i + 1 < j ? LSQ_LD(reinterpret_cast<const uint4 *>(T.pinfo + (i + 1))) : z;
+    uint4 raw;
+    uint32_t p;
+    if (!(i < j) || (int32_t)r1.x > x) {
+        if (i == lo) return 0xFFFFFFFFu;
+        raw = r0;
+        p = i - 1;
+    } else if (!(i + 1 < j) || (int32_t)r2.x > x) {
+        raw = r1;
+        p = i;
     } else {
-        while (i < j && LSQ_LD(&T.pinfo[i].pos) <= x) ++i;
+        uint32_t a = i + 2, b = j;  // number of pieces with pos <= x among [i+2, j)
+        while (a < b) {
+            const uint32_t mid = (a + b) >> 1;
+            if (LSQ_LD(&T.pinfo[mid].pos) <= x) a = mid + 1;
+            else b = mid;
+        }
+        p = a - 1;
+        raw = LSQ_LD(reinterpret_cast<const uint4 *>(T.pinfo + p));
     }
-    if (i == lo) return 0xFFFFFFFFu;
-    const uint4 raw = LSQ_LD(reinterpret_cast<const uint4 *>(T.pinfo + (i - 1)));
     out.pos = (int32_t)raw.x;
     out.cov_end = (int32_t)raw.y;
     out.stab_off = raw.z;
     out.stab_n = raw.w;
-    return i - 1;
+    return p;
 }
 
 // In-place "erase [b,e) then optionally insert v at b" on one component (.x or .y) of an int2 list.

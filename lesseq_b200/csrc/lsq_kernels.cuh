@@ -21,12 +21,13 @@ namespace lsq {
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
 __global__ void __launch_bounds__(256) lsq_filter_kernel(FilterParams P, int2 *__restrict__ work) {
-    __shared__ uint32_t s_need[8], s_kept[8];
-    __shared__ unsigned long long s_base;
+    __shared__ uint32_t s_cnt[4];  // kept reads, GENERAL reads, ext slots of GENERAL reads, warps done
     const Tables &T = P.T;
     const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool in_range = r < P.n_reads;
-    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint32_t lane = lane_id();
+    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
     FilteredRead fr;
     fr.n = 0;
     fr.key = KEY_DROPPED(T);
@@ -36,53 +37,46 @@ __global__ void __launch_bounds__(256) lsq_filter_kernel(FilterParams P, int2 *_
     if (in_range) fr = filter_read(P, r, work);
     const bool kept = fr.key != KEY_DROPPED(T);
     const bool general = kept && fr.key >= T.n_pieces;
-    // allocation of ext entries (1 + n slots per GENERAL read): warp scan, block scan over the 8
-    // warp totals, ONE global atomic per block for the cursor and one for the kept count
-    const uint32_t need = general ? fr.n + 1u : 0u;
-    uint32_t incl = need;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-        if (lane >= (uint32_t)d) incl += v;
+    if (in_range) {
+        ReadRec rec;
+        if (general) {
+            // the ext entry of read r lives at slot blk_off[r] + r: 1 header + n <= 1 + raw blocks,
+            // so no allocation is needed and the slots of different reads never overlap
+            const uint32_t base = __ldg(P.blk_off + r);
+            const uint32_t off = base + (uint32_t)r;
+            P.ext[off] = make_int2((int32_t)(uint32_t)r, (int32_t)((fr.strand << 24) | (fr.n & 0xFFFFFFu)));
+            if (fr.n == 1) {
+                P.ext[off + 1] = fr.first;
+            } else {
+                for (uint32_t i = 0; i < fr.n; ++i) P.ext[off + 1 + i] = work[base + i];
+            }
+            rec.x = off;
+            rec.y = fr.n;  // used only for the byte accounting of the count kernel
+        } else {
+            rec.x = (uint32_t)fr.first.x;
+            rec.y = (uint32_t)(fr.first.y - fr.first.x) | (fr.strand << 16);
+        }
+        P.rkey[r] = fr.key;
+        P.rec[r] = rec;
     }
+    // kept / GENERAL counts: warp ballots -> shared counters -> the last warp of the block to
+    // finish issues the two global reductions (no block-wide barrier on the way)
     const unsigned kept_mask = __ballot_sync(0xFFFFFFFFu, kept);
     const unsigned gen_mask = __ballot_sync(0xFFFFFFFFu, general);
-    if (lane == 31) s_need[warp] = incl;
-    if (lane == 0) s_kept[warp] = (uint32_t)__popc(kept_mask) | ((uint32_t)__popc(gen_mask) << 16);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t tot = 0, k = 0, g = 0;
-        for (int w = 0; w < 8; ++w) {
-            const uint32_t t = s_need[w];
-            s_need[w] = tot;
-            tot += t;
-            k += s_kept[w] & 0xFFFFu;
-            g += s_kept[w] >> 16;
+    const uint32_t gen_slots = __reduce_add_sync(0xFFFFFFFFu, general ? fr.n + 1u : 0u);
+    if (lane == 0) {
+        if (kept_mask) atomicAdd(&s_cnt[0], (uint32_t)__popc(kept_mask));
+        if (gen_mask) atomicAdd(&s_cnt[1], (uint32_t)__popc(gen_mask));
+        if (gen_slots) atomicAdd(&s_cnt[2], gen_slots);
+        __threadfence_block();
+        const uint32_t done = atomicAdd(&s_cnt[3], 1u) + 1u;
+        if (done == (blockDim.x >> 5)) {
+            const uint32_t k = atomicAdd(&s_cnt[0], 0u), g = atomicAdd(&s_cnt[1], 0u), sl = atomicAdd(&s_cnt[2], 0u);
+            if (k) atomicAdd(P.counters + 0, (unsigned long long)k);
+            if (sl) atomicAdd(P.counters + 1, (unsigned long long)sl);
+            if (g) atomicAdd(P.counters + 3, (unsigned long long)g);
         }
-        s_base = tot ? atomicAdd(P.counters + 1, (unsigned long long)tot) : 0ull;
-        if (k) atomicAdd(P.counters + 0, (unsigned long long)k);
-        if (g) atomicAdd(P.counters + 3, (unsigned long long)g);
     }
-    __syncthreads();
-    if (!in_range) return;
-    ReadRec rec;
-    if (general) {
-        const uint32_t off = (uint32_t)(s_base + s_need[warp] + incl - need);
-        P.ext[off] = make_int2((int32_t)(uint32_t)r, (int32_t)((fr.strand << 24) | (fr.n & 0xFFFFFFu)));
-        if (fr.n == 1) {
-            P.ext[off + 1] = fr.first;
-        } else {
-            const uint32_t base = __ldg(P.blk_off + r);
-            for (uint32_t i = 0; i < fr.n; ++i) P.ext[off + 1 + i] = work[base + i];
-        }
-        rec.x = off;
-        rec.y = 0;
-    } else {
-        rec.x = (uint32_t)fr.first.x;
-        rec.y = (uint32_t)(fr.first.y - fr.first.x) | (fr.strand << 16);
-    }
-    P.rkey[r] = fr.key;
-    P.rec[r] = rec;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -147,9 +141,10 @@ __device__ __forceinline__ ChunkTables chunk_tables(const CountParams &P, unsign
 __device__ __forceinline__ void aggregate_runs(const CountParams &P, uint32_t lane, bool head_has, unsigned run_mask,
                                                uint32_t run_end, bool single_run, uint32_t cm, uint32_t ml,
                                                uint32_t slot_off, uint32_t x) {
-    const unsigned b1 = __ballot_sync(0xFFFFFFFFu, cm == 1u);
-    const unsigned b2 = __ballot_sync(0xFFFFFFFFu, cm == 2u);
-    const unsigned b3 = __ballot_sync(0xFFFFFFFFu, cm == 3u);
+    // cm is 1, 2 or 3 for events with at most two forms (bit k = compatible with form k);
+    // larger tables were updated by the caller and arrive as the 0x80000000 marker
+    const unsigned f0 = __ballot_sync(0xFFFFFFFFu, (cm & 1u) != 0u);
+    const unsigned f1 = __ballot_sync(0xFFFFFFFFu, (cm & 2u) != 0u);
     uint32_t v;
     if (single_run) {  // warp-uniform: the whole warp is one run
         v = __reduce_add_sync(0xFFFFFFFFu, ml);
@@ -162,7 +157,8 @@ __device__ __forceinline__ void aggregate_runs(const CountParams &P, uint32_t la
         }
     }
     if (head_has) {
-        const uint32_t c1 = __popc(b1 & run_mask), c2 = __popc(b2 & run_mask), c3 = __popc(b3 & run_mask);
+        const uint32_t c1 = __popc(f0 & ~f1 & run_mask), c2 = __popc(f1 & ~f0 & run_mask),
+                       c3 = __popc(f0 & f1 & run_mask);
         if (c1) atomicAdd(P.slot_cnt + slot_off, (unsigned long long)c1);
         if (c2) atomicAdd(P.slot_cnt + slot_off + 1u, (unsigned long long)c2);
         if (c3) atomicAdd(P.slot_cnt + slot_off + 2u, (unsigned long long)c3);
@@ -207,7 +203,6 @@ __global__ void __launch_bounds__(COUNT_BLOCK, GENERAL ? 3 : 5) lsq_count_kernel
         }
     };
     if (producer && blockIdx.x < n_chunks) issue(blockIdx.x, 0);
-    unsigned long long my_valid = 0;
     uint32_t j = 0;
     for (unsigned long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x, ++j) {
         const uint32_t stage = j & 1u;
@@ -272,7 +267,6 @@ __global__ void __launch_bounds__(COUNT_BLOCK, GENERAL ? 3 : 5) lsq_count_kernel
                         }
                     }
                     aggregate_runs(P, lane, head && has, run_mask, run_end, single_run, cm, ml, slot_off, x);
-                    my_valid += (cm != 0);
                 }
             } else {
                 ReadView rv;
@@ -312,15 +306,12 @@ __global__ void __launch_bounds__(COUNT_BLOCK, GENERAL ? 3 : 5) lsq_count_kernel
                         }
                     }
                     aggregate_runs(P, lane, head && has, run_mask, run_end, single_run, cm, ml, slot_off, x);
-                    my_valid += (cm != 0);
                 }
             }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[stage]);  // this warp no longer reads the stage
     }
-    const unsigned vsum = __reduce_add_sync(0xFFFFFFFFu, (unsigned)my_valid);
-    if (lane == 0 && vsum) atomicAdd(P.stats, (unsigned long long)vsum);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -367,6 +358,7 @@ __global__ void __launch_bounds__(128) lsq_finalize_kernel(SolveParams P) {
                 if ((mk >> k) & 1ull) iso[k] += c;
         }
         P.n_valid[(size_t)m * P.T.E + h.out_ev] = nv;
+        if (nv && P.pairs_valid) atomicAdd(P.pairs_valid, nv);
         P.bases_out[(size_t)m * P.T.E + h.out_ev] = P.bases[(size_t)m * P.T.E + x];
     }
     for (uint32_t k = 0; k < h.K; ++k) P.iso_count[h.out_form + k] = iso[k];

@@ -146,6 +146,7 @@ struct SolveParams {
     int with_se;
     int small_enabled;             // events with K <= 2 are solved by lsq_solve_small_kernel
     unsigned int *work_counter;    // dynamic event fetch of lsq_solve_small_kernel
+    unsigned long long *pairs_valid;  // finalize: total valid (read, event) pairs (statistics)
 };
 
 }  // namespace lsq

@@ -61,3 +61,59 @@ def gather_results(count, solve, root=0):
     for k, v in (solve or {}).items():
         out[k] = gather_rows(v, root)
     return out
+
+
+class DeviceGather:
+    """One NCCL all_gather per step of every rank's result arrays, device to device.
+
+    Sizes (events, forms per shard) are exchanged once at construction.  `gather(ctx)` packs the
+    context's device result arrays into one byte buffer, all-gathers it over NVLink and leaves the
+    bytes of all shards in rank order on every rank's device; `unpack()` (rank 0, outside any
+    timed region if only the device-resident state matters) reassembles numpy arrays in gene-rank
+    order."""
+
+    FIELDS = (("n_valid", 8, "M*E", np.uint64), ("bases", 8, "M*E", np.uint64), ("iso_count", 8, "F", np.uint64),
+              ("theta", 8, "F", np.float64), ("rpkm", 8, "F", np.float64), ("loglik", 8, "E", np.float64),
+              ("ll_per_read", 8, "E", np.float64), ("iters", 4, "E", np.uint32))
+
+    def __init__(self, E_local, F_local, M):
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        sizes = torch.zeros(self.world, 2, dtype=torch.int64, device=dev)
+        sizes[self.rank, 0], sizes[self.rank, 1] = E_local, F_local
+        dist.all_reduce(sizes)
+        self.sizes = sizes.cpu().numpy()
+        self.M = M
+        self.nbytes = [self._bytes(int(e), int(f)) for e, f in self.sizes]
+        self.maxb = (max(self.nbytes) + 15) // 16 * 16
+        self.send = torch.zeros(self.maxb, dtype=torch.uint8, device=dev)
+        self.recv = torch.zeros(self.world * self.maxb, dtype=torch.uint8, device=dev)
+
+    def _count(self, kind, E, F):
+        return {"M*E": self.M * E, "F": F, "E": E}[kind]
+
+    def _bytes(self, E, F):
+        return sum(w * self._count(kind, E, F) for _, w, kind, _ in self.FIELDS)
+
+    def gather(self, ctx):
+        res = ctx.device_results()
+        off = 0
+        for name, w, _, _ in self.FIELDS:
+            b = res[name].view(torch.uint8)
+            self.send[off:off + b.numel()] = b
+            off += b.numel()
+        dist.all_gather_into_tensor(self.recv, self.send)
+        return self.recv
+
+    def unpack(self):
+        raw = self.recv.cpu().numpy()
+        parts = {name: [] for name, _, _, _ in self.FIELDS}
+        for r in range(self.world):
+            E, F = int(self.sizes[r, 0]), int(self.sizes[r, 1])
+            off = r * self.maxb
+            for name, w, kind, dt in self.FIELDS:
+                n = self._count(kind, E, F)
+                a = raw[off:off + n * w].view(dt)
+                parts[name].append(a.reshape(self.M, E) if kind == "M*E" else a)
+                off += n * w
+        return {k: np.concatenate(v, axis=1 if v[0].ndim == 2 else 0) for k, v in parts.items()}

@@ -149,7 +149,7 @@ int main(int argc, char **argv) {
             FilteredRead fr = filter_read(FP, r, work.data());
             ReadRec q;
             if (fr.key != KEY_DROPPED(T) && fr.key >= T.n_pieces) {
-                uint32_t off = (uint32_t)counters[1];
+                uint32_t off = R.blk_off[r] + (uint32_t)r;
                 counters[1] += fr.n + 1;
                 ext2[off] = make_int2((int32_t)r, (int32_t)((fr.strand << 24) | (fr.n & 0xFFFFFFu)));
                 if (fr.n == 1) ext2[off + 1] = fr.first;

@@ -162,6 +162,7 @@ def _synth_case(api, tmp_path, name, n_genes, n_reads, seed, **kw):
     ("C1", 500, 200000, {}),
     ("C2", 400, 200000, {}),
     ("C4", 400, 200000, {"overhang_frac": 0.02}),
+    ("C2", 3000, 2000000, {"overhang_frac": 0.01}),
 ])
 def test_synthetic_configs_match_oracle(api, oracle_bin, tmp_path, name, n_genes, n_reads, kw):
     """BASELINE-shaped inputs at a size the oracle finishes in seconds, through the drop-in
