@@ -11,11 +11,13 @@
 #define LSQ_HD __device__ __forceinline__
 #define LSQ_COLD __device__ __noinline__  /* rare paths: kept out of line so the hot loop stays I-cache resident */
 #define LSQ_LD(p) __ldg(p)
+#define LSQ_LD_STREAM(p) __ldcs(p) /* read-once input streams: evict-first, keep L2 for the tables */
 #define LSQ_NO_UNROLL _Pragma("unroll 1")
 #else
 #define LSQ_HD inline
 #define LSQ_COLD inline
 #define LSQ_LD(p) (*(p))
+#define LSQ_LD_STREAM(p) (*(p))
 #define LSQ_NO_UNROLL
 #endif
 
@@ -176,9 +178,9 @@ LSQ_HD FilteredRead filter_read(const FilterParams &P, uint64_t r, int2 *work) {
     out.first = make_int2(0, 0);
     out.strand = 0;
     out.at_piece_start = 0;
-    const uint32_t base = LSQ_LD(P.blk_off + r);
-    const uint32_t nraw = LSQ_LD(P.blk_off + r + 1) - base;
-    const uint32_t cs0 = LSQ_LD(P.read_cs + r);
+    const uint32_t base = LSQ_LD_STREAM(P.blk_off + r);
+    const uint32_t nraw = LSQ_LD_STREAM(P.blk_off + r + 1) - base;
+    const uint32_t cs0 = LSQ_LD_STREAM(P.read_cs + r);
     const bool mixed = (cs0 & 0x80000000u) != 0;
     uint32_t chrom = 0xFFFFFFFFu;  // annotation id of the last registered block
     bool registered = false;
@@ -194,7 +196,7 @@ LSQ_HD FilteredRead filter_read(const FilterParams &P, uint64_t r, int2 *work) {
     first_pi.stab_n = 0;
     bool first_valid = false;
     for (uint32_t j = 0; j < nraw; ++j) {
-        int2 b = LSQ_LD(P.blk + base + j);
+        int2 b = LSQ_LD_STREAM(P.blk + base + j);
         uint32_t cs = mixed ? LSQ_LD(P.blk_cs + base + j) : cs0;
         uint32_t c = LSQ_LD(P.chrom_remap + (cs & 0xFFFFu));
         bool keep;

@@ -56,8 +56,8 @@ __global__ void __launch_bounds__(256) lsq_filter_kernel(FilterParams P, int2 *_
             rec.x = (uint32_t)fr.first.x;
             rec.y = (uint32_t)(fr.first.y - fr.first.x) | (fr.strand << 16);
         }
-        P.rkey[r] = fr.key;
-        P.rec[r] = rec;
+        __stcs(P.rkey + r, fr.key);  // streamed to the sort: do not displace the tables in L2
+        __stcs(P.rec + r, rec);
     }
     // kept / GENERAL counts: warp ballots -> shared counters -> the last warp of the block to
     // finish issues the two global reductions (no block-wide barrier on the way)
@@ -223,8 +223,8 @@ __global__ void __launch_bounds__(COUNT_BLOCK, GENERAL ? 3 : 5) lsq_count_kernel
         uint32_t key_n = 0xFFFFFFFFu;
         ReadRec rec_n = make_uint2(0u, 0u);
         if (i < end) {
-            key_n = __ldg(P.g_key + i);
-            rec_n = __ldg(P.g_rec + i);
+            key_n = __ldcs(P.g_key + i);
+            rec_n = __ldcs(P.g_rec + i);
         }
         for (int it = 0; it < COUNT_ITEMS; ++it, i += 32u) {
             if (i - lane >= end) break;  // warp-uniform
@@ -233,8 +233,8 @@ __global__ void __launch_bounds__(COUNT_BLOCK, GENERAL ? 3 : 5) lsq_count_kernel
             const ReadRec rec = rec_n;
             key_n = 0xFFFFFFFFu;
             if (it + 1 < COUNT_ITEMS && i + 32u < end) {
-                key_n = __ldg(P.g_key + i + 32u);
-                rec_n = __ldg(P.g_rec + i + 32u);
+                key_n = __ldcs(P.g_key + i + 32u);
+                rec_n = __ldcs(P.g_rec + i + 32u);
             }
             uint32_t so = 0, nent = 0;
             if (act) {
