@@ -137,8 +137,10 @@ typedef struct lsq_solve_out {
     double *loglik;      /* [E] reads_log_likelihood at the final theta */
     double *ll_per_read; /* [E] the printed column: loglik / sum n_valid, or 0 */
     uint32_t *iters;     /* [E] EM iterations executed (0: closed-form branches) */
-    double *se;          /* [n_forms] or NULL: standard errors from the observed Fisher
-                            information (extension; the reference never computes them) */
+    double *se;          /* [n_forms] or NULL: standard errors from the observed Fisher information at
+                            theta (per-read term of common/fim.h:322-367, inverse as linalg.h:28-71).
+                            Extension: no reference program evaluates fim.h, so there is no oracle.
+                            NaN when undefined (no reads, singular information, more than 16 forms). */
 } lsq_solve_out;
 
 /* Device timings of the last lsq_count / lsq_solve call (CUDA events on the context's stream). */

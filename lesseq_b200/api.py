@@ -256,9 +256,10 @@ class Context:
         ll = np.zeros(self.E)
         lp = np.zeros(self.E)
         it = np.zeros(self.E, dtype=np.uint32)
-        out = _lib.SolveOut(_ptr(th), _ptr(rp), _ptr(ll), _ptr(lp), _ptr(it), None)
+        se = np.zeros(self.F)
+        out = _lib.SolveOut(_ptr(th), _ptr(rp), _ptr(ll), _ptr(lp), _ptr(it), _ptr(se))
         check(self._lib.lsq_get_solve(self._c, C.byref(out)))
-        return {"theta": th, "rpkm": rp, "loglik": ll, "ll_per_read": lp, "iters": it}
+        return {"theta": th, "rpkm": rp, "loglik": ll, "ll_per_read": lp, "iters": it, "se": se}
 
     def device_results(self):
         """Zero-copy torch views (CUDA) of the result arrays; uint64 arrays are viewed as int64."""

@@ -715,7 +715,7 @@ int lsq_get_solve(lsq_ctx *c, lsq_solve_out *o) {
     if (o->loglik && E) LSQ_CUDA(cudaMemcpyAsync(o->loglik, c->d_ll.p, E * 8, cudaMemcpyDeviceToHost, s));
     if (o->ll_per_read && E) LSQ_CUDA(cudaMemcpyAsync(o->ll_per_read, c->d_llpr.p, E * 8, cudaMemcpyDeviceToHost, s));
     if (o->iters && E) LSQ_CUDA(cudaMemcpyAsync(o->iters, c->d_iters.p, E * 4, cudaMemcpyDeviceToHost, s));
-    if (o->se) return fail(LSQ_ERR_ARG, "standard errors are not available in this build");
+    if (o->se && F) LSQ_CUDA(cudaMemcpyAsync(o->se, c->d_se.p, F * 8, cudaMemcpyDeviceToHost, s));
     LSQ_CUDA(cudaStreamSynchronize(s));
     return LSQ_OK;
 }

@@ -387,9 +387,12 @@ __device__ __forceinline__ double class_prob(uint64_t mk, const double *theta, c
     return s;
 }
 
+constexpr int SE_MAX_FORMS = 16;  // standard errors are computed for events with at most 16 forms
+
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) lsq_solve_kernel(SolveParams P) {
     __shared__ double s_theta[WARPS][2][LSQ_MAX_FORMS_PER_EVENT_DEV];
+    __shared__ double s_fim[WARPS][SE_MAX_FORMS - 1][2 * (SE_MAX_FORMS - 1)];  // [I | identity]
     const uint32_t lane = lane_id();
     const uint32_t w = threadIdx.x >> 5;
     const uint32_t E = P.T.E;
@@ -466,6 +469,88 @@ __global__ void __launch_bounds__(WARPS * 32) lsq_solve_kernel(SolveParams P) {
                 double ratio = __ddiv_rn(ll_old, ll);
                 if (!(fabs(__dsub_rn(1.0, ratio)) > 1E-6) || iters >= P.max_iters) break;
                 ll_old = ll;  // the next iteration's old_ll is this very value (same theta, same order)
+            }
+        }
+        __syncwarp();
+        // Standard errors (extension, no oracle in the reference): observed Fisher information of
+        // the free parameters theta_0..theta_{K-2} (theta_{K-1} eliminated), per-read term as in
+        // common/fim.h:322-367: I_pq = sum_c n_c (v_cp - v_cK)(v_cq - v_cK) / s_c^2, inverted by
+        // Gauss-Jordan with partial pivoting (the reference's linalg.h uses a GSL LU for the same).
+        {
+            const uint32_t D = K - 1u;
+            if (K == 1u) {
+                if (lane == 0) P.se[h.out_form] = 0.0;
+            } else if (!any || K > (uint32_t)SE_MAX_FORMS) {
+                for (uint32_t k = lane; k < K; k += 32) P.se[h.out_form + k] = nan("");
+            } else {
+                double(*A)[2 * (SE_MAX_FORMS - 1)] = s_fim[w];
+                for (uint32_t p = 0; p < D; ++p)
+                    for (uint32_t q = p; q < D; ++q) {
+                        double part = 0.0;
+                        for (uint32_t m = 0; m < P.M; ++m) {
+                            ClassRange cr = class_range(P, h, m);
+                            const double *G = P.G + (size_t)m * P.T.F + h.form_off;
+                            for (uint32_t i = lane; i < cr.n; i += 32) {
+                                unsigned long long c = cr.cnt[i];
+                                if (!c) continue;
+                                uint64_t mk = cr.mask ? cr.mask[i] : (uint64_t)(i + 1u);
+                                double sc = class_prob(mk, th_new, G);
+                                if (!(sc > 0.0)) continue;
+                                double vK = ((mk >> D) & 1ull) ? G[D] : 0.0;
+                                double vp = (((mk >> p) & 1ull) ? G[p] : 0.0) - vK;
+                                double vq = (((mk >> q) & 1ull) ? G[q] : 0.0) - vK;
+                                part += (double)c * (vp / sc) * (vq / sc);
+                            }
+                        }
+                        double v = warp_sum(part);
+                        if (lane == 0) {
+                            A[p][q] = v;
+                            A[q][p] = v;
+                        }
+                    }
+                __syncwarp();
+                for (uint32_t i = lane; i < D * D; i += 32) A[i / D][D + i % D] = (i / D == i % D) ? 1.0 : 0.0;
+                __syncwarp();
+                bool singular = false;
+                for (uint32_t r = 0; r < D; ++r) {  // lane j owns column j of the augmented matrix
+                    uint32_t piv = r;
+                    double best = fabs(A[r][r]);
+                    for (uint32_t i = r + 1; i < D; ++i)
+                        if (fabs(A[i][r]) > best) {
+                            best = fabs(A[i][r]);
+                            piv = i;
+                        }
+                    if (!(best > 0.0)) {
+                        singular = true;
+                        break;
+                    }
+                    __syncwarp();
+                    if (lane < 2 * D) {
+                        double a = A[r][lane], b = A[piv][lane];
+                        A[r][lane] = b;
+                        A[piv][lane] = a;
+                    }
+                    __syncwarp();
+                    const double pv = A[r][r];
+                    __syncwarp();
+                    if (lane < 2 * D) A[r][lane] /= pv;
+                    __syncwarp();
+                    for (uint32_t i = 0; i < D; ++i) {
+                        if (i == r) continue;
+                        const double f = A[i][r];
+                        __syncwarp();
+                        if (lane < 2 * D) A[i][lane] -= f * A[r][lane];
+                        __syncwarp();
+                    }
+                }
+                if (singular) {
+                    for (uint32_t k = lane; k < K; k += 32) P.se[h.out_form + k] = nan("");
+                } else {
+                    double tot = 0.0;
+                    for (uint32_t i = 0; i < D * D; ++i) tot += A[i / D][D + i % D];
+                    for (uint32_t k = lane; k < D; k += 32) P.se[h.out_form + k] = sqrt(A[k][D + k]);
+                    if (lane == 0) P.se[h.out_form + D] = sqrt(tot);
+                }
             }
         }
         __syncwarp();
@@ -570,8 +655,28 @@ __global__ void __launch_bounds__(128) lsq_solve_small_kernel(SolveParams P) {
                 ll_old = ll;
             }
         }
+        // standard error from the observed Fisher information of the free parameter theta_0
+        // (theta_1 = 1 - theta_0): I = sum_c n_c (v_c0 - v_c1)^2 / s_c^2 with v_ck = G_k [k in c]
+        // (per-read term of common/fim.h:322-367); se_0 = se_1 = I^{-1/2}.  Extension: the reference
+        // never evaluates fim.h, so this has no oracle.
+        double se = 0.0;
+        if (K == 2) {
+            double info = 0.0;
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                const double p0 = th0 * G[m][0], p1 = th1 * G[m][1], s3 = p0 + p1;
+                if (cnt[m][0] != 0.0 && p0 > 0.0) info += cnt[m][0] * (G[m][0] / p0) * (G[m][0] / p0);
+                if (cnt[m][1] != 0.0 && p1 > 0.0) info += cnt[m][1] * (G[m][1] / p1) * (G[m][1] / p1);
+                if (cnt[m][2] != 0.0 && s3 > 0.0) {
+                    const double d = (G[m][0] - G[m][1]) / s3;
+                    info += cnt[m][2] * d * d;
+                }
+            }
+            se = any && info > 0.0 ? sqrt(1.0 / info) : nan("");
+        }
         for (uint32_t k = 0; k < K; ++k) {
             const double th = k == 0 ? th0 : th1;
+            P.se[h.out_form + k] = se;
             double r = 0.0;
 #pragma unroll
             for (int m = 0; m < M; ++m) r = __dadd_rn(r, __dmul_rn((double)P.bases[(size_t)m * E + x], th));

@@ -400,3 +400,20 @@ def test_solve_stress_injected_classes(api):
         for k in range(K):
             assert num_close(float(sol["theta"][int(foff[e]) + k]), float(th[k])), (e, k)
         assert num_close(float(sol["loglik"][e]), float(ll)), e
+        # standard errors (extension, no reference oracle): observed Fisher information of the free
+        # parameters, numpy restatement of the per-read term of common/fim.h:322-367
+        D = K - 1
+        info = np.zeros((D, D))
+        for mk, c in classes:
+            v = np.array([G[k] if (mk >> k) & 1 else 0.0 for k in range(K)])
+            sc = float(np.dot(th, v))
+            if sc > 0:
+                d = (v[:D] - v[D]) / sc
+                info += c * np.outer(d, d)
+        se = sol["se"][int(foff[e]):int(foff[e]) + K]
+        if np.linalg.cond(info) < 1e8:
+            cov = np.linalg.inv(info)
+            exp = np.sqrt(np.concatenate([np.diag(cov), [cov.sum()]]))
+            assert np.allclose(se, exp, rtol=1e-6, atol=0), (e, K, se, exp)
+        else:
+            assert np.all(np.isnan(se) | (se >= 0))
