@@ -340,8 +340,15 @@ LSQ_HD void walk_mask(const ReadView &rv, const int2 *seg, uint32_t S, uint64_t 
 // Wide events (S > 64): the same walk, checking one form on the fly with its prefix counts
 // pf[s] = number of form segments with index < s.  The read's index list must be a contiguous
 // run of the form's list (common/read.h:44-79).
-LSQ_COLD bool walk_wide(const ReadView &rv, const int2 *seg, uint32_t S,
-                                 const uint32_t *__restrict__ pf, uint32_t &matched) {
+// (Cold functions take scalars and return packed values: a reference to a caller's local would
+// force that local into thread-private memory in the hot kernel.)  Returns (ok << 32) | matched.
+LSQ_COLD uint64_t walk_wide(int2 b0, uint32_t n, const int2 *blk_ptr, const int2 *seg, uint32_t S,
+                            const uint32_t *__restrict__ pf) {
+    ReadView rv;
+    rv.b0 = b0;
+    rv.n = n;
+    rv.ridx = 0;
+    rv.blk = blk_ptr;
     uint32_t it = 0, b = 0;
     int32_t cont = 0;
     bool found = false, ok = true;
@@ -385,8 +392,7 @@ LSQ_COLD bool walk_wide(const ReadView &rv, const int2 *seg, uint32_t S,
         if (!consumed) break;
         ++b;
     }
-    matched = ml;
-    return ok && last_added != 0xFFFFFFFFu;
+    return ((uint64_t)((ok && last_added != 0xFFFFFFFFu) ? 1u : 0u) << 32) | ml;
 }
 
 // Table-driven evaluation of a FAST-class read [s,e) against a FAST stab entry: the block starts
@@ -422,16 +428,13 @@ LSQ_HD uint32_t hash_mask(uint64_t m) {
 // The lower_bound skip of count.cpp:429-432: a read starting exactly at the event start is
 // passed over when its key (start, end, strand, name) sorts before the probe
 // (gs, ge, event strand, event name) under the comparator of count.cpp:64-85.
-LSQ_COLD bool tie_resolve(const CountParams &P, const EvHdr &h, const ReadView &rv, uint32_t strand) {
-    uint8_t t = LSQ_LD(P.strand_tbl + strand * P.T.n_ann_strands + h.strand);
-    if (t & 1u) return true;
-    if (!(t & 2u)) return false;
-    uint32_t mode = h.flags & EV_TIE_MASK;
-    if (mode == 0u) return false;
-    if (mode == 1u) return true;
-    // a read set without comment/header lines carries no line numbers: read i is "read-<i+1>"
-    uint32_t ln = P.line_num ? LSQ_LD(P.line_num + rv.read_index()) : rv.read_index() + 1u;
-    return digits_less(ln, P.T.tie_pool + h.tie_off, h.tie_len);
+LSQ_COLD bool tie_resolve(uint32_t strand_rel, uint32_t tie_mode, uint32_t line_num, const char *sfx,
+                          uint32_t sfx_len) {
+    if (strand_rel & 1u) return true;      // read strand string < event strand string
+    if (!(strand_rel & 2u)) return false;  // greater
+    if (tie_mode == 0u) return false;
+    if (tie_mode == 1u) return true;
+    return digits_less(line_num, sfx, sfx_len);
 }
 
 LSQ_HD bool tie_skipped(const CountParams &P, const EvHdr &h, const ReadView &rv, uint32_t strand) {
@@ -439,7 +442,11 @@ LSQ_HD bool tie_skipped(const CountParams &P, const EvHdr &h, const ReadView &rv
     int32_t r_end = rv.last_end();
     if (r_end < h.ge) return true;
     if (r_end > h.ge) return false;
-    return tie_resolve(P, h, rv, strand);
+    // a read set without comment/header lines carries no line numbers: read i is "read-<i+1>"
+    const uint32_t ridx = rv.read_index();
+    const uint32_t ln = P.line_num ? LSQ_LD(P.line_num + ridx) : ridx + 1u;
+    return tie_resolve(LSQ_LD(P.strand_tbl + strand * P.T.n_ann_strands + h.strand), h.flags & EV_TIE_MASK, ln,
+                       P.T.tie_pool + h.tie_off, h.tie_len);
 }
 
 // One (read, event) pair -> form compatibility mask of a VALID read (0 otherwise) and matched bases.
@@ -466,10 +473,9 @@ LSQ_HD uint64_t eval_pair(const CountParams &P, const EvHdr &h, const int2 *seg,
         const uint32_t *pf = P.T.pfx + h.pfx_off;
         LSQ_NO_UNROLL
         for (uint32_t k = 0; k < h.K; ++k) {
-            uint32_t mk;
-            bool ok = walk_wide(rv, seg, h.S, pf + (size_t)k * (h.S + 1u), mk);
-            ml = mk;
-            cm |= (uint64_t)ok << k;
+            const uint64_t w = walk_wide(rv.b0, rv.n, rv.blk, seg, h.S, pf + (size_t)k * (h.S + 1u));
+            ml = (uint32_t)w;
+            cm |= (w >> 32) << k;
         }
     }
     if (cm == 0) return 0;

@@ -82,19 +82,22 @@ __global__ void __launch_bounds__(256) lsq_filter_kernel(FilterParams P, int2 *_
 // ---------------------------------------------------------------------------------------------
 // Count kernel
 // ---------------------------------------------------------------------------------------------
-__device__ __noinline__ void bump_class(const CountParams &P, const EvHdr &h, uint64_t cm) {
-    if (!(h.flags & EV_HASH)) {
-        atomicAdd(P.slot_cnt + h.slot_off + (uint32_t)(cm - 1ull), 1ull);
+// Per-lane update of a class table with more than 3 classes (dense K <= 8, or hashed).  Cold:
+// scalar arguments only, so the hot kernel keeps its event header in registers.
+__device__ __noinline__ void bump_class(unsigned long long *slot_cnt, unsigned long long *slot_mask,
+                                        uint32_t slot_cap, bool hashed, uint64_t cm) {
+    if (!hashed) {
+        atomicAdd(slot_cnt + (uint32_t)(cm - 1ull), 1ull);
         return;
     }
-    uint32_t capm = h.slot_cap - 1u;
+    const uint32_t capm = slot_cap - 1u;
     uint32_t i = hash_mask(cm) & capm;
     while (true) {
-        unsigned long long *kp = P.slot_mask + h.slot_off + i;
+        unsigned long long *kp = slot_mask + i;
         unsigned long long cur = *((volatile unsigned long long *)kp);
         if (cur == 0ull) cur = atomicCAS(kp, 0ull, (unsigned long long)cm);
         if (cur == 0ull || cur == cm) {
-            atomicAdd(P.slot_cnt + h.slot_off + i, 1ull);
+            atomicAdd(slot_cnt + i, 1ull);
             return;
         }
         i = (i + 1u) & capm;
@@ -301,7 +304,8 @@ __global__ void __launch_bounds__(COUNT_BLOCK, GENERAL ? 3 : 5) lsq_count_kernel
                                                        total_len, ml);
                         cm = (uint32_t)c64;
                         if (c64 != 0 && en.K > 2) {
-                            bump_class(P, h, c64);
+                            bump_class(P.slot_cnt + h.slot_off, P.slot_mask + h.slot_off, h.slot_cap,
+                                       (h.flags & EV_HASH) != 0, c64);
                             cm = 0x80000000u;
                         }
                     }
