@@ -149,14 +149,6 @@ int lsq_ctx_create(int device, lsq_ctx **out) {
     cudaDeviceProp prop;
     LSQ_CUDA(cudaGetDeviceProperties(&prop, device));
     c->n_sms = prop.multiProcessorCount;
-    // The filter and the GENERAL count kernel gather 16-32 byte records at random addresses; asking
-    // L2 for 32-byte fills instead of promoted 64/128-byte ones avoids fetching bytes nobody reads
-    // (a hint: coalesced streams still fetch whole lines).  LSQ_L2_FETCH=64|128 overrides.
-    {
-        size_t gran = 32;
-        if (const char *e = getenv("LSQ_L2_FETCH")) gran = (size_t)atoi(e);
-        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
-    }
     LSQ_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->own_stream = true;
     for (auto &ev : c->ev) LSQ_CUDA(cudaEventCreate(&ev));

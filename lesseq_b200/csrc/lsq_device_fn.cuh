@@ -264,12 +264,12 @@ LSQ_HD FilteredRead filter_read(const FilterParams &P, uint64_t r, int2 *work) {
 // Per (read, event) pair
 // ---------------------------------------------------------------------------------------------
 struct ReadView {
-    int2 b0;          // first kept block
+    int2 b0, b1, b2;  // kept blocks 0..2 held in registers (reads with more blocks read the rest from blk)
     uint32_t n;       // kept blocks
     uint32_t ridx;    // original read index (names the read: "read-<line_num[ridx]>")
     const int2 *blk;  // kept blocks 0..n-1 (GENERAL class: inside the ext entry)
-    LSQ_HD int2 block(uint32_t j) const { return j == 0 ? b0 : LSQ_LD(blk + j); }
-    LSQ_HD int32_t last_end() const { return n == 1 ? b0.y : LSQ_LD(blk + n - 1).y; }
+    LSQ_HD int2 block(uint32_t j) const { return j == 0 ? b0 : (j == 1 ? b1 : (j == 2 ? b2 : LSQ_LD(blk + j))); }
+    LSQ_HD int32_t last_end() const { return block(n - 1).y; }
     LSQ_HD uint32_t read_index() const { return ridx; }
 };
 
@@ -346,6 +346,8 @@ LSQ_COLD uint64_t walk_wide(int2 b0, uint32_t n, const int2 *blk_ptr, const int2
                             const uint32_t *__restrict__ pf) {
     ReadView rv;
     rv.b0 = b0;
+    rv.b1 = n > 1 ? LSQ_LD(blk_ptr + 1) : b0;
+    rv.b2 = n > 2 ? LSQ_LD(blk_ptr + 2) : b0;
     rv.n = n;
     rv.ridx = 0;
     rv.blk = blk_ptr;

@@ -273,21 +273,26 @@ __global__ void __launch_bounds__(COUNT_BLOCK, GENERAL ? 3 : 5) lsq_count_kernel
                 }
             } else {
                 ReadView rv;
-                rv.b0 = make_int2(0, 0);
+                rv.b0 = rv.b1 = rv.b2 = make_int2(0, 0);
                 rv.n = 1;
                 rv.ridx = 0;
                 rv.blk = nullptr;
                 uint32_t strand = 0, total_len = 0;
                 if (act) {
+                    // one pass over the ext entry: header and up to three blocks go to registers
                     const int2 *entry = P.ext + rec.x;
                     const int2 hd = __ldg(entry);
+                    rv.b0 = __ldg(entry + 1);
+                    const uint32_t nn = rec.y;  // kept blocks, also stored in the sorted record
+                    if (nn > 1) rv.b1 = __ldg(entry + 2);
+                    if (nn > 2) rv.b2 = __ldg(entry + 3);
                     rv.ridx = (uint32_t)hd.x;
-                    rv.n = (uint32_t)hd.y & 0xFFFFFFu;
+                    rv.n = nn;
                     strand = (uint32_t)hd.y >> 24;
                     rv.blk = entry + 1;
-                    rv.b0 = __ldg(entry + 1);
-                    total_len = (uint32_t)(rv.b0.y - rv.b0.x);
-                    for (uint32_t b = 1; b < rv.n; ++b) {
+                    total_len = (uint32_t)(rv.b0.y - rv.b0.x) + (uint32_t)(rv.b1.y - rv.b1.x) +
+                                (uint32_t)(rv.b2.y - rv.b2.x);
+                    for (uint32_t b = 3; b < nn; ++b) {
                         const int2 blk = __ldg(rv.blk + b);
                         total_len += (uint32_t)(blk.y - blk.x);
                     }

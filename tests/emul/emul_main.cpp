@@ -188,10 +188,13 @@ int main(int argc, char **argv) {
                 strand = (uint32_t)entry[0].y >> 24;
                 rv.blk = entry + 1;
                 rv.b0 = entry[1];
+                rv.b1 = rv.n > 1 ? entry[2] : entry[1];
+                rv.b2 = rv.n > 2 ? entry[3] : entry[1];
                 total = 0;
                 for (uint32_t b = 0; b < rv.n; ++b) total += (uint32_t)(rv.blk[b].y - rv.blk[b].x);
             } else {
                 rv.b0 = make_int2((int32_t)q.x, (int32_t)q.x + (int32_t)(q.y & 0xFFFFu));
+                rv.b1 = rv.b2 = rv.b0;
                 rv.n = 1;
                 rv.ridx = 0;
                 rv.blk = nullptr;
