@@ -265,8 +265,8 @@ int lsq_set_reads(lsq_ctx *c, uint32_t m, uint32_t read_type, uint64_t read_leng
     if (m >= LSQ_MAX_METHODS) return fail(LSQ_ERR_RANGE, "read set index >= LSQ_MAX_METHODS");
     if (read_type != LSQ_READ_MEDIUM && read_type != LSQ_READ_SHORT)
         return fail(LSQ_ERR_FORMAT, "unknown read type");
-    if (r->n_blocks + r->n_reads > 0xFFFFFFF0ull)
-        return fail(LSQ_ERR_RANGE, "read set exceeds 2^32 reads + blocks");
+    if (r->n_blocks + 2 * r->n_reads > 0xFFFFFFF0ull)
+        return fail(LSQ_ERR_RANGE, "read set exceeds 2^32 (blocks + 2 * reads)");
     if (r->n_strand_names > 256 || r->n_chrom_names > 65536)
         return fail(LSQ_ERR_RANGE, "read dictionaries too large");
     LSQ_CUDA(cudaSetDevice(c->device));
@@ -485,7 +485,7 @@ int lsq_count(lsq_ctx *c) {
         LSQ_CUDA(c->d_rec.ensure(std::max<size_t>(n, 1) * sizeof(lsq::ReadRec)));
         LSQ_CUDA(c->d_srec.ensure(std::max<size_t>(n, 1) * sizeof(lsq::ReadRec)));
         LSQ_CUDA(c->d_work.ensure(std::max<size_t>(nb, 1) * 8));
-        LSQ_CUDA(c->d_ext.ensure(std::max<size_t>(nb + n, 1) * 8));
+        LSQ_CUDA(c->d_ext.ensure((nb + 2 * n + 2) * 8));
         size_t cub_bytes = 0;
         const int end_bit = (int)bits_for(T.n_pieces * 2u);  // keys 0 .. 2 * n_pieces (= dropped)
         cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, c->d_rkey.as<uint32_t>(), c->d_skey.as<uint32_t>(),

@@ -154,6 +154,10 @@ LSQ_HD bool is_fast_read(uint32_t n, uint32_t at_piece_start, int2 first, uint32
            (piece_stab_n & PIECE_ALL_FAST) != 0;
 }
 
+// Slot of read r's ext entry (GENERAL class): even, so the entry is 16-byte aligned; entries of
+// consecutive reads cannot overlap because an entry has at most 1 + (raw blocks of r) slots.
+LSQ_HD uint32_t ext_slot(uint32_t blk_off_r, uint32_t r) { return (blk_off_r + 2u * r) & ~1u; }
+
 // Sort key of a read that is a candidate of no event: one past the largest real key.
 LSQ_HD uint32_t KEY_DROPPED(const Tables &T) { return T.n_pieces * 2u; }
 

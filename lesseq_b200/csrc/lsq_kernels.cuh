@@ -40,15 +40,18 @@ __global__ void __launch_bounds__(256) lsq_filter_kernel(FilterParams P, int2 *_
     if (in_range) {
         ReadRec rec;
         if (general) {
-            // the ext entry of read r lives at slot blk_off[r] + r: 1 header + n <= 1 + raw blocks,
-            // so no allocation is needed and the slots of different reads never overlap
+            // the ext entry of read r lives at the even slot (blk_off[r] + 2r) & ~1: 1 header + n
+            // <= 1 + raw blocks, so no allocation is needed, entries of different reads never
+            // overlap, and an entry is 16-byte aligned (header + first block = one 128-bit access)
             const uint32_t base = __ldg(P.blk_off + r);
-            const uint32_t off = base + (uint32_t)r;
-            P.ext[off] = make_int2((int32_t)(uint32_t)r, (int32_t)((fr.strand << 24) | (fr.n & 0xFFFFFFu)));
+            const uint32_t off = ext_slot(base, (uint32_t)r);
+            const int2 hd = make_int2((int32_t)(uint32_t)r, (int32_t)((fr.strand << 24) | (fr.n & 0xFFFFFFu)));
             if (fr.n == 1) {
-                P.ext[off + 1] = fr.first;
+                *reinterpret_cast<int4 *>(P.ext + off) = make_int4(hd.x, hd.y, fr.first.x, fr.first.y);
             } else {
-                for (uint32_t i = 0; i < fr.n; ++i) P.ext[off + 1 + i] = work[base + i];
+                const int2 w0 = work[base];
+                *reinterpret_cast<int4 *>(P.ext + off) = make_int4(hd.x, hd.y, w0.x, w0.y);
+                for (uint32_t i = 1; i < fr.n; ++i) P.ext[off + 1 + i] = work[base + i];
             }
             rec.x = off;
             rec.y = fr.n;  // used only for the byte accounting of the count kernel
@@ -280,12 +283,18 @@ __global__ void __launch_bounds__(COUNT_BLOCK, GENERAL ? 3 : 5) lsq_count_kernel
                 uint32_t strand = 0, total_len = 0;
                 if (act) {
                     // one pass over the ext entry: header and up to three blocks go to registers
-                    const int2 *entry = P.ext + rec.x;
-                    const int2 hd = __ldg(entry);
-                    rv.b0 = __ldg(entry + 1);
+                    const int2 *entry = P.ext + rec.x;  // 16-byte aligned
+                    const int4 q0 = __ldg(reinterpret_cast<const int4 *>(entry));
+                    const int2 hd = make_int2(q0.x, q0.y);
+                    rv.b0 = make_int2(q0.z, q0.w);
                     const uint32_t nn = rec.y;  // kept blocks, also stored in the sorted record
-                    if (nn > 1) rv.b1 = __ldg(entry + 2);
-                    if (nn > 2) rv.b2 = __ldg(entry + 3);
+                    if (nn > 2) {
+                        const int4 q1 = __ldg(reinterpret_cast<const int4 *>(entry + 2));
+                        rv.b1 = make_int2(q1.x, q1.y);
+                        rv.b2 = make_int2(q1.z, q1.w);
+                    } else if (nn > 1) {
+                        rv.b1 = __ldg(entry + 2);
+                    }
                     rv.ridx = (uint32_t)hd.x;
                     rv.n = nn;
                     strand = (uint32_t)hd.y >> 24;

@@ -144,12 +144,12 @@ int main(int argc, char **argv) {
         FP.rkey = rkey.data();
         FP.rec = rec.data();
         FP.counters = counters;
-        std::vector<int2> ext2(std::max<size_t>(nb + n, 1));
+        std::vector<int2> ext2(nb + 2 * n + 2);
         for (size_t r = 0; r < n; ++r) {  // lsq_filter_kernel, one "thread" at a time
             FilteredRead fr = filter_read(FP, r, work.data());
             ReadRec q;
             if (fr.key != KEY_DROPPED(T) && fr.key >= T.n_pieces) {
-                uint32_t off = R.blk_off[r] + (uint32_t)r;
+                uint32_t off = ext_slot(R.blk_off[r], (uint32_t)r);
                 counters[1] += fr.n + 1;
                 ext2[off] = make_int2((int32_t)r, (int32_t)((fr.strand << 24) | (fr.n & 0xFFFFFFu)));
                 if (fr.n == 1) ext2[off + 1] = fr.first;
