@@ -99,14 +99,14 @@ struct lsq_ctx {
     lsq::HostTables H;  // host mirror (internal order): headers, permutation, form segment lengths
     std::map<std::string, uint32_t> chrom_id;
     std::vector<std::string> strand_names;
-    DevBuf d_hdr, d_seg, d_fmask, d_pfx, d_tie, d_bp_chrom_off, d_bp_pos, d_stab_off, d_stab, d_cov_off, d_bp_bkt_off, d_bp_bkt, d_pinfo,
+    DevBuf d_hdr, d_seg, d_fmask, d_pfx, d_tie, d_bp_chrom_off, d_bp_pos, d_stab_off, d_stab, d_cov_off, d_bp_bkt_off, d_bp_bkt, d_pinfo, d_chrom_meta,
         d_cov_start, d_cov_end, d_form_len;
     // read sets
     ReadSet sets[LSQ_MAX_METHODS];
     uint32_t M = 0;  // highest declared index + 1
     // per-run state
     DevBuf d_slot_cnt, d_slot_mask, d_bases, d_G, d_counters;
-    DevBuf d_rkey, d_rec, d_work, d_ext, d_skey, d_srec, d_cub;
+    DevBuf d_rkey, d_rec, d_ext, d_skey, d_srec, d_cub;
     DevBuf d_n_valid, d_bases_out, d_iso, d_theta, d_rpkm, d_se, d_ll, d_llpr, d_iters;
     bool counted = false, finalized = false, solved = false;
     uint32_t solved_M = 0;
@@ -204,6 +204,7 @@ int lsq_upload_events(lsq_ctx *c, const lsq_event_tables *t) {
     LSQ_CUDA(upload(c->d_tie, H.tie, s));
     LSQ_CUDA(upload(c->d_bp_chrom_off, H.bp_chrom_off, s));
     LSQ_CUDA(upload(c->d_pinfo, H.pinfo, s));
+    LSQ_CUDA(upload(c->d_chrom_meta, H.chrom_meta, s));
     {
         std::vector<uint32_t> padded(H.stab_off);  // slack so 16-byte aligned bulk copies stay in bounds
         padded.resize(padded.size() + 8, padded.back());
@@ -228,6 +229,7 @@ int lsq_upload_events(lsq_ctx *c, const lsq_event_tables *t) {
     T.tie_pool = c->d_tie.as<char>();
     T.bp_chrom_off = c->d_bp_chrom_off.as<uint32_t>();
     T.pinfo = c->d_pinfo.as<lsq::PieceInfo>();
+    T.chrom_meta = c->d_chrom_meta.as<uint4>();
     T.stab_off = c->d_stab_off.as<uint32_t>();
     T.stab = c->d_stab.as<lsq::StabEntry>();
     T.bp_bkt_off = c->d_bp_bkt_off.as<uint32_t>();
@@ -484,7 +486,6 @@ int lsq_count(lsq_ctx *c) {
         LSQ_CUDA(c->d_skey.ensure(std::max<size_t>(n, 1) * 4));
         LSQ_CUDA(c->d_rec.ensure(std::max<size_t>(n, 1) * sizeof(lsq::ReadRec)));
         LSQ_CUDA(c->d_srec.ensure(std::max<size_t>(n, 1) * sizeof(lsq::ReadRec)));
-        LSQ_CUDA(c->d_work.ensure(std::max<size_t>(nb, 1) * 8));
         LSQ_CUDA(c->d_ext.ensure((nb + 2 * n + 2) * 8));
         size_t cub_bytes = 0;
         const int end_bit = (int)bits_for(T.n_pieces * 2u);  // keys 0 .. 2 * n_pieces (= dropped)
@@ -511,7 +512,7 @@ int lsq_count(lsq_ctx *c) {
             FP.rkey = c->d_rkey.as<uint32_t>();
             FP.rec = c->d_rec.as<lsq::ReadRec>();
             FP.counters = counters;
-            lsq::lsq_filter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(FP, c->d_work.as<int2>());
+            lsq::lsq_filter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(FP);
             LSQ_CUDA(cudaGetLastError());
             tm.launches++;
         }
@@ -520,6 +521,12 @@ int lsq_count(lsq_ctx *c) {
             LSQ_CUDA(cub::DeviceRadixSort::SortPairs(c->d_cub.p, cub_bytes, c->d_rkey.as<uint32_t>(),
                                                      c->d_skey.as<uint32_t>(), c->d_rec.as<lsq::ReadRec>(),
                                                      c->d_srec.as<lsq::ReadRec>(), (int64_t)n, 0, end_bit, s));
+        }
+        if (n) {
+            lsq::lsq_class_bounds_kernel<<<1, 32, 0, s>>>(c->d_skey.as<uint32_t>(), (unsigned long long)n, T.n_pieces,
+                                                          counters);
+            LSQ_CUDA(cudaGetLastError());
+            tm.launches++;
         }
         LSQ_CUDA(cudaEventRecord(c->ev[2], s));
         if (n) {
@@ -534,7 +541,7 @@ int lsq_count(lsq_ctx *c) {
             CP.slot_cnt = slot_cnt;
             CP.slot_mask = slot_mask;
             CP.bases = bases;
-            CP.stats = counters + 2;
+            CP.stats = counters + 1;  // ext slots read by the GENERAL instantiation
             // the class sizes are only known on the device: both instantiations get a grid that
             // covers the whole read set and walk their own range of the sorted arrays
             const size_t chunks = (n + lsq::COUNT_CHUNK - 1) / lsq::COUNT_CHUNK;

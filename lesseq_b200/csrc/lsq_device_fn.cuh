@@ -68,10 +68,11 @@ LSQ_HD uint32_t upper_bound_i32(const int32_t *__restrict__ a, uint32_t lo, uint
 // before the first piece.  One load of two adjacent bucket ranks, then a short scan over
 // consecutive 16-byte PieceInfo records (a binary search when a bucket is unusually crowded).
 LSQ_HD uint32_t find_piece(const Tables &T, uint32_t c, int32_t x, PieceInfo &out) {
-    const uint32_t lo = LSQ_LD(T.bp_chrom_off + c), hi = LSQ_LD(T.bp_chrom_off + c + 1);
+    const uint4 cm = LSQ_LD(T.chrom_meta + c);
+    const uint32_t lo = cm.x, hi = cm.y;
     uint32_t i = lo, j = hi;
     if (x >= 0) {
-        const uint32_t b0 = LSQ_LD(T.bp_bkt_off + c), nb = LSQ_LD(T.bp_bkt_off + c + 1) - b0 - 1u;
+        const uint32_t b0 = cm.z, nb = cm.w;
         const uint32_t b = (uint32_t)x >> T.bp_shift;
         if (b >= nb) {
             i = j = hi;
@@ -174,7 +175,7 @@ struct FilteredRead {
 // chromosome; kept blocks are merged into the read's interval list (work[0..n), used only when
 // the read has more than one raw block); the read's chromosome/strand are those of the last
 // registered block; the stab piece is looked up for the first kept start.
-LSQ_HD FilteredRead filter_read(const FilterParams &P, uint64_t r, int2 *work) {
+LSQ_HD FilteredRead filter_read(const FilterParams &P, uint64_t r) {
     const Tables &T = P.T;
     FilteredRead out;
     out.n = 0;
@@ -191,7 +192,10 @@ LSQ_HD FilteredRead filter_read(const FilterParams &P, uint64_t r, int2 *work) {
     int32_t last_end = 0;
     uint32_t n = 0;
     int2 first = make_int2(0, 0);
-    work += base;
+    // the read's interval list is built in place in its ext entry (blocks start one slot after
+    // the header); it is only touched when the read has more than one raw block
+    int2 *work = P.ext + ext_slot(base, (uint32_t)r) + 1;
+    uint32_t first_chrom = 0xFFFFFFFFu;
     uint32_t first_piece = 0xFFFFFFFFu;  // piece of `first` when it was found while filtering
     PieceInfo first_pi;
     first_pi.pos = 0;
@@ -229,6 +233,7 @@ LSQ_HD FilteredRead filter_read(const FilterParams &P, uint64_t r, int2 *work) {
             first_piece = pidx;
             first_pi = pi;
             first_valid = true;
+            first_chrom = c;
             if (nraw > 1) work[0] = b;
         } else if (b.x >= last_end) {
             if (b.x == last_end) {  // starts where the last interval ends: the two fuse
@@ -254,8 +259,7 @@ LSQ_HD FilteredRead filter_read(const FilterParams &P, uint64_t r, int2 *work) {
         // filtering is reused when it was looked up on that chromosome for this very start
         uint32_t p = first_piece;
         PieceInfo pi = first_pi;
-        const uint32_t c_first = LSQ_LD(P.chrom_remap + ((mixed ? LSQ_LD(P.blk_cs + base) : cs0) & 0xFFFFu));
-        if (!first_valid || mixed || c_first != chrom) p = find_piece(T, chrom, first.x, pi);
+        if (!first_valid || first_chrom != chrom) p = find_piece(T, chrom, first.x, pi);
         if (p != 0xFFFFFFFFu && (pi.stab_n & ~PIECE_ALL_FAST) > 0) {
             out.at_piece_start = pi.pos == first.x ? 1u : 0u;
             out.key = is_fast_read(n, out.at_piece_start, first, pi.stab_n) ? p : T.n_pieces + p;

@@ -20,66 +20,48 @@ namespace lsq {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
-__global__ void __launch_bounds__(256) lsq_filter_kernel(FilterParams P, int2 *__restrict__ work) {
-    __shared__ uint32_t s_cnt[4];  // kept reads, GENERAL reads, ext slots of GENERAL reads, warps done
+__global__ void __launch_bounds__(256) lsq_filter_kernel(FilterParams P) {
     const Tables &T = P.T;
     const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool in_range = r < P.n_reads;
-    const uint32_t lane = lane_id();
-    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
-    __syncthreads();
-    FilteredRead fr;
-    fr.n = 0;
-    fr.key = KEY_DROPPED(T);
-    fr.first = make_int2(0, 0);
-    fr.strand = 0;
-    fr.at_piece_start = 0;
-    if (in_range) fr = filter_read(P, r, work);
+    if (r >= P.n_reads) return;
+    const FilteredRead fr = filter_read(P, r);
     const bool kept = fr.key != KEY_DROPPED(T);
-    const bool general = kept && fr.key >= T.n_pieces;
-    if (in_range) {
-        ReadRec rec;
-        if (general) {
-            // the ext entry of read r lives at the even slot (blk_off[r] + 2r) & ~1: 1 header + n
-            // <= 1 + raw blocks, so no allocation is needed, entries of different reads never
-            // overlap, and an entry is 16-byte aligned (header + first block = one 128-bit access)
-            const uint32_t base = __ldg(P.blk_off + r);
-            const uint32_t off = ext_slot(base, (uint32_t)r);
-            const int2 hd = make_int2((int32_t)(uint32_t)r, (int32_t)((fr.strand << 24) | (fr.n & 0xFFFFFFu)));
-            if (fr.n == 1) {
-                *reinterpret_cast<int4 *>(P.ext + off) = make_int4(hd.x, hd.y, fr.first.x, fr.first.y);
-            } else {
-                const int2 w0 = work[base];
-                *reinterpret_cast<int4 *>(P.ext + off) = make_int4(hd.x, hd.y, w0.x, w0.y);
-                for (uint32_t i = 1; i < fr.n; ++i) P.ext[off + 1 + i] = work[base + i];
-            }
-            rec.x = off;
-            rec.y = fr.n;  // used only for the byte accounting of the count kernel
-        } else {
-            rec.x = (uint32_t)fr.first.x;
-            rec.y = (uint32_t)(fr.first.y - fr.first.x) | (fr.strand << 16);
-        }
-        __stcs(P.rkey + r, fr.key);  // streamed to the sort: do not displace the tables in L2
-        __stcs(P.rec + r, rec);
+    ReadRec rec;
+    if (kept && fr.key >= T.n_pieces) {
+        // GENERAL class: the ext entry of read r lives at the even slot (blk_off[r] + 2r) & ~1:
+        // 1 header + n <= 1 + raw blocks, so no allocation is needed, entries of different reads
+        // never overlap, and header + first block form one aligned 128-bit access.  Blocks 1..n-1
+        // were left in place by filter_read.
+        const uint32_t off = ext_slot(__ldg(P.blk_off + r), (uint32_t)r);
+        *reinterpret_cast<int4 *>(P.ext + off) =
+            make_int4((int32_t)(uint32_t)r, (int32_t)((fr.strand << 24) | (fr.n & 0xFFFFFFu)), fr.first.x, fr.first.y);
+        rec.x = off;
+        rec.y = fr.n;
+    } else {
+        rec.x = (uint32_t)fr.first.x;
+        rec.y = (uint32_t)(fr.first.y - fr.first.x) | (fr.strand << 16);
     }
-    // kept / GENERAL counts: warp ballots -> shared counters -> the last warp of the block to
-    // finish issues the two global reductions (no block-wide barrier on the way)
-    const unsigned kept_mask = __ballot_sync(0xFFFFFFFFu, kept);
-    const unsigned gen_mask = __ballot_sync(0xFFFFFFFFu, general);
-    const uint32_t gen_slots = __reduce_add_sync(0xFFFFFFFFu, general ? fr.n + 1u : 0u);
-    if (lane == 0) {
-        if (kept_mask) atomicAdd(&s_cnt[0], (uint32_t)__popc(kept_mask));
-        if (gen_mask) atomicAdd(&s_cnt[1], (uint32_t)__popc(gen_mask));
-        if (gen_slots) atomicAdd(&s_cnt[2], gen_slots);
-        __threadfence_block();
-        const uint32_t done = atomicAdd(&s_cnt[3], 1u) + 1u;
-        if (done == (blockDim.x >> 5)) {
-            const uint32_t k = atomicAdd(&s_cnt[0], 0u), g = atomicAdd(&s_cnt[1], 0u), sl = atomicAdd(&s_cnt[2], 0u);
-            if (k) atomicAdd(P.counters + 0, (unsigned long long)k);
-            if (sl) atomicAdd(P.counters + 1, (unsigned long long)sl);
-            if (g) atomicAdd(P.counters + 3, (unsigned long long)g);
+    __stcs(P.rkey + r, fr.key);  // streamed to the sort: do not displace the tables in L2
+    __stcs(P.rec + r, rec);
+}
+
+// After the sort: class sizes from the sorted keys (two binary searches by one thread) --
+// counters[0] = kept reads (key < 2 n_pieces), counters[3] = GENERAL reads (n_pieces <= key).
+__global__ void lsq_class_bounds_kernel(const uint32_t *__restrict__ g_key, unsigned long long n, uint32_t n_pieces,
+                                        unsigned long long *counters) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    auto lower = [&](uint32_t v) {
+        unsigned long long lo = 0, hi = n;
+        while (lo < hi) {
+            unsigned long long mid = (lo + hi) >> 1;
+            if (g_key[mid] < v) lo = mid + 1;
+            else hi = mid;
         }
-    }
+        return lo;
+    };
+    const unsigned long long kept = lower(2u * n_pieces), fast = lower(n_pieces);
+    counters[0] = kept;
+    counters[3] = kept - fast;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -210,6 +192,7 @@ __global__ void __launch_bounds__(COUNT_BLOCK, GENERAL ? 3 : 5) lsq_count_kernel
     };
     if (producer && blockIdx.x < n_chunks) issue(blockIdx.x, 0);
     uint32_t j = 0;
+    uint32_t my_slots = 0;  // GENERAL: ext slots read (byte accounting)
     for (unsigned long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x, ++j) {
         const uint32_t stage = j & 1u;
         if (producer && chunk + gridDim.x < n_chunks) {
@@ -297,6 +280,7 @@ __global__ void __launch_bounds__(COUNT_BLOCK, GENERAL ? 3 : 5) lsq_count_kernel
                     }
                     rv.ridx = (uint32_t)hd.x;
                     rv.n = nn;
+                    my_slots += nn + 1u;
                     strand = (uint32_t)hd.y >> 24;
                     rv.blk = entry + 1;
                     total_len = (uint32_t)(rv.b0.y - rv.b0.x) + (uint32_t)(rv.b1.y - rv.b1.x) +
@@ -329,6 +313,10 @@ __global__ void __launch_bounds__(COUNT_BLOCK, GENERAL ? 3 : 5) lsq_count_kernel
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[stage]);  // this warp no longer reads the stage
+    }
+    if (GENERAL) {
+        const uint32_t sl = __reduce_add_sync(0xFFFFFFFFu, my_slots);
+        if (lane == 0 && sl) atomicAdd(P.stats, (unsigned long long)sl);
     }
 }
 

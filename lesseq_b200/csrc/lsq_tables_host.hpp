@@ -29,6 +29,7 @@ struct HostTables {
     std::vector<PieceInfo> pinfo;
     uint32_t bp_shift = 0;
     std::vector<uint32_t> bp_bkt_off, bp_bkt;
+    std::vector<uint4> chrom_meta;
 
     // Table view over the HOST arrays (CPU replay harness only).
     Tables host_view() const {
@@ -50,6 +51,7 @@ struct HostTables {
         T.stab = stab.data();
         T.bp_shift = bp_shift;
         T.bp_bkt_off = bp_bkt_off.data();
+        T.chrom_meta = chrom_meta.data();
         T.bp_bkt = bp_bkt.data();
         T.cov_off = cov_off.data();
         T.cov_start = cov_start.data();
@@ -349,6 +351,10 @@ inline int build_host_tables(const lsq_event_tables *t, HostTables &H, std::stri
     H.cov_end.assign(t->cov_end, t->cov_end + H.cov_off.back());
     H.tie.assign(tie_pool.begin(), tie_pool.end());
     build_bucket_index(H.bp_pos, H.bp_chrom_off, H.bp_shift, H.bp_bkt_off, H.bp_bkt);
+    H.chrom_meta.resize(std::max<uint32_t>(t->n_chroms, 1));
+    for (uint32_t ch = 0; ch < t->n_chroms; ++ch)
+        H.chrom_meta[ch] = make_uint4(H.bp_chrom_off[ch], H.bp_chrom_off[ch + 1], H.bp_bkt_off[ch],
+                                      H.bp_bkt_off[ch + 1] - H.bp_bkt_off[ch] - 1u);
     H.pinfo.resize(H.bp_pos.size());
     for (uint32_t ch = 0; ch < t->n_chroms; ++ch) {
         const int32_t *cs = H.cov_start.data() + H.cov_off[ch], *ce = H.cov_end.data() + H.cov_off[ch];

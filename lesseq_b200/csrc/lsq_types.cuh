@@ -90,6 +90,7 @@ struct Tables {
     // bucket indexes: position >> shift -> rank of the bucket start in the sorted array, so a
     // lookup is one table load plus a short forward scan instead of a full binary search
     uint32_t bp_shift;
+    const uint4 *chrom_meta;       // [n_chroms] {first piece, end piece, first bucket, buckets - 1}
     const uint32_t *bp_bkt_off;    // [n_chroms+1] first bucket of each chromosome
     const uint32_t *bp_bkt;        // [buckets + n_chroms] rank of the first piece starting in or after the bucket
 };

@@ -128,7 +128,7 @@ int main(int argc, char **argv) {
         }
         std::vector<uint8_t> stbl;
         strand_table(R.strand_ptrs.data(), (uint32_t)R.strand_ptrs.size(), ann_strands, stbl);
-        std::vector<int2> work(std::max<size_t>(nb, 1)), ext(std::max<size_t>(nb, 1));
+        std::vector<int2> ext2(nb + 2 * n + 2);
         std::vector<uint32_t> rkey(n);
         std::vector<ReadRec> rec(n);
         unsigned long long counters[4] = {0, 0, 0, 0};
@@ -140,21 +140,18 @@ int main(int argc, char **argv) {
         FP.read_cs = R.read_cs.data();
         FP.blk_cs = R.any_mixed ? R.blk_cs.data() : nullptr;
         FP.chrom_remap = remap.data();
-        FP.ext = ext.data();
+        FP.ext = ext2.data();
         FP.rkey = rkey.data();
         FP.rec = rec.data();
         FP.counters = counters;
-        std::vector<int2> ext2(nb + 2 * n + 2);
         for (size_t r = 0; r < n; ++r) {  // lsq_filter_kernel, one "thread" at a time
-            FilteredRead fr = filter_read(FP, r, work.data());
+            FilteredRead fr = filter_read(FP, r);
             ReadRec q;
             if (fr.key != KEY_DROPPED(T) && fr.key >= T.n_pieces) {
                 uint32_t off = ext_slot(R.blk_off[r], (uint32_t)r);
                 counters[1] += fr.n + 1;
                 ext2[off] = make_int2((int32_t)r, (int32_t)((fr.strand << 24) | (fr.n & 0xFFFFFFu)));
-                if (fr.n == 1) ext2[off + 1] = fr.first;
-                else
-                    for (uint32_t i = 0; i < fr.n; ++i) ext2[off + 1 + i] = work[R.blk_off[r] + i];
+                ext2[off + 1] = fr.first;  // blocks 1..n-1 were left in place by filter_read
                 q.x = off;
                 q.y = 0;
             } else {
