@@ -126,9 +126,11 @@ __device__ __forceinline__ ChunkTables chunk_tables(const CountParams &P, unsign
 
 // One q-step of the run aggregation: per-class counts of each run via ballots restricted to the
 // run's lane mask, matched bases via a segmented shuffle reduction, reductions by the head lane.
+// Staged chunks accumulate in block-local shared-memory counters (4 per staged stab entry: three
+// classes + bases) that are flushed once per chunk; other chunks reduce straight to global memory.
 __device__ __forceinline__ void aggregate_runs(const CountParams &P, uint32_t lane, bool head_has, unsigned run_mask,
                                                uint32_t run_end, bool single_run, uint32_t cm, uint32_t ml,
-                                               uint32_t slot_off, uint32_t x) {
+                                               uint32_t slot_off, uint32_t x, uint32_t *s_ctr /* or null */) {
     // cm is 1, 2 or 3 for events with at most two forms (bit k = compatible with form k);
     // larger tables were updated by the caller and arrive as the 0x80000000 marker
     const unsigned f0 = __ballot_sync(0xFFFFFFFFu, (cm & 1u) != 0u);
@@ -147,10 +149,17 @@ __device__ __forceinline__ void aggregate_runs(const CountParams &P, uint32_t la
     if (head_has) {
         const uint32_t c1 = __popc(f0 & ~f1 & run_mask), c2 = __popc(f1 & ~f0 & run_mask),
                        c3 = __popc(f0 & f1 & run_mask);
-        if (c1) atomicAdd(P.slot_cnt + slot_off, (unsigned long long)c1);
-        if (c2) atomicAdd(P.slot_cnt + slot_off + 1u, (unsigned long long)c2);
-        if (c3) atomicAdd(P.slot_cnt + slot_off + 2u, (unsigned long long)c3);
-        if (v) atomicAdd(P.bases + x, (unsigned long long)v);
+        if (s_ctr) {
+            if (c1) atomicAdd(s_ctr + 0, c1);
+            if (c2) atomicAdd(s_ctr + 1, c2);
+            if (c3) atomicAdd(s_ctr + 2, c3);
+            if (v) atomicAdd(s_ctr + 3, v);
+        } else {
+            if (c1) atomicAdd(P.slot_cnt + slot_off, (unsigned long long)c1);
+            if (c2) atomicAdd(P.slot_cnt + slot_off + 1u, (unsigned long long)c2);
+            if (c3) atomicAdd(P.slot_cnt + slot_off + 2u, (unsigned long long)c3);
+            if (v) atomicAdd(P.bases + x, (unsigned long long)v);
+        }
     }
 }
 
@@ -163,7 +172,11 @@ __global__ void __launch_bounds__(COUNT_BLOCK, GENERAL ? 3 : 5) lsq_count_kernel
     __shared__ __align__(128) StabEntry s_ent[2][COUNT_MAX_ENT];
     __shared__ __align__(16) uint32_t s_off[2][COUNT_MAX_OFF];
     __shared__ __align__(8) uint64_t s_full[2], s_empty[2];
+    __shared__ uint32_t s_ctr[2][COUNT_MAX_ENT][4];  // block-local counters of the staged entries
+    __shared__ uint32_t s_done[2];                   // warps that finished the chunk of a stage
     const Tables &T = P.T;
+    for (uint32_t i = threadIdx.x; i < 2u * COUNT_MAX_ENT * 4u; i += COUNT_BLOCK) (&s_ctr[0][0][0])[i] = 0u;
+    if (threadIdx.x < 2) s_done[threadIdx.x] = 0u;
     const unsigned long long n_fast = P.counters[0] - P.counters[3];
     const unsigned long long r_begin = GENERAL ? n_fast : 0ull, r_end = GENERAL ? P.counters[0] : n_fast;
     const uint32_t key_bias = GENERAL ? T.n_pieces : 0u;
@@ -207,6 +220,7 @@ __global__ void __launch_bounds__(COUNT_BLOCK, GENERAL ? 3 : 5) lsq_count_kernel
         __syncwarp();
         const StabEntry *ent = ct.staged ? s_ent[stage] - ct.e0 : T.stab;
         const uint32_t *off = ct.staged ? s_off[stage] - ct.pa : T.stab_off;
+        uint32_t(*ctr)[4] = ct.staged ? s_ctr[stage] - ct.e0 : nullptr;
         // software pipeline: the next iteration's key and record are loaded before this one is used
         unsigned long long i = base + (unsigned long long)(warp * COUNT_ITEMS * 32u) + lane;
         uint32_t key_n = 0xFFFFFFFFu;
@@ -255,7 +269,8 @@ __global__ void __launch_bounds__(COUNT_BLOCK, GENERAL ? 3 : 5) lsq_count_kernel
                             cm = 0x80000000u;
                         }
                     }
-                    aggregate_runs(P, lane, head && has, run_mask, run_end, single_run, cm, ml, slot_off, x);
+                    aggregate_runs(P, lane, head && has, run_mask, run_end, single_run, cm, ml, slot_off, x,
+                                   ctr ? ctr[so + q] : nullptr);
                 }
             } else {
                 ReadView rv;
@@ -307,11 +322,39 @@ __global__ void __launch_bounds__(COUNT_BLOCK, GENERAL ? 3 : 5) lsq_count_kernel
                             cm = 0x80000000u;
                         }
                     }
-                    aggregate_runs(P, lane, head && has, run_mask, run_end, single_run, cm, ml, slot_off, x);
+                    aggregate_runs(P, lane, head && has, run_mask, run_end, single_run, cm, ml, slot_off, x,
+                                   ctr ? ctr[so + q] : nullptr);
                 }
             }
         }
         __syncwarp();
+        // the last warp of the block to finish this chunk flushes the stage's shared counters to
+        // global memory; the stage is released (empty barrier) only after the flush, so the
+        // counters and the staged entries they refer to cannot be overwritten before
+        uint32_t last = 0;
+        if (lane == 0) {
+            __threadfence_block();
+            last = atomicAdd(&s_done[stage], 1u) == (uint32_t)(COUNT_WARPS - 1);
+        }
+        last = __shfl_sync(0xFFFFFFFFu, last, 0);
+        if (last) {
+            __threadfence_block();
+            if (ct.staged) {
+                const uint32_t nctr = (ct.e1 - ct.e0) * 4u;
+                uint32_t *flat = &s_ctr[stage][0][0];
+                for (uint32_t i = lane; i < nctr; i += 32u) {
+                    const uint32_t v = flat[i];
+                    if (!v) continue;
+                    flat[i] = 0u;
+                    const StabEntry &en = s_ent[stage][i >> 2];
+                    if ((i & 3u) == 3u) atomicAdd(P.bases + en.x, (unsigned long long)v);
+                    else atomicAdd(P.slot_cnt + en.slot_off + (i & 3u), (unsigned long long)v);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) s_done[stage] = 0u;
+            __syncwarp();
+        }
         if (lane == 0) mbar_arrive(&s_empty[stage]);  // this warp no longer reads the stage
     }
     if (GENERAL) {
