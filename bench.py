@@ -39,7 +39,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C4"])
+    ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C4", "C5"],
+                    help="C5 = solve stress: 500k events with 2-16 forms, class tables injected (solve only)")
+    ap.add_argument("--events", type=int, default=500000, help="events of the C5 workload")
     ap.add_argument("--reads", type=int, default=None, help="reads per GPU (default: the workload's)")
     ap.add_argument("--genes", type=int, default=None)
     ap.add_argument("--sample-reads", type=int, default=300000, help="reads of the CPU reference sample")
@@ -358,8 +360,91 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_solve_stress(args):
+    """BASELINE config 5: batched EM (+ standard errors) over injected compatibility-class tables.
+    value = events/s of lsq_solve, device resident; e2e adds lsq_set_classes (H2D) and lsq_get_solve."""
+    import numpy as np
+    import torch
+    from lesseq_b200 import build
+    build.build()
+    from lesseq_b200 import api, synth
+    torch.cuda.set_device(0)
+    E = args.events
+    S = synth.make_solve_stress_fast(E, 5)
+    nch = S["n_chroms"]
+    cov_off = np.arange(nch + 1)
+    ann = api.ArrayAnnotation(
+        ev_chrom=S["ev_chrom"], ev_strand=np.zeros(E), ev_gs=S["ev_gs"], ev_ge=S["ev_ge"], ev_seg_off=S["seg_off"],
+        ev_form_off=S["form_off"], seg_start=S["seg_start"], seg_end=S["seg_end"], form_seg_off=S["form_seg_off"],
+        form_seg_idx=S["form_seg_idx"], cov_off=cov_off, cov_start=np.zeros(nch), cov_end=np.full(nch, 2 ** 31 - 2),
+        chrom_names=["chr%d" % (i + 1) for i in range(nch)], strand_names=["+"])
+    stream = torch.cuda.current_stream()
+    ctx = api.Context(0, stream=stream.cuda_stream)
+    ctx.upload_events(ann)
+    ctx.set_classes(0, "SHORT_READ", 75, S["cls_off"], S["cls_mask"], S["cls_cnt"], S["bases"])
+    trb = [float(S["bases"].sum())]
+    for _ in range(args.warmup):
+        ctx.solve(trb)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    solve_ms = 0.0
+    for _ in range(args.steps):
+        ctx.solve(trb)
+        solve_ms += ctx.timings()["solve_ms"]
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    sol = ctx.get_solve()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record(stream)
+    for _ in range(args.steps):
+        ctx.set_classes(0, "SHORT_READ", 75, S["cls_off"], S["cls_mask"], S["cls_cnt"], S["bases"])
+        ctx.solve(trb)
+        sol2 = ctx.get_solve()
+    t1.record(stream)
+    torch.cuda.synchronize()
+    e2e_ms = t0.elapsed_time(t1) / args.steps
+    clocks = sampler.stop()
+    assert np.array_equal(sol["theta"], sol2["theta"])
+    C = np.diff(S["cls_off"].astype(np.int64))
+    K = S["K"]
+    it = sol["iters"].astype(np.float64)
+    flops = float((it * C * (7 * K + 2)).sum() + (4 * K).sum())       # SURVEY 8d: C(7K+2) per EM iteration
+    bytes_alg = float((16 * C + 24 * K + 16).sum())                    # class table + G/len/theta/rpkm per event
+    peak, peak_src = hbm_peak()
+    kms = solve_ms / args.steps
+    line = {
+        "metric": "events_per_sec_solved", "value": E / (ms / 1000.0), "unit": "events/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C5: solve stress, %d events with 2-16 forms, K..3K compatibility classes each, "
+                               "batched FP64 EM + observed-information standard errors" % E,
+                   "l2_policy": "class tables (%.0f MB) exceed nothing; solve is latency bound" % (bytes_alg / 1e6)},
+        "clocks": clocks,
+        "e2e": {"value": E / (e2e_ms / 1000.0), "unit": "events/s",
+                "h2d_bytes_per_step": int(S["cls_off"].nbytes + S["cls_mask"].nbytes + S["cls_cnt"].nbytes + S["bases"].nbytes),
+                "d2h_bytes_per_step": int(sum(v.nbytes for v in sol.values())), "ms_per_step": e2e_ms},
+        "gpu_launches": int(ctx.timings()["launches"]) * args.steps,
+        "roofline": {"bound": "hbm", "kernel": "lsq_solve_kernel<8>", "achieved": bytes_alg / (kms * 1e-3) / 1e9,
+                     "peak": peak, "unit": "GB/s", "frac": bytes_alg / (kms * 1e-3) / 1e9 / peak, "traffic": None,
+                     "peak_source": peak_src, "ms_per_launch": kms,
+                     "fp64_gflops_algorithmic": flops / (kms * 1e-3) / 1e9},
+        "em_iters_mean": float(it.mean()), "em_iters_max": int(it.max()),
+    }
+    print(json.dumps(line), flush=True)
+    ctx.close()
+
+
 def main():
     args = parse_args()
+    if args.workload == "C5":
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable":
+                              "C5 feeds class tables directly; the reference has no such entry point"}))
+            return
+        return run_solve_stress(args)
     if args.impl == "reference":
         run_reference(args)
     else:

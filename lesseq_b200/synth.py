@@ -323,3 +323,66 @@ def make_solve_stress(n_events, seed, k_range=(2, 16)):
         "cls_off": np.array(cls_off, dtype=np.uint64), "cls_mask": np.array(cls_mask, dtype=np.uint64),
         "cls_cnt": np.array(cls_cnt, dtype=np.uint64), "bases": np.array(bases, dtype=np.uint64),
     }
+
+
+def make_solve_stress_fast(n_events, seed, k_range=(2, 16)):
+    """Vectorised variant of make_solve_stress for the full BASELINE config-5 size (500 k events):
+    same shapes (K~U{2..16}, S~U{K..2K}, C~U{K..3K} classes, log-normal multiplicities); class masks
+    are drawn independently (duplicates within an event are legal and simply act as two classes)."""
+    rng = np.random.default_rng(seed)
+    E = n_events
+    K = rng.integers(k_range[0], k_range[1] + 1, E)
+    S = K + (rng.random(E) * (K + 1)).astype(np.int64)
+    seg_off = np.zeros(E + 1, dtype=np.int64)
+    seg_off[1:] = np.cumsum(S)
+    form_off = np.zeros(E + 1, dtype=np.int64)
+    form_off[1:] = np.cumsum(K)
+    nseg = int(seg_off[-1])
+    ev_of_seg = np.repeat(np.arange(E), S)
+    lens = rng.integers(30, 400, nseg)
+    gaps = rng.integers(0, 300, nseg) * (rng.random(nseg) < 0.7)
+    first = np.zeros(nseg, dtype=bool)
+    first[seg_off[:-1]] = True
+    step = lens + gaps
+    step[first] += 2000                      # distance between events
+    # events are laid out left to right on 16 chromosomes so coordinates stay far below 2^31
+    n_chroms = 16
+    ev_chrom = (np.arange(E) * n_chroms // max(E, 1)).astype(np.int64)
+    cum = np.cumsum(step)
+    chrom_first_seg = seg_off[np.searchsorted(ev_chrom, np.arange(n_chroms))]
+    base_of_chrom = cum[chrom_first_seg] - step[chrom_first_seg]
+    ends = cum - base_of_chrom[ev_chrom[ev_of_seg]] + 1000
+    seg_end = ends
+    seg_start = ends - lens
+    ev_gs = seg_start[seg_off[:-1]]
+    ev_ge = seg_end[seg_off[1:] - 1]
+    # forms: membership of every (form, segment-of-its-event) pair, at least one segment per form
+    nform = int(form_off[-1])
+    ev_of_form = np.repeat(np.arange(E), K)
+    s_per_form = S[ev_of_form]
+    pair_off = np.zeros(nform + 1, dtype=np.int64)
+    pair_off[1:] = np.cumsum(s_per_form)
+    npair = int(pair_off[-1])
+    member = rng.random(npair) < 0.6
+    forced = pair_off[:-1] + (rng.random(nform) * s_per_form).astype(np.int64)
+    member[forced] = True
+    local_idx = np.arange(npair) - np.repeat(pair_off[:-1], s_per_form)
+    form_seg_idx = local_idx[member]
+    cnt_per_form = np.add.reduceat(member.astype(np.int64), pair_off[:-1])
+    form_seg_off = np.zeros(nform + 1, dtype=np.int64)
+    form_seg_off[1:] = np.cumsum(cnt_per_form)
+    # classes
+    C = K + (rng.random(E) * (2 * K + 1)).astype(np.int64)
+    C = np.minimum(C, (1 << K) - 1)
+    cls_off = np.zeros(E + 1, dtype=np.uint64)
+    cls_off[1:] = np.cumsum(C)
+    ncls = int(cls_off[-1])
+    k_of_cls = np.repeat(K, C)
+    cls_mask = (1 + (rng.random(ncls) * ((1 << k_of_cls) - 1)).astype(np.int64)).astype(np.uint64)
+    cls_cnt = np.maximum(1, np.exp(rng.normal(3.0, 2.0, ncls))).astype(np.uint64)
+    bases = np.add.reduceat(cls_cnt, cls_off[:-1].astype(np.int64)) * np.uint64(75)
+    return {"n_events": E, "K": K, "S": S, "seg_off": seg_off, "form_off": form_off, "seg_start": seg_start,
+            "seg_end": seg_end, "ev_gs": ev_gs, "ev_ge": ev_ge, "ev_chrom": ev_chrom, "n_chroms": n_chroms,
+            "form_seg_off": form_seg_off,
+            "form_seg_idx": form_seg_idx, "cls_off": cls_off, "cls_mask": cls_mask, "cls_cnt": cls_cnt,
+            "bases": bases.astype(np.uint64)}
