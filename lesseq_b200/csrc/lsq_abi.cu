@@ -398,9 +398,14 @@ int lsq_set_classes(lsq_ctx *c, uint32_t m, uint32_t read_type, uint64_t read_le
 
 static int ensure_run_buffers(lsq_ctx *c) {
     const size_t E = std::max<uint32_t>(c->E, 1), F = std::max<uint32_t>(c->F, 1);
+    // class slot tables only for read sets that are counted on the device (injected class tables
+    // bring their own storage); indexed by read set, so size them up to the last counted one
+    uint32_t m_slots = 0;
+    for (uint32_t m = 0; m < c->M; ++m)
+        if (c->sets[m].declared && !c->sets[m].injected) m_slots = m + 1;
     const size_t slots = std::max<uint64_t>(c->T.total_slots, 1);
-    LSQ_CUDA(c->d_slot_cnt.ensure((size_t)LSQ_MAX_METHODS * slots * 8));
-    LSQ_CUDA(c->d_slot_mask.ensure((size_t)LSQ_MAX_METHODS * slots * 8));
+    LSQ_CUDA(c->d_slot_cnt.ensure(std::max<size_t>((size_t)m_slots * slots, 1) * 8));
+    LSQ_CUDA(c->d_slot_mask.ensure(std::max<size_t>((size_t)m_slots * slots, 1) * 8));
     LSQ_CUDA(c->d_bases.ensure((size_t)LSQ_MAX_METHODS * E * 8));
     LSQ_CUDA(c->d_counters.ensure(128 * 8));
     LSQ_CUDA(c->d_n_valid.ensure((size_t)LSQ_MAX_METHODS * E * 8));
