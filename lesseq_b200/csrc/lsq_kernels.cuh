@@ -466,6 +466,50 @@ __global__ void __launch_bounds__(WARPS * 32) lsq_solve_kernel(SolveParams P) {
         __syncwarp();
         uint32_t iters = 0;
         double ll = 0.0;
+        // Each lane keeps the (mask, count) classes it owns in registers together with the class
+        // probability s_c at the current theta, so an EM iteration evaluates s_c once per class
+        // instead of once per (class, form).  Lanes own classes in the same order as the strided
+        // loops of the general path below, so both paths add in the same order (same bits).
+        constexpr int CPL = 3;  // classes per lane held in registers: up to 96 classes per event
+        uint64_t cmk[CPL];
+        double ccnt[CPL], cs[CPL];
+        const double *cG[CPL];
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+            cmk[j] = 0;
+            ccnt[j] = 0.0;
+            cs[j] = 1.0;
+            cG[j] = P.G;
+        }
+        uint32_t nown = 0;
+        for (uint32_t m = 0; m < P.M; ++m) {
+            ClassRange cr = class_range(P, h, m);
+            const double *G = P.G + (size_t)m * P.T.F + h.form_off;
+            for (uint32_t i = lane; i < cr.n; i += 32) {
+                unsigned long long c = cr.cnt[i];
+                if (!c) continue;
+                uint64_t mk = cr.mask ? cr.mask[i] : (uint64_t)(i + 1u);
+#pragma unroll
+                for (int j = 0; j < CPL; ++j)
+                    if (nown == (uint32_t)j) {
+                        cmk[j] = mk;
+                        ccnt[j] = (double)c;
+                        cG[j] = G;
+                    }
+                ++nown;
+            }
+        }
+        const bool cached = !__any_sync(0xFFFFFFFFu, nown > (uint32_t)CPL);
+        auto refresh = [&](const double *th) {  // s_c at theta and the log-likelihood (read.h:620-636)
+            double part = 0.0;
+#pragma unroll
+            for (int j = 0; j < CPL; ++j)
+                if ((uint32_t)j < nown) {
+                    cs[j] = class_prob(cmk[j], th, cG[j]);
+                    part = __dadd_rn(part, __dmul_rn(ccnt[j], log(cs[j])));
+                }
+            return warp_sum(part);
+        };
         auto loglik = [&](const double *th) {  // read.h:620-636
             double part = 0.0;
             for (uint32_t m = 0; m < P.M; ++m) {
@@ -485,7 +529,32 @@ __global__ void __launch_bounds__(WARPS * 32) lsq_solve_kernel(SolveParams P) {
         } else if (K == 1) {
             if (lane == 0) th_new[0] = 1.0;  // solve.cpp:801-802
             __syncwarp();
-            ll = loglik(th_new);
+            ll = cached ? refresh(th_new) : loglik(th_new);
+        } else if (cached) {
+            double ll_old = refresh(th_new);
+            while (true) {  // read.h:647-659
+                __syncwarp();
+                for (uint32_t k = lane; k < K; k += 32) th_old[k] = th_new[k];
+                __syncwarp();
+                for (uint32_t k = 0; k < K; ++k) {  // read.h:597-617; cs[] holds s_c at th_old
+                    double part = 0.0;
+                    const double tk = th_old[k];
+#pragma unroll
+                    for (int j = 0; j < CPL; ++j)
+                        if ((uint32_t)j < nown && ((cmk[j] >> k) & 1ull) && cs[j] > 0.0) {
+                            const double lp = __dmul_rn(tk, cG[j][k]);
+                            if (lp > 0.0) part = __dadd_rn(part, __dmul_rn(ccnt[j], __ddiv_rn(lp, cs[j])));
+                        }
+                    const double z = warp_sum(part);
+                    if (lane == 0) th_new[k] = __ddiv_rn(z, n_total);
+                }
+                __syncwarp();
+                ll = refresh(th_new);
+                ++iters;
+                const double ratio = __ddiv_rn(ll_old, ll);
+                if (!(fabs(__dsub_rn(1.0, ratio)) > 1E-6) || iters >= P.max_iters) break;
+                ll_old = ll;
+            }
         } else {
             double ll_old = loglik(th_new);
             while (true) {  // read.h:647-659
@@ -536,6 +605,17 @@ __global__ void __launch_bounds__(WARPS * 32) lsq_solve_kernel(SolveParams P) {
                 for (uint32_t p = 0; p < D; ++p)
                     for (uint32_t q = p; q < D; ++q) {
                         double part = 0.0;
+                        if (cached) {  // cs[] holds s_c at the final theta
+#pragma unroll
+                            for (int j = 0; j < CPL; ++j)
+                                if ((uint32_t)j < nown && cs[j] > 0.0) {
+                                    const double *G = cG[j];
+                                    const double vK = ((cmk[j] >> D) & 1ull) ? G[D] : 0.0;
+                                    const double vp = (((cmk[j] >> p) & 1ull) ? G[p] : 0.0) - vK;
+                                    const double vq = (((cmk[j] >> q) & 1ull) ? G[q] : 0.0) - vK;
+                                    part += ccnt[j] * (vp / cs[j]) * (vq / cs[j]);
+                                }
+                        } else
                         for (uint32_t m = 0; m < P.M; ++m) {
                             ClassRange cr = class_range(P, h, m);
                             const double *G = P.G + (size_t)m * P.T.F + h.form_off;
