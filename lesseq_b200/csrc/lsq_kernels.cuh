@@ -439,7 +439,7 @@ __device__ __forceinline__ double class_prob(uint64_t mk, const double *theta, c
 constexpr int SE_MAX_FORMS = 16;  // standard errors are computed for events with at most 16 forms
 
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) lsq_solve_kernel(SolveParams P) {
+__global__ void __launch_bounds__(WARPS * 32, 3) lsq_solve_kernel(SolveParams P) {
     __shared__ double s_theta[WARPS][2][LSQ_MAX_FORMS_PER_EVENT_DEV];
     __shared__ double s_fim[WARPS][SE_MAX_FORMS - 1][2 * (SE_MAX_FORMS - 1)];  // [I | identity]
     const uint32_t lane = lane_id();
