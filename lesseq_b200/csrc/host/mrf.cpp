@@ -11,7 +11,9 @@
 
 #include <climits>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <thread>
 
 #include "annotation.hpp"
 
@@ -47,34 +49,27 @@ inline const char *find_ch(const char *b, const char *e, char c) {
 
 }  // namespace
 
-int parse_mrf(const char *path, lsqh_reads &R) {
-    FILE *f = fopen(path, "rb");
-    if (!f) {
-        set_error(std::string("cannot read reads file ") + path);
-        return LSQ_ERR_IO;
-    }
-    std::string buf;
-    {
-        char tmp[1 << 16];
-        size_t n;
-        while ((n = fread(tmp, 1, sizeof tmp, f)) > 0) buf.append(tmp, n);
-        fclose(f);
-    }
-    if (buf.empty()) {
-        set_error(std::string("empty reads file ") + path);
-        return LSQ_ERR_IO;
-    }
-    const char *p = buf.data(), *end = p + buf.size();
-    const char *nl = find_ch(p, end, '\n');
-    p = nl ? nl + 1 : end;  // first line skipped unconditionally (:283)
-    uint64_t line_num = 0;
-    R.blk_off.push_back(0);
-    bool any_mixed = false;
-    std::string key;
-    // small caches: consecutive blocks nearly always repeat chromosome and strand
+namespace {
+
+struct ChunkOut {  // per-thread result, merged in file order
+    Dictionary chroms, strands;
+    std::vector<uint32_t> nblk, read_cs, blk_cs, line_num;
+    std::vector<int32_t> blk;
+    int err = LSQ_OK;
+    uint64_t err_line = 0;
+    std::string err_msg;
+};
+
+// Parses the '\n'-terminated lines of [p, end); `line_num` is the number of the line before p.
+void parse_chunk(const char *p, const char *end, uint64_t line_num, ChunkOut &R) {
     std::string last_chr, last_strand;
     uint32_t last_chr_id = 0, last_strand_id = 0;
     bool have_chr = false, have_strand = false;
+    auto failed = [&](int code, const std::string &msg) {
+        R.err = code;
+        R.err_line = line_num;
+        R.err_msg = msg;
+    };
     while (p < end) {
         const char *le = find_ch(p, end, '\n');
         if (!le) break;  // unterminated last line is never processed (:285)
@@ -83,34 +78,25 @@ int parse_mrf(const char *path, lsqh_reads &R) {
         p = le + 1;
         if (ls < le && *ls == '#') continue;
         if ((size_t)(le - ls) == 15 && memcmp(ls, "AlignmentBlocks", 15) == 0) continue;
-        if (line_num > UINT32_MAX) {
-            set_error("more than 2^32-1 lines in one MRF file");
-            return LSQ_ERR_RANGE;
-        }
+        if (line_num > UINT32_MAX) return failed(LSQ_ERR_RANGE, "more than 2^32-1 lines in one MRF file");
         uint32_t first_cs = 0;
         bool mixed = false;
-        size_t nb = 0;
+        uint32_t nb = 0;
         const char *b0 = ls;
         while (true) {
             const char *c1 = find_ch(b0, le, ':');
             const char *c2 = c1 ? find_ch(c1 + 1, le, ':') : nullptr;
             const char *c3 = c2 ? find_ch(c2 + 1, le, ':') : nullptr;
-            if (!c3) {
-                set_error("Lexical_cast error when converting arguments to numeric values (MRF line " +
-                          std::to_string(line_num) + ")");
-                return LSQ_ERR_PARSE;
-            }
+            if (!c3)
+                return failed(LSQ_ERR_PARSE, "Lexical_cast error when converting arguments to numeric values (MRF line " +
+                                                 std::to_string(line_num) + ")");
             const char *c4 = find_ch(c3 + 1, le, ':');
             long s, e;
-            if (!strict_long(c2 + 1, c3, s) || !strict_long(c3 + 1, c4 ? c4 : le, e)) {
-                set_error("Lexical_cast error when converting arguments to numeric values (MRF line " +
-                          std::to_string(line_num) + ")");
-                return LSQ_ERR_PARSE;
-            }
-            if (s - 1 < INT32_MIN || s - 1 > INT32_MAX || e < INT32_MIN || e > INT32_MAX) {
-                set_error("MRF coordinate outside int32 at line " + std::to_string(line_num));
-                return LSQ_ERR_RANGE;
-            }
+            if (!strict_long(c2 + 1, c3, s) || !strict_long(c3 + 1, c4 ? c4 : le, e))
+                return failed(LSQ_ERR_PARSE, "Lexical_cast error when converting arguments to numeric values (MRF line " +
+                                                 std::to_string(line_num) + ")");
+            if (s - 1 < INT32_MIN || s - 1 > INT32_MAX || e < INT32_MIN || e > INT32_MAX)
+                return failed(LSQ_ERR_RANGE, "MRF coordinate outside int32 at line " + std::to_string(line_num));
             uint32_t cid, sid;
             if (have_chr && last_chr.size() == (size_t)(c1 - b0) && memcmp(last_chr.data(), b0, c1 - b0) == 0) {
                 cid = last_chr_id;
@@ -127,11 +113,7 @@ int parse_mrf(const char *path, lsqh_reads &R) {
                 sid = last_strand_id = R.strands.intern(last_strand);
                 have_strand = true;
             }
-            if (cid > 0xFFFF || sid > 0xFF) {
-                set_error("too many distinct chromosome (65536) or strand (256) strings in MRF file");
-                return LSQ_ERR_RANGE;
-            }
-            uint32_t cs = cid | (sid << 16);
+            uint32_t cs = cid | (sid << 16);  // chunk-local ids, remapped when chunks are merged
             if (nb == 0) first_cs = cs;
             else if (cs != first_cs) mixed = true;
             R.blk.push_back((int32_t)(s - 1));
@@ -143,14 +125,122 @@ int parse_mrf(const char *path, lsqh_reads &R) {
             if (!comma) break;
             b0 = comma + 1;
         }
-        if (R.blk_cs.size() > UINT32_MAX) {
-            set_error("more than 2^32-1 alignment blocks in one MRF file");
-            return LSQ_ERR_RANGE;
-        }
         R.read_cs.push_back(first_cs | (mixed ? LSQ_READ_MIXED : 0u));
         R.line_num.push_back((uint32_t)line_num);
-        R.blk_off.push_back((uint32_t)R.blk_cs.size());
-        any_mixed |= mixed;
+        R.nblk.push_back(nb);
+    }
+}
+
+}  // namespace
+
+int parse_mrf(const char *path, lsqh_reads &R) {
+    FILE *f = fopen(path, "rb");
+    if (!f) {
+        set_error(std::string("cannot read reads file ") + path);
+        return LSQ_ERR_IO;
+    }
+    std::string buf;
+    {
+        fseek(f, 0, SEEK_END);
+        long sz = ftell(f);
+        fseek(f, 0, SEEK_SET);
+        if (sz > 0) {
+            buf.resize((size_t)sz);
+            size_t got = fread(&buf[0], 1, (size_t)sz, f);
+            buf.resize(got);
+        }
+        fclose(f);
+    }
+    if (buf.empty()) {
+        set_error(std::string("empty reads file ") + path);
+        return LSQ_ERR_IO;
+    }
+    const char *p = buf.data(), *end = p + buf.size();
+    const char *nl = find_ch(p, end, '\n');
+    p = nl ? nl + 1 : end;  // first line skipped unconditionally (:283)
+
+    // split the body at line boundaries; every chunk is parsed by its own thread
+    unsigned nthreads = std::thread::hardware_concurrency();
+    if (const char *e = getenv("LSQ_THREADS")) nthreads = (unsigned)atoi(e);
+    nthreads = std::max(1u, std::min(nthreads, 64u));
+    const size_t body = (size_t)(end - p);
+    if (body < (1u << 20)) nthreads = 1;
+    std::vector<const char *> cut(nthreads + 1, end);
+    cut[0] = p;
+    for (unsigned t = 1; t < nthreads; ++t) {
+        const char *q = p + body / nthreads * t;
+        if (q < cut[t - 1]) q = cut[t - 1];
+        const char *n2 = find_ch(q, end, '\n');
+        cut[t] = n2 ? n2 + 1 : end;
+    }
+    std::vector<uint64_t> first_line(nthreads + 1, 0);  // lines before each chunk
+    {
+        std::vector<uint64_t> lines(nthreads, 0);
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nthreads; ++t)
+            th.emplace_back([&, t]() {
+                uint64_t n = 0;
+                for (const char *q = cut[t]; q < cut[t + 1];) {
+                    const char *x = (const char *)memchr(q, '\n', cut[t + 1] - q);
+                    if (!x) break;
+                    ++n;
+                    q = x + 1;
+                }
+                lines[t] = n;
+            });
+        for (auto &x : th) x.join();
+        for (unsigned t = 0; t < nthreads; ++t) first_line[t + 1] = first_line[t] + lines[t];
+    }
+    std::vector<ChunkOut> out(nthreads);
+    {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nthreads; ++t)
+            th.emplace_back([&, t]() { parse_chunk(cut[t], cut[t + 1], first_line[t], out[t]); });
+        for (auto &x : th) x.join();
+    }
+    for (unsigned t = 0; t < nthreads; ++t)  // the first failing line in file order decides, as in a serial scan
+        if (out[t].err) {
+            set_error(out[t].err_msg);
+            return out[t].err;
+        }
+    size_t n_reads = 0, n_blocks = 0;
+    for (auto &o : out) {
+        n_reads += o.read_cs.size();
+        n_blocks += o.blk_cs.size();
+    }
+    if (n_blocks > UINT32_MAX) {
+        set_error("more than 2^32-1 alignment blocks in one MRF file");
+        return LSQ_ERR_RANGE;
+    }
+    R.blk_off.reserve(n_reads + 1);
+    R.read_cs.reserve(n_reads);
+    R.line_num.reserve(n_reads);
+    R.blk_cs.reserve(n_blocks);
+    R.blk.reserve(2 * n_blocks);
+    R.blk_off.push_back(0);
+    bool any_mixed = false;
+    for (auto &o : out) {  // merge in file order: global dictionary ids follow first appearance
+        std::vector<uint32_t> cmap(o.chroms.names.size()), smap(o.strands.names.size());
+        for (size_t i = 0; i < cmap.size(); ++i) cmap[i] = R.chroms.intern(o.chroms.names[i]);
+        for (size_t i = 0; i < smap.size(); ++i) smap[i] = R.strands.intern(o.strands.names[i]);
+        if (R.chroms.names.size() > 0x10000 || R.strands.names.size() > 0x100) {
+            set_error("too many distinct chromosome (65536) or strand (256) strings in MRF file");
+            return LSQ_ERR_RANGE;
+        }
+        auto remap = [&](uint32_t cs) {
+            return cmap[cs & 0xFFFFu] | (smap[(cs >> 16) & 0xFFu] << 16) | (cs & LSQ_READ_MIXED);
+        };
+        // two reads of different chunks may have used the same local id for different names, so
+        // "mixed" has to be re-derived only within a read, which stays inside one chunk
+        for (size_t i = 0; i < o.read_cs.size(); ++i) {
+            R.read_cs.push_back(remap(o.read_cs[i]));
+            any_mixed |= (o.read_cs[i] & LSQ_READ_MIXED) != 0;
+            R.line_num.push_back(o.line_num[i]);
+            R.blk_off.push_back(R.blk_off.back() + o.nblk[i]);
+        }
+        for (uint32_t cs : o.blk_cs) R.blk_cs.push_back(remap(cs));
+        R.blk.insert(R.blk.end(), o.blk.begin(), o.blk.end());
+        o = ChunkOut();
     }
     R.any_mixed = any_mixed;
     R.chrom_ptrs = R.chroms.c_ptrs();

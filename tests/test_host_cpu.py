@@ -191,3 +191,44 @@ def test_cli_argument_errors(built_lib, tmp_path):
     assert api.run_program("count", bad)[0] == 134
     rc, out, err = api.run_program("solve", sa[:-1])
     assert rc == 1 and "Usage" in err
+
+
+def test_parallel_mrf_parser_matches_serial(built_lib, tmp_path):
+    """The chunk-parallel MRF parser (csrc/host/mrf.cpp) must produce the serial result: read
+    numbering across chunks (comment lines count), dictionary ids in order of first appearance,
+    chimeric reads flagged."""
+    import random
+    from lesseq_b200 import api
+    rng = random.Random(3)
+    lines = ["AlignmentBlocks"]
+    for i in range(60000):
+        r = rng.random()
+        if r < 0.01:
+            lines.append("# comment %d" % i)
+        elif r < 0.02:
+            lines.append("chrB%d:.:5:9:1:5,chr1:+:100:120:6:26" % (i % 7))
+        else:
+            s = rng.randint(1, 10 ** 6)
+            lines.append("chr%d:%s:%d:%d:1:50" % (rng.randint(1, 5), "+-"[rng.randint(0, 1)], s, s + 49))
+    p = tmp_path / "big.mrf"
+    p.write_text("\n".join(lines) + "\n")
+    assert p.stat().st_size > (1 << 20)
+
+    def load(threads):
+        os.environ["LSQ_THREADS"] = str(threads)
+        try:
+            r = api.Reads.from_mrf(p)
+        finally:
+            del os.environ["LSQ_THREADS"]
+        n, nb = r.n_reads, r.n_blocks
+        u32 = C.POINTER(C.c_uint32)
+        arr = lambda ptr, k: np.ctypeslib.as_array(C.cast(ptr, u32), shape=(k,)).copy()  # noqa: E731
+        return (n, nb, arr(r.view.line_num, n), arr(r.view.read_cs, n), arr(r.view.blk_off, n + 1),
+                np.ctypeslib.as_array(C.cast(r.view.blk, C.POINTER(C.c_int32)), shape=(2 * nb,)).copy(),
+                [r.view.chrom_names[i] for i in range(r.view.n_chrom_names)],
+                [r.view.strand_names[i] for i in range(r.view.n_strand_names)])
+
+    a, b = load(1), load(7)
+    assert a[0] == b[0] and a[1] == b[1] and a[6] == b[6] and a[7] == b[7]
+    for x, y in zip(a[2:6], b[2:6]):
+        assert np.array_equal(x, y)
