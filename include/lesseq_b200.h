@@ -145,8 +145,8 @@ typedef struct lsq_solve_out {
 
 /* Device timings of the last lsq_count / lsq_solve call (CUDA events on the context's stream). */
 typedef struct lsq_timings {
-    float filter_ms, index_ms, gather_ms, count_ms, finalize_ms, solve_ms;
-    float count_kernel_ms; /* the count kernel alone (summed over read sets) */
+    float filter_ms, index_ms, reserved_ms, count_ms, finalize_ms, solve_ms;
+    float count_kernel_ms; /* the two count kernel instantiations (summed over read sets) */
     uint32_t launches;     /* kernels launched by the last lsq_count + lsq_solve */
     uint32_t count_launches;
     uint64_t reads_in, reads_kept, pairs_valid; /* summed over read sets */

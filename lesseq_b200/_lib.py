@@ -59,7 +59,7 @@ class SolveOut(C.Structure):
 
 class Timings(C.Structure):
     _fields_ = [
-        ("filter_ms", C.c_float), ("index_ms", C.c_float), ("gather_ms", C.c_float), ("count_ms", C.c_float),
+        ("filter_ms", C.c_float), ("index_ms", C.c_float), ("reserved_ms", C.c_float), ("count_ms", C.c_float),
         ("finalize_ms", C.c_float), ("solve_ms", C.c_float), ("count_kernel_ms", C.c_float),
         ("launches", C.c_uint32), ("count_launches", C.c_uint32),
         ("reads_in", C.c_uint64), ("reads_kept", C.c_uint64), ("pairs_valid", C.c_uint64),

@@ -99,7 +99,7 @@ struct lsq_ctx {
     lsq::HostTables H;  // host mirror (internal order): headers, permutation, form segment lengths
     std::map<std::string, uint32_t> chrom_id;
     std::vector<std::string> strand_names;
-    DevBuf d_hdr, d_seg, d_fmask, d_pfx, d_tie, d_bp_chrom_off, d_bp_pos, d_stab_off, d_stab, d_cov_off, d_bp_bkt_off, d_bp_bkt, d_pinfo, d_chrom_meta,
+    DevBuf d_hdr, d_seg, d_fmask, d_pfx, d_tie, d_bp_chrom_off, d_stab_off, d_stab, d_cov_off, d_bp_bkt_off, d_bp_bkt, d_pinfo, d_chrom_meta,
         d_cov_start, d_cov_end, d_form_len;
     // read sets
     ReadSet sets[LSQ_MAX_METHODS];
@@ -109,7 +109,6 @@ struct lsq_ctx {
     DevBuf d_rkey, d_rec, d_ext, d_skey, d_srec, d_cub;
     DevBuf d_n_valid, d_bases_out, d_iso, d_theta, d_rpkm, d_se, d_ll, d_llpr, d_iters;
     bool counted = false, finalized = false, solved = false;
-    uint32_t solved_M = 0;
     // timing
     cudaEvent_t ev[16] = {};
     lsq_timings tm{};
@@ -590,7 +589,6 @@ int lsq_count(lsq_ctx *c) {
     LSQ_CUDA(cudaEventElapsedTime(&f, c->ev[4], c->ev[5]));
     tm.filter_ms = acc[0];
     tm.index_ms = acc[1];
-    tm.gather_ms = 0;
     tm.count_ms = acc[3];
     tm.count_kernel_ms = acc[3];
     tm.finalize_ms = f;
@@ -713,7 +711,6 @@ int lsq_solve(lsq_ctx *c, const double *total_read_bases, uint32_t n_methods) {
     LSQ_CUDA(cudaStreamSynchronize(s));
     LSQ_CUDA(cudaEventElapsedTime(&c->tm.solve_ms, c->ev[6], c->ev[7]));
     c->solved = true;
-    c->solved_M = c->M;
     return LSQ_OK;
 }
 

@@ -5,7 +5,6 @@
 
 namespace lsq {
 
-constexpr uint32_t KEY_NONE_BITS = 0xFFFFFFFFu;
 constexpr int DENSE_MAX_FORMS = 8;  // events with K <= 8 use a direct-indexed class table
 constexpr int LSQ_MAX_FORMS_PER_EVENT_DEV = 64;
 
@@ -106,7 +105,7 @@ struct FilterParams {
     int2 *ext;                    // [n_blocks + n_reads] worst case (header + blocks per general read)
     uint32_t *rkey;               // [n_reads] stab piece or n_pieces (= dropped)
     ReadRec *rec;                 // [n_reads]
-    unsigned long long *counters; // [0] kept reads, [1] ext cursor, [2] valid pairs
+    unsigned long long *counters; // per read set: [0] kept reads, [1] ext slots read, [3] GENERAL reads
 };
 
 struct CountParams {
@@ -120,7 +119,7 @@ struct CountParams {
     unsigned long long *slot_cnt;   // this read set's class counters
     unsigned long long *slot_mask;  // hash keys (EV_HASH events)
     unsigned long long *bases;      // [E] internal order
-    unsigned long long *stats;      // [0] valid pairs
+    unsigned long long *stats;      // ext slots read by the GENERAL instantiation (byte accounting)
 };
 
 struct SolveParams {
