@@ -53,7 +53,26 @@ GNAME_POOL = ["1", "10", "100", "2", "21", "3", "z", "uc001", "read-3", "read-",
               "A", "b", "9", "read-2x", "r", "read", "~t"]
 
 
-def make_case(seed, n_events=None, n_reads=None, two_sets=None):
+def _weird_form(rng, ex):
+    """Annotation shapes a curated Events.r output never has but the reference accepts: exons out
+    of order, zero-length exons, exact duplicates, overlapping exons inside one form."""
+    ex = list(ex)
+    r = rng.random()
+    if r < 0.3 and len(ex) > 1:
+        i = rng.randrange(len(ex) - 1)
+        ex[i], ex[i + 1] = ex[i + 1], ex[i]               # out of order
+    elif r < 0.5:
+        s = rng.choice(ex)[rng.randint(0, 1)] + rng.randint(-3, 3)
+        ex.insert(rng.randrange(len(ex) + 1), (max(0, s), max(0, s)))  # zero-length exon
+    elif r < 0.7:
+        ex.insert(rng.randrange(len(ex) + 1), rng.choice(ex))          # duplicate exon
+    elif r < 0.9:
+        s, e = rng.choice(ex)
+        ex.append((max(0, s - rng.randint(0, 20)), e + rng.randint(0, 20)))  # overlapping, appended last
+    return ex
+
+
+def make_case(seed, n_events=None, n_reads=None, two_sets=None, weird=False):
     rng = random.Random(seed)
     n_events = n_events or rng.randint(1, 6)
     chroms = ["chr1", "chr2", "chrX"][: rng.randint(1, 3)]
@@ -73,6 +92,8 @@ def make_case(seed, n_events=None, n_reads=None, two_sets=None):
         fl = [base] + [_derive_form(rng, base) for _ in range(k - 1)]
         st = rng.choice(strands)
         for i, ex in enumerate(fl):
+            if weird and rng.random() < 0.5:
+                ex = _weird_form(rng, ex)
             fname = "%s|%d" % (g, i + 1)
             fst = st if rng.random() < 0.9 else rng.choice(strands)
             forms_lines.append("\t".join([

@@ -195,7 +195,21 @@ def main():
         c["expect"] = exp
         fuzz.append(c)
     json.dump(fuzz, open(os.path.join(HERE, "fuzz.json"), "w"), indent=0)
-    print("wrote", len(seeds), "seed and", len(fuzz), "fuzz cases")
+    # annotation shapes outside what Events.r emits: exons out of order, zero-length, duplicated,
+    # overlapping inside one form (ExonSet::insert / build_isoform_array corner cases)
+    weird = []
+    seed = 20000
+    while len(weird) < 40:
+        c = fuzzgen.make_case(seed, weird=True)
+        c["name"] = "weird_%d" % seed
+        seed += 1
+        exp = run_case(c)
+        if exp["count_rc"] not in (0, 1) or exp["solve_rc"] not in (0, 1):
+            continue
+        c["expect"] = exp
+        weird.append(c)
+    json.dump(weird, open(os.path.join(HERE, "weird.json"), "w"), indent=0)
+    print("wrote", len(seeds), "seed,", len(fuzz), "fuzz and", len(weird), "weird-annotation cases")
 
 
 if __name__ == "__main__":

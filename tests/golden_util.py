@@ -24,4 +24,4 @@ def materialise(case, d):
 
 
 def all_cases():
-    return load("seed.json") + load("fuzz.json")
+    return load("seed.json") + load("fuzz.json") + load("weird.json")

@@ -25,7 +25,7 @@ def api():
 
 
 SEED_CASES = golden_util.load("seed.json")
-FUZZ_CASES = golden_util.load("fuzz.json")
+FUZZ_CASES = golden_util.load("fuzz.json") + golden_util.load("weird.json")
 
 
 @pytest.mark.parametrize("case", SEED_CASES, ids=[c["name"] for c in SEED_CASES])
@@ -56,7 +56,7 @@ def format_tables(api, ann, M, cnt, sol, prec):
 
 
 def test_abi_matches_reference_golden_fuzz(api, tmp_path):
-    """The 80 fuzz fixtures (reference binary outputs) through the ctypes mirror of the C ABI in
+    """The 80 fuzz + 40 weird-annotation fixtures (reference binary outputs) through the ctypes mirror of the C ABI in
     one process: count tables identical, solve tables within tolerance."""
     ctx = api.Context(0)
     for case in FUZZ_CASES:
