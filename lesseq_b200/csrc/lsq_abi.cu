@@ -492,7 +492,7 @@ int lsq_count(lsq_ctx *c) {
         LSQ_CUDA(c->d_srec.ensure(std::max<size_t>(n, 1) * sizeof(lsq::ReadRec)));
         LSQ_CUDA(c->d_ext.ensure((nb + 2 * n + 2) * 8));
         size_t cub_bytes = 0;
-        const int end_bit = (int)bits_for(T.n_pieces * 2u);  // keys 0 .. 2 * n_pieces (= dropped)
+        const int end_bit = (int)bits_for(T.n_pieces * 3u);  // keys 0 .. 3 * n_pieces (= dropped)
         cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, c->d_rkey.as<uint32_t>(), c->d_skey.as<uint32_t>(),
                                         c->d_rec.as<lsq::ReadRec>(), c->d_srec.as<lsq::ReadRec>(), (int64_t)n, 0,
                                         end_bit, s);
@@ -551,12 +551,14 @@ int lsq_count(lsq_ctx *c) {
             const size_t chunks = (n + lsq::COUNT_CHUNK - 1) / lsq::COUNT_CHUNK;
             unsigned grid_f = (unsigned)std::min<size_t>(chunks, (size_t)c->n_sms * 5);
             unsigned grid_g = (unsigned)std::min<size_t>(chunks, (size_t)c->n_sms * 3);
-            lsq::lsq_count_kernel<false><<<grid_f, lsq::COUNT_BLOCK, 0, s>>>(CP);
+            lsq::lsq_count_kernel<0><<<grid_f, lsq::COUNT_BLOCK, 0, s>>>(CP);
             LSQ_CUDA(cudaGetLastError());
-            lsq::lsq_count_kernel<true><<<grid_g, lsq::COUNT_BLOCK, 0, s>>>(CP);
+            lsq::lsq_count_kernel<1><<<grid_g, lsq::COUNT_BLOCK, 0, s>>>(CP);
             LSQ_CUDA(cudaGetLastError());
-            tm.launches += 2;
-            tm.count_launches += 2;
+            lsq::lsq_count_kernel<2><<<grid_g, lsq::COUNT_BLOCK, 0, s>>>(CP);
+            LSQ_CUDA(cudaGetLastError());
+            tm.launches += 3;
+            tm.count_launches += 3;
         }
         LSQ_CUDA(cudaEventRecord(c->ev[3], s));
         LSQ_CUDA(cudaMemcpyAsync(c->h_counters.data() + (size_t)m * 4, counters, 4 * 8, cudaMemcpyDeviceToHost, s));

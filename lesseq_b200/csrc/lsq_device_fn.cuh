@@ -160,12 +160,41 @@ LSQ_HD bool is_fast_read(uint32_t n, uint32_t at_piece_start, int2 first, uint32
 LSQ_HD uint32_t ext_slot(uint32_t blk_off_r, uint32_t r) { return (blk_off_r + 2u * r) & ~1u; }
 
 // Sort key of a read that is a candidate of no event: one past the largest real key.
-LSQ_HD uint32_t KEY_DROPPED(const Tables &T) { return T.n_pieces * 2u; }
+LSQ_HD uint32_t KEY_DROPPED(const Tables &T) { return T.n_pieces * 3u; }
+
+// PAIR class: exactly two kept blocks, not on the first position of the piece, and everything fits
+// the 8-byte record: x = (start - piece start) [16 bits] | length of block 0 [11 bits] << 16,
+// y = (gap between the blocks - 1) [22 bits] | length of block 1 [... 8 low bits << 22 | strand << 30]
+// -- see pack_pair / unpack_pair.  Such reads are evaluated by the general walk straight from
+// registers, without an ext entry.
+constexpr uint32_t PAIR_MAX_OFF = 0xFFFFu, PAIR_MAX_LEN = 0x7FFu, PAIR_MAX_GAP = 0x3FFFFFu;
+LSQ_HD bool is_pair_read(uint32_t n, uint32_t at_piece_start, int2 b0, int2 b1, int32_t piece_pos, uint32_t strand) {
+    return n == 2u && !at_piece_start && (uint32_t)(b0.x - piece_pos) <= PAIR_MAX_OFF &&
+           (uint32_t)(b0.y - b0.x) <= PAIR_MAX_LEN && (uint32_t)(b1.y - b1.x) <= PAIR_MAX_LEN && b1.x > b0.y &&
+           (uint32_t)(b1.x - b0.y - 1) <= PAIR_MAX_GAP && strand < 4u;
+}
+LSQ_HD ReadRec pack_pair(int2 b0, int2 b1, int32_t piece_pos, uint32_t strand) {
+    ReadRec r;
+    const uint32_t len1 = (uint32_t)(b1.y - b1.x);
+    r.x = (uint32_t)(b0.x - piece_pos) | ((uint32_t)(b0.y - b0.x) << 16) | ((len1 & 0x1Fu) << 27);
+    r.y = (uint32_t)(b1.x - b0.y - 1) | ((len1 >> 5) << 22) | (strand << 28);
+    return r;
+}
+LSQ_HD void unpack_pair(ReadRec r, int32_t piece_pos, int2 &b0, int2 &b1, uint32_t &strand) {
+    const uint32_t len0 = (r.x >> 16) & 0x7FFu, len1 = ((r.x >> 27) & 0x1Fu) | (((r.y >> 22) & 0x3Fu) << 5);
+    b0.x = piece_pos + (int32_t)(r.x & 0xFFFFu);
+    b0.y = b0.x + (int32_t)len0;
+    b1.x = b0.y + 1 + (int32_t)(r.y & 0x3FFFFFu);
+    b1.y = b1.x + (int32_t)len1;
+    strand = r.y >> 28;
+}
 
 // Result of the per-read load filter.
 struct FilteredRead {
     uint32_t n;       // kept intervals (0: read dropped)
-    uint32_t key;     // piece (FAST class), n_pieces + piece (GENERAL), KEY_DROPPED when no candidate
+    uint32_t key;     // piece (FAST), n_pieces + piece (PAIR), 2 n_pieces + piece (GENERAL), KEY_DROPPED
+    int2 second;      // second kept interval (n >= 2)
+    int32_t piece_pos;  // first position of the read's piece
     int2 first;       // first kept interval
     uint32_t strand;  // file strand id of the last registered block
     uint32_t at_piece_start;  // 1 when the first kept start is the first position of its piece
@@ -183,6 +212,8 @@ LSQ_HD FilteredRead filter_read(const FilterParams &P, uint64_t r) {
     out.first = make_int2(0, 0);
     out.strand = 0;
     out.at_piece_start = 0;
+    out.second = make_int2(0, 0);
+    out.piece_pos = 0;
     const uint32_t base = LSQ_LD_STREAM(P.blk_off + r);
     const uint32_t nraw = LSQ_LD_STREAM(P.blk_off + r + 1) - base;
     const uint32_t cs0 = LSQ_LD_STREAM(P.read_cs + r);
@@ -262,7 +293,11 @@ LSQ_HD FilteredRead filter_read(const FilterParams &P, uint64_t r) {
         if (!first_valid || first_chrom != chrom) p = find_piece(T, chrom, first.x, pi);
         if (p != 0xFFFFFFFFu && (pi.stab_n & ~PIECE_ALL_FAST) > 0) {
             out.at_piece_start = pi.pos == first.x ? 1u : 0u;
-            out.key = is_fast_read(n, out.at_piece_start, first, pi.stab_n) ? p : T.n_pieces + p;
+            out.piece_pos = pi.pos;
+            if (n >= 2) out.second = work[1];
+            if (is_fast_read(n, out.at_piece_start, first, pi.stab_n)) out.key = p;
+            else if (is_pair_read(n, out.at_piece_start, first, out.second, pi.pos, out.strand)) out.key = T.n_pieces + p;
+            else out.key = 2u * T.n_pieces + p;
         }
     }
     return out;

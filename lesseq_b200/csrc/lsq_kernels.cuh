@@ -27,7 +27,9 @@ __global__ void __launch_bounds__(256) lsq_filter_kernel(FilterParams P) {
     const FilteredRead fr = filter_read(P, r);
     const bool kept = fr.key != KEY_DROPPED(T);
     ReadRec rec;
-    if (kept && fr.key >= T.n_pieces) {
+    if (kept && fr.key >= T.n_pieces && fr.key < 2u * T.n_pieces) {
+        rec = pack_pair(fr.first, fr.second, fr.piece_pos, fr.strand);  // PAIR class: two blocks inline
+    } else if (kept && fr.key >= 2u * T.n_pieces) {
         // GENERAL class: the ext entry of read r lives at the even slot (blk_off[r] + 2r) & ~1:
         // 1 header + n <= 1 + raw blocks, so no allocation is needed, entries of different reads
         // never overlap, and header + first block form one aligned 128-bit access.  Blocks 1..n-1
@@ -45,8 +47,8 @@ __global__ void __launch_bounds__(256) lsq_filter_kernel(FilterParams P) {
     __stcs(P.rec + r, rec);
 }
 
-// After the sort: class sizes from the sorted keys (two binary searches by one thread) --
-// counters[0] = kept reads (key < 2 n_pieces), counters[3] = GENERAL reads (n_pieces <= key).
+// After the sort: class sizes from the sorted keys (three binary searches by one thread) --
+// counters[0] = kept reads (key < 3 n_pieces), counters[2] = PAIR reads, counters[3] = GENERAL reads.
 __global__ void lsq_class_bounds_kernel(const uint32_t *__restrict__ g_key, unsigned long long n, uint32_t n_pieces,
                                         unsigned long long *counters) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -59,9 +61,10 @@ __global__ void lsq_class_bounds_kernel(const uint32_t *__restrict__ g_key, unsi
         }
         return lo;
     };
-    const unsigned long long kept = lower(2u * n_pieces), fast = lower(n_pieces);
+    const unsigned long long kept = lower(3u * n_pieces), fast = lower(n_pieces), pair_end = lower(2u * n_pieces);
     counters[0] = kept;
-    counters[3] = kept - fast;
+    counters[2] = pair_end - fast;
+    counters[3] = kept - pair_end;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -163,12 +166,14 @@ __device__ __forceinline__ void aggregate_runs(const CountParams &P, uint32_t la
     }
 }
 
-// GENERAL = false: FAST-class reads, positions [0, n_fast) of the sorted arrays -- purely table
-// driven.  GENERAL = true: positions [n_fast, n_kept) -- the general walk over the ext entries.
-// Two instantiations keep the lean kernel's register count (and so its occupancy) independent
-// of the walk's.
-template <bool GENERAL>
-__global__ void __launch_bounds__(COUNT_BLOCK, GENERAL ? 3 : 5) lsq_count_kernel(CountParams P) {
+// CLS 0: FAST-class reads, positions [0, n_fast) of the sorted arrays -- purely table driven.
+// CLS 1: PAIR-class reads [n_fast, n_fast + n_pair) -- the general walk over two blocks held in the
+// sorted record.  CLS 2: GENERAL reads [.., n_kept) -- the general walk over the ext entries.
+// Separate instantiations keep the lean kernel's register count (and so its occupancy)
+// independent of the walk's.
+template <int CLS>
+__global__ void __launch_bounds__(COUNT_BLOCK, CLS ? 3 : 5) lsq_count_kernel(CountParams P) {
+    constexpr bool GENERAL = CLS != 0;
     __shared__ __align__(128) StabEntry s_ent[2][COUNT_MAX_ENT];
     __shared__ __align__(16) uint32_t s_off[2][COUNT_MAX_OFF];
     __shared__ __align__(8) uint64_t s_full[2], s_empty[2];
@@ -177,9 +182,11 @@ __global__ void __launch_bounds__(COUNT_BLOCK, GENERAL ? 3 : 5) lsq_count_kernel
     const Tables &T = P.T;
     for (uint32_t i = threadIdx.x; i < 2u * COUNT_MAX_ENT * 4u; i += COUNT_BLOCK) (&s_ctr[0][0][0])[i] = 0u;
     if (threadIdx.x < 2) s_done[threadIdx.x] = 0u;
-    const unsigned long long n_fast = P.counters[0] - P.counters[3];
-    const unsigned long long r_begin = GENERAL ? n_fast : 0ull, r_end = GENERAL ? P.counters[0] : n_fast;
-    const uint32_t key_bias = GENERAL ? T.n_pieces : 0u;
+    const unsigned long long n_fast = P.counters[0] - P.counters[3] - P.counters[2];
+    const unsigned long long n_pair_end = n_fast + P.counters[2];
+    const unsigned long long r_begin = CLS == 0 ? 0ull : (CLS == 1 ? n_fast : n_pair_end);
+    const unsigned long long r_end = CLS == 0 ? n_fast : (CLS == 1 ? n_pair_end : P.counters[0]);
+    const uint32_t key_bias = (uint32_t)CLS * T.n_pieces;
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
     const bool producer = threadIdx.x == 0;
     if (producer) {
@@ -279,7 +286,14 @@ __global__ void __launch_bounds__(COUNT_BLOCK, GENERAL ? 3 : 5) lsq_count_kernel
                 rv.ridx = 0;
                 rv.blk = nullptr;
                 uint32_t strand = 0, total_len = 0;
-                if (act) {
+                if (CLS == 1) {
+                    if (act) {  // two blocks, relative to the first position of the piece
+                        const int32_t ppos = __ldg(&T.pinfo[key - key_bias].pos);
+                        unpack_pair(rec, ppos, rv.b0, rv.b1, strand);
+                        rv.n = 2;
+                        total_len = (uint32_t)(rv.b0.y - rv.b0.x) + (uint32_t)(rv.b1.y - rv.b1.x);
+                    }
+                } else if (act) {
                     // one pass over the ext entry: header and up to three blocks go to registers
                     const int2 *entry = P.ext + rec.x;  // 16-byte aligned
                     const int4 q0 = __ldg(reinterpret_cast<const int4 *>(entry));
@@ -357,7 +371,7 @@ __global__ void __launch_bounds__(COUNT_BLOCK, GENERAL ? 3 : 5) lsq_count_kernel
         }
         if (lane == 0) mbar_arrive(&s_empty[stage]);  // this warp no longer reads the stage
     }
-    if (GENERAL) {
+    if (CLS == 2) {
         const uint32_t sl = __reduce_add_sync(0xFFFFFFFFu, my_slots);
         if (lane == 0 && sl) atomicAdd(P.stats, (unsigned long long)sl);
     }

@@ -147,7 +147,9 @@ int main(int argc, char **argv) {
         for (size_t r = 0; r < n; ++r) {  // lsq_filter_kernel, one "thread" at a time
             FilteredRead fr = filter_read(FP, r);
             ReadRec q;
-            if (fr.key != KEY_DROPPED(T) && fr.key >= T.n_pieces) {
+            if (fr.key != KEY_DROPPED(T) && fr.key >= T.n_pieces && fr.key < 2u * T.n_pieces) {
+                q = pack_pair(fr.first, fr.second, fr.piece_pos, fr.strand);
+            } else if (fr.key != KEY_DROPPED(T) && fr.key >= 2u * T.n_pieces) {
                 uint32_t off = ext_slot(R.blk_off[r], (uint32_t)r);
                 counters[1] += fr.n + 1;
                 ext2[off] = make_int2((int32_t)r, (int32_t)((fr.strand << 24) | (fr.n & 0xFFFFFFu)));
@@ -174,11 +176,19 @@ int main(int argc, char **argv) {
             uint32_t key = rkey[r];
             if (key == KEY_DROPPED(T)) break;
             ReadRec q = rec[r];
-            const bool gen = key >= T.n_pieces;
-            const uint32_t piece = gen ? key - T.n_pieces : key;
+            const uint32_t cls = key / T.n_pieces;
+            const bool gen = cls != 0;
+            const uint32_t piece = key - cls * T.n_pieces;
             ReadView rv;
             uint32_t strand, total;
-            if (gen) {
+            if (cls == 1) {
+                unpack_pair(q, T.pinfo[piece].pos, rv.b0, rv.b1, strand);
+                rv.b2 = rv.b0;
+                rv.n = 2;
+                rv.ridx = 0;
+                rv.blk = nullptr;
+                total = (uint32_t)(rv.b0.y - rv.b0.x) + (uint32_t)(rv.b1.y - rv.b1.x);
+            } else if (gen) {
                 const int2 *entry = ext2.data() + q.x;
                 rv.ridx = (uint32_t)entry[0].x;
                 rv.n = (uint32_t)entry[0].y & 0xFFFFFFu;
