@@ -385,12 +385,12 @@ LSQ_HD void walk_mask(const ReadView &rv, const int2 *seg, uint32_t S, uint64_t 
 // run of the form's list (common/read.h:44-79).
 // (Cold functions take scalars and return packed values: a reference to a caller's local would
 // force that local into thread-private memory in the hot kernel.)  Returns (ok << 32) | matched.
-LSQ_COLD uint64_t walk_wide(int2 b0, uint32_t n, const int2 *blk_ptr, const int2 *seg, uint32_t S,
+LSQ_COLD uint64_t walk_wide(int2 b0, int2 b1, int2 b2, uint32_t n, const int2 *blk_ptr, const int2 *seg, uint32_t S,
                             const uint32_t *__restrict__ pf) {
     ReadView rv;
     rv.b0 = b0;
-    rv.b1 = n > 1 ? LSQ_LD(blk_ptr + 1) : b0;
-    rv.b2 = n > 2 ? LSQ_LD(blk_ptr + 2) : b0;
+    rv.b1 = b1;
+    rv.b2 = b2;
     rv.n = n;
     rv.ridx = 0;
     rv.blk = blk_ptr;
@@ -518,7 +518,7 @@ LSQ_HD uint64_t eval_pair(const CountParams &P, const EvHdr &h, const int2 *seg,
         const uint32_t *pf = P.T.pfx + h.pfx_off;
         LSQ_NO_UNROLL
         for (uint32_t k = 0; k < h.K; ++k) {
-            const uint64_t w = walk_wide(rv.b0, rv.n, rv.blk, seg, h.S, pf + (size_t)k * (h.S + 1u));
+            const uint64_t w = walk_wide(rv.b0, rv.b1, rv.b2, rv.n, rv.blk, seg, h.S, pf + (size_t)k * (h.S + 1u));
             ml = (uint32_t)w;
             cm |= (w >> 32) << k;
         }
