@@ -20,11 +20,7 @@ namespace lsq {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
-#ifndef FILTER_MIN_BLOCKS
-#define FILTER_MIN_BLOCKS 6
-#endif
-
-__global__ void __launch_bounds__(256, FILTER_MIN_BLOCKS) lsq_filter_kernel(FilterParams P) {
+__global__ void __launch_bounds__(256) lsq_filter_kernel(FilterParams P) {
     const Tables &T = P.T;
     const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= P.n_reads) return;
