@@ -404,27 +404,33 @@ __device__ __forceinline__ ClassRange class_range(const SolveParams &P, const Ev
 
 // One thread per event: n_valid[m], bases[m] and per-form tallies in the caller's order.
 __global__ void __launch_bounds__(128) lsq_finalize_kernel(SolveParams P) {
-    uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= P.T.E) return;
-    const EvHdr h = P.T.hdr[x];
-    unsigned long long iso[LSQ_MAX_FORMS_PER_EVENT_DEV];
-    for (uint32_t k = 0; k < h.K; ++k) iso[k] = 0;
-    for (uint32_t m = 0; m < P.M; ++m) {
-        ClassRange cr = class_range(P, h, m);
-        unsigned long long nv = 0;
-        for (uint32_t i = 0; i < cr.n; ++i) {
-            unsigned long long c = cr.cnt[i];
-            if (!c) continue;
-            unsigned long long mk = cr.mask ? cr.mask[i] : (unsigned long long)(i + 1u);
-            nv += c;
-            for (uint32_t k = 0; k < h.K; ++k)
-                if ((mk >> k) & 1ull) iso[k] += c;
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long pairs = 0;
+    if (x < P.T.E) {
+        const EvHdr h = P.T.hdr[x];
+        unsigned long long iso[LSQ_MAX_FORMS_PER_EVENT_DEV];
+        for (uint32_t k = 0; k < h.K; ++k) iso[k] = 0;
+        for (uint32_t m = 0; m < P.M; ++m) {
+            ClassRange cr = class_range(P, h, m);
+            unsigned long long nv = 0;
+            for (uint32_t i = 0; i < cr.n; ++i) {
+                unsigned long long c = cr.cnt[i];
+                if (!c) continue;
+                unsigned long long mk = cr.mask ? cr.mask[i] : (unsigned long long)(i + 1u);
+                nv += c;
+                for (uint32_t k = 0; k < h.K; ++k)
+                    if ((mk >> k) & 1ull) iso[k] += c;
+            }
+            P.n_valid[(size_t)m * P.T.E + h.out_ev] = nv;
+            P.bases_out[(size_t)m * P.T.E + h.out_ev] = P.bases[(size_t)m * P.T.E + x];
+            pairs += nv;
         }
-        P.n_valid[(size_t)m * P.T.E + h.out_ev] = nv;
-        if (nv && P.pairs_valid) atomicAdd(P.pairs_valid, nv);
-        P.bases_out[(size_t)m * P.T.E + h.out_ev] = P.bases[(size_t)m * P.T.E + x];
+        for (uint32_t k = 0; k < h.K; ++k) P.iso_count[h.out_form + k] = iso[k];
     }
-    for (uint32_t k = 0; k < h.K; ++k) P.iso_count[h.out_form + k] = iso[k];
+    // statistics: total valid (read, event) pairs, one atomic per warp
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) pairs += __shfl_xor_sync(0xFFFFFFFFu, pairs, d);
+    if ((threadIdx.x & 31u) == 0 && pairs && P.pairs_valid) atomicAdd(P.pairs_valid, pairs);
 }
 
 // ---------------------------------------------------------------------------------------------
