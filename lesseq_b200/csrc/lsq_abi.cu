@@ -99,10 +99,8 @@ struct lsq_ctx {
     lsq::HostTables H;  // host mirror (internal order): headers, permutation, form segment lengths
     std::map<std::string, uint32_t> chrom_id;
     std::vector<std::string> strand_names;
-    DevBuf d_hdr, d_seg, d_fmask, d_pfx, d_tie, d_bp_chrom_off, d_stab_off, d_stab, d_cov_off, d_bp_bkt_off, d_pinfo, d_chrom_meta,
+    DevBuf d_hdr, d_seg, d_fmask, d_pfx, d_tie, d_bp_chrom_off, d_stab_off, d_stab, d_cov_off, d_bp_bkt_off, d_bp_bkt, d_pinfo, d_chrom_meta,
         d_cov_start, d_cov_end, d_form_len;
-    size_t lookup_bytes = 0, bkt_byte_off = 0;  // d_pinfo holds PieceInfo[] then the bucket index
-    size_t l2_persist_max = 0, l2_window_max = 0;
     // read sets
     ReadSet sets[LSQ_MAX_METHODS];
     uint32_t M = 0;  // highest declared index + 1
@@ -150,9 +148,6 @@ int lsq_ctx_create(int device, lsq_ctx **out) {
     cudaDeviceProp prop;
     LSQ_CUDA(cudaGetDeviceProperties(&prop, device));
     c->n_sms = prop.multiProcessorCount;
-    c->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
-    c->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
-    if (c->l2_persist_max) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>(c->l2_persist_max, 64u << 20));
     LSQ_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->own_stream = true;
     for (auto &ev : c->ev) LSQ_CUDA(cudaEventCreate(&ev));
@@ -207,22 +202,7 @@ int lsq_upload_events(lsq_ctx *c, const lsq_event_tables *t) {
     LSQ_CUDA(upload(c->d_pfx, H.pfx, s));
     LSQ_CUDA(upload(c->d_tie, H.tie, s));
     LSQ_CUDA(upload(c->d_bp_chrom_off, H.bp_chrom_off, s));
-    {
-        // PieceInfo records and the bucket index are gathered at random by the load filter: keep
-        // them in ONE allocation so a single L2 persistence window can cover both
-        const size_t pbytes = (H.pinfo.size() * sizeof(lsq::PieceInfo) + 255) / 256 * 256;
-        const size_t bbytes = std::max<size_t>(H.bp_bkt.size(), 1) * 4;
-        LSQ_CUDA(c->d_pinfo.ensure(pbytes + bbytes));
-        if (!H.pinfo.empty())
-            LSQ_CUDA(cudaMemcpyAsync(c->d_pinfo.p, H.pinfo.data(), H.pinfo.size() * sizeof(lsq::PieceInfo),
-                                     cudaMemcpyHostToDevice, s));
-        if (!H.bp_bkt.empty())
-            LSQ_CUDA(cudaMemcpyAsync((char *)c->d_pinfo.p + pbytes, H.bp_bkt.data(), H.bp_bkt.size() * 4,
-                                     cudaMemcpyHostToDevice, s));
-        c->lookup_bytes = pbytes + bbytes;
-        c->bkt_byte_off = pbytes;
-        LSQ_CUDA(cudaStreamSynchronize(s));
-    }
+    LSQ_CUDA(upload(c->d_pinfo, H.pinfo, s));
     LSQ_CUDA(upload(c->d_chrom_meta, H.chrom_meta, s));
     {
         std::vector<uint32_t> padded(H.stab_off);  // slack so 16-byte aligned bulk copies stay in bounds
@@ -232,6 +212,7 @@ int lsq_upload_events(lsq_ctx *c, const lsq_event_tables *t) {
     }
     LSQ_CUDA(upload(c->d_stab, H.stab, s));
     LSQ_CUDA(upload(c->d_bp_bkt_off, H.bp_bkt_off, s));
+    LSQ_CUDA(upload(c->d_bp_bkt, H.bp_bkt, s));
     LSQ_CUDA(upload(c->d_cov_off, H.cov_off, s));
     LSQ_CUDA(upload(c->d_cov_start, H.cov_start, s));
     LSQ_CUDA(upload(c->d_cov_end, H.cov_end, s));
@@ -251,7 +232,7 @@ int lsq_upload_events(lsq_ctx *c, const lsq_event_tables *t) {
     T.stab_off = c->d_stab_off.as<uint32_t>();
     T.stab = c->d_stab.as<lsq::StabEntry>();
     T.bp_bkt_off = c->d_bp_bkt_off.as<uint32_t>();
-    T.bp_bkt = reinterpret_cast<const uint32_t *>((const char *)c->d_pinfo.p + c->bkt_byte_off);
+    T.bp_bkt = c->d_bp_bkt.as<uint32_t>();
     T.cov_off = c->d_cov_off.as<uint32_t>();
     T.cov_start = c->d_cov_start.as<int32_t>();
     T.cov_end = c->d_cov_end.as<int32_t>();
@@ -535,27 +516,9 @@ int lsq_count(lsq_ctx *c) {
             FP.rkey = c->d_rkey.as<uint32_t>();
             FP.rec = c->d_rec.as<lsq::ReadRec>();
             FP.counters = counters;
-            // the read streams (GBs) would otherwise evict the few-MB lookup tables from L2 between
-            // gathers: pin the tables for the duration of the filter
-            const bool persist = c->l2_persist_max && c->l2_window_max && c->lookup_bytes &&
-                                 c->lookup_bytes <= std::min<size_t>(c->l2_persist_max, 64u << 20);
-            cudaStreamAttrValue attr;
-            memset(&attr, 0, sizeof attr);
-            if (persist) {
-                attr.accessPolicyWindow.base_ptr = c->d_pinfo.p;
-                attr.accessPolicyWindow.num_bytes = std::min(c->lookup_bytes, c->l2_window_max);
-                attr.accessPolicyWindow.hitRatio = 1.0f;
-                attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-                attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-                cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr);
-            }
             lsq::lsq_filter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(FP);
             LSQ_CUDA(cudaGetLastError());
             tm.launches++;
-            if (persist) {
-                attr.accessPolicyWindow.num_bytes = 0;
-                cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr);
-            }
         }
         LSQ_CUDA(cudaEventRecord(c->ev[1], s));
         if (n) {
