@@ -463,6 +463,73 @@ LSQ_HD uint32_t eval_fast(const StabEntry &en, int32_t s, int32_t e, uint32_t &m
     return cm;
 }
 
+// Two-block (PAIR class) read against a FAST stab entry of a plain event (S <= 64): block 0 starts
+// in chain segment 0 and is resolved with the entry's chain ends exactly as in eval_fast; block 1
+// can only attach when block 0 ended exactly on a segment end, and then only at the exact start
+// of a later segment (read.h:226-262: `cur_start > cur_exon_start -> break`), from where it runs
+// through abutting segments.  Same result as walk_mask + the tests of eval_pair for such reads,
+// without the generic block/segment loops.  No tie-break: PAIR reads never start on a piece start.
+LSQ_HD uint64_t eval_pair2(const StabEntry &en, const EvHdr &h, const int2 *seg, const uint64_t *fm, int2 b0,
+                           int2 b1, uint32_t total_len, uint32_t &matched) {
+    matched = 0;
+    const uint32_t j0 = en.meta & 0xFFFFu, nchain = (en.meta >> 16) & 3u;
+    const int32_t cend = en.c[2];
+    uint32_t i0 = b0.y <= en.c[0] ? 0u : (b0.y <= en.c[1] ? 1u : 2u);
+    if (i0 >= nchain) i0 = nchain - 1u;
+    uint64_t rmask = ((2ull << (j0 + i0)) - 1ull) & ~((1ull << j0) - 1ull);
+    uint32_t ml;
+    if (b0.y > cend) {
+        ml = (uint32_t)(cend - b0.x);  // block 0 overhangs its chain: the read is truncated there
+    } else {
+        ml = (uint32_t)(b0.y - b0.x);
+        const int32_t ci = i0 == 0u ? en.c[0] : (i0 == 1u ? en.c[1] : en.c[2]);
+        if (b0.y == ci) {  // consumed on a segment end: block 1 may attach at a later segment start
+            uint32_t it = j0 + i0 + 1u;
+            const uint32_t S = h.S;
+            LSQ_NO_UNROLL
+            while (it < S) {
+                int2 sg = seg[it];
+                if (!(sg.x < b1.y)) break;
+                if (b1.x < sg.y) {
+                    if (b1.x == sg.x) {
+                        int32_t cs = b1.x;
+                        while (true) {
+                            rmask |= 1ull << it;
+                            const int32_t m = lsq_min(sg.y, b1.y);
+                            ml += (uint32_t)(m - cs);
+                            if (b1.y <= sg.y) break;  // block 1 consumed
+                            cs = sg.y;
+                            ++it;
+                            if (!(it < S)) break;
+                            const int2 nx = seg[it];
+                            if (nx.x != sg.y) break;  // no abutting segment: truncated
+                            sg = nx;
+                        }
+                    }
+                    break;  // starts inside or before this segment without matching its start
+                }
+                ++it;
+            }
+        }
+    }
+    const uint32_t hi = 63u - (uint32_t)lsq_clz64(rmask);
+    const uint64_t low = rmask & (0ull - rmask);
+    const uint64_t span = ((2ull << hi) - 1ull) & ~(low - 1ull);
+    uint64_t cm;
+    if (h.K <= 2u) {
+        cm = (uint64_t)((fm[0] & span) == rmask);
+        if (h.K == 2u) cm |= (uint64_t)((fm[1] & span) == rmask) << 1;
+    } else {
+        cm = 0;
+        LSQ_NO_UNROLL
+        for (uint32_t k = 0; k < h.K; ++k) cm |= (uint64_t)((fm[k] & span) == rmask) << k;
+    }
+    if (cm == 0) return 0;
+    if (ml != total_len && !(lsq_div((double)ml, (double)total_len) > 0.98)) return 0;
+    matched = ml;
+    return cm;
+}
+
 LSQ_HD uint32_t hash_mask(uint64_t m) {
     m ^= m >> 33;
     m *= 0xff51afd7ed558ccdULL;

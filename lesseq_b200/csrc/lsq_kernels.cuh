@@ -327,8 +327,10 @@ __global__ void __launch_bounds__(COUNT_BLOCK, CLS ? 3 : 5) lsq_count_kernel(Cou
                         slot_off = en.slot_off;
                         x = en.x;
                         const EvHdr h = T.hdr[x];
-                        const uint64_t c64 = eval_pair(P, h, T.seg + h.seg_off, T.fmask + h.form_off, rv, strand,
-                                                       total_len, ml);
+                        const uint64_t c64 =
+                            (CLS == 1 && (en.meta & SE_FAST))
+                                ? eval_pair2(en, h, T.seg + h.seg_off, T.fmask + h.form_off, rv.b0, rv.b1, total_len, ml)
+                                : eval_pair(P, h, T.seg + h.seg_off, T.fmask + h.form_off, rv, strand, total_len, ml);
                         cm = (uint32_t)c64;
                         if (c64 != 0 && en.K > 2) {
                             bump_class(P.slot_cnt + h.slot_off, P.slot_mask + h.slot_off, h.slot_cap,

@@ -219,6 +219,8 @@ int main(int argc, char **argv) {
                     return 3;
                 }
                 if (!gen) cm = eval_fast(en, rv.b0.x, rv.b0.y, ml);
+                else if (cls == 1 && (en.meta & SE_FAST))
+                    cm = eval_pair2(en, h, T.seg + h.seg_off, T.fmask + h.form_off, rv.b0, rv.b1, total, ml);
                 else cm = eval_pair(CP, h, T.seg + h.seg_off, T.fmask + h.form_off, rv, strand, total, ml);
                 if (cm) {
                     hist[m][x][cm]++;
