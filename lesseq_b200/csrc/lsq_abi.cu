@@ -11,7 +11,6 @@
 #include <string>
 #include <vector>
 
-#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
 
@@ -100,13 +99,14 @@ struct lsq_ctx {
     std::map<std::string, uint32_t> chrom_id;
     std::vector<std::string> strand_names;
     DevBuf d_hdr, d_seg, d_fmask, d_pfx, d_tie, d_bp_chrom_off, d_stab_off, d_stab, d_cov_off, d_bp_bkt_off, d_bp_bkt, d_pinfo, d_chrom_meta,
-        d_cov_start, d_cov_end, d_form_len;
+        d_cov_start, d_cov_end, d_form_len, d_bkt_piece;
     // read sets
     ReadSet sets[LSQ_MAX_METHODS];
     uint32_t M = 0;  // highest declared index + 1
     // per-run state
     DevBuf d_slot_cnt, d_slot_mask, d_bases, d_G, d_counters;
-    DevBuf d_rkey, d_rec, d_ext, d_skey, d_srec, d_cub;
+    DevBuf d_ext, d_pool, d_part;  // d_part: state | owner | work lists | counters of the partition
+    bool filter_smem_set = false;
     DevBuf d_n_valid, d_bases_out, d_iso, d_theta, d_rpkm, d_se, d_ll, d_llpr, d_iters;
     bool counted = false, finalized = false, solved = false;
     // timing
@@ -217,6 +217,7 @@ int lsq_upload_events(lsq_ctx *c, const lsq_event_tables *t) {
     LSQ_CUDA(upload(c->d_cov_start, H.cov_start, s));
     LSQ_CUDA(upload(c->d_cov_end, H.cov_end, s));
     LSQ_CUDA(upload(c->d_form_len, H.form_len, s));
+    LSQ_CUDA(upload(c->d_bkt_piece, H.bkt_piece, s));
     LSQ_CUDA(cudaStreamSynchronize(s));
 
     lsq::Tables &T = c->T;
@@ -236,6 +237,7 @@ int lsq_upload_events(lsq_ctx *c, const lsq_event_tables *t) {
     T.cov_off = c->d_cov_off.as<uint32_t>();
     T.cov_start = c->d_cov_start.as<int32_t>();
     T.cov_end = c->d_cov_end.as<int32_t>();
+    T.bkt_piece = c->d_bkt_piece.as<uint32_t>();
     c->E = H.E;
     c->F = H.F;
     c->chrom_id.clear();
@@ -486,17 +488,34 @@ int lsq_count(lsq_ctx *c) {
         unsigned long long *slot_mask = c->d_slot_mask.as<unsigned long long>() + (size_t)m * T.total_slots;
         unsigned long long *bases = c->d_bases.as<unsigned long long>() + (size_t)m * E;
         unsigned long long *counters = c->d_counters.as<unsigned long long>() + (size_t)m * 4;
-        LSQ_CUDA(c->d_rkey.ensure(std::max<size_t>(n, 1) * 4));
-        LSQ_CUDA(c->d_skey.ensure(std::max<size_t>(n, 1) * 4));
-        LSQ_CUDA(c->d_rec.ensure(std::max<size_t>(n, 1) * sizeof(lsq::ReadRec)));
-        LSQ_CUDA(c->d_srec.ensure(std::max<size_t>(n, 1) * sizeof(lsq::ReadRec)));
         LSQ_CUDA(c->d_ext.ensure((nb + 2 * n + 2) * 8));
-        size_t cub_bytes = 0;
-        const int end_bit = (int)bits_for(T.n_pieces * 3u);  // keys 0 .. 3 * n_pieces (= dropped)
-        cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, c->d_rkey.as<uint32_t>(), c->d_skey.as<uint32_t>(),
-                                        c->d_rec.as<lsq::ReadRec>(), c->d_srec.as<lsq::ReadRec>(), (int64_t)n, 0,
-                                        end_bit, s);
-        LSQ_CUDA(c->d_cub.ensure(std::max<size_t>(cub_bytes, 1)));
+        // partition state: every bin owns a current and a spare chunk from the start, and a further
+        // chunk is only allocated when a bin has filled one, so n / PART_CHUNK + 2 n_bins suffice
+        lsq::PartState PS;
+        PS.n_bins = 3u * T.n_bkt;
+        PS.pool_cap = (uint32_t)(n / lsq::PART_CHUNK) + 2u * PS.n_bins + 1u;
+        if ((uint64_t)PS.pool_cap * lsq::PART_CHUNK > 0xFFFFFFFFull)
+            return fail(LSQ_ERR_RANGE, "read set too large for 32-bit record slots");
+        {
+            const size_t cap = PS.pool_cap;
+            LSQ_CUDA(c->d_pool.ensure(cap * lsq::PART_CHUNK * sizeof(uint4)));
+            LSQ_CUDA(c->d_part.ensure((size_t)PS.n_bins * 12 + cap * 4 + 3 * cap * 4 + 64));
+            unsigned char *base = c->d_part.as<unsigned char>();
+            PS.state = reinterpret_cast<unsigned long long *>(base);
+            PS.next_chunk = reinterpret_cast<uint32_t *>(base + (size_t)PS.n_bins * 8);
+            PS.owner = PS.next_chunk + PS.n_bins;
+            PS.wl = PS.owner + cap;
+            PS.wl_n = PS.wl + 3 * cap;
+            PS.pool_next = PS.wl_n + 4;
+            PS.pool = c->d_pool.as<uint4>();
+        }
+        const size_t filt_smem = lsq::filter_smem_bytes(PS.n_bins);
+        if (!c->filter_smem_set) {
+            LSQ_CUDA(cudaFuncSetAttribute(lsq::lsq_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            LSQ_CUDA(cudaFuncSetAttribute(lsq::lsq_count_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)lsq::COUNT_FAST_DYN_SMEM));
+            c->filter_smem_set = true;
+        }
 
         LSQ_CUDA(cudaEventRecord(c->ev[0], s));
         LSQ_CUDA(cudaMemsetAsync(slot_cnt, 0, std::max<uint64_t>(T.total_slots, 1) * 8, s));
@@ -513,32 +532,22 @@ int lsq_count(lsq_ctx *c) {
             FP.blk_cs = rs.blk_cs;
             FP.chrom_remap = rs.d_chrom_remap.as<uint32_t>();
             FP.ext = c->d_ext.as<int2>();
-            FP.rkey = c->d_rkey.as<uint32_t>();
-            FP.rec = c->d_rec.as<lsq::ReadRec>();
+            FP.part = PS;
             FP.counters = counters;
-            lsq::lsq_filter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(FP);
+            lsq::lsq_part_init_kernel<<<(PS.n_bins + 255) / 256, 256, 0, s>>>(PS, T.n_bkt);
             LSQ_CUDA(cudaGetLastError());
-            tm.launches++;
-        }
-        LSQ_CUDA(cudaEventRecord(c->ev[1], s));
-        if (n) {
-            LSQ_CUDA(cub::DeviceRadixSort::SortPairs(c->d_cub.p, cub_bytes, c->d_rkey.as<uint32_t>(),
-                                                     c->d_skey.as<uint32_t>(), c->d_rec.as<lsq::ReadRec>(),
-                                                     c->d_srec.as<lsq::ReadRec>(), (int64_t)n, 0, end_bit, s));
-        }
-        if (n) {
-            lsq::lsq_class_bounds_kernel<<<1, 32, 0, s>>>(c->d_skey.as<uint32_t>(), (unsigned long long)n, T.n_pieces,
-                                                          counters);
+            LSQ_CUDA(cudaEventRecord(c->ev[1], s));
+            lsq::lsq_filter_kernel<<<(unsigned)((n + lsq::FILT_TILE - 1) / lsq::FILT_TILE), lsq::FILT_BLOCK, filt_smem, s>>>(FP);
             LSQ_CUDA(cudaGetLastError());
-            tm.launches++;
+            tm.launches += 2;
+        } else {
+            LSQ_CUDA(cudaEventRecord(c->ev[1], s));
         }
         LSQ_CUDA(cudaEventRecord(c->ev[2], s));
         if (n) {
             lsq::CountParams CP;
             CP.T = T;
-            CP.counters = counters;
-            CP.g_key = c->d_skey.as<uint32_t>();
-            CP.g_rec = c->d_srec.as<lsq::ReadRec>();
+            CP.part = PS;
             CP.ext = c->d_ext.as<int2>();
             CP.line_num = rs.line_num;
             CP.strand_tbl = rs.d_strand_tbl.as<uint8_t>();
@@ -546,12 +555,11 @@ int lsq_count(lsq_ctx *c) {
             CP.slot_mask = slot_mask;
             CP.bases = bases;
             CP.stats = counters + 1;  // ext slots read by the GENERAL instantiation
-            // the class sizes are only known on the device: both instantiations get a grid that
-            // covers the whole read set and walk their own range of the sorted arrays
-            const size_t chunks = (n + lsq::COUNT_CHUNK - 1) / lsq::COUNT_CHUNK;
-            unsigned grid_f = (unsigned)std::min<size_t>(chunks, (size_t)c->n_sms * 5);
-            unsigned grid_g = (unsigned)std::min<size_t>(chunks, (size_t)c->n_sms * 3);
-            lsq::lsq_count_kernel<0><<<grid_f, lsq::COUNT_BLOCK, 0, s>>>(CP);
+            // the work lists are only known on the device: every instantiation gets a grid of
+            // resident blocks that stride over its own list
+            unsigned grid_f = (unsigned)std::min<size_t>(PS.pool_cap, (size_t)c->n_sms * 4);
+            unsigned grid_g = (unsigned)std::min<size_t>(PS.pool_cap, (size_t)c->n_sms * 3);
+            lsq::lsq_count_kernel<0><<<grid_f, lsq::COUNT_BLOCK, lsq::COUNT_FAST_DYN_SMEM, s>>>(CP);
             LSQ_CUDA(cudaGetLastError());
             lsq::lsq_count_kernel<1><<<grid_g, lsq::COUNT_BLOCK, 0, s>>>(CP);
             LSQ_CUDA(cudaGetLastError());
@@ -564,17 +572,19 @@ int lsq_count(lsq_ctx *c) {
         LSQ_CUDA(cudaMemcpyAsync(c->h_counters.data() + (size_t)m * 4, counters, 4 * 8, cudaMemcpyDeviceToHost, s));
         LSQ_CUDA(cudaStreamSynchronize(s));
         float f;
-        LSQ_CUDA(cudaEventElapsedTime(&f, c->ev[0], c->ev[1]));
-        acc[0] += f;
-        LSQ_CUDA(cudaEventElapsedTime(&f, c->ev[1], c->ev[2]));
+        LSQ_CUDA(cudaEventElapsedTime(&f, c->ev[0], c->ev[1]));  // counter resets + partition init
         acc[1] += f;
+        LSQ_CUDA(cudaEventElapsedTime(&f, c->ev[1], c->ev[2]));  // filter + partition kernel
+        acc[0] += f;
         LSQ_CUDA(cudaEventElapsedTime(&f, c->ev[2], c->ev[3]));
         acc[3] += f;
+        const unsigned long long *hc = c->h_counters.data() + (size_t)m * 4;
+        const unsigned long long kept = hc[0] + hc[2] + hc[3];  // FAST + PAIR + GENERAL reads
         tm.reads_in += n;
-        tm.reads_kept += c->h_counters[(size_t)m * 4 + 0];
-        // algorithmic bytes of the count kernel: key (4) + record (8) per kept read, plus the ext
+        tm.reads_kept += kept;
+        // algorithmic bytes of the count kernels: one 16-byte partitioned record per kept read, plus the ext
         // entry (8-byte header + 8 bytes per kept block) of every GENERAL-class read
-        tm.count_bytes += c->h_counters[(size_t)m * 4 + 0] * 12ull + c->h_counters[(size_t)m * 4 + 1] * 8ull;
+        tm.count_bytes += kept * 16ull + hc[1] * 8ull;
     }
     c->counted = true;
     c->finalized = false;

@@ -190,9 +190,14 @@ LSQ_HD void unpack_pair(ReadRec r, int32_t piece_pos, int2 &b0, int2 &b1, uint32
 }
 
 // Result of the per-read load filter.
+constexpr uint32_t CLS_FAST = 0, CLS_PAIR = 1, CLS_GENERAL = 2, CLS_DROPPED = 3;
 struct FilteredRead {
     uint32_t n;       // kept intervals (0: read dropped)
     uint32_t key;     // piece (FAST), n_pieces + piece (PAIR), 2 n_pieces + piece (GENERAL), KEY_DROPPED
+    uint32_t cls;     // CLS_*: key / n_pieces
+    uint32_t piece;   // key - cls * n_pieces (undefined when dropped)
+    uint32_t stab_off;  // first stab entry of the piece: selects the stab bucket
+    uint32_t stab_n;    // stab entries of the piece
     int2 second;      // second kept interval (n >= 2)
     int32_t piece_pos;  // first position of the read's piece
     int2 first;       // first kept interval
@@ -204,7 +209,34 @@ struct FilteredRead {
 // chromosome; kept blocks are merged into the read's interval list (work[0..n), used only when
 // the read has more than one raw block); the read's chromosome/strand are those of the last
 // registered block; the stab piece is looked up for the first kept start.
-LSQ_HD FilteredRead filter_read(const FilterParams &P, uint64_t r) {
+// The filter is written against a read context that says where its inputs come from, so that the
+// kernel can hand it blocks, lookup answers and piece records it has already fetched (several
+// reads at a time) while the CPU replay and the fallback path fetch on demand:
+//   ctx.blk(j)          raw block j of the read
+//   ctx.lookup(j, c, b) for block j = [b.x, b.y) on chromosome c: the piece holding b.x in bits
+//                       0-30 (PIECE_NONE: before the first piece) and, in bit 31, whether the
+//                       covered region of that piece reaches b.y
+//   ctx.pinfo(p)        the 16-byte PieceInfo of piece p
+constexpr uint32_t PIECE_NONE = 0x7FFFFFFFu;
+
+LSQ_HD uint32_t lookup_direct(const Tables &T, uint32_t c, int2 b) {
+    PieceInfo pi;
+    const uint32_t pidx = find_piece(T, c, b.x, pi);
+    if (pidx == 0xFFFFFFFFu) return PIECE_NONE;
+    return pidx | (pi.cov_end >= b.y ? 0x80000000u : 0u);
+}
+
+struct DirectCtx {  // everything on demand, lookups through find_piece
+    const FilterParams &P;
+    uint32_t base;
+    LSQ_HD int2 blk(uint32_t j) const { return LSQ_LD_STREAM(P.blk + base + j); }
+    LSQ_HD uint32_t lookup(uint32_t, uint32_t c, int2 b) const { return lookup_direct(P.T, c, b); }
+    LSQ_HD uint4 pinfo(uint32_t p) const { return LSQ_LD(reinterpret_cast<const uint4 *>(P.T.pinfo + p)); }
+};
+
+template <class Ctx>
+LSQ_HD FilteredRead filter_read_t(const FilterParams &P, uint64_t r, uint32_t base, uint32_t nraw, uint32_t cs0,
+                                  const Ctx &ctx) {
     const Tables &T = P.T;
     FilteredRead out;
     out.n = 0;
@@ -214,32 +246,29 @@ LSQ_HD FilteredRead filter_read(const FilterParams &P, uint64_t r) {
     out.at_piece_start = 0;
     out.second = make_int2(0, 0);
     out.piece_pos = 0;
-    const uint32_t base = LSQ_LD_STREAM(P.blk_off + r);
-    const uint32_t nraw = LSQ_LD_STREAM(P.blk_off + r + 1) - base;
-    const uint32_t cs0 = LSQ_LD_STREAM(P.read_cs + r);
+    out.cls = CLS_DROPPED;
+    out.piece = 0;
+    out.stab_off = 0;
+    out.stab_n = 0;
     const bool mixed = (cs0 & 0x80000000u) != 0;
     uint32_t chrom = 0xFFFFFFFFu;  // annotation id of the last registered block
     bool registered = false;
     int32_t last_end = 0;
     uint32_t n = 0;
-    int2 first = make_int2(0, 0);
-    // the read's interval list is built in place in its ext entry (blocks start one slot after
-    // the header); it is only touched when the read has more than one raw block
+    int2 first = make_int2(0, 0), second = make_int2(0, 0);
+    // The read's interval list lives in registers while it has at most two intervals; a third
+    // interval or an out-of-order block spills it to the read's ext entry (blocks start one slot
+    // after the header), where the general list update works in place.
     int2 *work = P.ext + ext_slot(base, (uint32_t)r) + 1;
+    bool spilled = false;
     uint32_t first_chrom = 0xFFFFFFFFu;
     uint32_t first_piece = 0xFFFFFFFFu;  // piece of `first` when it was found while filtering
-    PieceInfo first_pi;
-    first_pi.pos = 0;
-    first_pi.cov_end = 0;
-    first_pi.stab_off = 0;
-    first_pi.stab_n = 0;
     bool first_valid = false;
     for (uint32_t j = 0; j < nraw; ++j) {
-        int2 b = LSQ_LD_STREAM(P.blk + base + j);
-        uint32_t cs = mixed ? LSQ_LD(P.blk_cs + base + j) : cs0;
-        uint32_t c = LSQ_LD(P.chrom_remap + (cs & 0xFFFFu));
+        const int2 b = ctx.blk(j);
+        const uint32_t cs = mixed ? LSQ_LD(P.blk_cs + base + j) : cs0;
+        const uint32_t c = LSQ_LD(P.chrom_remap + (cs & 0xFFFFu));
         bool keep;
-        PieceInfo pi;
         uint32_t pidx = 0xFFFFFFFFu;
         if (!(b.x < b.y)) {
             keep = true;  // a nil block is "contained" (interval_list.hpp:398-401)
@@ -248,8 +277,9 @@ LSQ_HD FilteredRead filter_read(const FilterParams &P, uint64_t r) {
             // start must reach the block end
             keep = false;
             if (c != 0xFFFFFFFFu) {
-                pidx = find_piece(T, c, b.x, pi);
-                keep = pidx != 0xFFFFFFFFu && pi.cov_end >= b.y;
+                const uint32_t res = ctx.lookup(j, c, b);
+                pidx = res & PIECE_NONE;
+                keep = pidx != PIECE_NONE && (res >> 31) != 0u;
             }
         }
         if (!keep) continue;
@@ -262,24 +292,38 @@ LSQ_HD FilteredRead filter_read(const FilterParams &P, uint64_t r) {
             last_end = b.y;
             n = 1;
             first_piece = pidx;
-            first_pi = pi;
             first_valid = true;
             first_chrom = c;
-            if (nraw > 1) work[0] = b;
         } else if (b.x >= last_end) {
             if (b.x == last_end) {  // starts where the last interval ends: the two fuse
                 last_end = b.y;
                 if (n == 1) first.y = b.y;
-                work[n - 1].y = b.y;
+                if (n == 2) second.y = b.y;
+                if (spilled) work[n - 1].y = b.y;
             } else {
-                work[n] = b;
+                if (n == 1) {
+                    second = b;
+                } else {
+                    if (!spilled) {
+                        work[0] = first;
+                        work[1] = second;
+                        spilled = true;
+                    }
+                    work[n] = b;
+                }
                 last_end = b.y;
                 ++n;
             }
         } else {  // out of order or overlapping: general list update
+            if (!spilled) {
+                work[0] = first;
+                if (n >= 2) work[1] = second;
+                spilled = true;
+            }
             n = list_add(work, n, b.x, b.y);
             first_valid = first_valid && work[0].x == first.x;
             first = work[0];
+            if (n >= 2) second = work[1];
             last_end = work[n - 1].y;
         }
     }
@@ -289,18 +333,187 @@ LSQ_HD FilteredRead filter_read(const FilterParams &P, uint64_t r) {
         // the read's chromosome is that of the LAST registered block; the piece found while
         // filtering is reused when it was looked up on that chromosome for this very start
         uint32_t p = first_piece;
-        PieceInfo pi = first_pi;
-        if (!first_valid || first_chrom != chrom) p = find_piece(T, chrom, first.x, pi);
+        PieceInfo pi;
+        if (!first_valid || first_chrom != chrom) {
+            p = find_piece(T, chrom, first.x, pi);
+        } else {
+            const uint4 raw = ctx.pinfo(p);
+            pi.pos = (int32_t)raw.x;
+            pi.cov_end = (int32_t)raw.y;
+            pi.stab_off = raw.z;
+            pi.stab_n = raw.w;
+        }
         if (p != 0xFFFFFFFFu && (pi.stab_n & ~PIECE_ALL_FAST) > 0) {
             out.at_piece_start = pi.pos == first.x ? 1u : 0u;
             out.piece_pos = pi.pos;
-            if (n >= 2) out.second = work[1];
-            if (is_fast_read(n, out.at_piece_start, first, pi.stab_n)) out.key = p;
-            else if (is_pair_read(n, out.at_piece_start, first, out.second, pi.pos, out.strand)) out.key = T.n_pieces + p;
-            else out.key = 2u * T.n_pieces + p;
+            if (n >= 2) out.second = second;
+            if (is_fast_read(n, out.at_piece_start, first, pi.stab_n)) out.cls = CLS_FAST;
+            else if (is_pair_read(n, out.at_piece_start, first, out.second, pi.pos, out.strand)) out.cls = CLS_PAIR;
+            else out.cls = CLS_GENERAL;
+            out.key = out.cls * T.n_pieces + p;
+            out.piece = p;
+            out.stab_off = pi.stab_off;
+            out.stab_n = pi.stab_n & ~PIECE_ALL_FAST;
         }
     }
     return out;
+}
+
+// The ext entry of a GENERAL read: header {read index, (strand << 24) | n} at its slot, then the
+// kept blocks.  Blocks 2.. were spilled by the filter; the first two come from its registers.
+LSQ_HD void write_ext_entry(int2 *ext, uint32_t off, uint32_t r, const FilteredRead &fr) {
+    ext[off] = make_int2((int32_t)r, (int32_t)((fr.strand << 24) | (fr.n & 0xFFFFFFu)));
+    ext[off + 1] = fr.first;
+    if (fr.n >= 2u) ext[off + 2] = fr.second;
+}
+
+LSQ_HD FilteredRead filter_read(const FilterParams &P, uint64_t r) {
+    const uint32_t base = LSQ_LD_STREAM(P.blk_off + r);
+    const uint32_t nraw = LSQ_LD_STREAM(P.blk_off + r + 1) - base;
+    const uint32_t cs0 = LSQ_LD_STREAM(P.read_cs + r);
+    const DirectCtx ctx{P, base};
+    return filter_read_t(P, r, base, nraw, cs0, ctx);
+}
+
+// ---------------------------------------------------------------------------------------------
+// The piece lookup of one block, split into stages (chromosome -> bucket slot -> candidate
+// pieces -> selection) so that the kernel can issue the loads of one stage for several blocks
+// before it consumes any of them: the chain of dependent L2 accesses, not arithmetic, bounds
+// the filter.  A stage hands the block over to find_piece (SP_DEFER) when it meets a case it
+// does not cover; both give identical answers (tests/emul replays block_lookup).
+// ---------------------------------------------------------------------------------------------
+constexpr int SP_DROP = 0, SP_GO = 1, SP_DEFER = 2;
+struct BlockProbe {
+    int2 b;          // the block
+    uint32_t c;      // annotation chromosome id
+    uint32_t lo;     // first piece of the chromosome
+    uint32_t slot;   // bucket slot: pieces [bp_bkt[slot], bp_bkt[slot + 1]) start inside the bucket of b.x
+};
+
+LSQ_HD int block_stage_chrom(const FilterParams &P, int2 b, uint32_t cs, BlockProbe &q) {
+    q.b = b;
+    q.c = LSQ_LD(P.chrom_remap + (cs & 0xFFFFu));
+    q.lo = 0;
+    q.slot = 0;
+    if (!(b.x < b.y)) return SP_DROP;         // nil blocks are never looked up
+    if (q.c == 0xFFFFFFFFu) return SP_DROP;   // chromosome without annotation
+    if (b.x < 0) return SP_DEFER;
+    const uint4 cm = LSQ_LD(P.T.chrom_meta + q.c);
+    const uint32_t bk = (uint32_t)b.x >> P.T.bp_shift;
+    if (bk >= cm.w) return SP_DEFER;
+    q.lo = cm.x;
+    q.slot = cm.z + bk;
+    return SP_GO;
+}
+
+// Candidate pieces of the bucket range [i, j): i-1 (starts before the bucket), i and i+1; indices
+// clamped so that the loads can be issued unconditionally (pinfo carries one sentinel).  Of each
+// candidate only {pos, cov_end} is needed.
+LSQ_HD void block_stage_cand(const BlockProbe &q, uint32_t i, uint32_t j, uint32_t &a0, uint32_t &a1, uint32_t &a2) {
+    a0 = i > q.lo ? i - 1 : i;
+    a1 = i;
+    a2 = i + 1 < j ? i + 1 : i;
+}
+
+// Selection among the candidates: the answer of `lookup`, or SP_DEFER for a crowded bucket.
+LSQ_HD int block_stage_select(const BlockProbe &q, uint32_t i, uint32_t j, int2 r0, int2 r1, int2 r2, uint32_t &res) {
+    const int32_t x = q.b.x;
+    res = PIECE_NONE;
+    uint32_t p;
+    int32_t cov_end;
+    if (!(i < j) || r1.x > x) {
+        if (i == q.lo) return SP_GO;  // before the first piece of the chromosome
+        p = i - 1;
+        cov_end = r0.y;
+    } else if (!(i + 1 < j) || r2.x > x) {
+        p = i;
+        cov_end = r1.y;
+    } else if (i + 2 == j) {
+        p = i + 1;
+        cov_end = r2.y;
+    } else {
+        return SP_DEFER;  // find_piece searches the bucket
+    }
+    res = p | (cov_end >= q.b.y ? 0x80000000u : 0u);
+    return SP_GO;
+}
+
+// Sequential composition of the stages (CPU replay; the kernel runs the same stages batched).
+LSQ_HD uint32_t block_lookup(const FilterParams &P, int2 b, uint32_t cs) {
+    BlockProbe q;
+    int st = block_stage_chrom(P, b, cs, q);
+    if (st == SP_DROP) return PIECE_NONE;
+    uint32_t res = PIECE_NONE;
+    if (st == SP_GO) {
+        const uint32_t i = LSQ_LD(P.T.bp_bkt + q.slot), j = LSQ_LD(P.T.bp_bkt + q.slot + 1);
+        uint32_t a0, a1, a2;
+        block_stage_cand(q, i, j, a0, a1, a2);
+        st = block_stage_select(q, i, j, LSQ_LD(reinterpret_cast<const int2 *>(P.T.pinfo + a0)),
+                                LSQ_LD(reinterpret_cast<const int2 *>(P.T.pinfo + a1)),
+                                LSQ_LD(reinterpret_cast<const int2 *>(P.T.pinfo + a2)), res);
+    }
+    if (st == SP_DEFER) res = lookup_direct(P.T, q.c, b);
+    return res;
+}
+
+// The filter for the common read -- exactly one raw block b, chromosome/strand ids from read_cs --
+// given the lookup answer `res` of that block (nil blocks and blocks on chromosomes without
+// annotation answer PIECE_NONE) and, for a kept block, the PieceInfo `raw` of the answered piece.
+// Same result as filter_read_t on such a read, without its interval-list machinery.
+LSQ_HD bool single_kept(uint32_t res) { return (res & PIECE_NONE) != PIECE_NONE && (res >> 31) != 0u; }
+LSQ_HD FilteredRead single_decide(const Tables &T, int2 b, uint32_t cs0, uint32_t res, uint4 raw) {
+    FilteredRead out;
+    out.n = 0;
+    out.key = KEY_DROPPED(T);
+    out.first = b;
+    out.strand = (cs0 >> 16) & 0xFFu;
+    out.at_piece_start = 0;
+    out.second = make_int2(0, 0);
+    out.piece_pos = 0;
+    out.cls = CLS_DROPPED;
+    out.piece = 0;
+    out.stab_off = 0;
+    out.stab_n = 0;
+    if (!single_kept(res)) return out;
+    out.n = 1;
+    const uint32_t stab_n = raw.w;
+    if ((stab_n & ~PIECE_ALL_FAST) == 0u) return out;  // candidate of no event
+    const uint32_t p = res & PIECE_NONE;
+    out.at_piece_start = (int32_t)raw.x == b.x ? 1u : 0u;
+    out.piece_pos = (int32_t)raw.x;
+    out.cls = is_fast_read(1u, out.at_piece_start, b, stab_n) ? CLS_FAST : CLS_GENERAL;
+    out.key = out.cls * T.n_pieces + p;
+    out.piece = p;
+    out.stab_off = raw.z;
+    out.stab_n = stab_n & ~PIECE_ALL_FAST;
+    return out;
+}
+
+// The load filter as the kernel runs it: every block answered by block_lookup, single-block reads
+// decided by single_decide, all others by filter_read_t.
+struct StagedCtx {
+    const FilterParams &P;
+    uint32_t base, cs0;
+    LSQ_HD int2 blk(uint32_t j) const { return LSQ_LD_STREAM(P.blk + base + j); }
+    LSQ_HD uint32_t lookup(uint32_t j, uint32_t, int2 b) const {
+        const uint32_t cs = (cs0 & 0x80000000u) ? LSQ_LD(P.blk_cs + base + j) : cs0;
+        return block_lookup(P, b, cs);
+    }
+    LSQ_HD uint4 pinfo(uint32_t p) const { return LSQ_LD(reinterpret_cast<const uint4 *>(P.T.pinfo + p)); }
+};
+LSQ_HD FilteredRead filter_dispatch(const FilterParams &P, uint64_t r) {
+    const uint32_t base = LSQ_LD_STREAM(P.blk_off + r);
+    const uint32_t nraw = LSQ_LD_STREAM(P.blk_off + r + 1) - base;
+    const uint32_t cs0 = LSQ_LD_STREAM(P.read_cs + r);
+    if (nraw == 1u && !(cs0 & 0x80000000u)) {
+        const int2 b = LSQ_LD_STREAM(P.blk + base);
+        const uint32_t res = block_lookup(P, b, cs0);
+        const uint4 raw = single_kept(res) ? LSQ_LD(reinterpret_cast<const uint4 *>(P.T.pinfo + (res & PIECE_NONE)))
+                                           : make_uint4(0u, 0u, 0u, 0u);
+        return single_decide(P.T, b, cs0, res, raw);
+    }
+    const StagedCtx ctx{P, base, cs0};
+    return filter_read_t(P, r, base, nraw, cs0, ctx);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -1,8 +1,9 @@
 // Hand-written sm_100a kernels of the count + solve hot path.
 //
-//   lsq_filter_kernel  per-block covered-region filter + per-read interval list + stab piece key
+//   lsq_filter_kernel  per-block covered-region filter + per-read interval list + stab piece key,
+//                      partition of the kept reads by (read class, stab bucket)
 //                      (count/count.cpp:319-324; jsc/util/interval_list.hpp:396-422, 462-503;
-//                       index key of count.cpp:346-364)
+//                       read index of count.cpp:346-364)
 //   lsq_count_kernel   candidate scan, Read_single::build walk, compatibility, validity, class
 //                      histogram (count.cpp:421-482; common/read.h:44-79, 204-274)
 //   lsq_finalize_kernel per-event n_valid and per-form tallies from the class histogram
@@ -16,55 +17,322 @@
 namespace lsq {
 
 // ---------------------------------------------------------------------------------------------
-// Filter kernel: one thread per read.
+// Filter + partition kernel: one CTA per tile of FILT_TILE consecutive reads.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
-__global__ void __launch_bounds__(256) lsq_filter_kernel(FilterParams P) {
-    const Tables &T = P.T;
-    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= P.n_reads) return;
-    const FilteredRead fr = filter_read(P, r);
-    const bool kept = fr.key != KEY_DROPPED(T);
-    ReadRec rec;
-    if (kept && fr.key >= T.n_pieces && fr.key < 2u * T.n_pieces) {
-        rec = pack_pair(fr.first, fr.second, fr.piece_pos, fr.strand);  // PAIR class: two blocks inline
-    } else if (kept && fr.key >= 2u * T.n_pieces) {
-        // GENERAL class: the ext entry of read r lives at the even slot (blk_off[r] + 2r) & ~1:
-        // 1 header + n <= 1 + raw blocks, so no allocation is needed, entries of different reads
-        // never overlap, and header + first block form one aligned 128-bit access.  Blocks 1..n-1
-        // were left in place by filter_read.
-        const uint32_t off = ext_slot(__ldg(P.blk_off + r), (uint32_t)r);
-        *reinterpret_cast<int4 *>(P.ext + off) =
-            make_int4((int32_t)(uint32_t)r, (int32_t)((fr.strand << 24) | (fr.n & 0xFFFFFFu)), fr.first.x, fr.first.y);
-        rec.x = off;
-        rec.y = fr.n;
-    } else {
-        rec.x = (uint32_t)fr.first.x;
-        rec.y = (uint32_t)(fr.first.y - fr.first.x) | (fr.strand << 16);
-    }
-    __stcs(P.rkey + r, fr.key);  // streamed to the sort: do not displace the tables in L2
-    __stcs(P.rec + r, rec);
+constexpr int FILT_BLOCK = 512;
+constexpr int FILT_ITEMS = 4;                         // reads per thread (all kept in flight together)
+constexpr int FILT_LBATCH = 3;                        // block lookups kept in flight per thread
+constexpr int FILT_RBATCH = 3;                        // bin reservations kept in flight per thread
+constexpr int FILT_TILE = FILT_BLOCK * FILT_ITEMS;    // 2048 reads
+constexpr int FILT_MAX_BLK = 4096;                    // raw blocks of a tile whose lookups are staged
+static_assert((uint32_t)FILT_TILE <= PART_CHUNK, "a tile's reservation may span at most two chunks");
+
+// dynamic shared memory of the filter kernel
+__host__ __device__ inline size_t filter_smem_bytes(uint32_t n_bins) {
+    return (size_t)FILT_TILE * (16 + 4 + 2) + (size_t)FILT_MAX_BLK * 4 + (size_t)n_bins * (4 + 4 + 2) + 64;
 }
 
-// After the sort: class sizes from the sorted keys (three binary searches by one thread) --
-// counters[0] = kept reads (key < 3 n_pieces), counters[2] = PAIR reads, counters[3] = GENERAL reads.
-__global__ void lsq_class_bounds_kernel(const uint32_t *__restrict__ g_key, unsigned long long n, uint32_t n_pieces,
-                                        unsigned long long *counters) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    auto lower = [&](uint32_t v) {
-        unsigned long long lo = 0, hi = n;
-        while (lo < hi) {
-            unsigned long long mid = (lo + hi) >> 1;
-            if (g_key[mid] < v) lo = mid + 1;
-            else hi = mid;
+// Read context of the filter kernel (see filter_read_t): blocks and piece records are fetched on
+// demand, lookup answers come from the tile's shared staging.
+struct TileCtx {
+    const FilterParams &P;
+    const uint32_t *s_blk;
+    uint32_t base, tbase;
+    int2 b0, b1;  // the first two raw blocks, fetched by the caller
+    bool staged;
+    __device__ __forceinline__ int2 blk(uint32_t j) const { return j == 0u ? b0 : (j == 1u ? b1 : __ldg(P.blk + base + j)); }
+    __device__ __forceinline__ uint32_t lookup(uint32_t j, uint32_t c, int2 b) const {
+        return staged ? s_blk[base - tbase + j] : lookup_direct(P.T, c, b);
+    }
+    __device__ __forceinline__ uint4 pinfo(uint32_t p) const {
+        return __ldg(reinterpret_cast<const uint4 *>(P.T.pinfo + p));
+    }
+};
+
+__global__ void lsq_part_init_kernel(PartState S, uint32_t n_bkt) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= S.n_bins) return;
+    // every bin starts with chunk b, which is also the first work item of its class
+    S.state[b] = (unsigned long long)b << 32;
+    S.next_chunk[b] = S.n_bins + b;
+    S.owner[b] = b;
+    const uint32_t cls = b / n_bkt;
+    S.wl[(size_t)cls * S.pool_cap + (b - cls * n_bkt)] = b;
+    if (b < 3u) S.wl_n[b] = n_bkt;
+    if (b == 0u) *S.pool_next = 2u * S.n_bins;
+}
+
+// Phase A: every thread expands the chromosome/strand ids of its reads over their raw blocks.
+// Phase B: the tile's raw blocks (contiguous in blk[]) are spread over the threads regardless of
+//          the reads they belong to, and every thread runs the staged piece lookup
+//          (lsq_device_fn.cuh) on FILT_LBATCH blocks at a time, so the loads of each stage
+//          (block, bucket slot, candidate pieces) are in flight together and no lane idles
+//          because its read has fewer blocks than its neighbour's.  Answers go to shared memory.
+// Phase C: single-block reads (4 in 5) are decided by single_decide with block and piece record
+//          fetched for all of the thread's reads at once; the others go to a block-local list
+//          that is spread densely over the threads and takes filter_read_t (interval list, read
+//          class).  Records of the kept reads are staged in shared memory.
+// Phase D: one thread per non-empty bin reserves room for the tile's records of that bin with a
+//          single 64-bit atomicAdd on (chunk, fill); the reservation that takes the last slot of
+//          a chunk allocates the next chunk and publishes it.
+// Phase E: records go from shared memory to their slots (writes of one bin are contiguous; L2
+//          merges them into full sectors before they reach HBM).
+__global__ void __launch_bounds__(FILT_BLOCK, 2) lsq_filter_kernel(FilterParams P) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    const Tables &T = P.T;
+    const PartState &S = P.part;
+    const uint32_t n_bins = S.n_bins;
+    uint4 *s_rec = reinterpret_cast<uint4 *>(s_raw);  // PartRec of the tile's reads
+    uint32_t *s_br = reinterpret_cast<uint32_t *>(s_rec + FILT_TILE);  // bin | rank << 16
+    uint32_t *s_blk = s_br + FILT_TILE;              // per raw block: chromosome/strand ids, then the lookup answer
+    uint32_t *s_A = s_blk + FILT_MAX_BLK;            // per bin: records of the tile, then first slot
+    uint32_t *s_B = s_A + n_bins;                    // per bin: slot base after a chunk switch
+    uint32_t *s_n = s_B + n_bins;                    // [0] listed reads
+    uint16_t *s_multi = reinterpret_cast<uint16_t *>(s_n + 4);  // reads for filter_read_t (tile-local index)
+    uint16_t *s_split = s_multi + FILT_TILE;         // per bin: records before the chunk switch
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t i = tid; i < n_bins; i += FILT_BLOCK) s_A[i] = 0u;
+    if (tid == 0) s_n[0] = 0u;
+    const uint64_t tile0 = (uint64_t)blockIdx.x * FILT_TILE;
+    const uint64_t tile1 = min(tile0 + (uint64_t)FILT_TILE, P.n_reads);
+    const uint32_t n_bkt = T.n_bkt;
+    const uint32_t tbase = __ldg(P.blk_off + tile0);
+    const uint32_t tile_nblk = __ldg(P.blk_off + tile1) - tbase;
+    const bool staged = tile_nblk <= (uint32_t)FILT_MAX_BLK;  // block-uniform
+
+    // ---- phase A --------------------------------------------------------------------------
+    uint32_t rbase[FILT_ITEMS], rn[FILT_ITEMS], rcs[FILT_ITEMS];  // absolute block offset, raw blocks, ids
+#pragma unroll
+    for (int k = 0; k < FILT_ITEMS; ++k) {
+        const uint64_t r = tile0 + tid + (uint32_t)k * FILT_BLOCK;
+        rbase[k] = 0u;
+        rn[k] = 0u;
+        rcs[k] = 0u;
+        if (r < tile1) {
+            rbase[k] = __ldcs(P.blk_off + r);
+            rn[k] = __ldcs(P.blk_off + r + 1) - rbase[k];
+            rcs[k] = __ldcs(P.read_cs + r);
         }
-        return lo;
+    }
+    if (staged) {
+#pragma unroll
+        for (int k = 0; k < FILT_ITEMS; ++k) {
+            const uint32_t rel = rbase[k] - tbase;
+            if (rcs[k] & 0x80000000u) {
+                for (uint32_t j = 0; j < rn[k]; ++j) s_blk[rel + j] = __ldg(P.blk_cs + rbase[k] + j);
+            } else {
+                if (rn[k] >= 1u) s_blk[rel] = rcs[k];
+                for (uint32_t j = 1; j < rn[k]; ++j) s_blk[rel + j] = rcs[k];
+            }
+        }
+    }
+    __syncthreads();
+    // ---- phase B --------------------------------------------------------------------------
+    if (staged) {
+#pragma unroll 1
+        for (uint32_t k0 = tid; k0 < tile_nblk; k0 += FILT_BLOCK * FILT_LBATCH) {
+            int st[FILT_LBATCH];
+            BlockProbe q[FILT_LBATCH];
+            int2 b[FILT_LBATCH];
+#pragma unroll
+            for (int u = 0; u < FILT_LBATCH; ++u) {
+                const uint32_t k = k0 + (uint32_t)u * FILT_BLOCK;
+                st[u] = k < tile_nblk ? SP_GO : -1;
+                b[u] = st[u] == SP_GO ? __ldcs(P.blk + tbase + k) : make_int2(0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < FILT_LBATCH; ++u) {
+                const uint32_t k = k0 + (uint32_t)u * FILT_BLOCK;
+                if (st[u] == SP_GO) st[u] = block_stage_chrom(P, b[u], s_blk[k], q[u]);
+            }
+            uint32_t bi[FILT_LBATCH], bj[FILT_LBATCH];
+#pragma unroll
+            for (int u = 0; u < FILT_LBATCH; ++u) {
+                bi[u] = bj[u] = 0;
+                if (st[u] == SP_GO) {
+                    bi[u] = __ldg(T.bp_bkt + q[u].slot);
+                    bj[u] = __ldg(T.bp_bkt + q[u].slot + 1);
+                }
+            }
+            int2 r0[FILT_LBATCH], r1[FILT_LBATCH], r2[FILT_LBATCH];
+#pragma unroll
+            for (int u = 0; u < FILT_LBATCH; ++u) {
+                r0[u] = r1[u] = r2[u] = make_int2(0, 0);
+                if (st[u] == SP_GO) {
+                    uint32_t a0, a1, a2;
+                    block_stage_cand(q[u], bi[u], bj[u], a0, a1, a2);
+                    r0[u] = __ldg(reinterpret_cast<const int2 *>(T.pinfo + a0));
+                    r1[u] = __ldg(reinterpret_cast<const int2 *>(T.pinfo + a1));
+                    r2[u] = __ldg(reinterpret_cast<const int2 *>(T.pinfo + a2));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < FILT_LBATCH; ++u) {
+                const uint32_t k = k0 + (uint32_t)u * FILT_BLOCK;
+                if (st[u] < 0) continue;
+                uint32_t res = PIECE_NONE;
+                if (st[u] == SP_GO) st[u] = block_stage_select(q[u], bi[u], bj[u], r0[u], r1[u], r2[u], res);
+                if (st[u] == SP_DEFER) res = lookup_direct(T, q[u].c, b[u]);
+                s_blk[k] = res;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- phase C --------------------------------------------------------------------------
+    // record of a kept read -> shared staging (and the ext entry of a GENERAL read)
+    auto emit = [&](uint32_t li, uint64_t r, uint32_t base, const FilteredRead &fr) {
+        uint32_t br = BIN_NONE;
+        if (fr.cls != CLS_DROPPED) {
+            uint32_t cls = fr.cls;
+            const uint32_t so = fr.stab_off, nent = fr.stab_n;
+            if (so > PREC_MAX_SO || nent > PREC_MAX_N) cls = CLS_GENERAL;  // the piece does not fit the record
+            uint4 rec;
+            rec.x = so | (nent << PREC_SO_BITS);
+            if (cls == CLS_PAIR) {
+                const ReadRec pr = pack_pair(fr.first, fr.second, fr.piece_pos, fr.strand);  // two blocks inline
+                rec.y = (uint32_t)fr.piece_pos;
+                rec.z = pr.x;
+                rec.w = pr.y;
+            } else if (cls == CLS_GENERAL) {
+                // the ext entry of read r lives at the even slot (blk_off[r] + 2r) & ~1: 1 header +
+                // n <= 1 + raw blocks, so no allocation is needed, entries of different reads never
+                // overlap, and header + first block form one aligned 128-bit access
+                const uint32_t off = ext_slot(base, (uint32_t)r);
+                *reinterpret_cast<int4 *>(P.ext + off) = make_int4(
+                    (int32_t)(uint32_t)r, (int32_t)((fr.strand << 24) | (fr.n & 0xFFFFFFu)), fr.first.x, fr.first.y);
+                if (fr.n >= 2u) P.ext[off + 2] = fr.second;  // further blocks were spilled by the filter
+                rec.x = 0u;
+                rec.y = fr.piece;
+                rec.z = off;
+                rec.w = fr.n;
+            } else {
+                rec.y = 0u;
+                rec.z = (uint32_t)fr.first.x;
+                rec.w = (uint32_t)(fr.first.y - fr.first.x) | (fr.strand << 16);
+            }
+            const uint32_t bin = cls * n_bkt + (so >> T.bkt_shift);
+            const uint32_t rank = atomicAdd(&s_A[bin], 1u);
+            s_rec[li] = rec;
+            br = bin | (rank << 16);
+        }
+        s_br[li] = br;
     };
-    const unsigned long long kept = lower(3u * n_pieces), fast = lower(n_pieces), pair_end = lower(2u * n_pieces);
-    counters[0] = kept;
-    counters[2] = pair_end - fast;
-    counters[3] = kept - pair_end;
+    {
+        int2 b0[FILT_ITEMS];
+        uint32_t res[FILT_ITEMS];
+        uint4 pi0[FILT_ITEMS];
+        bool single[FILT_ITEMS];
+#pragma unroll
+        for (int k = 0; k < FILT_ITEMS; ++k) {
+            single[k] = staged && rn[k] == 1u && !(rcs[k] & 0x80000000u);
+            b0[k] = single[k] ? __ldg(P.blk + rbase[k]) : make_int2(0, 0);
+            res[k] = single[k] ? s_blk[rbase[k] - tbase] : PIECE_NONE;
+        }
+#pragma unroll
+        for (int k = 0; k < FILT_ITEMS; ++k)
+            pi0[k] = single_kept(res[k]) ? __ldg(reinterpret_cast<const uint4 *>(T.pinfo + (res[k] & PIECE_NONE)))
+                                         : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int k = 0; k < FILT_ITEMS; ++k) {
+            const uint32_t li = tid + (uint32_t)k * FILT_BLOCK;
+            const uint64_t r = tile0 + li;
+            if (single[k]) {
+                emit(li, r, rbase[k], single_decide(T, b0[k], rcs[k], res[k], pi0[k]));
+            } else if (r < tile1 && rn[k] != 0u) {
+                s_multi[atomicAdd(&s_n[0], 1u)] = (uint16_t)li;
+                s_rec[li] = make_uint4(rbase[k], rn[k], rcs[k], 0u);  // the read's inputs travel with the list entry
+            } else {
+                s_br[li] = BIN_NONE;  // no blocks, or past the end of the read set
+            }
+        }
+    }
+    __syncthreads();
+    {
+        const uint32_t nm = s_n[0];
+#pragma unroll 1
+        for (uint32_t k = tid; k < nm; k += FILT_BLOCK) {
+            const uint32_t li = s_multi[k];
+            const uint64_t r = tile0 + li;
+            const uint4 in = s_rec[li];
+            const uint32_t base = in.x, nraw = in.y;
+            const int2 b0 = __ldg(P.blk + base);
+            const int2 b1 = nraw >= 2u ? __ldg(P.blk + base + 1) : make_int2(0, 0);
+            const TileCtx ctx{P, s_blk, base, tbase, b0, b1, staged};
+            emit(li, r, base, filter_read_t(P, r, base, nraw, in.z, ctx));
+        }
+    }
+    __syncthreads();
+    // ---- phase D --------------------------------------------------------------------------
+    uint32_t kept[3] = {0u, 0u, 0u};
+#pragma unroll 1
+    for (uint32_t b0 = tid; b0 < n_bins; b0 += FILT_BLOCK * FILT_RBATCH) {
+        uint32_t c[FILT_RBATCH];
+        unsigned long long old[FILT_RBATCH];
+#pragma unroll
+        for (int u = 0; u < FILT_RBATCH; ++u) {
+            const uint32_t bin = b0 + (uint32_t)u * FILT_BLOCK;
+            c[u] = bin < n_bins ? s_A[bin] : 0u;
+            old[u] = 0ull;
+            if (c[u]) old[u] = atomicAdd(S.state + bin, (unsigned long long)c[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < FILT_RBATCH; ++u) {
+            if (!c[u]) continue;
+            const uint32_t bin = b0 + (uint32_t)u * FILT_BLOCK;
+            const uint32_t cls = (bin >= n_bkt ? 1u : 0u) + (bin >= 2u * n_bkt ? 1u : 0u);
+            kept[0] += cls == 0u ? c[u] : 0u;
+            kept[1] += cls == 1u ? c[u] : 0u;
+            kept[2] += cls == 2u ? c[u] : 0u;
+            unsigned long long *st = S.state + bin;
+            unsigned long long o = old[u];
+            while ((uint32_t)o >= PART_CHUNK) {
+                // the chunk was full: wait until the reservation that filled it has installed the
+                // next chunk, then try again
+                while ((uint32_t)(*reinterpret_cast<volatile unsigned long long *>(st)) >= PART_CHUNK) {
+                }
+                o = atomicAdd(st, (unsigned long long)c[u]);
+            }
+            const uint32_t f = (uint32_t)o, chunk = (uint32_t)(o >> 32);
+            uint32_t slotB = 0, first = 0xFFFFu;
+            if (f + c[u] >= PART_CHUNK) {
+                // this reservation takes the chunk's last slot: install the bin's spare chunk.  Others
+                // wait for the exchange, so nothing else happens before it; a spare equal to the
+                // current chunk is the previous switch's, whose successor is not published yet.
+                first = PART_CHUNK - f;
+                volatile uint32_t *nx = S.next_chunk + bin;
+                uint32_t j = *nx;
+                while (j == chunk) j = *nx;
+                atomicExch(st, ((unsigned long long)j << 32) | (unsigned long long)(c[u] - first));
+                slotB = j * PART_CHUNK - first;  // slot of rank r >= first is slotB + r
+                S.owner[j] = bin;
+                const uint32_t w = atomicAdd(S.wl_n + cls, 1u);
+                S.wl[(size_t)cls * S.pool_cap + w] = j;
+                *nx = atomicAdd(S.pool_next, 1u);
+                __threadfence();
+            }
+            s_A[bin] = chunk * PART_CHUNK + f;
+            s_B[bin] = slotB;
+            s_split[bin] = (uint16_t)first;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const uint32_t v = __reduce_add_sync(0xFFFFFFFFu, kept[k]);
+        if (lane_id() == 0 && v) atomicAdd(P.counters + (k == 0 ? 0 : k + 1), (unsigned long long)v);
+    }
+    __syncthreads();
+    // ---- phase E --------------------------------------------------------------------------
+#pragma unroll
+    for (int k = 0; k < FILT_ITEMS; ++k) {
+        const uint32_t li = tid + (uint32_t)k * FILT_BLOCK;
+        const uint32_t br = s_br[li];
+        const uint32_t bin = br & 0xFFFFu, rank = br >> 16;
+        if (bin == BIN_NONE) continue;
+        const uint32_t slot = (rank < (uint32_t)s_split[bin] ? s_A[bin] : s_B[bin]) + rank;
+        S.pool[slot] = s_rec[li];
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -92,214 +360,222 @@ __device__ __noinline__ void bump_class(unsigned long long *slot_cnt, unsigned l
     }
 }
 
-// Count kernel.  Reads arrive sorted by (stab piece, multi-block flag): a warp holds a few RUNS of
-// reads with the same key.  Every lane evaluates its own read against the j-th stab entry of its
-// own piece (lanes of a run share the entry, so the loads broadcast); per-class counts of a run
-// are formed with __ballot_sync/__popc restricted to the run's lane mask, the matched bases with a
-// segmented shuffle reduction, and the run's head lane issues the global reductions.
+// Count kernel.  A work item is one chunk of one bin: up to PART_CHUNK reads of one class whose
+// first kept start lies in one stab bucket, in no particular order.  The bucket's stab entries
+// are contiguous in memory and are staged in shared memory by a bulk async copy (TMA, completion
+// on an mbarrier) while the threads fetch their reads; every (read, stab entry) pair is
+// evaluated by one lane and tallied with shared-memory atomics into four block-local counters
+// per staged entry (classes {0}, {1}, {0,1} of events with at most two forms, and matched
+// bases), which are flushed to the global 64-bit counters once per item.  Events with more
+// forms update their class tables directly.  Buckets whose entries do not fit (pathological
+// nesting) are read through L1/L2 and tallied with global atomics.
 //
-// A CTA works on chunks of COUNT_CHUNK consecutive reads.  The stab entries and offsets of a
-// chunk's piece range are contiguous in memory and are staged in shared memory by bulk async
-// copies (TMA) one chunk ahead: full[stage] completes when the bytes have landed, empty[stage]
-// when all warps have released the stage.  Chunks whose tables do not fit are read through L1/L2.
+// FAST reads meet 1.7 entries on average but up to five, so a lane-per-read loop would leave most
+// lanes idle: instead every warp first expands its reads into a queue of (entry, start, length)
+// pairs in shared memory (offsets from a warp scan of the list lengths) and then evaluates the
+// pairs densely, one per lane.
 constexpr int COUNT_BLOCK = 256;
 constexpr int COUNT_WARPS = COUNT_BLOCK / 32;
-constexpr int COUNT_ITEMS = 8;
-constexpr int COUNT_CHUNK = COUNT_BLOCK * COUNT_ITEMS;
-constexpr int COUNT_MAX_ENT = 256;     // staged stab entries per stage (8 KB)
-constexpr int COUNT_MAX_OFF = 512;     // staged offsets per stage (2 KB)
+constexpr int COUNT_ITEMS = (int)PART_CHUNK / COUNT_BLOCK;  // 8 reads per thread and item
+constexpr int COUNT_ROUND = 4;          // FAST: reads per thread expanded together
+constexpr int COUNT_QCAP = 448;         // FAST: pair queue per warp (8 bytes per pair; dynamic shared memory)
+constexpr size_t COUNT_FAST_DYN_SMEM = (size_t)COUNT_QCAP * 8 * (COUNT_BLOCK / 32);
+constexpr int COUNT_MAX_ENT = 576;      // staged stab entries (18 KB): a bucket window + the longest stab list
+constexpr int PAIR_QCAP = 256;          // PAIR: pair queue per warp (one read per lane and round)
+constexpr uint32_t CTR_MAX_BASES = 1u << 20;  // larger matched lengths bypass the 32-bit block counters
 
-struct ChunkTables {
-    uint32_t e0, e1;   // stab entry range
-    uint32_t pa, noff; // 16-byte aligned offset slice
+struct ItemTables {
+    uint32_t chunk, n;   // pool chunk and its fill
+    uint32_t e0, e1;     // stab entry range of the bucket
     bool staged;
 };
 
-__device__ __forceinline__ ChunkTables chunk_tables(const CountParams &P, unsigned long long base,
-                                                    unsigned long long end, uint32_t key_bias) {
-    ChunkTables c;
-    const uint32_t pf = __ldg(P.g_key + base) - key_bias, pl = __ldg(P.g_key + end - 1) - key_bias;
-    c.e0 = __ldg(P.T.stab_off + pf);
-    c.e1 = __ldg(P.T.stab_off + pl + 1);
-    c.pa = pf & ~3u;
-    c.noff = ((pl + 2 - c.pa) + 3u) & ~3u;
-    c.staged = (c.e1 - c.e0) <= (uint32_t)COUNT_MAX_ENT && c.noff <= (uint32_t)COUNT_MAX_OFF && c.e1 > c.e0;
+template <int CLS>
+__device__ __forceinline__ ItemTables item_tables(const CountParams &P, uint32_t it) {
+    const PartState &S = P.part;
+    ItemTables c;
+    c.chunk = __ldg(S.wl + (size_t)CLS * S.pool_cap + it);
+    const uint32_t bin = __ldg(S.owner + c.chunk);
+    const unsigned long long st = __ldg(S.state + bin);
+    c.n = (uint32_t)(st >> 32) == c.chunk ? min((uint32_t)st, PART_CHUNK) : PART_CHUNK;
+    const uint32_t bkt = bin - (uint32_t)CLS * P.T.n_bkt;
+    const uint32_t p_lo = __ldg(P.T.bkt_piece + bkt), p_hi = __ldg(P.T.bkt_piece + bkt + 1);
+    c.e0 = __ldg(P.T.stab_off + p_lo);
+    c.e1 = __ldg(P.T.stab_off + p_hi);
+    c.staged = (c.e1 - c.e0) <= (uint32_t)COUNT_MAX_ENT && c.e1 > c.e0;
     return c;
 }
 
-// One q-step of the run aggregation: per-class counts of each run via ballots restricted to the
-// run's lane mask, matched bases via a segmented shuffle reduction, reductions by the head lane.
-// Staged chunks accumulate in block-local shared-memory counters (4 per staged stab entry: three
-// classes + bases) that are flushed once per chunk; other chunks reduce straight to global memory.
-__device__ __forceinline__ void aggregate_runs(const CountParams &P, uint32_t lane, bool head_has, unsigned run_mask,
-                                               uint32_t run_end, bool single_run, uint32_t cm, uint32_t ml,
-                                               uint32_t slot_off, uint32_t x, uint32_t *s_ctr /* or null */) {
-    // cm is 1, 2 or 3 for events with at most two forms (bit k = compatible with form k);
-    // larger tables were updated by the caller and arrive as the 0x80000000 marker
-    const unsigned f0 = __ballot_sync(0xFFFFFFFFu, (cm & 1u) != 0u);
-    const unsigned f1 = __ballot_sync(0xFFFFFFFFu, (cm & 2u) != 0u);
-    uint32_t v;
-    if (single_run) {  // warp-uniform: the whole warp is one run
-        v = __reduce_add_sync(0xFFFFFFFFu, ml);
-    } else {
-        v = ml;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_down_sync(0xFFFFFFFFu, v, d);
-            if (lane + (uint32_t)d < run_end) v += t;
-        }
-    }
-    if (head_has) {
-        const uint32_t c1 = __popc(f0 & ~f1 & run_mask), c2 = __popc(f1 & ~f0 & run_mask),
-                       c3 = __popc(f0 & f1 & run_mask);
-        if (s_ctr) {
-            if (c1) atomicAdd(s_ctr + 0, c1);
-            if (c2) atomicAdd(s_ctr + 1, c2);
-            if (c3) atomicAdd(s_ctr + 2, c3);
-            if (v) atomicAdd(s_ctr + 3, v);
-        } else {
-            if (c1) atomicAdd(P.slot_cnt + slot_off, (unsigned long long)c1);
-            if (c2) atomicAdd(P.slot_cnt + slot_off + 1u, (unsigned long long)c2);
-            if (c3) atomicAdd(P.slot_cnt + slot_off + 2u, (unsigned long long)c3);
-            if (v) atomicAdd(P.bases + x, (unsigned long long)v);
-        }
-    }
-}
-
-// CLS 0: FAST-class reads, positions [0, n_fast) of the sorted arrays -- purely table driven.
-// CLS 1: PAIR-class reads [n_fast, n_fast + n_pair) -- the general walk over two blocks held in the
-// sorted record.  CLS 2: GENERAL reads [.., n_kept) -- the general walk over the ext entries.
-// Separate instantiations keep the lean kernel's register count (and so its occupancy)
-// independent of the walk's.
+// CLS 0: FAST reads -- purely table driven.  CLS 1: PAIR reads -- two blocks held in the record.
+// CLS 2: GENERAL reads -- the walk of read.h:204-274 over the ext entries.  Separate
+// instantiations keep the lean kernel's register count (and so its occupancy) independent of
+// the walk's.
 template <int CLS>
-__global__ void __launch_bounds__(COUNT_BLOCK, CLS ? 3 : 5) lsq_count_kernel(CountParams P) {
-    constexpr bool GENERAL = CLS != 0;
-    __shared__ __align__(128) StabEntry s_ent[2][COUNT_MAX_ENT];
-    __shared__ __align__(16) uint32_t s_off[2][COUNT_MAX_OFF];
-    __shared__ __align__(8) uint64_t s_full[2], s_empty[2];
-    __shared__ uint32_t s_ctr[2][COUNT_MAX_ENT][4];  // block-local counters of the staged entries
-    __shared__ uint32_t s_done[2];                   // warps that finished the chunk of a stage
+__global__ void __launch_bounds__(COUNT_BLOCK, CLS == 0 ? 4 : 3) lsq_count_kernel(CountParams P) {
+    __shared__ __align__(128) StabEntry s_ent[COUNT_MAX_ENT];
+    __shared__ __align__(16) uint32_t s_ctr[COUNT_MAX_ENT][4];  // block-local counters of the staged entries
+    extern __shared__ __align__(16) uint2 s_q[];  // FAST: pair queues, COUNT_QCAP entries per warp
+    __shared__ __align__(16) uint4 s_pr[CLS == 1 ? COUNT_WARPS : 1][CLS == 1 ? 32 : 1];        // PAIR: parked reads
+    __shared__ uint32_t s_pq[CLS == 1 ? COUNT_WARPS : 1][CLS == 1 ? PAIR_QCAP : 1];            // PAIR: pair queues
+    __shared__ __align__(8) uint64_t s_full;
     const Tables &T = P.T;
-    for (uint32_t i = threadIdx.x; i < 2u * COUNT_MAX_ENT * 4u; i += COUNT_BLOCK) (&s_ctr[0][0][0])[i] = 0u;
-    if (threadIdx.x < 2) s_done[threadIdx.x] = 0u;
-    const unsigned long long n_fast = P.counters[0] - P.counters[3] - P.counters[2];
-    const unsigned long long n_pair_end = n_fast + P.counters[2];
-    const unsigned long long r_begin = CLS == 0 ? 0ull : (CLS == 1 ? n_fast : n_pair_end);
-    const unsigned long long r_end = CLS == 0 ? n_fast : (CLS == 1 ? n_pair_end : P.counters[0]);
-    const uint32_t key_bias = (uint32_t)CLS * T.n_pieces;
-    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-    const bool producer = threadIdx.x == 0;
-    if (producer) {
-        mbar_init(&s_full[0], 1);
-        mbar_init(&s_full[1], 1);
-        mbar_init(&s_empty[0], COUNT_WARPS);
-        mbar_init(&s_empty[1], COUNT_WARPS);
-    }
+    const PartState &S = P.part;
+    const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+    for (uint32_t i = tid; i < (uint32_t)COUNT_MAX_ENT * 4u; i += COUNT_BLOCK) (&s_ctr[0][0])[i] = 0u;
+    if (tid == 0) mbar_init(&s_full, 1);
     __syncthreads();
-    const unsigned long long n_chunks = (r_end - r_begin + COUNT_CHUNK - 1) / COUNT_CHUNK;
-    auto issue = [&](unsigned long long chunk, uint32_t stage) {  // producer only
-        const unsigned long long base = r_begin + chunk * COUNT_CHUNK;
-        const unsigned long long end = min(base + (unsigned long long)COUNT_CHUNK, r_end);
-        const ChunkTables c = chunk_tables(P, base, end, key_bias);
-        if (c.staged) {
-            const uint32_t ebytes = (c.e1 - c.e0) * (uint32_t)sizeof(StabEntry), obytes = c.noff * 4u;
-            mbar_expect_tx(&s_full[stage], ebytes + obytes);
-            bulk_g2s(s_ent[stage], T.stab + c.e0, ebytes, &s_full[stage]);
-            bulk_g2s(s_off[stage], T.stab_off + c.pa, obytes, &s_full[stage]);
-        } else {
-            mbar_arrive(&s_full[stage]);
-        }
-    };
-    if (producer && blockIdx.x < n_chunks) issue(blockIdx.x, 0);
-    uint32_t j = 0;
+    const uint32_t n_items = __ldg(S.wl_n + CLS);
     uint32_t my_slots = 0;  // GENERAL: ext slots read (byte accounting)
-    for (unsigned long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x, ++j) {
-        const uint32_t stage = j & 1u;
-        if (producer && chunk + gridDim.x < n_chunks) {
-            const uint32_t ns = (j + 1u) & 1u;
-            if (j + 1u >= 2u) mbar_wait(&s_empty[ns], (((j + 1u) >> 1) - 1u) & 1u);
-            issue(chunk + gridDim.x, ns);
+    uint32_t phase = 0;
+#pragma unroll 1
+    for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const ItemTables ct = item_tables<CLS>(P, it);
+        if (ct.n == 0u) continue;  // block-uniform
+        if (ct.staged && tid == 0) {
+            const uint32_t ebytes = (ct.e1 - ct.e0) * (uint32_t)sizeof(StabEntry);
+            mbar_expect_tx(&s_full, ebytes);
+            bulk_g2s(s_ent, T.stab + ct.e0, ebytes, &s_full);
         }
-        const unsigned long long base = r_begin + chunk * COUNT_CHUNK;
-        const unsigned long long end = min(base + (unsigned long long)COUNT_CHUNK, r_end);
-        const ChunkTables ct = chunk_tables(P, base, end, key_bias);
-        if (lane == 0) mbar_wait(&s_full[stage], (j >> 1) & 1u);  // one poller per warp
-        __syncwarp();
-        const StabEntry *ent = ct.staged ? s_ent[stage] - ct.e0 : T.stab;
-        const uint32_t *off = ct.staged ? s_off[stage] - ct.pa : T.stab_off;
-        uint32_t(*ctr)[4] = ct.staged ? s_ctr[stage] - ct.e0 : nullptr;
-        // software pipeline: the next iteration's key and record are loaded before this one is used
-        unsigned long long i = base + (unsigned long long)(warp * COUNT_ITEMS * 32u) + lane;
-        uint32_t key_n = 0xFFFFFFFFu;
-        ReadRec rec_n = make_uint2(0u, 0u);
-        if (i < end) {
-            key_n = __ldcs(P.g_key + i);
-            rec_n = __ldcs(P.g_rec + i);
+        // FAST: all of the thread's reads of this item are fetched while the entries are in flight;
+        // the other classes keep one read in flight ahead of the one being walked
+        constexpr int NPRE = CLS == 0 ? COUNT_ITEMS : 1;
+        uint4 rec[NPRE];
+        const uint4 *pool = S.pool + (size_t)ct.chunk * PART_CHUNK;
+#pragma unroll
+        for (int k = 0; k < NPRE; ++k) {
+            const uint32_t i = tid + (uint32_t)k * COUNT_BLOCK;
+            rec[k] = make_uint4(0u, 0u, 0u, 0u);  // no entries: past the end of the item
+            if (i < ct.n) rec[k] = __ldcs(pool + i);
         }
-        for (int it = 0; it < COUNT_ITEMS; ++it, i += 32u) {
-            if (i - lane >= end) break;  // warp-uniform
-            const bool act = i < end;
-            const uint32_t key = key_n;
-            const ReadRec rec = rec_n;
-            key_n = 0xFFFFFFFFu;
-            if (it + 1 < COUNT_ITEMS && i + 32u < end) {
-                key_n = __ldcs(P.g_key + i + 32u);
-                rec_n = __ldcs(P.g_rec + i + 32u);
-            }
-            uint32_t so = 0, nent = 0;
-            if (act) {
-                const uint32_t piece = key - key_bias;
-                so = off[piece];
-                nent = off[piece + 1] - so;
-            }
-            // runs of equal keys: head lane, lane mask and end of the run
-            const uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, key, 1);
-            const bool head = lane == 0 || key != prev;
-            const unsigned heads = __ballot_sync(0xFFFFFFFFu, head);
-            const bool single_run = heads == 1u;
-            const unsigned above = lane == 31 ? 0u : (heads >> (lane + 1));
-            const uint32_t run_end = above ? lane + (uint32_t)__ffs(above) : 32u;  // first lane of the next run
-            const unsigned run_mask = (run_end == 32u ? 0xFFFFFFFFu : ((1u << run_end) - 1u)) & ~((1u << lane) - 1u);
-            const uint32_t max_ent = __reduce_max_sync(0xFFFFFFFFu, nent);
-            if (!GENERAL) {
-                const int32_t s0 = (int32_t)rec.x, e0 = s0 + (int32_t)(rec.y & 0xFFFFu);
-                for (uint32_t q = 0; q < max_ent; ++q) {
-                    const bool has = q < nent;
-                    uint32_t cm = 0, ml = 0, slot_off = 0, x = 0;
-                    if (has) {
-                        const StabEntry en = ent[so + q];  // SE_FAST by construction of the class
-                        slot_off = en.slot_off;
-                        x = en.x;
-                        cm = eval_fast(en, s0, e0, ml);
-                        if (cm != 0 && en.K > 2) {  // dense class table with more than 3 classes
-                            atomicAdd(P.slot_cnt + slot_off + (cm - 1u), 1ull);
-                            cm = 0x80000000u;
-                        }
-                    }
-                    aggregate_runs(P, lane, head && has, run_mask, run_end, single_run, cm, ml, slot_off, x,
-                                   ctr ? ctr[so + q] : nullptr);
-                }
+        if (ct.staged) {
+            mbar_wait(&s_full, phase);
+            phase ^= 1u;
+        }
+        const StabEntry *ent = ct.staged ? s_ent - ct.e0 : T.stab;
+        uint32_t(*ctr)[4] = ct.staged ? s_ctr - ct.e0 : nullptr;
+        // tally of one valid (read, entry) pair with at most two forms
+        auto tally = [&](const StabEntry &en, uint32_t e, uint32_t cm, uint32_t ml) {
+            if (ctr && ml < CTR_MAX_BASES) {
+                atomicAdd(&ctr[e][cm - 1u], 1u);
+                atomicAdd(&ctr[e][3], ml);
             } else {
-                ReadView rv;
+                atomicAdd(P.slot_cnt + en.slot_off + (cm - 1u), 1ull);
+                atomicAdd(P.bases + en.x, (unsigned long long)ml);
+            }
+        };
+        auto tally_bases = [&](const StabEntry &en, uint32_t e, uint32_t ml) {
+            if (ctr && ml < CTR_MAX_BASES) atomicAdd(&ctr[e][3], ml);
+            else atomicAdd(P.bases + en.x, (unsigned long long)ml);
+        };
+        auto pair_fast = [&](uint32_t e, int32_t s0, int32_t e0) {  // one FAST read against stab entry e
+            const StabEntry en = ent[e];  // SE_FAST by construction of the class
+            uint32_t ml;
+            const uint32_t cm = eval_fast(en, s0, e0, ml);
+            if (cm == 0u) return;
+            if (en.K > 2) {  // dense class table with more than 3 classes
+                atomicAdd(P.slot_cnt + en.slot_off + (cm - 1u), 1ull);
+                tally_bases(en, e, ml);
+            } else {
+                tally(en, e, cm, ml);
+            }
+        };
+        if (CLS == 0) {
+            uint2 *wq = s_q + warp * COUNT_QCAP;
+#pragma unroll
+            for (int h = 0; h < COUNT_ITEMS / COUNT_ROUND; ++h) {
+                // pairs of this round: warp scan of the threads' list lengths
+                uint32_t mine = 0;
+#pragma unroll
+                for (int u = 0; u < COUNT_ROUND; ++u) mine += rec[h * COUNT_ROUND + u].x >> PREC_SO_BITS;
+                uint32_t incl = mine;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                    if (lane >= (uint32_t)d) incl += t;
+                }
+                const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                if (total == 0u) continue;  // warp-uniform
+                if (ct.staged && total <= (uint32_t)COUNT_QCAP) {
+                    // queue entry: x = entry relative to the bucket | length << 16, y = start
+                    uint32_t pos = incl - mine;
+#pragma unroll
+                    for (int u = 0; u < COUNT_ROUND; ++u) {
+                        const uint4 rc = rec[h * COUNT_ROUND + u];
+                        const uint32_t rel = (rc.x & PREC_MAX_SO) - ct.e0, nent = rc.x >> PREC_SO_BITS;
+                        const uint32_t hi = rc.w << 16;
+#pragma unroll 1
+                        for (uint32_t q = 0; q < nent; ++q) wq[pos++] = make_uint2((rel + q) | hi, rc.z);
+                    }
+                    __syncwarp();
+#pragma unroll 1
+                    for (uint32_t p = lane; p < total; p += 32u) {
+                        const uint2 d = wq[p];
+                        const int32_t s0 = (int32_t)d.y;
+                        pair_fast(ct.e0 + (d.x & 0xFFFFu), s0, s0 + (int32_t)(d.x >> 16));
+                    }
+                    __syncwarp();  // the queue is rewritten by the next round
+                } else {  // lane-per-read loop (unstaged bucket or an overfull queue)
+#pragma unroll
+                    for (int u = 0; u < COUNT_ROUND; ++u) {
+                        const uint4 rc = rec[h * COUNT_ROUND + u];
+                        const uint32_t so = rc.x & PREC_MAX_SO, nent = rc.x >> PREC_SO_BITS;
+                        const int32_t s0 = (int32_t)rc.z, e0 = s0 + (int32_t)(rc.w & 0xFFFFu);
+#pragma unroll 1
+                        for (uint32_t q = 0; q < nent; ++q) pair_fast(so + q, s0, e0);
+                    }
+                }
+            }
+        } else {
+            // one (read, stab entry) pair
+            auto eval_entry = [&](const ReadView &rv, uint32_t strand, uint32_t total_len, uint32_t e) {
+                const StabEntry en = ent[e];
+                const EvHdr h = T.hdr[en.x];
+                uint32_t ml;
+                const uint64_t c64 =
+                    (CLS == 1 && (en.meta & SE_FAST))
+                        ? eval_pair2(en, h, T.seg + h.seg_off, T.fmask + h.form_off, rv.b0, rv.b1, total_len, ml)
+                        : eval_pair(P, h, T.seg + h.seg_off, T.fmask + h.form_off, rv, strand, total_len, ml);
+                if (c64 == 0ull) return;
+                if (en.K > 2) {
+                    bump_class(P.slot_cnt + h.slot_off, P.slot_mask + h.slot_off, h.slot_cap, (h.flags & EV_HASH) != 0,
+                               c64);
+                    tally_bases(en, e, ml);
+                } else {
+                    tally(en, e, (uint32_t)c64, ml);
+                }
+            };
+            // PAIR: the two blocks of a record, relative to the first position of the piece
+            auto pair_view = [&](const uint4 rc, ReadView &rv, uint32_t &strand, uint32_t &total_len) {
                 rv.b0 = rv.b1 = rv.b2 = make_int2(0, 0);
-                rv.n = 1;
                 rv.ridx = 0;
                 rv.blk = nullptr;
+                unpack_pair(make_uint2(rc.z, rc.w), (int32_t)rc.y, rv.b0, rv.b1, strand);
+                rv.n = 2;
+                total_len = (uint32_t)(rv.b0.y - rv.b0.x) + (uint32_t)(rv.b1.y - rv.b1.x);
+            };
+            auto walk_entry = [&](const uint4 rc, uint32_t e) {  // PAIR read against stab entry e
+                ReadView rv;
+                uint32_t strand, total_len;
+                pair_view(rc, rv, strand, total_len);
+                eval_entry(rv, strand, total_len, e);
+            };
+            // one PAIR / GENERAL read against the stab entries of its piece, lane per read
+            auto walk = [&](const uint4 rc) {
+                uint32_t so = rc.x & PREC_MAX_SO, nent = rc.x >> PREC_SO_BITS;
+                ReadView rv;
                 uint32_t strand = 0, total_len = 0;
                 if (CLS == 1) {
-                    if (act) {  // two blocks, relative to the first position of the piece
-                        const int32_t ppos = __ldg(&T.pinfo[key - key_bias].pos);
-                        unpack_pair(rec, ppos, rv.b0, rv.b1, strand);
-                        rv.n = 2;
-                        total_len = (uint32_t)(rv.b0.y - rv.b0.x) + (uint32_t)(rv.b1.y - rv.b1.x);
-                    }
-                } else if (act) {
+                    pair_view(rc, rv, strand, total_len);
+                } else {
+                    rv.b0 = rv.b1 = rv.b2 = make_int2(0, 0);
+                    so = __ldg(T.stab_off + rc.y);  // the record names the piece
+                    nent = __ldg(T.stab_off + rc.y + 1) - so;
                     // one pass over the ext entry: header and up to three blocks go to registers
-                    const int2 *entry = P.ext + rec.x;  // 16-byte aligned
+                    const int2 *entry = P.ext + rc.z;  // 16-byte aligned
                     const int4 q0 = __ldg(reinterpret_cast<const int4 *>(entry));
                     const int2 hd = make_int2(q0.x, q0.y);
                     rv.b0 = make_int2(q0.z, q0.w);
-                    const uint32_t nn = rec.y;  // kept blocks, also stored in the sorted record
+                    const uint32_t nn = rc.w;  // kept blocks, also stored in the record
                     if (nn > 2) {
                         const int4 q1 = __ldg(reinterpret_cast<const int4 *>(entry + 2));
                         rv.b1 = make_int2(q1.x, q1.y);
@@ -319,59 +595,71 @@ __global__ void __launch_bounds__(COUNT_BLOCK, CLS ? 3 : 5) lsq_count_kernel(Cou
                         total_len += (uint32_t)(blk.y - blk.x);
                     }
                 }
-                for (uint32_t q = 0; q < max_ent; ++q) {
-                    const bool has = q < nent;
-                    uint32_t cm = 0, ml = 0, slot_off = 0, x = 0;
-                    if (has) {
-                        const StabEntry en = ent[so + q];
-                        slot_off = en.slot_off;
-                        x = en.x;
-                        const EvHdr h = T.hdr[x];
-                        const uint64_t c64 =
-                            (CLS == 1 && (en.meta & SE_FAST))
-                                ? eval_pair2(en, h, T.seg + h.seg_off, T.fmask + h.form_off, rv.b0, rv.b1, total_len, ml)
-                                : eval_pair(P, h, T.seg + h.seg_off, T.fmask + h.form_off, rv, strand, total_len, ml);
-                        cm = (uint32_t)c64;
-                        if (c64 != 0 && en.K > 2) {
-                            bump_class(P.slot_cnt + h.slot_off, P.slot_mask + h.slot_off, h.slot_cap,
-                                       (h.flags & EV_HASH) != 0, c64);
-                            cm = 0x80000000u;
-                        }
+#pragma unroll 1
+                for (uint32_t q = 0; q < nent; ++q) eval_entry(rv, strand, total_len, so + q);
+            };
+            if (CLS == 1 && ct.staged) {
+                // PAIR reads meet about two entries each and their evaluation is long, so the same
+                // expansion pays: per round every lane parks one read in the warp's shared slots and
+                // queues its (entry, slot) pairs; the pairs are then evaluated densely, one per lane.
+                uint4 *wr = s_pr[warp];
+                uint32_t *wq = s_pq[warp];
+                uint4 rec_c = rec[0];
+#pragma unroll 1
+                for (uint32_t i0 = tid & ~31u; i0 < ct.n; i0 += COUNT_BLOCK) {  // warp-uniform
+                    const uint32_t i = i0 + lane;
+                    const uint4 rc = i < ct.n ? rec_c : make_uint4(0u, 0u, 0u, 0u);
+                    if (i + COUNT_BLOCK < ct.n) rec_c = __ldcs(pool + i + COUNT_BLOCK);
+                    const uint32_t mine = rc.x >> PREC_SO_BITS;
+                    uint32_t incl = mine;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                        if (lane >= (uint32_t)d) incl += t;
                     }
-                    aggregate_runs(P, lane, head && has, run_mask, run_end, single_run, cm, ml, slot_off, x,
-                                   ctr ? ctr[so + q] : nullptr);
+                    const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                    if (total == 0u) continue;
+                    if (total <= (uint32_t)PAIR_QCAP) {
+                        wr[lane] = rc;
+                        const uint32_t rel = (rc.x & PREC_MAX_SO) - ct.e0;
+                        uint32_t pos = incl - mine;
+#pragma unroll 1
+                        for (uint32_t q = 0; q < mine; ++q) wq[pos++] = (rel + q) | (lane << 16);
+                        __syncwarp();
+#pragma unroll 1
+                        for (uint32_t p = lane; p < total; p += 32u) {
+                            const uint32_t d = wq[p];
+                            walk_entry(wr[d >> 16], ct.e0 + (d & 0xFFFFu));
+                        }
+                        __syncwarp();  // slots and queue are rewritten by the next round
+                    } else {
+                        walk(rc);
+                    }
+                }
+            } else {
+                uint4 rec_c = rec[0];
+#pragma unroll 1
+                for (uint32_t i = tid; i < ct.n; i += COUNT_BLOCK) {
+                    const uint4 rc = rec_c;
+                    if (i + COUNT_BLOCK < ct.n) rec_c = __ldcs(pool + i + COUNT_BLOCK);
+                    walk(rc);
                 }
             }
         }
-        __syncwarp();
-        // the last warp of the block to finish this chunk flushes the stage's shared counters to
-        // global memory; the stage is released (empty barrier) only after the flush, so the
-        // counters and the staged entries they refer to cannot be overwritten before
-        uint32_t last = 0;
-        if (lane == 0) {
-            __threadfence_block();
-            last = atomicAdd(&s_done[stage], 1u) == (uint32_t)(COUNT_WARPS - 1);
-        }
-        last = __shfl_sync(0xFFFFFFFFu, last, 0);
-        if (last) {
-            __threadfence_block();
-            if (ct.staged) {
-                const uint32_t nctr = (ct.e1 - ct.e0) * 4u;
-                uint32_t *flat = &s_ctr[stage][0][0];
-                for (uint32_t i = lane; i < nctr; i += 32u) {
-                    const uint32_t v = flat[i];
-                    if (!v) continue;
-                    flat[i] = 0u;
-                    const StabEntry &en = s_ent[stage][i >> 2];
-                    if ((i & 3u) == 3u) atomicAdd(P.bases + en.x, (unsigned long long)v);
-                    else atomicAdd(P.slot_cnt + en.slot_off + (i & 3u), (unsigned long long)v);
-                }
+        __syncthreads();
+        if (ct.staged) {  // flush the block-local counters of this item
+            const uint32_t nctr = (ct.e1 - ct.e0) * 4u;
+            uint32_t *flat = &s_ctr[0][0];
+            for (uint32_t i = tid; i < nctr; i += COUNT_BLOCK) {
+                const uint32_t v = flat[i];
+                if (!v) continue;
+                flat[i] = 0u;
+                const StabEntry &en = s_ent[i >> 2];
+                if ((i & 3u) == 3u) atomicAdd(P.bases + en.x, (unsigned long long)v);
+                else atomicAdd(P.slot_cnt + en.slot_off + (i & 3u), (unsigned long long)v);
             }
-            __syncwarp();
-            if (lane == 0) s_done[stage] = 0u;
-            __syncwarp();
         }
-        if (lane == 0) mbar_arrive(&s_empty[stage]);  // this warp no longer reads the stage
+        __syncthreads();  // the staged entries may be overwritten by the next item
     }
     if (CLS == 2) {
         const uint32_t sl = __reduce_add_sync(0xFFFFFFFFu, my_slots);

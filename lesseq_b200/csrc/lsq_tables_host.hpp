@@ -30,6 +30,8 @@ struct HostTables {
     uint32_t bp_shift = 0;
     std::vector<uint32_t> bp_bkt_off, bp_bkt;
     std::vector<uint4> chrom_meta;
+    uint32_t bkt_shift = 9, n_bkt = 1, max_stab_n = 0;
+    std::vector<uint32_t> bkt_piece;  // [n_bkt+1] first piece whose stab_off is >= b << bkt_shift
 
     // Table view over the HOST arrays (CPU replay harness only).
     Tables host_view() const {
@@ -56,6 +58,9 @@ struct HostTables {
         T.cov_off = cov_off.data();
         T.cov_start = cov_start.data();
         T.cov_end = cov_end.data();
+        T.bkt_shift = bkt_shift;
+        T.n_bkt = n_bkt;
+        T.bkt_piece = bkt_piece.data();
         return T;
     }
 };
@@ -63,14 +68,15 @@ struct HostTables {
 // Bucket index over per-chromosome sorted coordinate arrays (CSR `off`): bucket b of a
 // chromosome covers positions [b << shift, (b+1) << shift) and stores the rank (global index)
 // of the first element >= b << shift; one extra bucket per chromosome closes the last range.
-// The shift is chosen so that there are about four buckets per element (at most 2^25).
+// The shift is chosen so that there are about sixteen buckets per element (at most 2^25): pieces
+// cluster inside genes, and a bucket should rarely hold more than two piece starts.
 inline void build_bucket_index(const std::vector<int32_t> &arr, const std::vector<uint32_t> &off, uint32_t &shift,
                                std::vector<uint32_t> &bkt_off, std::vector<uint32_t> &bkt) {
     const size_t nch = off.size() - 1;
     uint64_t span = 0;
     for (size_t c = 0; c < nch; ++c)
         if (off[c + 1] > off[c]) span += (uint64_t)std::max<int32_t>(arr[off[c + 1] - 1], 0) + 1;
-    uint64_t want = std::min<uint64_t>(std::max<uint64_t>(4 * arr.size(), 1), 1ull << 25);
+    uint64_t want = std::min<uint64_t>(std::max<uint64_t>(16 * arr.size(), 1), 1ull << 25);
     shift = 0;
     while ((span >> shift) > want && shift < 30) ++shift;
     bkt_off.assign(nch + 1, 0);
@@ -355,7 +361,7 @@ inline int build_host_tables(const lsq_event_tables *t, HostTables &H, std::stri
     for (uint32_t ch = 0; ch < t->n_chroms; ++ch)
         H.chrom_meta[ch] = make_uint4(H.bp_chrom_off[ch], H.bp_chrom_off[ch + 1], H.bp_bkt_off[ch],
                                       H.bp_bkt_off[ch + 1] - H.bp_bkt_off[ch] - 1u);
-    H.pinfo.resize(H.bp_pos.size());
+    H.pinfo.assign(H.bp_pos.size() + 1, PieceInfo());  // one sentinel: clamped candidate loads stay in bounds
     for (uint32_t ch = 0; ch < t->n_chroms; ++ch) {
         const int32_t *cs = H.cov_start.data() + H.cov_off[ch], *ce = H.cov_end.data() + H.cov_off[ch];
         const size_t nc = H.cov_off[ch + 1] - H.cov_off[ch];
@@ -370,6 +376,22 @@ inline int build_host_tables(const lsq_event_tables *t, HostTables &H, std::stri
             size_t i = std::upper_bound(cs, cs + nc, pi.pos) - cs;
             pi.cov_end = (i > 0 && ce[i - 1] > pi.pos) ? ce[i - 1] : INT32_MIN;
         }
+    }
+    // stab buckets: windows of 2^bkt_shift stab entries, at most PART_MAX_BINS / 3 of them
+    {
+        const uint32_t n_stab = (uint32_t)H.stab.size(), n_pieces = (uint32_t)H.bp_pos.size();
+        H.bkt_shift = 9;
+        while (3ull * ((uint64_t)(n_stab >> H.bkt_shift) + 1ull) > (uint64_t)PART_MAX_BINS) ++H.bkt_shift;
+        H.n_bkt = (n_stab >> H.bkt_shift) + 1u;
+        H.bkt_piece.assign(H.n_bkt + 1, n_pieces);
+        uint32_t p = 0;
+        for (uint32_t b = 0; b <= H.n_bkt; ++b) {
+            const uint64_t lim = (uint64_t)b << H.bkt_shift;
+            while (p < n_pieces && (uint64_t)H.stab_off[p] < lim) ++p;
+            H.bkt_piece[b] = p;
+        }
+        H.max_stab_n = 0;
+        for (uint32_t q = 0; q < n_pieces; ++q) H.max_stab_n = std::max(H.max_stab_n, H.stab_off[q + 1] - H.stab_off[q]);
     }
     H.slot_total = slot_total;
     H.E = E;

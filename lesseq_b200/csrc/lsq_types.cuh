@@ -64,13 +64,48 @@ struct __align__(16) PieceInfo {
 constexpr uint32_t PIECE_ALL_FAST = 0x80000000u;
 static_assert(sizeof(PieceInfo) == 16, "PieceInfo layout");
 
-// Sorted read record (8 bytes), value type of the radix sort.  Keys: piece p for FAST-class reads
-// (one kept block, shorter than 64 Ki, not starting on the first position of its piece),
-// n_pieces + p for GENERAL-class reads, 2 * n_pieces for reads that are no candidates.
-//   fast   : x = start of the block, y = length (bits 0-15) | file strand id (bits 16-23)
-//   general: x = offset of the read's entry in ext[]:
-//            ext[x] = {original read index, (strand << 24) | n}, ext[x+1 .. x+n] = kept blocks
+// Read record (8 bytes).  The load filter drops every read that is a candidate of no event and appends the others to the
+// bin (read class, stab bucket) they belong to -- see PartState.  Read classes:
+//   FAST    one kept block, shorter than 64 Ki, not starting on the first position of its piece,
+//           every stab entry of the piece table-driven:
+//           x = start of the block, y = length (bits 0-15) | file strand id (bits 16-23)
+//   PAIR    two kept blocks that fit the record (pack_pair)
+//   GENERAL everything else: x = offset of the read's entry in ext[]:
+//           ext[x] = {original read index, (strand << 24) | n}, ext[x+1 .. x+n] = kept blocks
 typedef uint2 ReadRec;
+
+// Partition of the kept reads by (class, stab bucket).  A stab bucket is a run of consecutive
+// pieces whose stab entries fall into one window of 2^bkt_shift entries, so the tables a bucket
+// needs (its stab entries, their offsets and four counters per entry) fit in shared memory.
+// Bins grow in chunks of PART_CHUNK records taken from one pool: state[bin] packs the bin's
+// current chunk and its fill, so one 64-bit atomicAdd reserves room for a whole tile's records;
+// the reservation that takes the last slot of a chunk installs the bin's spare chunk (and then
+// allocates a new spare, off the critical path).  Each installed chunk is one work item of the
+// count kernel of its class (wl lists chunk ids per class).
+constexpr uint32_t PART_CHUNK_LOG2 = 11;
+constexpr uint32_t PART_CHUNK = 1u << PART_CHUNK_LOG2;
+constexpr uint32_t PART_MAX_BINS = 12288;  // shared-memory budget of the filter kernel (10 bytes per bin)
+constexpr uint32_t BIN_NONE = 0xFFFFu;     // read dropped
+
+struct PartState {
+    uint32_t n_bins;              // 3 * n_bkt: bin = class * n_bkt + (stab_off >> bkt_shift)
+    uint32_t pool_cap;            // chunks in the pool
+    unsigned long long *state;    // [n_bins] (current chunk << 32) | fill
+    uint32_t *next_chunk;         // [n_bins] spare chunk, installed when the current one is full
+    uint32_t *pool_next;          // chunks allocated so far
+    uint32_t *owner;              // [pool_cap] bin of chunk j
+    uint32_t *wl;                 // [3 * pool_cap] chunk ids per class
+    uint32_t *wl_n;               // [3] list lengths
+    uint4 *pool;                  // [pool_cap * PART_CHUNK] PartRec
+};
+
+// Partitioned record, 16 bytes (half a sector; one 128-bit access):
+//   x  first stab entry of the read's piece (bits 0-25) | number of entries (bits 26-31);
+//      FAST and PAIR reads whose piece does not fit are demoted to GENERAL
+//   y  PAIR: first position of the piece; GENERAL: the piece (its stab list is looked up)
+//   z, w  the ReadRec
+constexpr uint32_t PREC_SO_BITS = 26;
+constexpr uint32_t PREC_MAX_SO = (1u << PREC_SO_BITS) - 1u, PREC_MAX_N = 63u;
 
 struct Tables {
     uint32_t E, F, n_pieces, n_chroms, n_ann_strands;
@@ -92,6 +127,9 @@ struct Tables {
     const uint4 *chrom_meta;       // [n_chroms] {first piece, end piece, first bucket, buckets - 1}
     const uint32_t *bp_bkt_off;    // [n_chroms+1] first bucket of each chromosome
     const uint32_t *bp_bkt;        // [buckets + n_chroms] rank of the first piece starting in or after the bucket
+    // stab buckets (PartState): bucket of piece p = stab_off[p] >> bkt_shift
+    uint32_t bkt_shift, n_bkt;
+    const uint32_t *bkt_piece;     // [n_bkt+1] first piece whose stab_off is >= b << bkt_shift
 };
 
 struct FilterParams {
@@ -102,17 +140,14 @@ struct FilterParams {
     const uint32_t *read_cs;
     const uint32_t *blk_cs;       // may be null
     const uint32_t *chrom_remap;  // file chromosome id -> annotation id or 0xFFFFFFFF
-    int2 *ext;                    // [n_blocks + n_reads] worst case (header + blocks per general read)
-    uint32_t *rkey;               // [n_reads] stab piece or n_pieces (= dropped)
-    ReadRec *rec;                 // [n_reads]
-    unsigned long long *counters; // per read set: [0] kept reads, [1] ext slots read, [3] GENERAL reads
+    int2 *ext;                    // [n_blocks + 2 n_reads] worst case (header + blocks per general read)
+    PartState part;
+    unsigned long long *counters; // per read set: [0] FAST reads, [1] ext slots read, [2] PAIR reads, [3] GENERAL reads
 };
 
 struct CountParams {
     Tables T;
-    const unsigned long long *counters;
-    const uint32_t *g_key;
-    const ReadRec *g_rec;
+    PartState part;
     const int2 *ext;
     const uint32_t *line_num;
     const uint8_t *strand_tbl;   // [file strands x annotation strands] bit0: read < event, bit1: equal

@@ -141,19 +141,16 @@ int main(int argc, char **argv) {
         FP.blk_cs = R.any_mixed ? R.blk_cs.data() : nullptr;
         FP.chrom_remap = remap.data();
         FP.ext = ext2.data();
-        FP.rkey = rkey.data();
-        FP.rec = rec.data();
         FP.counters = counters;
         for (size_t r = 0; r < n; ++r) {  // lsq_filter_kernel, one "thread" at a time
-            FilteredRead fr = filter_read(FP, r);
+            FilteredRead fr = filter_dispatch(FP, r);  // staged single-block path or filter_read, as the kernel
             ReadRec q;
             if (fr.key != KEY_DROPPED(T) && fr.key >= T.n_pieces && fr.key < 2u * T.n_pieces) {
                 q = pack_pair(fr.first, fr.second, fr.piece_pos, fr.strand);
             } else if (fr.key != KEY_DROPPED(T) && fr.key >= 2u * T.n_pieces) {
                 uint32_t off = ext_slot(R.blk_off[r], (uint32_t)r);
                 counters[1] += fr.n + 1;
-                ext2[off] = make_int2((int32_t)r, (int32_t)((fr.strand << 24) | (fr.n & 0xFFFFFFu)));
-                ext2[off + 1] = fr.first;  // blocks 1..n-1 were left in place by filter_read
+                write_ext_entry(ext2.data(), off, (uint32_t)r, fr);  // blocks 2.. were spilled by the filter
                 q.x = off;
                 q.y = 0;
             } else {

@@ -322,6 +322,46 @@ def test_wide_and_many_form_events_match_oracle(api, oracle_bin, tmp_path):
         assert bad is None, "%s: %s" % (prog, bad)
 
 
+@pytest.mark.parametrize("depth", [70, 700])
+def test_deeply_nested_events_match_oracle(api, oracle_bin, tmp_path, depth):
+    """`depth` events stacked on the same exons: stab lists longer than a partitioned record can
+    name (>= 64: FAST and PAIR reads are demoted to the GENERAL class) and, at 700, longer than the
+    count kernel stages in shared memory (the bucket is read through L1/L2 instead)."""
+    import random
+    rng = random.Random(depth)
+    exons = [(1000, 1080), (1300, 1390), (1390, 1450), (1700, 1800), (2100, 2160)]
+    fl, ml, forms = [], [], []
+
+    def add(ev, name, ex):
+        fl.append("%s\tchr1\t+\t%d\t%d\t%d\t%s\t%s\n" % (name, ex[0][0], ex[-1][1], len(ex),
+                                                     ",".join(str(s) for s, _ in ex), ",".join(str(e) for _, e in ex)))
+        ml.append("%s\t%s\n" % (ev, name))
+        forms.append(ex)
+
+    for d in range(depth):
+        lo = rng.randrange(0, 2)
+        hi = rng.randrange(4, 6)
+        ex = exons[lo:hi]
+        add("N%d" % d, "N%d|1" % d, ex)
+        add("N%d" % d, "N%d|2" % d, [x for i, x in enumerate(ex) if i != 1 + rng.randrange(len(ex) - 2)])
+    add("SIDE", "S|1", [(5000, 5100), (5300, 5400)])
+    add("SIDE", "S|2", [(5000, 5100), (5200, 5250), (5300, 5400)])
+    fp, mp, rp = tmp_path / "ev.interval", tmp_path / "ev.map", tmp_path / "r.mrf"
+    fp.write_text("".join(fl))
+    mp.write_text("".join(ml))
+    lines = _walk_reads(rng, forms, 60, 6000 if depth < 100 else 3000)
+    rp.write_text("AlignmentBlocks\n" + "\n".join(lines) + "\n")
+    args = ["0", "p", str(tmp_path / "o_"), "LH_GENE_TXT", str(fp), "UCSC_GENE2ISOFORM", str(mp), "0", "100000",
+            "MRF_SINGLE", "SHORT_READ", "60", str(rp)]
+    for prog, a in (("count", args), ("solve", args + ["360000"])):
+        rc1, o1, e1 = oracle_bin.run_oracle(prog, a)
+        rc2, o2, e2 = api.run_program(prog, a, precision=17)
+        assert rc1 == 0 and rc2 == 0, e2
+        assert sum(float(r.split("\t")[1]) for r in o1.splitlines()) > 10000
+        bad = tables_match(o1, o2, prog == "solve")
+        assert bad is None, "%s: %s" % (prog, bad)
+
+
 def _numpy_em(K, G, classes, n_total):
     """EM of common/read.h:592-660 over (mask, count) classes, sequential double arithmetic."""
     theta = np.full(K, 1.0 / K)
