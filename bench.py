@@ -5,7 +5,7 @@
                     [--workload C2|C1|C4] [--reads R] [--genes G]
 
 A "step" is one full pass of the device pipeline over one batch of synthetic packed reads:
-load filter -> index (radix sort by stab piece) -> count -> finalize -> EM solve.
+load filter + partition by (read class, stab bucket) -> count -> finalize -> EM solve.
   value : reads/s of that pass, inputs already resident in HBM, CUDA-event timed, max over ranks
   e2e   : the same through the C ABI with HOST (pinned) buffers: lsq_set_reads (H2D) + lsq_count +
           lsq_solve + lsq_get_count/lsq_get_solve (D2H) inside the timed region
@@ -337,12 +337,13 @@ def run_ours(args):
             # every kernel of the step against the same measured HBM peak (algorithmic bytes / CUDA-event time)
             "kernels": [
                 {"name": "lsq_filter_kernel", "ms": phases["filter_ms"] / args.steps,
-                 "bytes": int(dev_reads.host_bytes() + 12 * n),
-                 "note": "reads the packed read set once, writes a 4-byte key + 8-byte record per read"},
-                {"name": "cub::DeviceRadixSort (3 onesweep passes + histogram) + lsq_class_bounds_kernel",
-                 "ms": phases["index_ms"] / args.steps, "bytes": int(n * (12 * 2 * 3 + 4)),
-                 "note": "library sort: plumbing, not a hand-written kernel"},
-                {"name": "lsq_count_kernel<0,1,2>", "ms": ck_ms, "bytes": int(tsum["count_bytes"])},
+                 "bytes": int(dev_reads.host_bytes() + 16 * tsum["reads_kept"]),
+                 "note": "reads the packed read set once, appends one 16-byte record per kept read to its "
+                         "(read class, stab bucket) bin"},
+                {"name": "counter memsets + lsq_part_init_kernel", "ms": phases["index_ms"] / args.steps, "bytes": 0,
+                 "note": "resets the class counters and the partition state (no sort in the pipeline)"},
+                {"name": "lsq_count_kernel<0,1,2>", "ms": ck_ms, "bytes": int(tsum["count_bytes"]),
+                 "note": "16 bytes per kept read + the ext entries of GENERAL-class reads"},
                 {"name": "lsq_solve_small_kernel<1>", "ms": phases["solve_ms"] / args.steps,
                  "bytes": int(n_events_total // world * 120), "note": "FP64 latency bound (log/div chains), not HBM"},
             ],

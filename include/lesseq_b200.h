@@ -143,10 +143,12 @@ typedef struct lsq_solve_out {
                             NaN when undefined (no reads, singular information, more than 16 forms). */
 } lsq_solve_out;
 
-/* Device timings of the last lsq_count / lsq_solve call (CUDA events on the context's stream). */
+/* Device timings of the last lsq_count / lsq_solve call (CUDA events on the context's stream).
+ * filter_ms: the load filter + partition kernel; index_ms: counter resets and partition set-up
+ * (the read index of count.cpp:346-364 is the partition itself: there is no sort). */
 typedef struct lsq_timings {
     float filter_ms, index_ms, reserved_ms, count_ms, finalize_ms, solve_ms;
-    float count_kernel_ms; /* the two count kernel instantiations (summed over read sets) */
+    float count_kernel_ms; /* the three count kernel instantiations (summed over read sets) */
     uint32_t launches;     /* kernels launched by the last lsq_count + lsq_solve */
     uint32_t count_launches;
     uint64_t reads_in, reads_kept, pairs_valid; /* summed over read sets */
@@ -170,8 +172,8 @@ int lsq_upload_events(lsq_ctx *ctx, const lsq_event_tables *tables);
 int lsq_set_reads(lsq_ctx *ctx, uint32_t m, uint32_t read_type, uint64_t read_length,
                   const lsq_packed_reads *reads);
 
-/* Filter + index + candidate scan + compatibility + histogram for every declared read set
- * (count.cpp:319-324, 346-364, 421-482).  Results stay on the device. */
+/* Load filter + read index (partition by stab bucket) + candidate scan + compatibility + histogram
+ * for every declared read set (count.cpp:319-324, 346-364, 421-482).  Results stay on the device. */
 int lsq_count(lsq_ctx *ctx);
 int lsq_get_count(lsq_ctx *ctx, lsq_count_out *out);
 

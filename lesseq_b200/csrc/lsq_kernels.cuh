@@ -26,12 +26,14 @@ constexpr int FILT_ITEMS = 4;                         // reads per thread (all k
 constexpr int FILT_LBATCH = 3;                        // block lookups kept in flight per thread
 constexpr int FILT_RBATCH = 3;                        // bin reservations kept in flight per thread
 constexpr int FILT_TILE = FILT_BLOCK * FILT_ITEMS;    // 2048 reads
-constexpr int FILT_MAX_BLK = 4096;                    // raw blocks of a tile whose lookups are staged
+constexpr int FILT_WREADS = 32 * FILT_ITEMS;          // 128 reads per warp
+constexpr int FILT_WBLK = 320;                        // raw blocks of a warp's reads whose lookups are staged
+constexpr int FILT_MAX_BLK = FILT_WBLK * (FILT_BLOCK / 32);
 static_assert((uint32_t)FILT_TILE <= PART_CHUNK, "a tile's reservation may span at most two chunks");
 
 // dynamic shared memory of the filter kernel
 __host__ __device__ inline size_t filter_smem_bytes(uint32_t n_bins) {
-    return (size_t)FILT_TILE * (16 + 4 + 2) + (size_t)FILT_MAX_BLK * 4 + (size_t)n_bins * (4 + 4 + 2) + 64;
+    return (size_t)FILT_TILE * (16 + 4 + 2) + (size_t)FILT_MAX_BLK * 4 + (size_t)n_bins * (4 + 4 + 2) + 64;  // <= 200 KB at PART_MAX_BINS
 }
 
 // Read context of the filter kernel (see filter_read_t): blocks and piece records are fetched on
@@ -64,19 +66,22 @@ __global__ void lsq_part_init_kernel(PartState S, uint32_t n_bkt) {
     if (b == 0u) *S.pool_next = 2u * S.n_bins;
 }
 
-// Phase A: every thread expands the chromosome/strand ids of its reads over their raw blocks.
-// Phase B: the tile's raw blocks (contiguous in blk[]) are spread over the threads regardless of
-//          the reads they belong to, and every thread runs the staged piece lookup
+// Phases A-C run per WARP on its own 128 reads of the tile, with warp-level synchronisation only,
+// so the sixteen warps of a block drift apart and cover each other's memory latencies:
+// Phase A: every lane expands the chromosome/strand ids of its reads over their raw blocks.
+// Phase B: the warp's raw blocks (contiguous in blk[]) are spread over the lanes regardless of
+//          the reads they belong to, and every lane runs the staged piece lookup
 //          (lsq_device_fn.cuh) on FILT_LBATCH blocks at a time, so the loads of each stage
 //          (block, bucket slot, candidate pieces) are in flight together and no lane idles
 //          because its read has fewer blocks than its neighbour's.  Answers go to shared memory.
 // Phase C: single-block reads (4 in 5) are decided by single_decide with block and piece record
-//          fetched for all of the thread's reads at once; the others go to a block-local list
-//          that is spread densely over the threads and takes filter_read_t (interval list, read
+//          fetched for all of the lane's reads at once; the others go to a warp-local list
+//          that is spread densely over the lanes and takes filter_read_t (interval list, read
 //          class).  Records of the kept reads are staged in shared memory.
+// Then, block-wide:
 // Phase D: one thread per non-empty bin reserves room for the tile's records of that bin with a
 //          single 64-bit atomicAdd on (chunk, fill); the reservation that takes the last slot of
-//          a chunk allocates the next chunk and publishes it.
+//          a chunk installs the bin's spare chunk.
 // Phase E: records go from shared memory to their slots (writes of one bin are contiguous; L2
 //          merges them into full sectors before they reach HBM).
 __global__ void __launch_bounds__(FILT_BLOCK, 2) lsq_filter_kernel(FilterParams P) {
@@ -86,65 +91,69 @@ __global__ void __launch_bounds__(FILT_BLOCK, 2) lsq_filter_kernel(FilterParams 
     const uint32_t n_bins = S.n_bins;
     uint4 *s_rec = reinterpret_cast<uint4 *>(s_raw);  // PartRec of the tile's reads
     uint32_t *s_br = reinterpret_cast<uint32_t *>(s_rec + FILT_TILE);  // bin | rank << 16
-    uint32_t *s_blk = s_br + FILT_TILE;              // per raw block: chromosome/strand ids, then the lookup answer
-    uint32_t *s_A = s_blk + FILT_MAX_BLK;            // per bin: records of the tile, then first slot
+    uint32_t *s_blk_all = s_br + FILT_TILE;          // per warp and raw block: chromosome/strand ids, then the lookup answer
+    uint32_t *s_A = s_blk_all + FILT_MAX_BLK;        // per bin: records of the tile, then first slot
     uint32_t *s_B = s_A + n_bins;                    // per bin: slot base after a chunk switch
-    uint32_t *s_n = s_B + n_bins;                    // [0] listed reads
-    uint16_t *s_multi = reinterpret_cast<uint16_t *>(s_n + 4);  // reads for filter_read_t (tile-local index)
-    uint16_t *s_split = s_multi + FILT_TILE;         // per bin: records before the chunk switch
-    const uint32_t tid = threadIdx.x;
+    uint16_t *s_multi_all = reinterpret_cast<uint16_t *>(s_B + n_bins);  // per warp: reads for filter_read_t (tile-local index)
+    uint16_t *s_split = s_multi_all + FILT_TILE;     // per bin: records before the chunk switch
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     for (uint32_t i = tid; i < n_bins; i += FILT_BLOCK) s_A[i] = 0u;
-    if (tid == 0) s_n[0] = 0u;
+    __syncthreads();
     const uint64_t tile0 = (uint64_t)blockIdx.x * FILT_TILE;
     const uint64_t tile1 = min(tile0 + (uint64_t)FILT_TILE, P.n_reads);
     const uint32_t n_bkt = T.n_bkt;
-    const uint32_t tbase = __ldg(P.blk_off + tile0);
-    const uint32_t tile_nblk = __ldg(P.blk_off + tile1) - tbase;
-    const bool staged = tile_nblk <= (uint32_t)FILT_MAX_BLK;  // block-uniform
+    // the warp's reads: [w0, w1), lane l owns w0 + l + 32 k
+    const uint64_t w0 = min(tile0 + (uint64_t)warp * FILT_WREADS, tile1), w1 = min(w0 + (uint64_t)FILT_WREADS, tile1);
+    uint32_t *s_blk = s_blk_all + warp * FILT_WBLK;
+    uint16_t *s_multi = s_multi_all + warp * FILT_WREADS;
 
     // ---- phase A --------------------------------------------------------------------------
     uint32_t rbase[FILT_ITEMS], rn[FILT_ITEMS], rcs[FILT_ITEMS];  // absolute block offset, raw blocks, ids
 #pragma unroll
     for (int k = 0; k < FILT_ITEMS; ++k) {
-        const uint64_t r = tile0 + tid + (uint32_t)k * FILT_BLOCK;
+        const uint64_t r = w0 + lane + (uint32_t)k * 32u;
         rbase[k] = 0u;
         rn[k] = 0u;
         rcs[k] = 0u;
-        if (r < tile1) {
+        if (r < w1) {
             rbase[k] = __ldcs(P.blk_off + r);
             rn[k] = __ldcs(P.blk_off + r + 1) - rbase[k];
             rcs[k] = __ldcs(P.read_cs + r);
         }
     }
+    const uint32_t wbase = __shfl_sync(0xFFFFFFFFu, rbase[0], 0);
+    const uint32_t w_nblk = w1 > w0 ? __ldg(P.blk_off + w1) - wbase : 0u;
+    const bool staged = w_nblk <= (uint32_t)FILT_WBLK;  // warp-uniform
     if (staged) {
 #pragma unroll
         for (int k = 0; k < FILT_ITEMS; ++k) {
-            const uint32_t rel = rbase[k] - tbase;
+            const uint32_t rel = rbase[k] - wbase;
             if (rcs[k] & 0x80000000u) {
                 for (uint32_t j = 0; j < rn[k]; ++j) s_blk[rel + j] = __ldg(P.blk_cs + rbase[k] + j);
             } else {
                 if (rn[k] >= 1u) s_blk[rel] = rcs[k];
-                for (uint32_t j = 1; j < rn[k]; ++j) s_blk[rel + j] = rcs[k];
+                if (rn[k] >= 2u) s_blk[rel + 1] = rcs[k];
+                for (uint32_t j = 2; j < rn[k]; ++j) s_blk[rel + j] = rcs[k];
             }
         }
     }
-    __syncthreads();
+    __syncwarp();
     // ---- phase B --------------------------------------------------------------------------
     if (staged) {
 #pragma unroll 1
-        for (uint32_t k0 = tid; k0 < tile_nblk; k0 += FILT_BLOCK * FILT_LBATCH) {
+        for (uint32_t k0 = lane; k0 < w_nblk; k0 += 32u * FILT_LBATCH) {
             int st[FILT_LBATCH];
             BlockProbe q[FILT_LBATCH];
             int2 b[FILT_LBATCH];
 #pragma unroll
             for (int u = 0; u < FILT_LBATCH; ++u) {
-                const uint32_t k = k0 + (uint32_t)u * FILT_BLOCK;
-                st[u] = k < tile_nblk ? SP_GO : -1;
-                b[u] = st[u] == SP_GO ? __ldcs(P.blk + tbase + k) : make_int2(0, 0);
+                const uint32_t k = k0 + (uint32_t)u * 32u;
+                st[u] = k < w_nblk ? SP_GO : -1;
+                b[u] = st[u] == SP_GO ? __ldcs(P.blk + wbase + k) : make_int2(0, 0);
             }
 #pragma unroll
             for (int u = 0; u < FILT_LBATCH; ++u) {
-                const uint32_t k = k0 + (uint32_t)u * FILT_BLOCK;
+                const uint32_t k = k0 + (uint32_t)u * 32u;
                 if (st[u] == SP_GO) st[u] = block_stage_chrom(P, b[u], s_blk[k], q[u]);
             }
             uint32_t bi[FILT_LBATCH], bj[FILT_LBATCH];
@@ -170,7 +179,7 @@ __global__ void __launch_bounds__(FILT_BLOCK, 2) lsq_filter_kernel(FilterParams 
             }
 #pragma unroll
             for (int u = 0; u < FILT_LBATCH; ++u) {
-                const uint32_t k = k0 + (uint32_t)u * FILT_BLOCK;
+                const uint32_t k = k0 + (uint32_t)u * 32u;
                 if (st[u] < 0) continue;
                 uint32_t res = PIECE_NONE;
                 if (st[u] == SP_GO) st[u] = block_stage_select(q[u], bi[u], bj[u], r0[u], r1[u], r2[u], res);
@@ -179,7 +188,7 @@ __global__ void __launch_bounds__(FILT_BLOCK, 2) lsq_filter_kernel(FilterParams 
             }
         }
     }
-    __syncthreads();
+    __syncwarp();
     // ---- phase C --------------------------------------------------------------------------
     // record of a kept read -> shared staging (and the ext entry of a GENERAL read)
     auto emit = [&](uint32_t li, uint64_t r, uint32_t base, const FilteredRead &fr) {
@@ -219,6 +228,7 @@ __global__ void __launch_bounds__(FILT_BLOCK, 2) lsq_filter_kernel(FilterParams 
         }
         s_br[li] = br;
     };
+    uint32_t n_listed = 0;  // warp-uniform
     {
         int2 b0[FILT_ITEMS];
         uint32_t res[FILT_ITEMS];
@@ -228,7 +238,7 @@ __global__ void __launch_bounds__(FILT_BLOCK, 2) lsq_filter_kernel(FilterParams 
         for (int k = 0; k < FILT_ITEMS; ++k) {
             single[k] = staged && rn[k] == 1u && !(rcs[k] & 0x80000000u);
             b0[k] = single[k] ? __ldg(P.blk + rbase[k]) : make_int2(0, 0);
-            res[k] = single[k] ? s_blk[rbase[k] - tbase] : PIECE_NONE;
+            res[k] = single[k] ? s_blk[rbase[k] - wbase] : PIECE_NONE;
         }
 #pragma unroll
         for (int k = 0; k < FILT_ITEMS; ++k)
@@ -236,32 +246,32 @@ __global__ void __launch_bounds__(FILT_BLOCK, 2) lsq_filter_kernel(FilterParams 
                                          : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
         for (int k = 0; k < FILT_ITEMS; ++k) {
-            const uint32_t li = tid + (uint32_t)k * FILT_BLOCK;
+            const uint32_t li = warp * FILT_WREADS + lane + (uint32_t)k * 32u;  // tile-local index
             const uint64_t r = tile0 + li;
+            const bool listed = !single[k] && r < w1 && rn[k] != 0u;
+            const unsigned lm = __ballot_sync(0xFFFFFFFFu, listed);
             if (single[k]) {
                 emit(li, r, rbase[k], single_decide(T, b0[k], rcs[k], res[k], pi0[k]));
-            } else if (r < tile1 && rn[k] != 0u) {
-                s_multi[atomicAdd(&s_n[0], 1u)] = (uint16_t)li;
+            } else if (listed) {
+                s_multi[n_listed + __popc(lm & ((1u << lane) - 1u))] = (uint16_t)li;
                 s_rec[li] = make_uint4(rbase[k], rn[k], rcs[k], 0u);  // the read's inputs travel with the list entry
             } else {
                 s_br[li] = BIN_NONE;  // no blocks, or past the end of the read set
             }
+            n_listed += __popc(lm);
         }
     }
-    __syncthreads();
-    {
-        const uint32_t nm = s_n[0];
+    __syncwarp();
 #pragma unroll 1
-        for (uint32_t k = tid; k < nm; k += FILT_BLOCK) {
-            const uint32_t li = s_multi[k];
-            const uint64_t r = tile0 + li;
-            const uint4 in = s_rec[li];
-            const uint32_t base = in.x, nraw = in.y;
-            const int2 b0 = __ldg(P.blk + base);
-            const int2 b1 = nraw >= 2u ? __ldg(P.blk + base + 1) : make_int2(0, 0);
-            const TileCtx ctx{P, s_blk, base, tbase, b0, b1, staged};
-            emit(li, r, base, filter_read_t(P, r, base, nraw, in.z, ctx));
-        }
+    for (uint32_t k = lane; k < n_listed; k += 32u) {
+        const uint32_t li = s_multi[k];
+        const uint64_t r = tile0 + li;
+        const uint4 in = s_rec[li];
+        const uint32_t base = in.x, nraw = in.y;
+        const int2 b0 = __ldg(P.blk + base);
+        const int2 b1 = nraw >= 2u ? __ldg(P.blk + base + 1) : make_int2(0, 0);
+        const TileCtx ctx{P, s_blk, base, wbase, b0, b1, staged};
+        emit(li, r, base, filter_read_t(P, r, base, nraw, in.z, ctx));
     }
     __syncthreads();
     // ---- phase D --------------------------------------------------------------------------
