@@ -275,7 +275,6 @@ __global__ void __launch_bounds__(FILT_BLOCK, 2) lsq_filter_kernel(FilterParams 
     }
     __syncthreads();
     // ---- phase D --------------------------------------------------------------------------
-    uint32_t kept[3] = {0u, 0u, 0u};
 #pragma unroll 1
     for (uint32_t b0 = tid; b0 < n_bins; b0 += FILT_BLOCK * FILT_RBATCH) {
         uint32_t c[FILT_RBATCH];
@@ -292,9 +291,6 @@ __global__ void __launch_bounds__(FILT_BLOCK, 2) lsq_filter_kernel(FilterParams 
             if (!c[u]) continue;
             const uint32_t bin = b0 + (uint32_t)u * FILT_BLOCK;
             const uint32_t cls = (bin >= n_bkt ? 1u : 0u) + (bin >= 2u * n_bkt ? 1u : 0u);
-            kept[0] += cls == 0u ? c[u] : 0u;
-            kept[1] += cls == 1u ? c[u] : 0u;
-            kept[2] += cls == 2u ? c[u] : 0u;
             unsigned long long *st = S.state + bin;
             unsigned long long o = old[u];
             while ((uint32_t)o >= PART_CHUNK) {
@@ -327,11 +323,6 @@ __global__ void __launch_bounds__(FILT_BLOCK, 2) lsq_filter_kernel(FilterParams 
             s_split[bin] = (uint16_t)first;
         }
     }
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const uint32_t v = __reduce_add_sync(0xFFFFFFFFu, kept[k]);
-        if (lane_id() == 0 && v) atomicAdd(P.counters + (k == 0 ? 0 : k + 1), (unsigned long long)v);
-    }
     __syncthreads();
     // ---- phase E --------------------------------------------------------------------------
 #pragma unroll
@@ -342,6 +333,23 @@ __global__ void __launch_bounds__(FILT_BLOCK, 2) lsq_filter_kernel(FilterParams 
         if (bin == BIN_NONE) continue;
         const uint32_t slot = (rank < (uint32_t)s_split[bin] ? s_A[bin] : s_B[bin]) + rank;
         S.pool[slot] = s_rec[li];
+    }
+}
+
+// Reads kept per class after the filter: every installed chunk of a bin is full except the current
+// one.  counters[0] = FAST, [2] = PAIR, [3] = GENERAL reads (statistics and byte accounting).
+__global__ void lsq_part_stats_kernel(PartState S, uint32_t n_bkt, unsigned long long *counters) {
+    __shared__ unsigned long long s_sum[3];
+    if (threadIdx.x < 3) s_sum[threadIdx.x] = 0ull;
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < S.n_bins; b += blockDim.x) {
+        const uint32_t cls = (b >= n_bkt ? 1u : 0u) + (b >= 2u * n_bkt ? 1u : 0u);
+        atomicAdd(&s_sum[cls], (unsigned long long)min((uint32_t)S.state[b], PART_CHUNK));
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        const unsigned long long full = (unsigned long long)(S.wl_n[threadIdx.x] - n_bkt) * PART_CHUNK;
+        counters[threadIdx.x == 0 ? 0 : threadIdx.x + 1] = full + s_sum[threadIdx.x];
     }
 }
 
