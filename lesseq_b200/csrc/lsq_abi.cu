@@ -233,7 +233,7 @@ int lsq_upload_events(lsq_ctx *c, const lsq_event_tables *t) {
     T.stab_off = c->d_stab_off.as<uint32_t>();
     T.stab = c->d_stab.as<lsq::StabEntry>();
     T.bp_bkt_off = c->d_bp_bkt_off.as<uint32_t>();
-    T.bp_bkt = c->d_bp_bkt.as<uint32_t>();
+    T.bp_bkt = c->d_bp_bkt.as<uint2>();
     T.cov_off = c->d_cov_off.as<uint32_t>();
     T.cov_start = c->d_cov_start.as<int32_t>();
     T.cov_end = c->d_cov_end.as<int32_t>();

@@ -65,48 +65,38 @@ LSQ_HD uint32_t upper_bound_i32(const int32_t *__restrict__ a, uint32_t lo, uint
 }
 
 // Piece containing position x on chromosome c (index into T.pinfo), or 0xFFFFFFFF when x lies
-// before the first piece.  One load of two adjacent bucket ranks, then a short scan over
-// consecutive 16-byte PieceInfo records (a binary search when a bucket is unusually crowded).
+// before the first piece.  One 8-byte bucket entry names the piece (bucket_rank); a crowded bucket,
+// a negative position or one past the last bucket takes a binary search over the piece starts.
 LSQ_HD uint32_t find_piece(const Tables &T, uint32_t c, int32_t x, PieceInfo &out) {
     const uint4 cm = LSQ_LD(T.chrom_meta + c);
     const uint32_t lo = cm.x, hi = cm.y;
     uint32_t i = lo, j = hi;
+    uint32_t n = 0xFFFFFFFFu;  // pieces of [i, j) starting at or below x, when the bucket word tells
     if (x >= 0) {
         const uint32_t b0 = cm.z, nb = cm.w;
         const uint32_t b = (uint32_t)x >> T.bp_shift;
         if (b >= nb) {
             i = j = hi;
+            n = 0;
         } else {
-            i = LSQ_LD(T.bp_bkt + b0 + b);
-            j = LSQ_LD(T.bp_bkt + b0 + b + 1);
+            const uint2 e = LSQ_LD(T.bp_bkt + b0 + b);
+            i = e.x;
+            n = bucket_rank(T.bp_shift, e.y, (uint32_t)x - (b << T.bp_shift));
+            if (n == 0xFFFFFFFFu) j = LSQ_LD(&T.bp_bkt[b0 + b + 1].x);
         }
     }
-    // pieces [i, j) start inside the bucket of x; piece i-1 (if any) starts before it.  The three
-    // candidates i-1, i, i+1 are fetched with independent 16-byte loads; only a bucket holding more
-    // than two piece starts at or below x needs the search loop.
-    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-    const uint4 r0 = i > lo ? LSQ_LD(reinterpret_cast<const uint4 *>(T.pinfo + (i - 1))) : z;
-    const uint4 r1 = i < j ? LSQ_LD(reinterpret_cast<const uint4 *>(T.pinfo + i)) : z;
-    const uint4 r2 = i + 1 < j ? LSQ_LD(reinterpret_cast<const uint4 *>(T.pinfo + (i + 1))) : z;
-    uint4 raw;
-    uint32_t p;
-    if (!(i < j) || (int32_t)r1.x > x) {
-        if (i == lo) return 0xFFFFFFFFu;
-        raw = r0;
-        p = i - 1;
-    } else if (!(i + 1 < j) || (int32_t)r2.x > x) {
-        raw = r1;
-        p = i;
-    } else {
-        uint32_t a = i + 2, b = j;  // number of pieces with pos <= x among [i+2, j)
+    if (n == 0xFFFFFFFFu) {  // number of pieces with pos <= x among [i, j)
+        uint32_t a = i, b = j;
         while (a < b) {
             const uint32_t mid = (a + b) >> 1;
             if (LSQ_LD(&T.pinfo[mid].pos) <= x) a = mid + 1;
             else b = mid;
         }
-        p = a - 1;
-        raw = LSQ_LD(reinterpret_cast<const uint4 *>(T.pinfo + p));
+        n = a - i;
     }
+    if (i + n == lo) return 0xFFFFFFFFu;
+    const uint32_t p = i + n - 1u;
+    const uint4 raw = LSQ_LD(reinterpret_cast<const uint4 *>(T.pinfo + p));
     out.pos = (int32_t)raw.x;
     out.cov_end = (int32_t)raw.y;
     out.stab_off = raw.z;
@@ -376,8 +366,8 @@ LSQ_HD FilteredRead filter_read(const FilterParams &P, uint64_t r) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// The piece lookup of one block, split into stages (chromosome -> bucket slot -> candidate
-// pieces -> selection) so that the kernel can issue the loads of one stage for several blocks
+// The piece lookup of one block, split into stages (chromosome -> bucket entry -> piece
+// record) so that the kernel can issue the loads of one stage for several blocks
 // before it consumes any of them: the chain of dependent L2 accesses, not arithmetic, bounds
 // the filter.  A stage hands the block over to find_piece (SP_DEFER) when it meets a case it
 // does not cover; both give identical answers (tests/emul replays block_lookup).
@@ -387,7 +377,8 @@ struct BlockProbe {
     int2 b;          // the block
     uint32_t c;      // annotation chromosome id
     uint32_t lo;     // first piece of the chromosome
-    uint32_t slot;   // bucket slot: pieces [bp_bkt[slot], bp_bkt[slot + 1]) start inside the bucket of b.x
+    uint32_t slot;   // bucket slot of b.x
+    uint32_t xo;     // offset of b.x inside its bucket
 };
 
 LSQ_HD int block_stage_chrom(const FilterParams &P, int2 b, uint32_t cs, BlockProbe &q) {
@@ -395,6 +386,7 @@ LSQ_HD int block_stage_chrom(const FilterParams &P, int2 b, uint32_t cs, BlockPr
     q.c = LSQ_LD(P.chrom_remap + (cs & 0xFFFFu));
     q.lo = 0;
     q.slot = 0;
+    q.xo = 0;
     if (!(b.x < b.y)) return SP_DROP;         // nil blocks are never looked up
     if (q.c == 0xFFFFFFFFu) return SP_DROP;   // chromosome without annotation
     if (b.x < 0) return SP_DEFER;
@@ -403,39 +395,23 @@ LSQ_HD int block_stage_chrom(const FilterParams &P, int2 b, uint32_t cs, BlockPr
     if (bk >= cm.w) return SP_DEFER;
     q.lo = cm.x;
     q.slot = cm.z + bk;
+    q.xo = (uint32_t)b.x - (bk << P.T.bp_shift);
     return SP_GO;
 }
 
-// Candidate pieces of the bucket range [i, j): i-1 (starts before the bucket), i and i+1; indices
-// clamped so that the loads can be issued unconditionally (pinfo carries one sentinel).  Of each
-// candidate only {pos, cov_end} is needed.
-LSQ_HD void block_stage_cand(const BlockProbe &q, uint32_t i, uint32_t j, uint32_t &a0, uint32_t &a1, uint32_t &a2) {
-    a0 = i > q.lo ? i - 1 : i;
-    a1 = i;
-    a2 = i + 1 < j ? i + 1 : i;
+// The piece of the block's start from its bucket entry e: SP_GO with p (PIECE_NONE: before the first
+// piece of the chromosome), or SP_DEFER for a crowded bucket (find_piece searches it).
+LSQ_HD int block_stage_piece(const Tables &T, const BlockProbe &q, uint2 e, uint32_t &p) {
+    p = PIECE_NONE;
+    const uint32_t n = bucket_rank(T.bp_shift, e.y, q.xo);
+    if (n == 0xFFFFFFFFu) return SP_DEFER;
+    if (e.x + n != q.lo) p = e.x + n - 1u;
+    return SP_GO;
 }
 
-// Selection among the candidates: the answer of `lookup`, or SP_DEFER for a crowded bucket.
-LSQ_HD int block_stage_select(const BlockProbe &q, uint32_t i, uint32_t j, int2 r0, int2 r1, int2 r2, uint32_t &res) {
-    const int32_t x = q.b.x;
-    res = PIECE_NONE;
-    uint32_t p;
-    int32_t cov_end;
-    if (!(i < j) || r1.x > x) {
-        if (i == q.lo) return SP_GO;  // before the first piece of the chromosome
-        p = i - 1;
-        cov_end = r0.y;
-    } else if (!(i + 1 < j) || r2.x > x) {
-        p = i;
-        cov_end = r1.y;
-    } else if (i + 2 == j) {
-        p = i + 1;
-        cov_end = r2.y;
-    } else {
-        return SP_DEFER;  // find_piece searches the bucket
-    }
-    res = p | (cov_end >= q.b.y ? 0x80000000u : 0u);
-    return SP_GO;
+// The lookup answer from the piece and its covered-region end.
+LSQ_HD uint32_t block_stage_answer(const BlockProbe &q, uint32_t p, int32_t cov_end) {
+    return p == PIECE_NONE ? PIECE_NONE : (p | (cov_end >= q.b.y ? 0x80000000u : 0u));
 }
 
 // Sequential composition of the stages (CPU replay; the kernel runs the same stages batched).
@@ -445,12 +421,9 @@ LSQ_HD uint32_t block_lookup(const FilterParams &P, int2 b, uint32_t cs) {
     if (st == SP_DROP) return PIECE_NONE;
     uint32_t res = PIECE_NONE;
     if (st == SP_GO) {
-        const uint32_t i = LSQ_LD(P.T.bp_bkt + q.slot), j = LSQ_LD(P.T.bp_bkt + q.slot + 1);
-        uint32_t a0, a1, a2;
-        block_stage_cand(q, i, j, a0, a1, a2);
-        st = block_stage_select(q, i, j, LSQ_LD(reinterpret_cast<const int2 *>(P.T.pinfo + a0)),
-                                LSQ_LD(reinterpret_cast<const int2 *>(P.T.pinfo + a1)),
-                                LSQ_LD(reinterpret_cast<const int2 *>(P.T.pinfo + a2)), res);
+        uint32_t p;
+        st = block_stage_piece(P.T, q, LSQ_LD(P.T.bp_bkt + q.slot), p);
+        if (st == SP_GO && p != PIECE_NONE) res = block_stage_answer(q, p, LSQ_LD(&P.T.pinfo[p].cov_end));
     }
     if (st == SP_DEFER) res = lookup_direct(P.T, q.c, b);
     return res;

@@ -23,7 +23,7 @@ __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
 constexpr int FILT_BLOCK = 512;
 constexpr int FILT_ITEMS = 4;                         // reads per thread (all kept in flight together)
-constexpr int FILT_LBATCH = 3;                        // block lookups kept in flight per thread
+constexpr int FILT_LBATCH = 2;                        // block lookups of multi-block reads kept in flight per thread
 constexpr int FILT_RBATCH = 3;                        // bin reservations kept in flight per thread
 constexpr int FILT_TILE = FILT_BLOCK * FILT_ITEMS;    // 2048 reads
 constexpr int FILT_WREADS = 32 * FILT_ITEMS;          // 128 reads per warp
@@ -33,7 +33,7 @@ static_assert((uint32_t)FILT_TILE <= PART_CHUNK, "a tile's reservation may span 
 
 // dynamic shared memory of the filter kernel
 __host__ __device__ inline size_t filter_smem_bytes(uint32_t n_bins) {
-    return (size_t)FILT_TILE * (16 + 4 + 2) + (size_t)FILT_MAX_BLK * 4 + (size_t)n_bins * (4 + 4 + 2) + 64;  // <= 200 KB at PART_MAX_BINS
+    return (size_t)FILT_TILE * (16 + 4 + 2) + (size_t)FILT_MAX_BLK * (4 + 2) + (size_t)n_bins * (4 + 4 + 2) + 64;  // <= 200 KB at PART_MAX_BINS
 }
 
 // Read context of the filter kernel (see filter_read_t): blocks and piece records are fetched on
@@ -68,16 +68,18 @@ __global__ void lsq_part_init_kernel(PartState S, uint32_t n_bkt) {
 
 // Phases A-C run per WARP on its own 128 reads of the tile, with warp-level synchronisation only,
 // so the sixteen warps of a block drift apart and cover each other's memory latencies:
-// Phase A: every lane expands the chromosome/strand ids of its reads over their raw blocks.
-// Phase B: the warp's raw blocks (contiguous in blk[]) are spread over the lanes regardless of
-//          the reads they belong to, and every lane runs the staged piece lookup
-//          (lsq_device_fn.cuh) on FILT_LBATCH blocks at a time, so the loads of each stage
-//          (block, bucket slot, candidate pieces) are in flight together and no lane idles
-//          because its read has fewer blocks than its neighbour's.  Answers go to shared memory.
-// Phase C: single-block reads (4 in 5) are decided by single_decide with block and piece record
-//          fetched for all of the lane's reads at once; the others go to a warp-local list
-//          that is spread densely over the lanes and takes filter_read_t (interval list, read
-//          class).  Records of the kept reads are staged in shared memory.
+// Phase A: every lane loads offsets and chromosome/strand ids of its four reads.  Reads with one
+//          raw block (4 in 5) are "singles"; the raw blocks of all other reads are appended to a
+//          warp-local list (their ids expanded per block in shared memory).
+// Phase S: singles, one lane per read, four reads in flight: block -> bucket entry (ONE 8-byte
+//          gather names the piece, lsq_types.cuh:bucket_rank) -> PieceInfo (ONE 16-byte gather:
+//          covered test, stab list, piece start) -> single_decide.  Two dependent gathers per
+//          read, nothing staged.
+// Phase B: the listed raw blocks are spread densely over the lanes regardless of the reads they
+//          belong to; same two gathers per block, answers go to shared memory.
+// Phase C: the multi-block reads, spread densely over the lanes, take filter_read_t (interval
+//          list, read class) with the staged answers.  Records of kept reads are staged in
+//          shared memory.
 // Then, block-wide:
 // Phase D: one thread per non-empty bin reserves room for the tile's records of that bin with a
 //          single 64-bit atomicAdd on (chunk, fill); the reservation that takes the last slot of
@@ -96,6 +98,7 @@ __global__ void __launch_bounds__(FILT_BLOCK, 2) lsq_filter_kernel(FilterParams 
     uint32_t *s_B = s_A + n_bins;                    // per bin: slot base after a chunk switch
     uint16_t *s_multi_all = reinterpret_cast<uint16_t *>(s_B + n_bins);  // per warp: reads for filter_read_t (tile-local index)
     uint16_t *s_split = s_multi_all + FILT_TILE;     // per bin: records before the chunk switch
+    uint16_t *s_list_all = s_split + n_bins;         // per warp: raw blocks of the multi-block reads (warp-local index)
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     for (uint32_t i = tid; i < n_bins; i += FILT_BLOCK) s_A[i] = 0u;
     __syncthreads();
@@ -106,6 +109,7 @@ __global__ void __launch_bounds__(FILT_BLOCK, 2) lsq_filter_kernel(FilterParams 
     const uint64_t w0 = min(tile0 + (uint64_t)warp * FILT_WREADS, tile1), w1 = min(w0 + (uint64_t)FILT_WREADS, tile1);
     uint32_t *s_blk = s_blk_all + warp * FILT_WBLK;
     uint16_t *s_multi = s_multi_all + warp * FILT_WREADS;
+    uint16_t *s_list = s_list_all + warp * FILT_WBLK;
 
     // ---- phase A --------------------------------------------------------------------------
     uint32_t rbase[FILT_ITEMS], rn[FILT_ITEMS], rcs[FILT_ITEMS];  // absolute block offset, raw blocks, ids
@@ -124,68 +128,74 @@ __global__ void __launch_bounds__(FILT_BLOCK, 2) lsq_filter_kernel(FilterParams 
     const uint32_t wbase = __shfl_sync(0xFFFFFFFFu, rbase[0], 0);
     const uint32_t w_nblk = w1 > w0 ? __ldg(P.blk_off + w1) - wbase : 0u;
     const bool staged = w_nblk <= (uint32_t)FILT_WBLK;  // warp-uniform
-    if (staged) {
+    bool single[FILT_ITEMS];
+    uint32_t n_mb = 0;  // listed raw blocks, warp-uniform
+    {
+        uint32_t mb = 0;
 #pragma unroll
         for (int k = 0; k < FILT_ITEMS; ++k) {
-            const uint32_t rel = rbase[k] - wbase;
-            if (rcs[k] & 0x80000000u) {
-                for (uint32_t j = 0; j < rn[k]; ++j) s_blk[rel + j] = __ldg(P.blk_cs + rbase[k] + j);
-            } else {
-                if (rn[k] >= 1u) s_blk[rel] = rcs[k];
-                if (rn[k] >= 2u) s_blk[rel + 1] = rcs[k];
-                for (uint32_t j = 2; j < rn[k]; ++j) s_blk[rel + j] = rcs[k];
+            single[k] = rn[k] == 1u && !(rcs[k] & 0x80000000u);
+            mb += single[k] ? 0u : rn[k];
+        }
+        if (staged) {
+            uint32_t incl = mb;
+#pragma unroll
+            for (uint32_t d = 1; d < 32u; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            n_mb = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            uint32_t pos = incl - mb;
+#pragma unroll
+            for (int k = 0; k < FILT_ITEMS; ++k) {
+                if (single[k]) continue;
+                const uint32_t rel = rbase[k] - wbase;
+                const bool mixed = (rcs[k] & 0x80000000u) != 0u;
+                for (uint32_t j = 0; j < rn[k]; ++j) {
+                    s_blk[rel + j] = mixed ? __ldg(P.blk_cs + rbase[k] + j) : rcs[k];
+                    s_list[pos++] = (uint16_t)(rel + j);
+                }
             }
         }
     }
     __syncwarp();
     // ---- phase B --------------------------------------------------------------------------
-    if (staged) {
 #pragma unroll 1
-        for (uint32_t k0 = lane; k0 < w_nblk; k0 += 32u * FILT_LBATCH) {
-            int st[FILT_LBATCH];
-            BlockProbe q[FILT_LBATCH];
-            int2 b[FILT_LBATCH];
+    for (uint32_t k0 = lane; k0 < n_mb; k0 += 32u * FILT_LBATCH) {
+        int st[FILT_LBATCH];
+        BlockProbe q[FILT_LBATCH];
+        uint32_t rel[FILT_LBATCH];
 #pragma unroll
-            for (int u = 0; u < FILT_LBATCH; ++u) {
-                const uint32_t k = k0 + (uint32_t)u * 32u;
-                st[u] = k < w_nblk ? SP_GO : -1;
-                b[u] = st[u] == SP_GO ? __ldcs(P.blk + wbase + k) : make_int2(0, 0);
-            }
+        for (int u = 0; u < FILT_LBATCH; ++u) {
+            const uint32_t k = k0 + (uint32_t)u * 32u;
+            st[u] = k < n_mb ? SP_GO : -1;
+            rel[u] = st[u] == SP_GO ? (uint32_t)s_list[k] : 0u;
+        }
+        int2 b[FILT_LBATCH];
 #pragma unroll
-            for (int u = 0; u < FILT_LBATCH; ++u) {
-                const uint32_t k = k0 + (uint32_t)u * 32u;
-                if (st[u] == SP_GO) st[u] = block_stage_chrom(P, b[u], s_blk[k], q[u]);
-            }
-            uint32_t bi[FILT_LBATCH], bj[FILT_LBATCH];
+        for (int u = 0; u < FILT_LBATCH; ++u) b[u] = st[u] == SP_GO ? __ldg(P.blk + wbase + rel[u]) : make_int2(0, 0);
 #pragma unroll
-            for (int u = 0; u < FILT_LBATCH; ++u) {
-                bi[u] = bj[u] = 0;
-                if (st[u] == SP_GO) {
-                    bi[u] = __ldg(T.bp_bkt + q[u].slot);
-                    bj[u] = __ldg(T.bp_bkt + q[u].slot + 1);
-                }
-            }
-            int2 r0[FILT_LBATCH], r1[FILT_LBATCH], r2[FILT_LBATCH];
+        for (int u = 0; u < FILT_LBATCH; ++u)
+            if (st[u] == SP_GO) st[u] = block_stage_chrom(P, b[u], s_blk[rel[u]], q[u]);
+        uint2 be[FILT_LBATCH];
 #pragma unroll
-            for (int u = 0; u < FILT_LBATCH; ++u) {
-                r0[u] = r1[u] = r2[u] = make_int2(0, 0);
-                if (st[u] == SP_GO) {
-                    uint32_t a0, a1, a2;
-                    block_stage_cand(q[u], bi[u], bj[u], a0, a1, a2);
-                    r0[u] = __ldg(reinterpret_cast<const int2 *>(T.pinfo + a0));
-                    r1[u] = __ldg(reinterpret_cast<const int2 *>(T.pinfo + a1));
-                    r2[u] = __ldg(reinterpret_cast<const int2 *>(T.pinfo + a2));
-                }
-            }
+        for (int u = 0; u < FILT_LBATCH; ++u) be[u] = st[u] == SP_GO ? __ldg(T.bp_bkt + q[u].slot) : make_uint2(0u, 0u);
+        uint32_t pp[FILT_LBATCH];
+        int32_t ce[FILT_LBATCH];
 #pragma unroll
-            for (int u = 0; u < FILT_LBATCH; ++u) {
-                const uint32_t k = k0 + (uint32_t)u * 32u;
-                if (st[u] < 0) continue;
-                uint32_t res = PIECE_NONE;
-                if (st[u] == SP_GO) st[u] = block_stage_select(q[u], bi[u], bj[u], r0[u], r1[u], r2[u], res);
-                if (st[u] == SP_DEFER) res = lookup_direct(T, q[u].c, b[u]);
-                s_blk[k] = res;
-            }
+        for (int u = 0; u < FILT_LBATCH; ++u) {
+            pp[u] = PIECE_NONE;
+            ce[u] = 0;
+            if (st[u] == SP_GO) st[u] = block_stage_piece(T, q[u], be[u], pp[u]);
+            if (st[u] == SP_GO && pp[u] != PIECE_NONE) ce[u] = __ldg(&T.pinfo[pp[u]].cov_end);
+        }
+#pragma unroll
+        for (int u = 0; u < FILT_LBATCH; ++u) {
+            if (st[u] < 0) continue;
+            uint32_t res = PIECE_NONE;
+            if (st[u] == SP_GO) res = block_stage_answer(q[u], pp[u], ce[u]);
+            if (st[u] == SP_DEFER) res = lookup_direct(T, q[u].c, b[u]);
+            s_blk[rel[u]] = res;
         }
     }
     __syncwarp();
@@ -228,22 +238,32 @@ __global__ void __launch_bounds__(FILT_BLOCK, 2) lsq_filter_kernel(FilterParams 
         }
         s_br[li] = br;
     };
+    // ---- phase S --------------------------------------------------------------------------
     uint32_t n_listed = 0;  // warp-uniform
     {
+        int st[FILT_ITEMS];
         int2 b0[FILT_ITEMS];
-        uint32_t res[FILT_ITEMS];
-        uint4 pi0[FILT_ITEMS];
-        bool single[FILT_ITEMS];
+        BlockProbe q[FILT_ITEMS];
 #pragma unroll
         for (int k = 0; k < FILT_ITEMS; ++k) {
-            single[k] = staged && rn[k] == 1u && !(rcs[k] & 0x80000000u);
-            b0[k] = single[k] ? __ldg(P.blk + rbase[k]) : make_int2(0, 0);
-            res[k] = single[k] ? s_blk[rbase[k] - wbase] : PIECE_NONE;
+            st[k] = single[k] ? SP_GO : -1;
+            b0[k] = single[k] ? __ldcs(P.blk + rbase[k]) : make_int2(0, 0);
         }
 #pragma unroll
         for (int k = 0; k < FILT_ITEMS; ++k)
-            pi0[k] = single_kept(res[k]) ? __ldg(reinterpret_cast<const uint4 *>(T.pinfo + (res[k] & PIECE_NONE)))
-                                         : make_uint4(0u, 0u, 0u, 0u);
+            if (st[k] == SP_GO) st[k] = block_stage_chrom(P, b0[k], rcs[k], q[k]);
+        uint2 be[FILT_ITEMS];
+#pragma unroll
+        for (int k = 0; k < FILT_ITEMS; ++k) be[k] = st[k] == SP_GO ? __ldg(T.bp_bkt + q[k].slot) : make_uint2(0u, 0u);
+        uint32_t pp[FILT_ITEMS];
+        uint4 raw[FILT_ITEMS];
+#pragma unroll
+        for (int k = 0; k < FILT_ITEMS; ++k) {
+            pp[k] = PIECE_NONE;
+            if (st[k] == SP_GO) st[k] = block_stage_piece(T, q[k], be[k], pp[k]);
+            if (st[k] == SP_DEFER) pp[k] = lookup_direct(T, q[k].c, b0[k]) & PIECE_NONE;  // crowded bucket: searched
+            raw[k] = pp[k] != PIECE_NONE ? __ldg(reinterpret_cast<const uint4 *>(T.pinfo + pp[k])) : make_uint4(0u, 0u, 0u, 0u);
+        }
 #pragma unroll
         for (int k = 0; k < FILT_ITEMS; ++k) {
             const uint32_t li = warp * FILT_WREADS + lane + (uint32_t)k * 32u;  // tile-local index
@@ -251,7 +271,8 @@ __global__ void __launch_bounds__(FILT_BLOCK, 2) lsq_filter_kernel(FilterParams 
             const bool listed = !single[k] && r < w1 && rn[k] != 0u;
             const unsigned lm = __ballot_sync(0xFFFFFFFFu, listed);
             if (single[k]) {
-                emit(li, r, rbase[k], single_decide(T, b0[k], rcs[k], res[k], pi0[k]));
+                const uint32_t res = block_stage_answer(q[k], pp[k], (int32_t)raw[k].y);
+                emit(li, r, rbase[k], single_decide(T, b0[k], rcs[k], res, raw[k]));
             } else if (listed) {
                 s_multi[n_listed + __popc(lm & ((1u << lane) - 1u))] = (uint16_t)li;
                 s_rec[li] = make_uint4(rbase[k], rn[k], rcs[k], 0u);  // the read's inputs travel with the list entry
@@ -261,6 +282,7 @@ __global__ void __launch_bounds__(FILT_BLOCK, 2) lsq_filter_kernel(FilterParams 
             n_listed += __popc(lm);
         }
     }
+    // ---- phase C --------------------------------------------------------------------------
     __syncwarp();
 #pragma unroll 1
     for (uint32_t k = lane; k < n_listed; k += 32u) {

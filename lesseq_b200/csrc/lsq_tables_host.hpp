@@ -28,7 +28,8 @@ struct HostTables {
     std::vector<int32_t> bp_pos, cov_start, cov_end;
     std::vector<PieceInfo> pinfo;
     uint32_t bp_shift = 0;
-    std::vector<uint32_t> bp_bkt_off, bp_bkt;
+    std::vector<uint32_t> bp_bkt_off;
+    std::vector<uint2> bp_bkt;
     std::vector<uint4> chrom_meta;
     uint32_t bkt_shift = 9, n_bkt = 1, max_stab_n = 0;
     std::vector<uint32_t> bkt_piece;  // [n_bkt+1] first piece whose stab_off is >= b << bkt_shift
@@ -65,20 +66,23 @@ struct HostTables {
     }
 };
 
-// Bucket index over per-chromosome sorted coordinate arrays (CSR `off`): bucket b of a
-// chromosome covers positions [b << shift, (b+1) << shift) and stores the rank (global index)
-// of the first element >= b << shift; one extra bucket per chromosome closes the last range.
-// The shift is chosen so that there are about sixteen buckets per element (at most 2^25): pieces
-// cluster inside genes, and a bucket should rarely hold more than two piece starts.
+// Bucket index over per-chromosome sorted piece starts (CSR `off`): bucket b of a chromosome covers
+// positions [b << shift, (b+1) << shift).  Its entry holds the rank (global index) of the first
+// piece starting at or after b << shift and, packed into one word (bucket_word, lsq_types.cuh),
+// the in-bucket offsets of the pieces that start inside it -- so the piece of a position is found
+// with ONE 8-byte load; only a bucket with more starts than fit the word falls back to a search.
+// One extra bucket per chromosome closes the last range.  The shift is chosen so that there are
+// about eight buckets per piece (at most 2^25): pieces cluster inside genes.
 inline void build_bucket_index(const std::vector<int32_t> &arr, const std::vector<uint32_t> &off, uint32_t &shift,
-                               std::vector<uint32_t> &bkt_off, std::vector<uint32_t> &bkt) {
+                               std::vector<uint32_t> &bkt_off, std::vector<uint2> &bkt) {
     const size_t nch = off.size() - 1;
     uint64_t span = 0;
     for (size_t c = 0; c < nch; ++c)
         if (off[c + 1] > off[c]) span += (uint64_t)std::max<int32_t>(arr[off[c + 1] - 1], 0) + 1;
-    uint64_t want = std::min<uint64_t>(std::max<uint64_t>(16 * arr.size(), 1), 1ull << 25);
+    uint64_t want = std::min<uint64_t>(std::max<uint64_t>(8 * arr.size(), 1), 1ull << 25);
     shift = 0;
     while ((span >> shift) > want && shift < 30) ++shift;
+    const uint32_t K = bucket_capacity(shift);
     bkt_off.assign(nch + 1, 0);
     bkt.clear();
     for (size_t c = 0; c < nch; ++c) {
@@ -87,9 +91,21 @@ inline void build_bucket_index(const std::vector<int32_t> &arr, const std::vecto
         uint32_t nb = hi > lo ? (uint32_t)(((uint64_t)std::max<int32_t>(arr[hi - 1], 0) >> shift) + 1) : 0;
         uint32_t i = lo;
         for (uint32_t b = 0; b <= nb; ++b) {  // nb + 1 entries: the last one is `hi`
-            int64_t start = (int64_t)b << shift;
+            const int64_t start = (int64_t)b << shift, end = start + ((int64_t)1 << shift);
             while (i < hi && (int64_t)arr[i] < start) ++i;
-            bkt.push_back(b == nb ? hi : i);
+            uint2 e = make_uint2(b == nb ? hi : i, 0u);
+            if (b < nb) {
+                uint32_t j = i;
+                while (j < hi && (int64_t)arr[j] < end) ++j;
+                const uint32_t cnt = j - i;
+                if (cnt > K) {
+                    e.y = BKT_MANY << 29;
+                } else {
+                    e.y = cnt << 29;
+                    for (uint32_t t = 0; t < cnt; ++t) e.y |= (uint32_t)((int64_t)arr[i + t] - start) << (t * shift);
+                }
+            }
+            bkt.push_back(e);
         }
     }
     bkt_off[nch] = (uint32_t)bkt.size();

@@ -3,6 +3,12 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#ifdef __CUDACC__
+#define LSQ_TYPES_HD __host__ __device__ __forceinline__
+#else
+#define LSQ_TYPES_HD inline
+#endif
+
 namespace lsq {
 
 constexpr int DENSE_MAX_FORMS = 8;  // events with K <= 8 use a direct-indexed class table
@@ -126,11 +132,29 @@ struct Tables {
     uint32_t bp_shift;
     const uint4 *chrom_meta;       // [n_chroms] {first piece, end piece, first bucket, buckets - 1}
     const uint32_t *bp_bkt_off;    // [n_chroms+1] first bucket of each chromosome
-    const uint32_t *bp_bkt;        // [buckets + n_chroms] rank of the first piece starting in or after the bucket
+    const uint2 *bp_bkt;           // [buckets + n_chroms] x: rank of the first piece starting in or after the bucket,
+                                   // y: the piece starts inside the bucket (bucket_word), so the piece of a
+                                   // position comes from ONE 8-byte load
     // stab buckets (PartState): bucket of piece p = stab_off[p] >> bkt_shift
     uint32_t bkt_shift, n_bkt;
     const uint32_t *bkt_piece;     // [n_bkt+1] first piece whose stab_off is >= b << bkt_shift
 };
+
+// Bucket word: bits 29-31 = number of piece starts inside the bucket (BKT_MANY: more than fit), then
+// bucket_capacity(shift) offsets of `shift` bits each (start - bucket start), ascending.
+constexpr uint32_t BKT_MANY = 7u;
+LSQ_TYPES_HD uint32_t bucket_capacity(uint32_t shift) {
+    return shift == 0u ? 4u : (29u / shift < 4u ? 29u / shift : 4u);
+}
+// Number of piece starts at or below in-bucket offset xo, or 0xFFFFFFFF when the bucket is crowded.
+LSQ_TYPES_HD uint32_t bucket_rank(uint32_t shift, uint32_t w, uint32_t xo) {
+    const uint32_t cnt = w >> 29;
+    if (cnt == BKT_MANY) return 0xFFFFFFFFu;
+    const uint32_t mask = (1u << shift) - 1u;
+    uint32_t n = 0;
+    for (uint32_t t = 0; t < cnt; ++t) n += xo >= ((w >> (t * shift)) & mask) ? 1u : 0u;
+    return n;
+}
 
 struct FilterParams {
     Tables T;
