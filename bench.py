@@ -277,12 +277,27 @@ def run_ours(args):
     cnt, sol = ctx.get_count(), ctx.get_solve()
 
     # ---- end to end through the C ABI with host buffers ---------------------------------------
-    # compact wire format: blocks per read (u8) instead of CSR offsets, implicit line numbers
+    # compact wire format (include/lesseq_b200.h): blocks per read (u8) instead of CSR offsets, implicit line
+    # numbers, one-byte chromosome/strand ids, block = start (i32) + length (u16); streamed (LSQ_READS_STREAM):
+    # the filter consumes the blocks while the copy engine is still delivering them
     blk_cnt = (reads["blk_off"][1:] - reads["blk_off"][:-1]).to(torch.uint8)
-    pinned = {"blk": reads["blk"].cpu().pin_memory(), "read_cs": reads["read_cs"].cpu().pin_memory(),
-              "blk_cnt": blk_cnt.cpu().pin_memory()}
-    host_reads = api.Reads.from_torch(None, pinned["blk"], pinned["read_cs"], None, reads["chrom_names"],
-                                      reads["strand_names"], blk_cnt=pinned["blk_cnt"])
+    cs = reads["read_cs"]
+    b2 = reads["blk"].view(-1, 2)
+    compact_ok = len(reads["chrom_names"]) <= 64 and len(reads["strand_names"]) <= 2 and \
+        int((b2[:, 1] - b2[:, 0]).max()) < 65536 and int((b2[:, 1] - b2[:, 0]).min()) >= 0 and not args.wide_wire
+    if compact_ok:
+        cs8 = ((cs & 0x3F) | (((cs >> 16) & 1) << 6) | (((cs >> 31) & 1) << 7)).to(torch.uint8)
+        pinned = {"blk_start": b2[:, 0].contiguous().cpu().pin_memory(),
+                  "blk_len": (b2[:, 1] - b2[:, 0]).to(torch.int16).cpu().pin_memory(),  # bit pattern of u16
+                  "read_cs8": cs8.cpu().pin_memory(), "blk_cnt": blk_cnt.cpu().pin_memory()}
+        host_reads = api.Reads.from_torch(None, None, None, None, reads["chrom_names"], reads["strand_names"],
+                                          blk_cnt=pinned["blk_cnt"], stream=not args.no_stream, read_cs8=pinned["read_cs8"],
+                                          blk_start=pinned["blk_start"], blk_len=pinned["blk_len"])
+    else:
+        pinned = {"blk": reads["blk"].cpu().pin_memory(), "read_cs": reads["read_cs"].cpu().pin_memory(),
+                  "blk_cnt": blk_cnt.cpu().pin_memory()}
+        host_reads = api.Reads.from_torch(None, pinned["blk"], pinned["read_cs"], None, reads["chrom_names"],
+                                          reads["strand_names"], blk_cnt=pinned["blk_cnt"], stream=not args.no_stream)
 
     def step_e2e():
         ctx.set_reads(0, "SHORT_READ", R, host_reads)

@@ -49,6 +49,12 @@ extern "C" {
 
 #define LSQ_READ_MIXED 0x80000000u /* read_cs flag: blocks differ in chromosome/strand */
 
+/* lsq_packed_reads.flags */
+#define LSQ_READS_STREAM 1u /* host buffers only: lsq_set_reads returns while the host->device copy is still in
+                               flight and the load filter of the next lsq_count consumes the blocks as they land
+                               (PCIe transfer and filter overlap).  The caller keeps the buffers valid and
+                               unmodified until that lsq_count has returned. */
+
 typedef struct lsq_ctx lsq_ctx;
 
 /* ---------------------------------------------------------------------------------------------
@@ -118,9 +124,15 @@ typedef struct lsq_packed_reads {
     const char *const *chrom_names;  /* always host memory */
     const char *const *strand_names; /* always host memory */
     uint32_t on_device;
-    uint32_t reserved0;
+    uint32_t flags;          /* LSQ_READS_* */
     const uint8_t *blk_cnt;  /* [n_reads] blocks per read (< 256); alternative to blk_off that costs a
                                 quarter of the host->device bytes (offsets are rebuilt by a device scan) */
+    /* Compact wire format (optional; lsqh_reads_compact produces it): the transfer over PCIe, not the
+     * kernels, bounds the end-to-end rate, so every array has a narrow alternative. */
+    const uint8_t *read_cs8;   /* [n_reads] alternative to read_cs: bits 0-5 chromosome id (< 64), bit 6 strand
+                                  id (< 2), bit 7 MIXED (per-block values in blk_cs) */
+    const int32_t *blk_start;  /* [n_blocks] with blk_len: alternative to blk -- start0 of every block ... */
+    const uint16_t *blk_len;   /* [n_blocks] ... and end - start0 (< 65536) */
 } lsq_packed_reads;
 
 /* Results of the counted path (count.cpp:421-492, solve.cpp:719-793), caller-owned host buffers. */
@@ -229,6 +241,9 @@ uint64_t lsqh_form_length(const lsqh_annotation *a, uint32_t f);
 int lsqh_mrf_parse(const char *path, lsqh_reads **out);
 void lsqh_reads_free(lsqh_reads *r);
 int lsqh_reads_view(const lsqh_reads *r, lsq_packed_reads *out);
+/* Derives the compact wire format (blk_cnt, read_cs8, blk_start + blk_len) of a parsed read set where the
+ * values fit; later views carry both representations and lsq_set_reads copies the narrow one. */
+int lsqh_reads_compact(lsqh_reads *r);
 
 /* Drop-in bodies of the two programs: same positional arguments (argv[0] = program name),
  * same stdout tables, log on stderr, same exit codes (0, 1; 134 is reported as abort()). */

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(PKG, "lib", "liblesseq_b200.so")
 LSQ_READ_MEDIUM = 1
 LSQ_READ_SHORT = 2
 LSQ_READ_MIXED = 0x80000000
+LSQ_READS_STREAM = 1
 LSQ_MAX_METHODS = 16
 READ_TYPES = {"MEDIUM_READ": LSQ_READ_MEDIUM, "SHORT_READ": LSQ_READ_SHORT}
 
@@ -43,8 +44,8 @@ class PackedReads(C.Structure):
         ("line_num", C.c_void_p),
         ("n_chrom_names", C.c_uint32), ("n_strand_names", C.c_uint32),
         ("chrom_names", c_strp), ("strand_names", c_strp),
-        ("on_device", C.c_uint32), ("reserved0", C.c_uint32),
-        ("blk_cnt", C.c_void_p),
+        ("on_device", C.c_uint32), ("flags", C.c_uint32),
+        ("blk_cnt", C.c_void_p), ("read_cs8", C.c_void_p), ("blk_start", C.c_void_p), ("blk_len", C.c_void_p),
     ]
 
 
@@ -107,6 +108,7 @@ SYMBOLS = {
     "lsqh_form_length": (C.c_uint64, [C.c_void_p, C.c_uint32]),
     "lsqh_mrf_parse": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "lsqh_reads_free": (None, [C.c_void_p]),
+    "lsqh_reads_compact": (C.c_int, [C.c_void_p]),
     "lsqh_reads_view": (C.c_int, [C.c_void_p, C.POINTER(PackedReads)]),
     "lsqh_count_main": (C.c_int, [C.c_int, c_strp]),
     "lsqh_solve_main": (C.c_int, [C.c_int, c_strp]),

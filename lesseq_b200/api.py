@@ -104,10 +104,14 @@ class Reads:
         self._lib = _lib.load()
 
     @classmethod
-    def from_mrf(cls, path):
+    def from_mrf(cls, path, compact=False):
+        """Parse an MRF_SINGLE file; compact=True also derives the compact wire format
+        (lsqh_reads_compact), which lsq_set_reads then prefers."""
         self = cls()
         self._h = C.c_void_p()
         check(self._lib.lsqh_mrf_parse(str(path).encode(), C.byref(self._h)))
+        if compact:
+            check(self._lib.lsqh_reads_compact(self._h))
         check(self._lib.lsqh_reads_view(self._h, C.byref(self.view)))
         return self
 
@@ -146,14 +150,17 @@ class Reads:
         return self
 
     @classmethod
-    def from_torch(cls, blk_off, blk, read_cs, line_num, chrom_names, strand_names, blk_cs=None, blk_cnt=None):
+    def from_torch(cls, blk_off, blk, read_cs, line_num, chrom_names, strand_names, blk_cs=None, blk_cnt=None,
+                   stream=False, read_cs8=None, blk_start=None, blk_len=None):
         """Tensors must be contiguous int32 (bit patterns of the uint32 fields; blk_cnt uint8); CUDA
         tensors are borrowed (on_device=1), CPU tensors (pinned or not) are host buffers.  Compact
         wire format: pass blk_off=None with blk_cnt (blocks per read) and/or line_num=None (implicit
-        1..n)."""
+        1..n); read_cs8 (uint8) instead of read_cs; blk_start (int32) + blk_len (int16 bit patterns of
+        uint16) instead of blk.  stream=True (host tensors): LSQ_READS_STREAM, the copy overlaps the
+        next count()."""
         self = cls()
-        ts = [t for t in (blk_off, blk, read_cs, line_num, blk_cs) if t is not None]
-        dev = blk.is_cuda
+        ts = [t for t in (blk_off, blk, read_cs, line_num, blk_cs, blk_start) if t is not None]
+        dev = (blk if blk is not None else blk_start).is_cuda
         for t in ts:
             assert t.is_contiguous() and t.element_size() == 4 and t.is_cuda == dev
         if blk_cnt is not None:
@@ -161,16 +168,27 @@ class Reads:
             ts.append(blk_cnt)
             self.view.blk_cnt = blk_cnt.data_ptr()
         assert blk_off is not None or blk_cnt is not None
+        if read_cs8 is not None:
+            assert read_cs8.is_contiguous() and read_cs8.element_size() == 1 and read_cs8.is_cuda == dev
+            ts.append(read_cs8)
+            self.view.read_cs8 = read_cs8.data_ptr()
+        if blk_len is not None:
+            assert blk_start is not None and blk_len.is_contiguous() and blk_len.element_size() == 2
+            assert blk_len.is_cuda == dev and blk_len.numel() == blk_start.numel()
+            ts.append(blk_len)
+            self.view.blk_start, self.view.blk_len = blk_start.data_ptr(), blk_len.data_ptr()
         self._keep += ts
         v = self.view
-        v.n_reads = read_cs.numel()
-        v.n_blocks = blk.numel() // 2
-        v.blk, v.read_cs = blk.data_ptr(), read_cs.data_ptr()
+        v.n_reads = (read_cs if read_cs is not None else read_cs8).numel()
+        v.n_blocks = blk.numel() // 2 if blk is not None else blk_start.numel()
+        v.blk = blk.data_ptr() if blk is not None else None
+        v.read_cs = read_cs.data_ptr() if read_cs is not None else None
         v.blk_off = blk_off.data_ptr() if blk_off is not None else None
         v.line_num = line_num.data_ptr() if line_num is not None else None
         if blk_cs is not None:
             v.blk_cs = blk_cs.data_ptr()
         v.on_device = 1 if dev else 0
+        v.flags = _lib.LSQ_READS_STREAM if (stream and not dev) else 0
         self._names(chrom_names, strand_names)
         return self
 
@@ -186,7 +204,8 @@ class Reads:
         """Bytes lsq_set_reads copies host->device for this read set."""
         n, nb = self.n_reads, self.n_blocks
         v = self.view
-        return ((n + 1) * 4 if v.blk_off else n) + nb * 8 + n * 4 + (n * 4 if v.line_num else 0)
+        return (((n + 1) * 4 if v.blk_off else n) + (nb * 6 if v.blk_len else nb * 8) + (n if v.read_cs8 else n * 4) +
+                (n * 4 if v.line_num else 0))
 
 
 class Context:

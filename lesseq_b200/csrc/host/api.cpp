@@ -110,7 +110,21 @@ int lsqh_reads_view(const lsqh_reads *r, lsq_packed_reads *v) {
     v->chrom_names = r->chrom_ptrs.data();
     v->strand_names = r->strand_ptrs.data();
     v->on_device = 0;
-    v->blk_cnt = nullptr;
+    v->blk_cnt = r->blk_cnt.size() == r->read_cs.size() && !r->blk_cnt.empty() ? r->blk_cnt.data() : nullptr;
+    v->read_cs8 = r->read_cs8.size() == r->read_cs.size() && !r->read_cs8.empty() ? r->read_cs8.data() : nullptr;
+    if (r->blk_len.size() == r->blk_cs.size() && !r->blk_len.empty()) {
+        v->blk_start = r->blk_start.data();
+        v->blk_len = r->blk_len.data();
+    }
+    return LSQ_OK;
+}
+
+int lsqh_reads_compact(lsqh_reads *r) {
+    if (!r) {
+        lsqh::set_error("lsqh_reads_compact: null argument");
+        return LSQ_ERR_ARG;
+    }
+    lsqh::compact_reads(*r);
     return LSQ_OK;
 }
 

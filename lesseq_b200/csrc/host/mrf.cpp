@@ -248,4 +248,42 @@ int parse_mrf(const char *path, lsqh_reads &R) {
     return LSQ_OK;
 }
 
+// Compact wire format: every array in its narrowest lossless form, or left empty when a value
+// does not fit (the view then carries only the wide array).
+void compact_reads(lsqh_reads &R) {
+    const size_t n = R.read_cs.size(), nb = R.blk_cs.size();
+    R.blk_cnt.clear();
+    R.read_cs8.clear();
+    R.blk_start.clear();
+    R.blk_len.clear();
+    bool ok = true;
+    R.blk_cnt.resize(n);
+    for (size_t i = 0; i < n && ok; ++i) {
+        const uint32_t c = R.blk_off[i + 1] - R.blk_off[i];
+        ok = c < 256u;
+        R.blk_cnt[i] = (uint8_t)c;
+    }
+    if (!ok) R.blk_cnt.clear();
+    if (R.chroms.names.size() <= 64 && R.strands.names.size() <= 2) {
+        R.read_cs8.resize(n);
+        for (size_t i = 0; i < n; ++i) {
+            const uint32_t cs = R.read_cs[i];
+            R.read_cs8[i] = (uint8_t)((cs & 0x3Fu) | (((cs >> 16) & 1u) << 6) | ((cs & LSQ_READ_MIXED) ? 0x80u : 0u));
+        }
+    }
+    ok = true;
+    R.blk_start.resize(nb);
+    R.blk_len.resize(nb);
+    for (size_t b = 0; b < nb && ok; ++b) {
+        const int64_t len = (int64_t)R.blk[2 * b + 1] - (int64_t)R.blk[2 * b];
+        ok = len >= 0 && len < 65536;
+        R.blk_start[b] = R.blk[2 * b];
+        R.blk_len[b] = (uint16_t)len;
+    }
+    if (!ok) {
+        R.blk_start.clear();
+        R.blk_len.clear();
+    }
+}
+
 }  // namespace lsqh

@@ -70,14 +70,18 @@ struct U8ToU32 {
 
 struct ReadSet {
     bool declared = false, injected = false, borrowed = false;
+    bool streamed = false;  // blk[] is still being copied when lsq_count launches the filter (LSQ_READS_STREAM)
     uint32_t type = 0;
     uint64_t read_length = 0;
     uint64_t n_reads = 0, n_blocks = 0;
     uint32_t n_file_strands = 0;
     // inputs (owned copies or borrowed device pointers)
-    DevBuf d_blk_off, d_blk, d_read_cs, d_blk_cs, d_line_num, d_blk_cnt, d_scan_tmp;
+    DevBuf d_blk_off, d_blk, d_read_cs, d_blk_cs, d_line_num, d_blk_cnt, d_scan_tmp, d_read_cs8, d_blk_start, d_blk_len;
     const uint32_t *blk_off = nullptr, *read_cs = nullptr, *blk_cs = nullptr, *line_num = nullptr;
     const int2 *blk = nullptr;
+    const uint8_t *read_cs8 = nullptr;  // compact wire format
+    const int32_t *blk_start = nullptr;
+    const uint16_t *blk_len = nullptr;
     DevBuf d_chrom_remap, d_strand_tbl;
     // injected classes (output order CSR)
     DevBuf d_inj_off, d_inj_mask, d_inj_cnt;
@@ -109,6 +113,11 @@ struct lsq_ctx {
     bool filter_smem_set = false;
     DevBuf d_n_valid, d_bases_out, d_iso, d_theta, d_rpkm, d_se, d_ll, d_llpr, d_iters;
     bool counted = false, finalized = false, solved = false;
+    // streamed read sets: copies run on their own stream and publish their progress to the filter
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_small = nullptr, ev_all[LSQ_MAX_METHODS] = {};
+    DevBuf d_progress;            // [LSQ_MAX_METHODS] blocks of blk[] landed so far
+    uint32_t *h_progress = nullptr;  // pinned: the values the copy stream writes after each chunk
     // timing
     cudaEvent_t ev[16] = {};
     lsq_timings tm{};
@@ -117,11 +126,8 @@ struct lsq_ctx {
 
 namespace {
 
-uint32_t bits_for(uint32_t v) {  // bits needed to represent values 0..v
-    uint32_t b = 1;
-    while (b < 32 && (v >> b)) ++b;
-    return b;
-}
+constexpr uint32_t STREAM_MAX_CHUNKS = 64;           // progress values per streamed read set
+constexpr size_t STREAM_MIN_CHUNK_BLOCKS = 2u << 20;  // 16 MB of blk[] per chunk at least
 
 }  // namespace
 
@@ -151,6 +157,11 @@ int lsq_ctx_create(int device, lsq_ctx **out) {
     LSQ_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->own_stream = true;
     for (auto &ev : c->ev) LSQ_CUDA(cudaEventCreate(&ev));
+    LSQ_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    LSQ_CUDA(cudaEventCreateWithFlags(&c->ev_small, cudaEventDisableTiming));
+    for (auto &ev : c->ev_all) LSQ_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    LSQ_CUDA(c->d_progress.ensure(LSQ_MAX_METHODS * sizeof(uint32_t)));
+    LSQ_CUDA(cudaMallocHost(&c->h_progress, LSQ_MAX_METHODS * STREAM_MAX_CHUNKS * sizeof(uint32_t)));
     *out = c;
     return LSQ_OK;
 }
@@ -159,6 +170,14 @@ int lsq_ctx_destroy(lsq_ctx *c) {
     if (!c) return LSQ_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) {
+        cudaStreamSynchronize(c->copy_stream);
+        cudaStreamDestroy(c->copy_stream);
+    }
+    if (c->ev_small) cudaEventDestroy(c->ev_small);
+    for (auto &ev : c->ev_all)
+        if (ev) cudaEventDestroy(ev);
+    if (c->h_progress) cudaFreeHost(c->h_progress);
     for (auto &ev : c->ev)
         if (ev) cudaEventDestroy(ev);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -283,53 +302,116 @@ int lsq_set_reads(lsq_ctx *c, uint32_t m, uint32_t read_type, uint64_t read_leng
     rs.n_blocks = r->n_blocks;
     rs.n_file_strands = r->n_strand_names;
     rs.borrowed = r->on_device != 0;
+    rs.streamed = !rs.borrowed && (r->flags & LSQ_READS_STREAM) != 0 && r->n_blocks > 0;
     if (!r->blk_off && !r->blk_cnt) return fail(LSQ_ERR_ARG, "lsq_set_reads: blk_off or blk_cnt is required");
+    const bool compact_blk = r->blk_start != nullptr && r->blk_len != nullptr;
+    if (!compact_blk && !r->blk && r->n_blocks) return fail(LSQ_ERR_ARG, "lsq_set_reads: blk or blk_start + blk_len is required");
+    if (!r->read_cs && !r->read_cs8 && r->n_reads) return fail(LSQ_ERR_ARG, "lsq_set_reads: read_cs or read_cs8 is required");
+    if (r->read_cs8 && (r->n_chrom_names > 64 || r->n_strand_names > 2))
+        return fail(LSQ_ERR_RANGE, "read_cs8 holds 64 chromosome and 2 strand ids at most");
     {
         const size_t n = r->n_reads, nb = r->n_blocks;
         const cudaMemcpyKind kind = rs.borrowed ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        rs.blk = nullptr;
+        rs.blk_start = nullptr;
+        rs.blk_len = nullptr;
+        rs.read_cs = nullptr;
+        rs.read_cs8 = nullptr;
+        rs.blk_cs = nullptr;
+        rs.line_num = nullptr;
+        rs.blk_off = nullptr;
+        const uint8_t *cnt = r->blk_cnt;
         if (rs.borrowed) {
-            rs.blk = reinterpret_cast<const int2 *>(r->blk);
-            rs.read_cs = r->read_cs;
+            if (compact_blk) {
+                rs.blk_start = r->blk_start;
+                rs.blk_len = r->blk_len;
+            } else {
+                rs.blk = reinterpret_cast<const int2 *>(r->blk);
+            }
+            if (r->read_cs8) rs.read_cs8 = r->read_cs8;
+            else rs.read_cs = r->read_cs;
             rs.blk_cs = r->blk_cs;
             rs.line_num = r->line_num;
             rs.blk_off = r->blk_off;
         } else {
-            LSQ_CUDA(rs.d_blk.ensure(std::max<size_t>(nb, 1) * 8));
-            LSQ_CUDA(rs.d_read_cs.ensure(std::max<size_t>(n, 1) * 4));
-            if (nb) LSQ_CUDA(cudaMemcpyAsync(rs.d_blk.p, r->blk, nb * 8, kind, s));
-            if (n) LSQ_CUDA(cudaMemcpyAsync(rs.d_read_cs.p, r->read_cs, n * 4, kind, s));
-            rs.line_num = nullptr;
+            // device buffers first (an allocation synchronises the device), then the copies: the per-read
+            // arrays, then the blocks.  A streamed set (LSQ_READS_STREAM) puts all copies on the copy stream,
+            // the blocks in chunks, each followed by a 4-byte write of the number of blocks landed so far; the
+            // compute stream only waits for the per-read arrays and the filter kernel polls the progress word.
+            if (compact_blk) {
+                LSQ_CUDA(rs.d_blk_start.ensure(std::max<size_t>(nb, 1) * 4));
+                LSQ_CUDA(rs.d_blk_len.ensure(std::max<size_t>(nb, 1) * 2));
+                rs.blk_start = rs.d_blk_start.as<int32_t>();
+                rs.blk_len = rs.d_blk_len.as<uint16_t>();
+            } else {
+                LSQ_CUDA(rs.d_blk.ensure(std::max<size_t>(nb, 1) * 8));
+                rs.blk = rs.d_blk.as<int2>();
+            }
+            bool any_mixed = false;
+            if (r->blk_cs) {
+                if (r->read_cs8) for (size_t i = 0; i < n && !any_mixed; ++i) any_mixed = (r->read_cs8[i] & 0x80u) != 0;
+                else for (size_t i = 0; i < n && !any_mixed; ++i) any_mixed = (r->read_cs[i] & LSQ_READ_MIXED) != 0;
+            }
+            if (r->read_cs8) LSQ_CUDA(rs.d_read_cs8.ensure(std::max<size_t>(n, 1)));
+            else LSQ_CUDA(rs.d_read_cs.ensure(std::max<size_t>(n, 1) * 4));
+            if (r->line_num) LSQ_CUDA(rs.d_line_num.ensure(std::max<size_t>(n, 1) * 4));
+            if (any_mixed) LSQ_CUDA(rs.d_blk_cs.ensure(std::max<size_t>(nb, 1) * 4));
+            LSQ_CUDA(rs.d_blk_off.ensure((n + 1) * 4));
+            if (!r->blk_off) LSQ_CUDA(rs.d_blk_cnt.ensure(std::max<size_t>(n, 1)));
+            if (rs.streamed) {
+                s = c->copy_stream;
+                LSQ_CUDA(cudaMemsetAsync(c->d_progress.as<uint32_t>() + m, 0, sizeof(uint32_t), s));
+            }
+            if (r->read_cs8) {
+                if (n) LSQ_CUDA(cudaMemcpyAsync(rs.d_read_cs8.p, r->read_cs8, n, kind, s));
+                rs.read_cs8 = rs.d_read_cs8.as<uint8_t>();
+            } else {
+                if (n) LSQ_CUDA(cudaMemcpyAsync(rs.d_read_cs.p, r->read_cs, n * 4, kind, s));
+                rs.read_cs = rs.d_read_cs.as<uint32_t>();
+            }
             if (r->line_num) {
-                LSQ_CUDA(rs.d_line_num.ensure(std::max<size_t>(n, 1) * 4));
                 if (n) LSQ_CUDA(cudaMemcpyAsync(rs.d_line_num.p, r->line_num, n * 4, kind, s));
                 rs.line_num = rs.d_line_num.as<uint32_t>();
             }
-            rs.blk_cs = nullptr;
-            if (r->blk_cs) {
-                bool any_mixed = false;
-                for (size_t i = 0; i < n && !any_mixed; ++i) any_mixed = (r->read_cs[i] & LSQ_READ_MIXED) != 0;
-                if (any_mixed) {
-                    LSQ_CUDA(rs.d_blk_cs.ensure(std::max<size_t>(nb, 1) * 4));
-                    LSQ_CUDA(cudaMemcpyAsync(rs.d_blk_cs.p, r->blk_cs, nb * 4, kind, s));
-                    rs.blk_cs = rs.d_blk_cs.as<uint32_t>();
-                }
+            if (any_mixed) {
+                LSQ_CUDA(cudaMemcpyAsync(rs.d_blk_cs.p, r->blk_cs, nb * 4, kind, s));
+                rs.blk_cs = rs.d_blk_cs.as<uint32_t>();
             }
-            rs.blk = rs.d_blk.as<int2>();
-            rs.read_cs = rs.d_read_cs.as<uint32_t>();
-            rs.blk_off = nullptr;
             if (r->blk_off) {
-                LSQ_CUDA(rs.d_blk_off.ensure((n + 1) * 4));
                 LSQ_CUDA(cudaMemcpyAsync(rs.d_blk_off.p, r->blk_off, (n + 1) * 4, kind, s));
                 rs.blk_off = rs.d_blk_off.as<uint32_t>();
-            }
-        }
-        if (!rs.blk_off) {  // rebuild the CSR offsets from the per-read block counts on the device
-            const uint8_t *cnt = r->blk_cnt;
-            if (!rs.borrowed) {
-                LSQ_CUDA(rs.d_blk_cnt.ensure(std::max<size_t>(n, 1)));
+            } else {
                 if (n) LSQ_CUDA(cudaMemcpyAsync(rs.d_blk_cnt.p, r->blk_cnt, n, kind, s));
                 cnt = rs.d_blk_cnt.as<uint8_t>();
             }
+            if (rs.streamed) LSQ_CUDA(cudaEventRecord(c->ev_small, s));
+            size_t chunk = std::max<size_t>(nb, 1);
+            if (rs.streamed) {
+                chunk = std::max<size_t>(STREAM_MIN_CHUNK_BLOCKS, (nb + STREAM_MAX_CHUNKS - 1) / STREAM_MAX_CHUNKS);
+                chunk = (chunk + 63) & ~(size_t)63;  // whole 128-byte lines of every array: no line straddles two chunks
+            }
+            uint32_t *hp = c->h_progress + (size_t)m * STREAM_MAX_CHUNKS;
+            uint32_t k = 0;
+            for (size_t b0 = 0; b0 < nb; b0 += chunk, ++k) {
+                const size_t b1 = std::min(nb, b0 + chunk);
+                if (compact_blk) {
+                    LSQ_CUDA(cudaMemcpyAsync(rs.d_blk_start.as<int32_t>() + b0, r->blk_start + b0, (b1 - b0) * 4, kind, s));
+                    LSQ_CUDA(cudaMemcpyAsync(rs.d_blk_len.as<uint16_t>() + b0, r->blk_len + b0, (b1 - b0) * 2, kind, s));
+                } else {
+                    LSQ_CUDA(cudaMemcpyAsync(rs.d_blk.as<int2>() + b0, r->blk + 2 * b0, (b1 - b0) * 8, kind, s));
+                }
+                if (rs.streamed) {
+                    hp[k] = (uint32_t)b1;
+                    LSQ_CUDA(cudaMemcpyAsync(c->d_progress.as<uint32_t>() + m, hp + k, sizeof(uint32_t), kind, s));
+                }
+            }
+            if (rs.streamed) {
+                LSQ_CUDA(cudaEventRecord(c->ev_all[m], s));
+                s = c->stream;  // everything below belongs to the compute stream, after the per-read arrays
+                LSQ_CUDA(cudaStreamWaitEvent(s, c->ev_small, 0));
+            }
+        }
+        if (!rs.blk_off) {  // rebuild the CSR offsets from the per-read block counts on the device
             LSQ_CUDA(rs.d_blk_off.ensure((n + 1) * 4));
             LSQ_CUDA(cudaMemsetAsync(rs.d_blk_off.p, 0, 4, s));
             if (n) {
@@ -529,8 +611,12 @@ int lsq_count(lsq_ctx *c) {
             FP.blk_off = rs.blk_off;
             FP.blk = rs.blk;
             FP.read_cs = rs.read_cs;
+            FP.read_cs8 = rs.read_cs8;
+            FP.blk_start = rs.blk_start;
+            FP.blk_len = rs.blk_len;
             FP.blk_cs = rs.blk_cs;
             FP.chrom_remap = rs.d_chrom_remap.as<uint32_t>();
+            FP.progress = rs.streamed ? c->d_progress.as<uint32_t>() + m : nullptr;
             FP.ext = c->d_ext.as<int2>();
             FP.part = PS;
             FP.counters = counters;
@@ -545,6 +631,7 @@ int lsq_count(lsq_ctx *c) {
         } else {
             LSQ_CUDA(cudaEventRecord(c->ev[1], s));
         }
+        if (rs.streamed) LSQ_CUDA(cudaStreamWaitEvent(s, c->ev_all[m], 0));  // the caller's buffers are free again
         LSQ_CUDA(cudaEventRecord(c->ev[2], s));
         if (n) {
             lsq::CountParams CP;

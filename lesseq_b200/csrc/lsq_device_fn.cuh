@@ -209,6 +209,29 @@ struct FilteredRead {
 //   ctx.pinfo(p)        the 16-byte PieceInfo of piece p
 constexpr uint32_t PIECE_NONE = 0x7FFFFFFFu;
 
+// Raw block i and the ids of read r, from the wide or the compact representation of the read set.
+LSQ_HD int2 load_block(const FilterParams &P, uint32_t i) {
+    if (P.blk_len != nullptr) {
+        const int32_t s = LSQ_LD(P.blk_start + i);
+        return make_int2(s, s + (int32_t)LSQ_LD(P.blk_len + i));
+    }
+    return LSQ_LD(P.blk + i);
+}
+LSQ_HD int2 load_block_stream(const FilterParams &P, uint32_t i) {
+    if (P.blk_len != nullptr) {
+        const int32_t s = LSQ_LD_STREAM(P.blk_start + i);
+        return make_int2(s, s + (int32_t)LSQ_LD_STREAM(P.blk_len + i));
+    }
+    return LSQ_LD_STREAM(P.blk + i);
+}
+LSQ_HD uint32_t load_read_cs(const FilterParams &P, uint64_t r) {
+    if (P.read_cs8 != nullptr) {
+        const uint32_t v = LSQ_LD_STREAM(P.read_cs8 + r);
+        return (v & 0x3Fu) | ((v & 0x40u) << 10) | ((v & 0x80u) << 24);
+    }
+    return LSQ_LD_STREAM(P.read_cs + r);
+}
+
 LSQ_HD uint32_t lookup_direct(const Tables &T, uint32_t c, int2 b) {
     PieceInfo pi;
     const uint32_t pidx = find_piece(T, c, b.x, pi);
@@ -219,7 +242,7 @@ LSQ_HD uint32_t lookup_direct(const Tables &T, uint32_t c, int2 b) {
 struct DirectCtx {  // everything on demand, lookups through find_piece
     const FilterParams &P;
     uint32_t base;
-    LSQ_HD int2 blk(uint32_t j) const { return LSQ_LD_STREAM(P.blk + base + j); }
+    LSQ_HD int2 blk(uint32_t j) const { return load_block_stream(P, base + j); }
     LSQ_HD uint32_t lookup(uint32_t, uint32_t c, int2 b) const { return lookup_direct(P.T, c, b); }
     LSQ_HD uint4 pinfo(uint32_t p) const { return LSQ_LD(reinterpret_cast<const uint4 *>(P.T.pinfo + p)); }
 };
@@ -360,7 +383,7 @@ LSQ_HD void write_ext_entry(int2 *ext, uint32_t off, uint32_t r, const FilteredR
 LSQ_HD FilteredRead filter_read(const FilterParams &P, uint64_t r) {
     const uint32_t base = LSQ_LD_STREAM(P.blk_off + r);
     const uint32_t nraw = LSQ_LD_STREAM(P.blk_off + r + 1) - base;
-    const uint32_t cs0 = LSQ_LD_STREAM(P.read_cs + r);
+    const uint32_t cs0 = load_read_cs(P, r);
     const DirectCtx ctx{P, base};
     return filter_read_t(P, r, base, nraw, cs0, ctx);
 }
@@ -467,7 +490,7 @@ LSQ_HD FilteredRead single_decide(const Tables &T, int2 b, uint32_t cs0, uint32_
 struct StagedCtx {
     const FilterParams &P;
     uint32_t base, cs0;
-    LSQ_HD int2 blk(uint32_t j) const { return LSQ_LD_STREAM(P.blk + base + j); }
+    LSQ_HD int2 blk(uint32_t j) const { return load_block_stream(P, base + j); }
     LSQ_HD uint32_t lookup(uint32_t j, uint32_t, int2 b) const {
         const uint32_t cs = (cs0 & 0x80000000u) ? LSQ_LD(P.blk_cs + base + j) : cs0;
         return block_lookup(P, b, cs);
@@ -477,9 +500,9 @@ struct StagedCtx {
 LSQ_HD FilteredRead filter_dispatch(const FilterParams &P, uint64_t r) {
     const uint32_t base = LSQ_LD_STREAM(P.blk_off + r);
     const uint32_t nraw = LSQ_LD_STREAM(P.blk_off + r + 1) - base;
-    const uint32_t cs0 = LSQ_LD_STREAM(P.read_cs + r);
+    const uint32_t cs0 = load_read_cs(P, r);
     if (nraw == 1u && !(cs0 & 0x80000000u)) {
-        const int2 b = LSQ_LD_STREAM(P.blk + base);
+        const int2 b = load_block_stream(P, base);
         const uint32_t res = block_lookup(P, b, cs0);
         const uint4 raw = single_kept(res) ? LSQ_LD(reinterpret_cast<const uint4 *>(P.T.pinfo + (res & PIECE_NONE)))
                                            : make_uint4(0u, 0u, 0u, 0u);

@@ -44,7 +44,7 @@ struct TileCtx {
     uint32_t base, tbase;
     int2 b0, b1;  // the first two raw blocks, fetched by the caller
     bool staged;
-    __device__ __forceinline__ int2 blk(uint32_t j) const { return j == 0u ? b0 : (j == 1u ? b1 : __ldg(P.blk + base + j)); }
+    __device__ __forceinline__ int2 blk(uint32_t j) const { return j == 0u ? b0 : (j == 1u ? b1 : load_block(P, base + j)); }
     __device__ __forceinline__ uint32_t lookup(uint32_t j, uint32_t c, int2 b) const {
         return staged ? s_blk[base - tbase + j] : lookup_direct(P.T, c, b);
     }
@@ -101,9 +101,16 @@ __global__ void __launch_bounds__(FILT_BLOCK, 2) lsq_filter_kernel(FilterParams 
     uint16_t *s_list_all = s_split + n_bins;         // per warp: raw blocks of the multi-block reads (warp-local index)
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     for (uint32_t i = tid; i < n_bins; i += FILT_BLOCK) s_A[i] = 0u;
-    __syncthreads();
     const uint64_t tile0 = (uint64_t)blockIdx.x * FILT_TILE;
     const uint64_t tile1 = min(tile0 + (uint64_t)FILT_TILE, P.n_reads);
+    if (P.progress != nullptr && tid == 0u) {
+        // streamed read set: the copy engine is still filling blk[]; wait until the tile's last block
+        // has landed (the per-read arrays were complete before the launch)
+        const uint32_t need = __ldg(P.blk_off + tile1);
+        while (*reinterpret_cast<const volatile uint32_t *>(P.progress) < need) __nanosleep(400);
+        __threadfence();
+    }
+    __syncthreads();
     const uint32_t n_bkt = T.n_bkt;
     // the warp's reads: [w0, w1), lane l owns w0 + l + 32 k
     const uint64_t w0 = min(tile0 + (uint64_t)warp * FILT_WREADS, tile1), w1 = min(w0 + (uint64_t)FILT_WREADS, tile1);
@@ -122,7 +129,7 @@ __global__ void __launch_bounds__(FILT_BLOCK, 2) lsq_filter_kernel(FilterParams 
         if (r < w1) {
             rbase[k] = __ldcs(P.blk_off + r);
             rn[k] = __ldcs(P.blk_off + r + 1) - rbase[k];
-            rcs[k] = __ldcs(P.read_cs + r);
+            rcs[k] = load_read_cs(P, r);
         }
     }
     const uint32_t wbase = __shfl_sync(0xFFFFFFFFu, rbase[0], 0);
@@ -173,7 +180,7 @@ __global__ void __launch_bounds__(FILT_BLOCK, 2) lsq_filter_kernel(FilterParams 
         }
         int2 b[FILT_LBATCH];
 #pragma unroll
-        for (int u = 0; u < FILT_LBATCH; ++u) b[u] = st[u] == SP_GO ? __ldg(P.blk + wbase + rel[u]) : make_int2(0, 0);
+        for (int u = 0; u < FILT_LBATCH; ++u) b[u] = st[u] == SP_GO ? load_block(P, wbase + rel[u]) : make_int2(0, 0);
 #pragma unroll
         for (int u = 0; u < FILT_LBATCH; ++u)
             if (st[u] == SP_GO) st[u] = block_stage_chrom(P, b[u], s_blk[rel[u]], q[u]);
@@ -247,7 +254,7 @@ __global__ void __launch_bounds__(FILT_BLOCK, 2) lsq_filter_kernel(FilterParams 
 #pragma unroll
         for (int k = 0; k < FILT_ITEMS; ++k) {
             st[k] = single[k] ? SP_GO : -1;
-            b0[k] = single[k] ? __ldcs(P.blk + rbase[k]) : make_int2(0, 0);
+            b0[k] = single[k] ? load_block_stream(P, rbase[k]) : make_int2(0, 0);
         }
 #pragma unroll
         for (int k = 0; k < FILT_ITEMS; ++k)
@@ -290,8 +297,8 @@ __global__ void __launch_bounds__(FILT_BLOCK, 2) lsq_filter_kernel(FilterParams 
         const uint64_t r = tile0 + li;
         const uint4 in = s_rec[li];
         const uint32_t base = in.x, nraw = in.y;
-        const int2 b0 = __ldg(P.blk + base);
-        const int2 b1 = nraw >= 2u ? __ldg(P.blk + base + 1) : make_int2(0, 0);
+        const int2 b0 = load_block(P, base);
+        const int2 b1 = nraw >= 2u ? load_block(P, base + 1) : make_int2(0, 0);
         const TileCtx ctx{P, s_blk, base, wbase, b0, b1, staged};
         emit(li, r, base, filter_read_t(P, r, base, nraw, in.z, ctx));
     }

@@ -164,6 +164,11 @@ struct FilterParams {
     const uint32_t *read_cs;
     const uint32_t *blk_cs;       // may be null
     const uint32_t *chrom_remap;  // file chromosome id -> annotation id or 0xFFFFFFFF
+    // compact wire format (include/lesseq_b200.h): alternatives to read_cs and blk, null when absent
+    const uint8_t *read_cs8;
+    const int32_t *blk_start;
+    const uint16_t *blk_len;
+    const uint32_t *progress;     // null, or: blocks of blk[] that have landed so far (streamed host->device copy)
     int2 *ext;                    // [n_blocks + 2 n_reads] worst case (header + blocks per general read)
     PartState part;
     unsigned long long *counters; // per read set: [0] FAST reads, [1] ext slots read, [2] PAIR reads, [3] GENERAL reads

@@ -248,6 +248,38 @@ def test_device_resident_reads_and_properties(api, tmp_path):
     assert np.array_equal(np.concatenate([p["iso_count"] for p in parts]), c["iso_count"])
 
 
+def test_streamed_host_reads_match_resident(api, tmp_path):
+    """LSQ_READS_STREAM: the filter consumes blk[] while the copy engine is still filling it.  Results
+    must be identical to the device-resident run, for a set large enough to take many chunks, a tiny
+    one, and when the same context streams twice in a row."""
+    import torch
+    from lesseq_b200 import synth
+    A, R, _ = synth.make_config("C2", n_genes=2000)
+    fp, mp = str(tmp_path / "ev.interval"), str(tmp_path / "ev.map")
+    A.write(fp, mp)
+    ann = api.Annotation(fp, mp)
+    ctx = api.Context(0)
+    ctx.upload_events(ann)
+    for n in (12_000_000, 5_000, 12_000_000):
+        rd = synth.make_reads(A, n, R, 11 + n % 7, device="cuda")
+        ctx.set_reads(0, "SHORT_READ", R, api.Reads.from_torch(rd["blk_off"], rd["blk"], rd["read_cs"],
+                                                               rd["line_num"], rd["chrom_names"], rd["strand_names"]))
+        ctx.count()
+        ref = ctx.get_count()
+        cnt = (rd["blk_off"][1:] - rd["blk_off"][:-1]).to(torch.uint8)
+        host = {k: rd[k].cpu().pin_memory() for k in ("blk", "read_cs")}
+        host["blk_cnt"] = cnt.cpu().pin_memory()
+        for stream in (True, False):
+            hr = api.Reads.from_torch(None, host["blk"], host["read_cs"], None, rd["chrom_names"], rd["strand_names"],
+                                      blk_cnt=host["blk_cnt"], stream=stream)
+            ctx.set_reads(0, "SHORT_READ", R, hr)
+            ctx.count()
+            got = ctx.get_count()
+            for k in ref:
+                assert np.array_equal(ref[k], got[k]), "streamed=%s n=%d: %s differs" % (stream, n, k)
+    ctx.close()
+
+
 def _walk_reads(rng, forms, L, n):
     """Reads of length <= L walking along randomly chosen forms (blocks cut at exon ends)."""
     lines = []
