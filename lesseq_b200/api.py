@@ -204,7 +204,7 @@ class Reads:
         """Bytes lsq_set_reads copies host->device for this read set."""
         n, nb = self.n_reads, self.n_blocks
         v = self.view
-        return (((n + 1) * 4 if v.blk_off else n) + (nb * 6 if v.blk_len else nb * 8) + (n if v.read_cs8 else n * 4) +
+        return ((n if v.blk_cnt else (n + 1) * 4) + (nb * 6 if v.blk_len else nb * 8) + (n if v.read_cs8 else n * 4) +
                 (n * 4 if v.line_num else 0))
 
 

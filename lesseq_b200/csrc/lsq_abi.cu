@@ -102,7 +102,7 @@ struct lsq_ctx {
     lsq::HostTables H;  // host mirror (internal order): headers, permutation, form segment lengths
     std::map<std::string, uint32_t> chrom_id;
     std::vector<std::string> strand_names;
-    DevBuf d_hdr, d_seg, d_fmask, d_pfx, d_tie, d_bp_chrom_off, d_stab_off, d_stab, d_cov_off, d_bp_bkt_off, d_bp_bkt, d_pinfo, d_chrom_meta,
+    DevBuf d_hdr, d_seg, d_fmask, d_pfx, d_tie, d_bp_chrom_off, d_stab_off, d_stab, d_cov_off, d_bp_bkt_off, d_bp_bkt, d_bp_sub, d_pinfo, d_chrom_meta,
         d_cov_start, d_cov_end, d_form_len, d_bkt_piece;
     // read sets
     ReadSet sets[LSQ_MAX_METHODS];
@@ -232,6 +232,7 @@ int lsq_upload_events(lsq_ctx *c, const lsq_event_tables *t) {
     LSQ_CUDA(upload(c->d_stab, H.stab, s));
     LSQ_CUDA(upload(c->d_bp_bkt_off, H.bp_bkt_off, s));
     LSQ_CUDA(upload(c->d_bp_bkt, H.bp_bkt, s));
+    LSQ_CUDA(upload(c->d_bp_sub, H.bp_sub, s));
     LSQ_CUDA(upload(c->d_cov_off, H.cov_off, s));
     LSQ_CUDA(upload(c->d_cov_start, H.cov_start, s));
     LSQ_CUDA(upload(c->d_cov_end, H.cov_end, s));
@@ -253,6 +254,7 @@ int lsq_upload_events(lsq_ctx *c, const lsq_event_tables *t) {
     T.stab = c->d_stab.as<lsq::StabEntry>();
     T.bp_bkt_off = c->d_bp_bkt_off.as<uint32_t>();
     T.bp_bkt = c->d_bp_bkt.as<uint2>();
+    T.bp_sub = c->d_bp_sub.as<uint2>();
     T.cov_off = c->d_cov_off.as<uint32_t>();
     T.cov_start = c->d_cov_start.as<int32_t>();
     T.cov_end = c->d_cov_end.as<int32_t>();
@@ -356,8 +358,9 @@ int lsq_set_reads(lsq_ctx *c, uint32_t m, uint32_t read_type, uint64_t read_leng
             else LSQ_CUDA(rs.d_read_cs.ensure(std::max<size_t>(n, 1) * 4));
             if (r->line_num) LSQ_CUDA(rs.d_line_num.ensure(std::max<size_t>(n, 1) * 4));
             if (any_mixed) LSQ_CUDA(rs.d_blk_cs.ensure(std::max<size_t>(nb, 1) * 4));
+            const bool use_cnt = r->blk_cnt != nullptr;  // a quarter of the bytes of blk_off
             LSQ_CUDA(rs.d_blk_off.ensure((n + 1) * 4));
-            if (!r->blk_off) LSQ_CUDA(rs.d_blk_cnt.ensure(std::max<size_t>(n, 1)));
+            if (use_cnt) LSQ_CUDA(rs.d_blk_cnt.ensure(std::max<size_t>(n, 1)));
             if (rs.streamed) {
                 s = c->copy_stream;
                 LSQ_CUDA(cudaMemsetAsync(c->d_progress.as<uint32_t>() + m, 0, sizeof(uint32_t), s));
@@ -377,7 +380,7 @@ int lsq_set_reads(lsq_ctx *c, uint32_t m, uint32_t read_type, uint64_t read_leng
                 LSQ_CUDA(cudaMemcpyAsync(rs.d_blk_cs.p, r->blk_cs, nb * 4, kind, s));
                 rs.blk_cs = rs.d_blk_cs.as<uint32_t>();
             }
-            if (r->blk_off) {
+            if (!use_cnt) {
                 LSQ_CUDA(cudaMemcpyAsync(rs.d_blk_off.p, r->blk_off, (n + 1) * 4, kind, s));
                 rs.blk_off = rs.d_blk_off.as<uint32_t>();
             } else {

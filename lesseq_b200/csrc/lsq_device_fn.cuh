@@ -65,13 +65,14 @@ LSQ_HD uint32_t upper_bound_i32(const int32_t *__restrict__ a, uint32_t lo, uint
 }
 
 // Piece containing position x on chromosome c (index into T.pinfo), or 0xFFFFFFFF when x lies
-// before the first piece.  One 8-byte bucket entry names the piece (bucket_rank); a crowded bucket,
-// a negative position or one past the last bucket takes a binary search over the piece starts.
+// before the first piece.  One 8-byte bucket entry names the piece (bucket_rank), a crowded bucket
+// takes one more entry (its sub-bucket); a crowded sub-bucket, a negative position or one past the
+// last bucket takes a binary search over the piece starts.
 LSQ_HD uint32_t find_piece(const Tables &T, uint32_t c, int32_t x, PieceInfo &out) {
     const uint4 cm = LSQ_LD(T.chrom_meta + c);
     const uint32_t lo = cm.x, hi = cm.y;
     uint32_t i = lo, j = hi;
-    uint32_t n = 0xFFFFFFFFu;  // pieces of [i, j) starting at or below x, when the bucket word tells
+    uint32_t n = 0xFFFFFFFFu;  // pieces of [i, j) starting at or below x, when a bucket word tells
     if (x >= 0) {
         const uint32_t b0 = cm.z, nb = cm.w;
         const uint32_t b = (uint32_t)x >> T.bp_shift;
@@ -80,9 +81,17 @@ LSQ_HD uint32_t find_piece(const Tables &T, uint32_t c, int32_t x, PieceInfo &ou
             n = 0;
         } else {
             const uint2 e = LSQ_LD(T.bp_bkt + b0 + b);
+            const uint32_t xo = (uint32_t)x - (b << T.bp_shift);
             i = e.x;
-            n = bucket_rank(T.bp_shift, e.y, (uint32_t)x - (b << T.bp_shift));
-            if (n == 0xFFFFFFFFu) j = LSQ_LD(&T.bp_bkt[b0 + b + 1].x);
+            if (!bucket_many(e.y)) {
+                n = bucket_rank(T.bp_shift, e.y, xo);
+            } else {
+                const uint32_t ss = bucket_sub_shift(T.bp_shift);
+                const uint2 e2 = LSQ_LD(T.bp_sub + (e.y & 0x1FFFFFFFu) + (xo >> ss));
+                i = e2.x;
+                if (!bucket_many(e2.y)) n = bucket_rank(ss, e2.y, xo & ((1u << ss) - 1u));
+                else j = i + (1u << ss) < hi ? i + (1u << ss) : hi;  // at most 2^ss starts in the sub-bucket
+            }
         }
     }
     if (n == 0xFFFFFFFFu) {  // number of pieces with pos <= x among [i, j)
@@ -395,13 +404,13 @@ LSQ_HD FilteredRead filter_read(const FilterParams &P, uint64_t r) {
 // the filter.  A stage hands the block over to find_piece (SP_DEFER) when it meets a case it
 // does not cover; both give identical answers (tests/emul replays block_lookup).
 // ---------------------------------------------------------------------------------------------
-constexpr int SP_DROP = 0, SP_GO = 1, SP_DEFER = 2;
+constexpr int SP_DROP = 0, SP_GO = 1, SP_DEFER = 2, SP_SUB = 3;
 struct BlockProbe {
     int2 b;          // the block
     uint32_t c;      // annotation chromosome id
     uint32_t lo;     // first piece of the chromosome
-    uint32_t slot;   // bucket slot of b.x
-    uint32_t xo;     // offset of b.x inside its bucket
+    uint32_t slot;   // bucket slot of b.x (SP_SUB: sub-bucket slot)
+    uint32_t xo;     // offset of b.x inside its bucket (SP_SUB: inside its sub-bucket)
 };
 
 LSQ_HD int block_stage_chrom(const FilterParams &P, int2 b, uint32_t cs, BlockProbe &q) {
@@ -423,11 +432,24 @@ LSQ_HD int block_stage_chrom(const FilterParams &P, int2 b, uint32_t cs, BlockPr
 }
 
 // The piece of the block's start from its bucket entry e: SP_GO with p (PIECE_NONE: before the first
-// piece of the chromosome), or SP_DEFER for a crowded bucket (find_piece searches it).
-LSQ_HD int block_stage_piece(const Tables &T, const BlockProbe &q, uint2 e, uint32_t &p) {
+// piece of the chromosome), or SP_SUB for a crowded bucket: q then names the sub-bucket entry.
+LSQ_HD int block_stage_piece(const Tables &T, BlockProbe &q, uint2 e, uint32_t &p) {
     p = PIECE_NONE;
+    if (bucket_many(e.y)) {
+        const uint32_t ss = bucket_sub_shift(T.bp_shift);
+        q.slot = (e.y & 0x1FFFFFFFu) + (q.xo >> ss);
+        q.xo &= (1u << ss) - 1u;
+        return SP_SUB;
+    }
     const uint32_t n = bucket_rank(T.bp_shift, e.y, q.xo);
-    if (n == 0xFFFFFFFFu) return SP_DEFER;
+    if (e.x + n != q.lo) p = e.x + n - 1u;
+    return SP_GO;
+}
+// ... from its sub-bucket entry: SP_GO with p, or SP_DEFER (find_piece searches a crowded sub-bucket).
+LSQ_HD int block_stage_sub(const Tables &T, const BlockProbe &q, uint2 e, uint32_t &p) {
+    p = PIECE_NONE;
+    if (bucket_many(e.y)) return SP_DEFER;
+    const uint32_t n = bucket_rank(bucket_sub_shift(T.bp_shift), e.y, q.xo);
     if (e.x + n != q.lo) p = e.x + n - 1u;
     return SP_GO;
 }
@@ -446,6 +468,7 @@ LSQ_HD uint32_t block_lookup(const FilterParams &P, int2 b, uint32_t cs) {
     if (st == SP_GO) {
         uint32_t p;
         st = block_stage_piece(P.T, q, LSQ_LD(P.T.bp_bkt + q.slot), p);
+        if (st == SP_SUB) st = block_stage_sub(P.T, q, LSQ_LD(P.T.bp_sub + q.slot), p);
         if (st == SP_GO && p != PIECE_NONE) res = block_stage_answer(q, p, LSQ_LD(&P.T.pinfo[p].cov_end));
     }
     if (st == SP_DEFER) res = lookup_direct(P.T, q.c, b);

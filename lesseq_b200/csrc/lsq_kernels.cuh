@@ -100,7 +100,8 @@ __global__ void __launch_bounds__(FILT_BLOCK, 2) lsq_filter_kernel(FilterParams 
     uint16_t *s_split = s_multi_all + FILT_TILE;     // per bin: records before the chunk switch
     uint16_t *s_list_all = s_split + n_bins;         // per warp: raw blocks of the multi-block reads (warp-local index)
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    for (uint32_t i = tid; i < n_bins; i += FILT_BLOCK) s_A[i] = 0u;
+    for (uint32_t i = tid; i < (n_bins + 3u) / 4u; i += FILT_BLOCK)  // may run into s_B, which is written before use
+        reinterpret_cast<uint4 *>(s_A)[i] = make_uint4(0u, 0u, 0u, 0u);
     const uint64_t tile0 = (uint64_t)blockIdx.x * FILT_TILE;
     const uint64_t tile1 = min(tile0 + (uint64_t)FILT_TILE, P.n_reads);
     if (P.progress != nullptr && tid == 0u) {
@@ -155,13 +156,19 @@ __global__ void __launch_bounds__(FILT_BLOCK, 2) lsq_filter_kernel(FilterParams 
             uint32_t pos = incl - mb;
 #pragma unroll
             for (int k = 0; k < FILT_ITEMS; ++k) {
-                if (single[k]) continue;
+                if (single[k] || rn[k] == 0u) continue;
                 const uint32_t rel = rbase[k] - wbase;
-                const bool mixed = (rcs[k] & 0x80000000u) != 0u;
-                for (uint32_t j = 0; j < rn[k]; ++j) {
-                    s_blk[rel + j] = mixed ? __ldg(P.blk_cs + rbase[k] + j) : rcs[k];
-                    s_list[pos++] = (uint16_t)(rel + j);
+                if (rcs[k] & 0x80000000u) {  // per-block ids (chimeric read)
+                    for (uint32_t j = 0; j < rn[k]; ++j) s_blk[rel + j] = __ldg(P.blk_cs + rbase[k] + j);
+                } else {
+                    s_blk[rel] = rcs[k];
+                    if (rn[k] >= 2u) s_blk[rel + 1] = rcs[k];
+                    for (uint32_t j = 2; j < rn[k]; ++j) s_blk[rel + j] = rcs[k];
                 }
+                s_list[pos] = (uint16_t)rel;
+                if (rn[k] >= 2u) s_list[pos + 1] = (uint16_t)(rel + 1u);
+                for (uint32_t j = 2; j < rn[k]; ++j) s_list[pos + j] = (uint16_t)(rel + j);
+                pos += rn[k];
             }
         }
     }
@@ -194,6 +201,7 @@ __global__ void __launch_bounds__(FILT_BLOCK, 2) lsq_filter_kernel(FilterParams 
             pp[u] = PIECE_NONE;
             ce[u] = 0;
             if (st[u] == SP_GO) st[u] = block_stage_piece(T, q[u], be[u], pp[u]);
+            if (st[u] == SP_SUB) st[u] = block_stage_sub(T, q[u], __ldg(T.bp_sub + q[u].slot), pp[u]);
             if (st[u] == SP_GO && pp[u] != PIECE_NONE) ce[u] = __ldg(&T.pinfo[pp[u]].cov_end);
         }
 #pragma unroll
@@ -268,7 +276,14 @@ __global__ void __launch_bounds__(FILT_BLOCK, 2) lsq_filter_kernel(FilterParams 
         for (int k = 0; k < FILT_ITEMS; ++k) {
             pp[k] = PIECE_NONE;
             if (st[k] == SP_GO) st[k] = block_stage_piece(T, q[k], be[k], pp[k]);
-            if (st[k] == SP_DEFER) pp[k] = lookup_direct(T, q[k].c, b0[k]) & PIECE_NONE;  // crowded bucket: searched
+        }
+#pragma unroll
+        for (int k = 0; k < FILT_ITEMS; ++k)  // crowded buckets (1 in 8 blocks): one more entry
+            if (st[k] == SP_SUB) be[k] = __ldg(T.bp_sub + q[k].slot);
+#pragma unroll
+        for (int k = 0; k < FILT_ITEMS; ++k) {
+            if (st[k] == SP_SUB) st[k] = block_stage_sub(T, q[k], be[k], pp[k]);
+            if (st[k] == SP_DEFER) pp[k] = lookup_direct(T, q[k].c, b0[k]) & PIECE_NONE;  // searched
             raw[k] = pp[k] != PIECE_NONE ? __ldg(reinterpret_cast<const uint4 *>(T.pinfo + pp[k])) : make_uint4(0u, 0u, 0u, 0u);
         }
 #pragma unroll

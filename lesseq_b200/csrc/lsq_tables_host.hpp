@@ -29,7 +29,7 @@ struct HostTables {
     std::vector<PieceInfo> pinfo;
     uint32_t bp_shift = 0;
     std::vector<uint32_t> bp_bkt_off;
-    std::vector<uint2> bp_bkt;
+    std::vector<uint2> bp_bkt, bp_sub;
     std::vector<uint4> chrom_meta;
     uint32_t bkt_shift = 9, n_bkt = 1, max_stab_n = 0;
     std::vector<uint32_t> bkt_piece;  // [n_bkt+1] first piece whose stab_off is >= b << bkt_shift
@@ -56,6 +56,7 @@ struct HostTables {
         T.bp_bkt_off = bp_bkt_off.data();
         T.chrom_meta = chrom_meta.data();
         T.bp_bkt = bp_bkt.data();
+        T.bp_sub = bp_sub.data();
         T.cov_off = cov_off.data();
         T.cov_start = cov_start.data();
         T.cov_end = cov_end.data();
@@ -68,13 +69,25 @@ struct HostTables {
 
 // Bucket index over per-chromosome sorted piece starts (CSR `off`): bucket b of a chromosome covers
 // positions [b << shift, (b+1) << shift).  Its entry holds the rank (global index) of the first
-// piece starting at or after b << shift and, packed into one word (bucket_word, lsq_types.cuh),
+// piece starting at or after b << shift and, packed into one word (lsq_types.cuh: bucket word),
 // the in-bucket offsets of the pieces that start inside it -- so the piece of a position is found
-// with ONE 8-byte load; only a bucket with more starts than fit the word falls back to a search.
+// with ONE 8-byte load.  A bucket with more starts than fit the word points to eight sub-buckets
+// of the same format (one more load); only a crowded sub-bucket falls back to a search.
 // One extra bucket per chromosome closes the last range.  The shift is chosen so that there are
 // about eight buckets per piece (at most 2^25): pieces cluster inside genes.
+inline uint32_t bucket_word(const std::vector<int32_t> &arr, uint32_t i, uint32_t hi, int64_t start, uint32_t shift,
+                            uint32_t &cnt) {
+    const int64_t end = start + ((int64_t)1 << shift);
+    uint32_t j = i;
+    while (j < hi && (int64_t)arr[j] < end) ++j;
+    cnt = j - i;
+    if (cnt > bucket_capacity(shift)) return BKT_MANY << 29;
+    uint32_t w = cnt << 29;
+    for (uint32_t t = 0; t < cnt; ++t) w |= (uint32_t)((int64_t)arr[i + t] - start) << (t * shift);
+    return w;
+}
 inline void build_bucket_index(const std::vector<int32_t> &arr, const std::vector<uint32_t> &off, uint32_t &shift,
-                               std::vector<uint32_t> &bkt_off, std::vector<uint2> &bkt) {
+                               std::vector<uint32_t> &bkt_off, std::vector<uint2> &bkt, std::vector<uint2> &sub) {
     const size_t nch = off.size() - 1;
     uint64_t span = 0;
     for (size_t c = 0; c < nch; ++c)
@@ -82,33 +95,39 @@ inline void build_bucket_index(const std::vector<int32_t> &arr, const std::vecto
     uint64_t want = std::min<uint64_t>(std::max<uint64_t>(8 * arr.size(), 1), 1ull << 25);
     shift = 0;
     while ((span >> shift) > want && shift < 30) ++shift;
-    const uint32_t K = bucket_capacity(shift);
+    const uint32_t ss = bucket_sub_shift(shift), n_sub = 1u << (shift - ss);
     bkt_off.assign(nch + 1, 0);
     bkt.clear();
+    sub.clear();
     for (size_t c = 0; c < nch; ++c) {
         bkt_off[c] = (uint32_t)bkt.size();
         uint32_t lo = off[c], hi = off[c + 1];
         uint32_t nb = hi > lo ? (uint32_t)(((uint64_t)std::max<int32_t>(arr[hi - 1], 0) >> shift) + 1) : 0;
         uint32_t i = lo;
         for (uint32_t b = 0; b <= nb; ++b) {  // nb + 1 entries: the last one is `hi`
-            const int64_t start = (int64_t)b << shift, end = start + ((int64_t)1 << shift);
+            const int64_t start = (int64_t)b << shift;
             while (i < hi && (int64_t)arr[i] < start) ++i;
             uint2 e = make_uint2(b == nb ? hi : i, 0u);
             if (b < nb) {
-                uint32_t j = i;
-                while (j < hi && (int64_t)arr[j] < end) ++j;
-                const uint32_t cnt = j - i;
-                if (cnt > K) {
-                    e.y = BKT_MANY << 29;
-                } else {
-                    e.y = cnt << 29;
-                    for (uint32_t t = 0; t < cnt; ++t) e.y |= (uint32_t)((int64_t)arr[i + t] - start) << (t * shift);
+                uint32_t cnt;
+                e.y = bucket_word(arr, i, hi, start, shift, cnt);
+                if (bucket_many(e.y)) {
+                    e.y |= (uint32_t)sub.size();  // < 2^29: there are at most 2^25 buckets of 8 sub-buckets
+                    uint32_t i2 = i;
+                    for (uint32_t t = 0; t < n_sub; ++t) {
+                        const int64_t s2 = start + ((int64_t)t << ss);
+                        while (i2 < hi && (int64_t)arr[i2] < s2) ++i2;
+                        uint32_t c2;
+                        const uint32_t w2 = bucket_word(arr, i2, hi, s2, ss, c2);
+                        sub.push_back(make_uint2(i2, w2));
+                    }
                 }
             }
             bkt.push_back(e);
         }
     }
     bkt_off[nch] = (uint32_t)bkt.size();
+    if (sub.empty()) sub.push_back(make_uint2(0u, 0u));
 }
 
 inline int tfail(std::string &err, int code, const std::string &msg) {
@@ -372,7 +391,7 @@ inline int build_host_tables(const lsq_event_tables *t, HostTables &H, std::stri
     H.cov_start.assign(t->cov_start, t->cov_start + H.cov_off.back());
     H.cov_end.assign(t->cov_end, t->cov_end + H.cov_off.back());
     H.tie.assign(tie_pool.begin(), tie_pool.end());
-    build_bucket_index(H.bp_pos, H.bp_chrom_off, H.bp_shift, H.bp_bkt_off, H.bp_bkt);
+    build_bucket_index(H.bp_pos, H.bp_chrom_off, H.bp_shift, H.bp_bkt_off, H.bp_bkt, H.bp_sub);
     H.chrom_meta.resize(std::max<uint32_t>(t->n_chroms, 1));
     for (uint32_t ch = 0; ch < t->n_chroms; ++ch)
         H.chrom_meta[ch] = make_uint4(H.bp_chrom_off[ch], H.bp_chrom_off[ch + 1], H.bp_bkt_off[ch],

@@ -135,24 +135,31 @@ struct Tables {
     const uint2 *bp_bkt;           // [buckets + n_chroms] x: rank of the first piece starting in or after the bucket,
                                    // y: the piece starts inside the bucket (bucket_word), so the piece of a
                                    // position comes from ONE 8-byte load
+    const uint2 *bp_sub;           // sub-buckets of the crowded buckets (same entry format, bucket_sub_shift)
     // stab buckets (PartState): bucket of piece p = stab_off[p] >> bkt_shift
     uint32_t bkt_shift, n_bkt;
     const uint32_t *bkt_piece;     // [n_bkt+1] first piece whose stab_off is >= b << bkt_shift
 };
 
-// Bucket word: bits 29-31 = number of piece starts inside the bucket (BKT_MANY: more than fit), then
-// bucket_capacity(shift) offsets of `shift` bits each (start - bucket start), ascending.
+// Bucket word: bits 29-31 = number of piece starts inside the bucket, then bucket_capacity(shift)
+// offsets of `shift` bits each (start - bucket start), ascending.  A bucket with more starts than fit
+// (BKT_MANY) keeps in bits 0-28 the index of its 2^(shift - sub_shift) sub-buckets in bp_sub[], which
+// have the same entry format over 2^sub_shift positions each; only a crowded SUB-bucket needs a search.
 constexpr uint32_t BKT_MANY = 7u;
 LSQ_TYPES_HD uint32_t bucket_capacity(uint32_t shift) {
     return shift == 0u ? 4u : (29u / shift < 4u ? 29u / shift : 4u);
 }
-// Number of piece starts at or below in-bucket offset xo, or 0xFFFFFFFF when the bucket is crowded.
+LSQ_TYPES_HD uint32_t bucket_sub_shift(uint32_t shift) { return shift > 3u ? shift - 3u : 0u; }
+LSQ_TYPES_HD bool bucket_many(uint32_t w) { return (w >> 29) == BKT_MANY; }
+// Number of piece starts at or below in-bucket offset xo (the word is not BKT_MANY).  Branch-free:
+// every lane of a warp takes the same four compares.
 LSQ_TYPES_HD uint32_t bucket_rank(uint32_t shift, uint32_t w, uint32_t xo) {
-    const uint32_t cnt = w >> 29;
-    if (cnt == BKT_MANY) return 0xFFFFFFFFu;
-    const uint32_t mask = (1u << shift) - 1u;
-    uint32_t n = 0;
-    for (uint32_t t = 0; t < cnt; ++t) n += xo >= ((w >> (t * shift)) & mask) ? 1u : 0u;
+    const uint32_t cnt = w >> 29, mask = (1u << shift) - 1u;
+    const uint32_t s2 = 2u * shift < 31u ? 2u * shift : 31u, s3 = 3u * shift < 31u ? 3u * shift : 31u;
+    uint32_t n = (cnt > 0u && xo >= (w & mask)) ? 1u : 0u;
+    n += (cnt > 1u && xo >= ((w >> shift) & mask)) ? 1u : 0u;
+    n += (cnt > 2u && xo >= ((w >> s2) & mask)) ? 1u : 0u;
+    n += (cnt > 3u && xo >= ((w >> s3) & mask)) ? 1u : 0u;
     return n;
 }
 

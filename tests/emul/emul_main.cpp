@@ -35,8 +35,105 @@ static double class_prob_h(uint64_t mk, const double *theta, const double *G) {
     return s;
 }
 
+// Self-test of the piece lookup (two-level bucket index of lsq_tables_host.hpp / find_piece and the
+// staged block_lookup of lsq_device_fn.cuh) against a linear scan, on clustered piece starts that
+// force large bucket shifts, crowded buckets and crowded sub-buckets.
+static int bucket_selftest(unsigned seed) {
+    uint64_t st = seed * 0x9E3779B97F4A7C15ull + 1;
+    auto rnd = [&](uint32_t n) {
+        st = st * 6364136223846793005ull + 1442695040888963407ull;
+        return (uint32_t)((st >> 33) % n);
+    };
+    const uint32_t nch = 1 + rnd(3);
+    std::vector<int32_t> pos;
+    std::vector<uint32_t> off(nch + 1, 0);
+    const uint32_t gap_scale = 1u << rnd(24);
+    for (uint32_t c = 0; c < nch; ++c) {
+        off[c] = (uint32_t)pos.size();
+        int32_t x = (int32_t)rnd(1000) - (rnd(4) == 0 ? 300 : 0);
+        const uint32_t clusters = 1 + rnd(60);
+        for (uint32_t k = 0; k < clusters; ++k) {
+            const uint32_t m = 1 + rnd(40), step = 1 + rnd(rnd(2) ? 3 : 40);
+            for (uint32_t i = 0; i < m; ++i) {
+                pos.push_back(x);
+                x += 1 + (int32_t)rnd(step);
+            }
+            x += (int32_t)rnd(gap_scale + 1);
+        }
+    }
+    off[nch] = (uint32_t)pos.size();
+    uint32_t shift = 0;
+    std::vector<uint32_t> bkt_off;
+    std::vector<uint2> bkt, sub;
+    build_bucket_index(pos, off, shift, bkt_off, bkt, sub);
+    std::vector<PieceInfo> pinfo(pos.size() + 1);
+    for (size_t i = 0; i < pos.size(); ++i) {
+        pinfo[i].pos = pos[i];
+        pinfo[i].cov_end = (i % 3) ? pos[i] + 50 : INT32_MIN;
+        pinfo[i].stab_off = (uint32_t)i;
+        pinfo[i].stab_n = 1;
+    }
+    std::vector<uint4> meta(nch);
+    std::vector<uint32_t> remap(nch);
+    for (uint32_t c = 0; c < nch; ++c) {
+        meta[c] = make_uint4(off[c], off[c + 1], bkt_off[c], bkt_off[c + 1] - bkt_off[c] - 1u);
+        remap[c] = c;
+    }
+    FilterParams P{};
+    P.T.bp_shift = shift;
+    P.T.bp_bkt = bkt.data();
+    P.T.bp_sub = sub.data();
+    P.T.pinfo = pinfo.data();
+    P.T.chrom_meta = meta.data();
+    P.chrom_remap = remap.data();
+    size_t checked = 0;
+    for (uint32_t c = 0; c < nch; ++c) {
+        const uint32_t lo = off[c], hi = off[c + 1];
+        if (lo == hi) continue;
+        const int32_t x0 = pos[lo] - 20, x1 = pos[hi - 1] + 2000;
+        const int32_t stride = (x1 - x0) > 4000000 ? 1 + (x1 - x0) / 4000000 : 1;
+        auto check = [&](int32_t x) {
+            uint32_t want = 0xFFFFFFFFu;  // last piece with pos <= x
+            {
+                uint32_t a = lo, b = hi;
+                while (a < b) {
+                    const uint32_t mid = (a + b) >> 1;
+                    if (pos[mid] <= x) a = mid + 1;
+                    else b = mid;
+                }
+                if (a > lo) want = a - 1;
+            }
+            PieceInfo pi;
+            const uint32_t got = find_piece(P.T, c, x, pi);
+            const int2 blk = make_int2(x, x + 30);
+            const uint32_t r1 = block_lookup(P, blk, c), r2 = lookup_direct(P.T, c, blk);
+            const uint32_t wr = want == 0xFFFFFFFFu ? PIECE_NONE : (want | (pinfo[want].cov_end >= x + 30 ? 0x80000000u : 0u));
+            if (got != want || r1 != wr || r2 != wr) {
+                fprintf(stderr, "bucket selftest: seed %u chrom %u x %d shift %u: find_piece %u, block_lookup %x, direct %x, want %u / %x\n",
+                        seed, c, x, shift, got, r1, r2, want, wr);
+                return false;
+            }
+            ++checked;
+            return true;
+        };
+        for (int32_t x = x0; x <= x1; x += stride)
+            if (!check(x)) return 1;
+        for (uint32_t i = lo; i < hi; ++i)  // every piece start and its neighbours
+            for (int32_t d = -1; d <= 1; ++d)
+                if (!check(pos[i] + d)) return 1;
+    }
+    printf("ok seed %u shift %u pieces %zu buckets %zu sub %zu checked %zu\n", seed, shift, pos.size(), bkt.size(), sub.size(), checked);
+    return 0;
+}
+
 int main(int argc, char **argv) {
     if (argc < 2) return 2;
+    if (std::string(argv[1]) == "bucket-selftest") {
+        const unsigned n = argc > 2 ? (unsigned)atoi(argv[2]) : 50;
+        for (unsigned seed = 1; seed <= n; ++seed)
+            if (bucket_selftest(seed)) return 1;
+        return 0;
+    }
     const bool solve = std::string(argv[1]) == "solve";
     argv += 1;
     argc -= 1;

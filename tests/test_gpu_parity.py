@@ -59,7 +59,7 @@ def test_abi_matches_reference_golden_fuzz(api, tmp_path):
     """The 80 fuzz + 40 weird-annotation fixtures (reference binary outputs) through the ctypes mirror of the C ABI in
     one process: count tables identical, solve tables within tolerance."""
     ctx = api.Context(0)
-    for case in FUZZ_CASES:
+    for ci, case in enumerate(FUZZ_CASES):
         d = tmp_path / case["name"]
         d.mkdir()
         ca, sa = golden_util.materialise(case, str(d))
@@ -73,7 +73,8 @@ def test_abi_matches_reference_golden_fuzz(api, tmp_path):
         ctx.upload_events(ann)
         M = len(case["sets"])
         for m, s in enumerate(case["sets"]):
-            ctx.set_reads(m, s["type"], s["read_length"], api.Reads.from_mrf(d / ("r%d.mrf" % m)))
+            # every other case goes through the compact wire format (lsqh_reads_compact)
+            ctx.set_reads(m, s["type"], s["read_length"], api.Reads.from_mrf(d / ("r%d.mrf" % m), compact=ci % 2 == 1))
         ctx.count()
         cnt = ctx.get_count()
         ctx.solve([s["total_read_bases"] for s in case["sets"]])
@@ -249,9 +250,9 @@ def test_device_resident_reads_and_properties(api, tmp_path):
 
 
 def test_streamed_host_reads_match_resident(api, tmp_path):
-    """LSQ_READS_STREAM: the filter consumes blk[] while the copy engine is still filling it.  Results
-    must be identical to the device-resident run, for a set large enough to take many chunks, a tiny
-    one, and when the same context streams twice in a row."""
+    """LSQ_READS_STREAM: the filter consumes blk[] while the copy engine is still filling it, from the
+    wide or the compact wire format.  Results must be identical to the device-resident run, for a set
+    large enough to take many chunks, a tiny one, and when the same context streams repeatedly."""
     import torch
     from lesseq_b200 import synth
     A, R, _ = synth.make_config("C2", n_genes=2000)
@@ -269,14 +270,25 @@ def test_streamed_host_reads_match_resident(api, tmp_path):
         cnt = (rd["blk_off"][1:] - rd["blk_off"][:-1]).to(torch.uint8)
         host = {k: rd[k].cpu().pin_memory() for k in ("blk", "read_cs")}
         host["blk_cnt"] = cnt.cpu().pin_memory()
+        b2 = rd["blk"].view(-1, 2)
+        cs = rd["read_cs"]
+        host["blk_start"] = b2[:, 0].contiguous().cpu().pin_memory()
+        host["blk_len"] = (b2[:, 1] - b2[:, 0]).to(torch.int16).cpu().pin_memory()
+        host["read_cs8"] = ((cs & 0x3F) | (((cs >> 16) & 1) << 6) | (((cs >> 31) & 1) << 7)).to(torch.uint8).cpu().pin_memory()
         for stream in (True, False):
-            hr = api.Reads.from_torch(None, host["blk"], host["read_cs"], None, rd["chrom_names"], rd["strand_names"],
-                                      blk_cnt=host["blk_cnt"], stream=stream)
-            ctx.set_reads(0, "SHORT_READ", R, hr)
-            ctx.count()
-            got = ctx.get_count()
-            for k in ref:
-                assert np.array_equal(ref[k], got[k]), "streamed=%s n=%d: %s differs" % (stream, n, k)
+            for compact in (False, True):
+                if compact:
+                    hr = api.Reads.from_torch(None, None, None, None, rd["chrom_names"], rd["strand_names"],
+                                              blk_cnt=host["blk_cnt"], stream=stream, read_cs8=host["read_cs8"],
+                                              blk_start=host["blk_start"], blk_len=host["blk_len"])
+                else:
+                    hr = api.Reads.from_torch(None, host["blk"], host["read_cs"], None, rd["chrom_names"],
+                                              rd["strand_names"], blk_cnt=host["blk_cnt"], stream=stream)
+                ctx.set_reads(0, "SHORT_READ", R, hr)
+                ctx.count()
+                got = ctx.get_count()
+                for k in ref:
+                    assert np.array_equal(ref[k], got[k]), "streamed=%s compact=%s n=%d: %s differs" % (stream, compact, n, k)
     ctx.close()
 
 

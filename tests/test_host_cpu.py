@@ -232,3 +232,52 @@ def test_parallel_mrf_parser_matches_serial(built_lib, tmp_path):
     assert a[0] == b[0] and a[1] == b[1] and a[6] == b[6] and a[7] == b[7]
     for x, y in zip(a[2:6], b[2:6]):
         assert np.array_equal(x, y)
+
+
+def test_piece_lookup_bucket_index_selftest(emul_bin):
+    """Two-level bucket index (lsq_tables_host.hpp) + find_piece / staged block_lookup
+    (lsq_device_fn.cuh) against a binary search over the piece starts: clustered starts, bucket
+    shifts 0..15, crowded buckets and sub-buckets, positions before/after every chromosome."""
+    p = subprocess.run([emul_bin, "bucket-selftest", "120"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr[-2000:]
+    shifts = {int(line.split()[4]) for line in p.stdout.splitlines() if line.startswith("ok")}
+    assert len(shifts) >= 10 and max(shifts) >= 12
+
+
+def test_compact_wire_format_is_lossless(tmp_path):
+    """lsqh_reads_compact: blk_cnt / read_cs8 / blk_start + blk_len expand to the wide arrays."""
+    import ctypes as C
+    import numpy as np
+    from lesseq_b200 import api, _lib
+    path = tmp_path / "r.mrf"
+    rows = ["# comment", "AlignmentBlocks"]
+    rng = np.random.default_rng(3)
+    for i in range(3000):
+        nb = int(rng.integers(1, 5))
+        s = int(rng.integers(1, 10 ** 6))
+        blocks = []
+        for _ in range(nb):
+            ln = int(rng.integers(1, 300))
+            chrom = "chr%d" % rng.integers(1, 25) if rng.random() < 0.02 else "chr%d" % (1 + i % 24)
+            blocks.append("%s:%s:%d:%d:1:%d" % (chrom, "+-"[i % 2], s, s + ln - 1, ln))
+            s += ln + int(rng.integers(0, 5000))
+        rows.append(",".join(blocks))
+    path.write_text("\n".join(rows) + "\n")
+    wide = api.Reads.from_mrf(str(path))
+    comp = api.Reads.from_mrf(str(path), compact=True)
+    v, w = comp.view, wide.view
+    n, nb = comp.n_reads, comp.n_blocks
+    assert (n, nb) == (wide.n_reads, wide.n_blocks) and v.blk_cnt and v.read_cs8 and v.blk_start and v.blk_len
+
+    def arr(ptr, ctype, count):
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(count,)).copy()
+    off = arr(w.blk_off, C.c_uint32, n + 1)
+    blk = arr(w.blk, C.c_int32, 2 * nb).reshape(-1, 2)
+    cs = arr(w.read_cs, C.c_uint32, n)
+    assert np.array_equal(arr(v.blk_cnt, C.c_uint8, n), np.diff(off))
+    assert np.array_equal(arr(v.blk_start, C.c_int32, nb), blk[:, 0])
+    assert np.array_equal(arr(v.blk_len, C.c_uint16, nb).astype(np.int64), blk[:, 1].astype(np.int64) - blk[:, 0])
+    cs8 = arr(v.read_cs8, C.c_uint8, n).astype(np.uint32)
+    assert np.array_equal((cs8 & 0x3F) | ((cs8 & 0x40) << 10) | ((cs8 & 0x80) << 24), cs)
+    assert (cs & _lib.LSQ_READ_MIXED).any()
+    assert comp.host_bytes() < 0.75 * wide.host_bytes()
