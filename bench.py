@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--genes", type=int, default=None)
     ap.add_argument("--sample-reads", type=int, default=300000, help="reads of the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--wide-wire", action="store_true", help="e2e: wide arrays (blk, read_cs) instead of the compact wire format")
+    ap.add_argument("--no-stream", action="store_true", help="e2e: copy everything before the filter starts (no LSQ_READS_STREAM)")
     return ap.parse_args()
 
 
@@ -350,7 +352,9 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": total_reads / (e2e_ms / 1000.0), "unit": UNIT,
                     "h2d_bytes_per_step": int(host_reads.host_bytes()), "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms},
+                    "ms_per_step": e2e_ms,
+                    "wire": ("compact (blk_cnt u8, read_cs8, blk_start i32 + blk_len u16)" if compact_ok else "blk_cnt u8 + wide blk/read_cs") +
+                            (", copy overlapped with the filter (LSQ_READS_STREAM)" if not args.no_stream else "")},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "lsq_filter_kernel (1 launch per step, %.0f%% of the step)" % (100.0 * fk_ms / ms),
                          "achieved": achieved, "peak": peak,
