@@ -628,7 +628,7 @@ int lsq_count(lsq_ctx *c) {
             LSQ_CUDA(cudaEventRecord(c->ev[1], s));
             lsq::lsq_filter_kernel<<<(unsigned)((n + lsq::FILT_TILE - 1) / lsq::FILT_TILE), lsq::FILT_BLOCK, filt_smem, s>>>(FP);
             LSQ_CUDA(cudaGetLastError());
-            lsq::lsq_part_stats_kernel<<<1, 256, 0, s>>>(PS, T.n_bkt, counters);
+            lsq::lsq_part_stats_kernel<<<(PS.n_bins + 255) / 256, 256, 0, s>>>(PS, T.n_bkt, counters);
             LSQ_CUDA(cudaGetLastError());
             tm.launches += 3;
         } else {

@@ -156,10 +156,11 @@ LSQ_TYPES_HD bool bucket_many(uint32_t w) { return (w >> 29) == BKT_MANY; }
 LSQ_TYPES_HD uint32_t bucket_rank(uint32_t shift, uint32_t w, uint32_t xo) {
     const uint32_t cnt = w >> 29, mask = (1u << shift) - 1u;
     const uint32_t s2 = 2u * shift < 31u ? 2u * shift : 31u, s3 = 3u * shift < 31u ? 3u * shift : 31u;
-    uint32_t n = (cnt > 0u && xo >= (w & mask)) ? 1u : 0u;
-    n += (cnt > 1u && xo >= ((w >> shift) & mask)) ? 1u : 0u;
-    n += (cnt > 2u && xo >= ((w >> s2) & mask)) ? 1u : 0u;
-    n += (cnt > 3u && xo >= ((w >> s3) & mask)) ? 1u : 0u;
+    // offsets ascend, so the tests are nested: bitwise ands keep the four compares free of branches
+    uint32_t n = (uint32_t)(cnt > 0u) & (uint32_t)(xo >= (w & mask));
+    n += (uint32_t)(cnt > 1u) & (uint32_t)(xo >= ((w >> shift) & mask));
+    n += (uint32_t)(cnt > 2u) & (uint32_t)(xo >= ((w >> s2) & mask));
+    n += (uint32_t)(cnt > 3u) & (uint32_t)(xo >= ((w >> s3) & mask));
     return n;
 }
 
