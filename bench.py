@@ -289,12 +289,13 @@ def run_ours(args):
         int((b2[:, 1] - b2[:, 0]).max()) < 65536 and int((b2[:, 1] - b2[:, 0]).min()) >= 0 and not args.wide_wire
     if compact_ok:
         cs8 = ((cs & 0x3F) | (((cs >> 16) & 1) << 6) | (((cs >> 31) & 1) << 7)).to(torch.uint8)
+        len8 = int((b2[:, 1] - b2[:, 0]).max()) < 256  # short reads: one byte per block length
         pinned = {"blk_start": b2[:, 0].contiguous().cpu().pin_memory(),
-                  "blk_len": (b2[:, 1] - b2[:, 0]).to(torch.int16).cpu().pin_memory(),  # bit pattern of u16
+                  "blk_len": (b2[:, 1] - b2[:, 0]).to(torch.uint8 if len8 else torch.int16).cpu().pin_memory(),  # u8 / bits of u16
                   "read_cs8": cs8.cpu().pin_memory(), "blk_cnt": blk_cnt.cpu().pin_memory()}
         host_reads = api.Reads.from_torch(None, None, None, None, reads["chrom_names"], reads["strand_names"],
                                           blk_cnt=pinned["blk_cnt"], stream=not args.no_stream, read_cs8=pinned["read_cs8"],
-                                          blk_start=pinned["blk_start"], blk_len=pinned["blk_len"])
+                                          blk_start=pinned["blk_start"], **{"blk_len8" if len8 else "blk_len": pinned["blk_len"]})
     else:
         pinned = {"blk": reads["blk"].cpu().pin_memory(), "read_cs": reads["read_cs"].cpu().pin_memory(),
                   "blk_cnt": blk_cnt.cpu().pin_memory()}
@@ -353,7 +354,7 @@ def run_ours(args):
             "e2e": {"value": total_reads / (e2e_ms / 1000.0), "unit": UNIT,
                     "h2d_bytes_per_step": int(host_reads.host_bytes()), "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms,
-                    "wire": ("compact (blk_cnt u8, read_cs8, blk_start i32 + blk_len u16)" if compact_ok else "blk_cnt u8 + wide blk/read_cs") +
+                    "wire": ("compact (blk_cnt u8, read_cs8 u8, blk_start i32 + blk_len u8/u16)" if compact_ok else "blk_cnt u8 + wide blk/read_cs") +
                             (", copy overlapped with the filter (LSQ_READS_STREAM)" if not args.no_stream else "")},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "lsq_filter_kernel (1 launch per step, %.0f%% of the step)" % (100.0 * fk_ms / ms),

@@ -133,6 +133,7 @@ typedef struct lsq_packed_reads {
                                   id (< 2), bit 7 MIXED (per-block values in blk_cs) */
     const int32_t *blk_start;  /* [n_blocks] with blk_len: alternative to blk -- start0 of every block ... */
     const uint16_t *blk_len;   /* [n_blocks] ... and end - start0 (< 65536) */
+    const uint8_t *blk_len8;   /* [n_blocks] instead of blk_len when every block is shorter than 256 (short reads) */
 } lsq_packed_reads;
 
 /* Results of the counted path (count.cpp:421-492, solve.cpp:719-793), caller-owned host buffers. */

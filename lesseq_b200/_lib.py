@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "lib", "liblesseq_b200.so")
+LIB_PATH = os.environ.get("LESSEQ_B200_LIB") or os.path.join(PKG, "lib", "liblesseq_b200.so")  # env: tuning builds only
 
 LSQ_READ_MEDIUM = 1
 LSQ_READ_SHORT = 2
@@ -45,7 +45,7 @@ class PackedReads(C.Structure):
         ("n_chrom_names", C.c_uint32), ("n_strand_names", C.c_uint32),
         ("chrom_names", c_strp), ("strand_names", c_strp),
         ("on_device", C.c_uint32), ("flags", C.c_uint32),
-        ("blk_cnt", C.c_void_p), ("read_cs8", C.c_void_p), ("blk_start", C.c_void_p), ("blk_len", C.c_void_p),
+        ("blk_cnt", C.c_void_p), ("read_cs8", C.c_void_p), ("blk_start", C.c_void_p), ("blk_len", C.c_void_p), ("blk_len8", C.c_void_p),
     ]
 
 

@@ -151,12 +151,12 @@ class Reads:
 
     @classmethod
     def from_torch(cls, blk_off, blk, read_cs, line_num, chrom_names, strand_names, blk_cs=None, blk_cnt=None,
-                   stream=False, read_cs8=None, blk_start=None, blk_len=None):
+                   stream=False, read_cs8=None, blk_start=None, blk_len=None, blk_len8=None):
         """Tensors must be contiguous int32 (bit patterns of the uint32 fields; blk_cnt uint8); CUDA
         tensors are borrowed (on_device=1), CPU tensors (pinned or not) are host buffers.  Compact
         wire format: pass blk_off=None with blk_cnt (blocks per read) and/or line_num=None (implicit
         1..n); read_cs8 (uint8) instead of read_cs; blk_start (int32) + blk_len (int16 bit patterns of
-        uint16) instead of blk.  stream=True (host tensors): LSQ_READS_STREAM, the copy overlaps the
+        uint16) or blk_len8 (uint8) instead of blk.  stream=True (host tensors): LSQ_READS_STREAM, the copy overlaps the
         next count()."""
         self = cls()
         ts = [t for t in (blk_off, blk, read_cs, line_num, blk_cs, blk_start) if t is not None]
@@ -177,6 +177,11 @@ class Reads:
             assert blk_len.is_cuda == dev and blk_len.numel() == blk_start.numel()
             ts.append(blk_len)
             self.view.blk_start, self.view.blk_len = blk_start.data_ptr(), blk_len.data_ptr()
+        if blk_len8 is not None:  # one byte per block length (every block shorter than 256)
+            assert blk_start is not None and blk_len8.is_contiguous() and blk_len8.element_size() == 1
+            assert blk_len8.is_cuda == dev and blk_len8.numel() == blk_start.numel()
+            ts.append(blk_len8)
+            self.view.blk_start, self.view.blk_len8 = blk_start.data_ptr(), blk_len8.data_ptr()
         self._keep += ts
         v = self.view
         v.n_reads = (read_cs if read_cs is not None else read_cs8).numel()
@@ -204,7 +209,7 @@ class Reads:
         """Bytes lsq_set_reads copies host->device for this read set."""
         n, nb = self.n_reads, self.n_blocks
         v = self.view
-        return ((n if v.blk_cnt else (n + 1) * 4) + (nb * 6 if v.blk_len else nb * 8) + (n if v.read_cs8 else n * 4) +
+        return ((n if v.blk_cnt else (n + 1) * 4) + (nb * 5 if v.blk_len8 else nb * 6 if v.blk_len else nb * 8) + (n if v.read_cs8 else n * 4) +
                 (n * 4 if v.line_num else 0))
 
 

@@ -115,6 +115,7 @@ int lsqh_reads_view(const lsqh_reads *r, lsq_packed_reads *v) {
     if (r->blk_len.size() == r->blk_cs.size() && !r->blk_len.empty()) {
         v->blk_start = r->blk_start.data();
         v->blk_len = r->blk_len.data();
+        if (r->blk_len8.size() == r->blk_len.size()) v->blk_len8 = r->blk_len8.data();
     }
     return LSQ_OK;
 }

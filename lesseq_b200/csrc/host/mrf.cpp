@@ -256,6 +256,7 @@ void compact_reads(lsqh_reads &R) {
     R.read_cs8.clear();
     R.blk_start.clear();
     R.blk_len.clear();
+    R.blk_len8.clear();
     bool ok = true;
     R.blk_cnt.resize(n);
     for (size_t i = 0; i < n && ok; ++i) {
@@ -283,6 +284,13 @@ void compact_reads(lsqh_reads &R) {
     if (!ok) {
         R.blk_start.clear();
         R.blk_len.clear();
+        return;
+    }
+    uint16_t longest = 0;
+    for (uint16_t l : R.blk_len) longest = std::max(longest, l);
+    if (longest < 256 && nb) {  // short reads: one byte per block length
+        R.blk_len8.resize(nb);
+        for (size_t b = 0; b < nb; ++b) R.blk_len8[b] = (uint8_t)R.blk_len[b];
     }
 }
 

@@ -12,7 +12,7 @@ struct lsqh_reads {
     std::vector<int32_t> blk;
     bool any_mixed = false;
     // compact wire format (lsqh_reads_compact); empty when not derived or when a value does not fit
-    std::vector<uint8_t> blk_cnt, read_cs8;
+    std::vector<uint8_t> blk_cnt, read_cs8, blk_len8;
     std::vector<int32_t> blk_start;
     std::vector<uint16_t> blk_len;
     std::vector<const char *> chrom_ptrs, strand_ptrs;

@@ -82,6 +82,7 @@ struct ReadSet {
     const uint8_t *read_cs8 = nullptr;  // compact wire format
     const int32_t *blk_start = nullptr;
     const uint16_t *blk_len = nullptr;
+    const uint8_t *blk_len8 = nullptr;
     DevBuf d_chrom_remap, d_strand_tbl;
     // injected classes (output order CSR)
     DevBuf d_inj_off, d_inj_mask, d_inj_cnt;
@@ -306,8 +307,9 @@ int lsq_set_reads(lsq_ctx *c, uint32_t m, uint32_t read_type, uint64_t read_leng
     rs.borrowed = r->on_device != 0;
     rs.streamed = !rs.borrowed && (r->flags & LSQ_READS_STREAM) != 0 && r->n_blocks > 0;
     if (!r->blk_off && !r->blk_cnt) return fail(LSQ_ERR_ARG, "lsq_set_reads: blk_off or blk_cnt is required");
-    const bool compact_blk = r->blk_start != nullptr && r->blk_len != nullptr;
-    if (!compact_blk && !r->blk && r->n_blocks) return fail(LSQ_ERR_ARG, "lsq_set_reads: blk or blk_start + blk_len is required");
+    const bool compact_blk = r->blk_start != nullptr && (r->blk_len != nullptr || r->blk_len8 != nullptr);
+    const bool len8 = compact_blk && r->blk_len8 != nullptr;
+    if (!compact_blk && !r->blk && r->n_blocks) return fail(LSQ_ERR_ARG, "lsq_set_reads: blk or blk_start + blk_len/blk_len8 is required");
     if (!r->read_cs && !r->read_cs8 && r->n_reads) return fail(LSQ_ERR_ARG, "lsq_set_reads: read_cs or read_cs8 is required");
     if (r->read_cs8 && (r->n_chrom_names > 64 || r->n_strand_names > 2))
         return fail(LSQ_ERR_RANGE, "read_cs8 holds 64 chromosome and 2 strand ids at most");
@@ -317,6 +319,7 @@ int lsq_set_reads(lsq_ctx *c, uint32_t m, uint32_t read_type, uint64_t read_leng
         rs.blk = nullptr;
         rs.blk_start = nullptr;
         rs.blk_len = nullptr;
+        rs.blk_len8 = nullptr;
         rs.read_cs = nullptr;
         rs.read_cs8 = nullptr;
         rs.blk_cs = nullptr;
@@ -326,7 +329,8 @@ int lsq_set_reads(lsq_ctx *c, uint32_t m, uint32_t read_type, uint64_t read_leng
         if (rs.borrowed) {
             if (compact_blk) {
                 rs.blk_start = r->blk_start;
-                rs.blk_len = r->blk_len;
+                if (len8) rs.blk_len8 = r->blk_len8;
+                else rs.blk_len = r->blk_len;
             } else {
                 rs.blk = reinterpret_cast<const int2 *>(r->blk);
             }
@@ -342,9 +346,10 @@ int lsq_set_reads(lsq_ctx *c, uint32_t m, uint32_t read_type, uint64_t read_leng
             // compute stream only waits for the per-read arrays and the filter kernel polls the progress word.
             if (compact_blk) {
                 LSQ_CUDA(rs.d_blk_start.ensure(std::max<size_t>(nb, 1) * 4));
-                LSQ_CUDA(rs.d_blk_len.ensure(std::max<size_t>(nb, 1) * 2));
+                LSQ_CUDA(rs.d_blk_len.ensure(std::max<size_t>(nb, 1) * (len8 ? 1 : 2)));
                 rs.blk_start = rs.d_blk_start.as<int32_t>();
-                rs.blk_len = rs.d_blk_len.as<uint16_t>();
+                if (len8) rs.blk_len8 = rs.d_blk_len.as<uint8_t>();
+                else rs.blk_len = rs.d_blk_len.as<uint16_t>();
             } else {
                 LSQ_CUDA(rs.d_blk.ensure(std::max<size_t>(nb, 1) * 8));
                 rs.blk = rs.d_blk.as<int2>();
@@ -391,7 +396,7 @@ int lsq_set_reads(lsq_ctx *c, uint32_t m, uint32_t read_type, uint64_t read_leng
             size_t chunk = std::max<size_t>(nb, 1);
             if (rs.streamed) {
                 chunk = std::max<size_t>(STREAM_MIN_CHUNK_BLOCKS, (nb + STREAM_MAX_CHUNKS - 1) / STREAM_MAX_CHUNKS);
-                chunk = (chunk + 63) & ~(size_t)63;  // whole 128-byte lines of every array: no line straddles two chunks
+                chunk = (chunk + 127) & ~(size_t)127;  // whole 128-byte lines of every array: no line straddles two chunks
             }
             uint32_t *hp = c->h_progress + (size_t)m * STREAM_MAX_CHUNKS;
             uint32_t k = 0;
@@ -399,7 +404,8 @@ int lsq_set_reads(lsq_ctx *c, uint32_t m, uint32_t read_type, uint64_t read_leng
                 const size_t b1 = std::min(nb, b0 + chunk);
                 if (compact_blk) {
                     LSQ_CUDA(cudaMemcpyAsync(rs.d_blk_start.as<int32_t>() + b0, r->blk_start + b0, (b1 - b0) * 4, kind, s));
-                    LSQ_CUDA(cudaMemcpyAsync(rs.d_blk_len.as<uint16_t>() + b0, r->blk_len + b0, (b1 - b0) * 2, kind, s));
+                    if (len8) LSQ_CUDA(cudaMemcpyAsync(rs.d_blk_len.as<uint8_t>() + b0, r->blk_len8 + b0, b1 - b0, kind, s));
+                    else LSQ_CUDA(cudaMemcpyAsync(rs.d_blk_len.as<uint16_t>() + b0, r->blk_len + b0, (b1 - b0) * 2, kind, s));
                 } else {
                     LSQ_CUDA(cudaMemcpyAsync(rs.d_blk.as<int2>() + b0, r->blk + 2 * b0, (b1 - b0) * 8, kind, s));
                 }
@@ -617,6 +623,7 @@ int lsq_count(lsq_ctx *c) {
             FP.read_cs8 = rs.read_cs8;
             FP.blk_start = rs.blk_start;
             FP.blk_len = rs.blk_len;
+            FP.blk_len8 = rs.blk_len8;
             FP.blk_cs = rs.blk_cs;
             FP.chrom_remap = rs.d_chrom_remap.as<uint32_t>();
             FP.progress = rs.streamed ? c->d_progress.as<uint32_t>() + m : nullptr;

@@ -220,16 +220,18 @@ constexpr uint32_t PIECE_NONE = 0x7FFFFFFFu;
 
 // Raw block i and the ids of read r, from the wide or the compact representation of the read set.
 LSQ_HD int2 load_block(const FilterParams &P, uint32_t i) {
-    if (P.blk_len != nullptr) {
+    if (P.blk_start != nullptr) {
         const int32_t s = LSQ_LD(P.blk_start + i);
-        return make_int2(s, s + (int32_t)LSQ_LD(P.blk_len + i));
+        const int32_t len = P.blk_len8 != nullptr ? (int32_t)LSQ_LD(P.blk_len8 + i) : (int32_t)LSQ_LD(P.blk_len + i);
+        return make_int2(s, s + len);
     }
     return LSQ_LD(P.blk + i);
 }
 LSQ_HD int2 load_block_stream(const FilterParams &P, uint32_t i) {
-    if (P.blk_len != nullptr) {
+    if (P.blk_start != nullptr) {
         const int32_t s = LSQ_LD_STREAM(P.blk_start + i);
-        return make_int2(s, s + (int32_t)LSQ_LD_STREAM(P.blk_len + i));
+        const int32_t len = P.blk_len8 != nullptr ? (int32_t)LSQ_LD_STREAM(P.blk_len8 + i) : (int32_t)LSQ_LD_STREAM(P.blk_len + i);
+        return make_int2(s, s + len);
     }
     return LSQ_LD_STREAM(P.blk + i);
 }

@@ -24,7 +24,10 @@ __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 constexpr int FILT_BLOCK = 512;
 constexpr int FILT_ITEMS = 4;                         // reads per thread (all kept in flight together)
 constexpr int FILT_LBATCH = 2;                        // block lookups of multi-block reads kept in flight per thread
-constexpr int FILT_RBATCH = 3;                        // bin reservations kept in flight per thread
+#ifndef LSQ_FILT_RBATCH
+#define LSQ_FILT_RBATCH 3
+#endif
+constexpr int FILT_RBATCH = LSQ_FILT_RBATCH;                        // bin reservations kept in flight per thread
 constexpr int FILT_TILE = FILT_BLOCK * FILT_ITEMS;    // 2048 reads
 constexpr int FILT_WREADS = 32 * FILT_ITEMS;          // 128 reads per warp
 constexpr int FILT_WBLK = 320;                        // raw blocks of a warp's reads whose lookups are staged
@@ -33,7 +36,7 @@ static_assert((uint32_t)FILT_TILE <= PART_CHUNK, "a tile's reservation may span 
 
 // dynamic shared memory of the filter kernel
 __host__ __device__ inline size_t filter_smem_bytes(uint32_t n_bins) {
-    return (size_t)FILT_TILE * (16 + 4 + 2 + 2) + (size_t)FILT_MAX_BLK * (4 + 2) + (size_t)n_bins * (4 + 4 + 2) + 64;  // <= 200 KB at PART_MAX_BINS
+    return (size_t)FILT_TILE * (16 + 4 + 2) + (size_t)FILT_MAX_BLK * (4 + 2) + (size_t)n_bins * (4 + 4 + 2) + 64;  // <= 200 KB at PART_MAX_BINS
 }
 
 // Read context of the filter kernel (see filter_read_t): blocks and piece records are fetched on
@@ -81,10 +84,9 @@ __global__ void lsq_part_init_kernel(PartState S, uint32_t n_bkt) {
 //          list, read class) with the staged answers.  Records of kept reads are staged in
 //          shared memory.
 // Then, block-wide:
-// Phase D: one thread per bin the tile has records for (listed on first use, so all reservations
-//          of a tile are in flight together) reserves room with a single 64-bit atomicAdd on
-//          (chunk, fill); the reservation that takes the last slot of a chunk installs the bin's
-//          spare chunk.
+// Phase D: one thread per non-empty bin reserves room for the tile's records of that bin with a
+//          single 64-bit atomicAdd on (chunk, fill); the reservation that takes the last slot of
+//          a chunk installs the bin's spare chunk.
 // Phase E: records go from shared memory to their slots (writes of one bin are contiguous; L2
 //          merges them into full sectors before they reach HBM).
 __global__ void __launch_bounds__(FILT_BLOCK, 2) lsq_filter_kernel(FilterParams P) {
@@ -97,15 +99,12 @@ __global__ void __launch_bounds__(FILT_BLOCK, 2) lsq_filter_kernel(FilterParams 
     uint32_t *s_blk_all = s_br + FILT_TILE;          // per warp and raw block: chromosome/strand ids, then the lookup answer
     uint32_t *s_A = s_blk_all + FILT_MAX_BLK;        // per bin: records of the tile, then first slot
     uint32_t *s_B = s_A + n_bins;                    // per bin: slot base after a chunk switch
-    uint32_t *s_nused = s_B + n_bins;                // number of bins the tile has records for (16-byte slot)
-    uint16_t *s_multi_all = reinterpret_cast<uint16_t *>(s_nused + 4);  // per warp: reads for filter_read_t (tile-local index)
-    uint16_t *s_used = s_multi_all + FILT_TILE;      // the bins the tile has records for, in order of first use
-    uint16_t *s_split = s_used + FILT_TILE;          // per bin: records before the chunk switch
+    uint16_t *s_multi_all = reinterpret_cast<uint16_t *>(s_B + n_bins);  // per warp: reads for filter_read_t (tile-local index)
+    uint16_t *s_split = s_multi_all + FILT_TILE;     // per bin: records before the chunk switch
     uint16_t *s_list_all = s_split + n_bins;         // per warp: raw blocks of the multi-block reads (warp-local index)
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     for (uint32_t i = tid; i < (n_bins + 3u) / 4u; i += FILT_BLOCK)  // may run into s_B, which is written before use
         reinterpret_cast<uint4 *>(s_A)[i] = make_uint4(0u, 0u, 0u, 0u);
-    if (tid == 0u) *s_nused = 0u;
     const uint64_t tile0 = (uint64_t)blockIdx.x * FILT_TILE;
     const uint64_t tile1 = min(tile0 + (uint64_t)FILT_TILE, P.n_reads);
     if (P.progress != nullptr && tid == 0u) {
@@ -252,7 +251,6 @@ __global__ void __launch_bounds__(FILT_BLOCK, 2) lsq_filter_kernel(FilterParams 
             }
             const uint32_t bin = cls * n_bkt + (so >> T.bkt_shift);
             const uint32_t rank = atomicAdd(&s_A[bin], 1u);
-            if (rank == 0u) s_used[atomicAdd(s_nused, 1u)] = (uint16_t)bin;  // first record of the tile in this bin
             s_rec[li] = rec;
             br = bin | (rank << 16);
         }
@@ -324,23 +322,21 @@ __global__ void __launch_bounds__(FILT_BLOCK, 2) lsq_filter_kernel(FilterParams 
     }
     __syncthreads();
     // ---- phase D --------------------------------------------------------------------------
-    const uint32_t n_used = *s_nused;
 #pragma unroll 1
-    for (uint32_t i0 = tid; i0 < n_used; i0 += FILT_BLOCK * FILT_RBATCH) {
-        uint32_t c[FILT_RBATCH], bins[FILT_RBATCH];
+    for (uint32_t b0 = tid; b0 < n_bins; b0 += FILT_BLOCK * FILT_RBATCH) {
+        uint32_t c[FILT_RBATCH];
         unsigned long long old[FILT_RBATCH];
 #pragma unroll
         for (int u = 0; u < FILT_RBATCH; ++u) {
-            const uint32_t i = i0 + (uint32_t)u * FILT_BLOCK;
-            bins[u] = i < n_used ? (uint32_t)s_used[i] : 0u;
-            c[u] = i < n_used ? s_A[bins[u]] : 0u;
+            const uint32_t bin = b0 + (uint32_t)u * FILT_BLOCK;
+            c[u] = bin < n_bins ? s_A[bin] : 0u;
             old[u] = 0ull;
-            if (c[u]) old[u] = atomicAdd(S.state + bins[u], (unsigned long long)c[u]);
+            if (c[u]) old[u] = atomicAdd(S.state + bin, (unsigned long long)c[u]);
         }
 #pragma unroll
         for (int u = 0; u < FILT_RBATCH; ++u) {
             if (!c[u]) continue;
-            const uint32_t bin = bins[u];
+            const uint32_t bin = b0 + (uint32_t)u * FILT_BLOCK;
             const uint32_t cls = (bin >= n_bkt ? 1u : 0u) + (bin >= 2u * n_bkt ? 1u : 0u);
             unsigned long long *st = S.state + bin;
             unsigned long long o = old[u];

@@ -176,6 +176,7 @@ struct FilterParams {
     const uint8_t *read_cs8;
     const int32_t *blk_start;
     const uint16_t *blk_len;
+    const uint8_t *blk_len8;      // instead of blk_len when every block is shorter than 256
     const uint32_t *progress;     // null, or: blocks of blk[] that have landed so far (streamed host->device copy)
     int2 *ext;                    // [n_blocks + 2 n_reads] worst case (header + blocks per general read)
     PartState part;

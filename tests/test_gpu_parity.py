@@ -274,13 +274,14 @@ def test_streamed_host_reads_match_resident(api, tmp_path):
         cs = rd["read_cs"]
         host["blk_start"] = b2[:, 0].contiguous().cpu().pin_memory()
         host["blk_len"] = (b2[:, 1] - b2[:, 0]).to(torch.int16).cpu().pin_memory()
+        host["blk_len8"] = (b2[:, 1] - b2[:, 0]).to(torch.uint8).cpu().pin_memory()  # 75-bp reads: every block < 256
         host["read_cs8"] = ((cs & 0x3F) | (((cs >> 16) & 1) << 6) | (((cs >> 31) & 1) << 7)).to(torch.uint8).cpu().pin_memory()
         for stream in (True, False):
-            for compact in (False, True):
+            for compact in (False, "blk_len", "blk_len8"):
                 if compact:
                     hr = api.Reads.from_torch(None, None, None, None, rd["chrom_names"], rd["strand_names"],
                                               blk_cnt=host["blk_cnt"], stream=stream, read_cs8=host["read_cs8"],
-                                              blk_start=host["blk_start"], blk_len=host["blk_len"])
+                                              blk_start=host["blk_start"], **{compact: host[compact]})
                 else:
                     hr = api.Reads.from_torch(None, host["blk"], host["read_cs"], None, rd["chrom_names"],
                                               rd["strand_names"], blk_cnt=host["blk_cnt"], stream=stream)

@@ -277,6 +277,12 @@ def test_compact_wire_format_is_lossless(tmp_path):
     assert np.array_equal(arr(v.blk_cnt, C.c_uint8, n), np.diff(off))
     assert np.array_equal(arr(v.blk_start, C.c_int32, nb), blk[:, 0])
     assert np.array_equal(arr(v.blk_len, C.c_uint16, nb).astype(np.int64), blk[:, 1].astype(np.int64) - blk[:, 0])
+    assert not v.blk_len8  # blocks of up to 299 bases do not fit a byte ...
+    short = tmp_path / "short.mrf"
+    short.write_text("AlignmentBlocks\n" + "\n".join("chr1:+:%d:%d:1:50" % (s, s + 49) for s in range(1, 400, 7)) + "\n")
+    sv = api.Reads.from_mrf(str(short), compact=True)  # ... 50-base blocks do
+    assert sv.view.blk_len8 and (arr(sv.view.blk_len8, C.c_uint8, sv.n_blocks) == 50).all()
+    assert sv.host_bytes() == sv.n_reads * (1 + 1 + 4) + sv.n_blocks * 5
     cs8 = arr(v.read_cs8, C.c_uint8, n).astype(np.uint32)
     assert np.array_equal((cs8 & 0x3F) | ((cs8 & 0x40) << 10) | ((cs8 & 0x80) << 24), cs)
     assert (cs & _lib.LSQ_READ_MIXED).any()
