@@ -83,7 +83,7 @@ struct ReadSet {
     const int32_t *blk_start = nullptr;
     const uint16_t *blk_len = nullptr;
     const uint8_t *blk_len8 = nullptr;
-    DevBuf d_chrom_remap, d_strand_tbl;
+    DevBuf d_chrom_remap, d_file_meta, d_strand_tbl;
     // injected classes (output order CSR)
     DevBuf d_inj_off, d_inj_mask, d_inj_cnt;
     std::vector<uint64_t> h_inj_off;
@@ -442,7 +442,11 @@ int lsq_set_reads(lsq_ctx *c, uint32_t m, uint32_t read_type, uint64_t read_leng
     }
     std::vector<uint8_t> tbl;
     lsq::strand_table(r->strand_names, r->n_strand_names, c->strand_names, tbl);
+    std::vector<uint4> fmeta(remap.size(), make_uint4(0u, 0u, 0u, 0u));
+    for (size_t i = 0; i < remap.size(); ++i)
+        if (remap[i] != 0xFFFFFFFFu) fmeta[i] = c->H.chrom_meta[remap[i]];
     LSQ_CUDA(upload(rs.d_chrom_remap, remap, s));
+    LSQ_CUDA(upload(rs.d_file_meta, fmeta, s));
     LSQ_CUDA(upload(rs.d_strand_tbl, tbl, s));
     LSQ_CUDA(cudaStreamSynchronize(s));
     c->M = std::max(c->M, m + 1);
@@ -626,6 +630,7 @@ int lsq_count(lsq_ctx *c) {
             FP.blk_len8 = rs.blk_len8;
             FP.blk_cs = rs.blk_cs;
             FP.chrom_remap = rs.d_chrom_remap.as<uint32_t>();
+            FP.file_meta = rs.d_file_meta.as<uint4>();
             FP.progress = rs.streamed ? c->d_progress.as<uint32_t>() + m : nullptr;
             FP.ext = c->d_ext.as<int2>();
             FP.part = PS;

@@ -409,7 +409,7 @@ LSQ_HD FilteredRead filter_read(const FilterParams &P, uint64_t r) {
 constexpr int SP_DROP = 0, SP_GO = 1, SP_DEFER = 2, SP_SUB = 3;
 struct BlockProbe {
     int2 b;          // the block
-    uint32_t c;      // annotation chromosome id
+    uint32_t c;      // file chromosome id
     uint32_t lo;     // first piece of the chromosome
     uint32_t slot;   // bucket slot of b.x (SP_SUB: sub-bucket slot)
     uint32_t xo;     // offset of b.x inside its bucket (SP_SUB: inside its sub-bucket)
@@ -417,14 +417,14 @@ struct BlockProbe {
 
 LSQ_HD int block_stage_chrom(const FilterParams &P, int2 b, uint32_t cs, BlockProbe &q) {
     q.b = b;
-    q.c = LSQ_LD(P.chrom_remap + (cs & 0xFFFFu));
+    q.c = cs & 0xFFFFu;
     q.lo = 0;
     q.slot = 0;
     q.xo = 0;
     if (!(b.x < b.y)) return SP_DROP;         // nil blocks are never looked up
-    if (q.c == 0xFFFFFFFFu) return SP_DROP;   // chromosome without annotation
+    const uint4 cm = LSQ_LD(P.file_meta + q.c);  // chrom_meta of the file chromosome's annotation id, or zeros
+    if (cm.x == cm.y) return SP_DROP;         // chromosome without annotation (no pieces)
     if (b.x < 0) return SP_DEFER;
-    const uint4 cm = LSQ_LD(P.T.chrom_meta + q.c);
     const uint32_t bk = (uint32_t)b.x >> P.T.bp_shift;
     if (bk >= cm.w) return SP_DEFER;
     q.lo = cm.x;
@@ -456,6 +456,11 @@ LSQ_HD int block_stage_sub(const Tables &T, const BlockProbe &q, uint2 e, uint32
     return SP_GO;
 }
 
+// SP_DEFER: the full search.
+LSQ_HD uint32_t block_stage_defer(const FilterParams &P, const BlockProbe &q) {
+    return lookup_direct(P.T, LSQ_LD(P.chrom_remap + q.c), q.b);
+}
+
 // The lookup answer from the piece and its covered-region end.
 LSQ_HD uint32_t block_stage_answer(const BlockProbe &q, uint32_t p, int32_t cov_end) {
     return p == PIECE_NONE ? PIECE_NONE : (p | (cov_end >= q.b.y ? 0x80000000u : 0u));
@@ -473,7 +478,7 @@ LSQ_HD uint32_t block_lookup(const FilterParams &P, int2 b, uint32_t cs) {
         if (st == SP_SUB) st = block_stage_sub(P.T, q, LSQ_LD(P.T.bp_sub + q.slot), p);
         if (st == SP_GO && p != PIECE_NONE) res = block_stage_answer(q, p, LSQ_LD(&P.T.pinfo[p].cov_end));
     }
-    if (st == SP_DEFER) res = lookup_direct(P.T, q.c, b);
+    if (st == SP_DEFER) res = block_stage_defer(P, q);
     return res;
 }
 

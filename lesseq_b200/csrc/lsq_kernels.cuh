@@ -23,7 +23,10 @@ __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
 constexpr int FILT_BLOCK = 512;
 constexpr int FILT_ITEMS = 4;                         // reads per thread (all kept in flight together)
-constexpr int FILT_LBATCH = 2;                        // block lookups of multi-block reads kept in flight per thread
+#ifndef LSQ_FILT_LBATCH
+#define LSQ_FILT_LBATCH 2
+#endif
+constexpr int FILT_LBATCH = LSQ_FILT_LBATCH;                        // block lookups of multi-block reads kept in flight per thread
 #ifndef LSQ_FILT_RBATCH
 #define LSQ_FILT_RBATCH 3
 #endif
@@ -212,7 +215,7 @@ __global__ void __launch_bounds__(FILT_BLOCK, 2) lsq_filter_kernel(FilterParams 
             if (st[u] < 0) continue;
             uint32_t res = PIECE_NONE;
             if (st[u] == SP_GO) res = block_stage_answer(q[u], pp[u], ce[u]);
-            if (st[u] == SP_DEFER) res = lookup_direct(T, q[u].c, b[u]);
+            if (st[u] == SP_DEFER) res = block_stage_defer(P, q[u]);
             s_blk[rel[u]] = res;
         }
     }
@@ -286,7 +289,7 @@ __global__ void __launch_bounds__(FILT_BLOCK, 2) lsq_filter_kernel(FilterParams 
 #pragma unroll
         for (int k = 0; k < FILT_ITEMS; ++k) {
             if (st[k] == SP_SUB) st[k] = block_stage_sub(T, q[k], be[k], pp[k]);
-            if (st[k] == SP_DEFER) pp[k] = lookup_direct(T, q[k].c, b0[k]) & PIECE_NONE;  // searched
+            if (st[k] == SP_DEFER) pp[k] = block_stage_defer(P, q[k]) & PIECE_NONE;  // searched
             raw[k] = pp[k] != PIECE_NONE ? __ldg(reinterpret_cast<const uint4 *>(T.pinfo + pp[k])) : make_uint4(0u, 0u, 0u, 0u);
         }
 #pragma unroll

@@ -172,6 +172,7 @@ struct FilterParams {
     const uint32_t *read_cs;
     const uint32_t *blk_cs;       // may be null
     const uint32_t *chrom_remap;  // file chromosome id -> annotation id or 0xFFFFFFFF
+    const uint4 *file_meta;       // file chromosome id -> chrom_meta of its annotation id (zeros: none)
     // compact wire format (include/lesseq_b200.h): alternatives to read_cs and blk, null when absent
     const uint8_t *read_cs8;
     const int32_t *blk_start;

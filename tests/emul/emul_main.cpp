@@ -86,6 +86,7 @@ static int bucket_selftest(unsigned seed) {
     P.T.pinfo = pinfo.data();
     P.T.chrom_meta = meta.data();
     P.chrom_remap = remap.data();
+    P.file_meta = meta.data();
     size_t checked = 0;
     for (uint32_t c = 0; c < nch; ++c) {
         const uint32_t lo = off[c], hi = off[c + 1];
@@ -237,6 +238,10 @@ int main(int argc, char **argv) {
         FP.read_cs = R.read_cs.data();
         FP.blk_cs = R.any_mixed ? R.blk_cs.data() : nullptr;
         FP.chrom_remap = remap.data();
+        std::vector<uint4> fmeta(remap.size(), make_uint4(0u, 0u, 0u, 0u));
+        for (size_t i = 0; i < remap.size(); ++i)
+            if (remap[i] != 0xFFFFFFFFu) fmeta[i] = H.chrom_meta[remap[i]];
+        FP.file_meta = fmeta.data();
         FP.ext = ext2.data();
         FP.counters = counters;
         for (size_t r = 0; r < n; ++r) {  // lsq_filter_kernel, one "thread" at a time
