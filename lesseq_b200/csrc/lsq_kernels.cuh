@@ -114,7 +114,11 @@ __global__ void __launch_bounds__(FILT_BLOCK, 2) lsq_filter_kernel(FilterParams 
         // streamed read set: the copy engine is still filling blk[]; wait until the tile's last block
         // has landed (the per-read arrays were complete before the launch)
         const uint32_t need = __ldg(P.blk_off + tile1);
-        while (*reinterpret_cast<const volatile uint32_t *>(P.progress) < need) __nanosleep(400);
+        uint32_t spins = 0;
+        while (*reinterpret_cast<const volatile uint32_t *>(P.progress) < need) {
+            __nanosleep(400);
+            if (++spins > 100000000u) __trap();  // ~40 s without progress: the copy died; fail instead of hanging
+        }
         __threadfence();
     }
     __syncthreads();

@@ -293,6 +293,50 @@ def test_streamed_host_reads_match_resident(api, tmp_path):
     ctx.close()
 
 
+def test_streamed_two_read_sets_pageable_and_csr(api, tmp_path):
+    """LSQ_READS_STREAM with two read sets in flight on the copy stream at once, from pageable (not
+    pinned) host memory, and with CSR offsets (blk_off) instead of block counts: same tables as the
+    device-resident run of the same two sets."""
+    import torch
+    from lesseq_b200 import synth
+    A, R, _ = synth.make_config("C4", n_genes=1500)
+    fp, mp = str(tmp_path / "ev.interval"), str(tmp_path / "ev.map")
+    A.write(fp, mp)
+    ann = api.Annotation(fp, mp)
+    ctx = api.Context(0)
+    ctx.upload_events(ann)
+    sets = [synth.make_reads(A, n, R, seed, device="cuda", overhang_frac=0.02) for n, seed in ((3_000_000, 21), (1_000_000, 22))]
+
+    def run(make):
+        for m, rd in enumerate(sets):
+            ctx.set_reads(m, "SHORT_READ" if m == 0 else "MEDIUM_READ", R, make(rd))
+        ctx.count()
+        c = ctx.get_count()
+        ctx.solve([rd["total_read_bases"] for rd in sets])
+        return c, ctx.get_solve()
+
+    keep = []
+
+    def resident(rd):
+        return api.Reads.from_torch(rd["blk_off"], rd["blk"], rd["read_cs"], rd["line_num"], rd["chrom_names"],
+                                    rd["strand_names"])
+
+    def streamed_pageable_csr(rd):
+        h = {k: rd[k].cpu() for k in ("blk_off", "blk", "read_cs", "line_num")}  # pageable
+        keep.append(h)
+        return api.Reads.from_torch(h["blk_off"], h["blk"], h["read_cs"], h["line_num"], rd["chrom_names"],
+                                    rd["strand_names"], stream=True)
+
+    c0, s0 = run(resident)
+    c1, s1 = run(streamed_pageable_csr)
+    assert int(c0["n_valid"].sum()) > 1_000_000
+    for k in c0:
+        assert np.array_equal(c0[k], c1[k]), k
+    for k in ("theta", "rpkm", "loglik"):
+        assert np.array_equal(s0[k], s1[k], equal_nan=True), k
+    ctx.close()
+
+
 def _walk_reads(rng, forms, L, n):
     """Reads of length <= L walking along randomly chosen forms (blocks cut at exon ends)."""
     lines = []
