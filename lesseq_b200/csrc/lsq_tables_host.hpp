@@ -4,6 +4,7 @@
 // prefix counts, tie-break data, class-slot layout and the stab arrangement.
 #pragma once
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -129,6 +130,8 @@ inline void build_bucket_index(const std::vector<int32_t> &arr, const std::vecto
     bkt_off[nch] = (uint32_t)bkt.size();
     if (sub.empty()) sub.push_back(make_uint2(0u, 0u));
 }
+
+constexpr uint64_t LSQ_PART_TARGET_BKT = 512;
 
 inline int tfail(std::string &err, int code, const std::string &msg) {
     err = msg;
@@ -415,8 +418,14 @@ inline int build_host_tables(const lsq_event_tables *t, HostTables &H, std::stri
     // stab buckets: windows of 2^bkt_shift stab entries, at most PART_MAX_BINS / 3 of them
     {
         const uint32_t n_stab = (uint32_t)H.stab.size(), n_pieces = (uint32_t)H.bp_pos.size();
-        H.bkt_shift = 9;
-        while (3ull * ((uint64_t)(n_stab >> H.bkt_shift) + 1ull) > (uint64_t)PART_MAX_BINS) ++H.bkt_shift;
+        // the smallest window (>= 16 entries) that gives at most LSQ_PART_TARGET_BKT buckets: small annotations
+        // still spread their reads over many bins (a bin's chunk switches serialise the tiles that meet there),
+        // large ones keep the per-tile bin arrays of the filter small
+        uint64_t target = LSQ_PART_TARGET_BKT;
+        if (const char *ev = getenv("LSQ_PART_TARGET_BKT")) target = std::max<uint64_t>(1, strtoull(ev, nullptr, 10));  // tuning only
+        target = std::min<uint64_t>(target, PART_MAX_BINS / 3);
+        H.bkt_shift = 4;
+        while ((uint64_t)(n_stab >> H.bkt_shift) + 1ull > target) ++H.bkt_shift;
         H.n_bkt = (n_stab >> H.bkt_shift) + 1u;
         H.bkt_piece.assign(H.n_bkt + 1, n_pieces);
         uint32_t p = 0;
