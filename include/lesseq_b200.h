@@ -245,6 +245,13 @@ int lsqh_reads_view(const lsqh_reads *r, lsq_packed_reads *out);
 /* Derives the compact wire format (blk_cnt, read_cs8, blk_start + blk_len) of a parsed read set where the
  * values fit; later views carry both representations and lsq_set_reads copies the narrow one. */
 int lsqh_reads_compact(lsqh_reads *r);
+/* On-disk packed cache of a parsed read set: the reference parses the same text in `count` and again in `solve`
+ * (count.cpp:279-339, solve.cpp:429-486).  source_path (may be NULL) stamps the pack with size and mtime of the text
+ * it was made from; lsqh_reads_load then fails with LSQ_ERR_IO when the text has changed (or the pack is missing,
+ * truncated or fails its checksum) and the caller parses the text instead.  The drop-in programs use
+ * `<reads_path>.lsqpack` only when the environment has LSQ_READ_CACHE=1 (the reference writes no files). */
+int lsqh_reads_save(const lsqh_reads *r, const char *pack_path, const char *source_path);
+int lsqh_reads_load(const char *pack_path, const char *source_path, lsqh_reads **out);
 
 /* Drop-in bodies of the two programs: same positional arguments (argv[0] = program name),
  * same stdout tables, log on stderr, same exit codes (0, 1; 134 is reported as abort()). */

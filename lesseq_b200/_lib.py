@@ -109,6 +109,8 @@ SYMBOLS = {
     "lsqh_mrf_parse": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "lsqh_reads_free": (None, [C.c_void_p]),
     "lsqh_reads_compact": (C.c_int, [C.c_void_p]),
+    "lsqh_reads_save": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p]),
+    "lsqh_reads_load": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p)]),
     "lsqh_reads_view": (C.c_int, [C.c_void_p, C.POINTER(PackedReads)]),
     "lsqh_count_main": (C.c_int, [C.c_int, c_strp]),
     "lsqh_solve_main": (C.c_int, [C.c_int, c_strp]),

@@ -115,6 +115,25 @@ class Reads:
         check(self._lib.lsqh_reads_view(self._h, C.byref(self.view)))
         return self
 
+    @classmethod
+    def from_pack(cls, pack_path, source_path=None, compact=False):
+        """Load a packed read cache (lsqh_reads_load); raises LsqError when it is missing, stale
+        with respect to source_path, or corrupt."""
+        self = cls()
+        self._h = C.c_void_p()
+        check(self._lib.lsqh_reads_load(str(pack_path).encode(), str(source_path).encode() if source_path else None,
+                                        C.byref(self._h)))
+        if compact:
+            check(self._lib.lsqh_reads_compact(self._h))
+        check(self._lib.lsqh_reads_view(self._h, C.byref(self.view)))
+        return self
+
+    def save_pack(self, pack_path, source_path=None):
+        """Write the packed read cache of a parsed file (lsqh_reads_save)."""
+        assert self._h, "only reads parsed by from_mrf / loaded by from_pack own a host read set"
+        check(self._lib.lsqh_reads_save(self._h, str(pack_path).encode(),
+                                        str(source_path).encode() if source_path else None))
+
     def __del__(self):
         if getattr(self, "_h", None):
             self._lib.lsqh_reads_free(self._h)
@@ -320,7 +339,7 @@ def ars_length(read_type, read_length, seg_len):
     return int(_lib.load().lsq_ars_length(rt, read_length, a.ctypes.data_as(_lib.c_u64p), len(a)))
 
 
-def run_program(prog, args, precision=None, timeout=None):
+def run_program(prog, args, precision=None, timeout=None, env_extra=None):
     """Run the drop-in `count` / `solve` executable (lesseq_b200/bin) with the reference's
     positional arguments; returns (returncode, stdout, stderr)."""
     exe = os.path.join(PKG, "bin", prog)
@@ -329,5 +348,6 @@ def run_program(prog, args, precision=None, timeout=None):
     env = dict(os.environ)
     if precision is not None:
         env["LSQ_PRECISION"] = str(precision)
+    env.update(env_extra or {})
     p = subprocess.run([exe] + [str(a) for a in args], env=env, capture_output=True, text=True, timeout=timeout)
     return p.returncode, p.stdout, p.stderr

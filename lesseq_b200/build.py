@@ -23,7 +23,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-Wno-unus
 
 def _sources():
     return ([os.path.join(CSRC, "lsq_abi.cu")] +
-            [os.path.join(CSRC, "host", f) for f in ("annotation.cpp", "mrf.cpp", "api.cpp")])
+            [os.path.join(CSRC, "host", f) for f in ("annotation.cpp", "mrf.cpp", "pack.cpp", "api.cpp")])
 
 
 def _deps():

@@ -120,6 +120,29 @@ int lsqh_reads_view(const lsqh_reads *r, lsq_packed_reads *v) {
     return LSQ_OK;
 }
 
+int lsqh_reads_save(const lsqh_reads *r, const char *pack_path, const char *source_path) {
+    if (!r || !pack_path) {
+        lsqh::set_error("lsqh_reads_save: null argument");
+        return LSQ_ERR_ARG;
+    }
+    return lsqh::save_reads(*r, pack_path, source_path);
+}
+
+int lsqh_reads_load(const char *pack_path, const char *source_path, lsqh_reads **out) {
+    if (!pack_path || !out) {
+        lsqh::set_error("lsqh_reads_load: null argument");
+        return LSQ_ERR_ARG;
+    }
+    lsqh_reads *r = new lsqh_reads();
+    int rc = lsqh::load_reads(pack_path, source_path, *r);
+    if (rc) {
+        delete r;
+        return rc;
+    }
+    *out = r;
+    return LSQ_OK;
+}
+
 int lsqh_reads_compact(lsqh_reads *r) {
     if (!r) {
         lsqh::set_error("lsqh_reads_compact: null argument");
@@ -303,7 +326,17 @@ int run_program(bool solve, int argc, char **argv) {
             cleanup();
             return 1;
         }
+        // opt-in packed cache next to the text file: `solve` reuses what `count` parsed
+        const char *cache = getenv("LSQ_READ_CACHE");
+        const bool use_cache = cache && cache[0] == '1';
+        const std::string pack = sets[m].path + ".lsqpack";
+        if (use_cache && lsqh_reads_load(pack.c_str(), sets[m].path.c_str(), &reads[m]) == LSQ_OK) {
+            logf(3, "Read pack %s", pack.c_str());
+            continue;
+        }
         rc = lsqh_mrf_parse(sets[m].path.c_str(), &reads[m]);
+        if (rc == LSQ_OK && use_cache && lsqh_reads_save(reads[m], pack.c_str(), sets[m].path.c_str()) != LSQ_OK)
+            logf(1, "%s", lsq_last_error());  // a cache that cannot be written is not an error
         if (rc == LSQ_ERR_IO) {
             fprintf(stderr, "Assertion `ifs.is_open() && !ifs.eof()' failed: %s\n", lsq_last_error());
             cleanup();

@@ -21,4 +21,7 @@ struct lsqh_reads {
 namespace lsqh {
 int parse_mrf(const char *path, lsqh_reads &out);
 void compact_reads(lsqh_reads &r);
+// on-disk packed cache (pack.cpp); source_path stamps / validates the text file the pack was made from
+int save_reads(const lsqh_reads &r, const char *pack_path, const char *source_path);
+int load_reads(const char *pack_path, const char *source_path, lsqh_reads &out);
 }

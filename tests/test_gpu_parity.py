@@ -337,6 +337,31 @@ def test_streamed_two_read_sets_pageable_and_csr(api, tmp_path):
     ctx.close()
 
 
+def test_cli_read_cache_is_transparent(api, tmp_path):
+    """LSQ_READ_CACHE=1: `count` writes <reads>.lsqpack, `solve` reads it; the tables are byte-identical
+    to the uncached programs, a changed text file is re-parsed, and nothing is written without the switch."""
+    case = next(c for c in SEED_CASES if c["expect"]["count_rc"] == 0 and c["expect"]["count17"])
+    ca, sa = golden_util.materialise(case, str(tmp_path))
+    mrfs = [a for a in ca if str(a).endswith(".mrf")]
+    assert mrfs
+    plain = {p: api.run_program(p, a, precision=17) for p, a in (("count", ca), ("solve", sa))}
+    assert not any(os.path.exists(str(m) + ".lsqpack") for m in mrfs)
+    on = {"LSQ_READ_CACHE": "1"}
+    rc, out, err = api.run_program("count", ca, precision=17, env_extra=on)
+    assert (rc, out) == plain["count"][:2], err
+    assert all(os.path.exists(str(m) + ".lsqpack") for m in mrfs)
+    stamps = [os.path.getmtime(str(m) + ".lsqpack") for m in mrfs]
+    rc, out, err = api.run_program("solve", sa, precision=17, env_extra=on)
+    assert (rc, out) == plain["solve"][:2], err
+    assert stamps == [os.path.getmtime(str(m) + ".lsqpack") for m in mrfs]  # reused, not rewritten
+    # the text changes: the stale pack must not be used
+    with open(str(mrfs[0]), "a") as f:
+        f.write("chrNowhere:+:1:50\n")
+    rc, out2, err = api.run_program("count", ca, precision=17, env_extra=on)
+    rc3, out3, _ = api.run_program("count", ca, precision=17)
+    assert rc == rc3 == 0 and out2 == out3
+
+
 def _walk_reads(rng, forms, L, n):
     """Reads of length <= L walking along randomly chosen forms (blocks cut at exon ends)."""
     lines = []

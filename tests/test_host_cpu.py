@@ -287,3 +287,63 @@ def test_compact_wire_format_is_lossless(tmp_path):
     assert np.array_equal((cs8 & 0x3F) | ((cs8 & 0x40) << 10) | ((cs8 & 0x80) << 24), cs)
     assert (cs & _lib.LSQ_READ_MIXED).any()
     assert comp.host_bytes() < 0.75 * wide.host_bytes()
+
+
+def test_read_pack_round_trip_and_staleness(tmp_path):
+    """lsqh_reads_save / lsqh_reads_load: the pack reproduces every array of the parsed file
+    (chimeric reads, comment lines, empty read lines included); a changed text file, a truncated
+    pack and a flipped byte are all refused."""
+    import ctypes as C
+    import numpy as np
+    from lesseq_b200 import api, _lib
+    rng = np.random.default_rng(11)
+    rows = ["# header comment", "AlignmentBlocks"]
+    for i in range(5000):
+        if i % 997 == 0:
+            rows.append("# comment in the middle")
+        nb = int(rng.integers(1, 4))
+        s = int(rng.integers(1, 10 ** 7))
+        blocks = []
+        for _ in range(nb):
+            ln = int(rng.integers(1, 120))
+            chrom = "chrX" if rng.random() < 0.01 else "chr%d" % (1 + i % 5)
+            blocks.append("%s:%s:%d:%d:1:%d" % (chrom, "+-"[i % 2], s, s + ln - 1, ln))
+            s += ln + int(rng.integers(0, 3000))
+        rows.append(",".join(blocks))
+    for mixed in (True, False):
+        d = tmp_path / ("m%d" % mixed)
+        d.mkdir()
+        text = "\n".join(r for r in rows if mixed or "chrX" not in r) + "\n"
+        src, pack = d / "r.mrf", d / "r.mrf.lsqpack"
+        src.write_text(text)
+        a = api.Reads.from_mrf(str(src))
+        a.save_pack(str(pack), str(src))
+        b = api.Reads.from_pack(str(pack), str(src))
+
+        def arrays(r):
+            v, n, nb = r.view, r.n_reads, r.n_blocks
+
+            def arr(ptr, ctype, count):
+                return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(count,)).copy() if ptr else None
+            names = ([v.chrom_names[i] for i in range(v.n_chrom_names)], [v.strand_names[i] for i in range(v.n_strand_names)])
+            return (n, nb, names, arr(v.blk_off, C.c_uint32, n + 1), arr(v.blk, C.c_int32, 2 * nb), arr(v.read_cs, C.c_uint32, n),
+                    arr(v.blk_cs, C.c_uint32, nb), arr(v.line_num, C.c_uint32, n))
+        xa, xb = arrays(a), arrays(b)
+        assert xa[:3] == xb[:3] and xa[0] > 4000
+        assert (xa[6] is not None) == mixed
+        for u, w in zip(xa[3:], xb[3:]):
+            assert (u is None and w is None) or np.array_equal(u, w)
+        # compact form of a loaded pack
+        c = api.Reads.from_pack(str(pack), None, compact=True)
+        assert c.view.blk_cnt and c.view.blk_len8
+        # truncated / corrupted packs
+        raw = pack.read_bytes()
+        for bad in (raw[:len(raw) // 2], raw[:-1], raw[:200] + bytes([raw[200] ^ 1]) + raw[201:], b"LSQPACK0" + raw[8:]):
+            (d / "bad.lsqpack").write_bytes(bad)
+            with pytest.raises(_lib.LsqError):
+                api.Reads.from_pack(str(d / "bad.lsqpack"), None)
+        # stale: the text changed after the pack was written
+        src.write_text(text + "chr1:+:5:20:1:16\n")
+        with pytest.raises(_lib.LsqError):
+            api.Reads.from_pack(str(pack), str(src))
+        api.Reads.from_pack(str(pack), None)  # without a source stamp check it still loads
