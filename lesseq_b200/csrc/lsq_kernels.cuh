@@ -21,7 +21,10 @@ namespace lsq {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
-constexpr int FILT_BLOCK = 512;
+#ifndef LSQ_FILT_BLOCK
+#define LSQ_FILT_BLOCK 512
+#endif
+constexpr int FILT_BLOCK = LSQ_FILT_BLOCK;  // 1024 threads per SM either way (64 registers per thread)
 constexpr int FILT_ITEMS = 4;                         // reads per thread (all kept in flight together)
 #ifndef LSQ_FILT_LBATCH
 #define LSQ_FILT_LBATCH 2
@@ -92,7 +95,7 @@ __global__ void lsq_part_init_kernel(PartState S, uint32_t n_bkt) {
 //          a chunk installs the bin's spare chunk.
 // Phase E: records go from shared memory to their slots (writes of one bin are contiguous; L2
 //          merges them into full sectors before they reach HBM).
-__global__ void __launch_bounds__(FILT_BLOCK, 2) lsq_filter_kernel(FilterParams P) {
+__global__ void __launch_bounds__(FILT_BLOCK, 1024 / FILT_BLOCK) lsq_filter_kernel(FilterParams P) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const Tables &T = P.T;
     const PartState &S = P.part;
@@ -455,6 +458,13 @@ constexpr size_t COUNT_FAST_DYN_SMEM = (size_t)COUNT_QCAP * 8 * (COUNT_BLOCK / 3
 constexpr int COUNT_MAX_ENT = 576;      // staged stab entries (18 KB): a bucket window + the longest stab list
 constexpr int PAIR_QCAP = 256;          // PAIR: pair queue per warp (one read per lane and round)
 constexpr uint32_t CTR_MAX_BASES = 1u << 20;  // larger matched lengths bypass the 32-bit block counters
+#ifndef LSQ_CTR_PACKED
+#define LSQ_CTR_PACKED 0
+#endif
+// packed class counter: reads in bits 20-31 (an item has at most PART_CHUNK = 2^11 reads), their matched bases in
+// bits 0-19 (2^11 reads of fewer than 2^9 matched bases each stay below 2^20)
+constexpr uint32_t CTR_PACK_SHIFT = 20, CTR_PACK_ONE = 1u << CTR_PACK_SHIFT, CTR_PACK_MAX_ML = 512u;
+static_assert(PART_CHUNK <= (1u << 11), "packed counters hold 2^11 reads per item");
 
 struct ItemTables {
     uint32_t chunk, n;   // pool chunk and its fill
@@ -527,10 +537,19 @@ __global__ void __launch_bounds__(COUNT_BLOCK, CLS == 0 ? 4 : 3) lsq_count_kerne
         uint32_t(*ctr)[4] = ct.staged ? s_ctr - ct.e0 : nullptr;
         // tally of one valid (read, entry) pair with at most two forms
         auto tally = [&](const StabEntry &en, uint32_t e, uint32_t cm, uint32_t ml) {
+#if LSQ_CTR_PACKED
+            if (ctr && ml < CTR_PACK_MAX_ML) {
+                atomicAdd(&ctr[e][cm - 1u], CTR_PACK_ONE | ml);  // class count and matched bases in one shared atomic
+            } else if (ctr && ml < CTR_MAX_BASES) {
+                atomicAdd(&ctr[e][cm - 1u], CTR_PACK_ONE);
+                atomicAdd(&ctr[e][3], ml);
+            } else {
+#else
             if (ctr && ml < CTR_MAX_BASES) {
                 atomicAdd(&ctr[e][cm - 1u], 1u);
                 atomicAdd(&ctr[e][3], ml);
             } else {
+#endif
                 atomicAdd(P.slot_cnt + en.slot_off + (cm - 1u), 1ull);
                 atomicAdd(P.bases + en.x, (unsigned long long)ml);
             }
@@ -727,8 +746,17 @@ __global__ void __launch_bounds__(COUNT_BLOCK, CLS == 0 ? 4 : 3) lsq_count_kerne
                 if (!v) continue;
                 flat[i] = 0u;
                 const StabEntry &en = s_ent[i >> 2];
+#if LSQ_CTR_PACKED
+                if ((i & 3u) == 3u) {
+                    atomicAdd(P.bases + en.x, (unsigned long long)v);
+                } else {
+                    atomicAdd(P.slot_cnt + en.slot_off + (i & 3u), (unsigned long long)(v >> CTR_PACK_SHIFT));
+                    if (v & (CTR_PACK_ONE - 1u)) atomicAdd(P.bases + en.x, (unsigned long long)(v & (CTR_PACK_ONE - 1u)));
+                }
+#else
                 if ((i & 3u) == 3u) atomicAdd(P.bases + en.x, (unsigned long long)v);
                 else atomicAdd(P.slot_cnt + en.slot_off + (i & 3u), (unsigned long long)v);
+#endif
             }
         }
         __syncthreads();  // the staged entries may be overwritten by the next item
