@@ -459,7 +459,7 @@ constexpr int COUNT_MAX_ENT = 576;      // staged stab entries (18 KB): a bucket
 constexpr int PAIR_QCAP = 256;          // PAIR: pair queue per warp (one read per lane and round)
 constexpr uint32_t CTR_MAX_BASES = 1u << 20;  // larger matched lengths bypass the 32-bit block counters
 #ifndef LSQ_CTR_PACKED
-#define LSQ_CTR_PACKED 0
+#define LSQ_CTR_PACKED 1
 #endif
 // packed class counter: reads in bits 20-31 (an item has at most PART_CHUNK = 2^11 reads), their matched bases in
 // bits 0-19 (2^11 reads of fewer than 2^9 matched bases each stay below 2^20)
