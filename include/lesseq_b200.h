@@ -232,6 +232,13 @@ typedef struct lsqh_reads lsqh_reads;
  * (shard_begin/shard_end are indices INTO the selection; pass 0, UINT64_MAX for everything). */
 int lsqh_annotation_load(const char *forms_path, const char *map_path, uint64_t begin, uint64_t end,
                          uint64_t shard_begin, uint64_t shard_end, lsqh_annotation **out);
+/* The same with the reference's format tokens.  forms_format: LH_GENE_TXT (the only one `count` accepts,
+ * count.cpp:141), or what `solve` also reads (solve.cpp:158-296): UCSC_GENE_TXT, UCSC_GFF, WORMBASE_GFF2,
+ * GENELETS_GFF3; map_format: UCSC_GENE2ISOFORM or WORMBASE_GENE2ISOFORMS (solve.cpp:310-329).  LSQ_ERR_FORMAT for
+ * any other token. */
+int lsqh_annotation_load_fmt(const char *forms_format, const char *forms_path, const char *map_format,
+                             const char *map_path, uint64_t begin, uint64_t end, uint64_t shard_begin,
+                             uint64_t shard_end, lsqh_annotation **out);
 void lsqh_annotation_free(lsqh_annotation *a);
 int lsqh_annotation_tables(const lsqh_annotation *a, lsq_event_tables *out); /* views into a */
 const char *lsqh_event_name(const lsqh_annotation *a, uint32_t e);

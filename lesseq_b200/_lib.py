@@ -101,6 +101,8 @@ SYMBOLS = {
     "lsq_ars_length": (C.c_uint64, [C.c_uint32, C.c_uint64, c_u64p, C.c_uint32]),
     "lsqh_annotation_load": (C.c_int, [C.c_char_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
                                        C.POINTER(C.c_void_p)]),
+    "lsqh_annotation_load_fmt": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint64, C.c_uint64,
+                                           C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p)]),
     "lsqh_annotation_free": (None, [C.c_void_p]),
     "lsqh_annotation_tables": (C.c_int, [C.c_void_p, C.POINTER(EventTables)]),
     "lsqh_event_name": (C.c_char_p, [C.c_void_p, C.c_uint32]),

@@ -22,13 +22,16 @@ def _ptr(a):
 
 
 class Annotation:
-    """Event model built from LH_GENE_TXT + UCSC_GENE2ISOFORM files (count/count.cpp:136-258)."""
+    """Event model built from LH_GENE_TXT + UCSC_GENE2ISOFORM files (count/count.cpp:136-258) or the
+    other annotation formats of solve/solve.cpp:158-329 (forms_format / map_format tokens)."""
 
-    def __init__(self, forms_path, map_path, begin=0, end=UINT64_MAX, shard=(0, UINT64_MAX)):
+    def __init__(self, forms_path, map_path, begin=0, end=UINT64_MAX, shard=(0, UINT64_MAX),
+                 forms_format="LH_GENE_TXT", map_format="UCSC_GENE2ISOFORM"):
         self._lib = _lib.load()
         self._h = C.c_void_p()
-        check(self._lib.lsqh_annotation_load(str(forms_path).encode(), str(map_path).encode(), begin, end,
-                                             shard[0], shard[1], C.byref(self._h)))
+        check(self._lib.lsqh_annotation_load_fmt(forms_format.encode(), str(forms_path).encode(), map_format.encode(),
+                                                 str(map_path).encode(), begin, end, shard[0], shard[1],
+                                                 C.byref(self._h)))
         self.tables = _lib.EventTables()
         check(self._lib.lsqh_annotation_tables(self._h, C.byref(self.tables)))
         self.n_events = self.tables.n_events

@@ -1,4 +1,6 @@
-// Host front end: LH_GENE_TXT + UCSC_GENE2ISOFORM -> event model.
+// Host front end: annotation files -> event model.  LH_GENE_TXT + UCSC_GENE2ISOFORM are the formats of `count`
+// and of the north-star path; `solve` also reads UCSC_GENE_TXT, UCSC_GFF, WORMBASE_GFF2, GENELETS_GFF3 forms and
+// WORMBASE_GENE2ISOFORMS maps (solve/solve.cpp:158-296, 310-329), which only differ in how the form rows are read.
 //
 // What the reference does at count/count.cpp:136-258 (and identically solve/solve.cpp:152-412
 // for these two formats), restated over flat vectors:
@@ -157,22 +159,19 @@ bool fits_i32(long v) { return v >= INT32_MIN && v <= INT32_MAX; }
 
 }  // namespace
 
-int load_annotation(const char *forms_path, const char *map_path, uint64_t begin, uint64_t end,
-                    uint64_t shard_begin, uint64_t shard_end, lsqh_annotation &A) {
-    FileLines ff(forms_path);
-    if (!ff.ok || ff.buf.empty()) {
-        set_error(std::string("cannot read forms file ") + forms_path);
-        return LSQ_ERR_IO;
-    }
-    std::vector<FormRow> rows;
+namespace {
+
+// LH_GENE_TXT (count.cpp:141-170) and UCSC_GENE_TXT (jsc/bioinfo/gene_anno.hpp:57-99, two more columns:
+// cdsStart cdsEnd): one form per line, name chrom strand txStart txEnd [cdsStart cdsEnd] exonCount starts ends.
+// A column that does not parse as a number ends the row as `istream >>` does: the fields after it stay empty.
+void read_gene_txt(const FileLines &ff, bool with_cds, std::vector<FormRow> &rows) {
     ff.each([&](const char *s, size_t n) {
         Tokens tk(s, n);
         FormRow r;
-        std::string tx0, tx1, cnt, es, ee;
+        std::string t, cnt, es, ee;
         bool ok = tk.next(r.name) && tk.next(r.chrom) && tk.next(r.strand);
         long v;
-        ok = ok && tk.next(tx0) && parse_long_token(tx0, v);
-        ok = ok && tk.next(tx1) && parse_long_token(tx1, v);
+        for (int k = 0; ok && k < (with_cds ? 4 : 2); ++k) ok = tk.next(t) && parse_long_token(t, v);
         if (ok && tk.next(cnt) && parse_long_token(cnt, v) && v >= 0) {
             r.exon_count = (uint64_t)v;
             if (tk.next(es)) split_exon_list(es, r.starts);
@@ -180,6 +179,115 @@ int load_annotation(const char *forms_path, const char *map_path, uint64_t begin
         }
         rows.push_back(std::move(r));
     });
+}
+
+// The GFF-like formats give one exon per line; the exons of a form are merged with interval_list semantics
+// and the forms come out in bytewise order of their names (set<string> inames, solve.cpp:161-296).
+struct GffForm {
+    std::string chrom, strand;
+    IntervalSet il;
+};
+void trim_quotes(std::string &s) {  // trim_if(iname, is_any_of("\""))
+    size_t b = 0, e = s.size();
+    while (b < e && s[b] == '"') ++b;
+    while (e > b && s[e - 1] == '"') --e;
+    s = s.substr(b, e - b);
+}
+int read_gff(const FileLines &ff, const std::string &fmt, std::vector<FormRow> &rows, std::string &err) {
+    const bool ucsc = fmt == "UCSC_GFF", wb = fmt == "WORMBASE_GFF2", genelets = fmt == "GENELETS_GFF3";
+    std::map<std::string, GffForm> forms;
+    size_t line_no = 0;
+    int rc = LSQ_OK;
+    ff.each([&](const char *s, size_t n) {
+        ++line_no;
+        if (rc || ((ucsc || genelets) && line_no <= 2)) return;  // two header lines (solve.cpp:164-165, 236-237)
+        Tokens tk(s, n);
+        std::string chr, tmp, type, t0, t1, strand, tail;
+        tk.next(chr);
+        tk.next(tmp);
+        tk.next(type);
+        if (genelets && type != "exon") return;
+        long start = 0, end = 0;
+        if (!(tk.next(t0) && parse_long_token(t0, start) && tk.next(t1) && parse_long_token(t1, end))) {
+            rc = LSQ_ERR_PARSE;  // the reference reads uninitialised longs here
+            err = fmt + " line " + std::to_string(line_no) + ": start/end are not numbers";
+            return;
+        }
+        tk.next(tmp);
+        tk.next(strand);
+        tk.next(tmp);
+        if (wb) tk.next(tmp);
+        tk.next(tail);  // form name (UCSC_GFF, WORMBASE_GFF2) or attribute list (GENELETS_GFF3)
+        auto add = [&](const std::string &iname, const std::string &chrom) {
+            GffForm &f = forms[iname];
+            f.chrom = chrom;
+            f.strand = strand;
+            f.il.add(start - 1, end);
+        };
+        if (!genelets) {
+            trim_quotes(tail);
+            add(tail, ucsc ? chr : "chr" + chr);
+            return;
+        }
+        size_t i = 0;
+        while (i <= tail.size()) {  // infos split at ';', names after "Parent=" split at ','
+            size_t j = tail.find(';', i);
+            if (j == std::string::npos) j = tail.size();
+            if (j - i > 7 && tail.compare(i, 7, "Parent=") == 0) {
+                size_t a = i + 7;
+                while (a <= j) {
+                    size_t b = tail.find(',', a);
+                    if (b == std::string::npos || b > j) b = j;
+                    if (b > a) add(tail.substr(a, b - a), "chr" + chr);
+                    a = b + 1;
+                }
+            }
+            i = j + 1;
+        }
+    });
+    if (rc) return rc;
+    for (auto &kv : forms) {
+        FormRow r;
+        r.name = kv.first;
+        r.chrom = kv.second.chrom;
+        r.strand = kv.second.strand;
+        r.exon_count = kv.second.il.starts.size();
+        r.starts = kv.second.il.starts;
+        r.ends = kv.second.il.ends;
+        rows.push_back(std::move(r));
+    }
+    return LSQ_OK;
+}
+
+}  // namespace
+
+int load_annotation(const char *forms_path, const char *map_path, uint64_t begin, uint64_t end,
+                    uint64_t shard_begin, uint64_t shard_end, lsqh_annotation &A) {
+    return load_annotation_fmt("LH_GENE_TXT", forms_path, "UCSC_GENE2ISOFORM", map_path, begin, end, shard_begin, shard_end, A);
+}
+
+int load_annotation_fmt(const char *forms_format, const char *forms_path, const char *map_format, const char *map_path,
+                        uint64_t begin, uint64_t end, uint64_t shard_begin, uint64_t shard_end, lsqh_annotation &A) {
+    const std::string ffmt = forms_format ? forms_format : "", mfmt = map_format ? map_format : "";
+    FileLines ff(forms_path);
+    if (!ff.ok || ff.buf.empty()) {
+        set_error(std::string("cannot read forms file ") + forms_path);
+        return LSQ_ERR_IO;
+    }
+    std::vector<FormRow> rows;
+    if (ffmt == "LH_GENE_TXT" || ffmt == "UCSC_GENE_TXT") {
+        read_gene_txt(ff, ffmt == "UCSC_GENE_TXT", rows);
+    } else if (ffmt == "UCSC_GFF" || ffmt == "WORMBASE_GFF2" || ffmt == "GENELETS_GFF3") {
+        std::string err;
+        int rc = read_gff(ff, ffmt, rows, err);
+        if (rc) {
+            set_error(err);
+            return rc;
+        }
+    } else {
+        set_error("Unknown file format error: " + ffmt);
+        return LSQ_ERR_FORMAT;
+    }
     std::unordered_map<std::string, size_t> name2row;  // later duplicates win (count.cpp:176-179)
     for (size_t i = 0; i < rows.size(); ++i) name2row[rows[i].name] = i;
 
@@ -188,14 +296,33 @@ int load_annotation(const char *forms_path, const char *map_path, uint64_t begin
         set_error(std::string("cannot read map file ") + map_path);
         return LSQ_ERR_IO;
     }
+    if (mfmt != "UCSC_GENE2ISOFORM" && mfmt != "WORMBASE_GENE2ISOFORMS") {
+        set_error("Unknown file format error: " + mfmt);
+        return LSQ_ERR_FORMAT;
+    }
+    const bool wb_map = mfmt == "WORMBASE_GENE2ISOFORMS";  // `gene form;form;...` (solve.cpp:318-329)
     std::map<std::string, std::vector<long> > ev2rows;  // std::map: bytewise lexicographic order
     mf.each([&](const char *s, size_t n) {
         Tokens tk(s, n);
         std::string g, f;
         tk.next(g);
         tk.next(f);
-        auto it = name2row.find(f);
-        ev2rows[g].push_back(it == name2row.end() ? -1 : (long)it->second);
+        std::vector<long> &dst = ev2rows[g];
+        auto push = [&](const std::string &name) {
+            auto it = name2row.find(name);
+            dst.push_back(it == name2row.end() ? -1 : (long)it->second);
+        };
+        if (!wb_map) {
+            push(f);
+            return;
+        }
+        size_t i = 0;
+        while (i < f.size()) {
+            size_t j = f.find(';', i);
+            if (j == std::string::npos) j = f.size();
+            if (j > i) push(f.substr(i, j - i));
+            i = j + 1;
+        }
     });
 
     std::vector<const std::pair<const std::string, std::vector<long> > *> selected;

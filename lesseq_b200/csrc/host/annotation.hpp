@@ -55,5 +55,8 @@ namespace lsqh {
 // Returns LSQ_OK or a negative LSQ_ERR_* (message via set_error()).
 int load_annotation(const char *forms_path, const char *map_path, uint64_t begin, uint64_t end,
                     uint64_t shard_begin, uint64_t shard_end, lsqh_annotation &out);
+// the same with the reference's format tokens (solve.cpp:158-296, 310-329); LSQ_ERR_FORMAT for an unknown token
+int load_annotation_fmt(const char *forms_format, const char *forms_path, const char *map_format, const char *map_path,
+                        uint64_t begin, uint64_t end, uint64_t shard_begin, uint64_t shard_end, lsqh_annotation &A);
 void set_error(const std::string &msg);  // shared thread-local error slot (abi.cu)
 }  // namespace lsqh

@@ -16,20 +16,27 @@
 
 extern "C" {
 
-int lsqh_annotation_load(const char *forms_path, const char *map_path, uint64_t begin, uint64_t end,
-                         uint64_t shard_begin, uint64_t shard_end, lsqh_annotation **out) {
-    if (!forms_path || !map_path || !out) {
+int lsqh_annotation_load_fmt(const char *forms_format, const char *forms_path, const char *map_format,
+                             const char *map_path, uint64_t begin, uint64_t end, uint64_t shard_begin,
+                             uint64_t shard_end, lsqh_annotation **out) {
+    if (!forms_format || !forms_path || !map_format || !map_path || !out) {
         lsqh::set_error("lsqh_annotation_load: null argument");
         return LSQ_ERR_ARG;
     }
     lsqh_annotation *a = new lsqh_annotation();
-    int rc = lsqh::load_annotation(forms_path, map_path, begin, end, shard_begin, shard_end, *a);
+    int rc = lsqh::load_annotation_fmt(forms_format, forms_path, map_format, map_path, begin, end, shard_begin, shard_end, *a);
     if (rc) {
         delete a;
         return rc;
     }
     *out = a;
     return LSQ_OK;
+}
+
+int lsqh_annotation_load(const char *forms_path, const char *map_path, uint64_t begin, uint64_t end,
+                         uint64_t shard_begin, uint64_t shard_end, lsqh_annotation **out) {
+    return lsqh_annotation_load_fmt("LH_GENE_TXT", forms_path, "UCSC_GENE2ISOFORM", map_path, begin, end, shard_begin,
+                                    shard_end, out);
 }
 
 void lsqh_annotation_free(lsqh_annotation *a) { delete a; }
@@ -280,7 +287,11 @@ int run_program(bool solve, int argc, char **argv) {
         fprintf(stderr, "Assertion `ifs.is_open() && !ifs.eof()' failed (%s).\n", form_path.c_str());
         return 134;
     }
-    if (form_format != "LH_GENE_TXT") {
+    // `count` reads LH_GENE_TXT only (count.cpp:141-183); `solve` also the formats of solve.cpp:158-296
+    const bool form_ok = form_format == "LH_GENE_TXT" ||
+                         (solve && (form_format == "UCSC_GENE_TXT" || form_format == "UCSC_GFF" ||
+                                    form_format == "WORMBASE_GFF2" || form_format == "GENELETS_GFF3"));
+    if (!form_ok) {
         logf(0, "Unknown file format error: %s", form_format.c_str());
         return 1;
     }
@@ -289,12 +300,13 @@ int run_program(bool solve, int argc, char **argv) {
         fprintf(stderr, "Assertion `ifs.is_open() && !ifs.eof()' failed (%s).\n", map_path.c_str());
         return 134;
     }
-    if (map_format != "UCSC_GENE2ISOFORM") {
+    if (map_format != "UCSC_GENE2ISOFORM" && !(solve && map_format == "WORMBASE_GENE2ISOFORMS")) {  // solve.cpp:318
         logf(0, "Unknown file format error: %s", map_format.c_str());
         return 1;
     }
     lsqh_annotation *ann = nullptr;
-    int rc = lsqh_annotation_load(form_path.c_str(), map_path.c_str(), begin, end, 0, UINT64_MAX, &ann);
+    int rc = lsqh_annotation_load_fmt(form_format.c_str(), form_path.c_str(), map_format.c_str(), map_path.c_str(), begin, end,
+                                      0, UINT64_MAX, &ann);
     if (rc == LSQ_ERR_IO) {
         fprintf(stderr, "Assertion `ifs.is_open() && !ifs.eof()' failed: %s\n", lsq_last_error());
         return 134;

@@ -160,7 +160,7 @@ int main(int argc, char **argv) {
         sets.push_back(r);
     }
     lsqh_annotation ann;
-    int rc = lsqh::load_annotation(form_path.c_str(), map_path.c_str(), begin, end, 0, UINT64_MAX, ann);
+    int rc = lsqh::load_annotation_fmt(argv[4], form_path.c_str(), argv[6], map_path.c_str(), begin, end, 0, UINT64_MAX, ann);
     if (rc) {
         fprintf(stderr, "emul: %s\n", g_err.c_str());
         return 1;

@@ -25,3 +25,19 @@ def materialise(case, d):
 
 def all_cases():
     return load("seed.json") + load("fuzz.json") + load("weird.json")
+
+
+def materialise_formats(case, d):
+    """Write a formats.json case (annotation in one of solve's other formats); returns (count_args, solve_args)."""
+    fp, mp = os.path.join(d, "ev.forms"), os.path.join(d, "ev.map")
+    open(fp, "w").write(case["forms"])
+    open(mp, "w").write(case["map"])
+    head = ["0", "p", os.path.join(d, "o_"), case["forms_format"], fp, case["map_format"], mp,
+            str(case["begin"]), str(case["end"])]
+    ca, sa = list(head), list(head)
+    for i, s in enumerate(case["sets"]):
+        rp = os.path.join(d, "r%d.mrf" % i)
+        open(rp, "w").write(s["mrf"])
+        ca += ["MRF_SINGLE", s["type"], str(s["read_length"]), rp]
+        sa += ["MRF_SINGLE", s["type"], str(s["read_length"]), rp, repr(s["total_read_bases"])]
+    return ca, sa

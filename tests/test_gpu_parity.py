@@ -571,3 +571,39 @@ def test_solve_stress_injected_classes(api):
             assert np.allclose(se, exp, rtol=1e-6, atol=0), (e, K, se, exp)
         else:
             assert np.all(np.isnan(se) | (se >= 0))
+
+
+def test_other_annotation_formats_match_reference(api, tmp_path):
+    """`solve` with UCSC_GENE_TXT / UCSC_GFF / WORMBASE_GFF2 / GENELETS_GFF3 forms and WORMBASE_GENE2ISOFORMS
+    maps (solve/solve.cpp:158-329) against the reference binary's outputs (tests/golden/formats.json): every
+    case through the ctypes mirror in one process, every seventh through the drop-in executable; `count`
+    keeps refusing them (count.cpp:141-183)."""
+    cases = golden_util.load("formats.json")
+    ctx = api.Context(0)
+    for ci, case in enumerate(cases):
+        d = tmp_path / ("c%d" % ci)
+        d.mkdir()
+        ca, sa = golden_util.materialise_formats(case, str(d))
+        exp = case["expect"]
+        ann = api.Annotation(sa[4], sa[6], case["begin"], case["end"], forms_format=case["forms_format"],
+                             map_format=case["map_format"])
+        assert ann.n_events > 0
+        ctx.upload_events(ann)
+        M = len(case["sets"])
+        for m, st in enumerate(case["sets"]):
+            ctx.set_reads(m, st["type"], st["read_length"], api.Reads.from_mrf(d / ("r%d.mrf" % m), compact=ci % 2 == 1))
+        ctx.count()
+        cnt = ctx.get_count()
+        ctx.solve([st["total_read_bases"] for st in case["sets"]])
+        sol = ctx.get_solve()
+        for prec in (17, 6):
+            _, st_tab = format_tables(api, ann, M, cnt, sol, prec)
+            bad = tables_match(exp["solve%d" % prec], st_tab, True, rel6=(prec == 6))
+            assert bad is None, (case["name"], prec, bad)
+        if ci % 7 == 0:
+            rc, out, err = api.run_program("solve", sa, precision=17)
+            assert rc == 0, err
+            assert tables_match(exp["solve17"], out, True) is None, case["name"]
+            rc, out, err = api.run_program("count", ca)
+            assert rc == 1 and out == "" and "Unknown file format error" in err
+    ctx.close()

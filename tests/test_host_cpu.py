@@ -347,3 +347,49 @@ def test_read_pack_round_trip_and_staleness(tmp_path):
         with pytest.raises(_lib.LsqError):
             api.Reads.from_pack(str(pack), str(src))
         api.Reads.from_pack(str(pack), None)  # without a source stamp check it still loads
+
+
+def test_other_annotation_formats_replayed_on_cpu_match_reference(emul_bin, tmp_path):
+    """UCSC_GENE_TXT / UCSC_GFF / WORMBASE_GFF2 / GENELETS_GFF3 forms and WORMBASE_GENE2ISOFORMS maps
+    (solve/solve.cpp:158-329) through the host front end + the CPU replay of the device functions, against
+    what the reference's solve binary printed for the same files (tests/golden/formats.json)."""
+    cases = golden_util.load("formats.json")
+    seen = set()
+    for case in cases:
+        d = tmp_path / case["name"].replace("|", "_")
+        d.mkdir()
+        _, sa = golden_util.materialise_formats(case, str(d))
+        rc, out = _run_emul(emul_bin, "solve", sa)
+        assert rc == 0, case["name"]
+        assert _close(case["expect"]["solve17"], out, True), case["name"]
+        seen.add((case["forms_format"], case["map_format"]))
+    assert len(cases) > 200 and len(seen) == 8
+
+
+def test_cli_accepts_solve_only_formats_like_the_reference(tmp_path):
+    """count.cpp:141-183 knows LH_GENE_TXT / UCSC_GENE2ISOFORM only and answers anything else with exit 1 and
+    "Unknown file format error"; solve.cpp:158-329 reads five forms formats and two map formats.  Without a GPU the
+    drop-in `solve` gets as far as creating the device context (exit 70: there is no CPU fallback)."""
+    from lesseq_b200 import api, build
+    build.build()
+    cases = golden_util.load("formats.json")
+    picked = {}
+    for c in cases:
+        picked.setdefault((c["forms_format"], c["map_format"]), c)
+    assert len(picked) == 8
+    for (ff, mf), case in picked.items():
+        d = tmp_path / (ff + mf)
+        d.mkdir()
+        ca, sa = golden_util.materialise_formats(case, str(d))
+        ann = api.Annotation(sa[4], sa[6], case["begin"], case["end"], forms_format=ff, map_format=mf)
+        assert ann.n_events > 0 and ann.n_forms >= ann.n_events
+        rc, out, err = api.run_program("count", ca)
+        assert rc == 1 and out == "" and "Unknown file format error" in err
+        rc, out, err = api.run_program("solve", sa)
+        assert rc in (0, 70), err
+        bad = list(sa)
+        bad[3] = "UCSC_BED"
+        rc, out, err = api.run_program("solve", bad)
+        assert rc == 1 and "Unknown file format error: UCSC_BED" in err
+    with pytest.raises(api.LsqError):
+        api.Annotation(sa[4], sa[6], forms_format="NOT_A_FORMAT")
