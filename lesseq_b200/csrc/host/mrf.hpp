@@ -1,15 +1,36 @@
 // Host front end: packed MRF_SINGLE reads (owner of the arrays an lsq_packed_reads views).
 #pragma once
 #include <cstdint>
+#include <memory>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "annotation.hpp"
 
+namespace lsqh {
+// std::vector whose resize() leaves trivially constructible elements uninitialised: the merge of the parser's
+// per-thread chunks and the pack loader overwrite every element anyway, and zero-filling gigabytes first is not free
+template <class T>
+struct NoInitAlloc : std::allocator<T> {
+    template <class U>
+    struct rebind {
+        typedef NoInitAlloc<U> other;
+    };
+    template <class U, class... A>
+    void construct(U *p, A &&... a) {
+        if constexpr (sizeof...(A) == 0) ::new ((void *)p) U;
+        else ::new ((void *)p) U(std::forward<A>(a)...);
+    }
+};
+template <class T>
+using Array = std::vector<T, NoInitAlloc<T> >;
+}  // namespace lsqh
+
 struct lsqh_reads {
     lsqh::Dictionary chroms, strands;
-    std::vector<uint32_t> blk_off, read_cs, blk_cs, line_num;
-    std::vector<int32_t> blk;
+    lsqh::Array<uint32_t> blk_off, read_cs, blk_cs, line_num;
+    lsqh::Array<int32_t> blk;
     bool any_mixed = false;
     // compact wire format (lsqh_reads_compact); empty when not derived or when a value does not fit
     std::vector<uint8_t> blk_cnt, read_cs8, blk_len8;

@@ -52,15 +52,17 @@ bool source_stamp(const char *path, uint64_t &size, int64_t &mtime_ns) {
     return true;
 }
 
-template <class T>
-bool put(FILE *f, const std::vector<T> &v, size_t n, uint64_t &h) {
+template <class V>
+bool put(FILE *f, const V &v, size_t n, uint64_t &h) {
+    typedef typename V::value_type T;
     if (v.size() < n) return false;
     h = fnv(h, v.data(), n * sizeof(T));
     return n == 0 || fwrite(v.data(), sizeof(T), n, f) == n;
 }
-template <class T>
-bool get(FILE *f, std::vector<T> &v, size_t n, uint64_t &h) {
-    v.resize(n);
+template <class V>
+bool get(FILE *f, V &v, size_t n, uint64_t &h) {
+    typedef typename V::value_type T;
+    v.resize(n);  // lsqh::Array: not zero-filled
     if (n && fread(v.data(), sizeof(T), n, f) != n) return false;
     h = fnv(h, v.data(), n * sizeof(T));
     return true;
