@@ -3,6 +3,9 @@
 // (count/count.cpp:88-501, solve/solve.cpp:102-856; only the LH_GENE_TXT / UCSC_GENE2ISOFORM /
 // MRF_SINGLE branches).  All counting and estimation is done by the lsq_* device path.
 #include <cerrno>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -229,6 +232,9 @@ struct ReadArg {
 };
 
 bool file_openable(const std::string &p) {  // assert(ifs.is_open() && !ifs.eof()), count.cpp:139
+    struct stat st;
+    if (stat(p.c_str(), &st) == 0 && !S_ISREG(st.st_mode) && !S_ISDIR(st.st_mode))
+        return access(p.c_str(), R_OK) == 0;  // a pipe (`<(zcat reads.mrf.gz)`) must be opened exactly once
     FILE *f = fopen(p.c_str(), "rb");
     if (!f) return false;
     fclose(f);

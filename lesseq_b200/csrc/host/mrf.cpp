@@ -187,36 +187,46 @@ void parse_chunk(const char *p, const char *end, ChunkOut &R) {
     R.n_lines = line_num;
 }
 
-struct MappedFile {  // read-only view of the whole file; no copy
+struct MappedFile {  // read-only view of the whole file: mapped when it is a regular file, read otherwise (pipes)
     const char *data = nullptr;
     size_t size = 0;
     bool ok = false;
+    void *map = nullptr;
+    std::string owned;
     explicit MappedFile(const char *path) {
         int fd = open(path, O_RDONLY);
         if (fd < 0) return;
         struct stat st;
-        if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) {
+        if (fstat(fd, &st) != 0) {
             close(fd);
             return;
         }
         ok = true;
-        size = (size_t)st.st_size;
-        if (size) {
-            void *m = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
-            if (m == MAP_FAILED) {
-                ok = false;
-                size = 0;
-            } else {
+        if (S_ISREG(st.st_mode) && st.st_size > 0) {
+            void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (m != MAP_FAILED) {
+                map = m;
+                size = (size_t)st.st_size;
                 data = static_cast<const char *>(m);
                 madvise(m, size, MADV_SEQUENTIAL);
                 madvise(m, size, MADV_WILLNEED);
             }
         }
+        if (!map) {  // a pipe, a character device, or a file system without mmap
+            char tmp[1 << 16];
+            ssize_t n;
+            while ((n = read(fd, tmp, sizeof tmp)) > 0) owned.append(tmp, (size_t)n);
+            ok = n == 0;
+            data = owned.data();
+            size = owned.size();
+        }
         close(fd);
     }
     ~MappedFile() {
-        if (data) munmap(const_cast<char *>(data), size);
+        if (map) munmap(map, size);
     }
+    MappedFile(const MappedFile &) = delete;
+    MappedFile &operator=(const MappedFile &) = delete;
 };
 
 template <class F>

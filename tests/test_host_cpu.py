@@ -393,3 +393,43 @@ def test_cli_accepts_solve_only_formats_like_the_reference(tmp_path):
         assert rc == 1 and "Unknown file format error: UCSC_BED" in err
     with pytest.raises(api.LsqError):
         api.Annotation(sa[4], sa[6], forms_format="NOT_A_FORMAT")
+
+
+def test_mrf_parser_reads_pipes_and_reports_lines(tmp_path):
+    """The memory-mapped parser falls back to reading when the path is a pipe (`<(zcat reads.mrf.gz)`); parse
+    errors name the file's line whatever the number of parser threads; results do not depend on the thread count."""
+    import ctypes as C
+    import numpy as np
+    from lesseq_b200 import api
+    lines = ["AlignmentBlocks"] + ["chr%d:%s:%d:%d:1:30" % (1 + i % 7, "+-"[i % 2], 100 + 13 * i, 129 + 13 * i) for i in range(60000)]
+    text = "\n".join(lines) + "\n"
+    assert len(text) > (1 << 20)  # large enough for the multi-threaded path
+    p = tmp_path / "r.mrf"
+    p.write_text(text)
+
+    def arrays(r):
+        v, n, nb = r.view, r.n_reads, r.n_blocks
+        f = lambda ptr, ct, k: np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(k,)).copy()  # noqa: E731
+        return f(v.blk_off, C.c_uint32, n + 1), f(v.blk, C.c_int32, 2 * nb), f(v.read_cs, C.c_uint32, n), f(v.line_num, C.c_uint32, n)
+    os.environ["LSQ_THREADS"] = "1"
+    one = arrays(api.Reads.from_mrf(str(p)))
+    os.environ["LSQ_THREADS"] = "5"
+    try:
+        many = arrays(api.Reads.from_mrf(str(p)))
+        for a, b in zip(one, many):
+            assert np.array_equal(a, b)
+        assert np.array_equal(one[3], np.arange(1, 60001, dtype=np.uint32))  # the skipped first line is not counted
+        fifo = tmp_path / "fifo"
+        os.mkfifo(str(fifo))
+        w = subprocess.Popen(["bash", "-c", "cat '%s' > '%s'" % (p, fifo)])
+        piped = arrays(api.Reads.from_mrf(str(fifo)))
+        w.wait()
+        for a, b in zip(one, piped):
+            assert np.array_equal(a, b)
+        bad = tmp_path / "bad.mrf"
+        bad.write_text("\n".join(lines[:50001] + ["chr1:+:12x:40:1:30"] + lines[50001:]) + "\n")
+        with pytest.raises(api.LsqError) as ei:
+            api.Reads.from_mrf(str(bad))
+        assert "MRF line 50001)" in str(ei.value)
+    finally:
+        del os.environ["LSQ_THREADS"]
