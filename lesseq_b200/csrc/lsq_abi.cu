@@ -71,6 +71,7 @@ struct U8ToU32 {
 struct ReadSet {
     bool declared = false, injected = false, borrowed = false;
     bool streamed = false;  // blk[] is still being copied when lsq_count launches the filter (LSQ_READS_STREAM)
+    bool copy_pending = false;  // a streamed copy into this set's buffers was enqueued and no lsq_count has waited for it
     uint32_t type = 0;
     uint64_t read_length = 0;
     uint64_t n_reads = 0, n_blocks = 0;
@@ -297,6 +298,10 @@ int lsq_set_reads(lsq_ctx *c, uint32_t m, uint32_t read_type, uint64_t read_leng
     LSQ_CUDA(cudaSetDevice(c->device));
     ReadSet &rs = c->sets[m];
     cudaStream_t s = c->stream;
+    if (rs.copy_pending) {  // the set is replaced before it was counted: its streamed copy must not land on the new data
+        LSQ_CUDA(cudaStreamWaitEvent(s, c->ev_all[m], 0));
+        rs.copy_pending = false;
+    }
     rs.declared = true;
     rs.injected = false;
     rs.type = read_type;
@@ -416,6 +421,7 @@ int lsq_set_reads(lsq_ctx *c, uint32_t m, uint32_t read_type, uint64_t read_leng
             }
             if (rs.streamed) {
                 LSQ_CUDA(cudaEventRecord(c->ev_all[m], s));
+                rs.copy_pending = true;
                 s = c->stream;  // everything below belongs to the compute stream, after the per-read arrays
                 LSQ_CUDA(cudaStreamWaitEvent(s, c->ev_small, 0));
             }
@@ -646,7 +652,10 @@ int lsq_count(lsq_ctx *c) {
         } else {
             LSQ_CUDA(cudaEventRecord(c->ev[1], s));
         }
-        if (rs.streamed) LSQ_CUDA(cudaStreamWaitEvent(s, c->ev_all[m], 0));  // the caller's buffers are free again
+        if (rs.streamed) {  // the caller's buffers are free again
+            LSQ_CUDA(cudaStreamWaitEvent(s, c->ev_all[m], 0));
+            rs.copy_pending = false;
+        }
         LSQ_CUDA(cudaEventRecord(c->ev[2], s));
         if (n) {
             lsq::CountParams CP;
