@@ -172,6 +172,29 @@ def test_device_functions_replayed_on_cpu_match_oracle_fuzz(emul_bin, oracle_bin
             assert rc1 == rc2 and _close(o1, o2, prog == "solve"), (seed, prog)
 
 
+def test_device_functions_replayed_on_cpu_match_oracle_midscale(emul_bin, oracle_bin, tmp_path):
+    """The C2 / C4 shapes at a size where the piece lookup runs with wide buckets (shift >= 7), crowded buckets and
+    their sub-buckets, and the MRF parser with several threads: host front end + table layout + device functions
+    replayed on the CPU against the oracle (which is pinned to the reference binaries)."""
+    from lesseq_b200 import synth
+    for cfg, seed in (("C2", 7), ("C4", 8)):
+        A, R, _ = synth.make_config(cfg, n_genes=3000)
+        d = tmp_path / cfg
+        d.mkdir()
+        fp, mp, rp = str(d / "ev.interval"), str(d / "ev.map"), str(d / "r.mrf")
+        A.write(fp, mp)
+        rd = synth.make_reads(A, 60000, R, seed, device="cpu", overhang_frac=0.02 if cfg == "C4" else 0.0)
+        synth.reads_to_mrf(rd, rp)
+        assert os.path.getsize(rp) > (1 << 20)
+        args = ["0", "p", str(d / "o_"), "LH_GENE_TXT", fp, "UCSC_GENE2ISOFORM", mp, "0", "10000000", "MRF_SINGLE",
+                "SHORT_READ", str(R), rp]
+        for prog, a in (("count", args), ("solve", args + [repr(rd["total_read_bases"])])):
+            rc1, o1, _ = oracle_bin.run_oracle(prog, a)
+            rc2, o2 = _run_emul(emul_bin, prog, a)
+            assert rc1 == 0 and rc2 == 0 and len(o1.splitlines()) > 15000
+            assert _close(o1, o2, prog == "solve"), (cfg, prog)
+
+
 def test_cli_argument_errors(built_lib, tmp_path):
     """Exit codes of the drop-in programs for malformed command lines (count.cpp:20-38, 95-129)."""
     from lesseq_b200 import api
