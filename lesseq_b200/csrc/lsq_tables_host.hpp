@@ -93,7 +93,9 @@ inline void build_bucket_index(const std::vector<int32_t> &arr, const std::vecto
     uint64_t span = 0;
     for (size_t c = 0; c < nch; ++c)
         if (off[c + 1] > off[c]) span += (uint64_t)std::max<int32_t>(arr[off[c + 1] - 1], 0) + 1;
-    uint64_t want = std::min<uint64_t>(std::max<uint64_t>(8 * arr.size(), 1), 1ull << 25);
+    uint64_t per_piece = 8;
+    if (const char *ev = getenv("LSQ_BKT_PER_PIECE")) per_piece = std::max<uint64_t>(1, strtoull(ev, nullptr, 10));  // tuning only
+    uint64_t want = std::min<uint64_t>(std::max<uint64_t>(per_piece * arr.size(), 1), 1ull << 25);
     shift = 0;
     while ((span >> shift) > want && shift < 30) ++shift;
     const uint32_t ss = bucket_sub_shift(shift), n_sub = 1u << (shift - ss);

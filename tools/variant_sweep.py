@@ -9,7 +9,8 @@ separate shared library built here (nvcc cross-compiles without a GPU) from the 
     # -> lesseq_b200/lib/var_*.so (git-ignored, they travel with the gpurun snapshot) + the command to run
 
 Hooks that exist today (lsq_kernels.cuh): LSQ_FILT_BLOCK, LSQ_FILT_LBATCH, LSQ_FILT_RBATCH, LSQ_CTR_PACKED;
-host side (environment, no rebuild): LSQ_PART_TARGET_BKT.  Remove the var_*.so files before committing a round.
+host side (environment, no rebuild): LSQ_PART_TARGET_BKT (stab buckets), LSQ_BKT_PER_PIECE (piece-lookup buckets per
+piece, default 8; 16 gives 128-bp buckets with four offsets per word at C2).  Remove the var_*.so files before committing a round.
 """
 import os
 import subprocess
