@@ -269,8 +269,10 @@ int load_annotation(const char *forms_path, const char *map_path, uint64_t begin
 int load_annotation_fmt(const char *forms_format, const char *forms_path, const char *map_format, const char *map_path,
                         uint64_t begin, uint64_t end, uint64_t shard_begin, uint64_t shard_end, lsqh_annotation &A) {
     const std::string ffmt = forms_format ? forms_format : "", mfmt = map_format ? map_format : "";
+    // An EMPTY file passes the reference's `assert(ifs.is_open() && !ifs.eof())` (eof is only set by a read): it
+    // simply yields no rows -- no forms, or no genes and therefore no output (verified against bin/count, bin/solve).
     FileLines ff(forms_path);
-    if (!ff.ok || ff.buf.empty()) {
+    if (!ff.ok) {
         set_error(std::string("cannot read forms file ") + forms_path);
         return LSQ_ERR_IO;
     }
@@ -292,7 +294,7 @@ int load_annotation_fmt(const char *forms_format, const char *forms_path, const 
     for (size_t i = 0; i < rows.size(); ++i) name2row[rows[i].name] = i;
 
     FileLines mf(map_path);
-    if (!mf.ok || mf.buf.empty()) {
+    if (!mf.ok) {
         set_error(std::string("cannot read map file ") + map_path);
         return LSQ_ERR_IO;
     }

@@ -317,6 +317,10 @@ int run_program(bool solve, int argc, char **argv) {
         fprintf(stderr, "Assertion `ifs.is_open() && !ifs.eof()' failed: %s\n", lsq_last_error());
         return 134;
     }
+    if (rc == LSQ_ERR_ARG) {  // a selected gene names a missing form, has no exon, ...: the reference dies on an assertion
+        fprintf(stderr, "Assertion `px != 0' failed: %s\n", lsq_last_error());
+        return 134;
+    }
     if (rc) {
         logf(0, "%s", lsq_last_error());
         return 1;

@@ -245,9 +245,10 @@ int parse_mrf(const char *path, lsqh_reads &R) {
         set_error(std::string("cannot read reads file ") + path);
         return LSQ_ERR_IO;
     }
-    if (mf.size == 0) {
-        set_error(std::string("empty reads file ") + path);
-        return LSQ_ERR_IO;
+    if (mf.size == 0) {  // an empty file passes the reference's open assertion and holds no reads (count.cpp:278-283)
+        R = lsqh_reads();
+        R.blk_off.assign(1, 0u);
+        return LSQ_OK;
     }
     const bool timing = getenv("LSQ_PARSE_TIMING") != nullptr;
     auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };

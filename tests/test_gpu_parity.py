@@ -607,3 +607,21 @@ def test_other_annotation_formats_match_reference(api, tmp_path):
             rc, out, err = api.run_program("count", ca)
             assert rc == 1 and out == "" and "Unknown file format error" in err
     ctx.close()
+
+
+def test_empty_and_header_only_reads_match_oracle(api, oracle_bin, tmp_path):
+    """A reads file with no bytes at all, or with nothing but its first line, counts nothing: every event prints
+    zero counts and the no-read branch of solve (uniform theta, zero rpkm; solve.cpp:797-826), as the reference does."""
+    case = golden_util.load("seed.json")[0]
+    ca, sa = golden_util.materialise(case, str(tmp_path))
+    for text in ("", "AlignmentBlocks\n", "AlignmentBlocks\n# only a comment\n"):
+        p = tmp_path / "none.mrf"
+        p.write_text(text)
+        c2, s2 = list(ca), list(sa)
+        c2[-1] = str(p)
+        s2[-2] = str(p)
+        for prog, a in (("count", c2), ("solve", s2)):
+            rc1, o1, _ = oracle_bin.run_oracle(prog, a)
+            rc2, o2, err = api.run_program(prog, a, precision=17)
+            assert rc1 == 0 and rc2 == 0, err
+            assert o1 != "" and tables_match(o1, o2, prog == "solve") is None, (repr(text), prog)

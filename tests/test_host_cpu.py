@@ -456,3 +456,43 @@ def test_mrf_parser_reads_pipes_and_reports_lines(tmp_path):
         assert "MRF line 50001)" in str(ei.value)
     finally:
         del os.environ["LSQ_THREADS"]
+
+
+def test_empty_input_files_behave_like_the_reference(emul_bin, oracle_bin, tmp_path):
+    """An EMPTY file passes the reference's open assertion (eof is only set by a read): an empty map selects no
+    gene (no output, exit 0), an empty reads file counts nothing, an empty forms file makes a selected gene name a
+    missing form (the reference dies on an assertion: exit 134 here).  The oracle was checked against the binaries
+    on exactly these inputs."""
+    from lesseq_b200 import api
+    case = golden_util.load("seed.json")[0]
+    ca, sa = golden_util.materialise(case, str(tmp_path))
+    empty = tmp_path / "empty"
+    empty.write_text("")
+
+    def variant(idx_count, idx_solve):
+        c2, s2 = list(ca), list(sa)
+        for i in idx_count:
+            c2[i] = str(empty)
+        for i in idx_solve:
+            s2[i] = str(empty)
+        return c2, s2
+    for name, (c2, s2) in {"map": variant([6], [6]), "forms+map": variant([4, 6], [4, 6]),
+                           "reads": variant([len(ca) - 1], [len(sa) - 2])}.items():
+        for prog, a in (("count", c2), ("solve", s2)):
+            rc1, o1, _ = oracle_bin.run_oracle(prog, a)
+            rc2, o2 = _run_emul(emul_bin, prog, a)
+            assert rc1 == 0 and rc2 == 0 and _close(o1, o2, prog == "solve"), (name, prog)
+            assert (o1 == "") == (name != "reads")
+            rc3, o3, err = api.run_program(prog, a, precision=17)
+            if name != "reads":
+                assert rc3 == 0 and o3 == "", (name, prog, err)  # decided before any device work
+            else:
+                assert rc3 in (0, 70), err  # 70: this machine has no GPU
+                assert rc3 == 70 or _close(o1, o3, prog == "solve")
+    c2, s2 = variant([4], [4])  # empty forms, the map still names them
+    for prog, a in (("count", c2), ("solve", s2)):
+        assert oracle_bin.run_oracle(prog, a)[0] != 0
+        rc, out, err = api.run_program(prog, a)
+        assert rc == 134 and out == "" and "not in the forms file" in err
+    r = api.Reads.from_mrf(str(empty))
+    assert r.n_reads == 0 and r.n_blocks == 0
