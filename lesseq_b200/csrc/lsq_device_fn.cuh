@@ -327,6 +327,7 @@ LSQ_HD FilteredRead filter_read_t(const FilterParams &P, uint64_t r, uint32_t ba
             } else {
                 if (n == 1) {
                     second = b;
+                    if (spilled) work[1] = b;  // an earlier merge already moved the list to the ext entry
                 } else {
                     if (!spilled) {
                         work[0] = first;

@@ -625,3 +625,24 @@ def test_empty_and_header_only_reads_match_oracle(api, oracle_bin, tmp_path):
             rc2, o2, err = api.run_program(prog, a, precision=17)
             assert rc1 == 0 and rc2 == 0, err
             assert o1 != "" and tables_match(o1, o2, prog == "solve") is None, (repr(text), prog)
+
+
+def test_merged_then_appended_then_out_of_order_blocks(api, oracle_bin, tmp_path):
+    """The live-fuzz regression of tests/test_host_cpu.py on the device: overlap, append, out-of-order blocks."""
+    (tmp_path / "ev.interval").write_text(
+        "~t|1\tchr2\t+\t749\t1039\t4\t749,792,888,1000\t770,888,916,1039,\n"
+        "~t|2\tchr2\t-\t749\t1039\t6\t749,753,792,888,910,987,\t751,770,892,910,916,1039\n"
+        "~t|3\tchr2\t-\t760\t1039\t4\t760,792,888,1000\t770,875,916,1039\n")
+    (tmp_path / "ev.map").write_text("~t\t~t|1\n~t\t~t|2\n~t\t~t|3\n")
+    (tmp_path / "r.mrf").write_text(
+        "AlignmentBlocks\n"
+        "chr2:-:843:892:1:50,chr2:-:889:910:51:72,chr2:-:913:916:73:76,chr2:-:911:912:77:78,chr2:-:988:1009:79:100\n"
+        "chr2:-:843:892:1:50,chr2:-:889:910:51:72,chr2:-:913:916:73:76,chr2:-:911:912:77:78\n"
+        "chr2:-:843:892:1:50,chr2:-:889:910:51:72,chr2:-:913:916:73:76\n")
+    args = ["0", "p", str(tmp_path / "o_"), "LH_GENE_TXT", str(tmp_path / "ev.interval"), "UCSC_GENE2ISOFORM",
+            str(tmp_path / "ev.map"), "0", "100", "MRF_SINGLE", "SHORT_READ", "36", str(tmp_path / "r.mrf")]
+    for prog, a in (("count", args), ("solve", args + ["288.0"])):
+        rc1, o1, _ = oracle_bin.run_oracle(prog, a)
+        rc2, o2, err = api.run_program(prog, a, precision=17)
+        assert rc1 == 0 and rc2 == 0, err
+        assert tables_match(o1, o2, prog == "solve") is None, prog

@@ -496,3 +496,25 @@ def test_empty_input_files_behave_like_the_reference(emul_bin, oracle_bin, tmp_p
         assert rc == 134 and out == "" and "not in the forms file" in err
     r = api.Reads.from_mrf(str(empty))
     assert r.n_reads == 0 and r.n_blocks == 0
+
+
+def test_merged_then_appended_then_out_of_order_blocks(emul_bin, oracle_bin, tmp_path):
+    """Regression (found by a live fuzz run against the reference binaries): blocks that first overlap (the list
+    shrinks to one interval in the ext entry), then append, then arrive out of order --
+    [842,892) [888,910) [912,916) [910,912) -- must leave [842,912) [912,916) like interval_list::add_interval."""
+    (tmp_path / "ev.interval").write_text(
+        "~t|1\tchr2\t+\t749\t1039\t4\t749,792,888,1000\t770,888,916,1039,\n"
+        "~t|2\tchr2\t-\t749\t1039\t6\t749,753,792,888,910,987,\t751,770,892,910,916,1039\n"
+        "~t|3\tchr2\t-\t760\t1039\t4\t760,792,888,1000\t770,875,916,1039\n")
+    (tmp_path / "ev.map").write_text("~t\t~t|1\n~t\t~t|2\n~t\t~t|3\n")
+    (tmp_path / "r.mrf").write_text(
+        "AlignmentBlocks\n"
+        "chr2:-:843:892:1:50,chr2:-:889:910:51:72,chr2:-:913:916:73:76,chr2:-:911:912:77:78,chr2:-:988:1009:79:100\n"
+        "chr2:-:843:892:1:50,chr2:-:889:910:51:72,chr2:-:913:916:73:76,chr2:-:911:912:77:78\n"
+        "chr2:-:843:892:1:50,chr2:-:889:910:51:72,chr2:-:913:916:73:76\n")
+    args = ["0", "p", str(tmp_path / "o_"), "LH_GENE_TXT", str(tmp_path / "ev.interval"), "UCSC_GENE2ISOFORM",
+            str(tmp_path / "ev.map"), "0", "100", "MRF_SINGLE", "SHORT_READ", "36", str(tmp_path / "r.mrf")]
+    rc1, o1, _ = oracle_bin.run_oracle("count", args)
+    rc2, o2 = _run_emul(emul_bin, "count", args)
+    assert rc1 == 0 and rc2 == 0 and o1 == o2
+    assert o1.splitlines() == ["~t\t2\t~t|1\t1", "~t\t2\t~t|2\t2", "~t\t2\t~t|3\t0"]
