@@ -5,12 +5,12 @@
                     [--workload C2|C1|C4] [--reads R] [--genes G]
 
 A "step" is one full pass of the device pipeline over one batch of synthetic packed reads:
-load filter + partition by (read class, stab bucket) -> count -> finalize -> EM solve.
+scan (load filter + candidate lookup + signature tally) -> expand -> general -> finalize -> EM solve.
   value : reads/s of that pass, inputs already resident in HBM, CUDA-event timed, max over ranks
   e2e   : the same through the C ABI with HOST (pinned) buffers: lsq_set_reads (H2D) + lsq_count +
           lsq_solve + lsq_get_count/lsq_get_solve (D2H) inside the timed region
-  roofline : the dominant kernel's (load filter + partition) algorithmic bytes / its CUDA-event duration vs the
-             measured HBM copy peak; the three count kernels are reported beside it
+  roofline : the dominant kernel (lsq_scan_kernel): SURVEY 8(d) algorithmic bytes N*(6+8*blocks/read) / its
+             CUDA-event duration vs the measured HBM copy peak
   cpu_baseline : the reference's own count + solve binaries (oracle/_ref) on a bounded text sample
 `--impl reference` times the reference binaries on all host cores (its own scale-out recipe:
 one process per disjoint gene range, each reading the whole read file).
@@ -62,7 +62,7 @@ def workload_config(args, world):
             "C4": "C4: junction-heavy 100bp reads over short exons, 2% junction overhangs"}[args.workload]
     cfg = {"workload": desc, "genes": genes, "reads_per_gpu": n, "read_length": R, "read_type": "SHORT_READ",
            "sharding": "gene-rank ranges x%d, covered regions of the whole range" % world,
-           "l2_policy": "inputs (%.1f GB packed reads per GPU) far exceed the 126 MB L2; no flush needed" % (n * 22e-9)}
+           }
     return cfg, R, n, genes
 
 
@@ -236,8 +236,27 @@ def run_ours(args):
     ann = api.Annotation(fp, mp, 0, api.UINT64_MAX, shard=(sb, se))
     assert ann.n_events == se - sb
     reads = synth.make_reads(A, n, R, 100 + rank, device="cuda", events=np.array(order[sb:se]))
-    dev_reads = api.Reads.from_torch(reads["blk_off"], reads["blk"], reads["read_cs"], reads["line_num"],
-                                     reads["chrom_names"], reads["strand_names"])
+    # resident layout = the compact packed form (include/lesseq_b200.h): blocks per read u8, chromosome/strand id u8,
+    # block start i32 + block length u8 (u16 when a block is 256 or longer); wide CSR arrays only if a value does not fit
+    blk_cnt = (reads["blk_off"][1:] - reads["blk_off"][:-1]).to(torch.uint8)
+    cs = reads["read_cs"]
+    b2 = reads["blk"].view(-1, 2)
+    blen = b2[:, 1] - b2[:, 0]
+    compact_ok = len(reads["chrom_names"]) <= 64 and len(reads["strand_names"]) <= 2 and \
+        int(blen.max()) < 65536 and int(blen.min()) >= 0 and not args.wide_wire
+    if compact_ok:
+        cs8 = ((cs & 0x3F) | (((cs >> 16) & 1) << 6) | (((cs >> 31) & 1) << 7)).to(torch.uint8)
+        len8 = int(blen.max()) < 256  # short reads: one byte per block length
+        compact = {"blk_start": b2[:, 0].contiguous(), "blk_len": blen.to(torch.uint8 if len8 else torch.int16).contiguous(),
+                   "read_cs8": cs8.contiguous(), "blk_cnt": blk_cnt.contiguous()}
+        dev_reads = api.Reads.from_torch(None, None, None, None, reads["chrom_names"], reads["strand_names"],
+                                         blk_cnt=compact["blk_cnt"], read_cs8=compact["read_cs8"], blk_start=compact["blk_start"],
+                                         **{"blk_len8" if len8 else "blk_len": compact["blk_len"]})
+    else:
+        dev_reads = api.Reads.from_torch(reads["blk_off"], reads["blk"], reads["read_cs"], reads["line_num"],
+                                         reads["chrom_names"], reads["strand_names"])
+    resident_bytes = int(dev_reads.host_bytes())
+    cfg["l2_policy"] = "inputs (%.2f GB packed reads per GPU) far exceed the 126 MB L2; no flush needed" % (resident_bytes / 1e9)
     trb = [reads["total_read_bases"]]
     stream = torch.cuda.current_stream()
     ctx = api.Context(local, stream=stream.cuda_stream)
@@ -263,12 +282,12 @@ def run_ours(args):
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    phases = {k: 0.0 for k in ("filter_ms", "index_ms", "count_kernel_ms", "finalize_ms", "solve_ms")}
+    phases = {k: 0.0 for k in ("clear_ms", "scan_ms", "expand_ms", "general_ms", "finalize_ms", "solve_ms")}
     launches = 0
     ev0.record(stream)
     for _ in range(args.steps):
         step_resident()
-        t = ctx.timings()
+        t = ctx.timings()  # waits for the step: per-kernel CUDA-event times of this very step
         for k in phases:
             phases[k] += t[k]
         launches += t["launches"]
@@ -279,20 +298,10 @@ def run_ours(args):
     cnt, sol = ctx.get_count(), ctx.get_solve()
 
     # ---- end to end through the C ABI with host buffers ---------------------------------------
-    # compact wire format (include/lesseq_b200.h): blocks per read (u8) instead of CSR offsets, implicit line
-    # numbers, one-byte chromosome/strand ids, block = start (i32) + length (u16); streamed (LSQ_READS_STREAM):
-    # the filter consumes the blocks while the copy engine is still delivering them
-    blk_cnt = (reads["blk_off"][1:] - reads["blk_off"][:-1]).to(torch.uint8)
-    cs = reads["read_cs"]
-    b2 = reads["blk"].view(-1, 2)
-    compact_ok = len(reads["chrom_names"]) <= 64 and len(reads["strand_names"]) <= 2 and \
-        int((b2[:, 1] - b2[:, 0]).max()) < 65536 and int((b2[:, 1] - b2[:, 0]).min()) >= 0 and not args.wide_wire
+    # the same compact form from pinned host memory, streamed (LSQ_READS_STREAM): the scan consumes the blocks while
+    # the copy engine is still delivering them
     if compact_ok:
-        cs8 = ((cs & 0x3F) | (((cs >> 16) & 1) << 6) | (((cs >> 31) & 1) << 7)).to(torch.uint8)
-        len8 = int((b2[:, 1] - b2[:, 0]).max()) < 256  # short reads: one byte per block length
-        pinned = {"blk_start": b2[:, 0].contiguous().cpu().pin_memory(),
-                  "blk_len": (b2[:, 1] - b2[:, 0]).to(torch.uint8 if len8 else torch.int16).cpu().pin_memory(),  # u8 / bits of u16
-                  "read_cs8": cs8.cpu().pin_memory(), "blk_cnt": blk_cnt.cpu().pin_memory()}
+        pinned = {k: v.cpu().pin_memory() for k, v in compact.items()}
         host_reads = api.Reads.from_torch(None, None, None, None, reads["chrom_names"], reads["strand_names"],
                                           blk_cnt=pinned["blk_cnt"], stream=not args.no_stream, read_cs8=pinned["read_cs8"],
                                           blk_start=pinned["blk_start"], **{"blk_len8" if len8 else "blk_len": pinned["blk_len"]})
@@ -337,14 +346,13 @@ def run_ours(args):
     n_events_total = len(ids)
     if rank == 0:
         peak, peak_src = hbm_peak()
-        ck_ms = phases["count_kernel_ms"] / args.steps
-        fk_ms = phases["filter_ms"] / args.steps
-        count_gbs = tsum["count_bytes"] / (ck_ms * 1e-3) / 1e9 if ck_ms > 0 else 0.0
-        # the dominant kernel of the step is the load filter + partition kernel (count.cpp:319-324 and
-        # the read index of :346-364): algorithmic bytes = the packed read set once + one 16-byte
-        # record per kept read
-        filter_bytes = int(dev_reads.host_bytes() + 16 * tsum["reads_kept"])
-        achieved = filter_bytes / (fk_ms * 1e-3) / 1e9 if fk_ms > 0 else 0.0
+        sk_ms = phases["scan_ms"] / args.steps
+        # algorithmic bytes of the count path = one pass over the packed reads, N * (6 + 8 * blocks/read)
+        # (2-byte chromosome id + 4-byte offset per read, 8 bytes per block); the resident layout is narrower
+        # (`resident_bytes`), so the kernel moves fewer bytes than that
+        n_blocks = int(reads["n_blocks"])
+        alg_bytes = int(6 * n + 8 * n_blocks)
+        achieved = alg_bytes / (sk_ms * 1e-3) / 1e9 if sk_ms > 0 else 0.0
         d2h = int(sum(v.nbytes for v in cnt.values()) + sum(v.nbytes for v in sol.values()))
         line = {
             "metric": METRIC, "value": total_reads / (ms / 1000.0), "unit": UNIT, "n_gpus": world,
@@ -355,32 +363,29 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(host_reads.host_bytes()), "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms,
                     "wire": ("compact (blk_cnt u8, read_cs8 u8, blk_start i32 + blk_len u8/u16)" if compact_ok else "blk_cnt u8 + wide blk/read_cs") +
-                            (", copy overlapped with the filter (LSQ_READS_STREAM)" if not args.no_stream else "")},
+                            (", copy overlapped with the scan (LSQ_READS_STREAM)" if not args.no_stream else "")},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "lsq_filter_kernel (1 launch per step, %.0f%% of the step)" % (100.0 * fk_ms / ms),
+            "roofline": {"bound": "hbm", "kernel": "lsq_scan_kernel (1 launch per step, %.0f%% of the step)" % (100.0 * sk_ms / ms),
                          "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(args, world, n, "filter_kernel"),
-                         "peak_source": peak_src, "bytes_per_launch": filter_bytes, "ms_per_launch": fk_ms,
-                         "count_kernels": {"kernel": "lsq_count_kernel<FAST|PAIR|GENERAL> (3 launches)", "achieved": count_gbs,
-                                           "frac": count_gbs / peak, "bytes_per_step": int(tsum["count_bytes"]),
-                                           "ms_per_step": ck_ms, "traffic": measured_traffic(args, world, n, "count_kernels")}},
-            # every kernel of the step against the same measured HBM peak (algorithmic bytes / CUDA-event time)
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(args, world, n, "scan_kernel"),
+                         "peak_source": peak_src, "bytes_per_launch": alg_bytes, "ms_per_launch": sk_ms,
+                         "bytes_note": "SURVEY 8(d): N*(6+8*blocks/read); the resident compact layout holds %d bytes" % resident_bytes,
+                         "limiter": "scattered L1TEX operations (2 table gathers + 1 reduction per read at ~1 lane-op/cycle/SM, "
+                                    "profiles/r02_microbench_gather_red_fp64.log), not HBM"},
+            # every kernel of the step (CUDA-event times)
             "kernels": [
-                {"name": "lsq_filter_kernel", "ms": phases["filter_ms"] / args.steps,
-                 "bytes": int(dev_reads.host_bytes() + 16 * tsum["reads_kept"]),
-                 "note": "reads the packed read set once, appends one 16-byte record per kept read to its "
-                         "(read class, stab bucket) bin"},
-                {"name": "counter memsets + lsq_part_init_kernel", "ms": phases["index_ms"] / args.steps, "bytes": 0,
-                 "note": "resets the class counters and the partition state (no sort in the pipeline)"},
-                {"name": "lsq_count_kernel<0,1,2>", "ms": ck_ms, "bytes": int(tsum["count_bytes"]),
-                 "note": "16 bytes per kept read + the ext entries of GENERAL-class reads"},
-                {"name": "lsq_solve_small_kernel<1>", "ms": phases["solve_ms"] / args.steps,
-                 "bytes": int(n_events_total // world * 120), "note": "FP64 latency bound (log/div chains), not HBM"},
+                {"name": "lsq_clear_kernel", "ms": phases["clear_ms"] / args.steps},
+                {"name": "lsq_scan_kernel", "ms": sk_ms},
+                {"name": "lsq_expand_kernel", "ms": phases["expand_ms"] / args.steps},
+                {"name": "lsq_general_kernel", "ms": phases["general_ms"] / args.steps},
+                {"name": "lsq_finalize_kernel", "ms": phases["finalize_ms"] / args.steps},
+                {"name": "lsq_solve_small_kernel<1>", "ms": phases["solve_ms"] / args.steps},
             ],
             "events_per_sec": n_events_total / (ms / 1000.0),
             "events": n_events_total,
             "phases_ms_per_step_rank0": {k: v / args.steps for k, v in phases.items()},
-            "reads_kept_rank0": int(tsum["reads_kept"]), "valid_pairs_rank0": int(tsum["pairs_valid"]),
+            "reads_rank0": {k: int(tsum[k]) for k in ("reads_in", "blocks_in", "reads_single", "reads_pair", "reads_general", "hash_full")},
+            "valid_pairs_rank0": int(tsum["pairs_valid"]),
             "em_iters_mean_rank0": float(sol["iters"].mean()), "em_iters_max_rank0": int(sol["iters"].max()),
             "em_iters_p99_rank0": float(np.percentile(sol["iters"], 99)),
         }
@@ -395,9 +400,6 @@ def run_ours(args):
                               % (args.sample_reads, len(A2.ev_gene), dt)}
             except Exception as ex:  # the oracle always exists; report why it could not run
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %s" % ex}
-        for k in line["kernels"]:
-            k["gbs"] = k["bytes"] / (k["ms"] * 1e-3) / 1e9 if k["ms"] > 0 else 0.0
-            k["frac_of_hbm_peak"] = k["gbs"] / peak
         print(json.dumps(line), flush=True)
     ctx.close()
     shutil.rmtree(tmp, ignore_errors=True)

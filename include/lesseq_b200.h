@@ -156,16 +156,20 @@ typedef struct lsq_solve_out {
                             NaN when undefined (no reads, singular information, more than 16 forms). */
 } lsq_solve_out;
 
-/* Device timings of the last lsq_count / lsq_solve call (CUDA events on the context's stream).
- * filter_ms: the load filter + partition kernel; index_ms: counter resets and partition set-up
- * (the read index of count.cpp:346-364 is the partition itself: there is no sort). */
+/* Device timings (CUDA events on the context's stream) and read statistics of the last lsq_count /
+ * lsq_solve.  lsq_count and lsq_solve only enqueue work; lsq_get_timings waits for it.
+ * scan_ms: the scan kernel -- load filter + candidate lookup + signature tally, the one pass over the reads;
+ * expand_ms: the expand kernel -- the walk of every distinct signature; general_ms: the general kernel. */
 typedef struct lsq_timings {
-    float filter_ms, index_ms, reserved_ms, count_ms, finalize_ms, solve_ms;
-    float count_kernel_ms; /* the three count kernel instantiations (summed over read sets) */
+    float clear_ms, scan_ms, expand_ms, general_ms, finalize_ms, solve_ms;
     uint32_t launches;     /* kernels launched by the last lsq_count + lsq_solve */
-    uint32_t count_launches;
-    uint64_t reads_in, reads_kept, pairs_valid; /* summed over read sets */
-    uint64_t count_bytes; /* algorithmic bytes streamed by the count kernel */
+    uint32_t reserved;
+    uint64_t reads_in, blocks_in;   /* summed over read sets */
+    uint64_t reads_single;          /* reads tallied by a single-block signature */
+    uint64_t reads_pair;            /* reads tallied by a two-block signature */
+    uint64_t reads_general;         /* reads walked one by one */
+    uint64_t hash_full;             /* two-block reads that found no hash slot (walked one by one) */
+    uint64_t pairs_valid;           /* valid (read, event) pairs */
 } lsq_timings;
 
 const char *lsq_last_error(void);
@@ -185,8 +189,9 @@ int lsq_upload_events(lsq_ctx *ctx, const lsq_event_tables *tables);
 int lsq_set_reads(lsq_ctx *ctx, uint32_t m, uint32_t read_type, uint64_t read_length,
                   const lsq_packed_reads *reads);
 
-/* Load filter + read index (partition by stab bucket) + candidate scan + compatibility + histogram
- * for every declared read set (count.cpp:319-324, 346-364, 421-482).  Results stay on the device. */
+/* Load filter + candidate lookup + compatibility + histogram for every declared read set
+ * (count.cpp:319-324, 346-364, 421-482).  Asynchronous: the work is enqueued on the context's stream and
+ * results stay on the device (lsq_get_count / lsq_get_solve / lsq_get_timings / lsq_ctx_sync wait for it). */
 int lsq_count(lsq_ctx *ctx);
 int lsq_get_count(lsq_ctx *ctx, lsq_count_out *out);
 

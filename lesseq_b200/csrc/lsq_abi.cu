@@ -11,9 +11,6 @@
 #include <string>
 #include <vector>
 
-#include <cub/device/device_scan.cuh>
-#include <cub/iterator/transform_input_iterator.cuh>
-
 #include "../../include/lesseq_b200.h"
 #include "lsq_kernels.cuh"
 #include "lsq_tables_host.hpp"
@@ -64,10 +61,6 @@ cudaError_t upload(DevBuf &b, const std::vector<T> &v, cudaStream_t s) {
     return cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
 }
 
-struct U8ToU32 {
-    __host__ __device__ uint32_t operator()(uint8_t v) const { return (uint32_t)v; }
-};
-
 struct ReadSet {
     bool declared = false, injected = false, borrowed = false;
     bool streamed = false;  // blk[] is still being copied when lsq_count launches the filter (LSQ_READS_STREAM)
@@ -77,8 +70,10 @@ struct ReadSet {
     uint64_t n_reads = 0, n_blocks = 0;
     uint32_t n_file_strands = 0;
     // inputs (owned copies or borrowed device pointers)
-    DevBuf d_blk_off, d_blk, d_read_cs, d_blk_cs, d_line_num, d_blk_cnt, d_scan_tmp, d_read_cs8, d_blk_start, d_blk_len;
+    DevBuf d_blk_off, d_blk, d_read_cs, d_blk_cs, d_line_num, d_blk_cnt, d_read_cs8, d_blk_start, d_blk_len;
+    DevBuf d_grp_base, d_sup_base;  // block-offset index of a compact read set (lsq_group_sum_kernel)
     const uint32_t *blk_off = nullptr, *read_cs = nullptr, *blk_cs = nullptr, *line_num = nullptr;
+    const uint8_t *blk_cnt = nullptr;
     const int2 *blk = nullptr;
     const uint8_t *read_cs8 = nullptr;  // compact wire format
     const int32_t *blk_start = nullptr;
@@ -105,14 +100,14 @@ struct lsq_ctx {
     std::map<std::string, uint32_t> chrom_id;
     std::vector<std::string> strand_names;
     DevBuf d_hdr, d_seg, d_fmask, d_pfx, d_tie, d_bp_chrom_off, d_stab_off, d_stab, d_cov_off, d_bp_bkt_off, d_bp_bkt, d_bp_sub, d_pinfo, d_chrom_meta,
-        d_cov_start, d_cov_end, d_form_len, d_bkt_piece;
+        d_cov_start, d_cov_end, d_form_len, d_sig_cut, d_sig_piece;
     // read sets
     ReadSet sets[LSQ_MAX_METHODS];
     uint32_t M = 0;  // highest declared index + 1
     // per-run state
     DevBuf d_slot_cnt, d_slot_mask, d_bases, d_G, d_counters;
-    DevBuf d_ext, d_pool, d_part;  // d_part: state | owner | work lists | counters of the partition
-    bool filter_smem_set = false;
+    DevBuf d_ext, d_scratch, d_gen_list;  // d_scratch: signature counters | hash | general-list length (cleared per read set)
+    uint32_t scan_flags = 0;
     DevBuf d_n_valid, d_bases_out, d_iso, d_theta, d_rpkm, d_se, d_ll, d_llpr, d_iters;
     bool counted = false, finalized = false, solved = false;
     // streamed read sets: copies run on their own stream and publish their progress to the filter
@@ -120,10 +115,12 @@ struct lsq_ctx {
     cudaEvent_t ev_small = nullptr, ev_all[LSQ_MAX_METHODS] = {};
     DevBuf d_progress;            // [LSQ_MAX_METHODS] blocks of blk[] landed so far
     uint32_t *h_progress = nullptr;  // pinned: the values the copy stream writes after each chunk
-    // timing
-    cudaEvent_t ev[16] = {};
+    // timing: events per read set (clear | scan | expand | general | end), then finalize and solve; read lazily
+    cudaEvent_t ev_set[LSQ_MAX_METHODS][5] = {};
+    cudaEvent_t ev[4] = {};  // finalize begin/end, solve begin/end
+    bool tm_count_pending = false, tm_solve_pending = false;
+    bool set_counted[LSQ_MAX_METHODS] = {};
     lsq_timings tm{};
-    std::vector<unsigned long long> h_counters;
 };
 
 namespace {
@@ -159,6 +156,9 @@ int lsq_ctx_create(int device, lsq_ctx **out) {
     LSQ_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->own_stream = true;
     for (auto &ev : c->ev) LSQ_CUDA(cudaEventCreate(&ev));
+    for (auto &row : c->ev_set)
+        for (auto &ev : row) LSQ_CUDA(cudaEventCreate(&ev));
+    if (const char *f = getenv("LSQ_SCAN_FLAGS")) c->scan_flags = (uint32_t)strtoul(f, nullptr, 0);  // debugging (SCAN_NO_*)
     LSQ_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     LSQ_CUDA(cudaEventCreateWithFlags(&c->ev_small, cudaEventDisableTiming));
     for (auto &ev : c->ev_all) LSQ_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -182,6 +182,9 @@ int lsq_ctx_destroy(lsq_ctx *c) {
     if (c->h_progress) cudaFreeHost(c->h_progress);
     for (auto &ev : c->ev)
         if (ev) cudaEventDestroy(ev);
+    for (auto &row : c->ev_set)
+        for (auto &ev : row)
+            if (ev) cudaEventDestroy(ev);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return LSQ_OK;
@@ -239,7 +242,8 @@ int lsq_upload_events(lsq_ctx *c, const lsq_event_tables *t) {
     LSQ_CUDA(upload(c->d_cov_start, H.cov_start, s));
     LSQ_CUDA(upload(c->d_cov_end, H.cov_end, s));
     LSQ_CUDA(upload(c->d_form_len, H.form_len, s));
-    LSQ_CUDA(upload(c->d_bkt_piece, H.bkt_piece, s));
+    LSQ_CUDA(upload(c->d_sig_cut, H.sig_cut, s));
+    LSQ_CUDA(upload(c->d_sig_piece, H.sig_piece, s));
     LSQ_CUDA(cudaStreamSynchronize(s));
 
     lsq::Tables &T = c->T;
@@ -260,7 +264,8 @@ int lsq_upload_events(lsq_ctx *c, const lsq_event_tables *t) {
     T.cov_off = c->d_cov_off.as<uint32_t>();
     T.cov_start = c->d_cov_start.as<int32_t>();
     T.cov_end = c->d_cov_end.as<int32_t>();
-    T.bkt_piece = c->d_bkt_piece.as<uint32_t>();
+    T.sig_cut = c->d_sig_cut.as<int32_t>();
+    T.sig_piece = c->d_sig_piece.as<uint32_t>();
     c->E = H.E;
     c->F = H.F;
     c->chrom_id.clear();
@@ -280,8 +285,7 @@ static int upload_G(lsq_ctx *c, uint32_t m, uint32_t read_type, uint64_t read_le
     LSQ_CUDA(c->d_G.ensure((size_t)LSQ_MAX_METHODS * std::max<uint32_t>(c->F, 1) * sizeof(double)));
     if (c->F)
         LSQ_CUDA(cudaMemcpyAsync(c->d_G.as<double>() + (size_t)m * c->F, G.data(), c->F * sizeof(double),
-                                 cudaMemcpyHostToDevice, c->stream));
-    LSQ_CUDA(cudaStreamSynchronize(c->stream));
+                                 cudaMemcpyHostToDevice, c->stream));  // pageable source: staged before the call returns
     return LSQ_OK;
 }
 
@@ -330,7 +334,7 @@ int lsq_set_reads(lsq_ctx *c, uint32_t m, uint32_t read_type, uint64_t read_leng
         rs.blk_cs = nullptr;
         rs.line_num = nullptr;
         rs.blk_off = nullptr;
-        const uint8_t *cnt = r->blk_cnt;
+        rs.blk_cnt = nullptr;
         if (rs.borrowed) {
             if (compact_blk) {
                 rs.blk_start = r->blk_start;
@@ -339,11 +343,22 @@ int lsq_set_reads(lsq_ctx *c, uint32_t m, uint32_t read_type, uint64_t read_leng
             } else {
                 rs.blk = reinterpret_cast<const int2 *>(r->blk);
             }
-            if (r->read_cs8) rs.read_cs8 = r->read_cs8;
-            else rs.read_cs = r->read_cs;
+            // the one-byte per-read arrays are read four reads at a time: own, padded copies (2 bytes per read)
+            if (r->read_cs8) {
+                LSQ_CUDA(rs.d_read_cs8.ensure(n + 4));
+                if (n) LSQ_CUDA(cudaMemcpyAsync(rs.d_read_cs8.p, r->read_cs8, n, kind, s));
+                rs.read_cs8 = rs.d_read_cs8.as<uint8_t>();
+            } else {
+                rs.read_cs = r->read_cs;
+            }
             rs.blk_cs = r->blk_cs;
             rs.line_num = r->line_num;
             rs.blk_off = r->blk_off;
+            if (r->blk_cnt) {
+                LSQ_CUDA(rs.d_blk_cnt.ensure(n + 4));
+                if (n) LSQ_CUDA(cudaMemcpyAsync(rs.d_blk_cnt.p, r->blk_cnt, n, kind, s));
+                rs.blk_cnt = rs.d_blk_cnt.as<uint8_t>();
+            }
         } else {
             // device buffers first (an allocation synchronises the device), then the copies: the per-read
             // arrays, then the blocks.  A streamed set (LSQ_READS_STREAM) puts all copies on the copy stream,
@@ -364,13 +379,13 @@ int lsq_set_reads(lsq_ctx *c, uint32_t m, uint32_t read_type, uint64_t read_leng
                 if (r->read_cs8) for (size_t i = 0; i < n && !any_mixed; ++i) any_mixed = (r->read_cs8[i] & 0x80u) != 0;
                 else for (size_t i = 0; i < n && !any_mixed; ++i) any_mixed = (r->read_cs[i] & LSQ_READ_MIXED) != 0;
             }
-            if (r->read_cs8) LSQ_CUDA(rs.d_read_cs8.ensure(std::max<size_t>(n, 1)));
+            if (r->read_cs8) LSQ_CUDA(rs.d_read_cs8.ensure(n + 4));
             else LSQ_CUDA(rs.d_read_cs.ensure(std::max<size_t>(n, 1) * 4));
             if (r->line_num) LSQ_CUDA(rs.d_line_num.ensure(std::max<size_t>(n, 1) * 4));
             if (any_mixed) LSQ_CUDA(rs.d_blk_cs.ensure(std::max<size_t>(nb, 1) * 4));
             const bool use_cnt = r->blk_cnt != nullptr;  // a quarter of the bytes of blk_off
-            LSQ_CUDA(rs.d_blk_off.ensure((n + 1) * 4));
-            if (use_cnt) LSQ_CUDA(rs.d_blk_cnt.ensure(std::max<size_t>(n, 1)));
+            if (use_cnt) LSQ_CUDA(rs.d_blk_cnt.ensure(n + 4));
+            else LSQ_CUDA(rs.d_blk_off.ensure((n + 1) * 4));
             if (rs.streamed) {
                 s = c->copy_stream;
                 LSQ_CUDA(cudaMemsetAsync(c->d_progress.as<uint32_t>() + m, 0, sizeof(uint32_t), s));
@@ -395,7 +410,7 @@ int lsq_set_reads(lsq_ctx *c, uint32_t m, uint32_t read_type, uint64_t read_leng
                 rs.blk_off = rs.d_blk_off.as<uint32_t>();
             } else {
                 if (n) LSQ_CUDA(cudaMemcpyAsync(rs.d_blk_cnt.p, r->blk_cnt, n, kind, s));
-                cnt = rs.d_blk_cnt.as<uint8_t>();
+                rs.blk_cnt = rs.d_blk_cnt.as<uint8_t>();
             }
             if (rs.streamed) LSQ_CUDA(cudaEventRecord(c->ev_small, s));
             size_t chunk = std::max<size_t>(nb, 1);
@@ -426,18 +441,20 @@ int lsq_set_reads(lsq_ctx *c, uint32_t m, uint32_t read_type, uint64_t read_leng
                 LSQ_CUDA(cudaStreamWaitEvent(s, c->ev_small, 0));
             }
         }
-        if (!rs.blk_off) {  // rebuild the CSR offsets from the per-read block counts on the device
-            LSQ_CUDA(rs.d_blk_off.ensure((n + 1) * 4));
-            LSQ_CUDA(cudaMemsetAsync(rs.d_blk_off.p, 0, 4, s));
-            if (n) {
-                cub::TransformInputIterator<uint32_t, U8ToU32, const uint8_t *> it(cnt, U8ToU32());
-                size_t tmp = 0;
-                cub::DeviceScan::InclusiveSum(nullptr, tmp, it, rs.d_blk_off.as<uint32_t>() + 1, (int64_t)n, s);
-                LSQ_CUDA(rs.d_scan_tmp.ensure(std::max<size_t>(tmp, 1)));
-                LSQ_CUDA(cub::DeviceScan::InclusiveSum(rs.d_scan_tmp.p, tmp, it, rs.d_blk_off.as<uint32_t>() + 1,
-                                                       (int64_t)n, s));
+        if (rs.blk_cnt) {  // block-offset index: first block of every group of SCAN_GROUP reads
+            const uint32_t n_groups = (uint32_t)((n + lsq::SCAN_GROUP - 1) / lsq::SCAN_GROUP);
+            const uint32_t n_super = (n_groups + lsq::SCAN_SUPER - 1) / lsq::SCAN_SUPER;
+            LSQ_CUDA(rs.d_grp_base.ensure(std::max<size_t>(n_groups, 1) * 4));
+            LSQ_CUDA(rs.d_sup_base.ensure(std::max<size_t>(n_super, 1) * 4));
+            if (n_groups) {
+                lsq::lsq_group_sum_kernel<<<n_super, lsq::SCAN_SUPER, 0, s>>>(rs.blk_cnt, n, n_groups, rs.d_grp_base.as<uint32_t>(),
+                                                                           rs.d_sup_base.as<uint32_t>());
+                LSQ_CUDA(cudaGetLastError());
+                lsq::lsq_super_scan_kernel<<<1, 1024, 0, s>>>(rs.d_sup_base.as<uint32_t>(), n_super);
+                LSQ_CUDA(cudaGetLastError());
             }
-            rs.blk_off = rs.d_blk_off.as<uint32_t>();
+        } else if (!rs.blk_off) {
+            return fail(LSQ_ERR_ARG, "lsq_set_reads: blk_off or blk_cnt is required");
         }
     }
     // dictionaries: file chromosome ids -> annotation ids; strand order table
@@ -454,7 +471,8 @@ int lsq_set_reads(lsq_ctx *c, uint32_t m, uint32_t read_type, uint64_t read_leng
     LSQ_CUDA(upload(rs.d_chrom_remap, remap, s));
     LSQ_CUDA(upload(rs.d_file_meta, fmeta, s));
     LSQ_CUDA(upload(rs.d_strand_tbl, tbl, s));
-    LSQ_CUDA(cudaStreamSynchronize(s));
+    // host buffers of a plain (not streamed) set are free again when this returns
+    if (!rs.borrowed && !rs.streamed) LSQ_CUDA(cudaStreamSynchronize(s));
     c->M = std::max(c->M, m + 1);
     c->counted = c->finalized = c->solved = false;
     return upload_G(c, m, read_type, read_length);
@@ -509,7 +527,7 @@ static int ensure_run_buffers(lsq_ctx *c) {
     LSQ_CUDA(c->d_slot_cnt.ensure(std::max<size_t>((size_t)m_slots * slots, 1) * 8));
     LSQ_CUDA(c->d_slot_mask.ensure(std::max<size_t>((size_t)m_slots * slots, 1) * 8));
     LSQ_CUDA(c->d_bases.ensure((size_t)LSQ_MAX_METHODS * E * 8));
-    LSQ_CUDA(c->d_counters.ensure(128 * 8));
+    LSQ_CUDA(c->d_counters.ensure((size_t)(LSQ_MAX_METHODS * lsq::CTR_N + 32) * 8));
     LSQ_CUDA(c->d_n_valid.ensure((size_t)LSQ_MAX_METHODS * E * 8));
     LSQ_CUDA(c->d_bases_out.ensure((size_t)LSQ_MAX_METHODS * E * 8));
     LSQ_CUDA(c->d_iso.ensure(F * 8));
@@ -548,7 +566,7 @@ static void fill_solve_params(lsq_ctx *c, lsq::SolveParams &P) {
     P.ll_per_read = c->d_llpr.as<double>();
     P.iters = c->d_iters.as<uint32_t>();
     P.max_iters = 10000000u;
-    P.pairs_valid = c->d_counters.as<unsigned long long>() + 110;
+    P.pairs_valid = c->d_counters.as<unsigned long long>() + LSQ_MAX_METHODS * lsq::CTR_N + 2;
 }
 
 static int run_finalize(lsq_ctx *c) {
@@ -565,6 +583,8 @@ static int run_finalize(lsq_ctx *c) {
     return LSQ_OK;
 }
 
+static inline size_t pad16(size_t bytes) { return (bytes + 15) & ~(size_t)15; }
+
 int lsq_count(lsq_ctx *c) {
     if (!c) return fail(LSQ_ERR_ARG, "null context");
     if (!c->have_tables) return fail(LSQ_ERR_STATE, "lsq_count before lsq_upload_events");
@@ -579,144 +599,123 @@ int lsq_count(lsq_ctx *c) {
     lsq_timings &tm = c->tm;
     memset(&tm, 0, sizeof tm);
     const uint32_t E = c->E;
-    float acc[5] = {0, 0, 0, 0, 0};
-    c->h_counters.assign((size_t)LSQ_MAX_METHODS * 4, 0);
     for (uint32_t m = 0; m < c->M; ++m) {
         ReadSet &rs = c->sets[m];
+        c->set_counted[m] = false;
         if (rs.injected) continue;
         const size_t n = rs.n_reads, nb = rs.n_blocks;
-        unsigned long long *slot_cnt = c->d_slot_cnt.as<unsigned long long>() + (size_t)m * T.total_slots;
-        unsigned long long *slot_mask = c->d_slot_mask.as<unsigned long long>() + (size_t)m * T.total_slots;
-        unsigned long long *bases = c->d_bases.as<unsigned long long>() + (size_t)m * E;
-        unsigned long long *counters = c->d_counters.as<unsigned long long>() + (size_t)m * 4;
         LSQ_CUDA(c->d_ext.ensure((nb + 2 * n + 2) * 8));
-        // partition state: every bin owns a current and a spare chunk from the start, and a further
-        // chunk is only allocated when a bin has filled one, so n / PART_CHUNK + 2 n_bins suffice
-        lsq::PartState PS;
-        PS.n_bins = 3u * T.n_bkt;
-        PS.pool_cap = (uint32_t)(n / lsq::PART_CHUNK) + 2u * PS.n_bins + 1u;
-        if ((uint64_t)PS.pool_cap * lsq::PART_CHUNK > 0xFFFFFFFFull)
-            return fail(LSQ_ERR_RANGE, "read set too large for 32-bit record slots");
-        {
-            const size_t cap = PS.pool_cap;
-            LSQ_CUDA(c->d_pool.ensure(cap * lsq::PART_CHUNK * sizeof(uint4)));
-            LSQ_CUDA(c->d_part.ensure((size_t)PS.n_bins * 12 + cap * 4 + 3 * cap * 4 + 64));
-            unsigned char *base = c->d_part.as<unsigned char>();
-            PS.state = reinterpret_cast<unsigned long long *>(base);
-            PS.next_chunk = reinterpret_cast<uint32_t *>(base + (size_t)PS.n_bins * 8);
-            PS.owner = PS.next_chunk + PS.n_bins;
-            PS.wl = PS.owner + cap;
-            PS.wl_n = PS.wl + 3 * cap;
-            PS.pool_next = PS.wl_n + 4;
-            PS.pool = c->d_pool.as<uint4>();
-        }
-        const size_t filt_smem = lsq::filter_smem_bytes(PS.n_bins);
-        if (!c->filter_smem_set) {
-            LSQ_CUDA(cudaFuncSetAttribute(lsq::lsq_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            LSQ_CUDA(cudaFuncSetAttribute(lsq::lsq_count_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)lsq::COUNT_FAST_DYN_SMEM));
-            c->filter_smem_set = true;
-        }
+        LSQ_CUDA(c->d_gen_list.ensure(std::max<size_t>(n, 1) * sizeof(uint2)));
+        // signature scratch: counters of the single-block signatures, hash of the two-block ones
+        const size_t n_sig = std::max<uint32_t>(T.n_sig, 1);
+        size_t want = std::min<size_t>(4 * (size_t)T.n_pieces, 2 * n);
+        size_t hcap = 1024;
+        while (hcap < want && hcap < ((size_t)1 << 28)) hcap <<= 1;
+        const size_t o_sig_dev = pad16(n_sig * 4), o_hash = o_sig_dev + pad16(n_sig * 8), o_hash_dev = o_hash + hcap * 16,
+                     o_gen_n = o_hash_dev + hcap * 8, scratch_bytes = o_gen_n + 16;
+        LSQ_CUDA(c->d_scratch.ensure(scratch_bytes));
+        unsigned char *sc = c->d_scratch.as<unsigned char>();
 
-        LSQ_CUDA(cudaEventRecord(c->ev[0], s));
-        LSQ_CUDA(cudaMemsetAsync(slot_cnt, 0, std::max<uint64_t>(T.total_slots, 1) * 8, s));
-        LSQ_CUDA(cudaMemsetAsync(slot_mask, 0, std::max<uint64_t>(T.total_slots, 1) * 8, s));
-        LSQ_CUDA(cudaMemsetAsync(bases, 0, std::max<uint32_t>(E, 1) * 8, s));
-        LSQ_CUDA(cudaMemsetAsync(counters, 0, 4 * 8, s));
-        if (n) {
-            lsq::FilterParams FP;
-            FP.T = T;
-            FP.n_reads = n;
-            FP.blk_off = rs.blk_off;
-            FP.blk = rs.blk;
-            FP.read_cs = rs.read_cs;
-            FP.read_cs8 = rs.read_cs8;
-            FP.blk_start = rs.blk_start;
-            FP.blk_len = rs.blk_len;
-            FP.blk_len8 = rs.blk_len8;
-            FP.blk_cs = rs.blk_cs;
-            FP.chrom_remap = rs.d_chrom_remap.as<uint32_t>();
-            FP.file_meta = rs.d_file_meta.as<uint4>();
-            FP.progress = rs.streamed ? c->d_progress.as<uint32_t>() + m : nullptr;
-            FP.ext = c->d_ext.as<int2>();
-            FP.part = PS;
-            FP.counters = counters;
-            lsq::lsq_part_init_kernel<<<(PS.n_bins + 255) / 256, 256, 0, s>>>(PS, T.n_bkt);
+        lsq::ScanParams P;
+        memset(&P, 0, sizeof P);
+        P.T = T;
+        P.n_reads = n;
+        P.blk_off = rs.blk_cnt ? nullptr : rs.blk_off;
+        P.blk_cnt = rs.blk_cnt;
+        P.grp_base = rs.d_grp_base.as<uint32_t>();
+        P.sup_base = rs.d_sup_base.as<uint32_t>();
+        P.blk = rs.blk;
+        P.read_cs = rs.read_cs;
+        P.read_cs8 = rs.read_cs8;
+        P.blk_start = rs.blk_start;
+        P.blk_len = rs.blk_len;
+        P.blk_len8 = rs.blk_len8;
+        P.blk_cs = rs.blk_cs;
+        P.chrom_remap = rs.d_chrom_remap.as<uint32_t>();
+        P.file_meta = rs.d_file_meta.as<uint4>();
+        P.progress = rs.streamed ? c->d_progress.as<uint32_t>() + m : nullptr;
+        P.line_num = rs.line_num;
+        P.strand_tbl = rs.d_strand_tbl.as<uint8_t>();
+        P.ext = c->d_ext.as<int2>();
+        P.sig_cnt = reinterpret_cast<uint32_t *>(sc);
+        P.sig_dev = reinterpret_cast<unsigned long long *>(sc + o_sig_dev);
+        P.hash = reinterpret_cast<ulonglong2 *>(sc + o_hash);
+        P.hash_dev = reinterpret_cast<unsigned long long *>(sc + o_hash_dev);
+        P.hash_mask = (uint32_t)(hcap - 1);
+        P.len0 = (uint32_t)std::min<uint64_t>(rs.read_length, 0x7FFFFFFFull);
+        P.gen_list = c->d_gen_list.as<uint2>();
+        P.gen_n = reinterpret_cast<uint32_t *>(sc + o_gen_n);
+        P.gen_cap = (uint32_t)std::min<size_t>(n, 0xFFFFFFFFull);
+        P.flags = c->scan_flags;
+        P.counters = c->d_counters.as<unsigned long long>() + (size_t)m * lsq::CTR_N;
+        P.slot_cnt = c->d_slot_cnt.as<unsigned long long>() + (size_t)m * T.total_slots;
+        P.slot_mask = c->d_slot_mask.as<unsigned long long>() + (size_t)m * T.total_slots;
+        P.bases = c->d_bases.as<unsigned long long>() + (size_t)m * E;
+
+        LSQ_CUDA(cudaEventRecord(c->ev_set[m][0], s));
+        {   // one launch clears the set's class tables, its counters and the signature scratch
+            lsq::ClearList L;
+            memset(&L, 0, sizeof L);
+            auto add = [&](void *p, size_t bytes) {
+                L.p[L.n] = reinterpret_cast<unsigned long long *>(p);
+                L.n8[L.n] = bytes / 8;
+                ++L.n;
+            };
+            add(P.slot_cnt, (size_t)T.total_slots * 8);
+            add(P.slot_mask, (size_t)T.total_slots * 8);
+            add(P.bases, (size_t)E * 8);
+            add(P.counters, lsq::CTR_N * 8);
+            add(sc, scratch_bytes);
+            lsq::lsq_clear_kernel<<<c->n_sms * 4, 256, 0, s>>>(L);
             LSQ_CUDA(cudaGetLastError());
-            LSQ_CUDA(cudaEventRecord(c->ev[1], s));
-            lsq::lsq_filter_kernel<<<(unsigned)((n + lsq::FILT_TILE - 1) / lsq::FILT_TILE), lsq::FILT_BLOCK, filt_smem, s>>>(FP);
-            LSQ_CUDA(cudaGetLastError());
-            lsq::lsq_part_stats_kernel<<<(PS.n_bins + 255) / 256, 256, 0, s>>>(PS, T.n_bkt, counters);
-            LSQ_CUDA(cudaGetLastError());
-            tm.launches += 3;
-        } else {
-            LSQ_CUDA(cudaEventRecord(c->ev[1], s));
+            tm.launches++;
         }
-        if (rs.streamed) {  // the caller's buffers are free again
+        LSQ_CUDA(cudaEventRecord(c->ev_set[m][1], s));
+        if (n) {
+            const uint64_t n_groups = (n + lsq::SCAN_GROUP - 1) / lsq::SCAN_GROUP;
+            const unsigned grid = (unsigned)std::min<uint64_t>((n_groups + lsq::SCAN_WARPS - 1) / lsq::SCAN_WARPS, (uint64_t)c->n_sms * lsq::SCAN_MINB);
+            lsq::lsq_scan_kernel<<<grid, lsq::SCAN_BLOCK, 0, s>>>(P);
+            LSQ_CUDA(cudaGetLastError());
+            tm.launches++;
+        }
+        if (rs.streamed) {  // the caller's buffers are free again once the copy has finished
             LSQ_CUDA(cudaStreamWaitEvent(s, c->ev_all[m], 0));
-            rs.copy_pending = false;
         }
-        LSQ_CUDA(cudaEventRecord(c->ev[2], s));
+        LSQ_CUDA(cudaEventRecord(c->ev_set[m][2], s));
         if (n) {
-            lsq::CountParams CP;
-            CP.T = T;
-            CP.part = PS;
-            CP.ext = c->d_ext.as<int2>();
-            CP.line_num = rs.line_num;
-            CP.strand_tbl = rs.d_strand_tbl.as<uint8_t>();
-            CP.slot_cnt = slot_cnt;
-            CP.slot_mask = slot_mask;
-            CP.bases = bases;
-            CP.stats = counters + 1;  // ext slots read by the GENERAL instantiation
-            // the work lists are only known on the device: every instantiation gets a grid of
-            // resident blocks that stride over its own list
-            unsigned grid_f = (unsigned)std::min<size_t>(PS.pool_cap, (size_t)c->n_sms * 4);
-            unsigned grid_g = (unsigned)std::min<size_t>(PS.pool_cap, (size_t)c->n_sms * 3);
-            lsq::lsq_count_kernel<0><<<grid_f, lsq::COUNT_BLOCK, lsq::COUNT_FAST_DYN_SMEM, s>>>(CP);
+            const uint64_t n_exp = (uint64_t)T.n_sig + hcap;
+            lsq::lsq_expand_kernel<<<(unsigned)((n_exp + 127) / 128), 128, 0, s>>>(P);
             LSQ_CUDA(cudaGetLastError());
-            lsq::lsq_count_kernel<1><<<grid_g, lsq::COUNT_BLOCK, 0, s>>>(CP);
-            LSQ_CUDA(cudaGetLastError());
-            lsq::lsq_count_kernel<2><<<grid_g, lsq::COUNT_BLOCK, 0, s>>>(CP);
-            LSQ_CUDA(cudaGetLastError());
-            tm.launches += 3;
-            tm.count_launches += 3;
+            tm.launches++;
         }
-        LSQ_CUDA(cudaEventRecord(c->ev[3], s));
-        LSQ_CUDA(cudaMemcpyAsync(c->h_counters.data() + (size_t)m * 4, counters, 4 * 8, cudaMemcpyDeviceToHost, s));
-        LSQ_CUDA(cudaStreamSynchronize(s));
-        float f;
-        LSQ_CUDA(cudaEventElapsedTime(&f, c->ev[0], c->ev[1]));  // counter resets + partition init
-        acc[1] += f;
-        LSQ_CUDA(cudaEventElapsedTime(&f, c->ev[1], c->ev[2]));  // filter + partition kernel
-        acc[0] += f;
-        LSQ_CUDA(cudaEventElapsedTime(&f, c->ev[2], c->ev[3]));
-        acc[3] += f;
-        const unsigned long long *hc = c->h_counters.data() + (size_t)m * 4;
-        const unsigned long long kept = hc[0] + hc[2] + hc[3];  // FAST + PAIR + GENERAL reads
+        LSQ_CUDA(cudaEventRecord(c->ev_set[m][3], s));
+        if (n) {
+            lsq::lsq_general_kernel<<<c->n_sms * 8, 128, 0, s>>>(P);
+            LSQ_CUDA(cudaGetLastError());
+            tm.launches++;
+        }
+        LSQ_CUDA(cudaEventRecord(c->ev_set[m][4], s));
+        c->set_counted[m] = true;
         tm.reads_in += n;
-        tm.reads_kept += kept;
-        // algorithmic bytes of the count kernels: one 16-byte partitioned record per kept read, plus the ext
-        // entry (8-byte header + 8 bytes per kept block) of every GENERAL-class read
-        tm.count_bytes += kept * 16ull + hc[1] * 8ull;
+        tm.blocks_in += nb;
     }
     c->counted = true;
     c->finalized = false;
     c->solved = false;
-    LSQ_CUDA(cudaEventRecord(c->ev[4], s));
+    LSQ_CUDA(cudaEventRecord(c->ev[0], s));
     rc = run_finalize(c);
     if (rc) return rc;
-    LSQ_CUDA(cudaEventRecord(c->ev[5], s));
-    unsigned long long pv = 0;
-    LSQ_CUDA(cudaMemcpyAsync(&pv, c->d_counters.as<unsigned long long>() + 110, 8, cudaMemcpyDeviceToHost, s));
-    LSQ_CUDA(cudaStreamSynchronize(s));
-    tm.pairs_valid = pv;
-    float f;
-    LSQ_CUDA(cudaEventElapsedTime(&f, c->ev[4], c->ev[5]));
-    tm.filter_ms = acc[0];
-    tm.index_ms = acc[1];
-    tm.count_ms = acc[3];
-    tm.count_kernel_ms = acc[3];
-    tm.finalize_ms = f;
+    LSQ_CUDA(cudaEventRecord(c->ev[1], s));
+    c->tm_count_pending = true;
+    c->tm_solve_pending = false;
+    // streamed sets: the contract is that the host buffers are free when lsq_count returns
+    for (uint32_t m = 0; m < c->M; ++m) {
+        ReadSet &rs = c->sets[m];
+        if (!rs.injected && rs.streamed && rs.copy_pending) {
+            LSQ_CUDA(cudaEventSynchronize(c->ev_all[m]));
+            rs.copy_pending = false;
+        }
+    }
     return LSQ_OK;
 }
 
@@ -815,8 +814,8 @@ int lsq_solve(lsq_ctx *c, const double *total_read_bases, uint32_t n_methods) {
     bool small = c->M <= 2;
     for (uint32_t m = 0; m < c->M; ++m) small = small && !c->sets[m].injected;
     P.small_enabled = small ? 1 : 0;
-    P.work_counter = reinterpret_cast<unsigned int *>(c->d_counters.as<unsigned long long>() + 100);
-    LSQ_CUDA(cudaEventRecord(c->ev[6], s));
+    P.work_counter = reinterpret_cast<unsigned int *>(c->d_counters.as<unsigned long long>() + LSQ_MAX_METHODS * lsq::CTR_N);
+    LSQ_CUDA(cudaEventRecord(c->ev[2], s));
     if (c->E && small) {
         LSQ_CUDA(cudaMemsetAsync(P.work_counter, 0, sizeof(unsigned int), s));
         unsigned grid = std::min<unsigned>((c->E + 127) / 128, (unsigned)c->n_sms * 8u);
@@ -832,9 +831,8 @@ int lsq_solve(lsq_ctx *c, const double *total_read_bases, uint32_t n_methods) {
         LSQ_CUDA(cudaGetLastError());
         c->tm.launches++;
     }
-    LSQ_CUDA(cudaEventRecord(c->ev[7], s));
-    LSQ_CUDA(cudaStreamSynchronize(s));
-    LSQ_CUDA(cudaEventElapsedTime(&c->tm.solve_ms, c->ev[6], c->ev[7]));
+    LSQ_CUDA(cudaEventRecord(c->ev[3], s));
+    c->tm_solve_pending = true;
     c->solved = true;
     return LSQ_OK;
 }
@@ -871,7 +869,40 @@ int lsq_get_device_results(lsq_ctx *c, lsq_device_results *o) {
 
 int lsq_get_timings(lsq_ctx *c, lsq_timings *o) {
     if (!c || !o) return fail(LSQ_ERR_ARG, "lsq_get_timings: null argument");
-    *o = c->tm;
+    LSQ_CUDA(cudaSetDevice(c->device));
+    if (c->tm_count_pending || c->tm_solve_pending) LSQ_CUDA(cudaStreamSynchronize(c->stream));
+    lsq_timings &tm = c->tm;
+    if (c->tm_count_pending) {
+        std::vector<unsigned long long> hc((size_t)LSQ_MAX_METHODS * lsq::CTR_N + 4, 0);
+        LSQ_CUDA(cudaMemcpy(hc.data(), c->d_counters.p, hc.size() * 8, cudaMemcpyDeviceToHost));
+        tm.clear_ms = tm.scan_ms = tm.expand_ms = tm.general_ms = 0.f;
+        tm.reads_single = tm.reads_pair = tm.reads_general = tm.hash_full = 0;
+        for (uint32_t m = 0; m < c->M; ++m) {
+            if (!c->set_counted[m]) continue;
+            float f;
+            LSQ_CUDA(cudaEventElapsedTime(&f, c->ev_set[m][0], c->ev_set[m][1]));
+            tm.clear_ms += f;
+            LSQ_CUDA(cudaEventElapsedTime(&f, c->ev_set[m][1], c->ev_set[m][2]));
+            tm.scan_ms += f;
+            LSQ_CUDA(cudaEventElapsedTime(&f, c->ev_set[m][2], c->ev_set[m][3]));
+            tm.expand_ms += f;
+            LSQ_CUDA(cudaEventElapsedTime(&f, c->ev_set[m][3], c->ev_set[m][4]));
+            tm.general_ms += f;
+            const unsigned long long *k = hc.data() + (size_t)m * lsq::CTR_N;
+            tm.reads_single += k[lsq::CTR_SINGLE_SIG];
+            tm.reads_pair += k[lsq::CTR_PAIR_SIG];
+            tm.reads_general += k[lsq::CTR_GENERAL];
+            tm.hash_full += k[lsq::CTR_HASH_FULL];
+        }
+        tm.pairs_valid = hc[(size_t)LSQ_MAX_METHODS * lsq::CTR_N + 2];
+        LSQ_CUDA(cudaEventElapsedTime(&tm.finalize_ms, c->ev[0], c->ev[1]));
+        c->tm_count_pending = false;
+    }
+    if (c->tm_solve_pending) {
+        LSQ_CUDA(cudaEventElapsedTime(&tm.solve_ms, c->ev[2], c->ev[3]));
+        c->tm_solve_pending = false;
+    }
+    *o = tm;
     return LSQ_OK;
 }
 

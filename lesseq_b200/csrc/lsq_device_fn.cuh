@@ -108,8 +108,8 @@ LSQ_HD uint32_t find_piece(const Tables &T, uint32_t c, int32_t x, PieceInfo &ou
     const uint4 raw = LSQ_LD(reinterpret_cast<const uint4 *>(T.pinfo + p));
     out.pos = (int32_t)raw.x;
     out.cov_end = (int32_t)raw.y;
-    out.stab_off = raw.z;
-    out.stab_n = raw.w;
+    out.sigw = raw.z;
+    out.cutw = raw.w;
     return p;
 }
 
@@ -145,63 +145,20 @@ LSQ_HD uint32_t list_add(int2 *L, uint32_t n, int32_t s, int32_t e) {
 }
 
 
-// Read classes (see ReadRec): the table-driven evaluator handles FAST reads, everything else
-// (several kept blocks, a start on the first position of a piece -- the only place the
-// lower_bound tie-break can apply --, or an over-long block) goes through the general walk.
-constexpr uint32_t FAST_MAX_LEN = 0xFFFFu;
-LSQ_HD bool is_fast_read(uint32_t n, uint32_t at_piece_start, int2 first, uint32_t piece_stab_n) {
-    return n == 1u && !at_piece_start && (uint32_t)(first.y - first.x) <= FAST_MAX_LEN &&
-           (piece_stab_n & PIECE_ALL_FAST) != 0;
-}
-
-// Slot of read r's ext entry (GENERAL class): even, so the entry is 16-byte aligned; entries of
+// Slot of read r's scratch entry in ext[]: even, so the entry is 16-byte aligned; entries of
 // consecutive reads cannot overlap because an entry has at most 1 + (raw blocks of r) slots.
 LSQ_HD uint32_t ext_slot(uint32_t blk_off_r, uint32_t r) { return (blk_off_r + 2u * r) & ~1u; }
 
-// Sort key of a read that is a candidate of no event: one past the largest real key.
-LSQ_HD uint32_t KEY_DROPPED(const Tables &T) { return T.n_pieces * 3u; }
-
-// PAIR class: exactly two kept blocks, not on the first position of the piece, and everything fits
-// the 8-byte record: x = (start - piece start) [16 bits] | length of block 0 [11 bits] << 16,
-// y = (gap between the blocks - 1) [22 bits] | length of block 1 [... 8 low bits << 22 | strand << 30]
-// -- see pack_pair / unpack_pair.  Such reads are evaluated by the general walk straight from
-// registers, without an ext entry.
-constexpr uint32_t PAIR_MAX_OFF = 0xFFFFu, PAIR_MAX_LEN = 0x7FFu, PAIR_MAX_GAP = 0x3FFFFFu;
-LSQ_HD bool is_pair_read(uint32_t n, uint32_t at_piece_start, int2 b0, int2 b1, int32_t piece_pos, uint32_t strand) {
-    return n == 2u && !at_piece_start && (uint32_t)(b0.x - piece_pos) <= PAIR_MAX_OFF &&
-           (uint32_t)(b0.y - b0.x) <= PAIR_MAX_LEN && (uint32_t)(b1.y - b1.x) <= PAIR_MAX_LEN && b1.x > b0.y &&
-           (uint32_t)(b1.x - b0.y - 1) <= PAIR_MAX_GAP && strand < 4u;
-}
-LSQ_HD ReadRec pack_pair(int2 b0, int2 b1, int32_t piece_pos, uint32_t strand) {
-    ReadRec r;
-    const uint32_t len1 = (uint32_t)(b1.y - b1.x);
-    r.x = (uint32_t)(b0.x - piece_pos) | ((uint32_t)(b0.y - b0.x) << 16) | ((len1 & 0x1Fu) << 27);
-    r.y = (uint32_t)(b1.x - b0.y - 1) | ((len1 >> 5) << 22) | (strand << 28);
-    return r;
-}
-LSQ_HD void unpack_pair(ReadRec r, int32_t piece_pos, int2 &b0, int2 &b1, uint32_t &strand) {
-    const uint32_t len0 = (r.x >> 16) & 0x7FFu, len1 = ((r.x >> 27) & 0x1Fu) | (((r.y >> 22) & 0x3Fu) << 5);
-    b0.x = piece_pos + (int32_t)(r.x & 0xFFFFu);
-    b0.y = b0.x + (int32_t)len0;
-    b1.x = b0.y + 1 + (int32_t)(r.y & 0x3FFFFFu);
-    b1.y = b1.x + (int32_t)len1;
-    strand = r.y >> 28;
-}
-
 // Result of the per-read load filter.
-constexpr uint32_t CLS_FAST = 0, CLS_PAIR = 1, CLS_GENERAL = 2, CLS_DROPPED = 3;
 struct FilteredRead {
     uint32_t n;       // kept intervals (0: read dropped)
-    uint32_t key;     // piece (FAST), n_pieces + piece (PAIR), 2 n_pieces + piece (GENERAL), KEY_DROPPED
-    uint32_t cls;     // CLS_*: key / n_pieces
-    uint32_t piece;   // key - cls * n_pieces (undefined when dropped)
-    uint32_t stab_off;  // first stab entry of the piece: selects the stab bucket
-    uint32_t stab_n;    // stab entries of the piece
-    int2 second;      // second kept interval (n >= 2)
-    int32_t piece_pos;  // first position of the read's piece
-    int2 first;       // first kept interval
+    uint32_t piece;   // piece holding the start of the first kept interval; PIECE_NONE: candidate of no event
+    uint32_t piece2;  // piece holding the start of the second kept interval when known, else PIECE_NONE
     uint32_t strand;  // file strand id of the last registered block
-    uint32_t at_piece_start;  // 1 when the first kept start is the first position of its piece
+    uint32_t mixed;   // the read's blocks carry their own chromosome/strand ids (chimeric read)
+    int2 first;       // first kept interval
+    int2 second;      // second kept interval (n >= 2)
+    uint4 raw;        // PieceInfo of `piece` (pos, cov_end, sigw, cutw)
 };
 
 // count.cpp:297-327 for one read: every block is tested against the covered regions of its
@@ -210,7 +167,7 @@ struct FilteredRead {
 // registered block; the stab piece is looked up for the first kept start.
 // The filter is written against a read context that says where its inputs come from, so that the
 // kernel can hand it blocks, lookup answers and piece records it has already fetched (several
-// reads at a time) while the CPU replay and the fallback path fetch on demand:
+// reads at a time) while the CPU replay and the general kernel fetch on demand:
 //   ctx.blk(j)          raw block j of the read
 //   ctx.lookup(j, c, b) for block j = [b.x, b.y) on chromosome c: the piece holding b.x in bits
 //                       0-30 (PIECE_NONE: before the first piece) and, in bit 31, whether the
@@ -219,7 +176,7 @@ struct FilteredRead {
 constexpr uint32_t PIECE_NONE = 0x7FFFFFFFu;
 
 // Raw block i and the ids of read r, from the wide or the compact representation of the read set.
-LSQ_HD int2 load_block(const FilterParams &P, uint32_t i) {
+LSQ_HD int2 load_block(const ScanParams &P, uint32_t i) {
     if (P.blk_start != nullptr) {
         const int32_t s = LSQ_LD(P.blk_start + i);
         const int32_t len = P.blk_len8 != nullptr ? (int32_t)LSQ_LD(P.blk_len8 + i) : (int32_t)LSQ_LD(P.blk_len + i);
@@ -227,7 +184,7 @@ LSQ_HD int2 load_block(const FilterParams &P, uint32_t i) {
     }
     return LSQ_LD(P.blk + i);
 }
-LSQ_HD int2 load_block_stream(const FilterParams &P, uint32_t i) {
+LSQ_HD int2 load_block_stream(const ScanParams &P, uint32_t i) {
     if (P.blk_start != nullptr) {
         const int32_t s = LSQ_LD_STREAM(P.blk_start + i);
         const int32_t len = P.blk_len8 != nullptr ? (int32_t)LSQ_LD_STREAM(P.blk_len8 + i) : (int32_t)LSQ_LD_STREAM(P.blk_len + i);
@@ -235,12 +192,15 @@ LSQ_HD int2 load_block_stream(const FilterParams &P, uint32_t i) {
     }
     return LSQ_LD_STREAM(P.blk + i);
 }
-LSQ_HD uint32_t load_read_cs(const FilterParams &P, uint64_t r) {
-    if (P.read_cs8 != nullptr) {
-        const uint32_t v = LSQ_LD_STREAM(P.read_cs8 + r);
-        return (v & 0x3Fu) | ((v & 0x40u) << 10) | ((v & 0x80u) << 24);
-    }
+LSQ_HD uint32_t expand_cs8(uint32_t v) { return (v & 0x3Fu) | ((v & 0x40u) << 10) | ((v & 0x80u) << 24); }
+LSQ_HD uint32_t load_read_cs(const ScanParams &P, uint64_t r) {
+    if (P.read_cs8 != nullptr) return expand_cs8(LSQ_LD_STREAM(P.read_cs8 + r));
     return LSQ_LD_STREAM(P.read_cs + r);
+}
+// Raw blocks of read r (the general kernel's access path; the scan kernel reads whole groups).
+LSQ_HD uint32_t load_read_nraw(const ScanParams &P, uint64_t r) {
+    if (P.blk_cnt != nullptr) return LSQ_LD(P.blk_cnt + r);
+    return LSQ_LD(P.blk_off + r + 1) - LSQ_LD(P.blk_off + r);
 }
 
 LSQ_HD uint32_t lookup_direct(const Tables &T, uint32_t c, int2 b) {
@@ -251,30 +211,27 @@ LSQ_HD uint32_t lookup_direct(const Tables &T, uint32_t c, int2 b) {
 }
 
 struct DirectCtx {  // everything on demand, lookups through find_piece
-    const FilterParams &P;
+    const ScanParams &P;
     uint32_t base;
-    LSQ_HD int2 blk(uint32_t j) const { return load_block_stream(P, base + j); }
+    LSQ_HD int2 blk(uint32_t j) const { return load_block(P, base + j); }
     LSQ_HD uint32_t lookup(uint32_t, uint32_t c, int2 b) const { return lookup_direct(P.T, c, b); }
     LSQ_HD uint4 pinfo(uint32_t p) const { return LSQ_LD(reinterpret_cast<const uint4 *>(P.T.pinfo + p)); }
 };
 
 template <class Ctx>
-LSQ_HD FilteredRead filter_read_t(const FilterParams &P, uint64_t r, uint32_t base, uint32_t nraw, uint32_t cs0,
+LSQ_HD FilteredRead filter_read_t(const ScanParams &P, uint64_t r, uint32_t base, uint32_t nraw, uint32_t cs0,
                                   const Ctx &ctx) {
     const Tables &T = P.T;
     FilteredRead out;
     out.n = 0;
-    out.key = KEY_DROPPED(T);
+    out.piece = PIECE_NONE;
+    out.piece2 = PIECE_NONE;
     out.first = make_int2(0, 0);
     out.strand = 0;
-    out.at_piece_start = 0;
     out.second = make_int2(0, 0);
-    out.piece_pos = 0;
-    out.cls = CLS_DROPPED;
-    out.piece = 0;
-    out.stab_off = 0;
-    out.stab_n = 0;
+    out.raw = make_uint4(0u, 0u, 0u, 0u);
     const bool mixed = (cs0 & 0x80000000u) != 0;
+    out.mixed = mixed ? 1u : 0u;
     uint32_t chrom = 0xFFFFFFFFu;  // annotation id of the last registered block
     bool registered = false;
     int32_t last_end = 0;
@@ -287,6 +244,7 @@ LSQ_HD FilteredRead filter_read_t(const FilterParams &P, uint64_t r, uint32_t ba
     bool spilled = false;
     uint32_t first_chrom = 0xFFFFFFFFu;
     uint32_t first_piece = 0xFFFFFFFFu;  // piece of `first` when it was found while filtering
+    uint32_t second_piece = PIECE_NONE;  // piece of `second` likewise
     bool first_valid = false;
     for (uint32_t j = 0; j < nraw; ++j) {
         const int2 b = ctx.blk(j);
@@ -327,6 +285,7 @@ LSQ_HD FilteredRead filter_read_t(const FilterParams &P, uint64_t r, uint32_t ba
             } else {
                 if (n == 1) {
                     second = b;
+                    second_piece = pidx;
                     if (spilled) work[1] = b;  // an earlier merge already moved the list to the ext entry
                 } else {
                     if (!spilled) {
@@ -349,55 +308,31 @@ LSQ_HD FilteredRead filter_read_t(const FilterParams &P, uint64_t r, uint32_t ba
             first_valid = first_valid && work[0].x == first.x;
             first = work[0];
             if (n >= 2) second = work[1];
+            second_piece = PIECE_NONE;
             last_end = work[n - 1].y;
         }
     }
     out.n = n;
     out.first = first;
+    if (n >= 2) {
+        out.second = second;
+        out.piece2 = second_piece;
+    }
     if (registered && n > 0 && chrom != 0xFFFFFFFFu) {
         // the read's chromosome is that of the LAST registered block; the piece found while
         // filtering is reused when it was looked up on that chromosome for this very start
         uint32_t p = first_piece;
-        PieceInfo pi;
         if (!first_valid || first_chrom != chrom) {
+            PieceInfo pi;
             p = find_piece(T, chrom, first.x, pi);
+            out.raw = make_uint4((uint32_t)pi.pos, (uint32_t)pi.cov_end, pi.sigw, pi.cutw);
+            out.piece2 = PIECE_NONE;
         } else {
-            const uint4 raw = ctx.pinfo(p);
-            pi.pos = (int32_t)raw.x;
-            pi.cov_end = (int32_t)raw.y;
-            pi.stab_off = raw.z;
-            pi.stab_n = raw.w;
+            out.raw = ctx.pinfo(p);
         }
-        if (p != 0xFFFFFFFFu && (pi.stab_n & ~PIECE_ALL_FAST) > 0) {
-            out.at_piece_start = pi.pos == first.x ? 1u : 0u;
-            out.piece_pos = pi.pos;
-            if (n >= 2) out.second = second;
-            if (is_fast_read(n, out.at_piece_start, first, pi.stab_n)) out.cls = CLS_FAST;
-            else if (is_pair_read(n, out.at_piece_start, first, out.second, pi.pos, out.strand)) out.cls = CLS_PAIR;
-            else out.cls = CLS_GENERAL;
-            out.key = out.cls * T.n_pieces + p;
-            out.piece = p;
-            out.stab_off = pi.stab_off;
-            out.stab_n = pi.stab_n & ~PIECE_ALL_FAST;
-        }
+        if (p != 0xFFFFFFFFu && (out.raw.z & PIECE_CAND)) out.piece = p;
     }
     return out;
-}
-
-// The ext entry of a GENERAL read: header {read index, (strand << 24) | n} at its slot, then the
-// kept blocks.  Blocks 2.. were spilled by the filter; the first two come from its registers.
-LSQ_HD void write_ext_entry(int2 *ext, uint32_t off, uint32_t r, const FilteredRead &fr) {
-    ext[off] = make_int2((int32_t)r, (int32_t)((fr.strand << 24) | (fr.n & 0xFFFFFFu)));
-    ext[off + 1] = fr.first;
-    if (fr.n >= 2u) ext[off + 2] = fr.second;
-}
-
-LSQ_HD FilteredRead filter_read(const FilterParams &P, uint64_t r) {
-    const uint32_t base = LSQ_LD_STREAM(P.blk_off + r);
-    const uint32_t nraw = LSQ_LD_STREAM(P.blk_off + r + 1) - base;
-    const uint32_t cs0 = load_read_cs(P, r);
-    const DirectCtx ctx{P, base};
-    return filter_read_t(P, r, base, nraw, cs0, ctx);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -416,7 +351,7 @@ struct BlockProbe {
     uint32_t xo;     // offset of b.x inside its bucket (SP_SUB: inside its sub-bucket)
 };
 
-LSQ_HD int block_stage_chrom(const FilterParams &P, int2 b, uint32_t cs, BlockProbe &q) {
+LSQ_HD int block_stage_chrom(const ScanParams &P, int2 b, uint32_t cs, BlockProbe &q) {
     q.b = b;
     q.c = cs & 0xFFFFu;
     q.lo = 0;
@@ -458,7 +393,7 @@ LSQ_HD int block_stage_sub(const Tables &T, const BlockProbe &q, uint2 e, uint32
 }
 
 // SP_DEFER: the full search.
-LSQ_HD uint32_t block_stage_defer(const FilterParams &P, const BlockProbe &q) {
+LSQ_HD uint32_t block_stage_defer(const ScanParams &P, const BlockProbe &q) {
     return lookup_direct(P.T, LSQ_LD(P.chrom_remap + q.c), q.b);
 }
 
@@ -468,7 +403,7 @@ LSQ_HD uint32_t block_stage_answer(const BlockProbe &q, uint32_t p, int32_t cov_
 }
 
 // Sequential composition of the stages (CPU replay; the kernel runs the same stages batched).
-LSQ_HD uint32_t block_lookup(const FilterParams &P, int2 b, uint32_t cs) {
+LSQ_HD uint32_t block_lookup(const ScanParams &P, int2 b, uint32_t cs) {
     BlockProbe q;
     int st = block_stage_chrom(P, b, cs, q);
     if (st == SP_DROP) return PIECE_NONE;
@@ -483,64 +418,171 @@ LSQ_HD uint32_t block_lookup(const FilterParams &P, int2 b, uint32_t cs) {
     return res;
 }
 
-// The filter for the common read -- exactly one raw block b, chromosome/strand ids from read_cs --
-// given the lookup answer `res` of that block (nil blocks and blocks on chromosomes without
-// annotation answer PIECE_NONE) and, for a kept block, the PieceInfo `raw` of the answered piece.
-// Same result as filter_read_t on such a read, without its interval-list machinery.
-LSQ_HD bool single_kept(uint32_t res) { return (res & PIECE_NONE) != PIECE_NONE && (res >> 31) != 0u; }
-LSQ_HD FilteredRead single_decide(const Tables &T, int2 b, uint32_t cs0, uint32_t res, uint4 raw) {
-    FilteredRead out;
-    out.n = 0;
-    out.key = KEY_DROPPED(T);
-    out.first = b;
-    out.strand = (cs0 >> 16) & 0xFFu;
-    out.at_piece_start = 0;
-    out.second = make_int2(0, 0);
-    out.piece_pos = 0;
-    out.cls = CLS_DROPPED;
-    out.piece = 0;
-    out.stab_off = 0;
-    out.stab_n = 0;
-    if (!single_kept(res)) return out;
-    out.n = 1;
-    const uint32_t stab_n = raw.w;
-    if ((stab_n & ~PIECE_ALL_FAST) == 0u) return out;  // candidate of no event
-    const uint32_t p = res & PIECE_NONE;
-    out.at_piece_start = (int32_t)raw.x == b.x ? 1u : 0u;
-    out.piece_pos = (int32_t)raw.x;
-    out.cls = is_fast_read(1u, out.at_piece_start, b, stab_n) ? CLS_FAST : CLS_GENERAL;
-    out.key = out.cls * T.n_pieces + p;
-    out.piece = p;
-    out.stab_off = raw.z;
-    out.stab_n = stab_n & ~PIECE_ALL_FAST;
-    return out;
+// ---------------------------------------------------------------------------------------------
+// Signature routing.  The walk of common/read.h:204-274 for a read whose first kept block starts in
+// piece p depends on the read only through (a) where its block ends fall among the cuts of their pieces
+// (PieceInfo), (b) whether a later block starts exactly on a piece start, and -- through the validity
+// rule matched/total > 0.98 (count.cpp:441-442) -- (c) the lengths, but only when some event matches the
+// read PARTLY.  So reads are counted per SIGNATURE and every distinct signature is evaluated once, on a
+// representative read, by the general evaluator (sig_rep_single / sig_rep_pair + eval_pair in
+// lsq_expand_kernel).  A read takes that route only when every partial match is certainly invalid
+// (the missing part is at least total/50 long, so matched/total <= 0.98 in exact arithmetic and the IEEE
+// quotient cannot exceed the double nearest 0.98); then a (read, event) pair is valid iff it matches fully,
+// which the signature decides, and its matched length is the read's total length.  Everything else goes
+// to lsq_general_kernel, which walks the read itself.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t RT_NONE = 0, RT_SINGLE = 1, RT_PAIR = 2, RT_GENERAL = 3;
+
+// Number of cuts of the piece `raw` below block end e (the block starts inside the piece); exact: e hits cut k;
+// q_prev: the largest cut below e (k > 0).
+LSQ_HD uint32_t cut_category(const Tables &T, uint4 raw, int32_t e, bool &exact, int32_t &q_prev) {
+    const uint32_t n = piece_ncuts(raw.z), so = raw.z & PIECE_SIG_MASK;
+    const int32_t pos = (int32_t)raw.x;
+    uint32_t k = 0;
+    int32_t q = 0;
+    q_prev = pos;
+    LSQ_NO_UNROLL
+    while (k < n) {
+        q = k == 0u ? pos + (int32_t)(raw.w & 0xFFFFu) : (k == 1u ? pos + (int32_t)(raw.w >> 16) : LSQ_LD(T.sig_cut + so + k));
+        if (!(q < e)) break;
+        q_prev = q;
+        ++k;
+    }
+    exact = k < n && q == e;
+    return k;
 }
 
-// The load filter as the kernel runs it: every block answered by block_lookup, single-block reads
-// decided by single_decide, all others by filter_read_t.
-struct StagedCtx {
-    const FilterParams &P;
-    uint32_t base, cs0;
-    LSQ_HD int2 blk(uint32_t j) const { return load_block_stream(P, base + j); }
-    LSQ_HD uint32_t lookup(uint32_t j, uint32_t, int2 b) const {
-        const uint32_t cs = (cs0 & 0x80000000u) ? LSQ_LD(P.blk_cs + base + j) : cs0;
-        return block_lookup(P, b, cs);
+// missing * 50 >= total: a match that misses `missing` of `total` bases fails matched/total > 0.98
+LSQ_HD bool surely_invalid(uint32_t missing, uint32_t total) { return (uint64_t)missing * 50ull >= (uint64_t)total; }
+
+// One kept block b of a read whose piece record is `raw` (a candidate piece): RT_SINGLE with the signature
+// slot, RT_NONE (valid for no event), or RT_GENERAL.
+LSQ_HD uint32_t route_single(const Tables &T, int2 b, uint4 raw, uint32_t &sig) {
+    sig = 0;
+    const uint32_t n = piece_ncuts(raw.z);
+    if (n == PIECE_NO_SIG) return RT_GENERAL;
+    if ((raw.z & PIECE_TIE) && (int32_t)raw.x == b.x) return RT_GENERAL;  // the lower_bound tie-break may apply
+    bool exact;
+    int32_t q_prev;
+    const uint32_t k = cut_category(T, raw, b.y, exact, q_prev);
+    // events whose chain ends below b.y match the read up to a cut <= q_prev only
+    if (k > 0u && !surely_invalid((uint32_t)(b.y - q_prev), (uint32_t)(b.y - b.x))) return RT_GENERAL;
+    if (k == n) return RT_NONE;  // the block runs past every chain
+    sig = (raw.z & PIECE_SIG_MASK) + k;
+    return RT_SINGLE;
+}
+
+// Two kept blocks b0 < b1 (disjoint, not abutting) on one chromosome; raw0 / raw1 the piece records of
+// their starts (raw0 a candidate piece).  RT_PAIR with the signature key, RT_NONE or RT_GENERAL.
+LSQ_HD uint32_t route_pair(const Tables &T, int2 b0, int2 b1, uint32_t p0, uint4 raw0, uint32_t p1, uint4 raw1,
+                           uint64_t &key) {
+    key = 0;
+    const uint32_t n0 = piece_ncuts(raw0.z);
+    if (n0 == PIECE_NO_SIG) return RT_GENERAL;
+    if ((raw0.z & PIECE_TIE) && (int32_t)raw0.x == b0.x) return RT_GENERAL;
+    const uint32_t len0 = (uint32_t)(b0.y - b0.x), len1 = (uint32_t)(b1.y - b1.x), total = len0 + len1;
+    // an event that does not take block 1 whole-heartedly matches at most block 0
+    if (!surely_invalid(len1, total)) return RT_GENERAL;
+    bool exact0, exact1;
+    int32_t qp;
+    const uint32_t k0 = cut_category(T, raw0, b0.y, exact0, qp);
+    // block 0 must end exactly on a segment end of the event for block 1 to attach (read.h:226-262); an end
+    // that is no cut is a segment end of no event; so is one past every chain
+    if (k0 == n0 || !exact0) return RT_NONE;
+    // ... and block 1 must start exactly on a later segment start, which is a piece start
+    if ((int32_t)raw1.x != b1.x || !(raw1.z & PIECE_CAND)) return RT_NONE;
+    const uint32_t n1 = piece_ncuts(raw1.z);
+    if (n1 == PIECE_NO_SIG) return RT_GENERAL;
+    const uint32_t k1 = cut_category(T, raw1, b1.y, exact1, qp);
+    if (k1 > 0u && !surely_invalid((uint32_t)(b1.y - qp), total)) return RT_GENERAL;
+    if (k1 == n1) return RT_NONE;
+    key = pair_key(p0, k0, p1, k1);
+    return RT_PAIR;
+}
+
+// Route of a filtered read.  raw1 is only read for two-block reads whose second piece is known.
+template <class PinfoFn>
+LSQ_HD uint32_t route_read(const ScanParams &P, const FilteredRead &fr, PinfoFn pinfo, uint32_t &sig, uint64_t &key,
+                           uint32_t &total) {
+    sig = 0;
+    key = 0;
+    total = 0;
+    if (fr.n == 0u || fr.piece == PIECE_NONE) return RT_NONE;
+    if (fr.mixed) return RT_GENERAL;
+    if (fr.n == 1u) {
+        total = (uint32_t)(fr.first.y - fr.first.x);
+        if (P.flags & SCAN_NO_SINGLE_SIG) return RT_GENERAL;
+        return route_single(P.T, fr.first, fr.raw, sig);
     }
-    LSQ_HD uint4 pinfo(uint32_t p) const { return LSQ_LD(reinterpret_cast<const uint4 *>(P.T.pinfo + p)); }
-};
-LSQ_HD FilteredRead filter_dispatch(const FilterParams &P, uint64_t r) {
-    const uint32_t base = LSQ_LD_STREAM(P.blk_off + r);
-    const uint32_t nraw = LSQ_LD_STREAM(P.blk_off + r + 1) - base;
+    if (fr.n == 2u && fr.piece2 != PIECE_NONE && !(P.flags & SCAN_NO_PAIR_SIG)) {
+        total = (uint32_t)(fr.first.y - fr.first.x) + (uint32_t)(fr.second.y - fr.second.x);
+        return route_pair(P.T, fr.first, fr.second, fr.piece, fr.raw, fr.piece2, pinfo(fr.piece2), key);
+    }
+    return RT_GENERAL;
+}
+
+// A read with exactly two raw blocks on one chromosome, as the scan kernel decides it without the interval-list
+// machinery: p / raw = piece and PieceInfo of each block's start (PIECE_NONE: none), kept = the block lies inside
+// one covered region (count.cpp:319).  Same outcome as filter_read_t + route_read: two kept blocks in order form a
+// pair, abutting ones fuse (interval_list.hpp:480-500), one kept block is a single-block read; overlapping or
+// out-of-order blocks go to the general path.  Nil blocks are never kept and never registered as intervals.
+LSQ_HD uint32_t route_double(const ScanParams &P, int2 b0, int2 b1, uint32_t p0, uint4 raw0, bool kept0, uint32_t p1,
+                             uint4 raw1, bool kept1, uint32_t &sig, uint64_t &key, uint32_t &total) {
+    sig = 0;
+    key = 0;
+    total = 0;
+    if (kept0 && kept1) {
+        if (b1.x > b0.y) {
+            if (!(raw0.z & PIECE_CAND)) return RT_NONE;
+            total = (uint32_t)(b0.y - b0.x) + (uint32_t)(b1.y - b1.x);
+            if (P.flags & SCAN_NO_PAIR_SIG) return RT_GENERAL;
+            return route_pair(P.T, b0, b1, p0, raw0, p1, raw1, key);
+        }
+        if (b1.x != b0.y) return RT_GENERAL;  // overlapping or out of order: general list update
+        b0.y = b1.y;                          // the two fuse into one interval
+    } else if (kept1) {
+        b0 = b1;
+        raw0 = raw1;
+    } else if (!kept0) {
+        return RT_NONE;
+    }
+    if (!(raw0.z & PIECE_CAND)) return RT_NONE;
+    total = (uint32_t)(b0.y - b0.x);
+    if (P.flags & SCAN_NO_SINGLE_SIG) return RT_GENERAL;
+    return route_single(P.T, b0, raw0, sig);
+}
+
+// kept: the lookup answer names a piece whose covered region reaches the block end
+LSQ_HD bool single_kept(uint32_t res) { return (res & PIECE_NONE) != PIECE_NONE && (res >> 31) != 0u; }
+
+// The scan kernel's decision for read r, replayed sequentially (tests/emul): single-block and two-block reads are
+// routed inline, everything else is left to the general kernel.
+LSQ_HD uint32_t scan_route(const ScanParams &P, uint64_t r, uint32_t base, uint32_t nraw, uint32_t &sig, uint64_t &key,
+                           uint32_t &total) {
+    sig = 0;
+    key = 0;
+    total = 0;
+    if (nraw == 0u) return RT_NONE;
     const uint32_t cs0 = load_read_cs(P, r);
-    if (nraw == 1u && !(cs0 & 0x80000000u)) {
-        const int2 b = load_block_stream(P, base);
-        const uint32_t res = block_lookup(P, b, cs0);
-        const uint4 raw = single_kept(res) ? LSQ_LD(reinterpret_cast<const uint4 *>(P.T.pinfo + (res & PIECE_NONE)))
-                                           : make_uint4(0u, 0u, 0u, 0u);
-        return single_decide(P.T, b, cs0, res, raw);
+    if (nraw > 2u || (cs0 & 0x80000000u)) return RT_GENERAL;
+    int2 b[2];
+    uint32_t p[2];
+    uint4 raw[2];
+    bool kept[2];
+    for (uint32_t j = 0; j < nraw; ++j) {
+        b[j] = load_block_stream(P, base + j);
+        const uint32_t res = block_lookup(P, b[j], cs0);
+        kept[j] = single_kept(res);
+        p[j] = res & PIECE_NONE;
+        raw[j] = p[j] != PIECE_NONE ? LSQ_LD(reinterpret_cast<const uint4 *>(P.T.pinfo + p[j])) : make_uint4(0u, 0u, 0u, 0u);
     }
-    const StagedCtx ctx{P, base, cs0};
-    return filter_read_t(P, r, base, nraw, cs0, ctx);
+    if (nraw == 1u) {
+        if (!kept[0] || !(raw[0].z & PIECE_CAND)) return RT_NONE;
+        total = (uint32_t)(b[0].y - b[0].x);
+        if (P.flags & SCAN_NO_SINGLE_SIG) return RT_GENERAL;
+        return route_single(P.T, b[0], raw[0], sig);
+    }
+    return route_double(P, b[0], b[1], p[0], raw[0], kept[0], p[1], raw[1], kept[1], sig, key, total);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -550,8 +592,9 @@ struct ReadView {
     int2 b0, b1, b2;  // kept blocks 0..2 held in registers (reads with more blocks read the rest from blk)
     uint32_t n;       // kept blocks
     uint32_t ridx;    // original read index (names the read: "read-<line_num[ridx]>")
-    const int2 *blk;  // kept blocks 0..n-1 (GENERAL class: inside the ext entry)
-    LSQ_HD int2 block(uint32_t j) const { return j == 0 ? b0 : (j == 1 ? b1 : (j == 2 ? b2 : LSQ_LD(blk + j))); }
+    const int2 *blk;  // kept blocks 0..n-1 (reads with more than two kept blocks: the read's ext entry, which the
+                      // same thread wrote in this kernel -- so plain loads, not the read-only path)
+    LSQ_HD int2 block(uint32_t j) const { return j == 0 ? b0 : (j == 1 ? b1 : (j == 2 ? b2 : blk[j])); }
     LSQ_HD int32_t last_end() const { return block(n - 1).y; }
     LSQ_HD uint32_t read_index() const { return ridx; }
 };
@@ -680,96 +723,6 @@ LSQ_COLD uint64_t walk_wide(int2 b0, int2 b1, int2 b2, uint32_t n, const int2 *b
     return ((uint64_t)((ok && last_added != 0xFFFFFFFFu) ? 1u : 0u) << 32) | ml;
 }
 
-// Table-driven evaluation of a FAST-class read [s,e) against a FAST stab entry: the block starts
-// inside chain segment 0 (not on the event start, so no tie-break applies); it is matched up to
-// min(e, end of the chain) and covers chain segments 0..i where c[i] is the first chain end >= e.
-// Same result as walk_mask + the compatibility test + the validity rule of eval_pair, without
-// touching the event tables.  Returns the form mask of a valid read (0 otherwise).
-LSQ_HD uint32_t eval_fast(const StabEntry &en, int32_t s, int32_t e, uint32_t &matched) {
-    matched = 0;
-    const int32_t cend = en.c[2];  // c[] is padded with the last chain end
-    uint32_t cm;
-    if (e <= en.c[0]) cm = en.cmask[0];
-    else if (e <= en.c[1]) cm = en.cmask[1];
-    else cm = en.cmask[2];
-    if (cm == 0) return 0;
-    const uint32_t total = (uint32_t)(e - s);
-    uint32_t ml = total;
-    if (e > cend) {  // the block overhangs the chain: truncated match, IEEE rule of count.cpp:441-442
-        ml = (uint32_t)(cend - s);
-        if (!(lsq_div((double)ml, (double)total) > 0.98)) return 0;
-    }
-    matched = ml;
-    return cm;
-}
-
-// Two-block (PAIR class) read against a FAST stab entry of a plain event (S <= 64): block 0 starts
-// in chain segment 0 and is resolved with the entry's chain ends exactly as in eval_fast; block 1
-// can only attach when block 0 ended exactly on a segment end, and then only at the exact start
-// of a later segment (read.h:226-262: `cur_start > cur_exon_start -> break`), from where it runs
-// through abutting segments.  Same result as walk_mask + the tests of eval_pair for such reads,
-// without the generic block/segment loops.  No tie-break: PAIR reads never start on a piece start.
-LSQ_HD uint64_t eval_pair2(const StabEntry &en, const EvHdr &h, const int2 *seg, const uint64_t *fm, int2 b0,
-                           int2 b1, uint32_t total_len, uint32_t &matched) {
-    matched = 0;
-    const uint32_t j0 = en.meta & 0xFFFFu, nchain = (en.meta >> 16) & 3u;
-    const int32_t cend = en.c[2];
-    uint32_t i0 = b0.y <= en.c[0] ? 0u : (b0.y <= en.c[1] ? 1u : 2u);
-    if (i0 >= nchain) i0 = nchain - 1u;
-    uint64_t rmask = ((2ull << (j0 + i0)) - 1ull) & ~((1ull << j0) - 1ull);
-    uint32_t ml;
-    if (b0.y > cend) {
-        ml = (uint32_t)(cend - b0.x);  // block 0 overhangs its chain: the read is truncated there
-    } else {
-        ml = (uint32_t)(b0.y - b0.x);
-        const int32_t ci = i0 == 0u ? en.c[0] : (i0 == 1u ? en.c[1] : en.c[2]);
-        if (b0.y == ci) {  // consumed on a segment end: block 1 may attach at a later segment start
-            uint32_t it = j0 + i0 + 1u;
-            const uint32_t S = h.S;
-            LSQ_NO_UNROLL
-            while (it < S) {
-                int2 sg = seg[it];
-                if (!(sg.x < b1.y)) break;
-                if (b1.x < sg.y) {
-                    if (b1.x == sg.x) {
-                        int32_t cs = b1.x;
-                        while (true) {
-                            rmask |= 1ull << it;
-                            const int32_t m = lsq_min(sg.y, b1.y);
-                            ml += (uint32_t)(m - cs);
-                            if (b1.y <= sg.y) break;  // block 1 consumed
-                            cs = sg.y;
-                            ++it;
-                            if (!(it < S)) break;
-                            const int2 nx = seg[it];
-                            if (nx.x != sg.y) break;  // no abutting segment: truncated
-                            sg = nx;
-                        }
-                    }
-                    break;  // starts inside or before this segment without matching its start
-                }
-                ++it;
-            }
-        }
-    }
-    const uint32_t hi = 63u - (uint32_t)lsq_clz64(rmask);
-    const uint64_t low = rmask & (0ull - rmask);
-    const uint64_t span = ((2ull << hi) - 1ull) & ~(low - 1ull);
-    uint64_t cm;
-    if (h.K <= 2u) {
-        cm = (uint64_t)((fm[0] & span) == rmask);
-        if (h.K == 2u) cm |= (uint64_t)((fm[1] & span) == rmask) << 1;
-    } else {
-        cm = 0;
-        LSQ_NO_UNROLL
-        for (uint32_t k = 0; k < h.K; ++k) cm |= (uint64_t)((fm[k] & span) == rmask) << k;
-    }
-    if (cm == 0) return 0;
-    if (ml != total_len && !(lsq_div((double)ml, (double)total_len) > 0.98)) return 0;
-    matched = ml;
-    return cm;
-}
-
 LSQ_HD uint32_t hash_mask(uint64_t m) {
     m ^= m >> 33;
     m *= 0xff51afd7ed558ccdULL;
@@ -789,7 +742,7 @@ LSQ_COLD bool tie_resolve(uint32_t strand_rel, uint32_t tie_mode, uint32_t line_
     return digits_less(line_num, sfx, sfx_len);
 }
 
-LSQ_HD bool tie_skipped(const CountParams &P, const EvHdr &h, const ReadView &rv, uint32_t strand) {
+LSQ_HD bool tie_skipped(const ScanParams &P, const EvHdr &h, const ReadView &rv, uint32_t strand) {
     if (rv.b0.x != h.gs) return false;
     int32_t r_end = rv.last_end();
     if (r_end < h.ge) return true;
@@ -803,7 +756,7 @@ LSQ_HD bool tie_skipped(const CountParams &P, const EvHdr &h, const ReadView &rv
 
 // One (read, event) pair -> form compatibility mask of a VALID read (0 otherwise) and matched bases.
 // Validity (count.cpp:438-448): compatible with some form and matched/total > 0.98 as IEEE doubles.
-LSQ_HD uint64_t eval_pair(const CountParams &P, const EvHdr &h, const int2 *seg,
+LSQ_HD uint64_t eval_pair(const ScanParams &P, const EvHdr &h, const int2 *seg,
                                               const uint64_t *fm, const ReadView &rv, uint32_t strand,
                                               uint32_t total_len, uint32_t &matched) {
     matched = 0;
@@ -837,5 +790,52 @@ LSQ_HD uint64_t eval_pair(const CountParams &P, const EvHdr &h, const int2 *seg,
     return cm;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Signature expansion: representative reads.  Any read of the signature gives the same full-match
+// outcome for every candidate event; the representative starts on the first position of the piece that
+// cannot trigger the tie-break and ends exactly on the cut that closes its category.
+// ---------------------------------------------------------------------------------------------
+LSQ_HD bool sig_rep_single(const Tables &T, uint32_t sig, ReadView &rv, uint32_t &piece) {
+    piece = LSQ_LD(T.sig_piece + sig);
+    const uint4 raw = LSQ_LD(reinterpret_cast<const uint4 *>(T.pinfo + piece));
+    const int32_t s = (int32_t)raw.x + ((raw.z & PIECE_TIE) ? 1 : 0), q = LSQ_LD(T.sig_cut + sig);
+    rv.b0 = make_int2(s, q);
+    rv.b1 = rv.b2 = make_int2(0, 0);
+    rv.n = 1;
+    rv.ridx = 0;
+    rv.blk = nullptr;
+    return s < q;
+}
+LSQ_HD bool sig_rep_pair(const Tables &T, uint64_t key, ReadView &rv, uint32_t &piece) {
+    const uint32_t p0 = (uint32_t)key & PIECE_SIG_MASK, k0 = (uint32_t)(key >> 26) & 15u;
+    const uint32_t p1 = (uint32_t)(key >> 30) & PIECE_SIG_MASK, k1 = (uint32_t)(key >> 56) & 15u;
+    piece = p0;
+    const uint4 raw0 = LSQ_LD(reinterpret_cast<const uint4 *>(T.pinfo + p0));
+    const uint4 raw1 = LSQ_LD(reinterpret_cast<const uint4 *>(T.pinfo + p1));
+    const int32_t s0 = (int32_t)raw0.x + ((raw0.z & PIECE_TIE) ? 1 : 0);
+    rv.b0 = make_int2(s0, LSQ_LD(T.sig_cut + (raw0.z & PIECE_SIG_MASK) + k0));
+    rv.b1 = make_int2((int32_t)raw1.x, LSQ_LD(T.sig_cut + (raw1.z & PIECE_SIG_MASK) + k1));
+    rv.b2 = make_int2(0, 0);
+    rv.n = 2;
+    rv.ridx = 0;
+    rv.blk = nullptr;
+    return rv.b0.x < rv.b0.y && rv.b0.y < rv.b1.x && rv.b1.x < rv.b1.y;
+}
+
+// Every candidate event of `piece` that the representative read matches FULLY: sink(event id, header, form mask).
+template <class Sink>
+LSQ_HD void expand_signature(const ScanParams &P, const ReadView &rv, uint32_t piece, Sink &&sink) {
+    const Tables &T = P.T;
+    const uint32_t total = (uint32_t)(rv.b0.y - rv.b0.x) + (rv.n > 1u ? (uint32_t)(rv.b1.y - rv.b1.x) : 0u);
+    const uint32_t e0 = LSQ_LD(T.stab_off + piece), e1 = LSQ_LD(T.stab_off + piece + 1);
+    LSQ_NO_UNROLL
+    for (uint32_t q = e0; q < e1; ++q) {
+        const uint32_t x = LSQ_LD(&T.stab[q].x);
+        const EvHdr h = T.hdr[x];
+        uint32_t ml;
+        const uint64_t cm = eval_pair(P, h, T.seg + h.seg_off, T.fmask + h.form_off, rv, 0u, total, ml);
+        if (cm != 0ull && ml == total) sink(x, h, cm);
+    }
+}
 
 }  // namespace lsq

@@ -32,8 +32,8 @@ struct HostTables {
     std::vector<uint32_t> bp_bkt_off;
     std::vector<uint2> bp_bkt, bp_sub;
     std::vector<uint4> chrom_meta;
-    uint32_t bkt_shift = 9, n_bkt = 1, max_stab_n = 0;
-    std::vector<uint32_t> bkt_piece;  // [n_bkt+1] first piece whose stab_off is >= b << bkt_shift
+    std::vector<int32_t> sig_cut;     // cut position of every signature slot (PieceInfo)
+    std::vector<uint32_t> sig_piece;  // piece of every signature slot
 
     // Table view over the HOST arrays (CPU replay harness only).
     Tables host_view() const {
@@ -43,6 +43,9 @@ struct HostTables {
         T.n_pieces = (uint32_t)bp_pos.size();
         T.n_chroms = n_chroms;
         T.n_ann_strands = n_strands;
+        T.n_sig = (uint32_t)sig_cut.size();
+        T.sig_cut = sig_cut.data();
+        T.sig_piece = sig_piece.data();
         T.total_slots = slot_total;
         T.hdr = hdr.data();
         T.seg = seg.data();
@@ -61,9 +64,6 @@ struct HostTables {
         T.cov_off = cov_off.data();
         T.cov_start = cov_start.data();
         T.cov_end = cov_end.data();
-        T.bkt_shift = bkt_shift;
-        T.n_bkt = n_bkt;
-        T.bkt_piece = bkt_piece.data();
         return T;
     }
 };
@@ -132,8 +132,6 @@ inline void build_bucket_index(const std::vector<int32_t> &arr, const std::vecto
     bkt_off[nch] = (uint32_t)bkt.size();
     if (sub.empty()) sub.push_back(make_uint2(0u, 0u));
 }
-
-constexpr uint64_t LSQ_PART_TARGET_BKT = 512;
 
 inline int tfail(std::string &err, int code, const std::string &msg) {
     err = msg;
@@ -344,33 +342,11 @@ inline int build_host_tables(const lsq_event_tables *t, HostTables &H, std::stri
             for (uint32_t q = first; q < ie; ++q) {
                 const EvHdr &h = hdr[q];
                 const int2 *sg = seg.data() + h.seg_off;
-                const bool plain = !(h.flags & (EV_WIDE | EV_HASH));
                 for (uint32_t j = 0; j < h.S; ++j) {
                     if (!(sg[j].x < sg[j].y)) continue;
                     StabEntry en;
-                    memset(&en, 0, sizeof en);
                     en.x = q;
-                    en.slot_off = h.slot_off;
-                    en.ge = h.ge;
-                    en.K = (uint8_t)h.K;
-                    // chain of abutting segments a single block starting in segment j runs through
-                    uint32_t nchain = 1;
-                    while (j + nchain < h.S && sg[j + nchain].x == sg[j + nchain - 1].y) ++nchain;
-                    bool fast = plain && nchain <= 3 && sg[j].x >= 0;
-                    if (fast) {
-                        for (uint32_t i = 0; i < 3; ++i) {
-                            uint32_t ii = std::min(i, nchain - 1);
-                            en.c[i] = sg[j + ii].y;
-                            uint64_t rmask = ((2ull << (j + ii)) - 1ull) & ~((1ull << j) - 1ull);
-                            uint8_t cm = 0;
-                            for (uint32_t k = 0; k < h.K; ++k)
-                                // a block covering consecutive segments j..j+ii is its own span, so
-                                // the contiguous-run test (read.h:44-79) is plain containment
-                                if ((fmask[h.form_off + k] & rmask) == rmask) cm |= (uint8_t)(1u << k);
-                            en.cmask[i] = cm;
-                        }
-                    }
-                    en.meta = (j & 0xFFFFu) | ((fast ? nchain : 0u) << 16) | (fast ? SE_FAST : 0u);
+                    en.meta = j & 0xFFFFu;
                     size_t a = std::lower_bound(bps.begin(), bps.end(), sg[j].x) - bps.begin();
                     size_t b = std::lower_bound(bps.begin(), bps.end(), sg[j].y) - bps.begin();
                     for (size_t p = a; p < b; ++p) {
@@ -402,42 +378,55 @@ inline int build_host_tables(const lsq_event_tables *t, HostTables &H, std::stri
         H.chrom_meta[ch] = make_uint4(H.bp_chrom_off[ch], H.bp_chrom_off[ch + 1], H.bp_bkt_off[ch],
                                       H.bp_bkt_off[ch + 1] - H.bp_bkt_off[ch] - 1u);
     H.pinfo.assign(H.bp_pos.size() + 1, PieceInfo());  // one sentinel: clamped candidate loads stay in bounds
+    H.sig_cut.clear();
+    H.sig_piece.clear();
     for (uint32_t ch = 0; ch < t->n_chroms; ++ch) {
         const int32_t *cs = H.cov_start.data() + H.cov_off[ch], *ce = H.cov_end.data() + H.cov_off[ch];
         const size_t nc = H.cov_off[ch + 1] - H.cov_off[ch];
         for (uint32_t p = H.bp_chrom_off[ch]; p < H.bp_chrom_off[ch + 1]; ++p) {
             PieceInfo &pi = H.pinfo[p];
             pi.pos = H.bp_pos[p];
-            pi.stab_off = H.stab_off[p];
-            pi.stab_n = H.stab_off[p + 1] - H.stab_off[p];
-            bool all_fast = pi.stab_n > 0;
-            for (uint32_t q = H.stab_off[p]; q < H.stab_off[p + 1]; ++q) all_fast = all_fast && (H.stab[q].meta & SE_FAST);
-            if (all_fast) pi.stab_n |= PIECE_ALL_FAST;
             size_t i = std::upper_bound(cs, cs + nc, pi.pos) - cs;
             pi.cov_end = (i > 0 && ce[i - 1] > pi.pos) ? ce[i - 1] : INT32_MIN;
+            pi.sigw = 0;
+            pi.cutw = 0;
+            if (H.stab_off[p + 1] == H.stab_off[p]) continue;
+            // cut list: the segment ends of every entry's chain of abutting segments (lsq_types.cuh: PieceInfo)
+            std::vector<int32_t> cuts;
+            bool tie = false;
+            for (uint32_t q = H.stab_off[p]; q < H.stab_off[p + 1]; ++q) {
+                const StabEntry &en = H.stab[q];
+                const EvHdr &h = hdr[en.x];
+                const int2 *sg = seg.data() + h.seg_off;
+                tie = tie || (en.meta & SE_AT_GS);
+                for (uint32_t j = en.meta & 0xFFFFu;; ++j) {
+                    cuts.push_back(sg[j].y);
+                    if (j + 1 >= h.S || sg[j + 1].x != sg[j].y) break;
+                }
+            }
+            std::sort(cuts.begin(), cuts.end());
+            cuts.erase(std::unique(cuts.begin(), cuts.end()), cuts.end());
+            uint32_t n = (uint32_t)cuts.size();
+            const size_t so = H.sig_cut.size();
+            bool usable = n <= PIECE_MAX_CUTS && so + n <= (size_t)PIECE_SIG_MASK;
+            for (uint32_t k = 0; k < n && k < 2u && usable; ++k)
+                usable = (int64_t)cuts[k] - (int64_t)pi.pos < 0xFFFF && cuts[k] > pi.pos;
+            pi.sigw = PIECE_CAND | (tie ? PIECE_TIE : 0u);
+            if (!usable) {
+                pi.sigw |= PIECE_NO_SIG << PIECE_SIG_BITS;
+                continue;
+            }
+            pi.sigw |= (uint32_t)so | (n << PIECE_SIG_BITS);
+            for (uint32_t k = 0; k < n; ++k) {
+                H.sig_cut.push_back(cuts[k]);
+                H.sig_piece.push_back(p);
+                if (k < 2u) pi.cutw |= (uint32_t)(cuts[k] - pi.pos) << (16u * k);
+            }
         }
     }
-    // stab buckets: windows of 2^bkt_shift stab entries, at most PART_MAX_BINS / 3 of them
-    {
-        const uint32_t n_stab = (uint32_t)H.stab.size(), n_pieces = (uint32_t)H.bp_pos.size();
-        // the smallest window (>= 16 entries) that gives at most LSQ_PART_TARGET_BKT buckets: small annotations
-        // still spread their reads over many bins (a bin's chunk switches serialise the tiles that meet there),
-        // large ones keep the per-tile bin arrays of the filter small
-        uint64_t target = LSQ_PART_TARGET_BKT;
-        if (const char *ev = getenv("LSQ_PART_TARGET_BKT")) target = std::max<uint64_t>(1, strtoull(ev, nullptr, 10));  // tuning only
-        target = std::min<uint64_t>(target, PART_MAX_BINS / 3);
-        H.bkt_shift = 4;
-        while ((uint64_t)(n_stab >> H.bkt_shift) + 1ull > target) ++H.bkt_shift;
-        H.n_bkt = (n_stab >> H.bkt_shift) + 1u;
-        H.bkt_piece.assign(H.n_bkt + 1, n_pieces);
-        uint32_t p = 0;
-        for (uint32_t b = 0; b <= H.n_bkt; ++b) {
-            const uint64_t lim = (uint64_t)b << H.bkt_shift;
-            while (p < n_pieces && (uint64_t)H.stab_off[p] < lim) ++p;
-            H.bkt_piece[b] = p;
-        }
-        H.max_stab_n = 0;
-        for (uint32_t q = 0; q < n_pieces; ++q) H.max_stab_n = std::max(H.max_stab_n, H.stab_off[q + 1] - H.stab_off[q]);
+    if (H.sig_cut.empty()) {  // never null on the device
+        H.sig_cut.push_back(0);
+        H.sig_piece.push_back(0);
     }
     H.slot_total = slot_total;
     H.E = E;

@@ -37,84 +37,54 @@ constexpr uint8_t EV_TIE_MASK = 0x3;   // 0: "read-N" never < name, 1: always, 2
 constexpr uint8_t EV_WIDE = 0x4;       // S > 64: prefix-count compatibility test
 constexpr uint8_t EV_HASH = 0x8;       // class table is an open-addressed hash (K > DENSE_MAX_FORMS)
 
-// Stab entry, 32 bytes: one (piece, event) pair of the stab arrangement.  Pieces are the
-// elementary intervals cut by every segment boundary and span end of the events of a chromosome,
-// so for a read whose first block starts in the piece, the segment j0 of event x that contains
-// the start is known in advance, and so is the chain of abutting segments a single block can run
-// through (common/read.h:226-262).  FAST entries carry the chain ends c[i] and the form
-// compatibility mask cmask[i] of a read covering chain segments 0..i, which decides a
-// single-block read with a few compares; everything else takes the general walk.
-struct __align__(16) StabEntry {
-    uint32_t x;         // internal event id
-    uint32_t slot_off;  // class slots of x (copy of EvHdr::slot_off)
-    int32_t ge;         // event end, first test of the lower_bound tie-break
-    uint32_t meta;      // bits 0-15 j0 | bits 16-17 chain length (1..3) | SE_* flags
-    int32_t c[3];       // chain segment ends, ascending
-    uint8_t cmask[3];   // form mask (K <= 8) when the block ends within chain segment i
-    uint8_t K;          // forms of x
+// Stab entry, 8 bytes: one (piece, event) pair of the stab arrangement.  Pieces are the elementary
+// intervals cut by every segment boundary and span end of the events of a chromosome (and by the
+// covered-region boundaries), so for a read whose first block starts in the piece, the segment j0 of
+// event x that contains the start is known in advance.  A piece lists only the events for which it
+// lies inside a segment: a first block that starts outside every segment of an event can never be
+// matched by the walk (common/read.h:226-262).
+struct __align__(8) StabEntry {
+    uint32_t x;      // internal event id
+    uint32_t meta;   // bits 0-15 j0 | SE_AT_GS
 };
-static_assert(sizeof(StabEntry) == 32, "StabEntry layout");
-constexpr uint32_t SE_FAST = 1u << 24;   // table-driven single-block evaluation is valid
+static_assert(sizeof(StabEntry) == 8, "StabEntry layout");
 constexpr uint32_t SE_AT_GS = 1u << 25;  // the piece starts at the event start (tie-break possible)
 
-// Per-piece record read by the load filter: one 16-byte load answers "is this block start inside
-// a covered region, and up to where" as well as "which stab list does a read starting here get".
+// Per-piece record read by the scan kernel: ONE 16-byte load answers "is this block start inside a covered
+// region, and up to where", "is a read starting here a candidate of any event" and -- through the cut list
+// -- "which outcome class does a block that starts here and ends at e fall into" (see lsq_scan_kernel).
 // Pieces are cut by the covered-region boundaries too, so a piece is covered entirely or not.
+//
+// Cut list of a piece: for every stab entry (event x, segment j0 holding the piece) the ends of the
+// segments of the chain of abutting segments that starts at j0 (common/read.h:226-262: a block can only
+// run from one segment into the next when they abut).  All entries' ends, distinct and ascending, are the
+// piece's cuts q_0 < q_1 < ...: the result of the walk for a block [s, e) with s inside the piece depends on
+// e only through the number of cuts below e (and on whether e hits a cut exactly when a further block
+// follows).  Signature slot sig_off + k counts the single-block reads with q_{k-1} < e <= q_k.
 struct __align__(16) PieceInfo {
     int32_t pos;        // first position of the piece
     int32_t cov_end;    // end of the covered region containing the piece, INT32_MIN if uncovered
-    uint32_t stab_off;  // first stab entry
-    uint32_t stab_n;    // number of stab entries (0: reads starting here are no candidates);
-                        // bit 31 (PIECE_ALL_FAST): every entry is table-driven (SE_FAST)
+    uint32_t sigw;      // bits 0-25 first signature slot | bits 26-29 number of cuts (PIECE_NO_SIG: none usable)
+                        // | bit 30 PIECE_CAND: the piece has stab entries | bit 31 PIECE_TIE: an entry's event
+                        // starts here, so the lower_bound tie-break (count.cpp:429-432) can apply
+    uint32_t cutw;      // cuts 0 and 1 as 16-bit offsets from pos (further cuts: Tables::sig_cut)
 };
-constexpr uint32_t PIECE_ALL_FAST = 0x80000000u;
+constexpr uint32_t PIECE_SIG_BITS = 26, PIECE_SIG_MASK = (1u << PIECE_SIG_BITS) - 1u;
+constexpr uint32_t PIECE_NO_SIG = 15u;   // cut count that disables the signature paths (too many / too far)
+constexpr uint32_t PIECE_MAX_CUTS = 14u;
+constexpr uint32_t PIECE_CAND = 1u << 30, PIECE_TIE = 1u << 31;
 static_assert(sizeof(PieceInfo) == 16, "PieceInfo layout");
+LSQ_TYPES_HD uint32_t piece_ncuts(uint32_t sigw) { return (sigw >> PIECE_SIG_BITS) & 15u; }
 
-// Read record (8 bytes).  The load filter drops every read that is a candidate of no event and appends the others to the
-// bin (read class, stab bucket) they belong to -- see PartState.  Read classes:
-//   FAST    one kept block, shorter than 64 Ki, not starting on the first position of its piece,
-//           every stab entry of the piece table-driven:
-//           x = start of the block, y = length (bits 0-15) | file strand id (bits 16-23)
-//   PAIR    two kept blocks that fit the record (pack_pair)
-//   GENERAL everything else: x = offset of the read's entry in ext[]:
-//           ext[x] = {original read index, (strand << 24) | n}, ext[x+1 .. x+n] = kept blocks
-typedef uint2 ReadRec;
-
-// Partition of the kept reads by (class, stab bucket).  A stab bucket is a run of consecutive
-// pieces whose stab entries fall into one window of 2^bkt_shift entries, so the tables a bucket
-// needs (its stab entries, their offsets and four counters per entry) fit in shared memory.
-// Bins grow in chunks of PART_CHUNK records taken from one pool: state[bin] packs the bin's
-// current chunk and its fill, so one 64-bit atomicAdd reserves room for a whole tile's records;
-// the reservation that takes the last slot of a chunk installs the bin's spare chunk (and then
-// allocates a new spare, off the critical path).  Each installed chunk is one work item of the
-// count kernel of its class (wl lists chunk ids per class).
-constexpr uint32_t PART_CHUNK_LOG2 = 11;
-constexpr uint32_t PART_CHUNK = 1u << PART_CHUNK_LOG2;
-constexpr uint32_t PART_MAX_BINS = 12288;  // shared-memory budget of the filter kernel (10 bytes per bin)
-constexpr uint32_t BIN_NONE = 0xFFFFu;     // read dropped
-
-struct PartState {
-    uint32_t n_bins;              // 3 * n_bkt: bin = class * n_bkt + (stab_off >> bkt_shift)
-    uint32_t pool_cap;            // chunks in the pool
-    unsigned long long *state;    // [n_bins] (current chunk << 32) | fill
-    uint32_t *next_chunk;         // [n_bins] spare chunk, installed when the current one is full
-    uint32_t *pool_next;          // chunks allocated so far
-    uint32_t *owner;              // [pool_cap] bin of chunk j
-    uint32_t *wl;                 // [3 * pool_cap] chunk ids per class
-    uint32_t *wl_n;               // [3] list lengths
-    uint4 *pool;                  // [pool_cap * PART_CHUNK] PartRec
-};
-
-// Partitioned record, 16 bytes (half a sector; one 128-bit access):
-//   x  first stab entry of the read's piece (bits 0-25) | number of entries (bits 26-31);
-//      FAST and PAIR reads whose piece does not fit are demoted to GENERAL
-//   y  PAIR: first position of the piece; GENERAL: the piece (its stab list is looked up)
-//   z, w  the ReadRec
-constexpr uint32_t PREC_SO_BITS = 26;
-constexpr uint32_t PREC_MAX_SO = (1u << PREC_SO_BITS) - 1u, PREC_MAX_N = 63u;
+// Signature of a two-block read (lsq_scan_kernel): piece of block 0 | cut hit by its end | piece of
+// block 1 (which starts exactly on the piece start) | cut category of its end.  Never 0: piece 1 > piece 0.
+LSQ_TYPES_HD uint64_t pair_key(uint32_t p0, uint32_t k0, uint32_t p1, uint32_t k1) {
+    return (uint64_t)p0 | ((uint64_t)k0 << 26) | ((uint64_t)p1 << 30) | ((uint64_t)k1 << 56);
+}
+constexpr uint32_t HASH_MAX_PROBES = 32;
 
 struct Tables {
-    uint32_t E, F, n_pieces, n_chroms, n_ann_strands;
+    uint32_t E, F, n_pieces, n_chroms, n_ann_strands, n_sig;
     uint64_t total_slots;
     const EvHdr *hdr;
     const int2 *seg;
@@ -125,20 +95,18 @@ struct Tables {
     const PieceInfo *pinfo;        // [n_pieces] sorted by position within a chromosome
     const uint32_t *stab_off;      // [n_pieces+1]
     const StabEntry *stab;         // candidate events of each piece
+    const int32_t *sig_cut;        // [n_sig] cut position of every signature slot
+    const uint32_t *sig_piece;     // [n_sig] piece of every signature slot
     const uint32_t *cov_off;       // [n_chroms+1]
     const int32_t *cov_start, *cov_end;
-    // bucket indexes: position >> shift -> rank of the bucket start in the sorted array, so a
-    // lookup is one table load plus a short forward scan instead of a full binary search
+    // bucket index: position >> shift -> rank of the bucket start in the sorted piece starts plus the
+    // in-bucket starts, so the piece of a position comes from ONE 8-byte load (bucket_word)
     uint32_t bp_shift;
     const uint4 *chrom_meta;       // [n_chroms] {first piece, end piece, first bucket, buckets - 1}
     const uint32_t *bp_bkt_off;    // [n_chroms+1] first bucket of each chromosome
     const uint2 *bp_bkt;           // [buckets + n_chroms] x: rank of the first piece starting in or after the bucket,
-                                   // y: the piece starts inside the bucket (bucket_word), so the piece of a
-                                   // position comes from ONE 8-byte load
+                                   // y: the piece starts inside the bucket (bucket_word)
     const uint2 *bp_sub;           // sub-buckets of the crowded buckets (same entry format, bucket_sub_shift)
-    // stab buckets (PartState): bucket of piece p = stab_off[p] >> bkt_shift
-    uint32_t bkt_shift, n_bkt;
-    const uint32_t *bkt_piece;     // [n_bkt+1] first piece whose stab_off is >= b << bkt_shift
 };
 
 // Bucket word: bits 29-31 = number of piece starts inside the bucket, then bucket_capacity(shift)
@@ -164,37 +132,56 @@ LSQ_TYPES_HD uint32_t bucket_rank(uint32_t shift, uint32_t w, uint32_t xo) {
     return n;
 }
 
-struct FilterParams {
+// Reads are processed in groups of SCAN_GROUP consecutive reads (one warp, four reads per lane).
+constexpr uint32_t SCAN_GROUP = 128;
+constexpr uint32_t SCAN_SUPER = 256;  // groups per super-group of the block-offset index (grp_base / sup_base)
+
+// Counters of the scan (statistics; per read set)
+constexpr int CTR_SINGLE_SIG = 0, CTR_PAIR_SIG = 1, CTR_GENERAL = 2, CTR_NONE = 3, CTR_HASH_FULL = 4, CTR_N = 8;
+
+// Everything the count path reads and writes for one read set.  Inputs come in two forms:
+//   wide     blk_off u32[n+1] (CSR), blk int2[B], read_cs u32[n]
+//   compact  blk_cnt u8[n] (+ the block-offset index grp_base/sup_base built by lsq_group_base_kernels),
+//            read_cs8 u8[n], blk_start i32[B] + blk_len u16[B] or blk_len8 u8[B]
+// and any mix of them (load_group / load_block / load_read_cs pick what is present).
+struct ScanParams {
     Tables T;
     uint64_t n_reads;
     const uint32_t *blk_off;
+    const uint8_t *blk_cnt;       // with grp_base/sup_base: instead of blk_off (padded to a multiple of 4 reads)
+    const uint32_t *grp_base;     // [groups] blocks before the group within its super-group
+    const uint32_t *sup_base;     // [super-groups] blocks before the super-group
     const int2 *blk;
     const uint32_t *read_cs;
     const uint32_t *blk_cs;       // may be null
     const uint32_t *chrom_remap;  // file chromosome id -> annotation id or 0xFFFFFFFF
     const uint4 *file_meta;       // file chromosome id -> chrom_meta of its annotation id (zeros: none)
-    // compact wire format (include/lesseq_b200.h): alternatives to read_cs and blk, null when absent
-    const uint8_t *read_cs8;
+    const uint8_t *read_cs8;      // padded to a multiple of 4 reads
     const int32_t *blk_start;
     const uint16_t *blk_len;
     const uint8_t *blk_len8;      // instead of blk_len when every block is shorter than 256
     const uint32_t *progress;     // null, or: blocks of blk[] that have landed so far (streamed host->device copy)
-    int2 *ext;                    // [n_blocks + 2 n_reads] worst case (header + blocks per general read)
-    PartState part;
-    unsigned long long *counters; // per read set: [0] FAST reads, [1] ext slots read, [2] PAIR reads, [3] GENERAL reads
-};
-
-struct CountParams {
-    Tables T;
-    PartState part;
-    const int2 *ext;
-    const uint32_t *line_num;
-    const uint8_t *strand_tbl;   // [file strands x annotation strands] bit0: read < event, bit1: equal
+    const uint32_t *line_num;     // null: read i is "read-<i+1>"
+    const uint8_t *strand_tbl;    // [file strands x annotation strands] bit0: read < event, bit1: equal
+    int2 *ext;                    // [n_blocks + 2 n_reads] scratch: interval lists of reads with > 2 kept blocks
+    // signature counters (per launch scratch, cleared before the scan)
+    uint32_t *sig_cnt;                // [n_sig] reads per (piece, cut category)
+    unsigned long long *sig_dev;      // [n_sig] sum of (read length - len0) over those reads
+    ulonglong2 *hash;                 // [hash_mask + 1] {pair_key, reads}; key 0 = empty
+    unsigned long long *hash_dev;     // [hash_mask + 1] sum of (read length - len0)
+    uint32_t hash_mask;
+    uint32_t len0;                    // the read set's nominal read length (the CLI's expected_read_length)
+    uint2 *gen_list;                  // [gen_cap] {read, first block} of the reads left to lsq_general_kernel
+    uint32_t *gen_n;
+    uint32_t gen_cap;
+    uint32_t flags;                   // SCAN_* below
+    unsigned long long *counters;     // [CTR_N]
+    // results
     unsigned long long *slot_cnt;   // this read set's class counters
     unsigned long long *slot_mask;  // hash keys (EV_HASH events)
     unsigned long long *bases;      // [E] internal order
-    unsigned long long *stats;      // ext slots read by the GENERAL instantiation (byte accounting)
 };
+constexpr uint32_t SCAN_NO_SINGLE_SIG = 1u, SCAN_NO_PAIR_SIG = 2u;  // debugging: send those reads to lsq_general_kernel
 
 struct SolveParams {
     Tables T;

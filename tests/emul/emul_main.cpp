@@ -3,9 +3,9 @@
 // The development container has no GPU, so kernel logic bugs would otherwise surface only on
 // gpurun calls.  This program compiles the product's own per-read / per-pair device functions
 // (lesseq_b200/csrc/lsq_device_fn.cuh, via the LSQ_HD switch) and the product's host table
-// layout (lsq_tables_host.hpp) with g++ and replays the filter -> index -> count pipeline
-// sequentially; the EM is restated over the class histogram with the same per-class
-// arithmetic as lsq_solve_kernel.  tests/test_emul_vs_oracle.py compares its output with the
+// layout (lsq_tables_host.hpp) with g++ and replays the scan (filter, routing, signature tally) ->
+// expand -> general pipeline sequentially; the EM is restated over the class histogram with the same
+// per-class arithmetic as lsq_solve_kernel.  tests/test_emul_vs_oracle.py compares its output with the
 // oracle.  It takes the same positional arguments as the reference programs.
 #include <algorithm>
 #include <cmath>
@@ -70,8 +70,8 @@ static int bucket_selftest(unsigned seed) {
     for (size_t i = 0; i < pos.size(); ++i) {
         pinfo[i].pos = pos[i];
         pinfo[i].cov_end = (i % 3) ? pos[i] + 50 : INT32_MIN;
-        pinfo[i].stab_off = (uint32_t)i;
-        pinfo[i].stab_n = 1;
+        pinfo[i].sigw = PIECE_CAND;
+        pinfo[i].cutw = 0;
     }
     std::vector<uint4> meta(nch);
     std::vector<uint32_t> remap(nch);
@@ -79,7 +79,7 @@ static int bucket_selftest(unsigned seed) {
         meta[c] = make_uint4(off[c], off[c + 1], bkt_off[c], bkt_off[c + 1] - bkt_off[c] - 1u);
         remap[c] = c;
     }
-    FilterParams P{};
+    ScanParams P{};
     P.T.bp_shift = shift;
     P.T.bp_bkt = bkt.data();
     P.T.bp_sub = sub.data();
@@ -227,10 +227,7 @@ int main(int argc, char **argv) {
         std::vector<uint8_t> stbl;
         strand_table(R.strand_ptrs.data(), (uint32_t)R.strand_ptrs.size(), ann_strands, stbl);
         std::vector<int2> ext2(nb + 2 * n + 2);
-        std::vector<uint32_t> rkey(n);
-        std::vector<ReadRec> rec(n);
-        unsigned long long counters[4] = {0, 0, 0, 0};
-        FilterParams FP{};
+        ScanParams FP{};
         FP.T = T;
         FP.n_reads = n;
         FP.blk_off = R.blk_off.data();
@@ -243,84 +240,89 @@ int main(int argc, char **argv) {
             if (remap[i] != 0xFFFFFFFFu) fmeta[i] = H.chrom_meta[remap[i]];
         FP.file_meta = fmeta.data();
         FP.ext = ext2.data();
-        FP.counters = counters;
-        for (size_t r = 0; r < n; ++r) {  // lsq_filter_kernel, one "thread" at a time
-            FilteredRead fr = filter_dispatch(FP, r);  // staged single-block path or filter_read, as the kernel
-            ReadRec q;
-            if (fr.key != KEY_DROPPED(T) && fr.key >= T.n_pieces && fr.key < 2u * T.n_pieces) {
-                q = pack_pair(fr.first, fr.second, fr.piece_pos, fr.strand);
-            } else if (fr.key != KEY_DROPPED(T) && fr.key >= 2u * T.n_pieces) {
-                uint32_t off = ext_slot(R.blk_off[r], (uint32_t)r);
-                counters[1] += fr.n + 1;
-                write_ext_entry(ext2.data(), off, (uint32_t)r, fr);  // blocks 2.. were spilled by the filter
-                q.x = off;
-                q.y = 0;
-            } else {
-                q.x = (uint32_t)fr.first.x;
-                q.y = (uint32_t)(fr.first.y - fr.first.x) | (fr.strand << 16);
-            }
-            rkey[r] = fr.key;
-            rec[r] = q;
-        }
-        std::vector<uint32_t> perm(n);
-        for (size_t i = 0; i < n; ++i) perm[i] = (uint32_t)i;
-        std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) { return rkey[a] < rkey[b]; });
-        CountParams CP{};
-        CP.T = T;
-        CP.ext = ext2.data();
-        CP.line_num = R.line_num.data();
-        CP.strand_tbl = stbl.data();
-        for (size_t i = 0; i < n; ++i) {  // lsq_count_kernel, one read at a time
-            uint32_t r = perm[i];
-            uint32_t key = rkey[r];
-            if (key == KEY_DROPPED(T)) break;
-            ReadRec q = rec[r];
-            const uint32_t cls = key / T.n_pieces;
-            const bool gen = cls != 0;
-            const uint32_t piece = key - cls * T.n_pieces;
-            ReadView rv;
-            uint32_t strand, total;
-            if (cls == 1) {
-                unpack_pair(q, T.pinfo[piece].pos, rv.b0, rv.b1, strand);
-                rv.b2 = rv.b0;
-                rv.n = 2;
-                rv.ridx = 0;
-                rv.blk = nullptr;
-                total = (uint32_t)(rv.b0.y - rv.b0.x) + (uint32_t)(rv.b1.y - rv.b1.x);
-            } else if (gen) {
-                const int2 *entry = ext2.data() + q.x;
-                rv.ridx = (uint32_t)entry[0].x;
-                rv.n = (uint32_t)entry[0].y & 0xFFFFFFu;
-                strand = (uint32_t)entry[0].y >> 24;
-                rv.blk = entry + 1;
-                rv.b0 = entry[1];
-                rv.b1 = rv.n > 1 ? entry[2] : entry[1];
-                rv.b2 = rv.n > 2 ? entry[3] : entry[1];
-                total = 0;
-                for (uint32_t b = 0; b < rv.n; ++b) total += (uint32_t)(rv.blk[b].y - rv.blk[b].x);
-            } else {
-                rv.b0 = make_int2((int32_t)q.x, (int32_t)q.x + (int32_t)(q.y & 0xFFFFu));
-                rv.b1 = rv.b2 = rv.b0;
-                rv.n = 1;
-                rv.ridx = 0;
-                rv.blk = nullptr;
-                strand = (q.y >> 16) & 0xFFu;
-                total = q.y & 0xFFFFu;
-            }
-            for (uint32_t s = T.stab_off[piece]; s < T.stab_off[piece + 1]; ++s) {
-                const StabEntry &en = T.stab[s];
-                uint32_t x = en.x;
-                const EvHdr &h = T.hdr[x];
-                uint32_t ml = 0;
-                uint64_t cm = 0;
-                if (!gen && !(en.meta & SE_FAST)) {
-                    fprintf(stderr, "emul: FAST-class read met a non-FAST entry\n");
+        FP.line_num = R.line_num.data();
+        FP.strand_tbl = stbl.data();
+        FP.len0 = (uint32_t)sets[m].len;
+        if (const char *f = getenv("LSQ_SCAN_FLAGS")) FP.flags = (uint32_t)strtoul(f, nullptr, 0);
+        // lsq_scan_kernel, one "thread" at a time: filter, route, tally the signature
+        std::vector<uint64_t> sig_cnt(T.n_sig, 0);
+        std::vector<int64_t> sig_dev(T.n_sig, 0);
+        std::map<uint64_t, std::pair<uint64_t, int64_t> > pair_sig;
+        std::vector<uint2> gen_list;
+        uint64_t n_single = 0, n_pair = 0;
+        for (size_t r = 0; r < n; ++r) {
+            const uint32_t base = R.blk_off[r], nraw = R.blk_off[r + 1] - base;
+            uint32_t sig, total;
+            uint64_t key;
+            const uint32_t rt = scan_route(FP, r, base, nraw, sig, key, total);  // inline single / two-block paths, as the kernel
+            if (rt == RT_SINGLE) {
+                if (sig >= T.n_sig) {
+                    fprintf(stderr, "emul: signature slot out of range\n");
                     return 3;
                 }
-                if (!gen) cm = eval_fast(en, rv.b0.x, rv.b0.y, ml);
-                else if (cls == 1 && (en.meta & SE_FAST))
-                    cm = eval_pair2(en, h, T.seg + h.seg_off, T.fmask + h.form_off, rv.b0, rv.b1, total, ml);
-                else cm = eval_pair(CP, h, T.seg + h.seg_off, T.fmask + h.form_off, rv, strand, total, ml);
+                sig_cnt[sig]++;
+                sig_dev[sig] += (int64_t)total - (int64_t)FP.len0;
+                ++n_single;
+            } else if (rt == RT_PAIR) {
+                auto &e = pair_sig[key];
+                e.first++;
+                e.second += (int64_t)total - (int64_t)FP.len0;
+                ++n_pair;
+            } else if (rt == RT_GENERAL) {
+                gen_list.push_back(make_uint2((uint32_t)r, base));
+            }
+        }
+        if (getenv("LSQ_EMUL_STATS"))
+            fprintf(stderr, "emul: reads %zu single-sig %llu pair-sig %llu (distinct %zu) general %zu\n", n, (unsigned long long)n_single,
+                    (unsigned long long)n_pair, pair_sig.size(), gen_list.size());
+        // lsq_expand_kernel
+        auto expand = [&](const ReadView &rv, uint32_t piece, uint64_t cnt, int64_t dev) {
+            const uint64_t b = (uint64_t)((int64_t)(cnt * (uint64_t)FP.len0) + dev);
+            expand_signature(FP, rv, piece, [&](uint32_t x, const EvHdr &, uint64_t cm) {
+                hist[m][x][cm] += cnt;
+                bases[m][x] += b;
+            });
+        };
+        for (uint32_t i = 0; i < T.n_sig; ++i) {
+            if (!sig_cnt[i]) continue;
+            ReadView rv;
+            uint32_t piece;
+            if (!sig_rep_single(T, i, rv, piece)) {
+                fprintf(stderr, "emul: counted signature without a representative read\n");
+                return 3;
+            }
+            expand(rv, piece, sig_cnt[i], sig_dev[i]);
+        }
+        for (auto &kv : pair_sig) {
+            ReadView rv;
+            uint32_t piece;
+            if (!sig_rep_pair(T, kv.first, rv, piece)) {
+                fprintf(stderr, "emul: counted pair signature without a representative read\n");
+                return 3;
+            }
+            expand(rv, piece, kv.second.first, kv.second.second);
+        }
+        // lsq_general_kernel, one read at a time
+        for (const uint2 &it : gen_list) {
+            const uint32_t r = it.x, base = it.y;
+            const uint32_t nraw = load_read_nraw(FP, r), cs0 = load_read_cs(FP, r);
+            const DirectCtx ctx{FP, base};
+            const FilteredRead fr = filter_read_t(FP, r, base, nraw, cs0, ctx);
+            if (fr.n == 0u || fr.piece == PIECE_NONE) continue;
+            ReadView rv;
+            rv.blk = FP.ext + ext_slot(base, r) + 1;
+            rv.b0 = fr.first;
+            rv.b1 = fr.n > 1u ? fr.second : make_int2(0, 0);
+            rv.b2 = fr.n > 2u ? rv.blk[2] : make_int2(0, 0);
+            rv.n = fr.n;
+            rv.ridx = r;
+            uint32_t total = 0;
+            for (uint32_t b = 0; b < fr.n; ++b) total += (uint32_t)(rv.block(b).y - rv.block(b).x);
+            for (uint32_t q = T.stab_off[fr.piece]; q < T.stab_off[fr.piece + 1]; ++q) {
+                const uint32_t x = T.stab[q].x;
+                const EvHdr &h = T.hdr[x];
+                uint32_t ml = 0;
+                const uint64_t cm = eval_pair(FP, h, T.seg + h.seg_off, T.fmask + h.form_off, rv, fr.strand, total, ml);
                 if (cm) {
                     hist[m][x][cm]++;
                     bases[m][x] += ml;

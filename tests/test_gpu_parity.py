@@ -212,7 +212,7 @@ def test_device_resident_reads_and_properties(api, tmp_path):
 
     ann = api.Annotation(fp, mp)
     c, (off, mask, cnt), sol, t = run(ann, reads)
-    assert t["reads_in"] == n and 0 < t["reads_kept"] <= n
+    assert t["reads_in"] == n and 0 < t["reads_single"] + t["reads_pair"] + t["reads_general"] <= n
     foff = ann.form_offsets()
     for e in range(ann.n_events):
         sl = slice(int(off[e]), int(off[e + 1]))

@@ -8,9 +8,9 @@ separate shared library built here (nvcc cross-compiles without a GPU) from the 
     python tools/variant_sweep.py FILT_RBATCH=6 "FILT_BLOCK=256 CTR_PACKED=0" FILT_LBATCH=3
     # -> lesseq_b200/lib/var_*.so (git-ignored, they travel with the gpurun snapshot) + the command to run
 
-Hooks that exist today (lsq_kernels.cuh): LSQ_FILT_BLOCK, LSQ_FILT_LBATCH, LSQ_FILT_RBATCH, LSQ_CTR_PACKED;
-host side (environment, no rebuild): LSQ_PART_TARGET_BKT (stab buckets), LSQ_BKT_PER_PIECE (piece-lookup buckets per
-piece, default 8; 16 gives 128-bp buckets with four offsets per word at C2).  Remove the var_*.so files before committing a round.
+Hooks that exist today (lsq_kernels.cuh): LSQ_SCAN_BLOCK, LSQ_SCAN_MINB, LSQ_SCAN_FLIGHT;
+host side (environment, no rebuild): LSQ_BKT_PER_PIECE (piece-lookup buckets per piece, default 8; 16 gives 128-bp buckets
+with four offsets per word at C2), LSQ_SCAN_FLAGS (1: no single-block signatures, 2: no pair signatures -- debugging).  Remove the var_*.so files before committing a round.
 """
 import os
 import subprocess
@@ -37,7 +37,7 @@ def main(specs):
             sys.stderr.write(p.stdout + p.stderr)
             return 1
         for line in (p.stdout + p.stderr).splitlines():  # registers / spills of the kernels that matter
-            if "Compiling entry function" in line and ("filter" in line or "count_kernel" in line):
+            if "Compiling entry function" in line and ("scan" in line or "general" in line):
                 print("  ", line.split("'")[1][:60], end=": ")
             elif "Used" in line and "registers" in line:
                 print(line.strip()[len("ptxas info    : "):], flush=True)
