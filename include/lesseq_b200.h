@@ -222,6 +222,44 @@ int lsq_get_device_results(lsq_ctx *ctx, lsq_device_results *out);
 
 int lsq_get_timings(lsq_ctx *ctx, lsq_timings *out);
 
+/* ---------------------------------------------------------------------------------------------
+ * Multi-GPU: gene-range shards with reads bucketed per shard.  The reference scales out by running one
+ * process per gene_begin_idx/gene_end_idx range, each reading the WHOLE read file and keeping what its range
+ * covers (count.cpp:113-114, 202-215, 319, 429-432).  Here rank d of n_ranks owns the events
+ * [shard_begin[d], shard_begin[d+1]) of the selection (output order = gene-rank order), every rank holds an
+ * arbitrary slice of the read set, and lsq_shard_reads sends each read to the ranks whose events it can be a
+ * candidate of -- over NCCL (NVLink / NVSwitch).  One process per GPU or one thread per GPU.
+ *   full  : context with the event tables of the WHOLE selection (it routes; it never counts)
+ *   shard : context with the tables of this rank's events, covered regions of the whole selection
+ *           (lsqh_annotation_load with shard_begin/shard_end)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct lsq_comm lsq_comm;
+#define LSQ_COMM_ID_BYTES 128
+#define LSQ_MAX_RANKS 16
+int lsq_comm_unique_id(void *id /* LSQ_COMM_ID_BYTES, filled on one rank and handed to all */);
+int lsq_comm_create(const void *id, int n_ranks, int rank, int device, lsq_comm **out); /* collective (ncclCommInitRank) */
+int lsq_comm_attach(void *nccl_comm /* an existing ncclComm_t */, int n_ranks, int rank, int device, lsq_comm **out);
+int lsq_comm_destroy(lsq_comm *comm);
+
+/* Which rank owns which event: shard_begin[n_ranks + 1], ascending, shard_begin[0] = 0, last = n_events. */
+int lsq_router_build(lsq_ctx *full, uint32_t n_ranks, const uint32_t *shard_begin);
+
+typedef struct lsq_shard_stats {
+    uint64_t reads_local, reads_sent, reads_received; /* sent counts a read once per destination */
+    uint64_t blocks_received;
+    float route_ms, exchange_ms;                      /* CUDA events: bucketing kernel, NCCL exchange */
+} lsq_shard_stats;
+/* Buckets read set m_src of `full` (this rank's slice, declared with lsq_set_reads; first_line = line number of
+ * its first read in the whole file, 1 for the first slice) per destination rank, exchanges the buckets and
+ * declares what arrives as read set m_dst of `shard` (device resident, with the reads' global line numbers).
+ * Collective: every rank of the communicator must call it. */
+int lsq_shard_reads(lsq_ctx *full, uint32_t m_src, lsq_ctx *shard, uint32_t m_dst, lsq_comm *comm, uint64_t first_line,
+                    lsq_shard_stats *stats /* may be NULL */);
+/* Gathers the per-event / per-form results of all shards on `root` in gene-rank order (one NCCL send/recv group;
+ * no collective runs inside the count/solve loop).  count/solve: host buffers for the WHOLE selection on root
+ * (NULL members and NULL structs are skipped; ignored on the other ranks).  Collective. */
+int lsq_gather(lsq_ctx *full, lsq_ctx *shard, lsq_comm *comm, int root, lsq_count_out *count, lsq_solve_out *solve);
+
 /* ARS length of one form (accessible_read_starts.h:48-89, 184-189, 221-274), host helper. */
 uint64_t lsq_ars_length(uint32_t read_type, uint64_t read_length, const uint64_t *seg_len, uint32_t n);
 

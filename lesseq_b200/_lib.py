@@ -14,6 +14,7 @@ LSQ_READ_MEDIUM = 1
 LSQ_READ_SHORT = 2
 LSQ_READ_MIXED = 0x80000000
 LSQ_READS_STREAM = 1
+LSQ_COMM_ID_BYTES = 128
 LSQ_MAX_METHODS = 16
 READ_TYPES = {"MEDIUM_READ": LSQ_READ_MEDIUM, "SHORT_READ": LSQ_READ_SHORT}
 
@@ -68,6 +69,11 @@ class Timings(C.Structure):
     ]
 
 
+class ShardStats(C.Structure):
+    _fields_ = [("reads_local", C.c_uint64), ("reads_sent", C.c_uint64), ("reads_received", C.c_uint64),
+                ("blocks_received", C.c_uint64), ("route_ms", C.c_float), ("exchange_ms", C.c_float)]
+
+
 class DeviceResults(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("n_valid", "bases", "iso_count", "theta", "rpkm", "loglik", "ll_per_read",
                                            "iters")]
@@ -98,6 +104,14 @@ SYMBOLS = {
     "lsq_get_solve": (C.c_int, [C.c_void_p, C.POINTER(SolveOut)]),
     "lsq_get_timings": (C.c_int, [C.c_void_p, C.POINTER(Timings)]),
     "lsq_get_device_results": (C.c_int, [C.c_void_p, C.POINTER(DeviceResults)]),
+    "lsq_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "lsq_comm_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "lsq_comm_attach": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "lsq_comm_destroy": (C.c_int, [C.c_void_p]),
+    "lsq_router_build": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p]),
+    "lsq_shard_reads": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64,
+                                  C.POINTER(ShardStats)]),
+    "lsq_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(CountOut), C.POINTER(SolveOut)]),
     "lsq_ars_length": (C.c_uint64, [C.c_uint32, C.c_uint64, c_u64p, C.c_uint32]),
     "lsqh_annotation_load": (C.c_int, [C.c_char_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
                                        C.POINTER(C.c_void_p)]),

@@ -336,6 +336,69 @@ class Context:
         return {k: getattr(t, k) for k, _ in _lib.Timings._fields_}
 
 
+class Comm:
+    """NCCL communicator of the gene-range shards (lsq_comm): one rank per GPU.  `uid` comes from
+    Comm.unique_id() on one rank and is handed to all (e.g. torch.distributed.broadcast_object_list)."""
+
+    def __init__(self, uid, n_ranks, rank, device):
+        self._lib = _lib.load()
+        self._c = C.c_void_p()
+        self.n_ranks, self.rank = n_ranks, rank
+        buf = C.create_string_buffer(bytes(uid), 128)
+        check(self._lib.lsq_comm_create(buf, n_ranks, rank, device, C.byref(self._c)))
+
+    @staticmethod
+    def unique_id():
+        buf = C.create_string_buffer(128)
+        check(_lib.load().lsq_comm_unique_id(buf))
+        return bytes(buf.raw)
+
+    def close(self):
+        if getattr(self, "_c", None):
+            self._lib.lsq_comm_destroy(self._c)
+            self._c = None
+
+    __del__ = close
+
+
+def router_build(full_ctx, shard_begin):
+    """Declare which rank owns which events of the whole selection held by `full_ctx`
+    (shard_begin: n_ranks + 1 ascending event indices, gene-rank order)."""
+    sb = np.ascontiguousarray(shard_begin, dtype=np.uint32)
+    check(full_ctx._lib.lsq_router_build(full_ctx._c, len(sb) - 1, _ptr(sb)))
+    full_ctx._shard_begin = sb
+
+
+def shard_reads(full_ctx, m_src, shard_ctx, m_dst, comm, first_line=1):
+    """Bucket read set m_src of full_ctx (this rank's slice) per owning rank, exchange over NCCL and declare what
+    arrives as read set m_dst of shard_ctx.  Collective.  Returns the lsq_shard_stats as a dict."""
+    st = _lib.ShardStats()
+    check(full_ctx._lib.lsq_shard_reads(full_ctx._c, m_src, shard_ctx._c, m_dst, comm._c, first_line, C.byref(st)))
+    shard_ctx.M = max(shard_ctx.M, m_dst + 1)
+    return {k: getattr(st, k) for k, _ in _lib.ShardStats._fields_}
+
+
+def gather(full_ctx, shard_ctx, comm, root=0, solved=True):
+    """Gather all shards' result rows on `root` in gene-rank order (lsq_gather).  Collective.  Returns
+    (count, solve) dicts for the whole selection on root, (None, None) elsewhere."""
+    M, E, F = shard_ctx.M, full_ctx.E, full_ctx.F
+    if comm.rank != root:
+        check(full_ctx._lib.lsq_gather(full_ctx._c, shard_ctx._c, comm._c, root, None, None))
+        return None, None
+    nv = np.zeros((M, E), dtype=np.uint64)
+    bs = np.zeros((M, E), dtype=np.uint64)
+    iso = np.zeros(F, dtype=np.uint64)
+    th, rp, se = np.zeros(F), np.zeros(F), np.zeros(F)
+    ll, lp = np.zeros(E), np.zeros(E)
+    it = np.zeros(E, dtype=np.uint32)
+    co = _lib.CountOut(_ptr(nv), _ptr(bs), _ptr(iso))
+    so = _lib.SolveOut(_ptr(th), _ptr(rp), _ptr(ll), _ptr(lp), _ptr(it), _ptr(se))
+    check(full_ctx._lib.lsq_gather(full_ctx._c, shard_ctx._c, comm._c, root, C.byref(co), C.byref(so) if solved else None))
+    count = {"n_valid": nv, "bases": bs, "iso_count": iso}
+    solve = {"theta": th, "rpkm": rp, "loglik": ll, "ll_per_read": lp, "iters": it, "se": se} if solved else None
+    return count, solve
+
+
 def ars_length(read_type, read_length, seg_len):
     rt = READ_TYPES[read_type] if isinstance(read_type, str) else read_type
     a = np.ascontiguousarray(seg_len, dtype=np.uint64)

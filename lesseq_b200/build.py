@@ -27,7 +27,8 @@ def _sources():
 
 
 def _deps():
-    return (glob.glob(os.path.join(CSRC, "*.cu*")) + glob.glob(os.path.join(CSRC, "host", "*")) +
+    return (glob.glob(os.path.join(CSRC, "*.cu*")) + glob.glob(os.path.join(CSRC, "*.hpp")) +
+            glob.glob(os.path.join(CSRC, "host", "*")) +
             [os.path.join(os.path.dirname(PKG), "include", "lesseq_b200.h"), os.path.abspath(__file__)])
 
 

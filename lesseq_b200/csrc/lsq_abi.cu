@@ -3,6 +3,9 @@
 //
 // No CPU fallback: every compute entry point needs a CUDA device and fails with LSQ_ERR_CUDA
 // otherwise.  Host code here only lays tables out and orchestrates launches.
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -14,6 +17,8 @@
 #include "../../include/lesseq_b200.h"
 #include "lsq_kernels.cuh"
 #include "lsq_tables_host.hpp"
+
+static_assert(lsq::ROUTE_MAX_RANKS == LSQ_MAX_RANKS, "rank limit of the router");
 
 namespace {
 
@@ -80,6 +85,7 @@ struct ReadSet {
     const uint16_t *blk_len = nullptr;
     const uint8_t *blk_len8 = nullptr;
     DevBuf d_chrom_remap, d_file_meta, d_strand_tbl;
+    std::vector<std::string> chrom_names, strand_names;  // the file dictionaries (kept for lsq_shard_reads)
     // injected classes (output order CSR)
     DevBuf d_inj_off, d_inj_mask, d_inj_cnt;
     std::vector<uint64_t> h_inj_off;
@@ -106,6 +112,11 @@ struct lsq_ctx {
     uint32_t M = 0;  // highest declared index + 1
     // per-run state
     DevBuf d_slot_cnt, d_slot_mask, d_bases, d_G, d_counters;
+    // router (multi-GPU; this context holds the tables of the whole selection)
+    uint32_t route_ranks = 0;
+    std::vector<uint32_t> shard_begin, form_begin;  // [n_ranks+1] event / form boundaries in output order
+    DevBuf d_owner, d_cursor, d_gather;
+    DevBuf d_out[LSQ_MAX_RANKS][6], d_in[6];  // outboxes per destination, inbox: cnt, cs, line, start|blk, len, blk_cs
     DevBuf d_ext, d_scratch, d_gen_list;  // d_scratch: signature counters | hash | general-list length (cleared per read set)
     uint32_t scan_flags = 0;
     DevBuf d_n_valid, d_bases_out, d_iso, d_theta, d_rpkm, d_se, d_ll, d_llpr, d_iters;
@@ -458,6 +469,13 @@ int lsq_set_reads(lsq_ctx *c, uint32_t m, uint32_t read_type, uint64_t read_leng
         }
     }
     // dictionaries: file chromosome ids -> annotation ids; strand order table
+    {
+        std::vector<std::string> cn(r->n_chrom_names), sn(r->n_strand_names);  // copied first: r may alias rs' own vectors
+        for (uint32_t i = 0; i < r->n_chrom_names; ++i) cn[i] = r->chrom_names[i];
+        for (uint32_t i = 0; i < r->n_strand_names; ++i) sn[i] = r->strand_names[i];
+        rs.chrom_names.swap(cn);
+        rs.strand_names.swap(sn);
+    }
     std::vector<uint32_t> remap(std::max<uint32_t>(r->n_chrom_names, 1), 0xFFFFFFFFu);
     for (uint32_t i = 0; i < r->n_chrom_names; ++i) {
         auto it = c->chrom_id.find(r->chrom_names[i]);
@@ -674,7 +692,9 @@ int lsq_count(lsq_ctx *c) {
         if (n) {
             const uint64_t n_groups = (n + lsq::SCAN_GROUP - 1) / lsq::SCAN_GROUP;
             const unsigned grid = (unsigned)std::min<uint64_t>((n_groups + lsq::SCAN_WARPS - 1) / lsq::SCAN_WARPS, (uint64_t)c->n_sms * lsq::SCAN_MINB);
-            lsq::lsq_scan_kernel<<<grid, lsq::SCAN_BLOCK, 0, s>>>(P);
+            const bool compact = P.blk_cnt && P.read_cs8 && P.blk_start && P.blk_len8;
+            if (compact) lsq::lsq_scan_kernel<true><<<grid, lsq::SCAN_BLOCK, 0, s>>>(P);
+            else lsq::lsq_scan_kernel<false><<<grid, lsq::SCAN_BLOCK, 0, s>>>(P);
             LSQ_CUDA(cudaGetLastError());
             tm.launches++;
         }
@@ -903,6 +923,378 @@ int lsq_get_timings(lsq_ctx *c, lsq_timings *o) {
         c->tm_solve_pending = false;
     }
     *o = tm;
+    return LSQ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Multi-GPU: NCCL is loaded on first use, so that single-GPU callers do not need it installed.
+// ---------------------------------------------------------------------------------------------
+}  // extern "C"
+
+namespace {
+
+struct NcclApi {
+    void *h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+
+int nccl_load() {
+    if (g_nccl.h) return LSQ_OK;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return fail(LSQ_ERR_CUDA, std::string("NCCL not available: ") + dlerror());
+#define LSQ_SYM(field, name)                                                              \
+    *reinterpret_cast<void **>(&g_nccl.field) = dlsym(h, name);                          \
+    if (!g_nccl.field) return fail(LSQ_ERR_CUDA, std::string("NCCL symbol missing: ") + name)
+    LSQ_SYM(GetUniqueId, "ncclGetUniqueId");
+    LSQ_SYM(CommInitRank, "ncclCommInitRank");
+    LSQ_SYM(CommDestroy, "ncclCommDestroy");
+    LSQ_SYM(GroupStart, "ncclGroupStart");
+    LSQ_SYM(GroupEnd, "ncclGroupEnd");
+    LSQ_SYM(Send, "ncclSend");
+    LSQ_SYM(Recv, "ncclRecv");
+    LSQ_SYM(AllGather, "ncclAllGather");
+    LSQ_SYM(GetErrorString, "ncclGetErrorString");
+#undef LSQ_SYM
+    g_nccl.h = h;
+    return LSQ_OK;
+}
+
+#define LSQ_NCCL(expr)                                                                                   \
+    do {                                                                                                 \
+        ncclResult_t r_ = (expr);                                                                        \
+        if (r_ != ncclSuccess) return fail(LSQ_ERR_CUDA, std::string(#expr) + ": " + g_nccl.GetErrorString(r_)); \
+    } while (0)
+
+}  // namespace
+
+struct lsq_comm {
+    ncclComm_t comm = nullptr;
+    int n_ranks = 0, rank = 0, device = 0;
+    bool owned = false;
+};
+
+extern "C" {
+
+int lsq_comm_unique_id(void *id) {
+    if (!id) return fail(LSQ_ERR_ARG, "lsq_comm_unique_id: null argument");
+    static_assert(sizeof(ncclUniqueId) == LSQ_COMM_ID_BYTES, "ncclUniqueId size");
+    int rc = nccl_load();
+    if (rc) return rc;
+    LSQ_NCCL(g_nccl.GetUniqueId(reinterpret_cast<ncclUniqueId *>(id)));
+    return LSQ_OK;
+}
+
+int lsq_comm_create(const void *id, int n_ranks, int rank, int device, lsq_comm **out) {
+    if (!id || !out) return fail(LSQ_ERR_ARG, "lsq_comm_create: null argument");
+    if (n_ranks < 1 || n_ranks > (int)LSQ_MAX_RANKS || rank < 0 || rank >= n_ranks)
+        return fail(LSQ_ERR_RANGE, "lsq_comm_create: 1..16 ranks");
+    int rc = nccl_load();
+    if (rc) return rc;
+    LSQ_CUDA(cudaSetDevice(device));
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof uid);
+    ncclComm_t comm;
+    LSQ_NCCL(g_nccl.CommInitRank(&comm, n_ranks, uid, rank));
+    lsq_comm *c = new lsq_comm();
+    c->comm = comm;
+    c->n_ranks = n_ranks;
+    c->rank = rank;
+    c->device = device;
+    c->owned = true;
+    *out = c;
+    return LSQ_OK;
+}
+
+int lsq_comm_attach(void *nccl_comm, int n_ranks, int rank, int device, lsq_comm **out) {
+    if (!nccl_comm || !out) return fail(LSQ_ERR_ARG, "lsq_comm_attach: null argument");
+    if (n_ranks < 1 || n_ranks > (int)LSQ_MAX_RANKS || rank < 0 || rank >= n_ranks)
+        return fail(LSQ_ERR_RANGE, "lsq_comm_attach: 1..16 ranks");
+    int rc = nccl_load();
+    if (rc) return rc;
+    lsq_comm *c = new lsq_comm();
+    c->comm = reinterpret_cast<ncclComm_t>(nccl_comm);
+    c->n_ranks = n_ranks;
+    c->rank = rank;
+    c->device = device;
+    c->owned = false;
+    *out = c;
+    return LSQ_OK;
+}
+
+int lsq_comm_destroy(lsq_comm *c) {
+    if (!c) return LSQ_OK;
+    if (c->owned && c->comm && g_nccl.h) g_nccl.CommDestroy(c->comm);
+    delete c;
+    return LSQ_OK;
+}
+
+int lsq_router_build(lsq_ctx *c, uint32_t n_ranks, const uint32_t *shard_begin) {
+    if (!c || !shard_begin) return fail(LSQ_ERR_ARG, "lsq_router_build: null argument");
+    if (!c->have_tables) return fail(LSQ_ERR_STATE, "lsq_router_build before lsq_upload_events");
+    if (n_ranks < 1 || n_ranks > LSQ_MAX_RANKS) return fail(LSQ_ERR_RANGE, "lsq_router_build: 1..16 ranks");
+    if (shard_begin[0] != 0 || shard_begin[n_ranks] != c->E) return fail(LSQ_ERR_ARG, "lsq_router_build: shard_begin must span all events");
+    for (uint32_t d = 0; d < n_ranks; ++d)
+        if (shard_begin[d] > shard_begin[d + 1]) return fail(LSQ_ERR_ARG, "lsq_router_build: shard_begin must ascend");
+    LSQ_CUDA(cudaSetDevice(c->device));
+    const lsq::HostTables &H = c->H;
+    c->route_ranks = n_ranks;
+    c->shard_begin.assign(shard_begin, shard_begin + n_ranks + 1);
+    // forms per shard: the events' form ranges in output order
+    std::vector<uint32_t> form_off(c->E + 1, 0);
+    for (uint32_t x = 0; x < c->E; ++x) form_off[H.hdr[x].out_ev + 1] = H.hdr[x].K;
+    for (uint32_t e = 0; e < c->E; ++e) form_off[e + 1] += form_off[e];
+    c->form_begin.resize(n_ranks + 1);
+    for (uint32_t d = 0; d <= n_ranks; ++d) c->form_begin[d] = form_off[shard_begin[d]];
+    // owner mask of every piece
+    const size_t np = H.bp_pos.size();
+    std::vector<unsigned long long> owner(np + 1, 0ull);
+    for (size_t p = 0; p < np; ++p)
+        for (uint32_t q = H.stab_off[p]; q < H.stab_off[p + 1]; ++q) {
+            const uint32_t e = H.hdr[H.stab[q].x].out_ev;
+            const uint32_t d = (uint32_t)(std::upper_bound(shard_begin, shard_begin + n_ranks + 1, e) - shard_begin) - 1u;
+            owner[p] |= 1ull << std::min(d, n_ranks - 1);
+        }
+    LSQ_CUDA(upload(c->d_owner, owner, c->stream));
+    LSQ_CUDA(c->d_cursor.ensure((size_t)(2 * LSQ_MAX_RANKS + 2 * LSQ_MAX_RANKS * LSQ_MAX_RANKS) * 8));
+    LSQ_CUDA(cudaStreamSynchronize(c->stream));
+    return LSQ_OK;
+}
+
+int lsq_shard_reads(lsq_ctx *full, uint32_t m_src, lsq_ctx *shard, uint32_t m_dst, lsq_comm *comm, uint64_t first_line,
+                    lsq_shard_stats *stats) {
+    if (!full || !shard || !comm) return fail(LSQ_ERR_ARG, "lsq_shard_reads: null argument");
+    if (full->route_ranks != (uint32_t)comm->n_ranks) return fail(LSQ_ERR_STATE, "lsq_shard_reads: lsq_router_build with the communicator's rank count first");
+    if (m_src >= LSQ_MAX_METHODS || !full->sets[m_src].declared || full->sets[m_src].injected)
+        return fail(LSQ_ERR_STATE, "lsq_shard_reads: read set m_src is not declared on the full context");
+    if (full->device != shard->device) return fail(LSQ_ERR_ARG, "lsq_shard_reads: both contexts must be on the communicator's device");
+    LSQ_CUDA(cudaSetDevice(full->device));
+    ReadSet &rs = full->sets[m_src];
+    cudaStream_t s = full->stream;
+    const uint32_t P = (uint32_t)comm->n_ranks, me = (uint32_t)comm->rank;
+    const size_t n = rs.n_reads, nb = rs.n_blocks;
+    if (first_line + n > 0xFFFFFFFFull) return fail(LSQ_ERR_RANGE, "line numbers exceed 32 bits");
+    const bool compact_blk = rs.blk_start != nullptr, len8 = rs.blk_len8 != nullptr, cs8 = rs.read_cs8 != nullptr;
+    const bool mixed = rs.blk_cs != nullptr;
+    const size_t blk_bytes = compact_blk ? 4 : 8, len_bytes = compact_blk ? (len8 ? 1 : 2) : 0, cs_bytes = cs8 ? 1 : 4;
+    // outboxes: worst case every read goes to one destination
+    lsq::RouteParams R;
+    memset(&R, 0, sizeof R);
+    R.n_ranks = P;
+    R.line_base = (uint32_t)(first_line - 1);
+    R.owner = full->d_owner.as<unsigned long long>();
+    R.cursor = full->d_cursor.as<unsigned long long>();
+    for (uint32_t d = 0; d < P; ++d) {
+        DevBuf *o = full->d_out[d];
+        LSQ_CUDA(o[0].ensure(n + 16));
+        LSQ_CUDA(o[1].ensure(n * cs_bytes + 16));
+        LSQ_CUDA(o[2].ensure(n * 4 + 16));
+        LSQ_CUDA(o[3].ensure(nb * blk_bytes + 16));
+        if (len_bytes) LSQ_CUDA(o[4].ensure(nb * len_bytes + 16));
+        if (mixed) LSQ_CUDA(o[5].ensure(nb * 4 + 16));
+        lsq::RouteBox &B = R.box[d];
+        B.blk_cnt = o[0].as<uint8_t>();
+        if (cs8) B.read_cs8 = o[1].as<uint8_t>();
+        else B.read_cs = o[1].as<uint32_t>();
+        B.line_num = o[2].as<uint32_t>();
+        if (compact_blk) {
+            B.blk_start = o[3].as<int32_t>();
+            if (len8) B.blk_len8 = o[4].as<uint8_t>();
+            else B.blk_len = o[4].as<uint16_t>();
+        } else {
+            B.blk = o[3].as<int2>();
+        }
+        if (mixed) B.blk_cs = o[5].as<uint32_t>();
+    }
+    lsq::ScanParams SP;
+    memset(&SP, 0, sizeof SP);
+    SP.T = full->T;
+    SP.n_reads = n;
+    SP.blk_off = rs.blk_cnt ? nullptr : rs.blk_off;
+    SP.blk_cnt = rs.blk_cnt;
+    SP.grp_base = rs.d_grp_base.as<uint32_t>();
+    SP.sup_base = rs.d_sup_base.as<uint32_t>();
+    SP.blk = rs.blk;
+    SP.read_cs = rs.read_cs;
+    SP.read_cs8 = rs.read_cs8;
+    SP.blk_start = rs.blk_start;
+    SP.blk_len = rs.blk_len;
+    SP.blk_len8 = rs.blk_len8;
+    SP.blk_cs = rs.blk_cs;
+    SP.chrom_remap = rs.d_chrom_remap.as<uint32_t>();
+    SP.file_meta = rs.d_file_meta.as<uint4>();
+    SP.line_num = rs.line_num;
+    cudaEvent_t *ev = full->ev_set[m_src];
+    if (rs.copy_pending) {  // a streamed slice: the router needs all of it
+        LSQ_CUDA(cudaStreamWaitEvent(s, full->ev_all[m_src], 0));
+    }
+    LSQ_CUDA(cudaEventRecord(ev[0], s));
+    LSQ_CUDA(cudaMemsetAsync(R.cursor, 0, 2 * LSQ_MAX_RANKS * 8, s));
+    if (n) {
+        const uint64_t n_groups = (n + lsq::SCAN_GROUP - 1) / lsq::SCAN_GROUP;
+        const unsigned grid = (unsigned)std::min<uint64_t>((n_groups + lsq::SCAN_WARPS - 1) / lsq::SCAN_WARPS, (uint64_t)full->n_sms * lsq::SCAN_MINB);
+        lsq::lsq_route_kernel<<<grid, lsq::SCAN_BLOCK, 0, s>>>(SP, R);
+        LSQ_CUDA(cudaGetLastError());
+    }
+    LSQ_CUDA(cudaEventRecord(ev[1], s));
+    // sizes: every rank learns how much every rank sends to every rank
+    unsigned long long *d_mat = R.cursor + 2 * LSQ_MAX_RANKS;
+    LSQ_NCCL(g_nccl.AllGather(R.cursor, d_mat, 2 * LSQ_MAX_RANKS, ncclUint64, comm->comm, s));
+    std::vector<unsigned long long> mat((size_t)P * 2 * LSQ_MAX_RANKS);
+    LSQ_CUDA(cudaMemcpyAsync(mat.data(), d_mat, mat.size() * 8, cudaMemcpyDeviceToHost, s));
+    LSQ_CUDA(cudaStreamSynchronize(s));
+    if (rs.copy_pending) rs.copy_pending = false;
+    auto sent_reads = [&](uint32_t src, uint32_t dst) { return (size_t)mat[(size_t)src * 2 * LSQ_MAX_RANKS + 2 * dst]; };
+    auto sent_blocks = [&](uint32_t src, uint32_t dst) { return (size_t)mat[(size_t)src * 2 * LSQ_MAX_RANKS + 2 * dst + 1]; };
+    size_t in_reads = 0, in_blocks = 0, out_reads = 0;
+    std::vector<size_t> roff(P + 1, 0), boff(P + 1, 0);
+    for (uint32_t src = 0; src < P; ++src) {
+        roff[src] = in_reads;
+        boff[src] = in_blocks;
+        in_reads += sent_reads(src, me);
+        in_blocks += sent_blocks(src, me);
+    }
+    for (uint32_t d = 0; d < P; ++d) out_reads += sent_reads(me, d);
+    if (in_blocks + 2 * in_reads > 0xFFFFFFF0ull) return fail(LSQ_ERR_RANGE, "received read set exceeds 2^32 (blocks + 2 * reads)");
+    DevBuf *in = full->d_in;
+    LSQ_CUDA(in[0].ensure(in_reads + 16));
+    LSQ_CUDA(in[1].ensure(in_reads * cs_bytes + 16));
+    LSQ_CUDA(in[2].ensure(in_reads * 4 + 16));
+    LSQ_CUDA(in[3].ensure(in_blocks * blk_bytes + 16));
+    if (len_bytes) LSQ_CUDA(in[4].ensure(in_blocks * len_bytes + 16));
+    if (mixed) LSQ_CUDA(in[5].ensure(in_blocks * 4 + 16));
+    LSQ_CUDA(cudaEventRecord(ev[2], s));
+    LSQ_NCCL(g_nccl.GroupStart());
+    for (uint32_t peer = 0; peer < P; ++peer) {
+        const size_t sr = sent_reads(me, peer), sb = sent_blocks(me, peer), rr = sent_reads(peer, me), rb = sent_blocks(peer, me);
+        DevBuf *o = full->d_out[peer];
+        const size_t unit[6] = {1, cs_bytes, 4, blk_bytes, len_bytes, (size_t)(mixed ? 4 : 0)};
+        for (int a = 0; a < 6; ++a) {
+            if (!unit[a]) continue;
+            const bool per_read = a < 3;
+            const size_t sbytes = (per_read ? sr : sb) * unit[a], rbytes = (per_read ? rr : rb) * unit[a];
+            const size_t roffb = (per_read ? roff[peer] : boff[peer]) * unit[a];
+            if (sbytes) LSQ_NCCL(g_nccl.Send(o[a].p, sbytes, ncclUint8, (int)peer, comm->comm, s));
+            if (rbytes) LSQ_NCCL(g_nccl.Recv(in[a].as<unsigned char>() + roffb, rbytes, ncclUint8, (int)peer, comm->comm, s));
+        }
+    }
+    LSQ_NCCL(g_nccl.GroupEnd());
+    LSQ_CUDA(cudaEventRecord(ev[3], s));
+    LSQ_CUDA(cudaStreamSynchronize(s));
+    // what arrived is read set m_dst of the shard context (borrowed device arrays)
+    lsq_packed_reads v;
+    memset(&v, 0, sizeof v);
+    v.n_reads = in_reads;
+    v.n_blocks = in_blocks;
+    v.blk_cnt = in[0].as<uint8_t>();
+    if (cs8) v.read_cs8 = in[1].as<uint8_t>();
+    else v.read_cs = in[1].as<uint32_t>();
+    v.line_num = in[2].as<uint32_t>();
+    if (compact_blk) {
+        v.blk_start = in[3].as<int32_t>();
+        if (len8) v.blk_len8 = in[4].as<uint8_t>();
+        else v.blk_len = in[4].as<uint16_t>();
+    } else {
+        v.blk = in[3].as<int32_t>();
+    }
+    if (mixed) v.blk_cs = in[5].as<uint32_t>();
+    std::vector<const char *> cn(full->sets[m_src].chrom_names.size()), sn(full->sets[m_src].strand_names.size());
+    for (size_t i = 0; i < cn.size(); ++i) cn[i] = full->sets[m_src].chrom_names[i].c_str();
+    for (size_t i = 0; i < sn.size(); ++i) sn[i] = full->sets[m_src].strand_names[i].c_str();
+    v.n_chrom_names = (uint32_t)cn.size();
+    v.n_strand_names = (uint32_t)sn.size();
+    v.chrom_names = cn.data();
+    v.strand_names = sn.data();
+    v.on_device = 1;
+    int rc = lsq_set_reads(shard, m_dst, rs.type, rs.read_length, &v);
+    if (rc) return rc;
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        stats->reads_local = n;
+        stats->reads_sent = out_reads;
+        stats->reads_received = in_reads;
+        stats->blocks_received = in_blocks;
+        LSQ_CUDA(cudaEventElapsedTime(&stats->route_ms, ev[0], ev[1]));
+        LSQ_CUDA(cudaEventElapsedTime(&stats->exchange_ms, ev[2], ev[3]));
+    }
+    return LSQ_OK;
+}
+
+int lsq_gather(lsq_ctx *full, lsq_ctx *shard, lsq_comm *comm, int root, lsq_count_out *count, lsq_solve_out *solve) {
+    if (!full || !shard || !comm) return fail(LSQ_ERR_ARG, "lsq_gather: null argument");
+    if (full->route_ranks != (uint32_t)comm->n_ranks) return fail(LSQ_ERR_STATE, "lsq_gather: lsq_router_build first");
+    if (!shard->finalized) return fail(LSQ_ERR_STATE, "lsq_gather before lsq_count");
+    LSQ_CUDA(cudaSetDevice(shard->device));
+    const uint32_t P = (uint32_t)comm->n_ranks, me = (uint32_t)comm->rank, M = shard->M;
+    const std::vector<uint32_t> &eb = full->shard_begin, &fb = full->form_begin;
+    const size_t E = full->E, F = full->F;
+    if (shard->E != eb[me + 1] - eb[me] || shard->F != fb[me + 1] - fb[me]) return fail(LSQ_ERR_ARG, "lsq_gather: the shard context does not hold this rank's events");
+    cudaStream_t s = shard->stream;
+    const bool solved = shard->solved;
+    // root buffer: n_valid [M][E] | bases [M][E] | iso [F] | theta [F] | rpkm [F] | se [F] | ll [E] | llpr [E] | iters [E] (u32)
+    const size_t o_nv = 0, o_bs = o_nv + M * E * 8, o_iso = o_bs + M * E * 8, o_th = o_iso + F * 8, o_rp = o_th + F * 8, o_se = o_rp + F * 8,
+                 o_ll = o_se + F * 8, o_lp = o_ll + E * 8, o_it = o_lp + E * 8, total = o_it + E * 4 + 16;
+    unsigned char *g = nullptr;
+    if ((int)me == root) {
+        LSQ_CUDA(full->d_gather.ensure(total));
+        g = full->d_gather.as<unsigned char>();
+    }
+    struct Arr {
+        const void *src;
+        size_t off, unit;
+        bool per_event, per_m;
+    };
+    const Arr arrs[9] = {{shard->d_n_valid.p, o_nv, 8, true, true}, {shard->d_bases_out.p, o_bs, 8, true, true},
+                         {shard->d_iso.p, o_iso, 8, false, false},  {shard->d_theta.p, o_th, 8, false, false},
+                         {shard->d_rpkm.p, o_rp, 8, false, false},   {shard->d_se.p, o_se, 8, false, false},
+                         {shard->d_ll.p, o_ll, 8, true, false},      {shard->d_llpr.p, o_lp, 8, true, false},
+                         {shard->d_iters.p, o_it, 4, true, false}};
+    LSQ_NCCL(g_nccl.GroupStart());
+    for (int a = 0; a < 9; ++a) {
+        if (a >= 3 && !solved) continue;
+        const Arr &A = arrs[a];
+        const size_t mine = A.per_event ? shard->E : shard->F;
+        const uint32_t reps = A.per_m ? M : 1;
+        for (uint32_t m = 0; m < reps; ++m) {
+            if (mine) LSQ_NCCL(g_nccl.Send(static_cast<const unsigned char *>(A.src) + (size_t)m * mine * A.unit, mine * A.unit, ncclUint8, root, comm->comm, s));
+            if ((int)me == root)
+                for (uint32_t d = 0; d < P; ++d) {
+                    const size_t cnt = A.per_event ? eb[d + 1] - eb[d] : fb[d + 1] - fb[d];
+                    const size_t at = A.per_event ? eb[d] : fb[d];
+                    const size_t row = A.per_event ? E : F;
+                    if (cnt) LSQ_NCCL(g_nccl.Recv(g + A.off + ((size_t)m * row + at) * A.unit, cnt * A.unit, ncclUint8, (int)d, comm->comm, s));
+                }
+        }
+    }
+    LSQ_NCCL(g_nccl.GroupEnd());
+    if ((int)me == root) {
+        auto d2h = [&](void *dst, size_t off, size_t bytes) {
+            return (dst && bytes) ? cudaMemcpyAsync(dst, g + off, bytes, cudaMemcpyDeviceToHost, s) : cudaSuccess;
+        };
+        if (count) {
+            LSQ_CUDA(d2h(count->n_valid, o_nv, M * E * 8));
+            LSQ_CUDA(d2h(count->bases, o_bs, M * E * 8));
+            LSQ_CUDA(d2h(count->iso_count, o_iso, F * 8));
+        }
+        if (solve && solved) {
+            LSQ_CUDA(d2h(solve->theta, o_th, F * 8));
+            LSQ_CUDA(d2h(solve->rpkm, o_rp, F * 8));
+            LSQ_CUDA(d2h(solve->se, o_se, F * 8));
+            LSQ_CUDA(d2h(solve->loglik, o_ll, E * 8));
+            LSQ_CUDA(d2h(solve->ll_per_read, o_lp, E * 8));
+            LSQ_CUDA(d2h(solve->iters, o_it, E * 4));
+        }
+    }
+    LSQ_CUDA(cudaStreamSynchronize(s));
     return LSQ_OK;
 }
 

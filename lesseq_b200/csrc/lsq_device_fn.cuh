@@ -434,21 +434,37 @@ LSQ_HD uint32_t block_lookup(const ScanParams &P, int2 b, uint32_t cs) {
 constexpr uint32_t RT_NONE = 0, RT_SINGLE = 1, RT_PAIR = 2, RT_GENERAL = 3;
 
 // Number of cuts of the piece `raw` below block end e (the block starts inside the piece); exact: e hits cut k;
-// q_prev: the largest cut below e (k > 0).
+// q_prev: the largest cut below e (k > 0).  The first two cuts come with the piece record.
 LSQ_HD uint32_t cut_category(const Tables &T, uint4 raw, int32_t e, bool &exact, int32_t &q_prev) {
-    const uint32_t n = piece_ncuts(raw.z), so = raw.z & PIECE_SIG_MASK;
+    const uint32_t n = piece_ncuts(raw.z);
     const int32_t pos = (int32_t)raw.x;
-    uint32_t k = 0;
-    int32_t q = 0;
+    const int32_t q0 = pos + (int32_t)(raw.w & 0xFFFFu), q1 = pos + (int32_t)(raw.w >> 16);
     q_prev = pos;
+    exact = false;
+    if (n == 0u) return 0u;
+    if (e <= q0) {
+        exact = e == q0;
+        return 0u;
+    }
+    q_prev = q0;
+    if (n == 1u) return 1u;
+    if (e <= q1) {
+        exact = e == q1;
+        return 1u;
+    }
+    q_prev = q1;
+    uint32_t k = 2;
+    const uint32_t so = raw.z & PIECE_SIG_MASK;
     LSQ_NO_UNROLL
-    while (k < n) {
-        q = k == 0u ? pos + (int32_t)(raw.w & 0xFFFFu) : (k == 1u ? pos + (int32_t)(raw.w >> 16) : LSQ_LD(T.sig_cut + so + k));
-        if (!(q < e)) break;
+    while (k < n) {  // one piece in twenty has more than two cuts
+        const int32_t q = LSQ_LD(T.sig_cut + so + k);
+        if (e <= q) {
+            exact = e == q;
+            break;
+        }
         q_prev = q;
         ++k;
     }
-    exact = k < n && q == e;
     return k;
 }
 

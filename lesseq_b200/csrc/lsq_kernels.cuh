@@ -112,19 +112,23 @@ __global__ void __launch_bounds__(1024) lsq_super_scan_kernel(uint32_t *__restri
 
 // ---------------------------------------------------------------------------------------------
 // Scan kernel.  A warp owns a group of 128 consecutive reads at a time (grid-stride over the groups);
-// nothing is shared between warps or lanes beyond two warp scans, so there is no shared memory and no
-// block-wide barrier anywhere: the warps of an SM drift apart and cover each other's L2 latencies.
+// warps share nothing, so there is no block-wide barrier anywhere: the warps of an SM drift apart and
+// cover each other's L2 latencies.  The loops are rolled on purpose: the whole kernel is ~1 k SASS
+// instructions and stays resident in the instruction cache.
 // Phase A: lane l owns reads 4l..4l+3 of the group: ONE 32-bit load brings their four block counts, one
 //          more their chromosome/strand ids; a warp scan of the counts gives every read's first block.
-// Phase S: reads with one raw block (4 in 5), SCAN_FLIGHT in flight per lane: block -> bucket entry (ONE 8-byte
+// Phase S: reads with one raw block (4 in 5), one per lane and round: block -> bucket entry (ONE 8-byte
 //          gather names the piece, lsq_types.cuh:bucket_rank) -> PieceInfo (ONE 16-byte gather: covered
 //          test, candidate test, cut list) -> route_single -> ONE 32-bit reduction on the signature
-//          counter.  Two dependent gathers and one reduction per read: the kernel is bound by the SM's rate
-//          of scattered L1TEX operations (one lane-operation per cycle, tools/microbench_gather.cu), not by HBM.
-// Phase D: reads with two raw blocks, one per lane and round: the same two gathers for both blocks ->
+//          counter.  Two dependent gathers and one reduction per read: the floor of the kernel is the SM's
+//          rate of scattered L1TEX operations (one lane-operation per cycle, tools/microbench_gather.cu),
+//          not HBM.
+// Phase D: reads with two raw blocks are first listed densely in the warp's shared-memory slice, then
+//          taken one per lane and round: the same two gathers for both blocks (in flight together) ->
 //          route_double (pair signature -> hash; fused or half-kept reads -> single signature).
 // Reads with more blocks, chimeric reads and every read the routing functions decline are listed for
-// lsq_general_kernel.
+// lsq_general_kernel.  Rare lookup cases (crowded bucket, position outside the bucket range) take
+// lookup_cold, out of line.
 // A streamed read set (lsq_set_reads with LSQ_READS_STREAM) is consumed while the copy engine is still
 // delivering it: lane 0 polls the landed-blocks word before the group's blocks are touched.
 // ---------------------------------------------------------------------------------------------
@@ -132,46 +136,58 @@ __global__ void __launch_bounds__(1024) lsq_super_scan_kernel(uint32_t *__restri
 #define LSQ_SCAN_BLOCK 256
 #endif
 #ifndef LSQ_SCAN_MINB
-#define LSQ_SCAN_MINB 4  // resident CTAs per SM
+#define LSQ_SCAN_MINB 4  // resident CTAs per SM (64 registers: no spills)
 #endif
 constexpr int SCAN_BLOCK = LSQ_SCAN_BLOCK;
 constexpr int SCAN_MINB = LSQ_SCAN_MINB;
 constexpr int SCAN_WARPS = SCAN_BLOCK / 32;
 constexpr int SCAN_ITEMS = 4;     // reads per lane
-#ifndef LSQ_SCAN_FLIGHT
-#define LSQ_SCAN_FLIGHT 2
-#endif
-constexpr int SCAN_FLIGHT = LSQ_SCAN_FLIGHT;  // single-block reads whose lookups a lane keeps in flight together
 static_assert(SCAN_ITEMS * 32 == (int)SCAN_GROUP, "a lane owns four consecutive reads of the group");
 
-// Pieces and piece records of N blocks, every stage issued for all of them before any result is consumed
-// (the chain of dependent L2 accesses, not arithmetic, bounds the kernel).  pp = PIECE_NONE: nil block,
-// chromosome without annotation, or a start before the first piece.
-template <int N>
-__device__ __forceinline__ void lookup_batch(const ScanParams &P, const int2 (&b)[N], const uint32_t (&cs)[N],
-                                             const bool (&act)[N], uint32_t (&pp)[N], uint4 (&raw)[N]) {
-    const Tables &T = P.T;
-    int st[N];
-    BlockProbe q[N];
-    uint2 be[N];
-#pragma unroll
-    for (int k = 0; k < N; ++k) st[k] = act[k] ? block_stage_chrom(P, b[k], cs[k], q[k]) : SP_DROP;
-#pragma unroll
-    for (int k = 0; k < N; ++k) be[k] = st[k] == SP_GO ? __ldg(T.bp_bkt + q[k].slot) : make_uint2(0u, 0u);
-#pragma unroll
-    for (int k = 0; k < N; ++k) {
-        pp[k] = PIECE_NONE;
-        if (st[k] == SP_GO) st[k] = block_stage_piece(T, q[k], be[k], pp[k]);
+// The piece of position x on file chromosome c by the full search (find_piece): positions below zero or past the
+// last bucket, crowded sub-buckets.  Out of line: the hot loop stays small.
+__device__ __noinline__ uint32_t lookup_cold(const ScanParams &P, uint32_t c, int32_t x) {
+    PieceInfo pi;
+    const uint32_t p = find_piece(P.T, __ldg(P.chrom_remap + c), x, pi);
+    return p == 0xFFFFFFFFu ? PIECE_NONE : p;
+}
+
+// The hot lookup, in two stages so that a lane can have the bucket entries of two blocks in flight together.
+// Stage 1: what to load.  how = 0: no piece can hold the block (nil block, chromosome without annotation);
+// 1: bucket entry at `slot`; 2: lookup_cold.
+struct Probe {
+    uint32_t slot, lo, how;
+};
+__device__ __forceinline__ Probe probe_of(const ScanParams &P, int2 b, uint4 cm) {
+    Probe q;
+    const uint32_t bk = (uint32_t)b.x >> P.T.bp_shift;
+    q.lo = cm.x;
+    q.slot = cm.z + bk;
+    q.how = (!(b.x < b.y) || cm.x == cm.y) ? 0u : ((b.x < 0 || bk >= cm.w) ? 2u : 1u);
+    return q;
+}
+// Stage 2: the piece from the bucket entry e (a crowded bucket names its sub-bucket: one more 8-byte load).
+__device__ __forceinline__ uint32_t piece_of(const ScanParams &P, int2 b, uint32_t c, Probe q, uint2 e) {
+    if (q.how != 1u) return q.how == 0u ? PIECE_NONE : lookup_cold(P, c, b.x);
+    uint32_t sh = P.T.bp_shift, xo = (uint32_t)b.x & ((1u << sh) - 1u);
+    if (bucket_many(e.y)) {
+        sh = bucket_sub_shift(sh);
+        e = __ldg(P.T.bp_sub + (e.y & 0x1FFFFFFFu) + (xo >> sh));
+        xo &= (1u << sh) - 1u;
+        if (bucket_many(e.y)) return lookup_cold(P, c, b.x);
     }
-#pragma unroll
-    for (int k = 0; k < N; ++k)  // crowded buckets (1 in 8 blocks): one more entry
-        if (st[k] == SP_SUB) be[k] = __ldg(T.bp_sub + q[k].slot);
-#pragma unroll
-    for (int k = 0; k < N; ++k) {
-        if (st[k] == SP_SUB) st[k] = block_stage_sub(T, q[k], be[k], pp[k]);
-        if (st[k] == SP_DEFER) pp[k] = block_stage_defer(P, q[k]) & PIECE_NONE;  // searched
-        raw[k] = pp[k] != PIECE_NONE ? __ldg(reinterpret_cast<const uint4 *>(T.pinfo + pp[k])) : make_uint4(0u, 0u, 0u, 0u);
+    const uint32_t n = e.x + bucket_rank(sh, e.y, xo);
+    return n != q.lo ? n - 1u : PIECE_NONE;
+}
+
+// Block i of the read set: the compact layout (start i32 + length u8) without any format test.
+template <bool COMPACT>
+__device__ __forceinline__ int2 scan_block(const ScanParams &P, uint32_t i) {
+    if (COMPACT) {
+        const int32_t s = __ldcs(P.blk_start + i);
+        return make_int2(s, s + (int32_t)__ldcs(P.blk_len8 + i));
     }
+    return load_block_stream(P, i);
 }
 
 // Tally of a two-block signature: open addressing, linear probing; the slot's key and count share one
@@ -193,16 +209,27 @@ __device__ __forceinline__ bool sig_hash_add(const ScanParams &P, uint64_t key, 
     return false;
 }
 
-__global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MINB) lsq_scan_kernel(ScanParams P) {
+// COMPACT: the read set is in the compact layout throughout (blk_cnt + index, read_cs8, blk_start + blk_len8) --
+// what the host front end and the benchmark produce; the other instantiation takes any mix of layouts.
+template <bool COMPACT>
+__global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MINB) lsq_scan_kernel(const __grid_constant__ ScanParams P) {
+    __shared__ uint2 s_dbl[SCAN_WARPS][SCAN_GROUP];  // per warp: its two-block reads {first block, chromosome id | group-local index << 24}
+    __shared__ uint2 s_gen[SCAN_WARPS][SCAN_GROUP];  // per warp: the group's reads for the general kernel {read, first block}
+    __shared__ uint32_t s_ngen[SCAN_WARPS];
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
     const uint64_t n_groups = (P.n_reads + SCAN_GROUP - 1) / SCAN_GROUP;
     uint32_t c_single = 0, c_pair = 0, c_general = 0, c_full = 0;  // statistics, flushed once per warp
+    const PieceInfo *const pinfo = P.T.pinfo;
+    const bool no_single = (P.flags & SCAN_NO_SINGLE_SIG) != 0u;
 
+    // general reads are parked in the warp's shared-memory slice (a shared atomic returns in ~30 cycles); the warp
+    // reserves their slots in the global list once per group -- a returning global atomic per read on the one list
+    // counter costs a full L2 round trip inside divergent code
     auto to_general = [&](uint64_t r, uint32_t base) {
-        const uint32_t slot = atomicAdd(P.gen_n, 1u);
-        if (slot < P.gen_cap) P.gen_list[slot] = make_uint2((uint32_t)r, base);
-        ++c_general;
+        s_gen[warp][atomicAdd(&s_ngen[warp], 1u)] = make_uint2((uint32_t)r, base);
     };
+    if (lane == 0) s_ngen[warp] = 0u;
+    __syncwarp();
     auto tally = [&](uint32_t rt, uint32_t sig, uint64_t key, uint32_t total, uint64_t r, uint32_t base) {
         if (rt == RT_SINGLE) {
             atomicAdd(P.sig_cnt + sig, 1u);
@@ -224,10 +251,13 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MINB) lsq_scan_kernel(ScanPar
         const uint64_t g0 = g * SCAN_GROUP, g1 = min(g0 + (uint64_t)SCAN_GROUP, P.n_reads);
         const uint64_t r0 = g0 + 4u * lane;
         // ---- phase A --------------------------------------------------------------------------
-        uint32_t rbase[SCAN_ITEMS], rn[SCAN_ITEMS], rcs[SCAN_ITEMS];  // first block, raw blocks, ids
-        uint32_t g_end;  // one past the group's last block (warp-uniform)
-        if (P.blk_cnt != nullptr) {
-            uint32_t c4 = 0;
+        uint32_t c4 = 0, v4 = 0;  // block counts and one-byte ids of my four reads (compact form)
+        uint32_t o;               // first block of my first read
+        uint32_t g_end;           // one past the group's last block (warp-uniform)
+        uint32_t dmask = 0;       // bit 8k+7: my read k has two raw blocks and is not chimeric
+        const bool compact_cnt = COMPACT || P.blk_cnt != nullptr, compact_cs = COMPACT || P.read_cs8 != nullptr;
+        if (compact_cs && r0 < g1) v4 = __ldcs(reinterpret_cast<const uint32_t *>(P.read_cs8 + r0));
+        if (compact_cnt) {
             if (r0 < g1) {
                 c4 = __ldcs(reinterpret_cast<const uint32_t *>(P.blk_cnt + r0));
                 if (r0 + 4 > g1) c4 &= 0xFFFFFFFFu >> (8u * (uint32_t)(r0 + 4 - g1));
@@ -241,32 +271,14 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MINB) lsq_scan_kernel(ScanPar
             }
             const uint32_t gbase = __ldg(P.sup_base + (g / SCAN_SUPER)) + __ldg(P.grp_base + g);
             g_end = gbase + __shfl_sync(0xFFFFFFFFu, incl, 31);
-            uint32_t o = gbase + incl - mine;
-#pragma unroll
-            for (int k = 0; k < SCAN_ITEMS; ++k) {
-                rn[k] = (c4 >> (8 * k)) & 0xFFu;
-                rbase[k] = o;
-                o += rn[k];
+            o = gbase + incl - mine;
+            if (compact_cs) {  // bytes of c4 equal to 2 (exact zero-byte test on c4 ^ 0x02020202), not chimeric
+                const uint32_t t = c4 ^ 0x02020202u;
+                dmask = ~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t | 0x7F7F7F7Fu) & ~v4 & 0x80808080u;
             }
         } else {
-#pragma unroll
-            for (int k = 0; k < SCAN_ITEMS; ++k) {
-                rbase[k] = 0u;
-                rn[k] = 0u;
-                if (r0 + k < g1) {
-                    rbase[k] = __ldcs(P.blk_off + r0 + k);
-                    rn[k] = __ldcs(P.blk_off + r0 + k + 1) - rbase[k];
-                }
-            }
+            o = r0 < g1 ? __ldcs(P.blk_off + r0) : 0u;
             g_end = __ldg(P.blk_off + g1);
-        }
-        if (P.read_cs8 != nullptr) {
-            const uint32_t v4 = r0 < g1 ? __ldcs(reinterpret_cast<const uint32_t *>(P.read_cs8 + r0)) : 0u;
-#pragma unroll
-            for (int k = 0; k < SCAN_ITEMS; ++k) rcs[k] = expand_cs8((v4 >> (8 * k)) & 0xFFu);
-        } else {
-#pragma unroll
-            for (int k = 0; k < SCAN_ITEMS; ++k) rcs[k] = r0 + k < g1 ? __ldcs(P.read_cs + r0 + k) : 0u;
         }
         if (P.progress != nullptr) {
             // streamed read set: the copy engine is still filling the block arrays; wait until the group's
@@ -281,61 +293,115 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MINB) lsq_scan_kernel(ScanPar
             }
             __syncwarp();
         }
-        // ---- phase S --------------------------------------------------------------------------
-        uint32_t dmask = 0;  // my reads with two raw blocks
+        // where my two-block reads go in the warp's list: known before the loop when both per-read arrays are compact
+        uint32_t nd = __popc(dmask), n_dbl = 0, dpos = 0;
+        if (compact_cnt && compact_cs) {
+            uint32_t incl = nd;
 #pragma unroll
-        for (int k = 0; k < SCAN_ITEMS; ++k) {
-            const bool plain = !(rcs[k] & 0x80000000u);
-            if (rn[k] == 2u && plain) dmask |= 1u << k;
-            else if (rn[k] > 2u || (rn[k] != 0u && !plain)) to_general(r0 + k, rbase[k]);  // three and more blocks, chimeric reads
+            for (uint32_t d = 1; d < 32u; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            n_dbl = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            dpos = incl - nd;
         }
-#pragma unroll
-        for (int h = 0; h < SCAN_ITEMS; h += SCAN_FLIGHT) {
-            int2 b[SCAN_FLIGHT];
-            bool act[SCAN_FLIGHT];
-            uint32_t cs[SCAN_FLIGHT], pp[SCAN_FLIGHT];
-            uint4 raw[SCAN_FLIGHT];
-#pragma unroll
-            for (int u = 0; u < SCAN_FLIGHT; ++u) {
-                act[u] = rn[h + u] == 1u && !(rcs[h + u] & 0x80000000u);
-                cs[u] = rcs[h + u];
-                b[u] = act[u] ? load_block_stream(P, rbase[h + u]) : make_int2(0, 0);
+        // ---- phase S --------------------------------------------------------------------------
+#pragma unroll 1
+        for (uint32_t k = 0; k < (uint32_t)SCAN_ITEMS; ++k) {
+            const uint64_t r = r0 + k;
+            uint32_t rn, c;
+            bool plain;
+            if (compact_cnt) rn = (c4 >> (8u * k)) & 0xFFu;
+            else rn = (r < g1 ? __ldcs(P.blk_off + r + 1) : o) - o;
+            if (compact_cs) {
+                const uint32_t v = v4 >> (8u * k);
+                c = v & 0x3Fu;
+                plain = !(v & 0x80u);
+            } else {
+                const uint32_t cs = r < g1 ? __ldcs(P.read_cs + r) : 0u;
+                c = cs & 0xFFFFu;
+                plain = !(cs & 0x80000000u);
             }
-            lookup_batch<SCAN_FLIGHT>(P, b, cs, act, pp, raw);
-#pragma unroll
-            for (int u = 0; u < SCAN_FLIGHT; ++u) {
-                if (!act[u] || pp[u] == PIECE_NONE || (int32_t)raw[u].y < b[u].y || !(raw[u].z & PIECE_CAND)) continue;
-                uint32_t sig;
-                const uint32_t total = (uint32_t)(b[u].y - b[u].x);
-                const uint32_t rt = (P.flags & SCAN_NO_SINGLE_SIG) ? RT_GENERAL : route_single(P.T, b[u], raw[u], sig);
-                tally(rt, sig, 0ull, total, r0 + h + u, rbase[h + u]);
+            const uint32_t base = o;
+            o += rn;
+            if (rn != 1u || !plain) {
+                if (rn == 2u && plain) {
+                    const uint2 d = make_uint2(base, c | ((4u * lane + k) << 24));
+                    if (compact_cnt && compact_cs) {
+                        s_dbl[warp][dpos++] = d;
+                    } else {  // mixed layouts: through the general-list slice, sorted out below
+                        s_dbl[warp][4u * lane + nd] = d;
+                        ++nd;
+                    }
+                } else if (rn != 0u) {
+                    to_general(r, base);  // three and more blocks, chimeric reads
+                }
+                continue;
             }
+            // the lookup chain of one single-block read
+            const int2 b = scan_block<COMPACT>(P, base);
+            const Probe q = probe_of(P, b, __ldg(P.file_meta + c));
+            const uint2 e = q.how == 1u ? __ldg(P.T.bp_bkt + q.slot) : make_uint2(0u, 0u);
+            const uint32_t p = piece_of(P, b, c, q, e);
+            if (p == PIECE_NONE) continue;
+            const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(pinfo + p));
+            if ((int32_t)raw.y < b.y || !(raw.z & PIECE_CAND)) continue;  // not inside a covered region / candidate of no event
+            uint32_t sig = 0;
+            const uint32_t rt = no_single ? RT_GENERAL : route_single(P.T, b, raw, sig);
+            tally(rt, sig, 0ull, (uint32_t)(b.y - b.x), r, base);
         }
         // ---- phase D --------------------------------------------------------------------------
-#pragma unroll 1
-        while (__any_sync(0xFFFFFFFFu, dmask != 0u)) {
-            const bool have = dmask != 0u;
-            const uint32_t k = have ? (uint32_t)__ffs((int)dmask) - 1u : 0u;
-            dmask &= dmask - 1u;
-            const uint32_t base = k == 0u ? rbase[0] : (k == 1u ? rbase[1] : (k == 2u ? rbase[2] : rbase[3]));
-            const uint32_t cs0 = k == 0u ? rcs[0] : (k == 1u ? rcs[1] : (k == 2u ? rcs[2] : rcs[3]));
-            int2 b[2];
-            bool act[2] = {have, have};
-            uint32_t cs2[2] = {cs0, cs0};
-            uint32_t pp[2];
-            uint4 raw[2];
-            b[0] = have ? load_block_stream(P, base) : make_int2(0, 0);
-            b[1] = have ? load_block_stream(P, base + 1u) : make_int2(0, 0);
-            lookup_batch<2>(P, b, cs2, act, pp, raw);
-            if (have) {
-                const bool kept0 = pp[0] != PIECE_NONE && (int32_t)raw[0].y >= b[0].y;
-                const bool kept1 = pp[1] != PIECE_NONE && (int32_t)raw[1].y >= b[1].y;
-                uint32_t sig, total;
-                uint64_t key;
-                const uint32_t rt = route_double(P, b[0], b[1], pp[0], raw[0], kept0, pp[1], raw[1], kept1, sig, key, total);
-                tally(rt, sig, key, total, r0 + k, base);
+        if (!(compact_cnt && compact_cs)) {  // mixed layouts: compact the sparse list (every lane wrote at 4 * lane)
+            uint32_t incl = nd;
+#pragma unroll
+            for (uint32_t d = 1; d < 32u; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= d) incl += t;
             }
+            n_dbl = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            uint2 mine[SCAN_ITEMS];
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < SCAN_ITEMS; ++j) mine[j] = s_dbl[warp][4u * lane + j];
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < SCAN_ITEMS; ++j)
+                if ((uint32_t)j < nd) s_dbl[warp][incl - nd + j] = mine[j];
         }
+        __syncwarp();
+#pragma unroll 1
+        for (uint32_t i = lane; i < n_dbl; i += 32u) {
+            const uint2 d = s_dbl[warp][i];
+            const uint32_t base = d.x, c = d.y & 0xFFFFu;
+            const uint64_t r = g0 + (d.y >> 24);
+            const int2 b0 = scan_block<COMPACT>(P, base), b1 = scan_block<COMPACT>(P, base + 1u);
+            const uint4 cm = __ldg(P.file_meta + c);
+            const Probe q0 = probe_of(P, b0, cm), q1 = probe_of(P, b1, cm);
+            const uint2 e0 = q0.how == 1u ? __ldg(P.T.bp_bkt + q0.slot) : make_uint2(0u, 0u);
+            const uint2 e1 = q1.how == 1u ? __ldg(P.T.bp_bkt + q1.slot) : make_uint2(0u, 0u);
+            const uint32_t p0 = piece_of(P, b0, c, q0, e0), p1 = piece_of(P, b1, c, q1, e1);
+            const uint4 raw0 = p0 != PIECE_NONE ? __ldg(reinterpret_cast<const uint4 *>(pinfo + p0)) : make_uint4(0u, 0u, 0u, 0u);
+            const uint4 raw1 = p1 != PIECE_NONE ? __ldg(reinterpret_cast<const uint4 *>(pinfo + p1)) : make_uint4(0u, 0u, 0u, 0u);
+            const bool kept0 = p0 != PIECE_NONE && (int32_t)raw0.y >= b0.y, kept1 = p1 != PIECE_NONE && (int32_t)raw1.y >= b1.y;
+            uint32_t sig, total;
+            uint64_t key;
+            const uint32_t rt = route_double(P, b0, b1, p0, raw0, kept0, p1, raw1, kept1, sig, key, total);
+            tally(rt, sig, key, total, r, base);
+        }
+        // ---- flush the group's general reads ------------------------------------------------------
+        __syncwarp();
+        const uint32_t n_gen = s_ngen[warp];
+        if (n_gen != 0u) {  // warp-uniform
+            uint32_t slot0 = 0;
+            if (lane == 0) slot0 = atomicAdd(P.gen_n, n_gen);
+            slot0 = __shfl_sync(0xFFFFFFFFu, slot0, 0);
+            for (uint32_t i = lane; i < n_gen; i += 32u)
+                if (slot0 + i < P.gen_cap) P.gen_list[slot0 + i] = s_gen[warp][i];
+            c_general += lane == 0 ? n_gen : 0u;
+            __syncwarp();
+            if (lane == 0) s_ngen[warp] = 0u;
+        }
+        __syncwarp();  // the lists are rewritten by the next group
     }
     c_single = __reduce_add_sync(0xFFFFFFFFu, c_single);
     c_pair = __reduce_add_sync(0xFFFFFFFFu, c_pair);
@@ -346,6 +412,113 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MINB) lsq_scan_kernel(ScanPar
         if (c_pair) atomicAdd(P.counters + CTR_PAIR_SIG, (unsigned long long)c_pair);
         if (c_general) atomicAdd(P.counters + CTR_GENERAL, (unsigned long long)c_general);
         if (c_full) atomicAdd(P.counters + CTR_HASH_FULL, (unsigned long long)c_full);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Route kernel (multi-GPU): one pass over the local slice of the read set; every read is appended to the
+// outbox of each rank that owns a candidate event at the piece of any of its blocks.  Same group / lane
+// layout and the same two-gather lookup as the scan kernel, plus one 8-byte gather of the piece's owner
+// mask.  Appends are aggregated per warp: one 64-bit reduction pair per (round, destination) reserves the
+// slots of all 32 lanes.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MINB) lsq_route_kernel(const __grid_constant__ ScanParams P,
+                                                                          const __grid_constant__ RouteParams R) {
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint64_t n_groups = (P.n_reads + SCAN_GROUP - 1) / SCAN_GROUP;
+    const PieceInfo *const pinfo = P.T.pinfo;
+#pragma unroll 1
+    for (uint64_t g = (uint64_t)blockIdx.x * SCAN_WARPS + warp; g < n_groups; g += (uint64_t)gridDim.x * SCAN_WARPS) {
+        const uint64_t g0 = g * SCAN_GROUP, g1 = min(g0 + (uint64_t)SCAN_GROUP, P.n_reads);
+        const uint64_t r0 = g0 + 4u * lane;
+        uint32_t c4 = 0, v4 = 0, o;
+        const bool compact_cnt = P.blk_cnt != nullptr, compact_cs = P.read_cs8 != nullptr;
+        if (compact_cnt) {
+            if (r0 < g1) {
+                c4 = __ldcs(reinterpret_cast<const uint32_t *>(P.blk_cnt + r0));
+                if (r0 + 4 > g1) c4 &= 0xFFFFFFFFu >> (8u * (uint32_t)(r0 + 4 - g1));
+            }
+            const uint32_t mine = __vsadu4(c4, 0u);
+            uint32_t incl = mine;
+#pragma unroll
+            for (uint32_t d = 1; d < 32u; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            o = __ldg(P.sup_base + (g / SCAN_SUPER)) + __ldg(P.grp_base + g) + incl - mine;
+        } else {
+            o = r0 < g1 ? __ldcs(P.blk_off + r0) : 0u;
+        }
+        if (compact_cs && r0 < g1) v4 = __ldcs(reinterpret_cast<const uint32_t *>(P.read_cs8 + r0));
+#pragma unroll 1
+        for (uint32_t k = 0; k < (uint32_t)SCAN_ITEMS; ++k) {
+            const uint64_t r = r0 + k;
+            uint32_t rn, cs;
+            if (compact_cnt) rn = (c4 >> (8u * k)) & 0xFFu;
+            else rn = (r < g1 ? __ldcs(P.blk_off + r + 1) : o) - o;
+            const uint32_t cs8 = (v4 >> (8u * k)) & 0xFFu;
+            if (compact_cs) cs = expand_cs8(cs8);
+            else cs = r < g1 ? __ldcs(P.read_cs + r) : 0u;
+            const uint32_t base = o;
+            o += rn;
+            // owners of the pieces of the read's blocks
+            unsigned long long mask = 0ull;
+#pragma unroll 1
+            for (uint32_t j = 0; j < rn; ++j) {
+                const int2 b = load_block_stream(P, base + j);
+                const uint32_t c = ((cs & 0x80000000u) ? __ldg(P.blk_cs + base + j) : cs) & 0xFFFFu;
+                const Probe q = probe_of(P, b, __ldg(P.file_meta + c));
+                const uint2 e = q.how == 1u ? __ldg(P.T.bp_bkt + q.slot) : make_uint2(0u, 0u);
+                const uint32_t p = piece_of(P, b, c, q, e);
+                if (p != PIECE_NONE && (__ldg(&pinfo[p].sigw) & PIECE_CAND)) mask |= __ldg(R.owner + p);
+            }
+            // append to every destination present in the warp
+            unsigned long long any = mask;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) any |= __shfl_xor_sync(0xFFFFFFFFu, any, d);
+#pragma unroll 1
+            while (any) {
+                const uint32_t d = (uint32_t)__ffsll((long long)any) - 1u;
+                any &= any - 1ull;
+                const bool sel = (mask >> d) & 1ull;
+                const unsigned bal = __ballot_sync(0xFFFFFFFFu, sel);
+                const uint32_t my_blk = sel ? rn : 0u;
+                uint32_t incl = my_blk;
+#pragma unroll
+                for (uint32_t s = 1; s < 32u; s <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, s);
+                    if (lane >= s) incl += t;
+                }
+                const uint32_t tot_blk = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                unsigned long long rb = 0ull, bb = 0ull;
+                if (lane == 0) {
+                    rb = atomicAdd(R.cursor + 2u * d, (unsigned long long)__popc(bal));
+                    bb = atomicAdd(R.cursor + 2u * d + 1u, (unsigned long long)tot_blk);
+                }
+                rb = __shfl_sync(0xFFFFFFFFu, rb, 0);
+                bb = __shfl_sync(0xFFFFFFFFu, bb, 0);
+                if (!sel) continue;
+                const RouteBox &B = R.box[d];
+                const size_t ri = (size_t)rb + __popc(bal & ((1u << lane) - 1u));
+                size_t bi = (size_t)bb + (incl - my_blk);
+                B.blk_cnt[ri] = (uint8_t)rn;
+                if (B.read_cs8) B.read_cs8[ri] = (uint8_t)cs8;
+                else B.read_cs[ri] = cs;
+                B.line_num[ri] = P.line_num ? __ldg(P.line_num + r) : R.line_base + (uint32_t)r + 1u;
+#pragma unroll 1
+                for (uint32_t j = 0; j < rn; ++j, ++bi) {
+                    const int2 b = load_block(P, base + j);
+                    if (B.blk_start) {
+                        B.blk_start[bi] = b.x;
+                        if (B.blk_len8) B.blk_len8[bi] = (uint8_t)(b.y - b.x);
+                        else B.blk_len[bi] = (uint16_t)(b.y - b.x);
+                    } else {
+                        B.blk[bi] = b;
+                    }
+                    if (B.blk_cs) B.blk_cs[bi] = (cs & 0x80000000u) ? __ldg(P.blk_cs + base + j) : cs;
+                }
+            }
+        }
     }
 }
 
@@ -379,7 +552,7 @@ __device__ __forceinline__ void bump_class(const ScanParams &P, const EvHdr &h, 
 // ones).  A slot that was hit takes the walk of read.h:204-274 once, on its representative read, for
 // every candidate event of its piece; events matched fully receive the slot's reads and bases.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) lsq_expand_kernel(ScanParams P) {
+__global__ void __launch_bounds__(128) lsq_expand_kernel(const __grid_constant__ ScanParams P) {
     const Tables &T = P.T;
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t n_hash = (uint64_t)P.hash_mask + 1u;
@@ -412,7 +585,7 @@ __global__ void __launch_bounds__(128) lsq_expand_kernel(ScanParams P) {
 // its ext entry) and walked against every candidate event of its piece: tie-break (count.cpp:429-432),
 // Read_single::build, compatibility, IEEE validity rule.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) lsq_general_kernel(ScanParams P) {
+__global__ void __launch_bounds__(128) lsq_general_kernel(const __grid_constant__ ScanParams P) {
     const Tables &T = P.T;
     const uint32_t n = min(*P.gen_n, P.gen_cap);
 #pragma unroll 1

@@ -183,6 +183,32 @@ struct ScanParams {
 };
 constexpr uint32_t SCAN_NO_SINGLE_SIG = 1u, SCAN_NO_PAIR_SIG = 2u;  // debugging: send those reads to lsq_general_kernel
 
+// Read bucketing per gene-range shard (count.cpp:202-215: every process of the reference reads the whole file and
+// keeps what its range covers).  The router runs on the tables of the WHOLE selection; owner[p] has bit d set when
+// rank d owns an event with a stab entry at piece p.  A read is sent to every rank owning a candidate event of ANY
+// of its blocks' pieces -- a superset of the ranks whose events it can count for (its first KEPT block decides
+// that), so each rank's tables, built with the covered regions of the whole selection, give the same tallies as
+// the single-GPU run.  Outboxes keep the read set's own layout (compact or wide).
+constexpr uint32_t ROUTE_MAX_RANKS = 16;  // = LSQ_MAX_RANKS of the public header
+struct RouteBox {
+    uint8_t *blk_cnt;      // [cap_reads]
+    uint8_t *read_cs8;     // compact ids ...
+    uint32_t *read_cs;     // ... or wide ids
+    uint32_t *line_num;    // [cap_reads] the read's line number in the whole file (its name, count.cpp:293-295)
+    int32_t *blk_start;    // compact blocks: start + length (u8 or u16) ...
+    uint8_t *blk_len8;
+    uint16_t *blk_len;
+    int2 *blk;             // ... or wide blocks
+    uint32_t *blk_cs;      // per-block ids (only when the read set has chimeric reads)
+};
+struct RouteParams {
+    uint32_t n_ranks;
+    uint32_t line_base;               // line number of local read 0 minus 1 when the set carries no line numbers
+    const unsigned long long *owner;  // [n_pieces]
+    unsigned long long *cursor;       // [2 * n_ranks] reads, blocks appended per destination
+    RouteBox box[ROUTE_MAX_RANKS];
+};
+
 struct SolveParams {
     Tables T;
     uint32_t M;

@@ -27,13 +27,14 @@ def gather_rows(local, root=0):
     use_cuda = dist.get_backend() == "nccl"
     dev = torch.device("cuda", torch.cuda.current_device()) if use_cuda else torch.device("cpu")
     a = np.ascontiguousarray(local)
-    flat = a.reshape(a.shape[0], -1) if a.ndim > 1 else a.reshape(-1, 1)
-    width = flat.shape[1]
+    width = int(np.prod(a.shape[1:])) if a.ndim > 1 else 1  # explicit: an empty shard has zero rows
+    flat = a.reshape(a.shape[0], width)
     sizes = torch.zeros(world, dtype=torch.int64, device=dev)
     sizes[rank] = flat.shape[0]
     dist.all_reduce(sizes)
     maxn = int(sizes.max().item())
-    raw = torch.from_numpy(flat.view(np.uint8).reshape(flat.shape[0], -1).copy())
+    nbytes = width * a.dtype.itemsize  # explicit: a rank whose shard is empty has zero rows
+    raw = torch.from_numpy(np.ascontiguousarray(flat).view(np.uint8).reshape(flat.shape[0], nbytes).copy())
     pad = torch.zeros((maxn, raw.shape[1]), dtype=torch.uint8)
     pad[: raw.shape[0]] = raw
     pad = pad.to(dev)
@@ -42,7 +43,7 @@ def gather_rows(local, root=0):
     if rank != root:
         return None
     parts = [o[: int(sizes[r].item())].cpu().numpy() for r, o in enumerate(out)]
-    cat = np.concatenate(parts, axis=0).view(a.dtype).reshape(-1, width)
+    cat = np.ascontiguousarray(np.concatenate(parts, axis=0)).view(a.dtype).reshape(-1, width)
     if a.ndim == 1:
         return cat.reshape(-1)
     return cat.reshape((-1,) + a.shape[1:])

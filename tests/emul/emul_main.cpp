@@ -127,6 +127,33 @@ static int bucket_selftest(unsigned seed) {
     return 0;
 }
 
+static lsq_event_tables tables_of(const lsqh_annotation &ann) {
+    lsq_event_tables t{};
+    t.n_events = (uint32_t)ann.ev_chrom.size();
+    t.n_forms = (uint32_t)ann.form_name.size();
+    t.n_segments = (uint32_t)ann.seg_start.size();
+    t.n_chroms = (uint32_t)ann.chroms.names.size();
+    t.n_strands = (uint32_t)ann.strands.names.size();
+    t.ev_chrom = ann.ev_chrom.data();
+    t.ev_strand = ann.ev_strand.data();
+    t.ev_gs = ann.ev_gs.data();
+    t.ev_ge = ann.ev_ge.data();
+    t.ev_seg_off = ann.ev_seg_off.data();
+    t.ev_form_off = ann.ev_form_off.data();
+    t.ev_name_off = ann.ev_name_off.data();
+    t.ev_names = ann.ev_names_pool.data();
+    t.seg_start = ann.seg_start.data();
+    t.seg_end = ann.seg_end.data();
+    t.form_seg_off = ann.form_seg_off.data();
+    t.form_seg_idx = ann.form_seg_idx.data();
+    t.cov_off = ann.cov_off.data();
+    t.cov_start = ann.cov_start.data();
+    t.cov_end = ann.cov_end.data();
+    t.chrom_names = ann.chrom_ptrs.data();
+    t.strand_names = ann.strand_ptrs.data();
+    return t;
+}
+
 int main(int argc, char **argv) {
     if (argc < 2) return 2;
     if (std::string(argv[1]) == "bucket-selftest") {
@@ -159,35 +186,75 @@ int main(int argc, char **argv) {
         r.trb = solve ? atof(argv[argi++]) : 0;
         sets.push_back(r);
     }
+    // LSQ_EMUL_SHARDS=P: the multi-GPU data flow, sequentially.  The reads are routed with the tables of the whole
+    // selection (owner mask of every block's piece, as lsq_route_kernel), then every gene-rank shard counts its own
+    // bucket with its own tables; the concatenated tables must equal the unsharded run.
+    uint32_t n_shards = 1;
+    if (const char *e = getenv("LSQ_EMUL_SHARDS")) n_shards = std::max(1, atoi(e));
+    std::vector<lsqh_reads> parsed(sets.size());
+    for (size_t m = 0; m < sets.size(); ++m)
+        if (lsqh::parse_mrf(sets[m].path.c_str(), parsed[m])) {
+            fprintf(stderr, "emul: %s\n", g_err.c_str());
+            return 1;
+        }
+    std::vector<std::vector<uint64_t> > owner_mask(sets.size());  // per read: ranks it is sent to
+    uint64_t n_sel = 0;
+    if (n_shards > 1) {
+        lsqh_annotation full;
+        if (lsqh::load_annotation_fmt(argv[4], form_path.c_str(), argv[6], map_path.c_str(), begin, end, 0, UINT64_MAX, full)) {
+            fprintf(stderr, "emul: %s\n", g_err.c_str());
+            return 1;
+        }
+        n_sel = full.ev_chrom.size();
+        lsq_event_tables ft = tables_of(full);
+        HostTables FH;
+        std::string ferr;
+        if (build_host_tables(&ft, FH, ferr)) return 1;
+        const Tables FT = FH.host_view();
+        std::vector<uint64_t> owner(FH.bp_pos.size() + 1, 0);
+        for (size_t p = 0; p < FH.bp_pos.size(); ++p)
+            for (uint32_t q = FH.stab_off[p]; q < FH.stab_off[p + 1]; ++q) {
+                const uint64_t e = FH.hdr[FH.stab[q].x].out_ev;
+                uint32_t d = 0;
+                while (d + 1 < n_shards && e >= (n_sel * (d + 1)) / n_shards) ++d;
+                owner[p] |= 1ull << d;
+            }
+        std::map<std::string, uint32_t> cid;
+        for (uint32_t i = 0; i < ft.n_chroms; ++i) cid[ft.chrom_names[i]] = i;
+        for (size_t m = 0; m < sets.size(); ++m) {
+            const lsqh_reads &R = parsed[m];
+            const size_t n = R.read_cs.size();
+            owner_mask[m].assign(n, 0);
+            std::vector<uint32_t> remap(std::max<size_t>(R.chroms.names.size(), 1), 0xFFFFFFFFu);
+            for (size_t i = 0; i < R.chroms.names.size(); ++i) {
+                auto it = cid.find(R.chroms.names[i]);
+                if (it != cid.end()) remap[i] = it->second;
+            }
+            std::vector<uint4> fmeta(remap.size(), make_uint4(0u, 0u, 0u, 0u));
+            for (size_t i = 0; i < remap.size(); ++i)
+                if (remap[i] != 0xFFFFFFFFu) fmeta[i] = FH.chrom_meta[remap[i]];
+            ScanParams RP{};
+            RP.T = FT;
+            RP.chrom_remap = remap.data();
+            RP.file_meta = fmeta.data();
+            for (size_t r = 0; r < n; ++r)
+                for (uint32_t j = R.blk_off[r]; j < R.blk_off[r + 1]; ++j) {
+                    const uint32_t cs = (R.read_cs[r] & 0x80000000u) ? R.blk_cs[j] : R.read_cs[r];
+                    const int2 b = make_int2(R.blk[2 * j], R.blk[2 * j + 1]);
+                    const uint32_t p = block_lookup(RP, b, cs) & PIECE_NONE;
+                    if (p != PIECE_NONE && (FT.pinfo[p].sigw & PIECE_CAND)) owner_mask[m][r] |= owner[p];
+                }
+        }
+    }
+    for (uint32_t shard = 0; shard < n_shards; ++shard) {
+    const uint64_t sb = n_shards > 1 ? (n_sel * shard) / n_shards : 0, se = n_shards > 1 ? (n_sel * (shard + 1)) / n_shards : UINT64_MAX;
     lsqh_annotation ann;
-    int rc = lsqh::load_annotation_fmt(argv[4], form_path.c_str(), argv[6], map_path.c_str(), begin, end, 0, UINT64_MAX, ann);
+    int rc = lsqh::load_annotation_fmt(argv[4], form_path.c_str(), argv[6], map_path.c_str(), begin, end, sb, se, ann);
     if (rc) {
         fprintf(stderr, "emul: %s\n", g_err.c_str());
         return 1;
     }
-    lsq_event_tables t{};
-    t.n_events = (uint32_t)ann.ev_chrom.size();
-    t.n_forms = (uint32_t)ann.form_name.size();
-    t.n_segments = (uint32_t)ann.seg_start.size();
-    t.n_chroms = (uint32_t)ann.chroms.names.size();
-    t.n_strands = (uint32_t)ann.strands.names.size();
-    t.ev_chrom = ann.ev_chrom.data();
-    t.ev_strand = ann.ev_strand.data();
-    t.ev_gs = ann.ev_gs.data();
-    t.ev_ge = ann.ev_ge.data();
-    t.ev_seg_off = ann.ev_seg_off.data();
-    t.ev_form_off = ann.ev_form_off.data();
-    t.ev_name_off = ann.ev_name_off.data();
-    t.ev_names = ann.ev_names_pool.data();
-    t.seg_start = ann.seg_start.data();
-    t.seg_end = ann.seg_end.data();
-    t.form_seg_off = ann.form_seg_off.data();
-    t.form_seg_idx = ann.form_seg_idx.data();
-    t.cov_off = ann.cov_off.data();
-    t.cov_start = ann.cov_start.data();
-    t.cov_end = ann.cov_end.data();
-    t.chrom_names = ann.chrom_ptrs.data();
-    t.strand_names = ann.strand_ptrs.data();
+    lsq_event_tables t = tables_of(ann);
     HostTables H;
     std::string err;
     rc = build_host_tables(&t, H, err);
@@ -197,7 +264,7 @@ int main(int argc, char **argv) {
     }
     const Tables T = H.host_view();
     const uint32_t E = H.E, M = (uint32_t)sets.size();
-    if (E == 0) return 0;
+    if (E == 0) continue;
     std::map<std::string, uint32_t> chrom_id;
     for (uint32_t i = 0; i < t.n_chroms; ++i) chrom_id[t.chrom_names[i]] = i;
     std::vector<std::string> ann_strands(ann.strands.names);
@@ -212,12 +279,7 @@ int main(int argc, char **argv) {
         else if (sets[m].type == "SHORT_READ") type = LSQ_READ_SHORT;
         else return 1;
         form_weights(H, type, sets[m].len, Gm[m]);
-        lsqh_reads R;
-        rc = lsqh::parse_mrf(sets[m].path.c_str(), R);
-        if (rc) {
-            fprintf(stderr, "emul: %s\n", g_err.c_str());
-            return 1;
-        }
+        const lsqh_reads &R = parsed[m];
         const size_t n = R.read_cs.size(), nb = R.blk_cs.size();
         std::vector<uint32_t> remap(std::max<size_t>(R.chroms.names.size(), 1), 0xFFFFFFFFu);
         for (size_t i = 0; i < R.chroms.names.size(); ++i) {
@@ -251,6 +313,7 @@ int main(int argc, char **argv) {
         std::vector<uint2> gen_list;
         uint64_t n_single = 0, n_pair = 0;
         for (size_t r = 0; r < n; ++r) {
+            if (n_shards > 1 && !((owner_mask[m][r] >> shard) & 1ull)) continue;  // not in this rank's bucket
             const uint32_t base = R.blk_off[r], nraw = R.blk_off[r + 1] - base;
             uint32_t sig, total;
             uint64_t key;
@@ -412,5 +475,6 @@ int main(int argc, char **argv) {
                        sum_supports > 1E-5 ? ll / sum_supports : 0.0);
         }
     }
+    }  // shards
     return 0;
 }

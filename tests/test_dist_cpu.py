@@ -66,6 +66,26 @@ def test_two_rank_sharding_and_gather(tmp_path):
     assert q.get(timeout=5) is True
 
 
+def test_more_ranks_than_events_gather(tmp_path):
+    """A rank whose shard is empty (world size above the number of selected genes) must still take part in the
+    gather: three ranks, two events."""
+    sys.path.insert(0, ROOT)
+    from lesseq_b200 import build, synth
+    build.build()
+    A = synth.make_annotation(2, 6, n_chroms=1, types=("SE",), exons_per_gene=(3, 3), events_per_gene=(1, 1))
+    A.write(str(tmp_path / "ev.interval"), str(tmp_path / "ev.map"))
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 3, port, str(tmp_path), q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True
+
+
 def test_shard_ranges_partition():
     sys.path.insert(0, ROOT)
     from lesseq_b200.dist import shard_range

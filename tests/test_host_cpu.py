@@ -195,6 +195,42 @@ def test_device_functions_replayed_on_cpu_match_oracle_midscale(emul_bin, oracle
             assert _close(o1, o2, prog == "solve"), (cfg, prog)
 
 
+def test_sharded_replay_with_bucketed_reads_equals_unsharded(emul_bin, tmp_path):
+    """Multi-GPU data flow on the CPU (LSQ_EMUL_SHARDS): reads are routed with the owner masks of the whole
+    selection's pieces (the rule of lsq_route_kernel), each gene-rank shard counts its own bucket with its own
+    tables (covered regions of the whole selection), and the concatenated tables equal the unsharded run byte
+    for byte -- count.cpp:202-215, 319 with SURVEY 8(e)'s caveat."""
+    from lesseq_b200 import synth
+    cases = []
+    for seed in range(7300, 7340):  # adversarial fuzz annotations: overlapping / nested events, chimeric reads
+        case = fuzzgen.make_case(seed)
+        d = tmp_path / ("s%d" % seed)
+        d.mkdir()
+        cases.append(fuzzgen.write_case(case, str(d)))
+    A, R, _ = synth.make_config("C2", n_genes=1500)
+    d = tmp_path / "c2"
+    d.mkdir()
+    fp, mp, rp = str(d / "ev.interval"), str(d / "ev.map"), str(d / "r.mrf")
+    A.write(fp, mp)
+    rd = synth.make_reads(A, 40000, R, 11, device="cpu")
+    synth.reads_to_mrf(rd, rp)
+    args = ["0", "p", str(d / "o_"), "LH_GENE_TXT", fp, "UCSC_GENE2ISOFORM", mp, "0", "10000000", "MRF_SINGLE",
+            "SHORT_READ", str(R), rp]
+    cases.append((args, args + [repr(rd["total_read_bases"])]))
+    n = 0
+    for ca, sa in cases:
+        for prog, a in (("count", ca), ("solve", sa)):
+            rc0, full = _run_emul(emul_bin, prog, a)
+            if rc0 != 0:
+                continue
+            for shards in (2, 3, 8):
+                env = dict(os.environ, LSQ_PRECISION="17", LSQ_EMUL_SHARDS=str(shards))
+                p = subprocess.run([emul_bin, prog] + [str(x) for x in a], env=env, capture_output=True, text=True)
+                assert p.returncode == 0 and p.stdout == full, (a[4], prog, shards)
+                n += 1
+    assert n > 150
+
+
 def test_cli_argument_errors(built_lib, tmp_path):
     """Exit codes of the drop-in programs for malformed command lines (count.cpp:20-38, 95-129)."""
     from lesseq_b200 import api
