@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(1024) lsq_super_scan_kernel(uint32_t *__restri
 // instructions and stays resident in the instruction cache.
 // Phase A: lane l owns reads 4l..4l+3 of the group: ONE 32-bit load brings their four block counts, one
 //          more their chromosome/strand ids; a warp scan of the counts gives every read's first block.
-// Phase S: reads with one raw block (4 in 5), one per lane and round: block -> bucket entry (ONE 8-byte
+// Phase S: reads with one raw block (4 in 5), SCAN_FLIGHT per lane and round: block -> bucket entry (ONE 8-byte
 //          gather names the piece, lsq_types.cuh:bucket_rank) -> PieceInfo (ONE 16-byte gather: covered
 //          test, candidate test, cut list) -> route_single -> ONE 32-bit reduction on the signature
 //          counter.  Two dependent gathers and one reduction per read: the floor of the kernel is the SM's
@@ -136,12 +136,19 @@ __global__ void __launch_bounds__(1024) lsq_super_scan_kernel(uint32_t *__restri
 #define LSQ_SCAN_BLOCK 256
 #endif
 #ifndef LSQ_SCAN_MINB
-#define LSQ_SCAN_MINB 4  // resident CTAs per SM (64 registers: no spills)
+#define LSQ_SCAN_MINB 5  // resident CTAs per SM (the kernel needs 48 registers; measured best of 3..6)
 #endif
 constexpr int SCAN_BLOCK = LSQ_SCAN_BLOCK;
 constexpr int SCAN_MINB = LSQ_SCAN_MINB;
 constexpr int SCAN_WARPS = SCAN_BLOCK / 32;
 constexpr int SCAN_ITEMS = 4;     // reads per lane
+#ifndef LSQ_SCAN_FLIGHT
+#define LSQ_SCAN_FLIGHT 2
+#endif
+constexpr int SCAN_FLIGHT = LSQ_SCAN_FLIGHT;  // single-block reads whose lookup chains a lane keeps in flight together (1, 2 or 4)
+static_assert(SCAN_ITEMS % SCAN_FLIGHT == 0, "rounds of SCAN_FLIGHT reads");
+constexpr uint32_t SCAN_GEN_FLUSH = 64;                          // the warp's general list is flushed when it holds this many reads
+constexpr uint32_t SCAN_GEN_CAP = SCAN_GEN_FLUSH + SCAN_GROUP;   // ... so a whole group always fits
 static_assert(SCAN_ITEMS * 32 == (int)SCAN_GROUP, "a lane owns four consecutive reads of the group");
 
 // The piece of position x on file chromosome c by the full search (find_piece): positions below zero or past the
@@ -183,11 +190,13 @@ __device__ __forceinline__ uint32_t piece_of(const ScanParams &P, int2 b, uint32
 // Block i of the read set: the compact layout (start i32 + length u8) without any format test.
 template <bool COMPACT>
 __device__ __forceinline__ int2 scan_block(const ScanParams &P, uint32_t i) {
+    // cached loads (L1): a lane's four reads, and its neighbours', share 128-byte lines, so three rounds of four hit L1
+    // instead of paying an HBM round trip each (a streaming, evict-first load would)
     if (COMPACT) {
-        const int32_t s = __ldcs(P.blk_start + i);
-        return make_int2(s, s + (int32_t)__ldcs(P.blk_len8 + i));
+        const int32_t s = __ldg(P.blk_start + i);
+        return make_int2(s, s + (int32_t)__ldg(P.blk_len8 + i));
     }
-    return load_block_stream(P, i);
+    return load_block(P, i);
 }
 
 // Tally of a two-block signature: open addressing, linear probing; the slot's key and count share one
@@ -214,7 +223,7 @@ __device__ __forceinline__ bool sig_hash_add(const ScanParams &P, uint64_t key, 
 template <bool COMPACT>
 __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MINB) lsq_scan_kernel(const __grid_constant__ ScanParams P) {
     __shared__ uint2 s_dbl[SCAN_WARPS][SCAN_GROUP];  // per warp: its two-block reads {first block, chromosome id | group-local index << 24}
-    __shared__ uint2 s_gen[SCAN_WARPS][SCAN_GROUP];  // per warp: the group's reads for the general kernel {read, first block}
+    __shared__ uint2 s_gen[SCAN_WARPS][SCAN_GEN_CAP];  // per warp: reads for the general kernel {read, first block}
     __shared__ uint32_t s_ngen[SCAN_WARPS];
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
     const uint64_t n_groups = (P.n_reads + SCAN_GROUP - 1) / SCAN_GROUP;
@@ -223,16 +232,31 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MINB) lsq_scan_kernel(const _
     const bool no_single = (P.flags & SCAN_NO_SINGLE_SIG) != 0u;
 
     // general reads are parked in the warp's shared-memory slice (a shared atomic returns in ~30 cycles); the warp
-    // reserves their slots in the global list once per group -- a returning global atomic per read on the one list
-    // counter costs a full L2 round trip inside divergent code
+    // reserves slots in the global list only when SCAN_GEN_FLUSH reads have gathered -- a returning global atomic on
+    // the one list counter is a full L2 round trip for the whole warp
     auto to_general = [&](uint64_t r, uint32_t base) {
+#ifndef LSQ_EXP_NO_GENERAL  /* timing experiments only */
         s_gen[warp][atomicAdd(&s_ngen[warp], 1u)] = make_uint2((uint32_t)r, base);
+#endif
+    };
+    auto flush_general = [&]() {  // called by the whole warp
+        const uint32_t n_gen = s_ngen[warp];
+        uint32_t slot0 = 0;
+        if (lane == 0) slot0 = atomicAdd(P.gen_n, n_gen);
+        slot0 = __shfl_sync(0xFFFFFFFFu, slot0, 0);
+        for (uint32_t i = lane; i < n_gen; i += 32u)
+            if (slot0 + i < P.gen_cap) P.gen_list[slot0 + i] = s_gen[warp][i];
+        c_general += lane == 0 ? n_gen : 0u;
+        __syncwarp();
+        if (lane == 0) s_ngen[warp] = 0u;
     };
     if (lane == 0) s_ngen[warp] = 0u;
     __syncwarp();
     auto tally = [&](uint32_t rt, uint32_t sig, uint64_t key, uint32_t total, uint64_t r, uint32_t base) {
         if (rt == RT_SINGLE) {
+#ifndef LSQ_EXP_NO_SIG_RED  /* timing experiments only */
             atomicAdd(P.sig_cnt + sig, 1u);
+#endif
             if (total != P.len0) atomicAdd(P.sig_dev + sig, (unsigned long long)(long long)((int)total - (int)P.len0));
             ++c_single;
         } else if (rt == RT_PAIR) {
@@ -306,49 +330,74 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MINB) lsq_scan_kernel(const _
             dpos = incl - nd;
         }
         // ---- phase S --------------------------------------------------------------------------
+        // SCAN_FLIGHT reads per round: their block loads, then their bucket gathers, then their piece-record gathers
+        // are issued together, so a lane has SCAN_FLIGHT dependent chains in flight instead of one
 #pragma unroll 1
-        for (uint32_t k = 0; k < (uint32_t)SCAN_ITEMS; ++k) {
-            const uint64_t r = r0 + k;
-            uint32_t rn, c;
-            bool plain;
-            if (compact_cnt) rn = (c4 >> (8u * k)) & 0xFFu;
-            else rn = (r < g1 ? __ldcs(P.blk_off + r + 1) : o) - o;
-            if (compact_cs) {
-                const uint32_t v = v4 >> (8u * k);
-                c = v & 0x3Fu;
-                plain = !(v & 0x80u);
-            } else {
-                const uint32_t cs = r < g1 ? __ldcs(P.read_cs + r) : 0u;
-                c = cs & 0xFFFFu;
-                plain = !(cs & 0x80000000u);
-            }
-            const uint32_t base = o;
-            o += rn;
-            if (rn != 1u || !plain) {
-                if (rn == 2u && plain) {
-                    const uint2 d = make_uint2(base, c | ((4u * lane + k) << 24));
-                    if (compact_cnt && compact_cs) {
-                        s_dbl[warp][dpos++] = d;
-                    } else {  // mixed layouts: through the general-list slice, sorted out below
-                        s_dbl[warp][4u * lane + nd] = d;
-                        ++nd;
-                    }
-                } else if (rn != 0u) {
-                    to_general(r, base);  // three and more blocks, chimeric reads
+        for (uint32_t k0 = 0; k0 < (uint32_t)SCAN_ITEMS; k0 += SCAN_FLIGHT) {
+            uint32_t base[SCAN_FLIGHT], c[SCAN_FLIGHT];
+            bool act[SCAN_FLIGHT];
+#pragma unroll
+            for (int u = 0; u < SCAN_FLIGHT; ++u) {
+                const uint32_t k = k0 + (uint32_t)u;
+                const uint64_t r = r0 + k;
+                uint32_t rn;
+                bool plain;
+                if (compact_cnt) rn = (c4 >> (8u * k)) & 0xFFu;
+                else rn = (r < g1 ? __ldcs(P.blk_off + r + 1) : o) - o;
+                if (compact_cs) {
+                    const uint32_t v = v4 >> (8u * k);
+                    c[u] = v & 0x3Fu;
+                    plain = !(v & 0x80u);
+                } else {
+                    const uint32_t cs = r < g1 ? __ldcs(P.read_cs + r) : 0u;
+                    c[u] = cs & 0xFFFFu;
+                    plain = !(cs & 0x80000000u);
                 }
-                continue;
+                base[u] = o;
+                o += rn;
+                act[u] = rn == 1u && plain;
+                if (!act[u]) {
+                    if (rn == 2u && plain) {
+                        const uint2 d = make_uint2(base[u], c[u] | ((4u * lane + k) << 24));
+                        if (compact_cnt && compact_cs) {
+                            s_dbl[warp][dpos++] = d;
+                        } else {  // mixed layouts: sparse list, compacted below
+                            s_dbl[warp][4u * lane + nd] = d;
+                            ++nd;
+                        }
+                    } else if (rn != 0u) {
+                        to_general(r, base[u]);  // three and more blocks, chimeric reads
+                    }
+                }
             }
-            // the lookup chain of one single-block read
-            const int2 b = scan_block<COMPACT>(P, base);
-            const Probe q = probe_of(P, b, __ldg(P.file_meta + c));
-            const uint2 e = q.how == 1u ? __ldg(P.T.bp_bkt + q.slot) : make_uint2(0u, 0u);
-            const uint32_t p = piece_of(P, b, c, q, e);
-            if (p == PIECE_NONE) continue;
-            const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(pinfo + p));
-            if ((int32_t)raw.y < b.y || !(raw.z & PIECE_CAND)) continue;  // not inside a covered region / candidate of no event
-            uint32_t sig = 0;
-            const uint32_t rt = no_single ? RT_GENERAL : route_single(P.T, b, raw, sig);
-            tally(rt, sig, 0ull, (uint32_t)(b.y - b.x), r, base);
+            int2 b[SCAN_FLIGHT];
+            Probe q[SCAN_FLIGHT];
+            uint2 e[SCAN_FLIGHT];
+            uint32_t p[SCAN_FLIGHT];
+            uint4 raw[SCAN_FLIGHT];
+#pragma unroll
+            for (int u = 0; u < SCAN_FLIGHT; ++u) b[u] = act[u] ? scan_block<COMPACT>(P, base[u]) : make_int2(0, 0);
+#pragma unroll
+            for (int u = 0; u < SCAN_FLIGHT; ++u) q[u] = probe_of(P, b[u], __ldg(P.file_meta + c[u]));
+#pragma unroll
+            for (int u = 0; u < SCAN_FLIGHT; ++u) e[u] = q[u].how == 1u ? __ldg(P.T.bp_bkt + q[u].slot) : make_uint2(0u, 0u);
+#pragma unroll
+            for (int u = 0; u < SCAN_FLIGHT; ++u) {
+                p[u] = piece_of(P, b[u], c[u], q[u], e[u]);
+#ifdef LSQ_EXP_NO_PINFO  /* timing experiments only */
+                if (p[u] != PIECE_NONE) ++c_full;
+                p[u] = PIECE_NONE;
+#endif
+                raw[u] = p[u] != PIECE_NONE ? __ldg(reinterpret_cast<const uint4 *>(pinfo + p[u])) : make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int u = 0; u < SCAN_FLIGHT; ++u) {
+                // kept: inside a covered region; candidate of some event
+                if (p[u] == PIECE_NONE || (int32_t)raw[u].y < b[u].y || !(raw[u].z & PIECE_CAND)) continue;
+                uint32_t sig = 0;
+                const uint32_t rt = no_single ? RT_GENERAL : route_single(P.T, b[u], raw[u], sig);
+                tally(rt, sig, 0ull, (uint32_t)(b[u].y - b[u].x), r0 + k0 + (uint32_t)u, base[u]);
+            }
         }
         // ---- phase D --------------------------------------------------------------------------
         if (!(compact_cnt && compact_cs)) {  // mixed layouts: compact the sparse list (every lane wrote at 4 * lane)
@@ -388,21 +437,13 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MINB) lsq_scan_kernel(const _
             const uint32_t rt = route_double(P, b0, b1, p0, raw0, kept0, p1, raw1, kept1, sig, key, total);
             tally(rt, sig, key, total, r, base);
         }
-        // ---- flush the group's general reads ------------------------------------------------------
+        // ---- flush the warp's general reads when enough have gathered --------------------------------
         __syncwarp();
-        const uint32_t n_gen = s_ngen[warp];
-        if (n_gen != 0u) {  // warp-uniform
-            uint32_t slot0 = 0;
-            if (lane == 0) slot0 = atomicAdd(P.gen_n, n_gen);
-            slot0 = __shfl_sync(0xFFFFFFFFu, slot0, 0);
-            for (uint32_t i = lane; i < n_gen; i += 32u)
-                if (slot0 + i < P.gen_cap) P.gen_list[slot0 + i] = s_gen[warp][i];
-            c_general += lane == 0 ? n_gen : 0u;
-            __syncwarp();
-            if (lane == 0) s_ngen[warp] = 0u;
-        }
+        if (s_ngen[warp] >= SCAN_GEN_FLUSH) flush_general();  // warp-uniform
         __syncwarp();  // the lists are rewritten by the next group
     }
+    __syncwarp();
+    if (s_ngen[warp] != 0u) flush_general();
     c_single = __reduce_add_sync(0xFFFFFFFFu, c_single);
     c_pair = __reduce_add_sync(0xFFFFFFFFu, c_pair);
     c_general = __reduce_add_sync(0xFFFFFFFFu, c_general);
