@@ -14,8 +14,10 @@ scan (load filter + candidate lookup + signature tally) -> expand -> general -> 
   cpu_baseline : the reference's own count + solve binaries (oracle/_ref) on a bounded text sample
 `--impl reference` times the reference binaries on all host cores (its own scale-out recipe:
 one process per disjoint gene range, each reading the whole read file).
-Multi-GPU: one process per GPU (torchrun), events sharded by gene rank, reads bucketed per shard,
-no collective inside the loop, one gather of results to rank 0 per step; scaling is weak.
+Multi-GPU (BASELINE config 3): one process per GPU (torchrun); ONE read set of fixed size (1 B reads) over all ranks,
+events sharded by gene rank; every step buckets each rank's slice per owning rank on the device, exchanges the buckets
+over NCCL, counts + solves the own events and gathers the result rows on rank 0 -- all inside the timed region;
+scaling is strong.
 """
 import argparse
 import json
@@ -44,6 +46,8 @@ def parse_args():
                     help="C5 = solve stress: 500k events with 2-16 forms, class tables injected (solve only)")
     ap.add_argument("--events", type=int, default=500000, help="events of the C5 workload")
     ap.add_argument("--reads", type=int, default=None, help="reads per GPU (default: the workload's)")
+    ap.add_argument("--reads-total", type=int, default=None,
+                    help="N > 1: size of the ONE read set shared by all ranks (default 1e9: BASELINE config 3)")
     ap.add_argument("--genes", type=int, default=None)
     ap.add_argument("--sample-reads", type=int, default=300000, help="reads of the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -204,6 +208,23 @@ def run_reference(args):
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+def compact_reads(reads, torch, wide):
+    """The compact packed form of a synthetic read set (include/lesseq_b200.h): blocks per read u8, chromosome/strand
+    id u8, block start i32 + block length u8 (u16 when a block is 256 or longer).  None when a value does not fit."""
+    blk_cnt = (reads["blk_off"][1:] - reads["blk_off"][:-1]).to(torch.uint8)
+    cs = reads["read_cs"]
+    b2 = reads["blk"].view(-1, 2)
+    blen = b2[:, 1] - b2[:, 0]
+    ok = len(reads["chrom_names"]) <= 64 and len(reads["strand_names"]) <= 2 and \
+        int(blen.max()) < 65536 and int(blen.min()) >= 0 and not wide
+    if not ok:
+        return None, False
+    cs8 = ((cs & 0x3F) | (((cs >> 16) & 1) << 6) | (((cs >> 31) & 1) << 7)).to(torch.uint8)
+    len8 = int(blen.max()) < 256  # short reads: one byte per block length
+    return {"blk_start": b2[:, 0].contiguous(), "blk_len": blen.to(torch.uint8 if len8 else torch.int16).contiguous(),
+            "read_cs8": cs8.contiguous(), "blk_cnt": blk_cnt.contiguous()}, len8
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -221,174 +242,222 @@ def run_ours(args):
         build.build()
     if world > 1:
         dist.barrier()
-    from lesseq_b200 import api, synth
-    from lesseq_b200 import dist as lsd
+    from lesseq_b200 import api, multi, synth
 
     cfg, R, n, genes = workload_config(args, world)
+    if world > 1:
+        # BASELINE config 3: ONE read set of fixed size (1 B reads) over all ranks; rank r holds reads
+        # [r * total / world, (r + 1) * total / world) of it, whatever events they hit
+        total_reads = args.reads_total or (args.reads * world if args.reads else 1_000_000_000)
+        n = total_reads // world
+        total_reads = n * world
+        cfg["workload"] = cfg["workload"].replace("C2:", "C3 (C2 genome, one read set of %d reads over %d GPUs):" % (total_reads, world))
+        cfg["reads_total"] = total_reads
+        cfg["reads_per_gpu"] = n
+        cfg["sharding"] = ("gene-rank ranges x%d (events), covered regions of the whole range; every rank holds 1/%d of the read "
+                           "set, buckets it per owning rank on the device and exchanges the buckets over NCCL" % (world, world))
+    else:
+        total_reads = n
     tmp = tempfile.mkdtemp(prefix="lsq_bench_")
     A, _, _ = synth.make_config(args.workload, n_genes=args.genes)
     fp, mp = os.path.join(tmp, "ev.interval"), os.path.join(tmp, "ev.map")
-    A.write(fp, mp)
-    # gene-rank order = bytewise lexicographic order of the event ids (count.cpp:204-215)
-    ids = [A.map_rows[2 * i][0] for i in range(len(A.ev_gene))]
-    order = sorted(range(len(ids)), key=lambda i: ids[i].encode())
-    sb, se = lsd.shard_range(len(ids), rank, world)
-    ann = api.Annotation(fp, mp, 0, api.UINT64_MAX, shard=(sb, se))
-    assert ann.n_events == se - sb
-    reads = synth.make_reads(A, n, R, 100 + rank, device="cuda", events=np.array(order[sb:se]))
-    # resident layout = the compact packed form (include/lesseq_b200.h): blocks per read u8, chromosome/strand id u8,
-    # block start i32 + block length u8 (u16 when a block is 256 or longer); wide CSR arrays only if a value does not fit
-    blk_cnt = (reads["blk_off"][1:] - reads["blk_off"][:-1]).to(torch.uint8)
-    cs = reads["read_cs"]
-    b2 = reads["blk"].view(-1, 2)
-    blen = b2[:, 1] - b2[:, 0]
-    compact_ok = len(reads["chrom_names"]) <= 64 and len(reads["strand_names"]) <= 2 and \
-        int(blen.max()) < 65536 and int(blen.min()) >= 0 and not args.wide_wire
+    if rank == 0:
+        A.write(fp, mp)
+    if world > 1:
+        box = [tmp]
+        dist.broadcast_object_list(box, src=0)
+        fp, mp = os.path.join(box[0], "ev.interval"), os.path.join(box[0], "ev.map")
+        dist.barrier()
+    n_events_total = len(A.ev_gene)
+    stream = torch.cuda.current_stream()
+    reads = synth.make_reads(A, n, R, 100 + rank, device="cuda")
+    compact, len8 = compact_reads(reads, torch, args.wide_wire)
+    compact_ok = compact is not None
     if compact_ok:
-        cs8 = ((cs & 0x3F) | (((cs >> 16) & 1) << 6) | (((cs >> 31) & 1) << 7)).to(torch.uint8)
-        len8 = int(blen.max()) < 256  # short reads: one byte per block length
-        compact = {"blk_start": b2[:, 0].contiguous(), "blk_len": blen.to(torch.uint8 if len8 else torch.int16).contiguous(),
-                   "read_cs8": cs8.contiguous(), "blk_cnt": blk_cnt.contiguous()}
         dev_reads = api.Reads.from_torch(None, None, None, None, reads["chrom_names"], reads["strand_names"],
                                          blk_cnt=compact["blk_cnt"], read_cs8=compact["read_cs8"], blk_start=compact["blk_start"],
                                          **{"blk_len8" if len8 else "blk_len": compact["blk_len"]})
+        pinned = {k: v.cpu().pin_memory() for k, v in compact.items()}
+        host_reads = api.Reads.from_torch(None, None, None, None, reads["chrom_names"], reads["strand_names"],
+                                          blk_cnt=pinned["blk_cnt"], stream=not args.no_stream and world == 1,
+                                          read_cs8=pinned["read_cs8"], blk_start=pinned["blk_start"],
+                                          **{"blk_len8" if len8 else "blk_len": pinned["blk_len"]})
     else:
         dev_reads = api.Reads.from_torch(reads["blk_off"], reads["blk"], reads["read_cs"], reads["line_num"],
                                          reads["chrom_names"], reads["strand_names"])
+        blk_cnt = (reads["blk_off"][1:] - reads["blk_off"][:-1]).to(torch.uint8)
+        pinned = {"blk": reads["blk"].cpu().pin_memory(), "read_cs": reads["read_cs"].cpu().pin_memory(),
+                  "blk_cnt": blk_cnt.cpu().pin_memory()}
+        host_reads = api.Reads.from_torch(None, pinned["blk"], pinned["read_cs"], None, reads["chrom_names"],
+                                          reads["strand_names"], blk_cnt=pinned["blk_cnt"], stream=not args.no_stream and world == 1)
     resident_bytes = int(dev_reads.host_bytes())
+    n_blocks = int(reads["n_blocks"])
     cfg["l2_policy"] = "inputs (%.2f GB packed reads per GPU) far exceed the 126 MB L2; no flush needed" % (resident_bytes / 1e9)
-    trb = [reads["total_read_bases"]]
-    stream = torch.cuda.current_stream()
-    ctx = api.Context(local, stream=stream.cuda_stream)
-    ctx.upload_events(ann)
+    trb_local = torch.tensor([reads["total_read_bases"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(trb_local)
+    trb = [float(trb_local[0])]
+    del reads
+    torch.cuda.empty_cache()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    ctx.set_reads(0, "SHORT_READ", R, dev_reads)
-    gatherer = lsd.DeviceGather(ann.n_events, ann.n_forms, 1) if world > 1 else None
+    phase_keys = ("clear_ms", "scan_ms", "expand_ms", "general_ms", "finalize_ms", "solve_ms")
+    if world == 1:
+        ann = api.Annotation(fp, mp)
+        ctx = api.Context(local, stream=stream.cuda_stream)
+        ctx.upload_events(ann)
+        ctx.set_reads(0, "SHORT_READ", R, dev_reads)
+
+        def step_resident():
+            ctx.count()
+            ctx.solve(trb)
+
+        def step_e2e():
+            ctx.set_reads(0, "SHORT_READ", R, host_reads)
+            ctx.count()
+            ctx.solve(trb)
+            return ctx.get_count(), ctx.get_solve()
+
+        def results():
+            return ctx.get_count(), ctx.get_solve()
+        tctx = ctx
+        shard_stats = lambda: None  # noqa: E731
+    else:
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)  # NCCL prints its version banner on stdout when a communicator is created: keep the ONE JSON line clean
+        try:
+            job = multi.ShardedJob(fp, mp, local, rank, world, stream=stream.cuda_stream)
+        finally:
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
+        first_line = 1 + rank * n
+        job.full.set_reads(0, "SHORT_READ", R, dev_reads)
+        last = {}
+
+        def sharded_pass():
+            # bucket this rank's slice per owning rank + exchange over NCCL, count and solve the own events, gather
+            last["stats"] = api.shard_reads(job.full, 0, job.shard, 0, job.comm, first_line)
+            job.shard.count()
+            job.shard.solve(trb)
+            last["out"] = api.gather(job.full, job.shard, job.comm, 0)
+
+        def step_resident():
+            sharded_pass()
+
+        def step_e2e():
+            job.full.set_reads(0, "SHORT_READ", R, host_reads)  # host -> device copy of this rank's slice
+            sharded_pass()
+            return last["out"]
+
+        def results():
+            return last["out"]
+        tctx = job.shard
+        shard_stats = lambda: last["stats"]  # noqa: E731
 
     # ---- device-resident pass ---------------------------------------------------------------
-    def step_resident():
-        ctx.count()
-        ctx.solve(trb)
-        if world > 1:
-            gatherer.gather(ctx)  # one NCCL all_gather of the result rows, device to device
-
     for _ in range(args.warmup):
         step_resident()
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    phases = {k: 0.0 for k in ("clear_ms", "scan_ms", "expand_ms", "general_ms", "finalize_ms", "solve_ms")}
+    phases = {k: 0.0 for k in phase_keys}
+    route = {"route_ms": 0.0, "exchange_ms": 0.0, "reads_received": 0, "reads_sent": 0}
     launches = 0
     ev0.record(stream)
     for _ in range(args.steps):
         step_resident()
-        t = ctx.timings()  # waits for the step: per-kernel CUDA-event times of this very step
+        t = tctx.timings()  # waits for the step: per-kernel CUDA-event times of this very step
         for k in phases:
             phases[k] += t[k]
-        launches += t["launches"]
+        launches += t["launches"] + (1 if world > 1 else 0)
+        st = shard_stats()
+        if st:
+            for k in route:
+                route[k] += st[k]
     ev1.record(stream)
     barrier()
     ms_local = ev0.elapsed_time(ev1) / args.steps
-    tsum = ctx.timings()
-    cnt, sol = ctx.get_count(), ctx.get_solve()
+    tsum = tctx.timings()
+    cnt, sol = results()
 
     # ---- end to end through the C ABI with host buffers ---------------------------------------
-    # the same compact form from pinned host memory, streamed (LSQ_READS_STREAM): the scan consumes the blocks while
-    # the copy engine is still delivering them
-    if compact_ok:
-        pinned = {k: v.cpu().pin_memory() for k, v in compact.items()}
-        host_reads = api.Reads.from_torch(None, None, None, None, reads["chrom_names"], reads["strand_names"],
-                                          blk_cnt=pinned["blk_cnt"], stream=not args.no_stream, read_cs8=pinned["read_cs8"],
-                                          blk_start=pinned["blk_start"], **{"blk_len8" if len8 else "blk_len": pinned["blk_len"]})
-    else:
-        pinned = {"blk": reads["blk"].cpu().pin_memory(), "read_cs": reads["read_cs"].cpu().pin_memory(),
-                  "blk_cnt": blk_cnt.cpu().pin_memory()}
-        host_reads = api.Reads.from_torch(None, pinned["blk"], pinned["read_cs"], None, reads["chrom_names"],
-                                          reads["strand_names"], blk_cnt=pinned["blk_cnt"], stream=not args.no_stream)
-
-    def step_e2e():
-        ctx.set_reads(0, "SHORT_READ", R, host_reads)
-        ctx.count()
-        ctx.solve(trb)
-        if world > 1:
-            gatherer.gather(ctx)
-            g = gatherer.unpack() if rank == 0 else None  # rank 0 reads the whole job's results
-            torch.cuda.synchronize()
-            return ctx.get_count(), ctx.get_solve(), g
-        return ctx.get_count(), ctx.get_solve(), None
-
     for _ in range(min(args.warmup, 2)):
         step_e2e()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
-        c2, s2, gathered = step_e2e()
+        c2, s2 = step_e2e()
     e1.record(stream)
     barrier()
     e2e_ms_local = e0.elapsed_time(e1) / args.steps
     clocks = sampler.stop() if sampler else None
-    assert np.array_equal(c2["iso_count"], cnt["iso_count"]) and np.array_equal(s2["theta"], sol["theta"])
-    if gathered is not None:  # rank 0's own shard comes first in gene-rank order
-        assert np.array_equal(gathered["theta"][:ann.n_forms], sol["theta"])
-        assert gathered["iters"].shape[0] == len(ids)
+    if rank == 0:
+        assert np.array_equal(c2["iso_count"], cnt["iso_count"]) and np.array_equal(s2["theta"], sol["theta"])
+        assert sol["iters"].shape[0] == n_events_total
 
     red = torch.tensor([ms_local, e2e_ms_local], dtype=torch.float64, device="cuda")
+    per_rank = torch.zeros(world, 4, dtype=torch.float64, device="cuda")
+    per_rank[rank] = torch.tensor([route["route_ms"] / args.steps, route["exchange_ms"] / args.steps,
+                                   route["reads_received"] / args.steps, phases["scan_ms"] / args.steps], dtype=torch.float64)
     if world > 1:
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
+        dist.all_reduce(per_rank)
     ms, e2e_ms = float(red[0]), float(red[1])
-    total_reads = n * world
-    n_events_total = len(ids)
     if rank == 0:
         peak, peak_src = hbm_peak()
         sk_ms = phases["scan_ms"] / args.steps
         # algorithmic bytes of the count path = one pass over the packed reads, N * (6 + 8 * blocks/read)
         # (2-byte chromosome id + 4-byte offset per read, 8 bytes per block); the resident layout is narrower
         # (`resident_bytes`), so the kernel moves fewer bytes than that
-        n_blocks = int(reads["n_blocks"])
-        alg_bytes = int(6 * n + 8 * n_blocks)
+        n_scanned = int(tsum["reads_in"])
+        alg_bytes = int(6 * n_scanned + 8 * int(tsum["blocks_in"]))
         achieved = alg_bytes / (sk_ms * 1e-3) / 1e9 if sk_ms > 0 else 0.0
         d2h = int(sum(v.nbytes for v in cnt.values()) + sum(v.nbytes for v in sol.values()))
         line = {
             "metric": METRIC, "value": total_reads / (ms / 1000.0), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "i32+f64", "data": "synthetic", "config": cfg,
+            "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "i32+f64", "data": "synthetic", "config": cfg,
             "clocks": clocks,
             "e2e": {"value": total_reads / (e2e_ms / 1000.0), "unit": UNIT,
-                    "h2d_bytes_per_step": int(host_reads.host_bytes()), "d2h_bytes_per_step": d2h,
+                    "h2d_bytes_per_step": int(host_reads.host_bytes()) * world, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms,
                     "wire": ("compact (blk_cnt u8, read_cs8 u8, blk_start i32 + blk_len u8/u16)" if compact_ok else "blk_cnt u8 + wide blk/read_cs") +
-                            (", copy overlapped with the scan (LSQ_READS_STREAM)" if not args.no_stream else "")},
+                            (", copy overlapped with the scan (LSQ_READS_STREAM)" if (not args.no_stream and world == 1) else "")},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "lsq_scan_kernel (1 launch per step, %.0f%% of the step)" % (100.0 * sk_ms / ms),
                          "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(args, world, n, "scan_kernel"),
                          "peak_source": peak_src, "bytes_per_launch": alg_bytes, "ms_per_launch": sk_ms,
-                         "bytes_note": "SURVEY 8(d): N*(6+8*blocks/read); the resident compact layout holds %d bytes" % resident_bytes,
-                         "limiter": "scattered L1TEX operations (2 table gathers + 1 reduction per read at ~1 lane-op/cycle/SM, "
-                                    "profiles/r02_microbench_gather_red_fp64.log), not HBM"},
-            # every kernel of the step (CUDA-event times)
-            "kernels": [
-                {"name": "lsq_clear_kernel", "ms": phases["clear_ms"] / args.steps},
-                {"name": "lsq_scan_kernel", "ms": sk_ms},
-                {"name": "lsq_expand_kernel", "ms": phases["expand_ms"] / args.steps},
-                {"name": "lsq_general_kernel", "ms": phases["general_ms"] / args.steps},
-                {"name": "lsq_finalize_kernel", "ms": phases["finalize_ms"] / args.steps},
-                {"name": "lsq_solve_small_kernel<1>", "ms": phases["solve_ms"] / args.steps},
-            ],
+                         "bytes_note": "SURVEY 8(d): N*(6+8*blocks/read) over the reads the kernel scanned; the resident compact "
+                                       "layout of this rank's slice holds %d bytes" % resident_bytes,
+                         "limiter": "instruction issue and scattered L1TEX operations (2 table gathers + 1 reduction per read; "
+                                    "floor 1.1 ms per 100 M reads, profiles/r02_microbench_gather_red_fp64.log), not HBM"},
+            # every kernel of the step (CUDA-event times, rank 0)
+            "kernels": [{"name": "lsq_" + k[:-3] + "_kernel", "ms": phases[k] / args.steps} for k in phase_keys],
             "events_per_sec": n_events_total / (ms / 1000.0),
             "events": n_events_total,
             "phases_ms_per_step_rank0": {k: v / args.steps for k, v in phases.items()},
             "reads_rank0": {k: int(tsum[k]) for k in ("reads_in", "blocks_in", "reads_single", "reads_pair", "reads_general", "hash_full")},
             "valid_pairs_rank0": int(tsum["pairs_valid"]),
-            "em_iters_mean_rank0": float(sol["iters"].mean()), "em_iters_max_rank0": int(sol["iters"].max()),
-            "em_iters_p99_rank0": float(np.percentile(sol["iters"], 99)),
+            "em_iters_mean": float(sol["iters"].mean()), "em_iters_max": int(sol["iters"].max()),
+            "em_iters_p99": float(np.percentile(sol["iters"], 99)),
         }
+        if world > 1:
+            pr = per_rank.cpu().numpy()
+            line["bucketing"] = {
+                "route_ms_per_rank": [round(float(x), 3) for x in pr[:, 0]],
+                "exchange_ms_per_rank": [round(float(x), 3) for x in pr[:, 1]],
+                "scan_ms_per_rank": [round(float(x), 3) for x in pr[:, 3]],
+                "reads_received_per_rank": [int(x) for x in pr[:, 2]],
+                "multiplicity": float(pr[:, 2].sum()) / total_reads,
+                "note": "a read is sent to every rank owning a candidate event of any of its blocks' pieces; gene-rank order "
+                        "is lexicographic in the event id, so the events of one gene live on several ranks"}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 A2, R2, fp2, mp2, rp2, trb2 = write_sample(args, tmp)
@@ -401,8 +470,13 @@ def run_ours(args):
             except Exception as ex:  # the oracle always exists; report why it could not run
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %s" % ex}
         print(json.dumps(line), flush=True)
-    ctx.close()
-    shutil.rmtree(tmp, ignore_errors=True)
+    if world == 1:
+        ctx.close()
+    else:
+        dist.barrier()
+        job.close()
+    if rank == 0:
+        shutil.rmtree(tmp, ignore_errors=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

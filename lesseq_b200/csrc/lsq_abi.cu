@@ -1065,7 +1065,7 @@ int lsq_router_build(lsq_ctx *c, uint32_t n_ranks, const uint32_t *shard_begin) 
             owner[p] |= 1ull << std::min(d, n_ranks - 1);
         }
     LSQ_CUDA(upload(c->d_owner, owner, c->stream));
-    LSQ_CUDA(c->d_cursor.ensure((size_t)(2 * LSQ_MAX_RANKS + 2 * LSQ_MAX_RANKS * LSQ_MAX_RANKS) * 8));
+    LSQ_CUDA(c->d_cursor.ensure((size_t)(LSQ_MAX_RANKS + LSQ_MAX_RANKS * LSQ_MAX_RANKS + 2 + LSQ_MAX_RANKS) * 8));
     LSQ_CUDA(cudaStreamSynchronize(c->stream));
     return LSQ_OK;
 }
@@ -1083,8 +1083,26 @@ int lsq_shard_reads(lsq_ctx *full, uint32_t m_src, lsq_ctx *shard, uint32_t m_ds
     const uint32_t P = (uint32_t)comm->n_ranks, me = (uint32_t)comm->rank;
     const size_t n = rs.n_reads, nb = rs.n_blocks;
     if (first_line + n > 0xFFFFFFFFull) return fail(LSQ_ERR_RANGE, "line numbers exceed 32 bits");
-    const bool compact_blk = rs.blk_start != nullptr, len8 = rs.blk_len8 != nullptr, cs8 = rs.read_cs8 != nullptr;
-    const bool mixed = rs.blk_cs != nullptr;
+    // The exchange format must be the same on every rank (each posts the sends its peers expect): the narrowest one
+    // all slices fit.  One tiny all-gather of the local capabilities.
+    bool compact_blk = rs.blk_start != nullptr, len8 = rs.blk_len8 != nullptr, cs8 = rs.read_cs8 != nullptr;
+    bool mixed = rs.blk_cs != nullptr;
+    {
+        unsigned long long *d_fmt = full->d_cursor.as<unsigned long long>() + LSQ_MAX_RANKS + LSQ_MAX_RANKS * LSQ_MAX_RANKS;
+        const unsigned long long mine = (compact_blk ? 1ull : 0ull) | (len8 ? 2ull : 0ull) | (cs8 ? 4ull : 0ull) | (mixed ? 8ull : 0ull);
+        LSQ_CUDA(cudaMemcpyAsync(d_fmt, &mine, 8, cudaMemcpyHostToDevice, s));
+        LSQ_NCCL(g_nccl.AllGather(d_fmt, d_fmt + 1, 1, ncclUint64, comm->comm, s));
+        unsigned long long all[LSQ_MAX_RANKS];
+        LSQ_CUDA(cudaMemcpyAsync(all, d_fmt + 1, (size_t)P * 8, cudaMemcpyDeviceToHost, s));
+        LSQ_CUDA(cudaStreamSynchronize(s));
+        for (uint32_t d = 0; d < P; ++d) {
+            compact_blk = compact_blk && (all[d] & 1ull);
+            len8 = len8 && (all[d] & 2ull);
+            cs8 = cs8 && (all[d] & 4ull);
+            mixed = mixed || (all[d] & 8ull);
+        }
+        len8 = len8 && compact_blk;  // else 16-bit lengths when every slice is compact, wide blocks otherwise
+    }
     const size_t blk_bytes = compact_blk ? 4 : 8, len_bytes = compact_blk ? (len8 ? 1 : 2) : 0, cs_bytes = cs8 ? 1 : 4;
     // outboxes: worst case every read goes to one destination
     lsq::RouteParams R;
@@ -1138,23 +1156,23 @@ int lsq_shard_reads(lsq_ctx *full, uint32_t m_src, lsq_ctx *shard, uint32_t m_ds
         LSQ_CUDA(cudaStreamWaitEvent(s, full->ev_all[m_src], 0));
     }
     LSQ_CUDA(cudaEventRecord(ev[0], s));
-    LSQ_CUDA(cudaMemsetAsync(R.cursor, 0, 2 * LSQ_MAX_RANKS * 8, s));
+    LSQ_CUDA(cudaMemsetAsync(R.cursor, 0, LSQ_MAX_RANKS * 8, s));
     if (n) {
         const uint64_t n_groups = (n + lsq::SCAN_GROUP - 1) / lsq::SCAN_GROUP;
-        const unsigned grid = (unsigned)std::min<uint64_t>((n_groups + lsq::SCAN_WARPS - 1) / lsq::SCAN_WARPS, (uint64_t)full->n_sms * lsq::SCAN_MINB);
+        const unsigned grid = (unsigned)std::min<uint64_t>((n_groups + lsq::SCAN_WARPS - 1) / lsq::SCAN_WARPS, (uint64_t)full->n_sms * 4);
         lsq::lsq_route_kernel<<<grid, lsq::SCAN_BLOCK, 0, s>>>(SP, R);
         LSQ_CUDA(cudaGetLastError());
     }
     LSQ_CUDA(cudaEventRecord(ev[1], s));
     // sizes: every rank learns how much every rank sends to every rank
-    unsigned long long *d_mat = R.cursor + 2 * LSQ_MAX_RANKS;
-    LSQ_NCCL(g_nccl.AllGather(R.cursor, d_mat, 2 * LSQ_MAX_RANKS, ncclUint64, comm->comm, s));
-    std::vector<unsigned long long> mat((size_t)P * 2 * LSQ_MAX_RANKS);
+    unsigned long long *d_mat = R.cursor + LSQ_MAX_RANKS;
+    LSQ_NCCL(g_nccl.AllGather(R.cursor, d_mat, LSQ_MAX_RANKS, ncclUint64, comm->comm, s));
+    std::vector<unsigned long long> mat((size_t)P * LSQ_MAX_RANKS);
     LSQ_CUDA(cudaMemcpyAsync(mat.data(), d_mat, mat.size() * 8, cudaMemcpyDeviceToHost, s));
     LSQ_CUDA(cudaStreamSynchronize(s));
     if (rs.copy_pending) rs.copy_pending = false;
-    auto sent_reads = [&](uint32_t src, uint32_t dst) { return (size_t)mat[(size_t)src * 2 * LSQ_MAX_RANKS + 2 * dst]; };
-    auto sent_blocks = [&](uint32_t src, uint32_t dst) { return (size_t)mat[(size_t)src * 2 * LSQ_MAX_RANKS + 2 * dst + 1]; };
+    auto sent_reads = [&](uint32_t src, uint32_t dst) { return (size_t)(mat[(size_t)src * LSQ_MAX_RANKS + dst] >> 32); };
+    auto sent_blocks = [&](uint32_t src, uint32_t dst) { return (size_t)(mat[(size_t)src * LSQ_MAX_RANKS + dst] & 0xFFFFFFFFull); };
     size_t in_reads = 0, in_blocks = 0, out_reads = 0;
     std::vector<size_t> roff(P + 1, 0), boff(P + 1, 0);
     for (uint32_t src = 0; src < P; ++src) {
@@ -1183,6 +1201,10 @@ int lsq_shard_reads(lsq_ctx *full, uint32_t m_src, lsq_ctx *shard, uint32_t m_ds
             const bool per_read = a < 3;
             const size_t sbytes = (per_read ? sr : sb) * unit[a], rbytes = (per_read ? rr : rb) * unit[a];
             const size_t roffb = (per_read ? roff[peer] : boff[peer]) * unit[a];
+            if (peer == me) {  // this rank's own bucket never leaves the device
+                if (sbytes) LSQ_CUDA(cudaMemcpyAsync(in[a].as<unsigned char>() + roffb, o[a].p, sbytes, cudaMemcpyDeviceToDevice, s));
+                continue;
+            }
             if (sbytes) LSQ_NCCL(g_nccl.Send(o[a].p, sbytes, ncclUint8, (int)peer, comm->comm, s));
             if (rbytes) LSQ_NCCL(g_nccl.Recv(in[a].as<unsigned char>() + roffb, rbytes, ncclUint8, (int)peer, comm->comm, s));
         }

@@ -460,11 +460,22 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MINB) lsq_scan_kernel(const _
 // Route kernel (multi-GPU): one pass over the local slice of the read set; every read is appended to the
 // outbox of each rank that owns a candidate event at the piece of any of its blocks.  Same group / lane
 // layout and the same two-gather lookup as the scan kernel, plus one 8-byte gather of the piece's owner
-// mask.  Appends are aggregated per warp: one 64-bit reduction pair per (round, destination) reserves the
-// slots of all 32 lanes.
+// mask.  Appends are reserved once per group of 128 reads: a warp scan per destination gives every lane
+// its offsets, lane d reserves destination d's slots (all destinations in ONE round trip to L2), a second
+// scan places the records.  Reads and blocks are reserved together (reads << 32 | blocks): the receiver
+// pairs them by prefix sums, so both orders must agree.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MINB) lsq_route_kernel(const __grid_constant__ ScanParams P,
-                                                                          const __grid_constant__ RouteParams R) {
+__device__ __forceinline__ unsigned long long warp_incl_scan64(unsigned long long v, uint32_t lane) {
+#pragma unroll
+    for (uint32_t s = 1; s < 32u; s <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, v, s);
+        if (lane >= s) v += t;
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(SCAN_BLOCK, 4) lsq_route_kernel(const __grid_constant__ ScanParams P,
+                                                                  const __grid_constant__ RouteParams R) {
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
     const uint64_t n_groups = (P.n_reads + SCAN_GROUP - 1) / SCAN_GROUP;
     const PieceInfo *const pinfo = P.T.pinfo;
@@ -491,64 +502,71 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MINB) lsq_route_kernel(const 
             o = r0 < g1 ? __ldcs(P.blk_off + r0) : 0u;
         }
         if (compact_cs && r0 < g1) v4 = __ldcs(reinterpret_cast<const uint32_t *>(P.read_cs8 + r0));
-#pragma unroll 1
-        for (uint32_t k = 0; k < (uint32_t)SCAN_ITEMS; ++k) {
+        // ---- owners of my four reads ---------------------------------------------------------------
+        uint32_t rn[SCAN_ITEMS], base[SCAN_ITEMS], cs[SCAN_ITEMS], mask[SCAN_ITEMS];
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) {
             const uint64_t r = r0 + k;
-            uint32_t rn, cs;
-            if (compact_cnt) rn = (c4 >> (8u * k)) & 0xFFu;
-            else rn = (r < g1 ? __ldcs(P.blk_off + r + 1) : o) - o;
-            const uint32_t cs8 = (v4 >> (8u * k)) & 0xFFu;
-            if (compact_cs) cs = expand_cs8(cs8);
-            else cs = r < g1 ? __ldcs(P.read_cs + r) : 0u;
-            const uint32_t base = o;
-            o += rn;
-            // owners of the pieces of the read's blocks
-            unsigned long long mask = 0ull;
+            if (compact_cnt) rn[k] = (c4 >> (8 * k)) & 0xFFu;
+            else rn[k] = (r < g1 ? __ldcs(P.blk_off + r + 1) : o) - o;
+            if (compact_cs) cs[k] = expand_cs8((v4 >> (8 * k)) & 0xFFu);
+            else cs[k] = r < g1 ? __ldcs(P.read_cs + r) : 0u;
+            base[k] = o;
+            o += rn[k];
+            unsigned long long m = 0ull;
 #pragma unroll 1
-            for (uint32_t j = 0; j < rn; ++j) {
-                const int2 b = load_block_stream(P, base + j);
-                const uint32_t c = ((cs & 0x80000000u) ? __ldg(P.blk_cs + base + j) : cs) & 0xFFFFu;
+            for (uint32_t j = 0; j < rn[k]; ++j) {
+                const int2 b = load_block(P, base[k] + j);
+                const uint32_t c = ((cs[k] & 0x80000000u) ? __ldg(P.blk_cs + base[k] + j) : cs[k]) & 0xFFFFu;
                 const Probe q = probe_of(P, b, __ldg(P.file_meta + c));
                 const uint2 e = q.how == 1u ? __ldg(P.T.bp_bkt + q.slot) : make_uint2(0u, 0u);
                 const uint32_t p = piece_of(P, b, c, q, e);
-                if (p != PIECE_NONE && (__ldg(&pinfo[p].sigw) & PIECE_CAND)) mask |= __ldg(R.owner + p);
+                if (p != PIECE_NONE && (__ldg(&pinfo[p].sigw) & PIECE_CAND)) m |= __ldg(R.owner + p);
             }
-            // append to every destination present in the warp
-            unsigned long long any = mask;
+            mask[k] = (uint32_t)m;  // at most ROUTE_MAX_RANKS = 16 ranks
+        }
+        uint32_t present = mask[0] | mask[1] | mask[2] | mask[3];
 #pragma unroll
-            for (int d = 16; d > 0; d >>= 1) any |= __shfl_xor_sync(0xFFFFFFFFu, any, d);
-#pragma unroll 1
-            while (any) {
-                const uint32_t d = (uint32_t)__ffsll((long long)any) - 1u;
-                any &= any - 1ull;
-                const bool sel = (mask >> d) & 1ull;
-                const unsigned bal = __ballot_sync(0xFFFFFFFFu, sel);
-                const uint32_t my_blk = sel ? rn : 0u;
-                uint32_t incl = my_blk;
+        for (int d = 16; d > 0; d >>= 1) present |= __shfl_xor_sync(0xFFFFFFFFu, present, d);
+        if (present == 0u) continue;  // warp-uniform
+        // what I send to destination d: reads << 32 | blocks
+        auto my_load = [&](uint32_t d) {
+            unsigned long long v = 0ull;
 #pragma unroll
-                for (uint32_t s = 1; s < 32u; s <<= 1) {
-                    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, s);
-                    if (lane >= s) incl += t;
-                }
-                const uint32_t tot_blk = __shfl_sync(0xFFFFFFFFu, incl, 31);
-                unsigned long long rb = 0ull, bb = 0ull;
-                if (lane == 0) {
-                    rb = atomicAdd(R.cursor + 2u * d, (unsigned long long)__popc(bal));
-                    bb = atomicAdd(R.cursor + 2u * d + 1u, (unsigned long long)tot_blk);
-                }
-                rb = __shfl_sync(0xFFFFFFFFu, rb, 0);
-                bb = __shfl_sync(0xFFFFFFFFu, bb, 0);
-                if (!sel) continue;
-                const RouteBox &B = R.box[d];
-                const size_t ri = (size_t)rb + __popc(bal & ((1u << lane) - 1u));
-                size_t bi = (size_t)bb + (incl - my_blk);
-                B.blk_cnt[ri] = (uint8_t)rn;
-                if (B.read_cs8) B.read_cs8[ri] = (uint8_t)cs8;
-                else B.read_cs[ri] = cs;
-                B.line_num[ri] = P.line_num ? __ldg(P.line_num + r) : R.line_base + (uint32_t)r + 1u;
+            for (int k = 0; k < SCAN_ITEMS; ++k)
+                if ((mask[k] >> d) & 1u) v += (1ull << 32) | (unsigned long long)rn[k];
+            return v;
+        };
+        // ---- pass 1: the group's totals per destination; lane d reserves destination d ----------------
+        unsigned long long my_total = 0ull;
 #pragma unroll 1
-                for (uint32_t j = 0; j < rn; ++j, ++bi) {
-                    const int2 b = load_block(P, base + j);
+        for (uint32_t pm = present; pm; pm &= pm - 1u) {
+            const uint32_t d = (uint32_t)__ffs((int)pm) - 1u;
+            const unsigned long long tot = __shfl_sync(0xFFFFFFFFu, warp_incl_scan64(my_load(d), lane), 31);
+            if (lane == d) my_total = tot;
+        }
+        unsigned long long my_rsv = 0ull;
+        if (my_total) my_rsv = atomicAdd(R.cursor + lane, my_total);
+        // ---- pass 2: place the records -----------------------------------------------------------------
+#pragma unroll 1
+        for (uint32_t pm = present; pm; pm &= pm - 1u) {
+            const uint32_t d = (uint32_t)__ffs((int)pm) - 1u;
+            const unsigned long long v = my_load(d);
+            const unsigned long long at = __shfl_sync(0xFFFFFFFFu, my_rsv, (int)d) + warp_incl_scan64(v, lane) - v;
+            if (v == 0ull) continue;
+            const RouteBox &B = R.box[d];
+            size_t ri = (size_t)(at >> 32), bi = (size_t)(at & 0xFFFFFFFFull);
+#pragma unroll
+            for (int k = 0; k < SCAN_ITEMS; ++k) {
+                if (!((mask[k] >> d) & 1u)) continue;
+                B.blk_cnt[ri] = (uint8_t)rn[k];
+                if (B.read_cs8) B.read_cs8[ri] = (uint8_t)((cs[k] & 0x3Fu) | ((cs[k] >> 10) & 0x40u) | ((cs[k] >> 24) & 0x80u));
+                else B.read_cs[ri] = cs[k];
+                B.line_num[ri] = P.line_num ? __ldg(P.line_num + r0 + k) : R.line_base + (uint32_t)(r0 + k) + 1u;
+                ++ri;
+#pragma unroll 1
+                for (uint32_t j = 0; j < rn[k]; ++j, ++bi) {
+                    const int2 b = load_block(P, base[k] + j);
                     if (B.blk_start) {
                         B.blk_start[bi] = b.x;
                         if (B.blk_len8) B.blk_len8[bi] = (uint8_t)(b.y - b.x);
@@ -556,7 +574,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MINB) lsq_route_kernel(const 
                     } else {
                         B.blk[bi] = b;
                     }
-                    if (B.blk_cs) B.blk_cs[bi] = (cs & 0x80000000u) ? __ldg(P.blk_cs + base + j) : cs;
+                    if (B.blk_cs) B.blk_cs[bi] = (cs[k] & 0x80000000u) ? __ldg(P.blk_cs + base[k] + j) : cs[k];
                 }
             }
         }

@@ -205,7 +205,7 @@ struct RouteParams {
     uint32_t n_ranks;
     uint32_t line_base;               // line number of local read 0 minus 1 when the set carries no line numbers
     const unsigned long long *owner;  // [n_pieces]
-    unsigned long long *cursor;       // [2 * n_ranks] reads, blocks appended per destination
+    unsigned long long *cursor;       // [n_ranks] appended per destination: reads << 32 | blocks
     RouteBox box[ROUTE_MAX_RANKS];
 };
 

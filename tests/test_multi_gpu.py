@@ -18,6 +18,7 @@ pytestmark = pytest.mark.gpu
 def _worker(rank, world, port, tmp, q):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import ctypes as C
     import torch
     import torch.distributed as dist
     from lesseq_b200 import api, multi, synth
@@ -38,11 +39,13 @@ def _worker(rank, world, port, tmp, q):
             v = whole.view
             n = int(v.n_reads)
             lo, hi = (n * rank) // world, (n * (rank + 1)) // world
-            off = np.ctypeslib.as_array(v.blk_off, shape=(n + 1,)).copy()
-            blk = np.ctypeslib.as_array(v.blk, shape=(2 * int(v.n_blocks),)).copy()
-            cs = np.ctypeslib.as_array(v.read_cs, shape=(n,)).copy()
-            ln = np.ctypeslib.as_array(v.line_num, shape=(n,)).copy()
-            bcs = np.ctypeslib.as_array(v.blk_cs, shape=(int(v.n_blocks),)).copy() if v.blk_cs else None
+            def arr(ptr, ctype, count):
+                return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(count,)).copy()
+            off = arr(v.blk_off, C.c_uint32, n + 1)
+            blk = arr(v.blk, C.c_int32, 2 * int(v.n_blocks))
+            cs = arr(v.read_cs, C.c_uint32, n)
+            ln = arr(v.line_num, C.c_uint32, n) if v.line_num else np.arange(1, n + 1, dtype=np.uint32)
+            bcs = arr(v.blk_cs, C.c_uint32, int(v.n_blocks)) if v.blk_cs else None
             cn = [v.chrom_names[i].decode() for i in range(v.n_chrom_names)]
             sn = [v.strand_names[i].decode() for i in range(v.n_strand_names)]
             sl = api.Reads.from_numpy(off[lo:hi + 1] - off[lo], blk[2 * off[lo]:2 * off[hi]], cs[lo:hi], ln[lo:hi], cn, sn,
@@ -109,6 +112,8 @@ def test_two_gpu_bucketing_exchange_gather_equals_single_gpu(tmp_path):
     for p in procs:
         p.start()
     for p in procs:
-        p.join(600)
+        p.join(420)
+        if p.is_alive():
+            p.kill()
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
