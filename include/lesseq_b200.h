@@ -163,7 +163,7 @@ typedef struct lsq_solve_out {
 typedef struct lsq_timings {
     float clear_ms, scan_ms, expand_ms, general_ms, finalize_ms, solve_ms;
     uint32_t launches;     /* kernels launched by the last lsq_count + lsq_solve */
-    uint32_t reserved;
+    uint32_t exact_events; /* events whose EM was replayed read by read in the reference's order (fragile stop rule) */
     uint64_t reads_in, blocks_in;   /* summed over read sets */
     uint64_t reads_single;          /* reads tallied by a single-block signature */
     uint64_t reads_pair;            /* reads tallied by a two-block signature */

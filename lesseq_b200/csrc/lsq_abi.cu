@@ -120,6 +120,8 @@ struct lsq_ctx {
     DevBuf d_ext, d_scratch, d_gen_list;  // d_scratch: signature counters | hash | general-list length (cleared per read set)
     uint32_t scan_flags = 0;
     DevBuf d_n_valid, d_bases_out, d_iso, d_theta, d_rpkm, d_se, d_ll, d_llpr, d_iters;
+    DevBuf d_flag, d_exact, d_exact_rec;  // order-exact EM replay: flag list + per-event flags; spans, segments; records
+    uint32_t exact_events = 0;            // events replayed by the last lsq_solve (statistics)
     bool counted = false, finalized = false, solved = false;
     // streamed read sets: copies run on their own stream and publish their progress to the filter
     cudaStream_t copy_stream = nullptr;
@@ -555,6 +557,7 @@ static int ensure_run_buffers(lsq_ctx *c) {
     LSQ_CUDA(c->d_ll.ensure(E * 8));
     LSQ_CUDA(c->d_llpr.ensure(E * 8));
     LSQ_CUDA(c->d_iters.ensure(E * 4));
+    LSQ_CUDA(c->d_flag.ensure((2 * E + 8) * 4));
     return LSQ_OK;
 }
 
@@ -584,6 +587,9 @@ static void fill_solve_params(lsq_ctx *c, lsq::SolveParams &P) {
     P.ll_per_read = c->d_llpr.as<double>();
     P.iters = c->d_iters.as<uint32_t>();
     P.max_iters = 10000000u;
+    P.flag_n = c->d_flag.as<uint32_t>();
+    P.flag_list = P.flag_n + 4;
+    P.ev_flag = P.flag_list + std::max<uint32_t>(c->E, 1);
     P.pairs_valid = c->d_counters.as<unsigned long long>() + LSQ_MAX_METHODS * lsq::CTR_N + 2;
 }
 
@@ -812,6 +818,121 @@ int lsq_get_classes(lsq_ctx *c, uint32_t m, uint64_t *cls_off, uint64_t *cls_mas
     return LSQ_OK;
 }
 
+// Order-exact EM replay of the flagged events (lsq_kernels.cuh: lsq_collect_kernel, lsq_exact_kernel).
+static int exact_replay(lsq_ctx *c, const lsq::SolveParams &P, uint32_t n_flag) {
+    cudaStream_t s = c->stream;
+    const uint32_t E = c->E, M = c->M;
+    const lsq::HostTables &H = c->H;
+    std::vector<uint32_t> flagged(n_flag);
+    std::vector<unsigned long long> nv((size_t)M * E);
+    LSQ_CUDA(cudaMemcpyAsync(flagged.data(), P.flag_list, (size_t)n_flag * 4, cudaMemcpyDeviceToHost, s));
+    LSQ_CUDA(cudaMemcpyAsync(nv.data(), c->d_n_valid.p, nv.size() * 8, cudaMemcpyDeviceToHost, s));
+    LSQ_CUDA(cudaStreamSynchronize(s));
+    // record segments: an event holds exactly its valid reads (of the read sets counted on the device)
+    std::vector<uint64_t> seg_off(n_flag + 1, 0);
+    for (uint32_t i = 0; i < n_flag; ++i) {
+        uint64_t tot = 0;
+        for (uint32_t m = 0; m < M; ++m)
+            if (!c->sets[m].injected) tot += nv[(size_t)m * E + H.hdr[flagged[i]].out_ev];
+        seg_off[i + 1] = seg_off[i] + tot;
+    }
+    // merged spans of the flagged events per chromosome: the collect kernel's pre-check
+    const uint32_t nch = H.n_chroms;
+    std::vector<std::vector<std::pair<int32_t, int32_t> > > spans(std::max<uint32_t>(nch, 1));
+    for (uint32_t i = 0; i < n_flag; ++i) {
+        const lsq::EvHdr &h = H.hdr[flagged[i]];
+        spans[H.ev_chrom[flagged[i]]].push_back(std::make_pair(h.gs, h.ge));
+    }
+    std::vector<int32_t> iv_start, iv_end;
+    std::vector<uint32_t> iv_off(nch + 1, 0);
+    for (uint32_t ch = 0; ch < nch; ++ch) {
+        std::sort(spans[ch].begin(), spans[ch].end());
+        for (auto &sp : spans[ch]) {
+            if (iv_start.size() > iv_off[ch] && sp.first <= iv_end.back()) iv_end.back() = std::max(iv_end.back(), sp.second);
+            else {
+                iv_start.push_back(sp.first);
+                iv_end.push_back(sp.second);
+            }
+        }
+        iv_off[ch + 1] = (uint32_t)iv_start.size();
+    }
+    // device layout: seg_off | seg_cur | iv_off | iv_start | iv_end | strand ranks (one row per read set)
+    const size_t niv = iv_start.size();
+    const size_t o_cur = (size_t)(n_flag + 1) * 8, o_ivoff = o_cur + (((size_t)n_flag * 4 + 7) & ~(size_t)7), o_ivs = o_ivoff + (size_t)(nch + 2) * 4,
+                 o_ive = o_ivs + niv * 4 + 4, o_sr = o_ive + niv * 4 + 4, bytes = o_sr + (size_t)LSQ_MAX_METHODS * 256;
+    LSQ_CUDA(c->d_exact.ensure(bytes));
+    LSQ_CUDA(c->d_exact_rec.ensure(std::max<uint64_t>(seg_off[n_flag], 1) * sizeof(lsq::ExactRec)));
+    unsigned char *d = c->d_exact.as<unsigned char>();
+    std::vector<unsigned char> hbuf(bytes, 0);
+    memcpy(hbuf.data(), seg_off.data(), (size_t)(n_flag + 1) * 8);
+    memcpy(hbuf.data() + o_ivoff, iv_off.data(), (size_t)(nch + 1) * 4);
+    if (niv) {
+        memcpy(hbuf.data() + o_ivs, iv_start.data(), niv * 4);
+        memcpy(hbuf.data() + o_ive, iv_end.data(), niv * 4);
+    }
+    for (uint32_t m = 0; m < M; ++m) {  // rank of every file strand string (bytewise order, count.cpp:64-85)
+        const std::vector<std::string> &sn = c->sets[m].strand_names;
+        for (size_t i = 0; i < sn.size() && i < 256; ++i) {
+            unsigned rank = 0;
+            for (size_t j = 0; j < sn.size(); ++j) rank += sn[j] < sn[i] ? 1u : 0u;
+            hbuf[o_sr + (size_t)m * 256 + i] = (unsigned char)rank;
+        }
+    }
+    LSQ_CUDA(cudaMemcpyAsync(d, hbuf.data(), bytes, cudaMemcpyHostToDevice, s));
+    for (uint32_t m = 0; m < M; ++m) {
+        ReadSet &rs = c->sets[m];
+        if (rs.injected || rs.n_reads == 0) continue;
+        lsq::ScanParams SP;
+        memset(&SP, 0, sizeof SP);
+        SP.T = c->T;
+        SP.n_reads = rs.n_reads;
+        SP.blk_off = rs.blk_cnt ? nullptr : rs.blk_off;
+        SP.blk_cnt = rs.blk_cnt;
+        SP.grp_base = rs.d_grp_base.as<uint32_t>();
+        SP.sup_base = rs.d_sup_base.as<uint32_t>();
+        SP.blk = rs.blk;
+        SP.read_cs = rs.read_cs;
+        SP.read_cs8 = rs.read_cs8;
+        SP.blk_start = rs.blk_start;
+        SP.blk_len = rs.blk_len;
+        SP.blk_len8 = rs.blk_len8;
+        SP.blk_cs = rs.blk_cs;
+        SP.chrom_remap = rs.d_chrom_remap.as<uint32_t>();
+        SP.file_meta = rs.d_file_meta.as<uint4>();
+        SP.line_num = rs.line_num;
+        SP.strand_tbl = rs.d_strand_tbl.as<uint8_t>();
+        LSQ_CUDA(c->d_ext.ensure((rs.n_blocks + 2 * rs.n_reads + 2) * 8));
+        SP.ext = c->d_ext.as<int2>();
+        lsq::CollectParams C;
+        C.ev_flag = P.ev_flag;
+        C.iv_chrom_off = reinterpret_cast<const uint32_t *>(d + o_ivoff);
+        C.iv_start = reinterpret_cast<const int32_t *>(d + o_ivs);
+        C.iv_end = reinterpret_cast<const int32_t *>(d + o_ive);
+        C.seg_off = reinterpret_cast<const uint64_t *>(d);
+        C.seg_cur = reinterpret_cast<uint32_t *>(d + o_cur);
+        C.rec = c->d_exact_rec.as<lsq::ExactRec>();
+        C.strand_rank = d + o_sr + (size_t)m * 256;
+        C.m = m;
+        const uint64_t n_groups = (rs.n_reads + lsq::SCAN_GROUP - 1) / lsq::SCAN_GROUP;
+        const unsigned grid = (unsigned)std::min<uint64_t>((n_groups + lsq::SCAN_WARPS - 1) / lsq::SCAN_WARPS, (uint64_t)c->n_sms * 4);
+        lsq::lsq_collect_kernel<<<grid, lsq::SCAN_BLOCK, 0, s>>>(SP, C);
+        LSQ_CUDA(cudaGetLastError());
+        c->tm.launches++;
+    }
+    lsq::ExactParams X;
+    X.n_flag = n_flag;
+    X.flag_list = P.flag_list;
+    X.seg_off = reinterpret_cast<const uint64_t *>(d);
+    X.seg_cur = reinterpret_cast<const uint32_t *>(d + o_cur);
+    X.rec = c->d_exact_rec.as<lsq::ExactRec>();
+    lsq::lsq_exact_kernel<<<(n_flag + 31) / 32, 32, 0, s>>>(P, X);
+    LSQ_CUDA(cudaGetLastError());
+    c->tm.launches++;
+    LSQ_CUDA(cudaStreamSynchronize(s));  // hbuf and friends go out of scope
+    c->exact_events = n_flag;
+    return LSQ_OK;
+}
+
 int lsq_solve(lsq_ctx *c, const double *total_read_bases, uint32_t n_methods) {
     if (!c || !total_read_bases) return fail(LSQ_ERR_ARG, "lsq_solve: null argument");
     if (!c->have_tables || c->M == 0) return fail(LSQ_ERR_STATE, "lsq_solve without tables / read sets");
@@ -836,6 +957,7 @@ int lsq_solve(lsq_ctx *c, const double *total_read_bases, uint32_t n_methods) {
     P.small_enabled = small ? 1 : 0;
     P.work_counter = reinterpret_cast<unsigned int *>(c->d_counters.as<unsigned long long>() + LSQ_MAX_METHODS * lsq::CTR_N);
     LSQ_CUDA(cudaEventRecord(c->ev[2], s));
+    LSQ_CUDA(cudaMemsetAsync(c->d_flag.p, 0, (size_t)(2 * std::max<uint32_t>(c->E, 1) + 8) * 4, s));
     if (c->E && small) {
         LSQ_CUDA(cudaMemsetAsync(P.work_counter, 0, sizeof(unsigned int), s));
         unsigned grid = std::min<unsigned>((c->E + 127) / 128, (unsigned)c->n_sms * 8u);
@@ -850,6 +972,18 @@ int lsq_solve(lsq_ctx *c, const double *total_read_bases, uint32_t n_methods) {
         lsq::lsq_solve_kernel<WARPS><<<grid, WARPS * 32, 0, s>>>(P);
         LSQ_CUDA(cudaGetLastError());
         c->tm.launches++;
+    }
+    // events whose stop decision is within summation-order noise of its threshold are replayed read by read (rare);
+    // this is the one host round trip of the lsq_count + lsq_solve pair
+    c->exact_events = 0;
+    if (c->E && !getenv("LSQ_NO_EXACT_EM")) {
+        uint32_t n_flag = 0;
+        LSQ_CUDA(cudaMemcpyAsync(&n_flag, P.flag_n, 4, cudaMemcpyDeviceToHost, s));
+        LSQ_CUDA(cudaStreamSynchronize(s));
+        if (n_flag) {
+            rc = exact_replay(c, P, n_flag);
+            if (rc) return rc;
+        }
     }
     LSQ_CUDA(cudaEventRecord(c->ev[3], s));
     c->tm_solve_pending = true;
@@ -919,6 +1053,7 @@ int lsq_get_timings(lsq_ctx *c, lsq_timings *o) {
         c->tm_count_pending = false;
     }
     if (c->tm_solve_pending) {
+        tm.exact_events = c->exact_events;
         LSQ_CUDA(cudaEventElapsedTime(&tm.solve_ms, c->ev[2], c->ev[3]));
         c->tm_solve_pending = false;
     }

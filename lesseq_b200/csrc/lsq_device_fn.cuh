@@ -37,6 +37,20 @@ LSQ_HD double lsq_div(double a, double b) {  // IEEE division, never contracted 
     return a / b;
 #endif
 }
+LSQ_HD double lsq_mul(double a, double b) {  // IEEE multiply / add that nvcc cannot contract into an FMA
+#ifdef __CUDA_ARCH__
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+LSQ_HD double lsq_add(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
 LSQ_HD int32_t lsq_max(int32_t a, int32_t b) { return a > b ? a : b; }
 LSQ_HD int32_t lsq_min(int32_t a, int32_t b) { return a < b ? a : b; }
 
@@ -852,6 +866,120 @@ LSQ_HD void expand_signature(const ScanParams &P, const ReadView &rv, uint32_t p
         const uint64_t cm = eval_pair(P, h, T.seg + h.seg_off, T.fmask + h.form_off, rv, 0u, total, ml);
         if (cm != 0ull && ml == total) sink(x, h, cm);
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Order-exact EM (common/read.h:592-660).  The solve kernels sum over compatibility CLASSES; the reference sums
+// over READS in index order (count.cpp:64-85: chromosome, start, end, strand string, read name), so their
+// log-likelihoods differ in the last bits.  That never matters -- except when the stop rule
+// |1 - ll_old / ll| > 1e-6 is decided within that noise: near the threshold, or when ll itself is rounding noise
+// (a boundary solution with all G_k = 1).  The solve kernels flag such events (em_stop_is_fragile); their valid
+// reads are then collected, put in the reference's order and the EM is replayed read by read with the
+// reference's own operation order, which makes theta bit-identical to the reference.
+// ---------------------------------------------------------------------------------------------
+struct ExactRec {
+    int32_t start, end;     // first kept start, last kept end of the read
+    uint32_t strand_rank;   // rank of the read's strand string among the file's strand strings (bytewise order)
+    uint32_t line_num;      // the read is named "read-<line_num>"
+    uint64_t mask;          // forms the read is compatible with
+    uint32_t m;             // read set
+    uint32_t pad;
+};
+
+// "read-<a>" < "read-<b>" as byte strings: compare the decimal digit strings.  Left-aligned to ten digits the
+// numbers compare like the strings; a proper prefix ("1" vs "10") is the smaller one.
+LSQ_HD uint64_t name_sort_key(uint32_t n) {
+    uint32_t nd = 1;
+    uint64_t p = 10;
+    while (nd < 10u && (uint64_t)n >= p) {
+        p *= 10;
+        ++nd;
+    }
+    uint64_t v = n;
+    for (uint32_t i = nd; i < 10u; ++i) v *= 10;
+    return (v << 4) | nd;
+}
+LSQ_HD bool exact_rec_less(const ExactRec &a, const ExactRec &b) {
+    if (a.m != b.m) return a.m < b.m;
+    if (a.start != b.start) return a.start < b.start;
+    if (a.end != b.end) return a.end < b.end;
+    if (a.strand_rank != b.strand_rank) return a.strand_rank < b.strand_rank;
+    return name_sort_key(a.line_num) < name_sort_key(b.line_num);
+}
+// In-place heapsort (no recursion, no extra memory): read names are unique, so the order is total.
+LSQ_HD void exact_sort(ExactRec *a, uint32_t n) {
+    if (n < 2u) return;
+    auto sift = [&](uint32_t root, uint32_t end) {
+        const ExactRec v = a[root];
+        while (true) {
+            uint32_t child = 2u * root + 1u;
+            if (child >= end) break;
+            if (child + 1u < end && exact_rec_less(a[child], a[child + 1u])) ++child;
+            if (!exact_rec_less(v, a[child])) break;
+            a[root] = a[child];
+            root = child;
+        }
+        a[root] = v;
+    };
+    for (uint32_t i = n / 2u; i-- > 0u;) sift(i, n);
+    for (uint32_t end = n - 1u; end > 0u; --end) {
+        const ExactRec t = a[0];
+        a[0] = a[end];
+        a[end] = t;
+        sift(0u, end);
+    }
+}
+
+// Is the EM's stop decision at distance `near` from the threshold (min over the iterations of
+// | |1 - ll_old/ll| - 1e-6 |), with final log-likelihood ll over n reads, safe against summation-order noise?
+LSQ_HD bool em_stop_is_fragile(double near, double ll, double n_reads) {
+    const double margin = 1E-12 > 4.5E-16 * n_reads ? 1E-12 : 4.5E-16 * n_reads;
+    return near < margin || (ll > -1E-8 && ll < 1E-8);
+}
+
+// reads_log_likelihood (read.h:620-636) over the sorted records: every form's term is added in form order, zeros
+// included, exactly as the reference's dense matrix row does.
+LSQ_HD double exact_loglik(const ExactRec *rec, uint32_t n, uint32_t K, const double *theta, const double *G, size_t g_stride) {
+    double ll = 0.0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const double *g = G + (size_t)rec[i].m * g_stride;
+        double s = 0.0;
+        for (uint32_t k = 0; k < K; ++k) s = lsq_add(s, lsq_mul(theta[k], ((rec[i].mask >> k) & 1ull) ? g[k] : 0.0));
+        ll = lsq_add(ll, log(s));
+    }
+    return ll;
+}
+// compute_iso_probs_EM (read.h:638-660) read by read.  theta (K doubles) receives the result, old_theta is scratch.
+// Returns the iterations executed; ll_out = the final log-likelihood.
+LSQ_HD uint32_t exact_em(const ExactRec *rec, uint32_t n, double n_total, uint32_t K, const double *G, size_t g_stride,
+                         double *theta, double *old_theta, double &ll_out, uint32_t max_iters) {
+    for (uint32_t k = 0; k < K; ++k) theta[k] = lsq_div(1.0, (double)K);
+    uint32_t iters = 0;
+    double ll = 0.0;
+    while (true) {
+        for (uint32_t k = 0; k < K; ++k) old_theta[k] = theta[k];
+        const double old_ll = exact_loglik(rec, n, K, old_theta, G, g_stride);
+        for (uint32_t k = 0; k < K; ++k) {  // compute_iso_probs_EM_step, read.h:592-618
+            double sum_zeta = 0.0;
+            for (uint32_t i = 0; i < n; ++i) {
+                const double *g = G + (size_t)rec[i].m * g_stride;
+                double s = 0.0;
+                for (uint32_t k2 = 0; k2 < K; ++k2)
+                    s = lsq_add(s, lsq_mul(old_theta[k2], ((rec[i].mask >> k2) & 1ull) ? g[k2] : 0.0));
+                if (s > 0.0) {
+                    const double lp = lsq_mul(old_theta[k], ((rec[i].mask >> k) & 1ull) ? g[k] : 0.0);
+                    if (lp > 0.0) sum_zeta = lsq_add(sum_zeta, lsq_div(lp, s));
+                }
+            }
+            theta[k] = lsq_div(sum_zeta, n_total);
+        }
+        ll = exact_loglik(rec, n, K, theta, G, g_stride);
+        ++iters;
+        const double d = 1.0 - lsq_div(old_ll, ll);
+        if (!((d < 0.0 ? -d : d) > 1E-6) || iters >= max_iters) break;
+    }
+    ll_out = ll;
+    return iters;
 }
 
 }  // namespace lsq

@@ -790,7 +790,7 @@ __global__ void __launch_bounds__(WARPS * 32, 3) lsq_solve_kernel(SolveParams P)
         for (uint32_t k = lane; k < K; k += 32) th_new[k] = __ddiv_rn(1.0, (double)K);
         __syncwarp();
         uint32_t iters = 0;
-        double ll = 0.0;
+        double ll = 0.0, near = 1E300;  // near: distance of the stop decision from its threshold (em_stop_is_fragile)
         // Each lane keeps the (mask, count) classes it owns in registers together with the class
         // probability s_c at the current theta, so an EM iteration evaluates s_c once per class
         // instead of once per (class, form).  Lanes own classes in the same order as the strided
@@ -877,7 +877,9 @@ __global__ void __launch_bounds__(WARPS * 32, 3) lsq_solve_kernel(SolveParams P)
                 ll = refresh(th_new);
                 ++iters;
                 const double ratio = __ddiv_rn(ll_old, ll);
-                if (!(fabs(__dsub_rn(1.0, ratio)) > 1E-6) || iters >= P.max_iters) break;
+                const double tk = fabs(__dsub_rn(1.0, ratio));
+                near = fmin(near, fabs(tk - 1E-6));
+                if (!(tk > 1E-6) || iters >= P.max_iters) break;
                 ll_old = ll;
             }
         } else {
@@ -910,7 +912,9 @@ __global__ void __launch_bounds__(WARPS * 32, 3) lsq_solve_kernel(SolveParams P)
                 ll = loglik(th_new);
                 ++iters;
                 double ratio = __ddiv_rn(ll_old, ll);
-                if (!(fabs(__dsub_rn(1.0, ratio)) > 1E-6) || iters >= P.max_iters) break;
+                const double tk = fabs(__dsub_rn(1.0, ratio));
+                near = fmin(near, fabs(tk - 1E-6));
+                if (!(tk > 1E-6) || iters >= P.max_iters) break;
                 ll_old = ll;  // the next iteration's old_ll is this very value (same theta, same order)
             }
         }
@@ -1023,6 +1027,11 @@ __global__ void __launch_bounds__(WARPS * 32, 3) lsq_solve_kernel(SolveParams P)
             P.loglik[h.out_ev] = ll;
             P.ll_per_read[h.out_ev] = (sum_supports > 1E-5) ? __ddiv_rn(ll, sum_supports) : 0.0;
             P.iters[h.out_ev] = iters;
+            if (iters != 0u && P.flag_n != nullptr && em_stop_is_fragile(near, ll, n_total)) {
+                const uint32_t fi = atomicAdd(P.flag_n, 1u);  // replayed read by read in the reference's order
+                P.flag_list[fi] = x;
+                P.ev_flag[x] = fi + 1u;
+            }
         }
         __syncwarp();
     }
@@ -1077,7 +1086,7 @@ __global__ void __launch_bounds__(128) lsq_solve_small_kernel(SolveParams P) {
             return ll;
         };
         uint32_t iters = 0;
-        double ll = 0.0;
+        double ll = 0.0, near = 1E300;
         if (!any) {
         } else if (K == 1) {
             th0 = 1.0;
@@ -1105,9 +1114,16 @@ __global__ void __launch_bounds__(128) lsq_solve_small_kernel(SolveParams P) {
                 ll = loglik(th0, th1);
                 ++iters;
                 const double ratio = __ddiv_rn(ll_old, ll);
-                if (!(fabs(__dsub_rn(1.0, ratio)) > 1E-6) || iters >= P.max_iters) break;
+                const double tk = fabs(__dsub_rn(1.0, ratio));
+                near = fmin(near, fabs(tk - 1E-6));
+                if (!(tk > 1E-6) || iters >= P.max_iters) break;
                 ll_old = ll;
             }
+        }
+        if (iters != 0u && P.flag_n != nullptr && em_stop_is_fragile(near, ll, n_total)) {
+            const uint32_t fi = atomicAdd(P.flag_n, 1u);  // replayed read by read in the reference's order
+            P.flag_list[fi] = x;
+            P.ev_flag[x] = fi + 1u;
         }
         // standard error from the observed Fisher information of the free parameter theta_0
         // (theta_1 = 1 - theta_0): I = sum_c n_c (v_c0 - v_c1)^2 / s_c^2 with v_ck = G_k [k in c]
@@ -1143,6 +1159,157 @@ __global__ void __launch_bounds__(128) lsq_solve_small_kernel(SolveParams P) {
         P.ll_per_read[h.out_ev] = (sum_supports > 1E-5) ? __ddiv_rn(ll, sum_supports) : 0.0;
         P.iters[h.out_ev] = iters;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Order-exact replay of the EM for the events the solve kernels flagged (lsq_device_fn.cuh: order-exact EM).
+// lsq_collect_kernel walks the read set once more: a read with a block inside the span of a flagged event takes
+// the general path (filter, walk) and leaves one record per flagged event it is valid for; lsq_exact_kernel puts
+// an event's records in the reference's index order and replays the EM read by read.  Rare: an event is flagged
+// when its stop decision lies within summation-order noise of the threshold.
+// ---------------------------------------------------------------------------------------------
+struct CollectParams {
+    const uint32_t *ev_flag;      // [E] index + 1 of the event in the flag list, 0: not flagged
+    const int32_t *iv_start;      // merged spans of the flagged events, sorted by (chromosome, start) ...
+    const int32_t *iv_end;        // ... inclusive ends
+    const uint32_t *iv_chrom_off; // [n_chroms + 1] interval range per annotation chromosome
+    const uint64_t *seg_off;      // [n_flag + 1] record range per flagged event
+    uint32_t *seg_cur;            // [n_flag] records written so far
+    ExactRec *rec;
+    const uint8_t *strand_rank;   // file strand id -> rank of its string
+    uint32_t m;
+};
+
+__global__ void __launch_bounds__(SCAN_BLOCK) lsq_collect_kernel(const __grid_constant__ ScanParams P,
+                                                                 const __grid_constant__ CollectParams C) {
+    const Tables &T = P.T;
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint64_t n_groups = (P.n_reads + SCAN_GROUP - 1) / SCAN_GROUP;
+#pragma unroll 1
+    for (uint64_t g = (uint64_t)blockIdx.x * SCAN_WARPS + warp; g < n_groups; g += (uint64_t)gridDim.x * SCAN_WARPS) {
+        const uint64_t g0 = g * SCAN_GROUP, g1 = min(g0 + (uint64_t)SCAN_GROUP, P.n_reads);
+        const uint64_t r0 = g0 + 4u * lane;
+        uint32_t c4 = 0, o;
+        if (P.blk_cnt != nullptr) {
+            if (r0 < g1) {
+                c4 = __ldg(reinterpret_cast<const uint32_t *>(P.blk_cnt + r0));
+                if (r0 + 4 > g1) c4 &= 0xFFFFFFFFu >> (8u * (uint32_t)(r0 + 4 - g1));
+            }
+            const uint32_t mine = __vsadu4(c4, 0u);
+            uint32_t incl = mine;
+#pragma unroll
+            for (uint32_t d = 1; d < 32u; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            o = __ldg(P.sup_base + (g / SCAN_SUPER)) + __ldg(P.grp_base + g) + incl - mine;
+        } else {
+            o = r0 < g1 ? __ldg(P.blk_off + r0) : 0u;
+        }
+#pragma unroll 1
+        for (uint32_t k = 0; k < (uint32_t)SCAN_ITEMS; ++k) {
+            const uint64_t r = r0 + k;
+            if (r >= g1) break;
+            const uint32_t nraw = P.blk_cnt != nullptr ? (c4 >> (8u * k)) & 0xFFu : __ldg(P.blk_off + r + 1) - o;
+            const uint32_t base = o;
+            o += nraw;
+            if (nraw == 0u) continue;
+            const uint32_t cs0 = load_read_cs(P, r);
+            // cheap pre-check: does any block start inside the span of a flagged event?
+            bool hit = false;
+            for (uint32_t j = 0; j < nraw && !hit; ++j) {
+                const int2 b = load_block(P, base + j);
+                const uint32_t cs = (cs0 & 0x80000000u) ? __ldg(P.blk_cs + base + j) : cs0;
+                const uint32_t c = __ldg(P.chrom_remap + (cs & 0xFFFFu));
+                if (c == 0xFFFFFFFFu) continue;
+                uint32_t lo = __ldg(C.iv_chrom_off + c), hi = __ldg(C.iv_chrom_off + c + 1);
+                while (lo < hi) {  // last interval with start <= b.x
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (__ldg(C.iv_start + mid) <= b.x) lo = mid + 1;
+                    else hi = mid;
+                }
+                hit = lo > __ldg(C.iv_chrom_off + c) && b.x <= __ldg(C.iv_end + lo - 1);
+            }
+            if (!hit) continue;
+            const DirectCtx ctx{P, base};
+            const FilteredRead fr = filter_read_t(P, r, base, nraw, cs0, ctx);
+            if (fr.n == 0u || fr.piece == PIECE_NONE) continue;
+            ReadView rv;
+            rv.blk = P.ext + ext_slot(base, (uint32_t)r) + 1;
+            rv.b0 = fr.first;
+            rv.b1 = fr.n > 1u ? fr.second : make_int2(0, 0);
+            rv.b2 = fr.n > 2u ? rv.blk[2] : make_int2(0, 0);
+            rv.n = fr.n;
+            rv.ridx = (uint32_t)r;
+            uint32_t total = 0;
+            for (uint32_t b = 0; b < fr.n; ++b) {
+                const int2 blk = rv.block(b);
+                total += (uint32_t)(blk.y - blk.x);
+            }
+            const uint32_t e0 = __ldg(T.stab_off + fr.piece), e1 = __ldg(T.stab_off + fr.piece + 1);
+            for (uint32_t q = e0; q < e1; ++q) {
+                const uint32_t x = __ldg(&T.stab[q].x);
+                const uint32_t fi = __ldg(C.ev_flag + x);
+                if (fi == 0u) continue;
+                const EvHdr h = T.hdr[x];
+                uint32_t ml;
+                const uint64_t cm = eval_pair(P, h, T.seg + h.seg_off, T.fmask + h.form_off, rv, fr.strand, total, ml);
+                if (cm == 0ull) continue;
+                const uint64_t at = C.seg_off[fi - 1u] + atomicAdd(C.seg_cur + (fi - 1u), 1u);
+                if (at >= C.seg_off[fi]) continue;  // cannot happen: the segment holds the event's n_valid records
+                ExactRec e;
+                e.start = fr.first.x;
+                e.end = rv.last_end();
+                e.strand_rank = __ldg(C.strand_rank + fr.strand);
+                e.line_num = P.line_num ? __ldg(P.line_num + r) : (uint32_t)r + 1u;
+                e.mask = cm;
+                e.m = C.m;
+                e.pad = 0u;
+                C.rec[at] = e;
+            }
+        }
+    }
+}
+
+struct ExactParams {
+    uint32_t n_flag;
+    const uint32_t *flag_list;
+    const uint64_t *seg_off;
+    const uint32_t *seg_cur;
+    ExactRec *rec;
+};
+
+// One thread per flagged event (they are few): sort, replay, overwrite the event's results.
+__global__ void __launch_bounds__(32) lsq_exact_kernel(const __grid_constant__ SolveParams P, const __grid_constant__ ExactParams X) {
+    const uint32_t fi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (fi >= X.n_flag) return;
+    const uint32_t x = X.flag_list[fi];
+    const EvHdr h = P.T.hdr[x];
+    const uint32_t K = h.K, E = P.T.E;
+    ExactRec *rec = X.rec + X.seg_off[fi];
+    const uint32_t n = min((uint32_t)(X.seg_off[fi + 1] - X.seg_off[fi]), X.seg_cur[fi]);
+    double n_total = 0.0, sum_supports = 0.0;
+    for (uint32_t m = 0; m < P.M; ++m) {
+        const unsigned long long nv = P.n_valid[(size_t)m * E + h.out_ev];
+        if (nv) n_total = __dadd_rn(n_total, (double)nv);
+        sum_supports = __dadd_rn(sum_supports, (double)nv);
+    }
+    if ((double)n != n_total) return;  // injected class tables have no reads to replay: keep the class-collapsed result
+    exact_sort(rec, n);
+    double theta[LSQ_MAX_FORMS_PER_EVENT_DEV], old_theta[LSQ_MAX_FORMS_PER_EVENT_DEV];
+    double ll;
+    const uint32_t iters = exact_em(rec, n, n_total, K, P.G + h.form_off, P.T.F, theta, old_theta, ll, P.max_iters);
+    for (uint32_t k = 0; k < K; ++k) {  // RPKM (solve.cpp:809-821) and outputs, as the solve kernels
+        double r = 0.0;
+        for (uint32_t m = 0; m < P.M; ++m) r = __dadd_rn(r, __dmul_rn((double)P.bases[(size_t)m * E + x], theta[k]));
+        r = __ddiv_rn(r, __ddiv_rn((double)P.form_len[h.form_off + k], 1.0E3));
+        r = __ddiv_rn(r, P.total_read_mbases);
+        P.theta[h.out_form + k] = theta[k];
+        P.rpkm[h.out_form + k] = r;
+    }
+    P.loglik[h.out_ev] = ll;
+    P.ll_per_read[h.out_ev] = (sum_supports > 1E-5) ? __ddiv_rn(ll, sum_supports) : 0.0;
+    P.iters[h.out_ev] = iters;
 }
 
 }  // namespace lsq

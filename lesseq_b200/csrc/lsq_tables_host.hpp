@@ -19,6 +19,7 @@ struct HostTables {
     uint64_t slot_total = 0;
     uint32_t max_forms = 0;
     std::vector<uint32_t> order;  // internal -> output event index
+    std::vector<uint32_t> ev_chrom;  // chromosome id per event, internal order
     std::vector<EvHdr> hdr;       // internal order + sentinel
     std::vector<int2> seg;
     std::vector<uint64_t> fmask, form_len, form_seg_len;
@@ -208,6 +209,7 @@ inline int build_host_tables(const lsq_event_tables *t, HostTables &H, std::stri
     });
     std::vector<lsq::EvHdr> &hdr = H.hdr;
     hdr.assign(E + 1, lsq::EvHdr());
+    H.ev_chrom.clear();
     H.max_forms = 0;
     std::vector<int2> &seg = H.seg;
     std::vector<uint64_t> &fmask = H.fmask, &form_len = H.form_len, &form_seg_len = H.form_seg_len;
@@ -230,6 +232,7 @@ inline int build_host_tables(const lsq_event_tables *t, HostTables &H, std::stri
         if (t->ev_ge[e] == INT32_MAX) return tfail(err, LSQ_ERR_RANGE, "event end at INT32_MAX");
         h.gs = t->ev_gs[e];
         h.ge = t->ev_ge[e];
+        H.ev_chrom.push_back(t->ev_chrom[e]);
         h.seg_off = (uint32_t)seg.size();
         h.form_off = (uint32_t)fmask.size();
         h.S = (uint16_t)S;

@@ -234,6 +234,10 @@ struct SolveParams {
     int small_enabled;             // events with K <= 2 are solved by lsq_solve_small_kernel
     unsigned int *work_counter;    // dynamic event fetch of lsq_solve_small_kernel
     unsigned long long *pairs_valid;  // finalize: total valid (read, event) pairs (statistics)
+    // events whose stop decision is fragile (em_stop_is_fragile): replayed read by read by lsq_exact_kernel
+    uint32_t *flag_n;     // null: no flagging
+    uint32_t *flag_list;  // [E] internal event ids
+    uint32_t *ev_flag;    // [E] index + 1 in flag_list, 0: not flagged
 };
 
 }  // namespace lsq

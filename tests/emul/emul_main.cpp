@@ -273,6 +273,15 @@ int main(int argc, char **argv) {
     std::vector<std::vector<std::map<uint64_t, uint64_t> > > hist(M, std::vector<std::map<uint64_t, uint64_t> >(E));
     std::vector<std::vector<uint64_t> > bases(M, std::vector<uint64_t>(E, 0));
     std::vector<std::vector<double> > Gm(M);
+    struct SetCtx {  // what the exact replay needs to walk the reads of a set again
+        std::vector<uint32_t> remap;
+        std::vector<uint4> fmeta;
+        std::vector<uint8_t> stbl;
+        std::vector<int2> ext2;
+        std::vector<uint32_t> strand_rank;
+        ScanParams FP;
+    };
+    std::vector<SetCtx> sctx(M);
     for (uint32_t m = 0; m < M; ++m) {
         uint32_t type;
         if (sets[m].type == "MEDIUM_READ") type = LSQ_READ_MEDIUM;
@@ -281,15 +290,22 @@ int main(int argc, char **argv) {
         form_weights(H, type, sets[m].len, Gm[m]);
         const lsqh_reads &R = parsed[m];
         const size_t n = R.read_cs.size(), nb = R.blk_cs.size();
-        std::vector<uint32_t> remap(std::max<size_t>(R.chroms.names.size(), 1), 0xFFFFFFFFu);
+        std::vector<uint32_t> &remap = sctx[m].remap;
+        remap.assign(std::max<size_t>(R.chroms.names.size(), 1), 0xFFFFFFFFu);
         for (size_t i = 0; i < R.chroms.names.size(); ++i) {
             auto it = chrom_id.find(R.chroms.names[i]);
             if (it != chrom_id.end()) remap[i] = it->second;
         }
-        std::vector<uint8_t> stbl;
+        std::vector<uint8_t> &stbl = sctx[m].stbl;
         strand_table(R.strand_ptrs.data(), (uint32_t)R.strand_ptrs.size(), ann_strands, stbl);
-        std::vector<int2> ext2(nb + 2 * n + 2);
-        ScanParams FP{};
+        std::vector<int2> &ext2 = sctx[m].ext2;
+        ext2.assign(nb + 2 * n + 2, make_int2(0, 0));
+        sctx[m].strand_rank.assign(R.strands.names.size(), 0);
+        for (size_t i = 0; i < R.strands.names.size(); ++i)
+            for (size_t j = 0; j < R.strands.names.size(); ++j)
+                if (R.strands.names[j] < R.strands.names[i]) sctx[m].strand_rank[i]++;
+        ScanParams &FP = sctx[m].FP;
+        FP = ScanParams{};
         FP.T = T;
         FP.n_reads = n;
         FP.blk_off = R.blk_off.data();
@@ -297,7 +313,8 @@ int main(int argc, char **argv) {
         FP.read_cs = R.read_cs.data();
         FP.blk_cs = R.any_mixed ? R.blk_cs.data() : nullptr;
         FP.chrom_remap = remap.data();
-        std::vector<uint4> fmeta(remap.size(), make_uint4(0u, 0u, 0u, 0u));
+        std::vector<uint4> &fmeta = sctx[m].fmeta;
+        fmeta.assign(remap.size(), make_uint4(0u, 0u, 0u, 0u));
         for (size_t i = 0; i < remap.size(); ++i)
             if (remap[i] != 0xFFFFFFFFu) fmeta[i] = H.chrom_meta[remap[i]];
         FP.file_meta = fmeta.data();
@@ -433,6 +450,7 @@ int main(int argc, char **argv) {
                 ll = loglik(theta);
             } else {
                 double ll_old = loglik(theta);
+                double near = 1e300;
                 while (true) {
                     std::vector<double> old_t = theta;
                     for (uint32_t k = 0; k < K; ++k) {
@@ -451,8 +469,57 @@ int main(int argc, char **argv) {
                         theta[k] = z / n_total;
                     }
                     ll = loglik(theta);
-                    if (!(fabs(1.0 - ll_old / ll) > 1E-6)) break;
+                    const double tk = fabs(1.0 - ll_old / ll);
+                    if (fabs(tk - 1E-6) < near) near = fabs(tk - 1E-6);
+                    if (!(tk > 1E-6)) break;
                     ll_old = ll;
+                }
+                if (em_stop_is_fragile(near, ll, n_total) && !getenv("LSQ_EMUL_NO_EXACT")) {
+                    // lsq_collect_kernel + lsq_exact_kernel: the event's valid reads in the reference's index
+                    // order, then the EM read by read
+                    std::vector<ExactRec> recs;
+                    for (uint32_t m = 0; m < M; ++m) {
+                        const lsqh_reads &R = parsed[m];
+                        const ScanParams &FP = sctx[m].FP;
+                        const size_t n = R.read_cs.size();
+                        for (size_t r = 0; r < n; ++r) {
+                            if (n_shards > 1 && !((owner_mask[m][r] >> shard) & 1ull)) continue;
+                            const uint32_t base = R.blk_off[r], nraw = R.blk_off[r + 1] - base;
+                            if (nraw == 0) continue;
+                            const DirectCtx dctx{FP, base};
+                            const FilteredRead fr = filter_read_t(FP, r, base, nraw, load_read_cs(FP, r), dctx);
+                            if (fr.n == 0u || fr.piece == PIECE_NONE) continue;
+                            ReadView rv;
+                            rv.blk = FP.ext + ext_slot(base, (uint32_t)r) + 1;
+                            rv.b0 = fr.first;
+                            rv.b1 = fr.n > 1u ? fr.second : make_int2(0, 0);
+                            rv.b2 = fr.n > 2u ? rv.blk[2] : make_int2(0, 0);
+                            rv.n = fr.n;
+                            rv.ridx = (uint32_t)r;
+                            uint32_t total = 0;
+                            for (uint32_t b = 0; b < fr.n; ++b) total += (uint32_t)(rv.block(b).y - rv.block(b).x);
+                            for (uint32_t q = T.stab_off[fr.piece]; q < T.stab_off[fr.piece + 1]; ++q) {
+                                if (T.stab[q].x != x) continue;
+                                uint32_t ml = 0;
+                                const uint64_t cm = eval_pair(FP, h, T.seg + h.seg_off, T.fmask + h.form_off, rv, fr.strand, total, ml);
+                                if (!cm) continue;
+                                ExactRec e;
+                                e.start = fr.first.x;
+                                e.end = rv.last_end();
+                                e.strand_rank = sctx[m].strand_rank[fr.strand];
+                                e.line_num = R.line_num[r];
+                                e.mask = cm;
+                                e.m = m;
+                                e.pad = 0;
+                                recs.push_back(e);
+                            }
+                        }
+                    }
+                    exact_sort(recs.data(), (uint32_t)recs.size());
+                    std::vector<double> Gflat((size_t)M * K), old_t(K);
+                    for (uint32_t m = 0; m < M; ++m)
+                        for (uint32_t k = 0; k < K; ++k) Gflat[(size_t)m * K + k] = Gm[m][h.form_off + k];
+                    exact_em(recs.data(), (uint32_t)recs.size(), n_total, K, Gflat.data(), K, theta.data(), old_t.data(), ll, 10000000u);
                 }
             }
             double mb = 0.0;
