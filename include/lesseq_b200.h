@@ -221,6 +221,9 @@ typedef struct lsq_device_results {
 int lsq_get_device_results(lsq_ctx *ctx, lsq_device_results *out);
 
 int lsq_get_timings(lsq_ctx *ctx, lsq_timings *out);
+/* FP64 FMA throughput of the context's device in TFLOP/s (a DFMA micro-benchmark, ~10 ms): the measured peak the
+ * solve kernels' arithmetic rate is quoted against. */
+int lsq_measure_fp64_peak(lsq_ctx *ctx, double *tflops);
 
 /* ---------------------------------------------------------------------------------------------
  * Multi-GPU: gene-range shards with reads bucketed per shard.  The reference scales out by running one

@@ -104,6 +104,7 @@ SYMBOLS = {
     "lsq_get_solve": (C.c_int, [C.c_void_p, C.POINTER(SolveOut)]),
     "lsq_get_timings": (C.c_int, [C.c_void_p, C.POINTER(Timings)]),
     "lsq_get_device_results": (C.c_int, [C.c_void_p, C.POINTER(DeviceResults)]),
+    "lsq_measure_fp64_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "lsq_comm_unique_id": (C.c_int, [C.c_void_p]),
     "lsq_comm_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "lsq_comm_attach": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),

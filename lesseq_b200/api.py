@@ -330,6 +330,12 @@ class Context:
     def sync(self):
         check(self._lib.lsq_ctx_sync(self._c))
 
+    def fp64_peak_tflops(self):
+        """Measured FP64 FMA throughput of the device (lsq_measure_fp64_peak)."""
+        v = C.c_double()
+        check(self._lib.lsq_measure_fp64_peak(self._c, C.byref(v)))
+        return float(v.value)
+
     def timings(self):
         t = _lib.Timings()
         check(self._lib.lsq_get_timings(self._c, C.byref(t)))

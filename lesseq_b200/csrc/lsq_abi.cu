@@ -120,6 +120,7 @@ struct lsq_ctx {
     DevBuf d_ext, d_scratch, d_gen_list;  // d_scratch: signature counters | hash | general-list length (cleared per read set)
     uint32_t scan_flags = 0;
     DevBuf d_n_valid, d_bases_out, d_iso, d_theta, d_rpkm, d_se, d_ll, d_llpr, d_iters;
+    DevBuf d_mid;  // work order of lsq_solve_mid_kernel
     DevBuf d_flag, d_exact, d_exact_rec;  // order-exact EM replay: flag list + per-event flags; spans, segments; records
     uint32_t exact_events = 0;            // events replayed by the last lsq_solve (statistics)
     bool counted = false, finalized = false, solved = false;
@@ -967,6 +968,28 @@ int lsq_solve(lsq_ctx *c, const double *total_read_bases, uint32_t n_methods) {
         c->tm.launches++;
     }
     if (c->E && (!small || c->H.max_forms > 2)) {
+        // events with up to 16 forms: one thread per event; the warp-per-event kernel then adds their standard errors and
+        // solves the larger events
+        P.mid_enabled = getenv("LSQ_NO_MID_SOLVE") ? 0 : 1;
+        if (P.mid_enabled) {
+            P.work_counter = P.work_counter + 1;  // its own fetch counter
+            LSQ_CUDA(cudaMemsetAsync(P.work_counter, 0, sizeof(unsigned int), s));
+            // work order: counting sort of the events by (classes, forms)
+            LSQ_CUDA(c->d_mid.ensure(((size_t)lsq::MID_KEY_BINS + 4 + std::max<uint32_t>(c->E, 1)) * 4));
+            uint32_t *hist = c->d_mid.as<uint32_t>(), *n_mid = hist + lsq::MID_KEY_BINS, *order = n_mid + 4;
+            LSQ_CUDA(cudaMemsetAsync(hist, 0, (lsq::MID_KEY_BINS + 4) * 4, s));
+            lsq::lsq_mid_key_kernel<<<(c->E + 255) / 256, 256, 0, s>>>(P, hist);
+            lsq::lsq_mid_scan_kernel<<<1, 1024, 0, s>>>(hist, n_mid);
+            lsq::lsq_mid_scatter_kernel<<<(c->E + 255) / 256, 256, 0, s>>>(P, hist, order);
+            LSQ_CUDA(cudaGetLastError());
+            c->tm.launches += 3;
+            P.mid_order = order;
+            P.mid_n = n_mid;
+            unsigned grid = std::min<unsigned>((c->E + lsq::MID_BLOCK - 1) / lsq::MID_BLOCK, (unsigned)c->n_sms * 4u);
+            lsq::lsq_solve_mid_kernel<<<grid, lsq::MID_BLOCK, 0, s>>>(P);
+            LSQ_CUDA(cudaGetLastError());
+            c->tm.launches++;
+        }
         constexpr int WARPS = 8;
         unsigned grid = std::min<unsigned>((c->E + WARPS - 1) / WARPS, (unsigned)c->n_sms * 8u);
         lsq::lsq_solve_kernel<WARPS><<<grid, WARPS * 32, 0, s>>>(P);
@@ -1018,6 +1041,24 @@ int lsq_get_device_results(lsq_ctx *c, lsq_device_results *o) {
     o->loglik = c->d_ll.as<double>();
     o->ll_per_read = c->d_llpr.as<double>();
     o->iters = c->d_iters.as<uint32_t>();
+    return LSQ_OK;
+}
+
+int lsq_measure_fp64_peak(lsq_ctx *c, double *tflops) {
+    if (!c || !tflops) return fail(LSQ_ERR_ARG, "lsq_measure_fp64_peak: null argument");
+    LSQ_CUDA(cudaSetDevice(c->device));
+    const int blocks = c->n_sms * 8, iters = 100000;
+    DevBuf out;
+    LSQ_CUDA(out.ensure((size_t)blocks * 256 * 8));
+    cudaStream_t s = c->stream;
+    lsq::lsq_dfma_kernel<<<blocks, 256, 0, s>>>(out.as<double>(), 1000);  // warm-up
+    LSQ_CUDA(cudaEventRecord(c->ev[2], s));
+    lsq::lsq_dfma_kernel<<<blocks, 256, 0, s>>>(out.as<double>(), iters);
+    LSQ_CUDA(cudaEventRecord(c->ev[3], s));
+    LSQ_CUDA(cudaStreamSynchronize(s));
+    float ms = 0.f;
+    LSQ_CUDA(cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]));
+    *tflops = 2.0 * blocks * 256.0 * (double)iters * 8.0 / (ms * 1e-3) / 1e12;
     return LSQ_OK;
 }
 

@@ -762,6 +762,8 @@ __device__ __forceinline__ double class_prob(uint64_t mk, const double *theta, c
 }
 
 constexpr int SE_MAX_FORMS = 16;  // standard errors are computed for events with at most 16 forms
+constexpr int MID_MAX_FORMS = 16; // events with at most 16 forms: one thread per event (lsq_solve_mid_kernel)
+constexpr int MID_BLOCK = 128;
 
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 3) lsq_solve_kernel(SolveParams P) {
@@ -774,6 +776,9 @@ __global__ void __launch_bounds__(WARPS * 32, 3) lsq_solve_kernel(SolveParams P)
         const EvHdr h = P.T.hdr[x];
         const uint32_t K = h.K;
         if (P.small_enabled && K <= 2) continue;  // solved by lsq_solve_small_kernel
+        // events with at most MID_MAX_FORMS forms were solved by lsq_solve_mid_kernel: only their standard errors are left
+        const bool em_done = P.mid_enabled && K <= (uint32_t)MID_MAX_FORMS;
+        if (em_done && K == 1u) continue;  // se = 0, written by the mid kernel
         double *th_old = s_theta[w][0], *th_new = s_theta[w][1];
         // N = total number of valid reads (read.h:599-602), sum of supports (solve.cpp:826)
         double n_total = 0.0, sum_supports = 0.0;
@@ -849,7 +854,11 @@ __global__ void __launch_bounds__(WARPS * 32, 3) lsq_solve_kernel(SolveParams P)
             }
             return warp_sum(part);
         };
-        if (!any) {
+        if (em_done) {
+            for (uint32_t k = lane; k < K; k += 32) th_new[k] = P.theta[h.out_form + k];
+            __syncwarp();
+            if (any && cached) refresh(th_new);  // s_c at the final theta, for the information matrix
+        } else if (!any) {
             // no valid read in any read set: uniform theta, log-likelihood 0 (solve.cpp:798-800)
         } else if (K == 1) {
             if (lane == 0) th_new[0] = 1.0;  // solve.cpp:801-802
@@ -1012,6 +1021,7 @@ __global__ void __launch_bounds__(WARPS * 32, 3) lsq_solve_kernel(SolveParams P)
             }
         }
         __syncwarp();
+        if (em_done) continue;  // theta, RPKM, log-likelihood and iterations were written by the mid kernel
         // RPKM (solve.cpp:809-821) and outputs
         for (uint32_t k = lane; k < K; k += 32) {
             double th = th_new[k];
@@ -1034,6 +1044,160 @@ __global__ void __launch_bounds__(WARPS * 32, 3) lsq_solve_kernel(SolveParams P)
             }
         }
         __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Work order of lsq_solve_mid_kernel: events sorted by (classes, forms), so that the 32 events a warp works on at
+// any time run class loops of the same length (lanes of one warp share an instruction stream).  Counting sort:
+// lsq_mid_key_kernel histograms the keys, one block scans the 2^12 bins, lsq_mid_scatter_kernel places the events.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t MID_KEY_BINS = 4096;  // key = min(classes, 255) << 4 | (forms - 1)
+__device__ __forceinline__ uint32_t mid_key(const SolveParams &P, const EvHdr &h) {
+    uint32_t c = 0;
+    for (uint32_t m = 0; m < P.M; ++m) {
+        if (P.inj_off[m]) c += (uint32_t)(P.inj_off[m][h.out_ev + 1] - P.inj_off[m][h.out_ev]);
+        else c += h.slot_cap;  // dense or hashed table: its capacity bounds the loop length
+    }
+    return (min(c, 255u) << 4) | ((h.K - 1u) & 15u);
+}
+__global__ void __launch_bounds__(256) lsq_mid_key_kernel(const __grid_constant__ SolveParams P, uint32_t *hist) {
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= P.T.E) return;
+    const EvHdr h = P.T.hdr[x];
+    if (h.K > (uint32_t)MID_MAX_FORMS) return;
+    atomicAdd(hist + mid_key(P, h), 1u);
+}
+__global__ void __launch_bounds__(1024) lsq_mid_scan_kernel(uint32_t *hist, uint32_t *n_mid) {  // exclusive scan of MID_KEY_BINS bins
+    __shared__ uint32_t s_w[32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    uint32_t v[4], sum = 0;
+    for (int j = 0; j < 4; ++j) {
+        v[j] = hist[tid * 4 + j];
+        sum += v[j];
+    }
+    uint32_t incl = sum;
+#pragma unroll
+    for (uint32_t d = 1; d < 32u; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31u) s_w[warp] = incl;
+    __syncthreads();
+    uint32_t before = 0;
+    for (uint32_t w = 0; w < warp; ++w) before += s_w[w];
+    uint32_t run = before + incl - sum;
+    for (int j = 0; j < 4; ++j) {
+        hist[tid * 4 + j] = run;
+        run += v[j];
+    }
+    if (tid == 1023u) *n_mid = run;
+}
+__global__ void __launch_bounds__(256) lsq_mid_scatter_kernel(const __grid_constant__ SolveParams P, uint32_t *cursor, uint32_t *order) {
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= P.T.E) return;
+    const EvHdr h = P.T.hdr[x];
+    if (h.K > (uint32_t)MID_MAX_FORMS) return;
+    order[atomicAdd(cursor + mid_key(P, h), 1u)] = x;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Solve kernel for events with at most MID_MAX_FORMS forms: one THREAD per event, dynamic event fetch (a lane takes
+// the next event as soon as its own has converged, so the spread of iteration counts -- mean 42, tail in the
+// thousands at BASELINE config 5 -- idles nobody).  One pass over the event's classes per iteration: the class
+// probability s_c = sum_k theta_k G_k [k in c] is formed once and gives both the log-likelihood term n_c log s_c and,
+// through t_c = n_c / s_c, every form's numerator z_k += theta_k G_k t_c -- so the pass that evaluates ll(theta_i)
+// for the stop rule also yields theta_{i+1} (read.h:592-660).  theta, theta*G and the numerators live in shared
+// memory, [form][thread], so the dynamic form index costs no local memory and lanes never conflict.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(MID_BLOCK) lsq_solve_mid_kernel(const __grid_constant__ SolveParams P) {
+    __shared__ double s_th[MID_MAX_FORMS][MID_BLOCK], s_w[MID_MAX_FORMS][MID_BLOCK], s_z[MID_MAX_FORMS][MID_BLOCK];
+    const uint32_t E = P.T.E, t = threadIdx.x;
+    while (true) {
+        const uint32_t wi = atomicAdd(P.work_counter, 1u);
+        if (wi >= *P.mid_n) return;
+        const uint32_t x = P.mid_order[wi];  // events in (classes, forms) order: see lsq_mid_key_kernel
+        const EvHdr h = P.T.hdr[x];
+        const uint32_t K = h.K;
+        if (P.small_enabled && K <= 2u) continue;
+        double n_total = 0.0, sum_supports = 0.0;
+        bool any = false;
+        for (uint32_t m = 0; m < P.M; ++m) {
+            const unsigned long long nv = P.n_valid[(size_t)m * E + h.out_ev];
+            if (nv) {
+                any = true;
+                n_total = __dadd_rn(n_total, (double)nv);
+            }
+            sum_supports = __dadd_rn(sum_supports, (double)nv);
+        }
+        // one pass at the theta in s_th: returns ll(theta), leaves the numerators of the next theta in s_z
+        auto pass = [&]() {
+            for (uint32_t k = 0; k < K; ++k) s_z[k][t] = 0.0;
+            double ll = 0.0;
+            for (uint32_t m = 0; m < P.M; ++m) {
+                const ClassRange cr = class_range(P, h, m);
+                const double *G = P.G + (size_t)m * P.T.F + h.form_off;
+                for (uint32_t k = 0; k < K; ++k) s_w[k][t] = __dmul_rn(s_th[k][t], __ldg(G + k));
+#pragma unroll 2
+                for (uint32_t i = 0; i < cr.n; ++i) {
+                    const unsigned long long c = __ldg(cr.cnt + i);
+                    if (!c) continue;
+                    const uint64_t mk = cr.mask ? __ldg(cr.mask + i) : (uint64_t)(i + 1u);
+                    double s = 0.0;
+                    for (uint64_t b = mk; b; b &= b - 1ull) s = __dadd_rn(s, s_w[__ffsll((long long)b) - 1][t]);
+                    const double n_c = (double)c;
+                    ll = __dadd_rn(ll, __dmul_rn(n_c, log(s)));
+                    if (s > 0.0) {
+                        const double tc = __ddiv_rn(n_c, s);
+                        for (uint64_t b = mk; b; b &= b - 1ull) {
+                            const int k = __ffsll((long long)b) - 1;
+                            const double wk = s_w[k][t];
+                            if (wk > 0.0) s_z[k][t] = __dadd_rn(s_z[k][t], __dmul_rn(wk, tc));
+                        }
+                    }
+                }
+            }
+            return ll;
+        };
+        for (uint32_t k = 0; k < K; ++k) s_th[k][t] = __ddiv_rn(1.0, (double)K);
+        uint32_t iters = 0;
+        double ll = 0.0, near = 1E300;
+        if (!any) {
+            // no valid read in any read set: uniform theta, log-likelihood 0 (solve.cpp:798-800)
+        } else if (K == 1u) {
+            s_th[0][t] = 1.0;  // solve.cpp:801-802
+            ll = pass();
+        } else {
+            double ll_old = pass();
+            while (true) {  // read.h:647-659
+                for (uint32_t k = 0; k < K; ++k) s_th[k][t] = __ddiv_rn(s_z[k][t], n_total);
+                ll = pass();
+                ++iters;
+                const double tk = fabs(__dsub_rn(1.0, __ddiv_rn(ll_old, ll)));
+                near = fmin(near, fabs(tk - 1E-6));
+                if (!(tk > 1E-6) || iters >= P.max_iters) break;
+                ll_old = ll;
+            }
+        }
+        if (iters != 0u && P.flag_n != nullptr && em_stop_is_fragile(near, ll, n_total)) {
+            const uint32_t fi = atomicAdd(P.flag_n, 1u);  // replayed read by read in the reference's order
+            P.flag_list[fi] = x;
+            P.ev_flag[x] = fi + 1u;
+        }
+        for (uint32_t k = 0; k < K; ++k) {  // RPKM (solve.cpp:809-821) and outputs
+            const double th = s_th[k][t];
+            double r = 0.0;
+            for (uint32_t m = 0; m < P.M; ++m) r = __dadd_rn(r, __dmul_rn((double)P.bases[(size_t)m * E + x], th));
+            r = __ddiv_rn(r, __ddiv_rn((double)P.form_len[h.form_off + k], 1.0E3));
+            r = __ddiv_rn(r, P.total_read_mbases);
+            P.theta[h.out_form + k] = th;
+            P.rpkm[h.out_form + k] = r;
+            if (K == 1u) P.se[h.out_form] = 0.0;
+            else if (!any) P.se[h.out_form + k] = nan("");
+        }
+        P.loglik[h.out_ev] = ll;
+        P.ll_per_read[h.out_ev] = (sum_supports > 1E-5) ? __ddiv_rn(ll, sum_supports) : 0.0;
+        P.iters[h.out_ev] = iters;
     }
 }
 
@@ -1310,6 +1474,17 @@ __global__ void __launch_bounds__(32) lsq_exact_kernel(const __grid_constant__ S
     P.loglik[h.out_ev] = ll;
     P.ll_per_read[h.out_ev] = (sum_supports > 1E-5) ? __ddiv_rn(ll, sum_supports) : 0.0;
     P.iters[h.out_ev] = iters;
+}
+
+// FP64 FMA throughput of the device (8 independent chains per thread): the denominator of the solve roofline.
+__global__ void __launch_bounds__(256) lsq_dfma_kernel(double *out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
 }  // namespace lsq

@@ -232,6 +232,9 @@ struct SolveParams {
     uint32_t max_iters;
     int with_se;
     int small_enabled;             // events with K <= 2 are solved by lsq_solve_small_kernel
+    int mid_enabled;               // events with K <= 16 are solved by lsq_solve_mid_kernel (the warp kernel adds their se)
+    const uint32_t *mid_order;     // those events sorted by (classes, forms)
+    const uint32_t *mid_n;
     unsigned int *work_counter;    // dynamic event fetch of lsq_solve_small_kernel
     unsigned long long *pairs_valid;  // finalize: total valid (read, event) pairs (statistics)
     // events whose stop decision is fragile (em_stop_is_fragile): replayed read by read by lsq_exact_kernel
