@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--genes", type=int, default=None)
     ap.add_argument("--sample-reads", type=int, default=300000, help="reads of the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cli-reads", type=int, default=10_000_000, help="reads of the MRF text the drop-in executables are timed on (0: skip)")
     ap.add_argument("--wide-wire", action="store_true", help="e2e: wide arrays (blk, read_cs) instead of the compact wire format")
     ap.add_argument("--no-stream", action="store_true", help="e2e: copy everything before the filter starts (no LSQ_READS_STREAM)")
     return ap.parse_args()
@@ -173,6 +174,68 @@ def cpu_reference_once(fp, mp, R, rp, trb, n_events, procs):
             if p.wait() != 0:
                 raise RuntimeError("CPU reference process failed")
     return time.time() - t0, kind
+
+
+def cli_e2e(args, tmp, torch):
+    """Wall clock of the drop-in executables (lesseq_b200/bin/count + solve: text in, table out) on an MRF_SINGLE text of
+    `--cli-reads` reads of the workload, next to the reference's own binaries on the first `--sample-reads` lines of the
+    SAME text (the reference needs ~20 s per million reads; its rate is what is compared)."""
+    from lesseq_b200 import api, synth
+    from oracle import runner
+    A, R, _ = synth.make_config(args.workload, n_genes=args.genes)
+    fp, mp, rp, sp = (os.path.join(tmp, x) for x in ("cli.interval", "cli.map", "cli.mrf", "cli_sample.mrf"))
+    A.write(fp, mp)
+    n = args.cli_reads
+    reads = synth.make_reads(A, n, R, 4321, device="cuda")
+    host = {k: reads[k].cpu().numpy() for k in ("blk_off", "blk", "read_cs", "line_num")}
+    trb = reads["total_read_bases"]
+    hr = api.Reads.from_numpy(host["blk_off"], host["blk"], host["read_cs"], host["line_num"], reads["chrom_names"], reads["strand_names"])
+    t0 = time.time()
+    hr.write_mrf(rp)
+    t_write = time.time() - t0
+    with open(rp) as f, open(sp, "w") as g:  # the bounded sample: header + the first sample-reads lines
+        for i, line in enumerate(f):
+            if i > args.sample_reads:
+                break
+            g.write(line)
+    size = os.path.getsize(rp)
+    head = ["0", "bench", os.path.join(tmp, "o_"), "LH_GENE_TXT", fp, "UCSC_GENE2ISOFORM", mp, "0", str(10 ** 9), "MRF_SINGLE", "SHORT_READ", str(R)]
+    walls, rows = {}, {}
+    for prog in ("count", "solve"):
+        a = head + [rp] + ([repr(trb)] if prog == "solve" else [])
+        best = None
+        for _ in range(2):  # first run pays the page-cache / driver warm-up; the second is reported
+            t0 = time.time()
+            rc, out, err = api.run_program(prog, a)
+            dt = time.time() - t0
+            if rc != 0:
+                raise RuntimeError("bin/%s failed: %s" % (prog, err[-300:]))
+            best = dt
+        walls[prog] = best
+        rows[prog] = out.count("\n")
+    ref = {}
+    if runner.ref_available() or runner.build_ref():
+        for prog in ("count", "solve"):
+            a = head + [sp] + ([repr(trb * args.sample_reads / n)] if prog == "solve" else [])
+            t0 = time.time()
+            rc, out, err = runner.run_ref(prog, a, prec17=False)
+            ref[prog] = time.time() - t0
+            if rc != 0:
+                raise RuntimeError("reference %s failed" % prog)
+    ours_rate = n / (walls["count"] + walls["solve"])
+    res = {"reads": n, "text_bytes": size, "wall_s": {k: round(v, 3) for k, v in walls.items()}, "reads_per_s": ours_rate,
+           "text_GB_per_s_count": size / walls["count"] / 1e9, "host_cores": os.cpu_count(), "table_rows": rows["count"],
+           "note": "bin/count then bin/solve, each: parse the text on all host cores (lsqh_mrf_parse) while a helper thread creates the CUDA "
+                   "context and uploads the event tables, compact host->device copy, scan + expand + general (+ solve), print the table; "
+                   "second of two runs (warm page cache); writing the text took %.1f s (not counted)" % t_write}
+    if ref:
+        ref_rate = args.sample_reads / (ref["count"] + ref["solve"])
+        res["reference"] = {"reads": args.sample_reads, "wall_s": {k: round(v, 3) for k, v in ref.items()}, "reads_per_s": ref_rate,
+                            "note": "the reference's own count + solve binaries (one thread each, as shipped) on the first %d lines of the same text" % args.sample_reads}
+        res["speedup_reads_per_s"] = ours_rate / ref_rate
+    del reads
+    torch.cuda.empty_cache()
+    return res
 
 
 def run_reference(args):
@@ -469,6 +532,12 @@ def run_ours(args):
                               % (args.sample_reads, len(A2.ev_gene), dt)}
             except Exception as ex:  # the oracle always exists; report why it could not run
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %s" % ex}
+            if args.cli_reads and args.workload != "C5":
+                try:
+                    ctx.close()
+                    line["cli_e2e"] = cli_e2e(args, tmp, torch)
+                except Exception as ex:
+                    line["cli_e2e"] = {"failed": str(ex)[:300]}
         print(json.dumps(line), flush=True)
     if world == 1:
         ctx.close()

@@ -291,6 +291,9 @@ const char *lsqh_event_name(const lsqh_annotation *a, uint32_t e);
 const char *lsqh_form_name(const lsqh_annotation *a, uint32_t f);
 uint64_t lsqh_form_length(const lsqh_annotation *a, uint32_t f);
 
+/* Writes host reads in the wide layout as MRF_SINGLE text (header line + one line per read, the format of
+ * count.cpp:279-327): the inverse of lsqh_mrf_parse, for test and benchmark inputs. */
+int lsqh_write_mrf(const lsq_packed_reads *reads, const char *path);
 /* Parses an MRF_SINGLE file into packed reads (count.cpp:279-339 without the filter). */
 int lsqh_mrf_parse(const char *path, lsqh_reads **out);
 void lsqh_reads_free(lsqh_reads *r);

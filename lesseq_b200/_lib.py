@@ -123,6 +123,7 @@ SYMBOLS = {
     "lsqh_event_name": (C.c_char_p, [C.c_void_p, C.c_uint32]),
     "lsqh_form_name": (C.c_char_p, [C.c_void_p, C.c_uint32]),
     "lsqh_form_length": (C.c_uint64, [C.c_void_p, C.c_uint32]),
+    "lsqh_write_mrf": (C.c_int, [C.POINTER(PackedReads), C.c_char_p]),
     "lsqh_mrf_parse": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "lsqh_reads_free": (None, [C.c_void_p]),
     "lsqh_reads_compact": (C.c_int, [C.c_void_p]),

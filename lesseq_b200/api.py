@@ -219,6 +219,10 @@ class Reads:
         self._names(chrom_names, strand_names)
         return self
 
+    def write_mrf(self, path):
+        """Write host reads in the wide layout as MRF_SINGLE text (lsqh_write_mrf)."""
+        check(self._lib.lsqh_write_mrf(C.byref(self.view), str(path).encode()))
+
     @property
     def n_reads(self):
         return int(self.view.n_reads)

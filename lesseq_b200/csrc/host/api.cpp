@@ -8,6 +8,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <thread>
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
@@ -288,6 +289,62 @@ int run_program(bool solve, int argc, char **argv) {
     int prec = 6;
     if (const char *p = getenv("LSQ_PRECISION")) prec = atoi(p);
 
+    // The read text does not depend on the annotation: it is parsed by a background thread from the start (the parser
+    // itself uses every core), while this thread loads the annotation and a third one sets up the device.  Errors are
+    // reported where the reference would meet them, so the outcomes are recorded and looked at in its order.
+    const uint32_t M = (uint32_t)sets.size();
+    struct Loaded {
+        int rc = 0;           // LSQ_* of the parser / loader
+        int stage = 0;        // 0 ok, 1 file not openable, 2 unknown format, 3 parse / load failure
+        bool from_pack = false;
+        std::string err, warn;
+    };
+    std::vector<lsqh_reads *> reads(M, nullptr);
+    std::vector<Loaded> loaded(M);
+    std::thread read_thread([&]() {
+        for (uint32_t m = 0; m < M; ++m) {
+            Loaded &L = loaded[m];
+            if (!file_openable(sets[m].path)) {
+                L.stage = 1;
+                break;  // the reference stops here
+            }
+            if (sets[m].format != "MRF_SINGLE") {
+                L.stage = 2;
+                break;
+            }
+            // opt-in packed cache next to the text file: `solve` reuses what `count` parsed
+            const char *cache = getenv("LSQ_READ_CACHE");
+            const bool use_cache = cache && cache[0] == '1';
+            const std::string pack = sets[m].path + ".lsqpack";
+            if (use_cache && lsqh_reads_load(pack.c_str(), sets[m].path.c_str(), &reads[m]) == LSQ_OK) {
+                L.from_pack = true;
+                continue;
+            }
+            L.rc = lsqh_mrf_parse(sets[m].path.c_str(), &reads[m]);
+            if (L.rc == LSQ_OK && use_cache && lsqh_reads_save(reads[m], pack.c_str(), sets[m].path.c_str()) != LSQ_OK)
+                L.warn = lsq_last_error();  // a cache that cannot be written is not an error
+            if (L.rc) {
+                L.stage = 3;
+                L.err = lsq_last_error();
+                break;
+            }
+            lsqh_reads_compact(reads[m]);  // the narrow layout where the values fit (9 instead of 22 bytes per read cross PCIe)
+        }
+    });
+    struct Joiner {  // every return path waits for the background loader
+        std::thread &t;
+        std::vector<lsqh_reads *> &r;
+        bool keep = false;
+        ~Joiner() {
+            if (t.joinable()) t.join();
+            if (!keep)
+                for (auto &x : r) {
+                    lsqh_reads_free(x);
+                    x = nullptr;
+                }
+        }
+    } read_joiner{read_thread, reads};
+
     logf(2, "Loading isoforms...");
     if (!file_openable(form_path)) {
         fprintf(stderr, "Assertion `ifs.is_open() && !ifs.eof()' failed (%s).\n", form_path.c_str());
@@ -329,48 +386,60 @@ int run_program(bool solve, int argc, char **argv) {
     lsqh_annotation_tables(ann, &tables);
     logf(2, "Selected %llu gene(s)", (unsigned long long)ann->n_selected);
 
-    const uint32_t M = (uint32_t)sets.size();
+    // The device context and the event tables are set up by a helper thread while the read text is parsed: creating a
+    // CUDA context takes as long as parsing tens of millions of reads.
+    int device = 0;
+    if (const char *d = getenv("LSQ_DEVICE")) device = atoi(d);
+    lsq_ctx *ctx = nullptr;
+    int dev_rc = 0;
+    std::string dev_err;
+    std::thread dev_thread;
+    const bool have_events = tables.n_events != 0;
+    if (have_events)
+        dev_thread = std::thread([&]() {
+            dev_rc = lsq_ctx_create(device, &ctx);
+            if (!dev_rc) dev_rc = lsq_upload_events(ctx, &tables);
+            if (dev_rc) dev_err = lsq_last_error();
+        });
+    auto join_dev = [&]() {
+        if (dev_thread.joinable()) dev_thread.join();
+    };
+
     logf(2, "Loading the reads from %u sampling method(s)", M);
-    std::vector<lsqh_reads *> reads(M, nullptr);
     auto cleanup = [&]() {
-        for (auto r : reads) lsqh_reads_free(r);
+        join_dev();
+        if (ctx) lsq_ctx_destroy(ctx);
+        ctx = nullptr;
         lsqh_annotation_free(ann);
     };
+    if (read_thread.joinable()) read_thread.join();
     for (uint32_t m = 0; m < M; ++m) {
+        const Loaded &L = loaded[m];
         logf(2, "Loading the reads from sampling method #%u", m);
-        if (!file_openable(sets[m].path)) {
+        if (L.stage == 1) {
             fprintf(stderr, "Assertion `ifs.is_open() && !ifs.eof()' failed (%s).\n", sets[m].path.c_str());
             cleanup();
             return 134;
         }
-        if (sets[m].format != "MRF_SINGLE") {
+        if (L.stage == 2) {
             logf(0, "Unknown file format error: %s", sets[m].format.c_str());
             cleanup();
             return 1;
         }
-        // opt-in packed cache next to the text file: `solve` reuses what `count` parsed
-        const char *cache = getenv("LSQ_READ_CACHE");
-        const bool use_cache = cache && cache[0] == '1';
-        const std::string pack = sets[m].path + ".lsqpack";
-        if (use_cache && lsqh_reads_load(pack.c_str(), sets[m].path.c_str(), &reads[m]) == LSQ_OK) {
-            logf(3, "Read pack %s", pack.c_str());
-            continue;
-        }
-        rc = lsqh_mrf_parse(sets[m].path.c_str(), &reads[m]);
-        if (rc == LSQ_OK && use_cache && lsqh_reads_save(reads[m], pack.c_str(), sets[m].path.c_str()) != LSQ_OK)
-            logf(1, "%s", lsq_last_error());  // a cache that cannot be written is not an error
-        if (rc == LSQ_ERR_IO) {
-            fprintf(stderr, "Assertion `ifs.is_open() && !ifs.eof()' failed: %s\n", lsq_last_error());
+        if (L.from_pack) logf(3, "Read pack %s.lsqpack", sets[m].path.c_str());
+        if (!L.warn.empty()) logf(1, "%s", L.warn.c_str());
+        if (L.stage == 3 && L.rc == LSQ_ERR_IO) {
+            fprintf(stderr, "Assertion `ifs.is_open() && !ifs.eof()' failed: %s\n", L.err.c_str());
             cleanup();
             return 134;
         }
-        if (rc) {
-            logf(0, "%s", lsq_last_error());
+        if (L.stage == 3) {
+            logf(0, "%s", L.err.c_str());
             cleanup();
             return 1;
         }
     }
-    if (tables.n_events == 0) {  // nothing selected: the per-gene loop never runs
+    if (!have_events) {  // nothing selected: the per-gene loop never runs
         logf(2, "Processed 0 genes... Done");
         cleanup();
         return 0;
@@ -386,20 +455,18 @@ int run_program(bool solve, int argc, char **argv) {
         }
     }
 
-    int device = 0;
-    if (const char *d = getenv("LSQ_DEVICE")) device = atoi(d);
-    lsq_ctx *ctx = nullptr;
     auto gpu_fail = [&]() {
-        logf(0, "lesseq_b200 device path failed: %s", lsq_last_error());
-        if (ctx) lsq_ctx_destroy(ctx);
+        logf(0, "lesseq_b200 device path failed: %s", dev_err.empty() ? lsq_last_error() : dev_err.c_str());
         cleanup();
         return 70;  // no CPU fallback
     };
-    if (lsq_ctx_create(device, &ctx)) return gpu_fail();
-    if (lsq_upload_events(ctx, &tables)) return gpu_fail();
+    join_dev();
+    if (dev_rc) return gpu_fail();
     for (uint32_t m = 0; m < M; ++m) {
+        // line numbers only when the file had comment lines (they ascend, so the last one tells)
         lsq_packed_reads view;
         lsqh_reads_view(reads[m], &view);
+        if (view.n_reads && view.line_num && view.line_num[view.n_reads - 1] == view.n_reads) view.line_num = nullptr;
         if (lsq_set_reads(ctx, m, types[m], sets[m].length, &view)) return gpu_fail();
     }
     logf(2, "Processing reads info for genes");
@@ -450,12 +517,75 @@ int run_program(bool solve, int argc, char **argv) {
     fwrite(out.data(), 1, out.size(), stdout);
     fflush(stdout);
     logf(2, "Processed %u genes... Done", E);
-    lsq_ctx_destroy(ctx);
     cleanup();
     return 0;
 }
 
 }  // namespace
 
-extern "C" int lsqh_count_main(int argc, char **argv) { return run_program(false, argc, argv); }
+extern "C" int lsqh_write_mrf(const lsq_packed_reads *r, const char *path) {
+    if (!r || !path || r->on_device || !r->blk_off || !r->blk || !r->read_cs) {
+        lsqh::set_error("lsqh_write_mrf: host reads in the wide layout (blk_off, blk, read_cs) are required");
+        return LSQ_ERR_ARG;
+    }
+    FILE *f = fopen(path, "w");
+    if (!f) {
+        lsqh::set_error(std::string("cannot write ") + path);
+        return LSQ_ERR_IO;
+    }
+    std::vector<char> buf(1u << 22);
+    setvbuf(f, nullptr, _IOFBF, 1u << 22);
+    fputs("AlignmentBlocks\n", f);
+    size_t used = 0;
+    auto put_num = [&](long v) {
+        char tmp[24];
+        int n = 0;
+        if (v < 0) {
+            buf[used++] = '-';
+            v = -v;
+        }
+        do {
+            tmp[n++] = (char)('0' + v % 10);
+            v /= 10;
+        } while (v);
+        while (n) buf[used++] = tmp[--n];
+    };
+    auto put_str = [&](const char *p) {
+        while (*p) buf[used++] = *p++;
+    };
+    for (uint64_t i = 0; i < r->n_reads; ++i) {
+        long q = 1;
+        for (uint32_t j = r->blk_off[i]; j < r->blk_off[i + 1]; ++j) {
+            const uint32_t cs = (r->read_cs[i] & LSQ_READ_MIXED) && r->blk_cs ? r->blk_cs[j] : r->read_cs[i];
+            if (j != r->blk_off[i]) buf[used++] = ',';
+            const long s0 = (long)r->blk[2 * j] + 1, e0 = r->blk[2 * j + 1];  // 1-based inclusive in the text (count.cpp:299-318)
+            put_str(r->chrom_names[cs & 0xFFFFu]);
+            buf[used++] = ':';
+            put_str(r->strand_names[(cs >> 16) & 0xFFu]);
+            buf[used++] = ':';
+            put_num(s0);
+            buf[used++] = ':';
+            put_num(e0);
+            buf[used++] = ':';
+            put_num(q);
+            buf[used++] = ':';
+            put_num(q + e0 - s0);
+            q += e0 - s0 + 1;
+        }
+        buf[used++] = '\n';
+        if (used > buf.size() - 4096) {
+            fwrite(buf.data(), 1, used, f);
+            used = 0;
+        }
+    }
+    fwrite(buf.data(), 1, used, f);
+    const bool ok = fclose(f) == 0;
+    if (!ok) {
+        lsqh::set_error(std::string("write error on ") + path);
+        return LSQ_ERR_IO;
+    }
+    return LSQ_OK;
+}
+
+int lsqh_count_main(int argc, char **argv) { return run_program(false, argc, argv); }
 extern "C" int lsqh_solve_main(int argc, char **argv) { return run_program(true, argc, argv); }

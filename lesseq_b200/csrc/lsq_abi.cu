@@ -926,7 +926,7 @@ static int exact_replay(lsq_ctx *c, const lsq::SolveParams &P, uint32_t n_flag) 
     X.seg_off = reinterpret_cast<const uint64_t *>(d);
     X.seg_cur = reinterpret_cast<const uint32_t *>(d + o_cur);
     X.rec = c->d_exact_rec.as<lsq::ExactRec>();
-    lsq::lsq_exact_kernel<<<(n_flag + 31) / 32, 32, 0, s>>>(P, X);
+    lsq::lsq_exact_kernel<<<n_flag, 32, 0, s>>>(P, X);
     LSQ_CUDA(cudaGetLastError());
     c->tm.launches++;
     LSQ_CUDA(cudaStreamSynchronize(s));  // hbuf and friends go out of scope

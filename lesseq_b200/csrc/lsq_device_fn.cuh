@@ -878,12 +878,10 @@ LSQ_HD void expand_signature(const ScanParams &P, const ReadView &rv, uint32_t p
 // reference's own operation order, which makes theta bit-identical to the reference.
 // ---------------------------------------------------------------------------------------------
 struct ExactRec {
-    int32_t start, end;     // first kept start, last kept end of the read
-    uint32_t strand_rank;   // rank of the read's strand string among the file's strand strings (bytewise order)
-    uint32_t line_num;      // the read is named "read-<line_num>"
-    uint64_t mask;          // forms the read is compatible with
-    uint32_t m;             // read set
-    uint32_t pad;
+    uint64_t k1;    // read set << 32 | first kept start (biased); after sorting bits 40-51 hold the read's class index
+    uint64_t k2;    // last kept end (biased) << 8 | rank of the read's strand string among the file's strand strings
+    uint64_t k3;    // name_sort_key of "read-<line_num>"
+    uint64_t mask;  // forms the read is compatible with
 };
 
 // "read-<a>" < "read-<b>" as byte strings: compare the decimal digit strings.  Left-aligned to ten digits the
@@ -899,12 +897,19 @@ LSQ_HD uint64_t name_sort_key(uint32_t n) {
     for (uint32_t i = nd; i < 10u; ++i) v *= 10;
     return (v << 4) | nd;
 }
+LSQ_HD ExactRec make_exact_rec(uint32_t m, int32_t start, int32_t end, uint32_t strand_rank, uint32_t line_num, uint64_t mask) {
+    ExactRec e;
+    e.k1 = ((uint64_t)m << 32) | (uint64_t)((uint32_t)start ^ 0x80000000u);
+    e.k2 = ((uint64_t)((uint32_t)end ^ 0x80000000u) << 8) | (uint64_t)(strand_rank & 0xFFu);
+    e.k3 = name_sort_key(line_num);
+    e.mask = mask;
+    return e;
+}
+LSQ_HD uint32_t exact_rec_set(const ExactRec &r) { return (uint32_t)(r.k1 >> 32) & 0xFFu; }
 LSQ_HD bool exact_rec_less(const ExactRec &a, const ExactRec &b) {
-    if (a.m != b.m) return a.m < b.m;
-    if (a.start != b.start) return a.start < b.start;
-    if (a.end != b.end) return a.end < b.end;
-    if (a.strand_rank != b.strand_rank) return a.strand_rank < b.strand_rank;
-    return name_sort_key(a.line_num) < name_sort_key(b.line_num);
+    if (a.k1 != b.k1) return a.k1 < b.k1;
+    if (a.k2 != b.k2) return a.k2 < b.k2;
+    return a.k3 < b.k3;
 }
 // In-place heapsort (no recursion, no extra memory): read names are unique, so the order is total.
 LSQ_HD void exact_sort(ExactRec *a, uint32_t n) {
@@ -937,43 +942,91 @@ LSQ_HD bool em_stop_is_fragile(double near, double ll, double n_reads) {
     return near < margin || (ll > -1E-8 && ll < 1E-8);
 }
 
-// reads_log_likelihood (read.h:620-636) over the sorted records: every form's term is added in form order, zeros
-// included, exactly as the reference's dense matrix row does.
-LSQ_HD double exact_loglik(const ExactRec *rec, uint32_t n, uint32_t K, const double *theta, const double *G, size_t g_stride) {
-    double ll = 0.0;
-    for (uint32_t i = 0; i < n; ++i) {
-        const double *g = G + (size_t)rec[i].m * g_stride;
-        double s = 0.0;
-        for (uint32_t k = 0; k < K; ++k) s = lsq_add(s, lsq_mul(theta[k], ((rec[i].mask >> k) & 1ull) ? g[k] : 0.0));
-        ll = lsq_add(ll, log(s));
-    }
-    return ll;
+// The reference evaluates, per read, s = sum_k theta_k M(i,k) (every form's term added in form order, zeros included),
+// log s for the log-likelihood (read.h:620-636) and theta_k M(i,k) / s for the E-step (read.h:592-618), and adds them up
+// read by read.  Those VALUES depend only on the read's class (read set, form mask): they are tabulated per class,
+// and only the additions run over the reads, in the reference's order -- same values, same order, same bits.
+constexpr uint32_t EXACT_MAX_CLS = 64, EXACT_MAX_TERMS = 1024;  // classes, classes * forms of the tabulated path
+
+LSQ_HD double exact_class_prob(uint64_t mask, uint32_t K, const double *theta, const double *g) {
+    double s = 0.0;
+    for (uint32_t k = 0; k < K; ++k) s = lsq_add(s, lsq_mul(theta[k], ((mask >> k) & 1ull) ? g[k] : 0.0));
+    return s;
 }
-// compute_iso_probs_EM (read.h:638-660) read by read.  theta (K doubles) receives the result, old_theta is scratch.
-// Returns the iterations executed; ll_out = the final log-likelihood.
-LSQ_HD uint32_t exact_em(const ExactRec *rec, uint32_t n, double n_total, uint32_t K, const double *G, size_t g_stride,
+
+// compute_iso_probs_EM (read.h:638-660) over the sorted records.  theta (K doubles) receives the result, old_theta is
+// scratch.  Returns the iterations executed; ll_out = the final log-likelihood.
+LSQ_HD uint32_t exact_em(ExactRec *rec, uint32_t n, double n_total, uint32_t K, const double *G, size_t g_stride,
                          double *theta, double *old_theta, double &ll_out, uint32_t max_iters) {
+    // classes of the event: distinct (read set, mask) pairs; a read's class index goes into bits 40-51 of k1
+    uint64_t cmask[EXACT_MAX_CLS];
+    uint32_t cset[EXACT_MAX_CLS];
+    uint32_t C = 0;
+    bool tab = true;
+    for (uint32_t i = 0; i < n && tab; ++i) {
+        const uint32_t m = exact_rec_set(rec[i]);
+        uint32_t c = 0;
+        while (c < C && !(cmask[c] == rec[i].mask && cset[c] == m)) ++c;
+        if (c == C) {
+            if (C == EXACT_MAX_CLS || (C + 1u) * K > EXACT_MAX_TERMS) {
+                tab = false;
+                break;
+            }
+            cmask[C] = rec[i].mask;
+            cset[C] = m;
+            ++C;
+        }
+        rec[i].k1 = (rec[i].k1 & 0xFFFF00FFFFFFFFFFull) | ((uint64_t)c << 40);
+    }
+    double term[EXACT_MAX_TERMS];  // [class][form] E-step terms
+    double lterm[EXACT_MAX_CLS];   // log-likelihood term per class
+    auto loglik = [&](const double *th) {
+        double ll = 0.0;
+        if (tab) {
+            for (uint32_t c = 0; c < C; ++c) lterm[c] = log(exact_class_prob(cmask[c], K, th, G + (size_t)cset[c] * g_stride));
+            for (uint32_t i = 0; i < n; ++i) ll = lsq_add(ll, lterm[(rec[i].k1 >> 40) & 0xFFu]);
+        } else {
+            for (uint32_t i = 0; i < n; ++i)
+                ll = lsq_add(ll, log(exact_class_prob(rec[i].mask, K, th, G + (size_t)exact_rec_set(rec[i]) * g_stride)));
+        }
+        return ll;
+    };
     for (uint32_t k = 0; k < K; ++k) theta[k] = lsq_div(1.0, (double)K);
     uint32_t iters = 0;
-    double ll = 0.0;
+    double ll = loglik(theta);  // the reference re-evaluates old_ll every iteration: the same theta in the same order gives the same bits
     while (true) {
         for (uint32_t k = 0; k < K; ++k) old_theta[k] = theta[k];
-        const double old_ll = exact_loglik(rec, n, K, old_theta, G, g_stride);
-        for (uint32_t k = 0; k < K; ++k) {  // compute_iso_probs_EM_step, read.h:592-618
-            double sum_zeta = 0.0;
-            for (uint32_t i = 0; i < n; ++i) {
-                const double *g = G + (size_t)rec[i].m * g_stride;
-                double s = 0.0;
-                for (uint32_t k2 = 0; k2 < K; ++k2)
-                    s = lsq_add(s, lsq_mul(old_theta[k2], ((rec[i].mask >> k2) & 1ull) ? g[k2] : 0.0));
-                if (s > 0.0) {
-                    const double lp = lsq_mul(old_theta[k], ((rec[i].mask >> k) & 1ull) ? g[k] : 0.0);
-                    if (lp > 0.0) sum_zeta = lsq_add(sum_zeta, lsq_div(lp, s));
+        const double old_ll = ll;
+        if (tab) {  // compute_iso_probs_EM_step, read.h:592-618: a skipped term (s <= 0 or lp <= 0) adds nothing, like + 0.0
+            for (uint32_t c = 0; c < C; ++c) {
+                const double *g = G + (size_t)cset[c] * g_stride;
+                const double sc = exact_class_prob(cmask[c], K, old_theta, g);
+                for (uint32_t k = 0; k < K; ++k) {
+                    const double lp = lsq_mul(old_theta[k], ((cmask[c] >> k) & 1ull) ? g[k] : 0.0);
+                    term[c * K + k] = (sc > 0.0 && lp > 0.0) ? lsq_div(lp, sc) : 0.0;
                 }
             }
-            theta[k] = lsq_div(sum_zeta, n_total);
+            for (uint32_t k = 0; k < K; ++k) theta[k] = 0.0;
+            for (uint32_t i = 0; i < n; ++i) {  // K independent running sums, each in read order
+                const double *t = term + ((rec[i].k1 >> 40) & 0xFFu) * K;
+                for (uint32_t k = 0; k < K; ++k) theta[k] = lsq_add(theta[k], t[k]);
+            }
+            for (uint32_t k = 0; k < K; ++k) theta[k] = lsq_div(theta[k], n_total);
+        } else {
+            for (uint32_t k = 0; k < K; ++k) {
+                double sum_zeta = 0.0;
+                for (uint32_t i = 0; i < n; ++i) {
+                    const double *g = G + (size_t)exact_rec_set(rec[i]) * g_stride;
+                    const double sc = exact_class_prob(rec[i].mask, K, old_theta, g);
+                    if (sc > 0.0) {
+                        const double lp = lsq_mul(old_theta[k], ((rec[i].mask >> k) & 1ull) ? g[k] : 0.0);
+                        if (lp > 0.0) sum_zeta = lsq_add(sum_zeta, lsq_div(lp, sc));
+                    }
+                }
+                theta[k] = lsq_div(sum_zeta, n_total);
+            }
         }
-        ll = exact_loglik(rec, n, K, theta, G, g_stride);
+        ll = loglik(theta);
         ++iters;
         const double d = 1.0 - lsq_div(old_ll, ll);
         if (!((d < 0.0 ? -d : d) > 1E-6) || iters >= max_iters) break;

@@ -1421,15 +1421,8 @@ __global__ void __launch_bounds__(SCAN_BLOCK) lsq_collect_kernel(const __grid_co
                 if (cm == 0ull) continue;
                 const uint64_t at = C.seg_off[fi - 1u] + atomicAdd(C.seg_cur + (fi - 1u), 1u);
                 if (at >= C.seg_off[fi]) continue;  // cannot happen: the segment holds the event's n_valid records
-                ExactRec e;
-                e.start = fr.first.x;
-                e.end = rv.last_end();
-                e.strand_rank = __ldg(C.strand_rank + fr.strand);
-                e.line_num = P.line_num ? __ldg(P.line_num + r) : (uint32_t)r + 1u;
-                e.mask = cm;
-                e.m = C.m;
-                e.pad = 0u;
-                C.rec[at] = e;
+                C.rec[at] = make_exact_rec(C.m, fr.first.x, rv.last_end(), __ldg(C.strand_rank + fr.strand),
+                                           P.line_num ? __ldg(P.line_num + r) : (uint32_t)r + 1u, cm);
             }
         }
     }
@@ -1443,10 +1436,10 @@ struct ExactParams {
     ExactRec *rec;
 };
 
-// One thread per flagged event (they are few): sort, replay, overwrite the event's results.
+// One block (one working thread) per flagged event (they are few): sort, replay, overwrite the event's results.
 __global__ void __launch_bounds__(32) lsq_exact_kernel(const __grid_constant__ SolveParams P, const __grid_constant__ ExactParams X) {
-    const uint32_t fi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (fi >= X.n_flag) return;
+    const uint32_t fi = blockIdx.x;
+    if (fi >= X.n_flag || threadIdx.x != 0) return;
     const uint32_t x = X.flag_list[fi];
     const EvHdr h = P.T.hdr[x];
     const uint32_t K = h.K, E = P.T.E;

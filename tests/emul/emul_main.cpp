@@ -503,15 +503,7 @@ int main(int argc, char **argv) {
                                 uint32_t ml = 0;
                                 const uint64_t cm = eval_pair(FP, h, T.seg + h.seg_off, T.fmask + h.form_off, rv, fr.strand, total, ml);
                                 if (!cm) continue;
-                                ExactRec e;
-                                e.start = fr.first.x;
-                                e.end = rv.last_end();
-                                e.strand_rank = sctx[m].strand_rank[fr.strand];
-                                e.line_num = R.line_num[r];
-                                e.mask = cm;
-                                e.m = m;
-                                e.pad = 0;
-                                recs.push_back(e);
+                                recs.push_back(make_exact_rec(m, fr.first.x, rv.last_end(), sctx[m].strand_rank[fr.strand], R.line_num[r], cm));
                             }
                         }
                     }
