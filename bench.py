@@ -200,17 +200,18 @@ def cli_e2e(args, tmp, torch):
             g.write(line)
     size = os.path.getsize(rp)
     head = ["0", "bench", os.path.join(tmp, "o_"), "LH_GENE_TXT", fp, "UCSC_GENE2ISOFORM", mp, "0", str(10 ** 9), "MRF_SINGLE", "SHORT_READ", str(R)]
-    walls, rows = {}, {}
+    walls, rows, marks = {}, {}, {}
     for prog in ("count", "solve"):
         a = head + [rp] + ([repr(trb)] if prog == "solve" else [])
         best = None
         for _ in range(2):  # first run pays the page-cache / driver warm-up; the second is reported
             t0 = time.time()
-            rc, out, err = api.run_program(prog, a)
+            rc, out, err = api.run_program(prog, a, env_extra={"LSQ_CLI_TIMING": "1"})
             dt = time.time() - t0
             if rc != 0:
                 raise RuntimeError("bin/%s failed: %s" % (prog, err[-300:]))
             best = dt
+            marks[prog] = {ln.split()[1]: float(ln.split()[2]) for ln in err.splitlines() if ln.startswith("[timing]")}
         walls[prog] = best
         rows[prog] = out.count("\n")
     ref = {}
@@ -224,7 +225,7 @@ def cli_e2e(args, tmp, torch):
                 raise RuntimeError("reference %s failed" % prog)
     ours_rate = n / (walls["count"] + walls["solve"])
     res = {"reads": n, "text_bytes": size, "wall_s": {k: round(v, 3) for k, v in walls.items()}, "reads_per_s": ours_rate,
-           "text_GB_per_s_count": size / walls["count"] / 1e9, "host_cores": os.cpu_count(), "table_rows": rows["count"],
+           "text_GB_per_s_count": size / walls["count"] / 1e9, "milestones_ms": marks, "host_cores": os.cpu_count(), "table_rows": rows["count"],
            "note": "bin/count then bin/solve, each: parse the text on all host cores (lsqh_mrf_parse) while a helper thread creates the CUDA "
                    "context and uploads the event tables, compact host->device copy, scan + expand + general (+ solve), print the table; "
                    "second of two runs (warm page cache); writing the text took %.1f s (not counted)" % t_write}
@@ -506,7 +507,7 @@ def run_ours(args):
             "events_per_sec": n_events_total / (ms / 1000.0),
             "events": n_events_total,
             "phases_ms_per_step_rank0": {k: v / args.steps for k, v in phases.items()},
-            "reads_rank0": {k: int(tsum[k]) for k in ("reads_in", "blocks_in", "reads_single", "reads_pair", "reads_general", "hash_full")},
+            "reads_rank0": {k: int(tsum[k]) for k in ("reads_in", "blocks_in", "reads_single", "reads_pair", "reads_triple", "reads_general", "hash_full")},
             "valid_pairs_rank0": int(tsum["pairs_valid"]), "em_exact_replays_rank0": int(tsum["exact_events"]),
             "em_iters_mean": float(sol["iters"].mean()), "em_iters_max": int(sol["iters"].max()),
             "em_iters_p99": float(np.percentile(sol["iters"], 99)),

@@ -248,7 +248,23 @@ void print_g(std::string &out, double v, int prec) {
     out += b;
 }
 
+// LSQ_CLI_TIMING=1: wall-clock milestones of the program on stderr (milliseconds since start)
+struct CliClock {
+    double t0;
+    bool on;
+    static double now() {
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    }
+    CliClock() : t0(now()), on(getenv("LSQ_CLI_TIMING") != nullptr) {}
+    void mark(const char *what) const {
+        if (on) fprintf(stderr, "[timing] %s %.1f\n", what, now() - t0);
+    }
+};
+
 int run_program(bool solve, int argc, char **argv) {
+    const CliClock clk;
     const int group = solve ? 5 : 4;
     if (argc < 10 + group) {
         logf(0, "%s", solve ? USAGE_SOLVE : USAGE_COUNT);
@@ -330,6 +346,7 @@ int run_program(bool solve, int argc, char **argv) {
             }
             lsqh_reads_compact(reads[m]);  // the narrow layout where the values fit (9 instead of 22 bytes per read cross PCIe)
         }
+        clk.mark("reads_parsed");
     });
     struct Joiner {  // every return path waits for the background loader
         std::thread &t;
@@ -384,6 +401,7 @@ int run_program(bool solve, int argc, char **argv) {
     }
     lsq_event_tables tables;
     lsqh_annotation_tables(ann, &tables);
+    clk.mark("annotation_loaded");
     logf(2, "Selected %llu gene(s)", (unsigned long long)ann->n_selected);
 
     // The device context and the event tables are set up by a helper thread while the read text is parsed: creating a
@@ -398,7 +416,9 @@ int run_program(bool solve, int argc, char **argv) {
     if (have_events)
         dev_thread = std::thread([&]() {
             dev_rc = lsq_ctx_create(device, &ctx);
+            clk.mark("device_context");
             if (!dev_rc) dev_rc = lsq_upload_events(ctx, &tables);
+            clk.mark("tables_uploaded");
             if (dev_rc) dev_err = lsq_last_error();
         });
     auto join_dev = [&]() {
@@ -469,6 +489,7 @@ int run_program(bool solve, int argc, char **argv) {
         if (view.n_reads && view.line_num && view.line_num[view.n_reads - 1] == view.n_reads) view.line_num = nullptr;
         if (lsq_set_reads(ctx, m, types[m], sets[m].length, &view)) return gpu_fail();
     }
+    clk.mark("reads_on_device");
     logf(2, "Processing reads info for genes");
     if (lsq_count(ctx)) return gpu_fail();
     const uint32_t E = tables.n_events, F = tables.n_forms;
@@ -486,6 +507,7 @@ int run_program(bool solve, int argc, char **argv) {
         // the reference warns once per read when a compatible form has no accessible start
         // (read.h:334-337); one summary line is logged here instead
     }
+    clk.mark("results_on_host");
     std::string out;
     out.reserve((size_t)F * 64);
     for (uint32_t e = 0; e < E; ++e) {
@@ -517,7 +539,9 @@ int run_program(bool solve, int argc, char **argv) {
     fwrite(out.data(), 1, out.size(), stdout);
     fflush(stdout);
     logf(2, "Processed %u genes... Done", E);
+    clk.mark("table_printed");
     cleanup();
+    clk.mark("done");
     return 0;
 }
 

@@ -1071,7 +1071,7 @@ int lsq_get_timings(lsq_ctx *c, lsq_timings *o) {
         std::vector<unsigned long long> hc((size_t)LSQ_MAX_METHODS * lsq::CTR_N + 4, 0);
         LSQ_CUDA(cudaMemcpy(hc.data(), c->d_counters.p, hc.size() * 8, cudaMemcpyDeviceToHost));
         tm.clear_ms = tm.scan_ms = tm.expand_ms = tm.general_ms = 0.f;
-        tm.reads_single = tm.reads_pair = tm.reads_general = tm.hash_full = 0;
+        tm.reads_single = tm.reads_pair = tm.reads_triple = tm.reads_general = tm.hash_full = 0;
         for (uint32_t m = 0; m < c->M; ++m) {
             if (!c->set_counted[m]) continue;
             float f;
@@ -1086,6 +1086,7 @@ int lsq_get_timings(lsq_ctx *c, lsq_timings *o) {
             const unsigned long long *k = hc.data() + (size_t)m * lsq::CTR_N;
             tm.reads_single += k[lsq::CTR_SINGLE_SIG];
             tm.reads_pair += k[lsq::CTR_PAIR_SIG];
+            tm.reads_triple += k[lsq::CTR_TRIPLE_SIG];
             tm.reads_general += k[lsq::CTR_GENERAL];
             tm.hash_full += k[lsq::CTR_HASH_FULL];
         }

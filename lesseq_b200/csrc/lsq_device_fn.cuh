@@ -445,7 +445,7 @@ LSQ_HD uint32_t block_lookup(const ScanParams &P, int2 b, uint32_t cs) {
 // which the signature decides, and its matched length is the read's total length.  Everything else goes
 // to lsq_general_kernel, which walks the read itself.
 // ---------------------------------------------------------------------------------------------
-constexpr uint32_t RT_NONE = 0, RT_SINGLE = 1, RT_PAIR = 2, RT_GENERAL = 3;
+constexpr uint32_t RT_NONE = 0, RT_SINGLE = 1, RT_PAIR = 2, RT_GENERAL = 3, RT_TRIPLE = 4;
 
 // Number of cuts of the piece `raw` below block end e (the block starts inside the piece); exact: e hits cut k;
 // q_prev: the largest cut below e (k > 0).  The first two cuts come with the piece record.
@@ -530,6 +530,39 @@ LSQ_HD uint32_t route_pair(const Tables &T, int2 b0, int2 b1, uint32_t p0, uint4
     return RT_PAIR;
 }
 
+// Three kept blocks b0 < b1 < b2 (disjoint, not abutting) on one chromosome.  RT_TRIPLE with the prefix key
+// (pair_key of blocks 0 and 1) and the cut category k2 of block 2, RT_NONE or RT_GENERAL.  Block 1 must be a whole
+// chain link for any event to take all three: it starts on a piece start and ends exactly on a cut; whatever
+// breaks that leaves at most blocks 0 and 1 matched, which is certainly invalid when block 2 is at least total/50.
+LSQ_HD uint32_t route_triple(const Tables &T, int2 b0, int2 b1, int2 b2, uint32_t p0, uint4 raw0, uint32_t p1, uint4 raw1,
+                             uint4 raw2, uint64_t &prefix, uint32_t &k2) {
+    prefix = 0;
+    k2 = 0;
+    const uint32_t n0 = piece_ncuts(raw0.z);
+    if (n0 == PIECE_NO_SIG) return RT_GENERAL;
+    if ((raw0.z & PIECE_TIE) && (int32_t)raw0.x == b0.x) return RT_GENERAL;
+    const uint32_t len2 = (uint32_t)(b2.y - b2.x);
+    const uint32_t total = (uint32_t)(b0.y - b0.x) + (uint32_t)(b1.y - b1.x) + len2;
+    if (!surely_invalid(len2, total)) return RT_GENERAL;
+    bool exact;
+    int32_t qp;
+    const uint32_t k0 = cut_category(T, raw0, b0.y, exact, qp);
+    if (k0 == n0 || !exact) return RT_NONE;
+    if ((int32_t)raw1.x != b1.x || !(raw1.z & PIECE_CAND)) return RT_NONE;
+    const uint32_t n1 = piece_ncuts(raw1.z);
+    if (n1 == PIECE_NO_SIG) return RT_GENERAL;
+    const uint32_t k1 = cut_category(T, raw1, b1.y, exact, qp);
+    if (k1 == n1 || !exact) return RT_NONE;
+    if ((int32_t)raw2.x != b2.x || !(raw2.z & PIECE_CAND)) return RT_NONE;
+    const uint32_t n2 = piece_ncuts(raw2.z);
+    if (n2 == PIECE_NO_SIG) return RT_GENERAL;
+    k2 = cut_category(T, raw2, b2.y, exact, qp);
+    if (k2 > 0u && !surely_invalid((uint32_t)(b2.y - qp), total)) return RT_GENERAL;
+    if (k2 == n2) return RT_NONE;
+    prefix = pair_key(p0, k0, p1, k1);
+    return RT_TRIPLE;
+}
+
 // Route of a filtered read.  raw1 is only read for two-block reads whose second piece is known.
 template <class PinfoFn>
 LSQ_HD uint32_t route_read(const ScanParams &P, const FilteredRead &fr, PinfoFn pinfo, uint32_t &sig, uint64_t &key,
@@ -594,11 +627,11 @@ LSQ_HD uint32_t scan_route(const ScanParams &P, uint64_t r, uint32_t base, uint3
     total = 0;
     if (nraw == 0u) return RT_NONE;
     const uint32_t cs0 = load_read_cs(P, r);
-    if (nraw > 2u || (cs0 & 0x80000000u)) return RT_GENERAL;
-    int2 b[2];
-    uint32_t p[2];
-    uint4 raw[2];
-    bool kept[2];
+    if (nraw > 3u || (cs0 & 0x80000000u)) return RT_GENERAL;
+    int2 b[3];
+    uint32_t p[3];
+    uint4 raw[3];
+    bool kept[3];
     for (uint32_t j = 0; j < nraw; ++j) {
         b[j] = load_block_stream(P, base + j);
         const uint32_t res = block_lookup(P, b[j], cs0);
@@ -612,7 +645,15 @@ LSQ_HD uint32_t scan_route(const ScanParams &P, uint64_t r, uint32_t base, uint3
         if (P.flags & SCAN_NO_SINGLE_SIG) return RT_GENERAL;
         return route_single(P.T, b[0], raw[0], sig);
     }
-    return route_double(P, b[0], b[1], p[0], raw[0], kept[0], p[1], raw[1], kept[1], sig, key, total);
+    if (nraw == 2u) return route_double(P, b[0], b[1], p[0], raw[0], kept[0], p[1], raw[1], kept[1], sig, key, total);
+    // three raw blocks: the signature route needs all three kept, in order, apart; anything else is general
+    if (!(kept[0] && kept[1] && kept[2] && b[1].x > b[0].y && b[2].x > b[1].y) || (P.flags & SCAN_NO_TRIPLE_SIG)) return RT_GENERAL;
+    if (!(raw[0].z & PIECE_CAND)) return RT_NONE;
+    total = (uint32_t)(b[0].y - b[0].x) + (uint32_t)(b[1].y - b[1].x) + (uint32_t)(b[2].y - b[2].x);
+    uint32_t k2;
+    const uint32_t rt = route_triple(P.T, b[0], b[1], b[2], p[0], raw[0], p[1], raw[1], raw[2], key, k2);
+    sig = (p[2] << 4) | k2;  // the caller keys the triple by (prefix = key, piece 2, k2)
+    return rt;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -852,11 +893,22 @@ LSQ_HD bool sig_rep_pair(const Tables &T, uint64_t key, ReadView &rv, uint32_t &
     return rv.b0.x < rv.b0.y && rv.b0.y < rv.b1.x && rv.b1.x < rv.b1.y;
 }
 
+// Representative of a three-block signature: `prefix` is the pair key its prefix slot holds.
+LSQ_HD bool sig_rep_triple(const Tables &T, uint64_t prefix, uint64_t key, ReadView &rv, uint32_t &piece) {
+    if (!sig_rep_pair(T, prefix, rv, piece)) return false;
+    const uint32_t p2 = (uint32_t)(key >> 30) & PIECE_SIG_MASK, k2 = (uint32_t)(key >> 56) & 15u;
+    const uint4 raw2 = LSQ_LD(reinterpret_cast<const uint4 *>(T.pinfo + p2));
+    rv.b2 = make_int2((int32_t)raw2.x, LSQ_LD(T.sig_cut + (raw2.z & PIECE_SIG_MASK) + k2));
+    rv.n = 3;
+    return rv.b1.y < rv.b2.x && rv.b2.x < rv.b2.y;
+}
+
 // Every candidate event of `piece` that the representative read matches FULLY: sink(event id, header, form mask).
 template <class Sink>
 LSQ_HD void expand_signature(const ScanParams &P, const ReadView &rv, uint32_t piece, Sink &&sink) {
     const Tables &T = P.T;
-    const uint32_t total = (uint32_t)(rv.b0.y - rv.b0.x) + (rv.n > 1u ? (uint32_t)(rv.b1.y - rv.b1.x) : 0u);
+    const uint32_t total = (uint32_t)(rv.b0.y - rv.b0.x) + (rv.n > 1u ? (uint32_t)(rv.b1.y - rv.b1.x) : 0u) +
+                           (rv.n > 2u ? (uint32_t)(rv.b2.y - rv.b2.x) : 0u);
     const uint32_t e0 = LSQ_LD(T.stab_off + piece), e1 = LSQ_LD(T.stab_off + piece + 1);
     LSQ_NO_UNROLL
     for (uint32_t q = e0; q < e1; ++q) {

@@ -142,6 +142,9 @@ constexpr int SCAN_BLOCK = LSQ_SCAN_BLOCK;
 constexpr int SCAN_MINB = LSQ_SCAN_MINB;
 constexpr int SCAN_WARPS = SCAN_BLOCK / 32;
 constexpr int SCAN_ITEMS = 4;     // reads per lane
+#ifndef LSQ_SCAN_TRIPLES
+#define LSQ_SCAN_TRIPLES 1  // three-block reads get a signature route of their own (0: they take the general path)
+#endif
 #ifndef LSQ_SCAN_FLIGHT
 #define LSQ_SCAN_FLIGHT 2
 #endif
@@ -199,23 +202,67 @@ __device__ __forceinline__ int2 scan_block(const ScanParams &P, uint32_t i) {
     return load_block(P, i);
 }
 
-// Tally of a two-block signature: open addressing, linear probing; the slot's key and count share one
-// 16-byte line segment, so a resident key costs one 8-byte load and one 64-bit reduction.
-__device__ __forceinline__ bool sig_hash_add(const ScanParams &P, uint64_t key, uint32_t total) {
+// Signature hash: open addressing, linear probing; a slot's key and count share one 16-byte line segment, so a resident
+// key costs one 8-byte load (and one 64-bit reduction to count it).  Returns the key's slot, or 0xFFFFFFFF when
+// HASH_MAX_PROBES slots were taken by other keys.
+__device__ __forceinline__ uint32_t sig_hash_slot(const ScanParams &P, uint64_t key) {
     uint32_t i = hash_mask(key) & P.hash_mask;
 #pragma unroll 1
     for (uint32_t probe = 0; probe < HASH_MAX_PROBES; ++probe) {
         unsigned long long *kp = &P.hash[i].x;
         unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(kp);
         if (cur == 0ull) cur = atomicCAS(kp, 0ull, (unsigned long long)key);
-        if (cur == 0ull || cur == key) {
-            atomicAdd(&P.hash[i].y, 1ull);
-            if (total != P.len0) atomicAdd(P.hash_dev + i, (unsigned long long)(long long)((int)total - (int)P.len0));
-            return true;
-        }
+        if (cur == 0ull || cur == key) return i;
         i = (i + 1u) & P.hash_mask;
     }
-    return false;
+    return 0xFFFFFFFFu;
+}
+__device__ __forceinline__ void sig_hash_count(const ScanParams &P, uint32_t slot, uint32_t total) {
+    atomicAdd(&P.hash[slot].y, 1ull);
+    if (total != P.len0) atomicAdd(P.hash_dev + slot, (unsigned long long)(long long)((int)total - (int)P.len0));
+}
+
+// A read with three raw blocks (rare outside long-read sets): out of line, so that its registers do not weigh on the
+// one- and two-block paths.
+template <bool COMPACT>
+__device__ __noinline__ uint32_t scan_triple(const ScanParams &P, uint32_t base, uint32_t c, uint32_t &sig, uint64_t &key,
+                                             uint32_t &total) {
+    const PieceInfo *const pinfo = P.T.pinfo;
+    sig = 0;
+    key = 0;
+    total = 0;
+    int2 b[3];
+    Probe q[3];
+    uint2 e[3];
+    uint32_t p[3];
+    uint4 raw[3];
+    const uint4 cm = __ldg(P.file_meta + c);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) b[j] = scan_block<COMPACT>(P, base + (uint32_t)j);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) q[j] = probe_of(P, b[j], cm);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) e[j] = q[j].how == 1u ? __ldg(P.T.bp_bkt + q[j].slot) : make_uint2(0u, 0u);
+    bool all_kept = true;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        p[j] = piece_of(P, b[j], c, q[j], e[j]);
+        raw[j] = p[j] != PIECE_NONE ? __ldg(reinterpret_cast<const uint4 *>(pinfo + p[j])) : make_uint4(0u, 0u, 0u, 0u);
+        all_kept = all_kept && p[j] != PIECE_NONE && (int32_t)raw[j].y >= b[j].y;
+    }
+    // the signature route needs all three blocks kept, in order, apart; anything else takes the general path
+    uint32_t rt = RT_GENERAL;
+    if (all_kept && b[1].x > b[0].y && b[2].x > b[1].y) {
+        if (!(raw[0].z & PIECE_CAND)) {
+            rt = RT_NONE;
+        } else {
+            total = (uint32_t)(b[0].y - b[0].x) + (uint32_t)(b[1].y - b[1].x) + (uint32_t)(b[2].y - b[2].x);
+            uint32_t k2;
+            rt = route_triple(P.T, b[0], b[1], b[2], p[0], raw[0], p[1], raw[1], raw[2], key, k2);
+            sig = (p[2] << 4) | k2;
+        }
+    }
+    return rt;
 }
 
 // COMPACT: the read set is in the compact layout throughout (blk_cnt + index, read_cs8, blk_start + blk_len8) --
@@ -223,13 +270,14 @@ __device__ __forceinline__ bool sig_hash_add(const ScanParams &P, uint64_t key, 
 template <bool COMPACT>
 __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MINB) lsq_scan_kernel(const __grid_constant__ ScanParams P) {
     __shared__ uint2 s_dbl[SCAN_WARPS][SCAN_GROUP];  // per warp: its two-block reads {first block, chromosome id | group-local index << 24}
+    __shared__ uint2 s_tri[SCAN_WARPS][SCAN_GROUP];    // per warp: its three-block reads, same format
     __shared__ uint2 s_gen[SCAN_WARPS][SCAN_GEN_CAP];  // per warp: reads for the general kernel {read, first block}
     __shared__ uint32_t s_ngen[SCAN_WARPS];
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
     const uint64_t n_groups = (P.n_reads + SCAN_GROUP - 1) / SCAN_GROUP;
-    uint32_t c_single = 0, c_pair = 0, c_general = 0, c_full = 0;  // statistics, flushed once per warp
+    uint32_t c_single = 0, c_pair = 0, c_triple = 0, c_general = 0, c_full = 0;  // statistics, flushed once per warp
     const PieceInfo *const pinfo = P.T.pinfo;
-    const bool no_single = (P.flags & SCAN_NO_SINGLE_SIG) != 0u;
+    const bool no_single = (P.flags & SCAN_NO_SINGLE_SIG) != 0u, no_triple = !LSQ_SCAN_TRIPLES || (P.flags & SCAN_NO_TRIPLE_SIG) != 0u;
 
     // general reads are parked in the warp's shared-memory slice (a shared atomic returns in ~30 cycles); the warp
     // reserves slots in the global list only when SCAN_GEN_FLUSH reads have gathered -- a returning global atomic on
@@ -260,8 +308,20 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MINB) lsq_scan_kernel(const _
             if (total != P.len0) atomicAdd(P.sig_dev + sig, (unsigned long long)(long long)((int)total - (int)P.len0));
             ++c_single;
         } else if (rt == RT_PAIR) {
-            if (sig_hash_add(P, key, total)) {
+            const uint32_t slot = sig_hash_slot(P, key);
+            if (slot != 0xFFFFFFFFu) {
+                sig_hash_count(P, slot, total);
                 ++c_pair;
+            } else {
+                ++c_full;
+                rt = RT_GENERAL;
+            }
+        } else if (rt == RT_TRIPLE) {  // key: the prefix (pair key of blocks 0 and 1); sig: piece 2 << 4 | cut category
+            const uint32_t ps = sig_hash_slot(P, key);  // interned, not counted
+            const uint32_t slot = ps != 0xFFFFFFFFu ? sig_hash_slot(P, triple_key(ps, sig >> 4, sig & 15u)) : 0xFFFFFFFFu;
+            if (slot != 0xFFFFFFFFu) {
+                sig_hash_count(P, slot, total);
+                ++c_triple;
             } else {
                 ++c_full;
                 rt = RT_GENERAL;
@@ -279,6 +339,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MINB) lsq_scan_kernel(const _
         uint32_t o;               // first block of my first read
         uint32_t g_end;           // one past the group's last block (warp-uniform)
         uint32_t dmask = 0;       // bit 8k+7: my read k has two raw blocks and is not chimeric
+        uint32_t tmask = 0;       // ... three raw blocks
         const bool compact_cnt = COMPACT || P.blk_cnt != nullptr, compact_cs = COMPACT || P.read_cs8 != nullptr;
         if (compact_cs && r0 < g1) v4 = __ldcs(reinterpret_cast<const uint32_t *>(P.read_cs8 + r0));
         if (compact_cnt) {
@@ -297,8 +358,9 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MINB) lsq_scan_kernel(const _
             g_end = gbase + __shfl_sync(0xFFFFFFFFu, incl, 31);
             o = gbase + incl - mine;
             if (compact_cs) {  // bytes of c4 equal to 2 (exact zero-byte test on c4 ^ 0x02020202), not chimeric
-                const uint32_t t = c4 ^ 0x02020202u;
+                const uint32_t t = c4 ^ 0x02020202u, t3 = c4 ^ 0x03030303u;
                 dmask = ~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t | 0x7F7F7F7Fu) & ~v4 & 0x80808080u;
+                if (!no_triple) tmask = ~(((t3 & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t3 | 0x7F7F7F7Fu) & ~v4 & 0x80808080u;
             }
         } else {
             o = r0 < g1 ? __ldcs(P.blk_off + r0) : 0u;
@@ -318,16 +380,20 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MINB) lsq_scan_kernel(const _
             __syncwarp();
         }
         // where my two-block reads go in the warp's list: known before the loop when both per-read arrays are compact
-        uint32_t nd = __popc(dmask), n_dbl = 0, dpos = 0;
-        if (compact_cnt && compact_cs) {
-            uint32_t incl = nd;
+        uint32_t nd = __popc(dmask), n_dbl = 0, dpos = 0, n_tri = 0, tpos = 0;
+        if (compact_cnt && compact_cs) {  // both counts in one scan: doubles in the low half, triples in the high half
+            const uint32_t mine = nd | ((uint32_t)__popc(tmask) << 16);
+            uint32_t incl = mine;
 #pragma unroll
             for (uint32_t d = 1; d < 32u; d <<= 1) {
                 const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
                 if (lane >= d) incl += t;
             }
-            n_dbl = __shfl_sync(0xFFFFFFFFu, incl, 31);
-            dpos = incl - nd;
+            const uint32_t tot = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            n_dbl = tot & 0xFFFFu;
+            n_tri = tot >> 16;
+            dpos = (incl - mine) & 0xFFFFu;
+            tpos = (incl - mine) >> 16;
         }
         // ---- phase S --------------------------------------------------------------------------
         // SCAN_FLIGHT reads per round: their block loads, then their bucket gathers, then their piece-record gathers
@@ -365,8 +431,10 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MINB) lsq_scan_kernel(const _
                             s_dbl[warp][4u * lane + nd] = d;
                             ++nd;
                         }
+                    } else if (rn == 3u && plain && compact_cnt && compact_cs && !no_triple) {
+                        s_tri[warp][tpos++] = make_uint2(base[u], c[u] | ((4u * lane + k) << 24));
                     } else if (rn != 0u) {
-                        to_general(r, base[u]);  // three and more blocks, chimeric reads
+                        to_general(r, base[u]);  // more blocks, chimeric reads
                     }
                 }
             }
@@ -437,6 +505,17 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MINB) lsq_scan_kernel(const _
             const uint32_t rt = route_double(P, b0, b1, p0, raw0, kept0, p1, raw1, kept1, sig, key, total);
             tally(rt, sig, key, total, r, base);
         }
+        // ---- phase T: three-block reads, one per lane and round ---------------------------------------------
+#pragma unroll 1
+        for (uint32_t i = lane; LSQ_SCAN_TRIPLES && i < n_tri; i += 32u) {
+            const uint2 d = s_tri[warp][i];
+            const uint32_t base = d.x, c = d.y & 0xFFFFu;
+            const uint64_t r = g0 + (d.y >> 24);
+            uint32_t sig, total;
+            uint64_t key;
+            const uint32_t rt = scan_triple<COMPACT>(P, base, c, sig, key, total);
+            tally(rt, sig, key, total, r, base);
+        }
         // ---- flush the warp's general reads when enough have gathered --------------------------------
         __syncwarp();
         if (s_ngen[warp] >= SCAN_GEN_FLUSH) flush_general();  // warp-uniform
@@ -446,11 +525,13 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MINB) lsq_scan_kernel(const _
     if (s_ngen[warp] != 0u) flush_general();
     c_single = __reduce_add_sync(0xFFFFFFFFu, c_single);
     c_pair = __reduce_add_sync(0xFFFFFFFFu, c_pair);
+    c_triple = __reduce_add_sync(0xFFFFFFFFu, c_triple);
     c_general = __reduce_add_sync(0xFFFFFFFFu, c_general);
     c_full = __reduce_add_sync(0xFFFFFFFFu, c_full);
     if (lane == 0) {
         if (c_single) atomicAdd(P.counters + CTR_SINGLE_SIG, (unsigned long long)c_single);
         if (c_pair) atomicAdd(P.counters + CTR_PAIR_SIG, (unsigned long long)c_pair);
+        if (c_triple) atomicAdd(P.counters + CTR_TRIPLE_SIG, (unsigned long long)c_triple);
         if (c_general) atomicAdd(P.counters + CTR_GENERAL, (unsigned long long)c_general);
         if (c_full) atomicAdd(P.counters + CTR_HASH_FULL, (unsigned long long)c_full);
     }
@@ -625,10 +706,14 @@ __global__ void __launch_bounds__(128) lsq_expand_kernel(const __grid_constant__
         if (!sig_rep_single(T, (uint32_t)i, rv, piece)) return;
     } else if (i - T.n_sig < n_hash) {
         const ulonglong2 e = P.hash[i - T.n_sig];
-        if (e.x == 0ull || e.y == 0ull) return;
+        if (e.x == 0ull || e.y == 0ull) return;  // empty, or a prefix that only three-block reads use
         cnt = e.y;
         dev = P.hash_dev[i - T.n_sig];
-        if (!sig_rep_pair(T, e.x, rv, piece)) return;
+        if (e.x & TRIPLE_KEY_BIT) {
+            if (!sig_rep_triple(T, P.hash[(uint32_t)e.x & 0x3FFFFFFFu].x, e.x, rv, piece)) return;
+        } else if (!sig_rep_pair(T, e.x, rv, piece)) {
+            return;
+        }
     } else {
         return;
     }

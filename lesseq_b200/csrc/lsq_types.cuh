@@ -82,6 +82,13 @@ LSQ_TYPES_HD uint64_t pair_key(uint32_t p0, uint32_t k0, uint32_t p1, uint32_t k
     return (uint64_t)p0 | ((uint64_t)k0 << 26) | ((uint64_t)p1 << 30) | ((uint64_t)k1 << 56);
 }
 constexpr uint32_t HASH_MAX_PROBES = 32;
+// Signature of a three-block read: the hash slot that interns its (piece 0, cut 0, piece 1, cut 1) prefix -- a pair
+// key, present with count 0 when no two-block read shares it -- then piece 2 and the cut category of its end.
+// Bit 63 tells the two kinds of key apart (a pair key uses bits 0-59).
+constexpr uint64_t TRIPLE_KEY_BIT = 1ull << 63;
+LSQ_TYPES_HD uint64_t triple_key(uint32_t prefix_slot, uint32_t p2, uint32_t k2) {
+    return TRIPLE_KEY_BIT | (uint64_t)prefix_slot | ((uint64_t)p2 << 30) | ((uint64_t)k2 << 56);
+}
 
 struct Tables {
     uint32_t E, F, n_pieces, n_chroms, n_ann_strands, n_sig;
@@ -137,7 +144,7 @@ constexpr uint32_t SCAN_GROUP = 128;
 constexpr uint32_t SCAN_SUPER = 256;  // groups per super-group of the block-offset index (grp_base / sup_base)
 
 // Counters of the scan (statistics; per read set)
-constexpr int CTR_SINGLE_SIG = 0, CTR_PAIR_SIG = 1, CTR_GENERAL = 2, CTR_NONE = 3, CTR_HASH_FULL = 4, CTR_N = 8;
+constexpr int CTR_SINGLE_SIG = 0, CTR_PAIR_SIG = 1, CTR_GENERAL = 2, CTR_NONE = 3, CTR_HASH_FULL = 4, CTR_TRIPLE_SIG = 5, CTR_N = 8;
 
 // Everything the count path reads and writes for one read set.  Inputs come in two forms:
 //   wide     blk_off u32[n+1] (CSR), blk int2[B], read_cs u32[n]
@@ -181,7 +188,7 @@ struct ScanParams {
     unsigned long long *slot_mask;  // hash keys (EV_HASH events)
     unsigned long long *bases;      // [E] internal order
 };
-constexpr uint32_t SCAN_NO_SINGLE_SIG = 1u, SCAN_NO_PAIR_SIG = 2u;  // debugging: send those reads to lsq_general_kernel
+constexpr uint32_t SCAN_NO_SINGLE_SIG = 1u, SCAN_NO_PAIR_SIG = 2u, SCAN_NO_TRIPLE_SIG = 4u;  // debugging: send those reads to lsq_general_kernel
 
 // Read bucketing per gene-range shard (count.cpp:202-215: every process of the reference reads the whole file and
 // keeps what its range covers).  The router runs on the tables of the WHOLE selection; owner[p] has bit d set when

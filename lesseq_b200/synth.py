@@ -325,6 +325,74 @@ def make_solve_stress(n_events, seed, k_range=(2, 16)):
     }
 
 
+def make_multiform_case(n_events, reads_per_event, read_len, seed, k_range=(2, 16)):
+    """BASELINE config 5 materialised: events with K~U{k_range} forms over S~U{K..2K} segments, every form a
+    random subset of the segments (written as one exon per member segment; 70 % of the gaps are introns, the others
+    abut), and reads drawn from the forms (Dirichlet proportions, uniform start on the spliced form, blocks cut at
+    segment ends with abutting pieces fused).  Returns (SynthAnnotation, packed reads dict of numpy arrays) -- small
+    enough to go through the reference's own solve binary."""
+    rng = np.random.default_rng(seed)
+    A = SynthAnnotation()
+    A.chrom_names = ["chr%d" % (c + 1) for c in range(4)]
+    cursor = [1000] * 4
+    blk, nblk, cs = [], [], []
+    for e in range(n_events):
+        c = e % 4
+        K = int(rng.integers(k_range[0], k_range[1] + 1))
+        S = int(rng.integers(K, 2 * K + 1))
+        lens = rng.integers(30, 400, S)
+        gaps = rng.integers(1, 300, S) * (rng.random(S) < 0.7)
+        segs = []
+        p = cursor[c] + 3000
+        for j in range(S):
+            p += int(gaps[j])
+            segs.append((p, p + int(lens[j])))
+            p += int(lens[j])
+        cursor[c] = p
+        forms = []
+        for k in range(K):
+            member = rng.random(S) < 0.6
+            member[rng.integers(0, S)] = True
+            forms.append([segs[j] for j in range(S) if member[j]])
+        strand = "+" if rng.random() < 0.5 else "-"
+        for k, f in enumerate(forms):
+            name = "M%d|%d" % (e, k + 1)
+            A.forms.append((name, c, strand, f))
+            A.map_rows.append(("mf_%d" % e, name))
+        A.ev_gene.append(e)
+        theta = rng.dirichlet(np.full(K, 0.7))
+        n = int(rng.integers(max(2, reads_per_event // 4), 2 * reads_per_event))
+        for k in rng.choice(K, size=n, p=theta):
+            f = forms[k]
+            T = sum(b - a for a, b in f)
+            if T < read_len:
+                continue
+            st = int(rng.integers(0, T - read_len + 1))
+            pieces, off = [], 0
+            for a, b in f:
+                lo, hi = max(st, off), min(st + read_len, off + (b - a))
+                if hi > lo:
+                    g0, g1 = a + lo - off, a + hi - off
+                    if pieces and pieces[-1][1] == g0:
+                        pieces[-1][1] = g1
+                    else:
+                        pieces.append([g0, g1])
+                off += b - a
+            nblk.append(len(pieces))
+            blk.extend(pieces)
+            cs.append(c | (int(rng.integers(0, 2)) << 16))
+    A.n_genes = n_events
+    A.chrom_len = [x + 10000 for x in cursor]
+    n = len(nblk)
+    off = np.zeros(n + 1, dtype=np.uint32)
+    off[1:] = np.cumsum(nblk)
+    b = np.asarray(blk, dtype=np.int32).reshape(-1)
+    reads = {"blk_off": off, "blk": b, "read_cs": np.asarray(cs, dtype=np.uint32), "line_num": np.arange(1, n + 1, dtype=np.uint32),
+             "chrom_names": list(A.chrom_names), "strand_names": ["-", "+"], "n_reads": n, "n_blocks": int(off[-1]),
+             "total_read_bases": float((b[1::2] - b[0::2]).sum())}
+    return A, reads
+
+
 def make_solve_stress_fast(n_events, seed, k_range=(2, 16)):
     """Vectorised variant of make_solve_stress for the full BASELINE config-5 size (500 k events):
     same shapes (K~U{2..16}, S~U{K..2K}, C~U{K..3K} classes, log-normal multiplicities); class masks

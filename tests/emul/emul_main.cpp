@@ -327,8 +327,10 @@ int main(int argc, char **argv) {
         std::vector<uint64_t> sig_cnt(T.n_sig, 0);
         std::vector<int64_t> sig_dev(T.n_sig, 0);
         std::map<uint64_t, std::pair<uint64_t, int64_t> > pair_sig;
+        std::map<std::pair<uint64_t, uint32_t>, std::pair<uint64_t, int64_t> > triple_sig;  // (prefix pair key, piece 2 << 4 | cut)
         std::vector<uint2> gen_list;
-        uint64_t n_single = 0, n_pair = 0;
+        uint64_t n_single = 0, n_pair = 0, n_triple = 0;
+        unsigned long long gen_by_blocks[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (size_t r = 0; r < n; ++r) {
             if (n_shards > 1 && !((owner_mask[m][r] >> shard) & 1ull)) continue;  // not in this rank's bucket
             const uint32_t base = R.blk_off[r], nraw = R.blk_off[r + 1] - base;
@@ -348,13 +350,23 @@ int main(int argc, char **argv) {
                 e.first++;
                 e.second += (int64_t)total - (int64_t)FP.len0;
                 ++n_pair;
+            } else if (rt == RT_TRIPLE) {
+                auto &e = triple_sig[std::make_pair(key, sig)];
+                e.first++;
+                e.second += (int64_t)total - (int64_t)FP.len0;
+                ++n_triple;
             } else if (rt == RT_GENERAL) {
                 gen_list.push_back(make_uint2((uint32_t)r, base));
+                gen_by_blocks[nraw < 7u ? nraw : 7u]++;
             }
         }
         if (getenv("LSQ_EMUL_STATS"))
-            fprintf(stderr, "emul: reads %zu single-sig %llu pair-sig %llu (distinct %zu) general %zu\n", n, (unsigned long long)n_single,
-                    (unsigned long long)n_pair, pair_sig.size(), gen_list.size());
+            fprintf(stderr, "emul: general reads by raw blocks 1:%llu 2:%llu 3:%llu 4:%llu 5:%llu 6:%llu 7+:%llu\n", gen_by_blocks[1],
+                    gen_by_blocks[2], gen_by_blocks[3], gen_by_blocks[4], gen_by_blocks[5], gen_by_blocks[6], gen_by_blocks[7]);
+        if (getenv("LSQ_EMUL_STATS"))
+            fprintf(stderr, "emul: reads %zu single-sig %llu pair-sig %llu (distinct %zu) triple-sig %llu (distinct %zu) general %zu\n", n,
+                    (unsigned long long)n_single, (unsigned long long)n_pair, pair_sig.size(), (unsigned long long)n_triple,
+                    triple_sig.size(), gen_list.size());
         // lsq_expand_kernel
         auto expand = [&](const ReadView &rv, uint32_t piece, uint64_t cnt, int64_t dev) {
             const uint64_t b = (uint64_t)((int64_t)(cnt * (uint64_t)FP.len0) + dev);
@@ -378,6 +390,15 @@ int main(int argc, char **argv) {
             uint32_t piece;
             if (!sig_rep_pair(T, kv.first, rv, piece)) {
                 fprintf(stderr, "emul: counted pair signature without a representative read\n");
+                return 3;
+            }
+            expand(rv, piece, kv.second.first, kv.second.second);
+        }
+        for (auto &kv : triple_sig) {
+            ReadView rv;
+            uint32_t piece;
+            if (!sig_rep_triple(T, kv.first.first, triple_key(0u, kv.first.second >> 4, kv.first.second & 15u), rv, piece)) {
+                fprintf(stderr, "emul: counted triple signature without a representative read\n");
                 return 3;
             }
             expand(rv, piece, kv.second.first, kv.second.second);

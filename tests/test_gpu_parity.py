@@ -160,7 +160,7 @@ def _synth_case(api, tmp_path, name, n_genes, n_reads, seed, **kw):
 
 
 @pytest.mark.parametrize("name,n_genes,n_reads,kw", [
-    ("C1", 500, 200000, {}),
+    ("C1", 500, 1000000, {}),   # BASELINE config 1 at its stated size
     ("C2", 400, 200000, {}),
     ("C4", 400, 200000, {"overhang_frac": 0.02}),
     ("C2", 3000, 2000000, {"overhang_frac": 0.01}),
@@ -178,6 +178,54 @@ def test_synthetic_configs_match_oracle(api, oracle_bin, tmp_path, name, n_genes
         assert len(o1.splitlines()) == 2 * len(A.ev_gene)
         bad = tables_match(o1, o2, prog == "solve")
         assert bad is None, "%s %s: %s" % (name, prog, bad)
+
+
+def test_c2_full_annotation_5m_reads_match_oracle(api, oracle_bin, tmp_path):
+    """BASELINE config 2's FULL annotation (20 000 genes, 69 930 events of all 8 types) with a 5 M-read text subsample of
+    the benched workload, through the drop-in executables at 17 digits against the pinned oracle."""
+    import torch
+    from lesseq_b200 import synth
+    A, R, _ = synth.make_config("C2")
+    fp, mp, rp = str(tmp_path / "ev.interval"), str(tmp_path / "ev.map"), str(tmp_path / "r.mrf")
+    A.write(fp, mp)
+    reads = synth.make_reads(A, 5_000_000, R, 100, device="cuda")  # the bench's generator and seed, first 5 M reads' worth
+    hr = api.Reads.from_numpy(reads["blk_off"].cpu().numpy(), reads["blk"].cpu().numpy(), reads["read_cs"].cpu().numpy(),
+                              reads["line_num"].cpu().numpy(), reads["chrom_names"], reads["strand_names"])
+    hr.write_mrf(rp)
+    trb = reads["total_read_bases"]
+    del reads
+    torch.cuda.empty_cache()
+    ca = ["0", "p", str(tmp_path / "o_"), "LH_GENE_TXT", fp, "UCSC_GENE2ISOFORM", mp, "0", "100000000", "MRF_SINGLE", "SHORT_READ", str(R), rp]
+    for prog, args in (("count", ca), ("solve", ca + [repr(trb)])):
+        rc1, o1, e1 = oracle_bin.run_oracle(prog, args)
+        rc2, o2, e2 = api.run_program(prog, args, precision=17)
+        assert rc1 == 0 and rc2 == 0, e2
+        assert len(o1.splitlines()) == 2 * len(A.ev_gene) == 139860
+        bad = tables_match(o1, o2, prog == "solve")
+        assert bad is None, "%s: %s" % (prog, bad)
+
+
+def test_c5_shaped_events_match_reference_solve_binary(api, oracle_bin, tmp_path):
+    """BASELINE config 5 materialised: 2 000 events with 2-16 forms over K..2K segments and reads drawn from
+    the forms, through the drop-in `solve` at 17 digits against the REFERENCE'S OWN BINARY (oracle/_ref/solve; the pinned
+    oracle where the binaries are not available) -- the multi-form EM, the mid and warp solve kernels and the hashed
+    class tables (K > 8) against the real thing rather than a numpy restatement."""
+    from lesseq_b200 import synth
+    A, reads = synth.make_multiform_case(2000, 120, 50, 55)
+    fp, mp, rp = str(tmp_path / "ev.interval"), str(tmp_path / "ev.map"), str(tmp_path / "r.mrf")
+    A.write(fp, mp)
+    api.Reads.from_numpy(reads["blk_off"], reads["blk"], reads["read_cs"], reads["line_num"], reads["chrom_names"],
+                         reads["strand_names"]).write_mrf(rp)
+    ca = ["0", "p", str(tmp_path / "o_"), "LH_GENE_TXT", fp, "UCSC_GENE2ISOFORM", mp, "0", "100000000", "MRF_SINGLE", "MEDIUM_READ", "50", rp]
+    sa = ca + [repr(reads["total_read_bases"])]
+    use_ref = oracle_bin.ref_available() or oracle_bin.build_ref()
+    for prog, args in (("count", ca), ("solve", sa)):
+        rc1, o1, e1 = oracle_bin.run_ref(prog, args) if use_ref else oracle_bin.run_oracle(prog, args)
+        rc2, o2, e2 = api.run_program(prog, args, precision=17)
+        assert rc1 == 0 and rc2 == 0, (e1[-300:], e2[-300:])
+        assert len(o1.splitlines()) == len(A.forms) > 15000
+        bad = tables_match(o1, o2, prog == "solve")
+        assert bad is None, "%s: %s" % (prog, bad)
 
 
 def test_device_resident_reads_and_properties(api, tmp_path):
