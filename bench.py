@@ -509,6 +509,7 @@ def run_ours(args):
             "phases_ms_per_step_rank0": {k: v / args.steps for k, v in phases.items()},
             "reads_rank0": {k: int(tsum[k]) for k in ("reads_in", "blocks_in", "reads_single", "reads_pair", "reads_triple", "reads_general", "hash_full")},
             "valid_pairs_rank0": int(tsum["pairs_valid"]), "em_exact_replays_rank0": int(tsum["exact_events"]),
+            "em_exact_replay_ms_rank0": float(tsum["exact_ms"]),  # part of solve_ms, last step
             "em_iters_mean": float(sol["iters"].mean()), "em_iters_max": int(sol["iters"].max()),
             "em_iters_p99": float(np.percentile(sol["iters"], 99)),
         }

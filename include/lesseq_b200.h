@@ -170,7 +170,8 @@ typedef struct lsq_timings {
     uint64_t reads_general;         /* reads walked one by one */
     uint64_t hash_full;             /* two-block reads that found no hash slot (walked one by one) */
     uint64_t pairs_valid;           /* valid (read, event) pairs */
-    uint64_t reads_triple;          /* reads tallied by a three-block signature */
+    uint64_t reads_triple;          /* reads tallied by a three-block signature (a build option, off by default) */
+    float exact_ms;                 /* part of solve_ms: the read-by-read replay of the exact_events (host wall clock) */
 } lsq_timings;
 
 const char *lsq_last_error(void);

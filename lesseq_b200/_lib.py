@@ -65,7 +65,7 @@ class Timings(C.Structure):
         ("finalize_ms", C.c_float), ("solve_ms", C.c_float),
         ("launches", C.c_uint32), ("exact_events", C.c_uint32),
         ("reads_in", C.c_uint64), ("blocks_in", C.c_uint64), ("reads_single", C.c_uint64), ("reads_pair", C.c_uint64),
-        ("reads_general", C.c_uint64), ("hash_full", C.c_uint64), ("pairs_valid", C.c_uint64), ("reads_triple", C.c_uint64),
+        ("reads_general", C.c_uint64), ("hash_full", C.c_uint64), ("pairs_valid", C.c_uint64), ("reads_triple", C.c_uint64), ("exact_ms", C.c_float),
     ]
 
 

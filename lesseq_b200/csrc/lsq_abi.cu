@@ -7,6 +7,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -122,7 +123,8 @@ struct lsq_ctx {
     DevBuf d_n_valid, d_bases_out, d_iso, d_theta, d_rpkm, d_se, d_ll, d_llpr, d_iters;
     DevBuf d_mid;  // work order of lsq_solve_mid_kernel
     DevBuf d_flag, d_exact, d_exact_rec;  // order-exact EM replay: flag list + per-event flags; spans, segments; records
-    uint32_t exact_events = 0;            // events replayed by the last lsq_solve (statistics)
+    uint32_t exact_events = 0;  // events replayed by the last lsq_solve (statistics)
+    float exact_ms = 0.f;       // host wall time of that replay (collect + sort + replay, its round trips included)
     bool counted = false, finalized = false, solved = false;
     // streamed read sets: copies run on their own stream and publish their progress to the filter
     cudaStream_t copy_stream = nullptr;
@@ -862,7 +864,8 @@ static int exact_replay(lsq_ctx *c, const lsq::SolveParams &P, uint32_t n_flag) 
     const size_t o_cur = (size_t)(n_flag + 1) * 8, o_ivoff = o_cur + (((size_t)n_flag * 4 + 7) & ~(size_t)7), o_ivs = o_ivoff + (size_t)(nch + 2) * 4,
                  o_ive = o_ivs + niv * 4 + 4, o_sr = o_ive + niv * 4 + 4, bytes = o_sr + (size_t)LSQ_MAX_METHODS * 256;
     LSQ_CUDA(c->d_exact.ensure(bytes));
-    LSQ_CUDA(c->d_exact_rec.ensure(std::max<uint64_t>(seg_off[n_flag], 1) * sizeof(lsq::ExactRec)));
+    const uint64_t n_rec = std::max<uint64_t>(seg_off[n_flag], 1);  // records, then one class byte per record
+    LSQ_CUDA(c->d_exact_rec.ensure(n_rec * sizeof(lsq::ExactRec) + n_rec + 16));
     unsigned char *d = c->d_exact.as<unsigned char>();
     std::vector<unsigned char> hbuf(bytes, 0);
     memcpy(hbuf.data(), seg_off.data(), (size_t)(n_flag + 1) * 8);
@@ -926,7 +929,8 @@ static int exact_replay(lsq_ctx *c, const lsq::SolveParams &P, uint32_t n_flag) 
     X.seg_off = reinterpret_cast<const uint64_t *>(d);
     X.seg_cur = reinterpret_cast<const uint32_t *>(d + o_cur);
     X.rec = c->d_exact_rec.as<lsq::ExactRec>();
-    lsq::lsq_exact_kernel<<<n_flag, 32, 0, s>>>(P, X);
+    X.cls = reinterpret_cast<uint8_t *>(X.rec + n_rec);
+    lsq::lsq_exact_kernel<<<n_flag, lsq::EXACT_BLOCK, 0, s>>>(P, X);
     LSQ_CUDA(cudaGetLastError());
     c->tm.launches++;
     LSQ_CUDA(cudaStreamSynchronize(s));  // hbuf and friends go out of scope
@@ -995,17 +999,24 @@ int lsq_solve(lsq_ctx *c, const double *total_read_bases, uint32_t n_methods) {
         lsq::lsq_solve_kernel<WARPS><<<grid, WARPS * 32, 0, s>>>(P);
         LSQ_CUDA(cudaGetLastError());
         c->tm.launches++;
+        grid = std::min<unsigned>((c->E + lsq::SE_WARPS - 1) / lsq::SE_WARPS, (unsigned)c->n_sms * 8u);
+        lsq::lsq_se_kernel<<<grid, lsq::SE_WARPS * 32, 0, s>>>(P);
+        LSQ_CUDA(cudaGetLastError());
+        c->tm.launches++;
     }
     // events whose stop decision is within summation-order noise of its threshold are replayed read by read (rare);
     // this is the one host round trip of the lsq_count + lsq_solve pair
     c->exact_events = 0;
+    c->exact_ms = 0.f;
     if (c->E && !getenv("LSQ_NO_EXACT_EM")) {
         uint32_t n_flag = 0;
         LSQ_CUDA(cudaMemcpyAsync(&n_flag, P.flag_n, 4, cudaMemcpyDeviceToHost, s));
         LSQ_CUDA(cudaStreamSynchronize(s));
         if (n_flag) {
+            const auto t0 = std::chrono::steady_clock::now();
             rc = exact_replay(c, P, n_flag);
             if (rc) return rc;
+            c->exact_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
         }
     }
     LSQ_CUDA(cudaEventRecord(c->ev[3], s));
@@ -1096,6 +1107,7 @@ int lsq_get_timings(lsq_ctx *c, lsq_timings *o) {
     }
     if (c->tm_solve_pending) {
         tm.exact_events = c->exact_events;
+        tm.exact_ms = c->exact_ms;
         LSQ_CUDA(cudaEventElapsedTime(&tm.solve_ms, c->ev[2], c->ev[3]));
         c->tm_solve_pending = false;
     }

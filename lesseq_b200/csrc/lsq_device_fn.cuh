@@ -1006,41 +1006,71 @@ LSQ_HD double exact_class_prob(uint64_t mask, uint32_t K, const double *theta, c
     return s;
 }
 
-// compute_iso_probs_EM (read.h:638-660) over the sorted records.  theta (K doubles) receives the result, old_theta is
-// scratch.  Returns the iterations executed; ll_out = the final log-likelihood.
+// compute_iso_probs_EM (read.h:638-660) over the sorted records, every term evaluated per read: for events with more
+// classes than the tables below hold.  theta (K doubles) receives the result, old_theta is scratch.  Returns the
+// iterations executed; ll_out = the final log-likelihood.
+LSQ_HD uint32_t exact_em_per_read(const ExactRec *rec, uint32_t n, double n_total, uint32_t K, const double *G, size_t g_stride,
+                                  double *theta, double *old_theta, double &ll_out, uint32_t max_iters) {
+    auto loglik = [&](const double *th) {
+        double ll = 0.0;
+        for (uint32_t i = 0; i < n; ++i)
+            ll = lsq_add(ll, log(exact_class_prob(rec[i].mask, K, th, G + (size_t)exact_rec_set(rec[i]) * g_stride)));
+        return ll;
+    };
+    for (uint32_t k = 0; k < K; ++k) theta[k] = lsq_div(1.0, (double)K);
+    uint32_t iters = 0;
+    double ll = loglik(theta);
+    while (true) {
+        for (uint32_t k = 0; k < K; ++k) old_theta[k] = theta[k];
+        const double old_ll = ll;
+        for (uint32_t k = 0; k < K; ++k) {
+            double sum_zeta = 0.0;
+            for (uint32_t i = 0; i < n; ++i) {
+                const double *g = G + (size_t)exact_rec_set(rec[i]) * g_stride;
+                const double sc = exact_class_prob(rec[i].mask, K, old_theta, g);
+                if (sc > 0.0) {
+                    const double lp = lsq_mul(old_theta[k], ((rec[i].mask >> k) & 1ull) ? g[k] : 0.0);
+                    if (lp > 0.0) sum_zeta = lsq_add(sum_zeta, lsq_div(lp, sc));
+                }
+            }
+            theta[k] = lsq_div(sum_zeta, n_total);
+        }
+        ll = loglik(theta);
+        ++iters;
+        const double d = 1.0 - lsq_div(old_ll, ll);
+        if (!((d < 0.0 ? -d : d) > 1E-6) || iters >= max_iters) break;
+    }
+    ll_out = ll;
+    return iters;
+}
+
+// The same with the terms tabulated per class (one thread; lsq_exact_kernel runs this computation with one thread per
+// running sum, the CPU replay of tests/emul runs it as written).
 LSQ_HD uint32_t exact_em(ExactRec *rec, uint32_t n, double n_total, uint32_t K, const double *G, size_t g_stride,
                          double *theta, double *old_theta, double &ll_out, uint32_t max_iters) {
     // classes of the event: distinct (read set, mask) pairs; a read's class index goes into bits 40-51 of k1
     uint64_t cmask[EXACT_MAX_CLS];
     uint32_t cset[EXACT_MAX_CLS];
     uint32_t C = 0;
-    bool tab = true;
-    for (uint32_t i = 0; i < n && tab; ++i) {
+    for (uint32_t i = 0; i < n; ++i) {
         const uint32_t m = exact_rec_set(rec[i]);
         uint32_t c = 0;
         while (c < C && !(cmask[c] == rec[i].mask && cset[c] == m)) ++c;
         if (c == C) {
-            if (C == EXACT_MAX_CLS || (C + 1u) * K > EXACT_MAX_TERMS) {
-                tab = false;
-                break;
-            }
+            if (C == EXACT_MAX_CLS || (C + 1u) * (K + 1u) > EXACT_MAX_TERMS + EXACT_MAX_CLS)
+                return exact_em_per_read(rec, n, n_total, K, G, g_stride, theta, old_theta, ll_out, max_iters);
             cmask[C] = rec[i].mask;
             cset[C] = m;
             ++C;
         }
         rec[i].k1 = (rec[i].k1 & 0xFFFF00FFFFFFFFFFull) | ((uint64_t)c << 40);
     }
-    double term[EXACT_MAX_TERMS];  // [class][form] E-step terms
-    double lterm[EXACT_MAX_CLS];   // log-likelihood term per class
+    double term[EXACT_MAX_TERMS + EXACT_MAX_CLS];  // [class][form] E-step terms
+    double lterm[EXACT_MAX_CLS];                   // log-likelihood term per class
     auto loglik = [&](const double *th) {
         double ll = 0.0;
-        if (tab) {
-            for (uint32_t c = 0; c < C; ++c) lterm[c] = log(exact_class_prob(cmask[c], K, th, G + (size_t)cset[c] * g_stride));
-            for (uint32_t i = 0; i < n; ++i) ll = lsq_add(ll, lterm[(rec[i].k1 >> 40) & 0xFFu]);
-        } else {
-            for (uint32_t i = 0; i < n; ++i)
-                ll = lsq_add(ll, log(exact_class_prob(rec[i].mask, K, th, G + (size_t)exact_rec_set(rec[i]) * g_stride)));
-        }
+        for (uint32_t c = 0; c < C; ++c) lterm[c] = log(exact_class_prob(cmask[c], K, th, G + (size_t)cset[c] * g_stride));
+        for (uint32_t i = 0; i < n; ++i) ll = lsq_add(ll, lterm[(rec[i].k1 >> 40) & 0xFFu]);
         return ll;
     };
     for (uint32_t k = 0; k < K; ++k) theta[k] = lsq_div(1.0, (double)K);
@@ -1049,35 +1079,21 @@ LSQ_HD uint32_t exact_em(ExactRec *rec, uint32_t n, double n_total, uint32_t K, 
     while (true) {
         for (uint32_t k = 0; k < K; ++k) old_theta[k] = theta[k];
         const double old_ll = ll;
-        if (tab) {  // compute_iso_probs_EM_step, read.h:592-618: a skipped term (s <= 0 or lp <= 0) adds nothing, like + 0.0
-            for (uint32_t c = 0; c < C; ++c) {
-                const double *g = G + (size_t)cset[c] * g_stride;
-                const double sc = exact_class_prob(cmask[c], K, old_theta, g);
-                for (uint32_t k = 0; k < K; ++k) {
-                    const double lp = lsq_mul(old_theta[k], ((cmask[c] >> k) & 1ull) ? g[k] : 0.0);
-                    term[c * K + k] = (sc > 0.0 && lp > 0.0) ? lsq_div(lp, sc) : 0.0;
-                }
-            }
-            for (uint32_t k = 0; k < K; ++k) theta[k] = 0.0;
-            for (uint32_t i = 0; i < n; ++i) {  // K independent running sums, each in read order
-                const double *t = term + ((rec[i].k1 >> 40) & 0xFFu) * K;
-                for (uint32_t k = 0; k < K; ++k) theta[k] = lsq_add(theta[k], t[k]);
-            }
-            for (uint32_t k = 0; k < K; ++k) theta[k] = lsq_div(theta[k], n_total);
-        } else {
+        // compute_iso_probs_EM_step, read.h:592-618: a skipped term (s <= 0 or lp <= 0) adds nothing, like + 0.0
+        for (uint32_t c = 0; c < C; ++c) {
+            const double *g = G + (size_t)cset[c] * g_stride;
+            const double sc = exact_class_prob(cmask[c], K, old_theta, g);
             for (uint32_t k = 0; k < K; ++k) {
-                double sum_zeta = 0.0;
-                for (uint32_t i = 0; i < n; ++i) {
-                    const double *g = G + (size_t)exact_rec_set(rec[i]) * g_stride;
-                    const double sc = exact_class_prob(rec[i].mask, K, old_theta, g);
-                    if (sc > 0.0) {
-                        const double lp = lsq_mul(old_theta[k], ((rec[i].mask >> k) & 1ull) ? g[k] : 0.0);
-                        if (lp > 0.0) sum_zeta = lsq_add(sum_zeta, lsq_div(lp, sc));
-                    }
-                }
-                theta[k] = lsq_div(sum_zeta, n_total);
+                const double lp = lsq_mul(old_theta[k], ((cmask[c] >> k) & 1ull) ? g[k] : 0.0);
+                term[c * K + k] = (sc > 0.0 && lp > 0.0) ? lsq_div(lp, sc) : 0.0;
             }
         }
+        for (uint32_t k = 0; k < K; ++k) theta[k] = 0.0;
+        for (uint32_t i = 0; i < n; ++i) {  // K independent running sums, each in read order
+            const double *t = term + ((rec[i].k1 >> 40) & 0xFFu) * K;
+            for (uint32_t k = 0; k < K; ++k) theta[k] = lsq_add(theta[k], t[k]);
+        }
+        for (uint32_t k = 0; k < K; ++k) theta[k] = lsq_div(theta[k], n_total);
         ll = loglik(theta);
         ++iters;
         const double d = 1.0 - lsq_div(old_ll, ll);

@@ -143,7 +143,10 @@ constexpr int SCAN_MINB = LSQ_SCAN_MINB;
 constexpr int SCAN_WARPS = SCAN_BLOCK / 32;
 constexpr int SCAN_ITEMS = 4;     // reads per lane
 #ifndef LSQ_SCAN_TRIPLES
-#define LSQ_SCAN_TRIPLES 1  // three-block reads get a signature route of their own (0: they take the general path)
+// 1: three-block reads get a signature route of their own (phase T) instead of the general path.  Correct and tested,
+// but off: at C4 it takes 1.0 ms off lsq_general_kernel and puts 1.2 ms on the scan (one more dependent chain of
+// lookups per group for ~4 reads of 128), at C2 it costs 0.13 ms for nothing (profiles/r02_elimination_experiments.txt).
+#define LSQ_SCAN_TRIPLES 0
 #endif
 #ifndef LSQ_SCAN_FLIGHT
 #define LSQ_SCAN_FLIGHT 2
@@ -270,7 +273,7 @@ __device__ __noinline__ uint32_t scan_triple(const ScanParams &P, uint32_t base,
 template <bool COMPACT>
 __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MINB) lsq_scan_kernel(const __grid_constant__ ScanParams P) {
     __shared__ uint2 s_dbl[SCAN_WARPS][SCAN_GROUP];  // per warp: its two-block reads {first block, chromosome id | group-local index << 24}
-    __shared__ uint2 s_tri[SCAN_WARPS][SCAN_GROUP];    // per warp: its three-block reads, same format
+    __shared__ uint2 s_tri[SCAN_WARPS][LSQ_SCAN_TRIPLES ? SCAN_GROUP : 1];    // per warp: its three-block reads, same format
     __shared__ uint2 s_gen[SCAN_WARPS][SCAN_GEN_CAP];  // per warp: reads for the general kernel {read, first block}
     __shared__ uint32_t s_ngen[SCAN_WARPS];
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
@@ -853,7 +856,6 @@ constexpr int MID_BLOCK = 128;
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 3) lsq_solve_kernel(SolveParams P) {
     __shared__ double s_theta[WARPS][2][LSQ_MAX_FORMS_PER_EVENT_DEV];
-    __shared__ double s_fim[WARPS][SE_MAX_FORMS - 1][2 * (SE_MAX_FORMS - 1)];  // [I | identity]
     const uint32_t lane = lane_id();
     const uint32_t w = threadIdx.x >> 5;
     const uint32_t E = P.T.E;
@@ -861,9 +863,8 @@ __global__ void __launch_bounds__(WARPS * 32, 3) lsq_solve_kernel(SolveParams P)
         const EvHdr h = P.T.hdr[x];
         const uint32_t K = h.K;
         if (P.small_enabled && K <= 2) continue;  // solved by lsq_solve_small_kernel
-        // events with at most MID_MAX_FORMS forms were solved by lsq_solve_mid_kernel: only their standard errors are left
-        const bool em_done = P.mid_enabled && K <= (uint32_t)MID_MAX_FORMS;
-        if (em_done && K == 1u) continue;  // se = 0, written by the mid kernel
+        // events with at most MID_MAX_FORMS forms are solved by lsq_solve_mid_kernel
+        if (P.mid_enabled && K <= (uint32_t)MID_MAX_FORMS) continue;
         double *th_old = s_theta[w][0], *th_new = s_theta[w][1];
         // N = total number of valid reads (read.h:599-602), sum of supports (solve.cpp:826)
         double n_total = 0.0, sum_supports = 0.0;
@@ -939,11 +940,7 @@ __global__ void __launch_bounds__(WARPS * 32, 3) lsq_solve_kernel(SolveParams P)
             }
             return warp_sum(part);
         };
-        if (em_done) {
-            for (uint32_t k = lane; k < K; k += 32) th_new[k] = P.theta[h.out_form + k];
-            __syncwarp();
-            if (any && cached) refresh(th_new);  // s_c at the final theta, for the information matrix
-        } else if (!any) {
+        if (!any) {
             // no valid read in any read set: uniform theta, log-likelihood 0 (solve.cpp:798-800)
         } else if (K == 1) {
             if (lane == 0) th_new[0] = 1.0;  // solve.cpp:801-802
@@ -1013,100 +1010,9 @@ __global__ void __launch_bounds__(WARPS * 32, 3) lsq_solve_kernel(SolveParams P)
             }
         }
         __syncwarp();
-        // Standard errors (extension, no oracle in the reference): observed Fisher information of
-        // the free parameters theta_0..theta_{K-2} (theta_{K-1} eliminated), per-read term as in
-        // common/fim.h:322-367: I_pq = sum_c n_c (v_cp - v_cK)(v_cq - v_cK) / s_c^2, inverted by
-        // Gauss-Jordan with partial pivoting (the reference's linalg.h uses a GSL LU for the same).
-        {
-            const uint32_t D = K - 1u;
-            if (K == 1u) {
-                if (lane == 0) P.se[h.out_form] = 0.0;
-            } else if (!any || K > (uint32_t)SE_MAX_FORMS) {
-                for (uint32_t k = lane; k < K; k += 32) P.se[h.out_form + k] = nan("");
-            } else {
-                double(*A)[2 * (SE_MAX_FORMS - 1)] = s_fim[w];
-                for (uint32_t p = 0; p < D; ++p)
-                    for (uint32_t q = p; q < D; ++q) {
-                        double part = 0.0;
-                        if (cached) {  // cs[] holds s_c at the final theta
-#pragma unroll
-                            for (int j = 0; j < CPL; ++j)
-                                if ((uint32_t)j < nown && cs[j] > 0.0) {
-                                    const double *G = cG[j];
-                                    const double vK = ((cmk[j] >> D) & 1ull) ? G[D] : 0.0;
-                                    const double vp = (((cmk[j] >> p) & 1ull) ? G[p] : 0.0) - vK;
-                                    const double vq = (((cmk[j] >> q) & 1ull) ? G[q] : 0.0) - vK;
-                                    part += ccnt[j] * (vp / cs[j]) * (vq / cs[j]);
-                                }
-                        } else
-                        for (uint32_t m = 0; m < P.M; ++m) {
-                            ClassRange cr = class_range(P, h, m);
-                            const double *G = P.G + (size_t)m * P.T.F + h.form_off;
-                            for (uint32_t i = lane; i < cr.n; i += 32) {
-                                unsigned long long c = cr.cnt[i];
-                                if (!c) continue;
-                                uint64_t mk = cr.mask ? cr.mask[i] : (uint64_t)(i + 1u);
-                                double sc = class_prob(mk, th_new, G);
-                                if (!(sc > 0.0)) continue;
-                                double vK = ((mk >> D) & 1ull) ? G[D] : 0.0;
-                                double vp = (((mk >> p) & 1ull) ? G[p] : 0.0) - vK;
-                                double vq = (((mk >> q) & 1ull) ? G[q] : 0.0) - vK;
-                                part += (double)c * (vp / sc) * (vq / sc);
-                            }
-                        }
-                        double v = warp_sum(part);
-                        if (lane == 0) {
-                            A[p][q] = v;
-                            A[q][p] = v;
-                        }
-                    }
-                __syncwarp();
-                for (uint32_t i = lane; i < D * D; i += 32) A[i / D][D + i % D] = (i / D == i % D) ? 1.0 : 0.0;
-                __syncwarp();
-                bool singular = false;
-                for (uint32_t r = 0; r < D; ++r) {  // lane j owns column j of the augmented matrix
-                    uint32_t piv = r;
-                    double best = fabs(A[r][r]);
-                    for (uint32_t i = r + 1; i < D; ++i)
-                        if (fabs(A[i][r]) > best) {
-                            best = fabs(A[i][r]);
-                            piv = i;
-                        }
-                    if (!(best > 0.0)) {
-                        singular = true;
-                        break;
-                    }
-                    __syncwarp();
-                    if (lane < 2 * D) {
-                        double a = A[r][lane], b = A[piv][lane];
-                        A[r][lane] = b;
-                        A[piv][lane] = a;
-                    }
-                    __syncwarp();
-                    const double pv = A[r][r];
-                    __syncwarp();
-                    if (lane < 2 * D) A[r][lane] /= pv;
-                    __syncwarp();
-                    for (uint32_t i = 0; i < D; ++i) {
-                        if (i == r) continue;
-                        const double f = A[i][r];
-                        __syncwarp();
-                        if (lane < 2 * D) A[i][lane] -= f * A[r][lane];
-                        __syncwarp();
-                    }
-                }
-                if (singular) {
-                    for (uint32_t k = lane; k < K; k += 32) P.se[h.out_form + k] = nan("");
-                } else {
-                    double tot = 0.0;
-                    for (uint32_t i = 0; i < D * D; ++i) tot += A[i / D][D + i % D];
-                    for (uint32_t k = lane; k < D; k += 32) P.se[h.out_form + k] = sqrt(A[k][D + k]);
-                    if (lane == 0) P.se[h.out_form + D] = sqrt(tot);
-                }
-            }
-        }
-        __syncwarp();
-        if (em_done) continue;  // theta, RPKM, log-likelihood and iterations were written by the mid kernel
+        // standard errors: lsq_se_kernel (events with at most SE_MAX_FORMS forms)
+        if (K > (uint32_t)SE_MAX_FORMS)
+            for (uint32_t k = lane; k < K; k += 32) P.se[h.out_form + k] = nan("");
         // RPKM (solve.cpp:809-821) and outputs
         for (uint32_t k = lane; k < K; k += 32) {
             double th = th_new[k];
@@ -1129,6 +1035,91 @@ __global__ void __launch_bounds__(WARPS * 32, 3) lsq_solve_kernel(SolveParams P)
             }
         }
         __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Standard errors (the north star's Fisher-information step; common/fim.h and linalg.h are dead code in the
+// reference, so there is no reference output to pin this to: the tests hold it against a numpy restatement).
+// Observed information of the free parameters theta_0..theta_{K-2} (theta_{K-1} = 1 - the rest) at the estimate,
+// per-read term as common/fim.h:322-367:  I_pq = sum_c n_c (v_cp - v_cK)(v_cq - v_cK) / s_c^2,  v_ck = G_k M(c,k);
+// se_k = sqrt((I^-1)_kk), se_{K-1} = sqrt(1' I^-1 1) (linalg.h:28-71 inverts with a GSL LU).
+// One warp per event, the augmented matrix [I | identity] in REGISTERS: lane j holds column j (2 (K-1) <= 30 columns),
+// so Gauss-Jordan elimination needs no shared memory and no barrier -- the pivot row's factors travel by shuffle.  Runs after the solve kernels, for every event with 3..SE_MAX_FORMS forms.
+// ---------------------------------------------------------------------------------------------
+constexpr int SE_DIM = SE_MAX_FORMS - 1;
+constexpr int SE_WARPS = 8;
+
+__global__ void __launch_bounds__(SE_WARPS * 32) lsq_se_kernel(const __grid_constant__ SolveParams P) {
+    const uint32_t lane = lane_id(), E = P.T.E;
+    for (uint32_t x = blockIdx.x * SE_WARPS + (threadIdx.x >> 5); x < E; x += gridDim.x * SE_WARPS) {
+        const EvHdr h = P.T.hdr[x];
+        const uint32_t K = h.K;
+        if ((P.small_enabled && K <= 2u) || K > (uint32_t)SE_MAX_FORMS) continue;
+        if (K == 1u) {
+            if (lane == 0u) P.se[h.out_form] = 0.0;
+            continue;
+        }
+        bool any = false;
+        for (uint32_t m = 0; m < P.M; ++m) any = any || P.n_valid[(size_t)m * E + h.out_ev] != 0ull;
+        const uint32_t D = K - 1u;
+        const double th = lane < K ? P.theta[h.out_form + lane] : 0.0;
+        double col[SE_DIM];
+#pragma unroll
+        for (int i = 0; i < SE_DIM; ++i) col[i] = 0.0;
+        for (uint32_t m = 0; any && m < P.M; ++m) {
+            const ClassRange cr = class_range(P, h, m);
+            const double g = lane < K ? __ldg(P.G + (size_t)m * P.T.F + h.form_off + lane) : 0.0;
+            for (uint32_t i = 0; i < cr.n; ++i) {
+                const unsigned long long c = __ldg(cr.cnt + i);
+                if (!c) continue;
+                const uint64_t mk = cr.mask ? __ldg(cr.mask + i) : (uint64_t)(i + 1u);
+                const double v = ((mk >> lane) & 1ull) ? g : 0.0;  // lanes >= K: g = 0
+                const double sc = warp_sum(th * v);
+                if (!(sc > 0.0)) continue;
+                const double w = (v - __shfl_sync(0xFFFFFFFFu, v, D)) / sc;
+                const double a = (double)c * w;
+#pragma unroll
+                for (int p = 0; p < SE_DIM; ++p)
+                    if ((uint32_t)p < D) col[p] = fma(a, __shfl_sync(0xFFFFFFFFu, w, p), col[p]);  // lane q < D: I[p][q]
+            }
+        }
+        if (lane >= D) {
+#pragma unroll
+            for (int i = 0; i < SE_DIM; ++i) col[i] = (lane - D == (uint32_t)i) ? 1.0 : 0.0;
+        }
+        bool singular = !any;
+#pragma unroll
+        for (int r = 0; r < SE_DIM; ++r) {
+            if ((uint32_t)r < D && !singular) {
+                // the information matrix is symmetric positive semi-definite: the diagonal entry is the pivot, no row
+                // exchange is needed for stability; a pivot that is not positive means a singular matrix
+                const double pv = __shfl_sync(0xFFFFFFFFu, col[r], r);
+                if (!(pv > 0.0)) {
+                    singular = true;
+                } else {
+                    col[r] /= pv;
+#pragma unroll
+                    for (int i = 0; i < SE_DIM; ++i)
+                        if (i != r && (uint32_t)i < D) col[i] = fma(-__shfl_sync(0xFFFFFFFFu, col[i], r), col[r], col[i]);
+                }
+            }
+        }
+        if (singular) {
+            if (lane < K) P.se[h.out_form + lane] = nan("");
+            continue;
+        }
+        // lane D + k holds column k of the inverse
+        double diag = 0.0, sum = 0.0;
+#pragma unroll
+        for (int i = 0; i < SE_DIM; ++i)
+            if ((uint32_t)i < D) {
+                if (lane - D == (uint32_t)i) diag = col[i];
+                sum += col[i];
+            }
+        const double tot = warp_sum((lane >= D && lane < 2u * D) ? sum : 0.0);
+        if (lane >= D && lane < 2u * D) P.se[h.out_form + lane - D] = sqrt(diag);
+        if (lane == 0u) P.se[h.out_form + D] = sqrt(tot);
     }
 }
 
@@ -1196,74 +1187,18 @@ __global__ void __launch_bounds__(256) lsq_mid_scatter_kernel(const __grid_const
 // memory, [form][thread], so the dynamic form index costs no local memory and lanes never conflict.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(MID_BLOCK) lsq_solve_mid_kernel(const __grid_constant__ SolveParams P) {
-    __shared__ double s_th[MID_MAX_FORMS][MID_BLOCK], s_w[MID_MAX_FORMS][MID_BLOCK], s_z[MID_MAX_FORMS][MID_BLOCK];
+    __shared__ double s_th[MID_MAX_FORMS][MID_BLOCK];
     const uint32_t E = P.T.E, t = threadIdx.x;
-    while (true) {
-        const uint32_t wi = atomicAdd(P.work_counter, 1u);
-        if (wi >= *P.mid_n) return;
-        const uint32_t x = P.mid_order[wi];  // events in (classes, forms) order: see lsq_mid_key_kernel
-        const EvHdr h = P.T.hdr[x];
+    // Every lane runs its own event, and every trip of the loop below is ONE likelihood pass for all lanes of the warp:
+    // a lane whose event has converged writes it out and takes the next event at the top of the next trip, so the
+    // lanes stay converged on the pass (the expensive part) although their events need different numbers of
+    // iterations.  phase: 0 = wants an event, 1 = first pass (ll at the uniform start), 2 = iterating (read.h:647-659).
+    uint32_t phase = 0, x = 0, iters = 0;
+    EvHdr h = {};
+    double n_total = 0.0, sum_supports = 0.0, ll_old = 0.0, near = 1E300;
+    bool alive = true;
+    auto finish = [&](double ll, bool any) {
         const uint32_t K = h.K;
-        if (P.small_enabled && K <= 2u) continue;
-        double n_total = 0.0, sum_supports = 0.0;
-        bool any = false;
-        for (uint32_t m = 0; m < P.M; ++m) {
-            const unsigned long long nv = P.n_valid[(size_t)m * E + h.out_ev];
-            if (nv) {
-                any = true;
-                n_total = __dadd_rn(n_total, (double)nv);
-            }
-            sum_supports = __dadd_rn(sum_supports, (double)nv);
-        }
-        // one pass at the theta in s_th: returns ll(theta), leaves the numerators of the next theta in s_z
-        auto pass = [&]() {
-            for (uint32_t k = 0; k < K; ++k) s_z[k][t] = 0.0;
-            double ll = 0.0;
-            for (uint32_t m = 0; m < P.M; ++m) {
-                const ClassRange cr = class_range(P, h, m);
-                const double *G = P.G + (size_t)m * P.T.F + h.form_off;
-                for (uint32_t k = 0; k < K; ++k) s_w[k][t] = __dmul_rn(s_th[k][t], __ldg(G + k));
-#pragma unroll 2
-                for (uint32_t i = 0; i < cr.n; ++i) {
-                    const unsigned long long c = __ldg(cr.cnt + i);
-                    if (!c) continue;
-                    const uint64_t mk = cr.mask ? __ldg(cr.mask + i) : (uint64_t)(i + 1u);
-                    double s = 0.0;
-                    for (uint64_t b = mk; b; b &= b - 1ull) s = __dadd_rn(s, s_w[__ffsll((long long)b) - 1][t]);
-                    const double n_c = (double)c;
-                    ll = __dadd_rn(ll, __dmul_rn(n_c, log(s)));
-                    if (s > 0.0) {
-                        const double tc = __ddiv_rn(n_c, s);
-                        for (uint64_t b = mk; b; b &= b - 1ull) {
-                            const int k = __ffsll((long long)b) - 1;
-                            const double wk = s_w[k][t];
-                            if (wk > 0.0) s_z[k][t] = __dadd_rn(s_z[k][t], __dmul_rn(wk, tc));
-                        }
-                    }
-                }
-            }
-            return ll;
-        };
-        for (uint32_t k = 0; k < K; ++k) s_th[k][t] = __ddiv_rn(1.0, (double)K);
-        uint32_t iters = 0;
-        double ll = 0.0, near = 1E300;
-        if (!any) {
-            // no valid read in any read set: uniform theta, log-likelihood 0 (solve.cpp:798-800)
-        } else if (K == 1u) {
-            s_th[0][t] = 1.0;  // solve.cpp:801-802
-            ll = pass();
-        } else {
-            double ll_old = pass();
-            while (true) {  // read.h:647-659
-                for (uint32_t k = 0; k < K; ++k) s_th[k][t] = __ddiv_rn(s_z[k][t], n_total);
-                ll = pass();
-                ++iters;
-                const double tk = fabs(__dsub_rn(1.0, __ddiv_rn(ll_old, ll)));
-                near = fmin(near, fabs(tk - 1E-6));
-                if (!(tk > 1E-6) || iters >= P.max_iters) break;
-                ll_old = ll;
-            }
-        }
         if (iters != 0u && P.flag_n != nullptr && em_stop_is_fragile(near, ll, n_total)) {
             const uint32_t fi = atomicAdd(P.flag_n, 1u);  // replayed read by read in the reference's order
             P.flag_list[fi] = x;
@@ -1283,6 +1218,105 @@ __global__ void __launch_bounds__(MID_BLOCK) lsq_solve_mid_kernel(const __grid_c
         P.loglik[h.out_ev] = ll;
         P.ll_per_read[h.out_ev] = (sum_supports > 1E-5) ? __ddiv_rn(ll, sum_supports) : 0.0;
         P.iters[h.out_ev] = iters;
+    };
+    while (true) {
+        if (phase == 0u && alive) {
+            while (true) {
+                const uint32_t wi = atomicAdd(P.work_counter, 1u);
+                if (wi >= *P.mid_n) {
+                    alive = false;
+                    break;
+                }
+                x = P.mid_order[wi];  // events in (classes, forms) order: see lsq_mid_key_kernel
+                h = P.T.hdr[x];
+                const uint32_t K = h.K;
+                if (P.small_enabled && K <= 2u) continue;
+                n_total = 0.0;
+                sum_supports = 0.0;
+                bool any = false;
+                for (uint32_t m = 0; m < P.M; ++m) {
+                    const unsigned long long nv = P.n_valid[(size_t)m * E + h.out_ev];
+                    if (nv) {
+                        any = true;
+                        n_total = __dadd_rn(n_total, (double)nv);
+                    }
+                    sum_supports = __dadd_rn(sum_supports, (double)nv);
+                }
+                for (uint32_t k = 0; k < K; ++k) s_th[k][t] = __ddiv_rn(1.0, (double)K);
+                iters = 0;
+                near = 1E300;
+                if (!any) {  // no valid read in any read set: uniform theta, log-likelihood 0 (solve.cpp:798-800)
+                    finish(0.0, false);
+                    continue;
+                }
+                if (K == 1u) s_th[0][t] = 1.0;  // solve.cpp:801-802
+                phase = 1u;
+                break;
+            }
+        }
+        if (__all_sync(0xFFFFFFFFu, !alive)) return;
+        if (!alive) continue;
+        // one pass at the theta in s_th: ll(theta) and the numerators z of the next theta.  w_k = theta_k G_k and z_k
+        // live in registers: the loops over the forms are unrolled to MID_MAX_FORMS with the class's mask bit as the
+        // predicate (adding nothing for a form outside the class, exactly like skipping it) and cut short, uniformly
+        // for the warp, at the largest K among its lanes' events
+        const uint32_t K = h.K, Kmax = __reduce_max_sync(__activemask(), K);
+        double z[MID_MAX_FORMS], w[MID_MAX_FORMS];
+#pragma unroll
+        for (int k = 0; k < MID_MAX_FORMS; ++k) z[k] = 0.0;
+        double ll = 0.0;
+        for (uint32_t m = 0; m < P.M; ++m) {
+            const ClassRange cr = class_range(P, h, m);
+            const double *G = P.G + (size_t)m * P.T.F + h.form_off;
+#pragma unroll
+            for (int k = 0; k < MID_MAX_FORMS; ++k) {
+                if ((uint32_t)k >= Kmax) break;
+                w[k] = (uint32_t)k < K ? __dmul_rn(s_th[k][t], __ldg(G + k)) : 0.0;
+            }
+#pragma unroll 1
+            for (uint32_t i = 0; i < cr.n; ++i) {
+                const unsigned long long c = __ldg(cr.cnt + i);
+                if (!c) continue;
+                const uint32_t mk = cr.mask ? (uint32_t)__ldg(cr.mask + i) : i + 1u;  // K <= 16: the low bits
+                double sm = 0.0;
+#pragma unroll
+                for (int k = 0; k < MID_MAX_FORMS; ++k) {
+                    if ((uint32_t)k >= Kmax) break;
+                    if (mk & (1u << k)) sm = __dadd_rn(sm, w[k]);
+                }
+                const double n_c = (double)c;
+                ll = __dadd_rn(ll, __dmul_rn(n_c, log(sm)));
+                if (sm > 0.0) {
+                    const double tc = __ddiv_rn(n_c, sm);
+#pragma unroll
+                    for (int k = 0; k < MID_MAX_FORMS; ++k) {
+                        if ((uint32_t)k >= Kmax) break;
+                        if ((mk & (1u << k)) && w[k] > 0.0) z[k] = __dadd_rn(z[k], __dmul_rn(w[k], tc));
+                    }
+                }
+            }
+        }
+        bool stop;
+        if (phase == 1u) {
+            stop = K == 1u;
+            phase = 2u;
+        } else {
+            ++iters;
+            const double tk = fabs(__dsub_rn(1.0, __ddiv_rn(ll_old, ll)));
+            near = fmin(near, fabs(tk - 1E-6));
+            stop = !(tk > 1E-6) || iters >= P.max_iters;
+        }
+        if (stop) {
+            finish(ll, true);
+            phase = 0u;
+        } else {
+            ll_old = ll;
+#pragma unroll
+            for (int k = 0; k < MID_MAX_FORMS; ++k) {
+                if ((uint32_t)k >= Kmax) break;
+                if ((uint32_t)k < K) s_th[k][t] = __ddiv_rn(z[k], n_total);
+            }
+        }
     }
 }
 
@@ -1519,16 +1553,38 @@ struct ExactParams {
     const uint64_t *seg_off;
     const uint32_t *seg_cur;
     ExactRec *rec;
+    uint8_t *cls;  // class index of every sorted record (same offsets as rec)
 };
 
-// One block (one working thread) per flagged event (they are few): sort, replay, overwrite the event's results.
-__global__ void __launch_bounds__(32) lsq_exact_kernel(const __grid_constant__ SolveParams P, const __grid_constant__ ExactParams X) {
-    const uint32_t fi = blockIdx.x;
-    if (fi >= X.n_flag || threadIdx.x != 0) return;
+constexpr int EXACT_BLOCK = 256;
+
+__device__ __forceinline__ void exact_cmpxchg(ExactRec *rec, uint32_t i, uint32_t l) {
+    const ExactRec a = rec[i], b = rec[l];
+    if (exact_rec_less(b, a)) {
+        rec[i] = b;
+        rec[l] = a;
+    }
+}
+
+// One block per flagged event (they are few): sort the event's records into the reference's read order, replay the
+// EM with the reference's own operation order, overwrite the event's results.  What is sequential in the reference
+// stays sequential here -- every running sum adds its terms read by read -- but the K + 1 running sums of one sweep
+// (the E-step numerators of the K forms and the log-likelihood, all at the same theta) run side by side, one thread
+// each, over per-class tables of the terms (exact_em in lsq_device_fn.cuh is the same computation on one thread; it
+// stays the fallback for events with more classes than the tables hold).
+__global__ void __launch_bounds__(EXACT_BLOCK) lsq_exact_kernel(const __grid_constant__ SolveParams P, const __grid_constant__ ExactParams X) {
+    __shared__ double s_tbl[EXACT_MAX_TERMS + 2 * EXACT_MAX_CLS];  // [class][K + 1]: E-step term per form, then the log term
+    __shared__ double s_theta[LSQ_MAX_FORMS_PER_EVENT_DEV], s_acc[LSQ_MAX_FORMS_PER_EVENT_DEV + 1];
+    __shared__ uint64_t s_cmask[EXACT_MAX_CLS];
+    __shared__ uint32_t s_cset[EXACT_MAX_CLS];
+    __shared__ uint32_t s_C, s_tab;
+    const uint32_t fi = blockIdx.x, t = threadIdx.x, lane = t & 31u;
+    if (fi >= X.n_flag) return;
     const uint32_t x = X.flag_list[fi];
     const EvHdr h = P.T.hdr[x];
     const uint32_t K = h.K, E = P.T.E;
     ExactRec *rec = X.rec + X.seg_off[fi];
+    uint8_t *cls = X.cls + X.seg_off[fi];
     const uint32_t n = min((uint32_t)(X.seg_off[fi + 1] - X.seg_off[fi]), X.seg_cur[fi]);
     double n_total = 0.0, sum_supports = 0.0;
     for (uint32_t m = 0; m < P.M; ++m) {
@@ -1537,21 +1593,139 @@ __global__ void __launch_bounds__(32) lsq_exact_kernel(const __grid_constant__ S
         sum_supports = __dadd_rn(sum_supports, (double)nv);
     }
     if ((double)n != n_total) return;  // injected class tables have no reads to replay: keep the class-collapsed result
-    exact_sort(rec, n);
-    double theta[LSQ_MAX_FORMS_PER_EVENT_DEV], old_theta[LSQ_MAX_FORMS_PER_EVENT_DEV];
-    double ll;
-    const uint32_t iters = exact_em(rec, n, n_total, K, P.G + h.form_off, P.T.F, theta, old_theta, ll, P.max_iters);
-    for (uint32_t k = 0; k < K; ++k) {  // RPKM (solve.cpp:809-821) and outputs, as the solve kernels
-        double r = 0.0;
-        for (uint32_t m = 0; m < P.M; ++m) r = __dadd_rn(r, __dmul_rn((double)P.bases[(size_t)m * E + x], theta[k]));
-        r = __ddiv_rn(r, __ddiv_rn((double)P.form_len[h.form_off + k], 1.0E3));
-        r = __ddiv_rn(r, P.total_read_mbases);
-        P.theta[h.out_form + k] = theta[k];
-        P.rpkm[h.out_form + k] = r;
+    // ---- sort: bitonic network in its all-ascending form (first step of a merge pairs i with i ^ (k - 1)), so the
+    // missing tail of a non-power-of-two n acts as +infinity and is never touched; names are unique, the order total
+    for (uint32_t k = 2; (k >> 1) < n; k <<= 1) {
+        for (uint32_t i = t; i < n; i += EXACT_BLOCK) {
+            const uint32_t l = i ^ (k - 1u);
+            if (l > i && l < n) exact_cmpxchg(rec, i, l);
+        }
+        __syncthreads();
+        for (uint32_t j = k >> 2; j > 0u; j >>= 1) {
+            for (uint32_t i = t; i < n; i += EXACT_BLOCK) {
+                const uint32_t l = i ^ j;
+                if (l > i && l < n) exact_cmpxchg(rec, i, l);
+            }
+            __syncthreads();
+        }
     }
-    P.loglik[h.out_ev] = ll;
-    P.ll_per_read[h.out_ev] = (sum_supports > 1E-5) ? __ddiv_rn(ll, sum_supports) : 0.0;
-    P.iters[h.out_ev] = iters;
+    // ---- classes of the event: distinct (read set, form mask) pairs, found by one warp, 32 records at a time
+    if (t < 32u) {
+        uint32_t C = 0;
+        bool tab = true;
+        for (uint32_t base = 0; base < n && tab; base += 32u) {
+            const uint32_t i = base + lane;
+            const bool have = i < n;
+            uint64_t mk = 0;
+            uint32_t m = 0, c = 0xFFFFFFFFu, from = 0;
+            if (have) {
+                mk = rec[i].mask;
+                m = exact_rec_set(rec[i]);
+            }
+            while (true) {
+                if (have && c == 0xFFFFFFFFu)
+                    for (uint32_t q = from; q < C; ++q)
+                        if (s_cmask[q] == mk && s_cset[q] == m) {
+                            c = q;
+                            break;
+                        }
+                const uint32_t unfound = __ballot_sync(0xFFFFFFFFu, have && c == 0xFFFFFFFFu);
+                if (unfound == 0u) break;
+                if (C == EXACT_MAX_CLS || (C + 1u) * (K + 1u) > EXACT_MAX_TERMS + EXACT_MAX_CLS) {
+                    tab = false;
+                    break;
+                }
+                if (lane == (uint32_t)__ffs((int)unfound) - 1u) {
+                    s_cmask[C] = mk;
+                    s_cset[C] = m;
+                }
+                __syncwarp();
+                from = C++;
+            }
+            if (tab && have) cls[i] = (uint8_t)c;
+        }
+        if (lane == 0u) {
+            s_C = C;
+            s_tab = tab ? 1u : 0u;
+        }
+    }
+    __syncthreads();
+    uint32_t iters = 0;
+    double ll = 0.0;
+    if (!s_tab) {
+        if (t == 0u) {
+            double theta[LSQ_MAX_FORMS_PER_EVENT_DEV], old_theta[LSQ_MAX_FORMS_PER_EVENT_DEV];
+            iters = exact_em_per_read(rec, n, n_total, K, P.G + h.form_off, P.T.F, theta, old_theta, ll, P.max_iters);
+            for (uint32_t k = 0; k < K; ++k) s_theta[k] = theta[k];
+        }
+    } else {
+        const uint32_t C = s_C, W = K + 1u;
+        if (t < K) s_theta[t] = lsq_div(1.0, (double)K);
+        double ll_old = 0.0;
+        bool first = true;
+        while (true) {
+            __syncthreads();
+            // tables at the current theta: per class the probability s (every form's term added in form order, zeros
+            // included -- read.h:620-636), log s, and theta_k M(c,k) / s (read.h:592-618: a skipped term adds nothing)
+            for (uint32_t c = t; c < C; c += EXACT_BLOCK)
+                s_tbl[c * W + K] = exact_class_prob(s_cmask[c], K, s_theta, P.G + h.form_off + (size_t)s_cset[c] * P.T.F);
+            __syncthreads();
+            for (uint32_t q = t; q < C * K; q += EXACT_BLOCK) {
+                const uint32_t c = q / K, k = q - c * K;
+                const double sc = s_tbl[c * W + K];
+                const double g = ((s_cmask[c] >> k) & 1ull) ? P.G[h.form_off + (size_t)s_cset[c] * P.T.F + k] : 0.0;
+                const double lp = lsq_mul(s_theta[k], g);
+                s_tbl[c * W + k] = (sc > 0.0 && lp > 0.0) ? lsq_div(lp, sc) : 0.0;
+            }
+            __syncthreads();
+            for (uint32_t c = t; c < C; c += EXACT_BLOCK) s_tbl[c * W + K] = log(s_tbl[c * W + K]);
+            __syncthreads();
+            // the sweep: thread a < K sums form a's E-step terms, thread K the log-likelihood, each in read order
+            if (t < W) {
+                double acc = 0.0;
+                const double *tb = s_tbl + t;
+                uint32_t i = 0;
+                if ((reinterpret_cast<uintptr_t>(cls) & 15u) == 0u)
+                    for (; i + 16u <= n; i += 16u) {
+                        const uint4 v = *reinterpret_cast<const uint4 *>(cls + i);
+                        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) acc = lsq_add(acc, tb[((w[j >> 2] >> (8 * (j & 3))) & 0xFFu) * W]);
+                    }
+                for (; i < n; ++i) acc = lsq_add(acc, tb[(uint32_t)cls[i] * W]);
+                s_acc[t] = acc;
+            }
+            __syncthreads();
+            ll = s_acc[K];
+            bool stop = false;
+            if (first) {
+                first = false;
+            } else {
+                ++iters;
+                const double d = 1.0 - lsq_div(ll_old, ll);
+                stop = !((d < 0.0 ? -d : d) > 1E-6) || iters >= P.max_iters;
+            }
+            if (stop) break;
+            ll_old = ll;
+            __syncthreads();
+            if (t < K) s_theta[t] = lsq_div(s_acc[t], n_total);
+        }
+    }
+    __syncthreads();
+    if (t < K) {  // RPKM (solve.cpp:809-821) and outputs, as the solve kernels
+        const double th = s_theta[t];
+        double r = 0.0;
+        for (uint32_t m = 0; m < P.M; ++m) r = __dadd_rn(r, __dmul_rn((double)P.bases[(size_t)m * E + x], th));
+        r = __ddiv_rn(r, __ddiv_rn((double)P.form_len[h.form_off + t], 1.0E3));
+        r = __ddiv_rn(r, P.total_read_mbases);
+        P.theta[h.out_form + t] = th;
+        P.rpkm[h.out_form + t] = r;
+    }
+    if (t == 0u) {
+        P.loglik[h.out_ev] = ll;
+        P.ll_per_read[h.out_ev] = (sum_supports > 1E-5) ? __ddiv_rn(ll, sum_supports) : 0.0;
+        P.iters[h.out_ev] = iters;
+    }
 }
 
 // FP64 FMA throughput of the device (8 independent chains per thread): the denominator of the solve roofline.
