@@ -859,10 +859,26 @@ static int exact_replay(lsq_ctx *c, const lsq::SolveParams &P, uint32_t n_flag) 
         }
         iv_off[ch + 1] = (uint32_t)iv_start.size();
     }
-    // device layout: seg_off | seg_cur | iv_off | iv_start | iv_end | strand ranks (one row per read set)
+    // coarse pre-check of the collect kernel: one bit per bin of 2^COLLECT_BIN_SHIFT positions that a flagged span overlaps
+    std::vector<uint32_t> bin_off(nch + 1, 0);
+    for (uint32_t ch = 0; ch < nch; ++ch) {
+        uint32_t nb = 0;
+        if (iv_off[ch + 1] > iv_off[ch] && iv_end[iv_off[ch + 1] - 1] >= 0)
+            nb = ((uint32_t)iv_end[iv_off[ch + 1] - 1] >> lsq::COLLECT_BIN_SHIFT) + 1u;
+        bin_off[ch + 1] = bin_off[ch] + nb;
+    }
+    std::vector<uint32_t> bin_bits((bin_off[nch] + 31) / 32 + 1, 0);
+    for (uint32_t ch = 0; ch < nch; ++ch)
+        for (uint32_t i = iv_off[ch]; i < iv_off[ch + 1]; ++i) {
+            if (iv_end[i] < 0) continue;
+            const uint32_t b0 = (uint32_t)std::max(iv_start[i], 0) >> lsq::COLLECT_BIN_SHIFT, b1 = (uint32_t)iv_end[i] >> lsq::COLLECT_BIN_SHIFT;
+            for (uint32_t b = b0; b <= b1; ++b) bin_bits[(bin_off[ch] + b) >> 5] |= 1u << ((bin_off[ch] + b) & 31u);
+        }
+    // device layout: seg_off | seg_cur | iv_off | iv_start | iv_end | strand ranks (one row per read set) | bin_off | bin_bits
     const size_t niv = iv_start.size();
     const size_t o_cur = (size_t)(n_flag + 1) * 8, o_ivoff = o_cur + (((size_t)n_flag * 4 + 7) & ~(size_t)7), o_ivs = o_ivoff + (size_t)(nch + 2) * 4,
-                 o_ive = o_ivs + niv * 4 + 4, o_sr = o_ive + niv * 4 + 4, bytes = o_sr + (size_t)LSQ_MAX_METHODS * 256;
+                 o_ive = o_ivs + niv * 4 + 4, o_sr = o_ive + niv * 4 + 4, o_boff = o_sr + (size_t)LSQ_MAX_METHODS * 256,
+                 o_bits = o_boff + (size_t)(nch + 2) * 4, bytes = o_bits + bin_bits.size() * 4;
     LSQ_CUDA(c->d_exact.ensure(bytes));
     const uint64_t n_rec = std::max<uint64_t>(seg_off[n_flag], 1);  // records, then one class byte per record
     LSQ_CUDA(c->d_exact_rec.ensure(n_rec * sizeof(lsq::ExactRec) + n_rec + 16));
@@ -874,6 +890,8 @@ static int exact_replay(lsq_ctx *c, const lsq::SolveParams &P, uint32_t n_flag) 
         memcpy(hbuf.data() + o_ivs, iv_start.data(), niv * 4);
         memcpy(hbuf.data() + o_ive, iv_end.data(), niv * 4);
     }
+    memcpy(hbuf.data() + o_boff, bin_off.data(), (size_t)(nch + 1) * 4);
+    memcpy(hbuf.data() + o_bits, bin_bits.data(), bin_bits.size() * 4);
     for (uint32_t m = 0; m < M; ++m) {  // rank of every file strand string (bytewise order, count.cpp:64-85)
         const std::vector<std::string> &sn = c->sets[m].strand_names;
         for (size_t i = 0; i < sn.size() && i < 256; ++i) {
@@ -912,6 +930,8 @@ static int exact_replay(lsq_ctx *c, const lsq::SolveParams &P, uint32_t n_flag) 
         C.iv_chrom_off = reinterpret_cast<const uint32_t *>(d + o_ivoff);
         C.iv_start = reinterpret_cast<const int32_t *>(d + o_ivs);
         C.iv_end = reinterpret_cast<const int32_t *>(d + o_ive);
+        C.bin_off = reinterpret_cast<const uint32_t *>(d + o_boff);
+        C.bin_bits = reinterpret_cast<const uint32_t *>(d + o_bits);
         C.seg_off = reinterpret_cast<const uint64_t *>(d);
         C.seg_cur = reinterpret_cast<uint32_t *>(d + o_cur);
         C.rec = c->d_exact_rec.as<lsq::ExactRec>();

@@ -994,6 +994,108 @@ LSQ_HD bool em_stop_is_fragile(double near, double ll, double n_reads) {
     return near < margin || (ll > -1E-8 && ll < 1E-8);
 }
 
+// ---------------------------------------------------------------------------------------------
+// A stop that em_stop_is_fragile cannot vouch for may still come out the same in EVERY summation order.  The common
+// case: forms not longer than a read (G = 1, or G = 0 for a form no read can start in) drive theta to a vertex in
+// one step, every read's probability becomes exactly 1, the log-likelihood exactly 0, and the stop test divides by
+// zero -- "fragile" by value, yet nothing in that run ever rounded.  em_result_is_order_free re-runs the
+// class-collapsed EM of such an event (they have few iterations) and certifies that
+//   * every E-step sum is exact: all its per-read terms are multiples of one power of two, 2^low, and their total
+//     stays below 2^(low + 52), so every partial sum in any order is representable -- the reference's sum and ours
+//     are the same number, and so is the next theta (one correctly rounded division);
+//   * every stop decision is the same in any order: a log-likelihood whose terms are all exactly 0 is exactly 0
+//     however it is added up; one that is not must be clearly non-zero, and the test value must keep the margin of
+//     em_stop_is_fragile from the threshold unless the division by an exact zero already decides it.
+// Certified events need no read-by-read replay.  visit(f) calls f(read set, form mask, reads) for every class with
+// reads; g(m, k) is G of form k for read set m.  Events with more than CERT_MAX_FORMS forms or CERT_MAX_ITERS
+// iterations are not examined.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t CERT_MAX_FORMS = 8, CERT_MAX_ITERS = 8;
+
+// exponent of the lowest set bit of x != 0 (x = odd * 2^result)
+LSQ_HD int low_bit_exponent(double x) {
+    int e;
+    uint64_t mant = (uint64_t)ldexp(frexp(x < 0.0 ? -x : x, &e), 53);
+    int tz = 0;
+    while (!(mant & 1ull)) {
+        mant >>= 1;
+        ++tz;
+    }
+    return e - 53 + tz;
+}
+
+template <class Visit, class GFn>
+LSQ_HD bool em_result_is_order_free(uint32_t K, double n_total, uint32_t iters_done, uint32_t max_iters, Visit visit, GFn g) {
+    if (K < 2u || K > CERT_MAX_FORMS || iters_done == 0u || iters_done > CERT_MAX_ITERS) return false;
+    double th[CERT_MAX_FORMS], z[CERT_MAX_FORMS];
+    int low[CERT_MAX_FORMS];
+    for (uint32_t k = 0; k < K; ++k) th[k] = lsq_div(1.0, (double)K);
+    auto prob = [&](uint32_t m, uint64_t mk) {
+        double sc = 0.0;
+        for (uint32_t k = 0; k < K; ++k)
+            if ((mk >> k) & 1ull) sc = lsq_add(sc, lsq_mul(th[k], g(m, k)));
+        return sc;
+    };
+    // log-likelihood at th; zero: every term is exactly 0
+    auto loglik = [&](bool &zero) {
+        double ll = 0.0;
+        bool all_zero = true;
+        visit([&](uint32_t m, uint64_t mk, double n_c) {
+            const double L = log(prob(m, mk));
+            if (L != 0.0) all_zero = false;
+            ll = lsq_add(ll, lsq_mul(n_c, L));
+        });
+        zero = all_zero;
+        return ll;
+    };
+    const double margin = 1E-12 > 4.5E-16 * n_total ? 1E-12 : 4.5E-16 * n_total;
+    bool old_zero;
+    double ll_old = loglik(old_zero);
+    if (!old_zero && !(ll_old < -1E-8 && ll_old > -1E300)) return false;
+    for (uint32_t it = 1;; ++it) {
+        for (uint32_t k = 0; k < K; ++k) {
+            z[k] = 0.0;
+            low[k] = 4096;
+        }
+        visit([&](uint32_t m, uint64_t mk, double n_c) {
+            const double sc = prob(m, mk);
+            if (!(sc > 0.0)) return;
+            for (uint32_t k = 0; k < K; ++k) {
+                if (!((mk >> k) & 1ull)) continue;
+                const double lp = lsq_mul(th[k], g(m, k));
+                if (!(lp > 0.0)) continue;
+                const double t = lsq_div(lp, sc);
+                const int lb = low_bit_exponent(t);
+                if (lb < low[k]) low[k] = lb;
+                z[k] = lsq_add(z[k], lsq_mul(n_c, t));
+            }
+        });
+        for (uint32_t k = 0; k < K; ++k) {
+            if (z[k] != 0.0 && !(z[k] < ldexp(1.0, low[k] + 52))) return false;  // some partial sum may round
+            th[k] = lsq_div(z[k], n_total);
+        }
+        bool zero;
+        const double ll = loglik(zero);
+        bool stop;
+        if (zero) {
+            stop = old_zero;  // 0 / 0: the test is false; x / 0 with x clearly non-zero: infinite, the test is true
+        } else {
+            if (!(ll < -1E-8 && ll > -1E300)) return false;
+            if (old_zero) {
+                stop = false;  // |1 - 0 / ll| = 1
+            } else {
+                const double d = 1.0 - lsq_div(ll_old, ll), tk = d < 0.0 ? -d : d, off = tk - 1E-6;
+                if ((off < 0.0 ? -off : off) < margin) return false;
+                stop = !(tk > 1E-6);
+            }
+        }
+        if (stop || it >= max_iters) return it == iters_done;
+        if (it >= iters_done) return false;  // the kernel stopped earlier than this run would: leave it to the replay
+        ll_old = ll;
+        old_zero = zero;
+    }
+}
+
 // The reference evaluates, per read, s = sum_k theta_k M(i,k) (every form's term added in form order, zeros included),
 // log s for the log-likelihood (read.h:620-636) and theta_k M(i,k) / s for the E-step (read.h:592-618), and adds them up
 // read by read.  Those VALUES depend only on the read's class (read set, form mask): they are tabulated per class,

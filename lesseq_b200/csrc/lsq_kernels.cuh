@@ -1028,7 +1028,16 @@ __global__ void __launch_bounds__(WARPS * 32, 3) lsq_solve_kernel(SolveParams P)
             P.loglik[h.out_ev] = ll;
             P.ll_per_read[h.out_ev] = (sum_supports > 1E-5) ? __ddiv_rn(ll, sum_supports) : 0.0;
             P.iters[h.out_ev] = iters;
-            if (iters != 0u && P.flag_n != nullptr && em_stop_is_fragile(near, ll, n_total)) {
+            if (iters != 0u && P.flag_n != nullptr && em_stop_is_fragile(near, ll, n_total) &&
+                !em_result_is_order_free(K, n_total, iters, P.max_iters, [&](auto f) {
+                    for (uint32_t m = 0; m < P.M; ++m) {
+                        const ClassRange cr = class_range(P, h, m);
+                        for (uint32_t i = 0; i < cr.n; ++i) {
+                            const unsigned long long c = cr.cnt[i];
+                            if (c) f(m, cr.mask ? (uint64_t)cr.mask[i] : (uint64_t)(i + 1u), (double)c);
+                        }
+                    }
+                }, [&](uint32_t m, uint32_t k) { return P.G[(size_t)m * P.T.F + h.form_off + k]; })) {
                 const uint32_t fi = atomicAdd(P.flag_n, 1u);  // replayed read by read in the reference's order
                 P.flag_list[fi] = x;
                 P.ev_flag[x] = fi + 1u;
@@ -1199,7 +1208,16 @@ __global__ void __launch_bounds__(MID_BLOCK) lsq_solve_mid_kernel(const __grid_c
     bool alive = true;
     auto finish = [&](double ll, bool any) {
         const uint32_t K = h.K;
-        if (iters != 0u && P.flag_n != nullptr && em_stop_is_fragile(near, ll, n_total)) {
+        if (iters != 0u && P.flag_n != nullptr && em_stop_is_fragile(near, ll, n_total) &&
+            !em_result_is_order_free(K, n_total, iters, P.max_iters, [&](auto f) {
+                for (uint32_t m = 0; m < P.M; ++m) {
+                    const ClassRange cr = class_range(P, h, m);
+                    for (uint32_t i = 0; i < cr.n; ++i) {
+                        const unsigned long long c = cr.cnt[i];
+                        if (c) f(m, cr.mask ? (uint64_t)cr.mask[i] : (uint64_t)(i + 1u), (double)c);
+                    }
+                }
+            }, [&](uint32_t m, uint32_t k) { return P.G[(size_t)m * P.T.F + h.form_off + k]; })) {
             const uint32_t fi = atomicAdd(P.flag_n, 1u);  // replayed read by read in the reference's order
             P.flag_list[fi] = x;
             P.ev_flag[x] = fi + 1u;
@@ -1403,7 +1421,14 @@ __global__ void __launch_bounds__(128) lsq_solve_small_kernel(SolveParams P) {
                 ll_old = ll;
             }
         }
-        if (iters != 0u && P.flag_n != nullptr && em_stop_is_fragile(near, ll, n_total)) {
+        if (iters != 0u && P.flag_n != nullptr && em_stop_is_fragile(near, ll, n_total) &&
+            !em_result_is_order_free(K, n_total, iters, P.max_iters, [&](auto f) {
+#pragma unroll
+                for (int m = 0; m < M; ++m)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j)
+                        if (cnt[m][j] != 0.0) f((uint32_t)m, (uint64_t)(j + 1), cnt[m][j]);
+            }, [&](uint32_t m, uint32_t k) { return G[m][k]; })) {
             const uint32_t fi = atomicAdd(P.flag_n, 1u);  // replayed read by read in the reference's order
             P.flag_list[fi] = x;
             P.ev_flag[x] = fi + 1u;
@@ -1451,11 +1476,14 @@ __global__ void __launch_bounds__(128) lsq_solve_small_kernel(SolveParams P) {
 // an event's records in the reference's index order and replays the EM read by read.  Rare: an event is flagged
 // when its stop decision lies within summation-order noise of the threshold.
 // ---------------------------------------------------------------------------------------------
+constexpr uint32_t COLLECT_BIN_SHIFT = 12;
 struct CollectParams {
     const uint32_t *ev_flag;      // [E] index + 1 of the event in the flag list, 0: not flagged
     const int32_t *iv_start;      // merged spans of the flagged events, sorted by (chromosome, start) ...
     const int32_t *iv_end;        // ... inclusive ends
     const uint32_t *iv_chrom_off; // [n_chroms + 1] interval range per annotation chromosome
+    const uint32_t *bin_off;      // [n_chroms + 1] first bin of the chromosome in bin_bits (COLLECT_BIN_SHIFT-wide bins
+    const uint32_t *bin_bits;     //  up to the chromosome's last flagged span); bit set: a flagged span overlaps the bin
     const uint64_t *seg_off;      // [n_flag + 1] record range per flagged event
     uint32_t *seg_cur;            // [n_flag] records written so far
     ExactRec *rec;
@@ -1504,7 +1532,10 @@ __global__ void __launch_bounds__(SCAN_BLOCK) lsq_collect_kernel(const __grid_co
                 const int2 b = load_block(P, base + j);
                 const uint32_t cs = (cs0 & 0x80000000u) ? __ldg(P.blk_cs + base + j) : cs0;
                 const uint32_t c = __ldg(P.chrom_remap + (cs & 0xFFFFu));
-                if (c == 0xFFFFFFFFu) continue;
+                if (c == 0xFFFFFFFFu || b.x < 0) continue;
+                // coarse: one bit per 4 kb bin (a table that stays in L1); exact: binary search of the merged spans
+                const uint32_t bin0 = __ldg(C.bin_off + c), bin = bin0 + ((uint32_t)b.x >> COLLECT_BIN_SHIFT);
+                if (bin >= __ldg(C.bin_off + c + 1) || !((__ldg(C.bin_bits + (bin >> 5)) >> (bin & 31u)) & 1u)) continue;
                 uint32_t lo = __ldg(C.iv_chrom_off + c), hi = __ldg(C.iv_chrom_off + c + 1);
                 while (lo < hi) {  // last interval with start <= b.x
                     const uint32_t mid = (lo + hi) >> 1;

@@ -471,6 +471,7 @@ int main(int argc, char **argv) {
                 ll = loglik(theta);
             } else {
                 double ll_old = loglik(theta);
+                uint32_t iters = 0;
                 double near = 1e300;
                 while (true) {
                     std::vector<double> old_t = theta;
@@ -490,12 +491,22 @@ int main(int argc, char **argv) {
                         theta[k] = z / n_total;
                     }
                     ll = loglik(theta);
+                    ++iters;
                     const double tk = fabs(1.0 - ll_old / ll);
                     if (fabs(tk - 1E-6) < near) near = fabs(tk - 1E-6);
                     if (!(tk > 1E-6)) break;
                     ll_old = ll;
                 }
-                if (em_stop_is_fragile(near, ll, n_total) && !getenv("LSQ_EMUL_NO_EXACT")) {
+                const bool fragile = em_stop_is_fragile(near, ll, n_total) &&
+                                     !em_result_is_order_free(K, n_total, iters, 0xFFFFFFFFu,
+                                                              [&](auto f) {
+                                                                  for (uint32_t m = 0; m < M; ++m)
+                                                                      for (auto &kv : hist[m][x]) f(m, (uint64_t)kv.first, (double)kv.second);
+                                                              },
+                                                              [&](uint32_t m, uint32_t k) { return Gm[m][h.form_off + k]; });
+                if (fragile && getenv("LSQ_EMUL_STATS"))
+                    fprintf(stderr, "emul: fragile event K %u reads %.0f near %.3g ll %.17g iters %u\n", K, n_total, near, ll, iters);
+                if (fragile && !getenv("LSQ_EMUL_NO_EXACT")) {
                     // lsq_collect_kernel + lsq_exact_kernel: the event's valid reads in the reference's index
                     // order, then the EM read by read
                     std::vector<ExactRec> recs;
