@@ -122,7 +122,7 @@ struct lsq_ctx {
     uint32_t scan_flags = 0;
     DevBuf d_n_valid, d_bases_out, d_iso, d_theta, d_rpkm, d_se, d_ll, d_llpr, d_iters;
     DevBuf d_mid;  // work order of lsq_solve_mid_kernel
-    DevBuf d_flag, d_exact, d_exact_rec;  // order-exact EM replay: flag list + per-event flags; spans, segments; records
+    DevBuf d_flag, d_exact, d_exact_rec, d_cand;  // order-exact EM replay: flag list + per-event flags; spans, segments; records
     uint32_t exact_events = 0;  // events replayed by the last lsq_solve (statistics)
     float exact_ms = 0.f;       // host wall time of that replay (collect + sort + replay, its round trips included)
     bool counted = false, finalized = false, solved = false;
@@ -859,29 +859,35 @@ static int exact_replay(lsq_ctx *c, const lsq::SolveParams &P, uint32_t n_flag) 
         }
         iv_off[ch + 1] = (uint32_t)iv_start.size();
     }
-    // coarse pre-check of the collect kernel: one bit per bin of 2^COLLECT_BIN_SHIFT positions that a flagged span overlaps
-    std::vector<uint32_t> bin_off(nch + 1, 0);
-    for (uint32_t ch = 0; ch < nch; ++ch) {
-        uint32_t nb = 0;
-        if (iv_off[ch + 1] > iv_off[ch] && iv_end[iv_off[ch + 1] - 1] >= 0)
-            nb = ((uint32_t)iv_end[iv_off[ch + 1] - 1] >> lsq::COLLECT_BIN_SHIFT) + 1u;
-        bin_off[ch + 1] = bin_off[ch] + nb;
+    // coarse test of the collect pass: one bit per bin of 2^COLLECT_BIN_SHIFT positions that a flagged span overlaps on
+    // any chromosome
+    uint32_t n_bins = 0;
+    for (size_t i = 0; i < iv_end.size(); ++i)
+        if (iv_end[i] >= 0) n_bins = std::max(n_bins, ((uint32_t)iv_end[i] >> lsq::COLLECT_BIN_SHIFT) + 1u);
+    std::vector<uint32_t> bin_bits((n_bins + 31) / 32 + 1, 0);
+    for (size_t i = 0; i < iv_end.size(); ++i) {
+        if (iv_end[i] < 0) continue;
+        const uint32_t b0 = (uint32_t)std::max(iv_start[i], 0) >> lsq::COLLECT_BIN_SHIFT, b1 = (uint32_t)iv_end[i] >> lsq::COLLECT_BIN_SHIFT;
+        for (uint32_t b = b0; b <= b1; ++b) bin_bits[b >> 5] |= 1u << (b & 31u);
     }
-    std::vector<uint32_t> bin_bits((bin_off[nch] + 31) / 32 + 1, 0);
-    for (uint32_t ch = 0; ch < nch; ++ch)
-        for (uint32_t i = iv_off[ch]; i < iv_off[ch + 1]; ++i) {
-            if (iv_end[i] < 0) continue;
-            const uint32_t b0 = (uint32_t)std::max(iv_start[i], 0) >> lsq::COLLECT_BIN_SHIFT, b1 = (uint32_t)iv_end[i] >> lsq::COLLECT_BIN_SHIFT;
-            for (uint32_t b = b0; b <= b1; ++b) bin_bits[(bin_off[ch] + b) >> 5] |= 1u << ((bin_off[ch] + b) & 31u);
-        }
-    // device layout: seg_off | seg_cur | iv_off | iv_start | iv_end | strand ranks (one row per read set) | bin_off | bin_bits
+    // device layout: seg_off | seg_cur | iv_off | iv_start | iv_end | strand ranks (one row per read set) | candidate counters | bin_bits | pre_off
     const size_t niv = iv_start.size();
     const size_t o_cur = (size_t)(n_flag + 1) * 8, o_ivoff = o_cur + (((size_t)n_flag * 4 + 7) & ~(size_t)7), o_ivs = o_ivoff + (size_t)(nch + 2) * 4,
-                 o_ive = o_ivs + niv * 4 + 4, o_sr = o_ive + niv * 4 + 4, o_boff = o_sr + (size_t)LSQ_MAX_METHODS * 256,
-                 o_bits = o_boff + (size_t)(nch + 2) * 4, bytes = o_bits + bin_bits.size() * 4;
+                 o_ive = o_ivs + niv * 4 + 4, o_sr = o_ive + niv * 4 + 4, o_candn = o_sr + (size_t)LSQ_MAX_METHODS * 256,
+                 o_bits = o_candn + (size_t)LSQ_MAX_METHODS * 4, o_poff = (o_bits + bin_bits.size() * 4 + 7) & ~(size_t)7,
+                 bytes = o_poff + (size_t)(n_flag + 1) * 8;
     LSQ_CUDA(c->d_exact.ensure(bytes));
-    const uint64_t n_rec = std::max<uint64_t>(seg_off[n_flag], 1);  // records, then one class byte per record
-    LSQ_CUDA(c->d_exact_rec.ensure(n_rec * sizeof(lsq::ExactRec) + n_rec + 16));
+    const uint64_t n_rec = std::max<uint64_t>(seg_off[n_flag], 1);  // records, then one class byte per record, then the chunk tables
+    std::vector<uint64_t> pre_off(n_flag + 1, 0);                   // rows of EXACT_MAX_CLS counters (ordered_sum)
+    uint64_t n_max = 0;
+    for (uint32_t i = 0; i < n_flag; ++i) {
+        const uint64_t n_i = seg_off[i + 1] - seg_off[i];
+        pre_off[i + 1] = pre_off[i] + (n_i >= lsq::ORD_MIN_N ? n_i / lsq::ORD_CHUNK + 2 : 0);
+        n_max = std::max(n_max, n_i);
+    }
+    const uint64_t o_cls = n_rec * sizeof(lsq::ExactRec), o_pre = (o_cls + n_rec + 15) & ~(uint64_t)15;
+    const uint64_t o_ctab = (o_pre + (pre_off[n_flag] + 1) * lsq::EXACT_MAX_CLS * 4 + 15) & ~(uint64_t)15;
+    LSQ_CUDA(c->d_exact_rec.ensure(o_ctab + (uint64_t)n_flag * lsq::EXACT_CTAB * 8));
     unsigned char *d = c->d_exact.as<unsigned char>();
     std::vector<unsigned char> hbuf(bytes, 0);
     memcpy(hbuf.data(), seg_off.data(), (size_t)(n_flag + 1) * 8);
@@ -890,8 +896,8 @@ static int exact_replay(lsq_ctx *c, const lsq::SolveParams &P, uint32_t n_flag) 
         memcpy(hbuf.data() + o_ivs, iv_start.data(), niv * 4);
         memcpy(hbuf.data() + o_ive, iv_end.data(), niv * 4);
     }
-    memcpy(hbuf.data() + o_boff, bin_off.data(), (size_t)(nch + 1) * 4);
     memcpy(hbuf.data() + o_bits, bin_bits.data(), bin_bits.size() * 4);
+    memcpy(hbuf.data() + o_poff, pre_off.data(), (size_t)(n_flag + 1) * 8);
     for (uint32_t m = 0; m < M; ++m) {  // rank of every file strand string (bytewise order, count.cpp:64-85)
         const std::vector<std::string> &sn = c->sets[m].strand_names;
         for (size_t i = 0; i < sn.size() && i < 256; ++i) {
@@ -930,18 +936,36 @@ static int exact_replay(lsq_ctx *c, const lsq::SolveParams &P, uint32_t n_flag) 
         C.iv_chrom_off = reinterpret_cast<const uint32_t *>(d + o_ivoff);
         C.iv_start = reinterpret_cast<const int32_t *>(d + o_ivs);
         C.iv_end = reinterpret_cast<const int32_t *>(d + o_ive);
-        C.bin_off = reinterpret_cast<const uint32_t *>(d + o_boff);
         C.bin_bits = reinterpret_cast<const uint32_t *>(d + o_bits);
+        C.n_bins = n_bins;
         C.seg_off = reinterpret_cast<const uint64_t *>(d);
         C.seg_cur = reinterpret_cast<uint32_t *>(d + o_cur);
         C.rec = c->d_exact_rec.as<lsq::ExactRec>();
         C.strand_rank = d + o_sr + (size_t)m * 256;
         C.m = m;
-        const uint64_t n_groups = (rs.n_reads + lsq::SCAN_GROUP - 1) / lsq::SCAN_GROUP;
-        const unsigned grid = (unsigned)std::min<uint64_t>((n_groups + lsq::SCAN_WARPS - 1) / lsq::SCAN_WARPS, (uint64_t)c->n_sms * 4);
-        lsq::lsq_collect_kernel<<<grid, lsq::SCAN_BLOCK, 0, s>>>(SP, C);
-        LSQ_CUDA(cudaGetLastError());
-        c->tm.launches++;
+        C.cand_n = reinterpret_cast<uint32_t *>(d + o_candn) + m;
+        // pass 1 lists the blocks that pass the coarse test; the list is sized for 1 block in 16 and grown on demand
+        uint32_t n_cand = 0;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            const uint64_t cap = attempt == 0 ? std::max<uint64_t>(rs.n_blocks / 16, 1u << 20) : (uint64_t)n_cand;
+            LSQ_CUDA(c->d_cand.ensure(cap * 4));
+            C.cand = c->d_cand.as<uint32_t>();
+            C.cand_cap = (uint32_t)std::min<uint64_t>(cap, 0xFFFFFFFFull);
+            if (attempt) LSQ_CUDA(cudaMemsetAsync(C.cand_n, 0, 4, s));
+            const unsigned grid = (unsigned)std::min<uint64_t>((rs.n_blocks / 4 + 255) / 256 + 1, (uint64_t)c->n_sms * 16);
+            lsq::lsq_collect_list_kernel<<<grid, 256, 0, s>>>(SP, C, rs.n_blocks);
+            LSQ_CUDA(cudaGetLastError());
+            c->tm.launches++;
+            LSQ_CUDA(cudaMemcpyAsync(&n_cand, C.cand_n, 4, cudaMemcpyDeviceToHost, s));
+            LSQ_CUDA(cudaStreamSynchronize(s));
+            if (n_cand <= C.cand_cap) break;
+        }
+        if (n_cand) {
+            const unsigned grid = (unsigned)std::min<uint64_t>(((uint64_t)n_cand + 127) / 128, (uint64_t)c->n_sms * 16);
+            lsq::lsq_collect_kernel<<<grid, 128, 0, s>>>(SP, C);
+            LSQ_CUDA(cudaGetLastError());
+            c->tm.launches++;
+        }
     }
     lsq::ExactParams X;
     X.n_flag = n_flag;
@@ -949,7 +973,29 @@ static int exact_replay(lsq_ctx *c, const lsq::SolveParams &P, uint32_t n_flag) 
     X.seg_off = reinterpret_cast<const uint64_t *>(d);
     X.seg_cur = reinterpret_cast<const uint32_t *>(d + o_cur);
     X.rec = c->d_exact_rec.as<lsq::ExactRec>();
-    X.cls = reinterpret_cast<uint8_t *>(X.rec + n_rec);
+    X.cls = c->d_exact_rec.as<uint8_t>() + o_cls;
+    X.pre = reinterpret_cast<uint32_t *>(c->d_exact_rec.as<uint8_t>() + o_pre);
+    X.pre_off = reinterpret_cast<const uint64_t *>(d + o_poff);
+    X.ctab = reinterpret_cast<unsigned long long *>(c->d_exact_rec.as<uint8_t>() + o_ctab);
+    X.total = seg_off[n_flag];
+    X.presorted = n_max > 8192 ? 1u : 0u;  // one block sorts a short event by itself; long ones take the whole device
+    if (X.presorted) {
+        const unsigned grid = (unsigned)((X.total + 255) / 256);
+        for (uint64_t k = 2; (k >> 1) < n_max; k <<= 1) {
+            X.sort_k = (uint32_t)k;
+            X.sort_j = 0;
+            lsq::lsq_exact_sort_kernel<<<grid, 256, 0, s>>>(X);
+            for (uint32_t j = (uint32_t)(k >> 2); j > 0; j >>= 1) {
+                X.sort_j = j;
+                lsq::lsq_exact_sort_kernel<<<grid, 256, 0, s>>>(X);
+            }
+            c->tm.launches += 1;  // counted per merge level, not per step
+        }
+        LSQ_CUDA(cudaMemsetAsync(X.ctab, 0, (size_t)n_flag * lsq::EXACT_CTAB * 8, s));
+        lsq::lsq_exact_classify_kernel<<<grid, 256, 0, s>>>(X);
+        LSQ_CUDA(cudaGetLastError());
+        c->tm.launches++;
+    }
     lsq::lsq_exact_kernel<<<n_flag, lsq::EXACT_BLOCK, 0, s>>>(P, X);
     LSQ_CUDA(cudaGetLastError());
     c->tm.launches++;

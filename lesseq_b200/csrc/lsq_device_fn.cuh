@@ -1108,6 +1108,121 @@ LSQ_HD double exact_class_prob(uint64_t mask, uint32_t K, const double *theta, c
     return s;
 }
 
+// ---------------------------------------------------------------------------------------------
+// The running sum  s <- fl(s + term[cls[i]]),  i = 0 .. n-1,  bit for bit, without n dependent additions.
+// All terms have one sign and take C <= 64 distinct values.  While s stays inside one binade [2^e, 2^(e+1)) it is an
+// integer multiple S of u = ulp(s), and fl(s + t) = (S + inc_t) u with the INTEGER inc_t = t/u rounded to nearest
+// (a term that is an exact half-way case rounds by the parity of S: such binades, rare and short, are added up one
+// by one).  So inside a binade the sum is integer arithmetic, order does not matter, and the only question is where
+// the binade ends: the first read at which S + (sum of inc) reaches 2^53.  A table of per-class read counts ahead of
+// every chunk of ORD_CHUNK reads answers that with a binary search over the chunks plus a walk through one chunk;
+// the addition that crosses into the next binade is done in floating point, and the next binade starts.  A sum over
+// n reads costs O(binades * (C log(n / ORD_CHUNK) + ORD_CHUNK)) instead of n.
+// pre[j * C + c]: reads of class c in chunks 0 .. j-1 (j = 0 .. n_chunks).  term[c * stride]: the term of class c; the
+// result is the sum of the MAGNITUDES (the caller gives it the terms' common sign).
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t ORD_CHUNK = 128;
+constexpr uint32_t ORD_MIN_N = 4096;  // shorter sequences are summed one by one
+
+LSQ_HD uint64_t ord_sat_mul(uint64_t inc, uint64_t cnt, uint64_t cap) {  // min(inc * cnt, cap)
+#ifdef __CUDA_ARCH__
+    if (__umul64hi(inc, cnt) != 0ull) return cap;
+    const uint64_t lo = inc * cnt;
+#else
+    const unsigned __int128 w = (unsigned __int128)inc * cnt;
+    if (w >> 64) return cap;
+    const uint64_t lo = (uint64_t)w;
+#endif
+    return lo > cap ? cap : lo;
+}
+
+LSQ_HD uint32_t ord_min(uint32_t a, uint32_t b) { return a < b ? a : b; }
+
+LSQ_HD double ordered_sum(const uint8_t *cls, uint32_t n, const double *term, uint32_t stride, uint32_t C, const uint32_t *pre) {
+    auto mag = [&](uint32_t c) { return fabs(term[c * stride]); };
+    double s = 0.0;
+    uint32_t i = 0;
+    const uint32_t n_chunks = (n + ORD_CHUNK - 1u) / ORD_CHUNK;
+    uint64_t inc[EXACT_MAX_CLS];
+    while (i < n) {
+        if (s == 0.0) {  // 0 + t is exact
+            s = mag(cls[i]);
+            ++i;
+            continue;
+        }
+        int e;  // s = m 2^e, 0.5 <= m < 1: the binade is [2^(e-1), 2^e), u = 2^(e-53)
+        (void)frexp(s, &e);
+        uint64_t S = (uint64_t)ldexp(s, 53 - e);
+        const uint64_t rem = (1ull << 53) - S;  // the sum leaves the binade when the increments reach rem
+        bool tie = false;
+        for (uint32_t c = 0; c < C; ++c) {
+            const double sc = ldexp(mag(c), 53 - e);  // t / u, exact (or underflows towards 0: far below 1/2)
+            if (!(sc < 9007199254740992.0)) {
+                inc[c] = rem;  // t alone leaves the binade
+            } else {
+                const double q = floor(sc), r = sc - q;
+                inc[c] = (uint64_t)q + (r > 0.5 ? 1ull : 0ull);
+                if (r == 0.5) tie = true;
+                if (inc[c] > rem) inc[c] = rem;
+            }
+        }
+        const double top = ldexp(1.0, e);
+        if (tie || e < -900) {  // one by one until the binade is left (also near the subnormal range, where u is not 2^(e-53))
+            while (i < n && s < top) {
+                s = lsq_add(s, mag(cls[i]));
+                ++i;
+            }
+            continue;
+        }
+        uint64_t acc = 0;  // increments taken inside this binade, < rem
+        bool crossed = false;
+        auto walk = [&](uint32_t end) {  // read by read up to `end`; stops before the read that would cross
+            while (i < end) {
+                const uint64_t d = inc[cls[i]];
+                if (d >= rem - acc) {
+                    crossed = true;
+                    return;
+                }
+                acc += d;
+                ++i;
+            }
+        };
+        walk(ord_min(n, (i / ORD_CHUNK + 1u) * ORD_CHUNK));  // to the end of the current chunk
+        if (!crossed && i < n) {
+            // i is a chunk boundary j0: the last boundary j whose reads [j0, j) all stay inside the binade
+            const uint32_t j0 = i / ORD_CHUNK;
+            const uint64_t room = rem - acc;
+            auto span = [&](uint32_t j) {  // min(sum of increments of chunks [j0, j), room)
+                uint64_t g = 0;
+                for (uint32_t c = 0; c < C && g < room; ++c) {
+                    const uint32_t cnt = LSQ_LD(pre + (size_t)j * C + c) - LSQ_LD(pre + (size_t)j0 * C + c);
+                    if (cnt) g += ord_sat_mul(inc[c], cnt, room);
+                }
+                return g < room ? g : room;
+            };
+            uint32_t lo = j0, hi = n_chunks;  // span(lo) < room always; find the largest such boundary
+            if (span(hi) < room) {
+                lo = hi;
+            } else {
+                while (hi - lo > 1u) {
+                    const uint32_t mid = lo + (hi - lo) / 2u;
+                    if (span(mid) < room) lo = mid;
+                    else hi = mid;
+                }
+            }
+            acc += span(lo);
+            i = ord_min(n, lo * ORD_CHUNK);
+            if (i < n) walk(ord_min(n, (lo + 1u) * ORD_CHUNK));  // the crossing read is in this chunk
+        }
+        s = ldexp((double)(S + acc), e - 53);  // exact: S + acc < 2^53
+        if (crossed) {
+            s = lsq_add(s, mag(cls[i]));
+            ++i;
+        }
+    }
+    return s;
+}
+
 // compute_iso_probs_EM (read.h:638-660) over the sorted records, every term evaluated per read: for events with more
 // classes than the tables below hold.  theta (K doubles) receives the result, old_theta is scratch.  Returns the
 // iterations executed; ll_out = the final log-likelihood.

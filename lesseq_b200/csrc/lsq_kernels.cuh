@@ -1482,8 +1482,11 @@ struct CollectParams {
     const int32_t *iv_start;      // merged spans of the flagged events, sorted by (chromosome, start) ...
     const int32_t *iv_end;        // ... inclusive ends
     const uint32_t *iv_chrom_off; // [n_chroms + 1] interval range per annotation chromosome
-    const uint32_t *bin_off;      // [n_chroms + 1] first bin of the chromosome in bin_bits (COLLECT_BIN_SHIFT-wide bins
-    const uint32_t *bin_bits;     //  up to the chromosome's last flagged span); bit set: a flagged span overlaps the bin
+    const uint32_t *bin_bits;     // coarse test: bit b set = a flagged span overlaps positions [b, b + 1) << COLLECT_BIN_SHIFT
+    uint32_t n_bins;              //  on some chromosome
+    uint32_t *cand;               // blocks that pass the coarse test
+    uint32_t *cand_n;
+    uint32_t cand_cap;
     const uint64_t *seg_off;      // [n_flag + 1] record range per flagged event
     uint32_t *seg_cur;            // [n_flag] records written so far
     ExactRec *rec;
@@ -1491,90 +1494,133 @@ struct CollectParams {
     uint32_t m;
 };
 
-__global__ void __launch_bounds__(SCAN_BLOCK) lsq_collect_kernel(const __grid_constant__ ScanParams P,
-                                                                 const __grid_constant__ CollectParams C) {
+// One read of the collect pass: exact pre-check of its blocks against the flagged events' spans, then the general
+// walk; a record for every flagged event the read is valid for.  first_hit: the block the candidate list named (the
+// read is taken only from its FIRST block that passes the coarse test, so that it is collected once).
+__device__ __forceinline__ bool collect_coarse_hit(const CollectParams &C, int32_t x) {
+    if (x < 0) return false;
+    const uint32_t bin = (uint32_t)x >> COLLECT_BIN_SHIFT;
+    return bin < C.n_bins && ((__ldg(C.bin_bits + (bin >> 5)) >> (bin & 31u)) & 1u);
+}
+
+__device__ void collect_read(const ScanParams &P, const CollectParams &C, uint64_t r, uint32_t base, uint32_t nraw, uint32_t first_hit) {
     const Tables &T = P.T;
-    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-    const uint64_t n_groups = (P.n_reads + SCAN_GROUP - 1) / SCAN_GROUP;
-#pragma unroll 1
-    for (uint64_t g = (uint64_t)blockIdx.x * SCAN_WARPS + warp; g < n_groups; g += (uint64_t)gridDim.x * SCAN_WARPS) {
-        const uint64_t g0 = g * SCAN_GROUP, g1 = min(g0 + (uint64_t)SCAN_GROUP, P.n_reads);
-        const uint64_t r0 = g0 + 4u * lane;
-        uint32_t c4 = 0, o;
-        if (P.blk_cnt != nullptr) {
-            if (r0 < g1) {
-                c4 = __ldg(reinterpret_cast<const uint32_t *>(P.blk_cnt + r0));
-                if (r0 + 4 > g1) c4 &= 0xFFFFFFFFu >> (8u * (uint32_t)(r0 + 4 - g1));
-            }
-            const uint32_t mine = __vsadu4(c4, 0u);
-            uint32_t incl = mine;
-#pragma unroll
-            for (uint32_t d = 1; d < 32u; d <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-                if (lane >= d) incl += t;
-            }
-            o = __ldg(P.sup_base + (g / SCAN_SUPER)) + __ldg(P.grp_base + g) + incl - mine;
+    const uint32_t cs0 = load_read_cs(P, r);
+    for (uint32_t j = 0; j < first_hit; ++j)
+        if (collect_coarse_hit(C, load_block(P, base + j).x)) return;  // an earlier candidate entry owns this read
+    bool hit = false;
+    for (uint32_t j = first_hit; j < nraw && !hit; ++j) {
+        const int2 b = load_block(P, base + j);
+        const uint32_t cs = (cs0 & 0x80000000u) ? __ldg(P.blk_cs + base + j) : cs0;
+        const uint32_t c = __ldg(P.chrom_remap + (cs & 0xFFFFu));
+        if (c == 0xFFFFFFFFu) continue;
+        uint32_t lo = __ldg(C.iv_chrom_off + c), hi = __ldg(C.iv_chrom_off + c + 1);
+        while (lo < hi) {  // last interval with start <= b.x
+            const uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(C.iv_start + mid) <= b.x) lo = mid + 1;
+            else hi = mid;
+        }
+        hit = lo > __ldg(C.iv_chrom_off + c) && b.x <= __ldg(C.iv_end + lo - 1);
+    }
+    if (!hit) return;
+    const DirectCtx ctx{P, base};
+    const FilteredRead fr = filter_read_t(P, r, base, nraw, cs0, ctx);
+    if (fr.n == 0u || fr.piece == PIECE_NONE) return;
+    ReadView rv;
+    rv.blk = P.ext + ext_slot(base, (uint32_t)r) + 1;
+    rv.b0 = fr.first;
+    rv.b1 = fr.n > 1u ? fr.second : make_int2(0, 0);
+    rv.b2 = fr.n > 2u ? rv.blk[2] : make_int2(0, 0);
+    rv.n = fr.n;
+    rv.ridx = (uint32_t)r;
+    uint32_t total = 0;
+    for (uint32_t b = 0; b < fr.n; ++b) {
+        const int2 blk = rv.block(b);
+        total += (uint32_t)(blk.y - blk.x);
+    }
+    const uint32_t e0 = __ldg(T.stab_off + fr.piece), e1 = __ldg(T.stab_off + fr.piece + 1);
+    for (uint32_t q = e0; q < e1; ++q) {
+        const uint32_t x = __ldg(&T.stab[q].x);
+        const uint32_t fi = __ldg(C.ev_flag + x);
+        if (fi == 0u) continue;
+        const EvHdr h = T.hdr[x];
+        uint32_t ml;
+        const uint64_t cm = eval_pair(P, h, T.seg + h.seg_off, T.fmask + h.form_off, rv, fr.strand, total, ml);
+        if (cm == 0ull) continue;
+        const uint64_t at = C.seg_off[fi - 1u] + atomicAdd(C.seg_cur + (fi - 1u), 1u);
+        if (at >= C.seg_off[fi]) continue;  // cannot happen: the segment holds the event's n_valid records
+        C.rec[at] = make_exact_rec(C.m, fr.first.x, rv.last_end(), __ldg(C.strand_rank + fr.strand),
+                                   P.line_num ? __ldg(P.line_num + r) : (uint32_t)r + 1u, cm);
+    }
+}
+
+// Pass 1 of the collect: the block starts of the whole read set streamed once, one coarse test each (one bit per
+// 2^COLLECT_BIN_SHIFT positions that a flagged event's span overlaps on ANY chromosome -- the table stays in L1);
+// the blocks that pass (a fraction of a percent) are listed.  HBM-bound: 4 bytes per block.
+__global__ void __launch_bounds__(256) lsq_collect_list_kernel(const __grid_constant__ ScanParams P, const __grid_constant__ CollectParams C,
+                                                               uint64_t n_blocks) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * 4u;
+    for (uint64_t b = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4u; b < n_blocks; b += stride) {
+        int32_t x[4];
+        if (P.blk_start != nullptr && b + 4u <= n_blocks && (reinterpret_cast<uintptr_t>(P.blk_start) & 15u) == 0u) {
+            const int4 v = __ldcs(reinterpret_cast<const int4 *>(P.blk_start + b));
+            x[0] = v.x, x[1] = v.y, x[2] = v.z, x[3] = v.w;
         } else {
-            o = r0 < g1 ? __ldg(P.blk_off + r0) : 0u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                x[j] = b + j < n_blocks ? (P.blk_start != nullptr ? __ldcs(P.blk_start + b + j) : __ldcs(&P.blk[b + j].x)) : -1;
         }
-#pragma unroll 1
-        for (uint32_t k = 0; k < (uint32_t)SCAN_ITEMS; ++k) {
-            const uint64_t r = r0 + k;
-            if (r >= g1) break;
-            const uint32_t nraw = P.blk_cnt != nullptr ? (c4 >> (8u * k)) & 0xFFu : __ldg(P.blk_off + r + 1) - o;
-            const uint32_t base = o;
-            o += nraw;
-            if (nraw == 0u) continue;
-            const uint32_t cs0 = load_read_cs(P, r);
-            // cheap pre-check: does any block start inside the span of a flagged event?
-            bool hit = false;
-            for (uint32_t j = 0; j < nraw && !hit; ++j) {
-                const int2 b = load_block(P, base + j);
-                const uint32_t cs = (cs0 & 0x80000000u) ? __ldg(P.blk_cs + base + j) : cs0;
-                const uint32_t c = __ldg(P.chrom_remap + (cs & 0xFFFFu));
-                if (c == 0xFFFFFFFFu || b.x < 0) continue;
-                // coarse: one bit per 4 kb bin (a table that stays in L1); exact: binary search of the merged spans
-                const uint32_t bin0 = __ldg(C.bin_off + c), bin = bin0 + ((uint32_t)b.x >> COLLECT_BIN_SHIFT);
-                if (bin >= __ldg(C.bin_off + c + 1) || !((__ldg(C.bin_bits + (bin >> 5)) >> (bin & 31u)) & 1u)) continue;
-                uint32_t lo = __ldg(C.iv_chrom_off + c), hi = __ldg(C.iv_chrom_off + c + 1);
-                while (lo < hi) {  // last interval with start <= b.x
-                    const uint32_t mid = (lo + hi) >> 1;
-                    if (__ldg(C.iv_start + mid) <= b.x) lo = mid + 1;
-                    else hi = mid;
-                }
-                hit = lo > __ldg(C.iv_chrom_off + c) && b.x <= __ldg(C.iv_end + lo - 1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (collect_coarse_hit(C, x[j])) {
+                const uint32_t at = atomicAdd(C.cand_n, 1u);
+                if (at < C.cand_cap) C.cand[at] = (uint32_t)(b + j);
             }
-            if (!hit) continue;
-            const DirectCtx ctx{P, base};
-            const FilteredRead fr = filter_read_t(P, r, base, nraw, cs0, ctx);
-            if (fr.n == 0u || fr.piece == PIECE_NONE) continue;
-            ReadView rv;
-            rv.blk = P.ext + ext_slot(base, (uint32_t)r) + 1;
-            rv.b0 = fr.first;
-            rv.b1 = fr.n > 1u ? fr.second : make_int2(0, 0);
-            rv.b2 = fr.n > 2u ? rv.blk[2] : make_int2(0, 0);
-            rv.n = fr.n;
-            rv.ridx = (uint32_t)r;
-            uint32_t total = 0;
-            for (uint32_t b = 0; b < fr.n; ++b) {
-                const int2 blk = rv.block(b);
-                total += (uint32_t)(blk.y - blk.x);
+    }
+}
+
+// Pass 2: one thread per listed block: find its read in the block-offset index, collect the read.
+__global__ void __launch_bounds__(128) lsq_collect_kernel(const __grid_constant__ ScanParams P, const __grid_constant__ CollectParams C) {
+    const uint32_t n_cand = min(*C.cand_n, C.cand_cap);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_cand; i += gridDim.x * blockDim.x) {
+        const uint32_t bi = C.cand[i];
+        uint64_t r;
+        uint32_t base;
+        if (P.blk_cnt != nullptr) {
+            const uint32_t n_groups = (uint32_t)((P.n_reads + SCAN_GROUP - 1) / SCAN_GROUP), n_sup = (n_groups + SCAN_SUPER - 1) / SCAN_SUPER;
+            uint32_t lo = 0, hi = n_sup;  // last super-group that starts at or before block bi
+            while (hi - lo > 1u) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (__ldg(P.sup_base + mid) <= bi) lo = mid;
+                else hi = mid;
             }
-            const uint32_t e0 = __ldg(T.stab_off + fr.piece), e1 = __ldg(T.stab_off + fr.piece + 1);
-            for (uint32_t q = e0; q < e1; ++q) {
-                const uint32_t x = __ldg(&T.stab[q].x);
-                const uint32_t fi = __ldg(C.ev_flag + x);
-                if (fi == 0u) continue;
-                const EvHdr h = T.hdr[x];
-                uint32_t ml;
-                const uint64_t cm = eval_pair(P, h, T.seg + h.seg_off, T.fmask + h.form_off, rv, fr.strand, total, ml);
-                if (cm == 0ull) continue;
-                const uint64_t at = C.seg_off[fi - 1u] + atomicAdd(C.seg_cur + (fi - 1u), 1u);
-                if (at >= C.seg_off[fi]) continue;  // cannot happen: the segment holds the event's n_valid records
-                C.rec[at] = make_exact_rec(C.m, fr.first.x, rv.last_end(), __ldg(C.strand_rank + fr.strand),
-                                           P.line_num ? __ldg(P.line_num + r) : (uint32_t)r + 1u, cm);
+            const uint32_t sb = __ldg(P.sup_base + lo);
+            uint32_t g = lo * SCAN_SUPER, ge = min(n_groups, (lo + 1u) * SCAN_SUPER);
+            while (ge - g > 1u) {  // last group of it that does
+                const uint32_t mid = (g + ge) >> 1;
+                if (sb + __ldg(P.grp_base + mid) <= bi) g = mid;
+                else ge = mid;
             }
+            base = sb + __ldg(P.grp_base + g);
+            r = (uint64_t)g * SCAN_GROUP;
+            uint32_t c = __ldg(P.blk_cnt + r);
+            while (base + c <= bi) {  // the read of the group that holds the block
+                base += c;
+                ++r;
+                c = __ldg(P.blk_cnt + r);
+            }
+        } else {
+            uint64_t lo = 0, hi = P.n_reads;  // last read with blk_off <= bi (reads without blocks share offsets: take the one that holds it)
+            while (hi - lo > 1u) {
+                const uint64_t mid = (lo + hi) >> 1;
+                if (__ldg(P.blk_off + mid) <= bi) lo = mid;
+                else hi = mid;
+            }
+            r = lo;
+            base = __ldg(P.blk_off + r);
         }
+        const uint32_t nraw = P.blk_cnt != nullptr ? (uint32_t)__ldg(P.blk_cnt + r) : __ldg(P.blk_off + r + 1) - base;
+        collect_read(P, C, r, base, nraw, bi - base);
     }
 }
 
@@ -1584,7 +1630,13 @@ struct ExactParams {
     const uint64_t *seg_off;
     const uint32_t *seg_cur;
     ExactRec *rec;
-    uint8_t *cls;  // class index of every sorted record (same offsets as rec)
+    uint8_t *cls;             // class index of every sorted record (same offsets as rec)
+    uint32_t *pre;            // per event: class counts ahead of every ORD_CHUNK reads (ordered_sum), rows of EXACT_MAX_CLS
+    const uint64_t *pre_off;  // [n_flag] first row of the event in pre
+    uint32_t presorted;       // the records were sorted and classified by grid-wide launches (large events)
+    unsigned long long *ctab; // per event EXACT_CTAB u64: class keys (form mask | read set << 56) in order of discovery, then an overflow flag
+    uint32_t sort_k, sort_j;  // lsq_exact_sort_kernel: the step of the bitonic network (j = 0: first step of merge k)
+    uint64_t total;           // records of all events
 };
 
 constexpr int EXACT_BLOCK = 256;
@@ -1595,6 +1647,58 @@ __device__ __forceinline__ void exact_cmpxchg(ExactRec *rec, uint32_t i, uint32_
         rec[i] = b;
         rec[l] = a;
     }
+}
+
+// One step of the bitonic network (same all-ascending form as in lsq_exact_kernel) over the records of ALL flagged
+// events at once, one thread per record: for events too large for one block to sort in reasonable time.  The host
+// launches the steps in order; an event shorter than the step's span is left untouched by it.
+__global__ void __launch_bounds__(256) lsq_exact_sort_kernel(const __grid_constant__ ExactParams X) {
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= X.total) return;
+    uint32_t lo = 0, hi = X.n_flag;  // the event of record g: last f with seg_off[f] <= g
+    while (hi - lo > 1u) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(X.seg_off + mid) <= g) lo = mid;
+        else hi = mid;
+    }
+    const uint64_t o = __ldg(X.seg_off + lo);
+    const uint32_t n = min((uint32_t)(__ldg(X.seg_off + lo + 1) - o), __ldg(X.seg_cur + lo)), i = (uint32_t)(g - o);
+    if (i >= n) return;
+    const uint32_t l = X.sort_j ? i ^ X.sort_j : i ^ (X.sort_k - 1u);
+    if (l > i && l < n) exact_cmpxchg(X.rec + o, i, l);
+}
+
+// Classes of the sorted records of all flagged events (large events): one thread per record finds or appends its
+// (form mask, read set) key in the event's table -- append-only, the first empty slot is claimed with a compare-and-swap.
+constexpr uint32_t EXACT_CTAB = EXACT_MAX_CLS + 1;
+__global__ void __launch_bounds__(256) lsq_exact_classify_kernel(const __grid_constant__ ExactParams X) {
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= X.total) return;
+    uint32_t lo = 0, hi = X.n_flag;
+    while (hi - lo > 1u) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(X.seg_off + mid) <= g) lo = mid;
+        else hi = mid;
+    }
+    const uint64_t o = __ldg(X.seg_off + lo);
+    const uint32_t n = min((uint32_t)(__ldg(X.seg_off + lo + 1) - o), __ldg(X.seg_cur + lo));
+    if ((uint32_t)(g - o) >= n) return;
+    const ExactRec r = X.rec[g];
+    unsigned long long *tab = X.ctab + (size_t)lo * EXACT_CTAB;
+    if (r.mask >> 56) {  // no room for the read set in the key: the event takes the per-read path
+        tab[EXACT_MAX_CLS] = 1ull;
+        return;
+    }
+    const unsigned long long key = r.mask | ((unsigned long long)exact_rec_set(r) << 56);
+    for (uint32_t q = 0; q < EXACT_MAX_CLS; ++q) {
+        unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(tab + q);
+        if (cur == 0ull) cur = atomicCAS(tab + q, 0ull, key);
+        if (cur == 0ull || cur == key) {
+            X.cls[g] = (uint8_t)q;
+            return;
+        }
+    }
+    tab[EXACT_MAX_CLS] = 1ull;  // more classes than the table holds
 }
 
 // One block per flagged event (they are few): sort the event's records into the reference's read order, replay the
@@ -1626,7 +1730,7 @@ __global__ void __launch_bounds__(EXACT_BLOCK) lsq_exact_kernel(const __grid_con
     if ((double)n != n_total) return;  // injected class tables have no reads to replay: keep the class-collapsed result
     // ---- sort: bitonic network in its all-ascending form (first step of a merge pairs i with i ^ (k - 1)), so the
     // missing tail of a non-power-of-two n acts as +infinity and is never touched; names are unique, the order total
-    for (uint32_t k = 2; (k >> 1) < n; k <<= 1) {
+    for (uint32_t k = 2; !X.presorted && (k >> 1) < n; k <<= 1) {
         for (uint32_t i = t; i < n; i += EXACT_BLOCK) {
             const uint32_t l = i ^ (k - 1u);
             if (l > i && l < n) exact_cmpxchg(rec, i, l);
@@ -1641,7 +1745,19 @@ __global__ void __launch_bounds__(EXACT_BLOCK) lsq_exact_kernel(const __grid_con
         }
     }
     // ---- classes of the event: distinct (read set, form mask) pairs, found by one warp, 32 records at a time
-    if (t < 32u) {
+    if (X.presorted) {  // lsq_exact_classify_kernel has filled cls and the event's class table
+        if (t == 0u) {
+            const unsigned long long *tab = X.ctab + (size_t)fi * EXACT_CTAB;
+            uint32_t C = 0;
+            while (C < EXACT_MAX_CLS && tab[C] != 0ull) {
+                s_cmask[C] = tab[C] & 0x00FFFFFFFFFFFFFFull;
+                s_cset[C] = (uint32_t)(tab[C] >> 56);
+                ++C;
+            }
+            s_C = C;
+            s_tab = (tab[EXACT_MAX_CLS] == 0ull && (C + 1u) * (K + 1u) <= EXACT_MAX_TERMS + EXACT_MAX_CLS) ? 1u : 0u;
+        }
+    } else if (t < 32u) {
         uint32_t C = 0;
         bool tab = true;
         for (uint32_t base = 0; base < n && tab; base += 32u) {
@@ -1681,6 +1797,29 @@ __global__ void __launch_bounds__(EXACT_BLOCK) lsq_exact_kernel(const __grid_con
         }
     }
     __syncthreads();
+    // long events: class counts ahead of every chunk of reads, for ordered_sum
+    const bool fast_sums = s_tab && n >= ORD_MIN_N;
+    uint32_t *pre = X.pre + X.pre_off[fi] * EXACT_MAX_CLS;
+    if (fast_sums) {
+        const uint32_t C = s_C, n_chunks = (n + ORD_CHUNK - 1u) / ORD_CHUNK;
+        for (uint32_t j = t; j < n_chunks; j += EXACT_BLOCK) {
+            uint32_t cnt[EXACT_MAX_CLS];
+            for (uint32_t c = 0; c < C; ++c) cnt[c] = 0;
+            const uint32_t i1 = min(n, (j + 1u) * ORD_CHUNK);
+            for (uint32_t i = j * ORD_CHUNK; i < i1; ++i) cnt[cls[i]]++;
+            for (uint32_t c = 0; c < C; ++c) pre[(size_t)(j + 1u) * C + c] = cnt[c];
+        }
+        __syncthreads();
+        if (t < C) {  // running totals down the chunks, one class per thread
+            uint32_t run = 0;
+            pre[t] = 0;
+            for (uint32_t j = 1; j <= n_chunks; ++j) {
+                run += pre[(size_t)j * C + t];
+                pre[(size_t)j * C + t] = run;
+            }
+        }
+        __syncthreads();
+    }
     uint32_t iters = 0;
     double ll = 0.0;
     if (!s_tab) {
@@ -1715,15 +1854,29 @@ __global__ void __launch_bounds__(EXACT_BLOCK) lsq_exact_kernel(const __grid_con
             if (t < W) {
                 double acc = 0.0;
                 const double *tb = s_tbl + t;
-                uint32_t i = 0;
-                if ((reinterpret_cast<uintptr_t>(cls) & 15u) == 0u)
-                    for (; i + 16u <= n; i += 16u) {
-                        const uint4 v = *reinterpret_cast<const uint4 *>(cls + i);
-                        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                // the fast path needs terms of one sign, all finite (the log terms are <= 0 unless a class probability
+                // rounds above 1)
+                bool pos = false, neg = false, fin = true;
+                for (uint32_t c = 0; c < C; ++c) {
+                    const double v = tb[c * W];
+                    pos = pos || v > 0.0;
+                    neg = neg || v < 0.0;
+                    fin = fin && (v - v == 0.0);
+                }
+                if (fast_sums && fin && !(pos && neg)) {
+                    acc = ordered_sum(cls, n, tb, W, C, pre);
+                    if (neg && acc != 0.0) acc = -acc;
+                } else {
+                    uint32_t i = 0;
+                    if ((reinterpret_cast<uintptr_t>(cls) & 15u) == 0u)
+                        for (; i + 16u <= n; i += 16u) {
+                            const uint4 v = *reinterpret_cast<const uint4 *>(cls + i);
+                            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) acc = lsq_add(acc, tb[((w[j >> 2] >> (8 * (j & 3))) & 0xFFu) * W]);
-                    }
-                for (; i < n; ++i) acc = lsq_add(acc, tb[(uint32_t)cls[i] * W]);
+                            for (int j = 0; j < 16; ++j) acc = lsq_add(acc, tb[((w[j >> 2] >> (8 * (j & 3))) & 0xFFu) * W]);
+                        }
+                    for (; i < n; ++i) acc = lsq_add(acc, tb[(uint32_t)cls[i] * W]);
+                }
                 s_acc[t] = acc;
             }
             __syncthreads();

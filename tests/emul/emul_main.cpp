@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <map>
+#include <random>
 #include <string>
 #include <vector>
 
@@ -154,12 +155,59 @@ static lsq_event_tables tables_of(const lsqh_annotation &ann) {
     return t;
 }
 
+// ordered_sum (the binade-exact running sum of lsq_exact_kernel) against the plain loop, bit for bit, on random class
+// sequences: terms spread over many binades, short ones (so that exact half-way cases occur), zeros, long runs.
+static int ordered_sum_selftest(unsigned seed) {
+    std::mt19937_64 rng(seed);
+    const uint32_t C = 1 + rng() % 64, n = 1 + rng() % (seed % 7 == 0 ? 3000000u : 200000u), stride = 1 + rng() % 3;
+    std::vector<double> term((size_t)C * stride, 0.0);
+    const int style = (int)(rng() % 4);
+    for (uint32_t c = 0; c < C; ++c) {
+        double t;
+        if (style == 0) t = ldexp((double)(1 + rng() % 7), -(int)(rng() % 12));                      // short: ties galore
+        else if (style == 1) t = ldexp((double)(rng() >> 11) / 9007199254740992.0, -(int)(rng() % 40));  // full mantissas
+        else if (style == 2) t = (rng() % 5 == 0) ? 0.0 : -log((double)(1 + rng() % 1000) / 1001.0);   // like log terms
+        else t = (double)(1 + rng() % 1000) / (double)(1 + rng() % 1000);
+        term[(size_t)c * stride] = (seed & 1) ? -t : t;
+    }
+    std::vector<uint8_t> cls(n);
+    uint32_t run = 0, cur = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        if (run == 0) {
+            cur = (uint32_t)(rng() % C);
+            run = 1 + (uint32_t)(rng() % (style == 3 ? 5000 : 8));
+        }
+        cls[i] = (uint8_t)cur;
+        --run;
+    }
+    const uint32_t n_chunks = (n + lsq::ORD_CHUNK - 1) / lsq::ORD_CHUNK;
+    std::vector<uint32_t> pre((size_t)(n_chunks + 1) * C, 0);
+    for (uint32_t j = 0; j < n_chunks; ++j) {
+        for (uint32_t c = 0; c < C; ++c) pre[(size_t)(j + 1) * C + c] = pre[(size_t)j * C + c];
+        for (uint32_t i = j * lsq::ORD_CHUNK; i < std::min(n, (j + 1) * lsq::ORD_CHUNK); ++i) pre[(size_t)(j + 1) * C + cls[i]]++;
+    }
+    double seq = 0.0;
+    for (uint32_t i = 0; i < n; ++i) seq = seq + fabs(term[(size_t)cls[i] * stride]);
+    const double fast = lsq::ordered_sum(cls.data(), n, term.data(), stride, C, pre.data());
+    if (memcmp(&seq, &fast, 8) != 0) {
+        fprintf(stderr, "ordered_sum selftest: seed %u C %u n %u style %d: %.17g != %.17g\n", seed, C, n, style, fast, seq);
+        return 1;
+    }
+    return 0;
+}
+
 int main(int argc, char **argv) {
     if (argc < 2) return 2;
     if (std::string(argv[1]) == "bucket-selftest") {
         const unsigned n = argc > 2 ? (unsigned)atoi(argv[2]) : 50;
         for (unsigned seed = 1; seed <= n; ++seed)
             if (bucket_selftest(seed)) return 1;
+        return 0;
+    }
+    if (std::string(argv[1]) == "ordered-sum-selftest") {
+        const unsigned n = argc > 2 ? (unsigned)atoi(argv[2]) : 200;
+        for (unsigned seed = 1; seed <= n; ++seed)
+            if (ordered_sum_selftest(seed)) return 1;
         return 0;
     }
     const bool solve = std::string(argv[1]) == "solve";

@@ -87,6 +87,32 @@ def test_abi_matches_reference_golden_fuzz(api, tmp_path):
     ctx.close()
 
 
+def test_large_fragile_events_match_reference_golden(api, tmp_path):
+    """tests/golden/em_fragile_large.json: events of 40-80 k reads with a fragile EM stop.  The replay takes the path
+    of large events (device-wide bitonic sort, lsq_exact_classify_kernel, ordered_sum); theta, RPKM and log-likelihood
+    within 1e-9 of the reference binaries, which a class-collapsed EM alone misses (tests/test_host_cpu.py)."""
+    for case in golden_util.load("em_fragile_large.json"):
+        d = tmp_path / case["name"]
+        d.mkdir()
+        ca, sa = golden_util.materialise(case, str(d))
+        ann = api.Annotation(ca[4], ca[6], case["begin"], case["end"])
+        ctx = api.Context(0)
+        ctx.upload_events(ann)
+        M = len(case["sets"])
+        for m, s in enumerate(case["sets"]):
+            ctx.set_reads(m, s["type"], s["read_length"], api.Reads.from_mrf(d / ("r%d.mrf" % m), compact=True))
+        ctx.count()
+        cnt = ctx.get_count()
+        ctx.solve([s["total_read_bases"] for s in case["sets"]])
+        sol = ctx.get_solve()
+        assert ctx.timings()["exact_events"] >= 1, case["name"]
+        ct, st = format_tables(api, ann, M, cnt, sol, 17)
+        assert tables_match(case["expect"]["count17"], ct, False) is None, case["name"]
+        bad = tables_match(case["expect"]["solve17"], st, True)
+        assert bad is None, (case["name"], bad)
+        ctx.close()
+
+
 def _oracle_dump(oracle_bin, prog, args, path):
     rc, out, err = oracle_bin.run_oracle(prog, args, dump=path)
     assert rc == 0, err

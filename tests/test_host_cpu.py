@@ -303,6 +303,29 @@ def test_piece_lookup_bucket_index_selftest(emul_bin):
     assert len(shifts) >= 10 and max(shifts) >= 12
 
 
+def test_ordered_sum_matches_sequential_sum_bit_for_bit(emul_bin):
+    """ordered_sum (lsq_device_fn.cuh: the running sum of lsq_exact_kernel taken binade by binade with integer
+    arithmetic) against the plain read-by-read loop on random class sequences: up to 64 classes, up to 3 M reads,
+    short terms (exact half-way cases), full mantissas, log-like terms, zeros, long runs, both signs."""
+    p = subprocess.run([emul_bin, "ordered-sum-selftest", "600"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr[-2000:]
+
+
+def test_large_fragile_events_replayed_on_cpu_match_reference(emul_bin, tmp_path):
+    """tests/golden/em_fragile_large.json (events of 40-80 k reads whose EM stop is decided inside the summation-order
+    noise; outputs of the reference binaries): the CPU replay of the device functions matches with the read-by-read
+    replay and does NOT match without it -- so the fixtures do exercise the replay."""
+    for case in golden_util.load("em_fragile_large.json"):
+        d = tmp_path / case["name"]
+        d.mkdir()
+        ca, sa = golden_util.materialise(case, str(d))
+        rc, out = _run_emul(emul_bin, "solve", sa)
+        assert rc == 0 and _close(case["expect"]["solve17"], out, True), case["name"]
+        env = dict(os.environ, LSQ_PRECISION="17", LSQ_EMUL_NO_EXACT="1")
+        p = subprocess.run([emul_bin, "solve"] + [str(a) for a in sa], env=env, capture_output=True, text=True)
+        assert p.returncode == 0 and not _close(case["expect"]["solve17"], p.stdout, True), case["name"]
+
+
 def test_compact_wire_format_is_lossless(tmp_path):
     """lsqh_reads_compact: blk_cnt / read_cs8 / blk_start + blk_len expand to the wide arrays."""
     import ctypes as C
