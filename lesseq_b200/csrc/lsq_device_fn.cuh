@@ -1121,7 +1121,7 @@ LSQ_HD double exact_class_prob(uint64_t mask, uint32_t K, const double *theta, c
 // pre[j * C + c]: reads of class c in chunks 0 .. j-1 (j = 0 .. n_chunks).  term[c * stride]: the term of class c; the
 // result is the sum of the MAGNITUDES (the caller gives it the terms' common sign).
 // ---------------------------------------------------------------------------------------------
-constexpr uint32_t ORD_CHUNK = 128;
+constexpr uint32_t ORD_CHUNK = 16;  // the walk through a chunk is the serial part: short chunks, a deeper search
 constexpr uint32_t ORD_MIN_N = 4096;  // shorter sequences are summed one by one
 
 LSQ_HD uint64_t ord_sat_mul(uint64_t inc, uint64_t cnt, uint64_t cap) {  // min(inc * cnt, cap)
@@ -1204,11 +1204,25 @@ LSQ_HD double ordered_sum(const uint8_t *cls, uint32_t n, const double *term, ui
             if (span(hi) < room) {
                 lo = hi;
             } else {
+#ifdef __CUDA_ARCH__
+                // on the device a whole warp runs this function on the same arguments (everything above is uniform):
+                // the lanes probe 32 boundaries at once, so the search takes log32 instead of log2 round trips to L2
+                const uint32_t lane = threadIdx.x & 31u;
+                while (hi - lo > 1u) {
+                    const uint32_t step = (hi - lo + 31u) / 32u;
+                    const bool below = span(ord_min(hi, lo + (lane + 1u) * step)) < room;  // true for a prefix of the lanes
+                    const uint32_t nb = (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, below));
+                    const uint32_t nlo = ord_min(hi, lo + nb * step), nhi = ord_min(hi, lo + (nb + 1u) * step);
+                    lo = nlo;
+                    hi = nhi;
+                }
+#else
                 while (hi - lo > 1u) {
                     const uint32_t mid = lo + (hi - lo) / 2u;
                     if (span(mid) < room) lo = mid;
                     else hi = mid;
                 }
+#endif
             }
             acc += span(lo);
             i = ord_min(n, lo * ORD_CHUNK);

@@ -1850,10 +1850,11 @@ __global__ void __launch_bounds__(EXACT_BLOCK) lsq_exact_kernel(const __grid_con
             __syncthreads();
             for (uint32_t c = t; c < C; c += EXACT_BLOCK) s_tbl[c * W + K] = log(s_tbl[c * W + K]);
             __syncthreads();
-            // the sweep: thread a < K sums form a's E-step terms, thread K the log-likelihood, each in read order
-            if (t < W) {
+            // the sweep: one warp per running sum (form a's E-step terms for a < K, the log-likelihood for a = K), each in
+            // read order; the lanes of the warp compute the same thing except inside ordered_sum's search
+            for (uint32_t a = t >> 5; a < W; a += EXACT_BLOCK / 32) {
                 double acc = 0.0;
-                const double *tb = s_tbl + t;
+                const double *tb = s_tbl + a;
                 // the fast path needs terms of one sign, all finite (the log terms are <= 0 unless a class probability
                 // rounds above 1)
                 bool pos = false, neg = false, fin = true;
@@ -1877,7 +1878,7 @@ __global__ void __launch_bounds__(EXACT_BLOCK) lsq_exact_kernel(const __grid_con
                         }
                     for (; i < n; ++i) acc = lsq_add(acc, tb[(uint32_t)cls[i] * W]);
                 }
-                s_acc[t] = acc;
+                if (lane == 0u) s_acc[a] = acc;
             }
             __syncthreads();
             ll = s_acc[K];
