@@ -317,6 +317,27 @@ int run_program(bool solve, int argc, char **argv) {
     };
     std::vector<lsqh_reads *> reads(M, nullptr);
     std::vector<Loaded> loaded(M);
+    // Creating the CUDA context takes a few hundred milliseconds and depends on nothing: it starts first.  A failure
+    // only matters if there turn out to be events to count.
+    int device = 0;
+    if (const char *d = getenv("LSQ_DEVICE")) device = atoi(d);
+    lsq_ctx *ctx = nullptr;
+    int dev_rc = 0;
+    std::string dev_err;
+    std::thread ctx_thread([&]() {
+        dev_rc = lsq_ctx_create(device, &ctx);
+        if (dev_rc) dev_err = lsq_last_error();
+        clk.mark("device_context");
+    });
+    struct CtxJoiner {  // every return path waits for the context and gives it back
+        std::thread &t;
+        lsq_ctx *&c;
+        ~CtxJoiner() {
+            if (t.joinable()) t.join();
+            if (c) lsq_ctx_destroy(c);
+            c = nullptr;
+        }
+    } ctx_joiner{ctx_thread, ctx};
     std::thread read_thread([&]() {
         for (uint32_t m = 0; m < M; ++m) {
             Loaded &L = loaded[m];
@@ -404,22 +425,17 @@ int run_program(bool solve, int argc, char **argv) {
     clk.mark("annotation_loaded");
     logf(2, "Selected %llu gene(s)", (unsigned long long)ann->n_selected);
 
-    // The device context and the event tables are set up by a helper thread while the read text is parsed: creating a
-    // CUDA context takes as long as parsing tens of millions of reads.
-    int device = 0;
-    if (const char *d = getenv("LSQ_DEVICE")) device = atoi(d);
-    lsq_ctx *ctx = nullptr;
-    int dev_rc = 0;
-    std::string dev_err;
+    // The event tables are uploaded by a helper thread (as soon as the context is there) while the read text is parsed.
     std::thread dev_thread;
     const bool have_events = tables.n_events != 0;
     if (have_events)
         dev_thread = std::thread([&]() {
-            dev_rc = lsq_ctx_create(device, &ctx);
-            clk.mark("device_context");
-            if (!dev_rc) dev_rc = lsq_upload_events(ctx, &tables);
+            if (ctx_thread.joinable()) ctx_thread.join();
+            if (!dev_rc) {
+                dev_rc = lsq_upload_events(ctx, &tables);
+                if (dev_rc) dev_err = lsq_last_error();
+            }
             clk.mark("tables_uploaded");
-            if (dev_rc) dev_err = lsq_last_error();
         });
     auto join_dev = [&]() {
         if (dev_thread.joinable()) dev_thread.join();
@@ -428,9 +444,7 @@ int run_program(bool solve, int argc, char **argv) {
     logf(2, "Loading the reads from %u sampling method(s)", M);
     auto cleanup = [&]() {
         join_dev();
-        if (ctx) lsq_ctx_destroy(ctx);
-        ctx = nullptr;
-        lsqh_annotation_free(ann);
+        lsqh_annotation_free(ann);  // the context goes with ctx_joiner
     };
     if (read_thread.joinable()) read_thread.join();
     for (uint32_t m = 0; m < M; ++m) {
