@@ -824,6 +824,14 @@ int lsq_get_classes(lsq_ctx *c, uint32_t m, uint64_t *cls_off, uint64_t *cls_mas
 // Order-exact EM replay of the flagged events (lsq_kernels.cuh: lsq_collect_kernel, lsq_exact_kernel).
 static int exact_replay(lsq_ctx *c, const lsq::SolveParams &P, uint32_t n_flag) {
     cudaStream_t s = c->stream;
+    // LSQ_EXACT_TIMING=1: wall-clock milestones of the replay on stderr (each one synchronises the stream)
+    const bool timing = getenv("LSQ_EXACT_TIMING") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto mark = [&](const char *what) {
+        if (!timing) return;
+        cudaStreamSynchronize(s);
+        fprintf(stderr, "[exact] %s %.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+    };
     const uint32_t E = c->E, M = c->M;
     const lsq::HostTables &H = c->H;
     std::vector<uint32_t> flagged(n_flag);
@@ -885,7 +893,7 @@ static int exact_replay(lsq_ctx *c, const lsq::SolveParams &P, uint32_t n_flag) 
         pre_off[i + 1] = pre_off[i] + (n_i >= lsq::ORD_MIN_N ? n_i / lsq::ORD_CHUNK + 2 : 0);
         n_max = std::max(n_max, n_i);
     }
-    const uint64_t o_cls = n_rec * sizeof(lsq::ExactRec), o_pre = (o_cls + n_rec + 15) & ~(uint64_t)15;
+    const uint64_t o_cls = n_rec * sizeof(lsq::ExactRec), o_pre = (o_cls + n_rec + 32ull * n_flag + 64 + 15) & ~(uint64_t)15;
     const uint64_t o_ctab = (o_pre + (pre_off[n_flag] + 1) * lsq::EXACT_MAX_CLS * 4 + 15) & ~(uint64_t)15;
     LSQ_CUDA(c->d_exact_rec.ensure(o_ctab + (uint64_t)n_flag * lsq::EXACT_CTAB * 8));
     unsigned char *d = c->d_exact.as<unsigned char>();
@@ -907,6 +915,8 @@ static int exact_replay(lsq_ctx *c, const lsq::SolveParams &P, uint32_t n_flag) 
         }
     }
     LSQ_CUDA(cudaMemcpyAsync(d, hbuf.data(), bytes, cudaMemcpyHostToDevice, s));
+    if (timing) fprintf(stderr, "[exact] events %u records %llu largest %llu\n", n_flag, (unsigned long long)seg_off[n_flag], (unsigned long long)n_max);
+    mark("tables on the device");
     for (uint32_t m = 0; m < M; ++m) {
         ReadSet &rs = c->sets[m];
         if (rs.injected || rs.n_reads == 0) continue;
@@ -967,6 +977,7 @@ static int exact_replay(lsq_ctx *c, const lsq::SolveParams &P, uint32_t n_flag) 
             c->tm.launches++;
         }
     }
+    mark("records collected");
     lsq::ExactParams X;
     X.n_flag = n_flag;
     X.flag_list = P.flag_list;
@@ -978,6 +989,7 @@ static int exact_replay(lsq_ctx *c, const lsq::SolveParams &P, uint32_t n_flag) 
     X.pre_off = reinterpret_cast<const uint64_t *>(d + o_poff);
     X.ctab = reinterpret_cast<unsigned long long *>(c->d_exact_rec.as<uint8_t>() + o_ctab);
     X.total = seg_off[n_flag];
+    X.scalar_sums = getenv("LSQ_EXACT_SCALAR_SUMS") ? 1u : 0u;
     X.presorted = n_max > 8192 ? 1u : 0u;  // one block sorts a short event by itself; long ones take the whole device
     if (X.presorted) {
         const unsigned grid = (unsigned)((X.total + 255) / 256);
@@ -996,10 +1008,12 @@ static int exact_replay(lsq_ctx *c, const lsq::SolveParams &P, uint32_t n_flag) 
         LSQ_CUDA(cudaGetLastError());
         c->tm.launches++;
     }
+    mark("sorted and classified");
     lsq::lsq_exact_kernel<<<n_flag, lsq::EXACT_BLOCK, 0, s>>>(P, X);
     LSQ_CUDA(cudaGetLastError());
     c->tm.launches++;
     LSQ_CUDA(cudaStreamSynchronize(s));  // hbuf and friends go out of scope
+    mark("replayed");
     c->exact_events = n_flag;
     return LSQ_OK;
 }

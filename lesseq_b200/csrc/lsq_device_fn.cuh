@@ -1138,10 +1138,16 @@ LSQ_HD uint64_t ord_sat_mul(uint64_t inc, uint64_t cnt, uint64_t cap) {  // min(
 
 LSQ_HD uint32_t ord_min(uint32_t a, uint32_t b) { return a < b ? a : b; }
 
-LSQ_HD double ordered_sum(const uint8_t *cls, uint32_t n, const double *term, uint32_t stride, uint32_t C, const uint32_t *pre) {
+constexpr uint32_t ORD_MAX_GUESS = 96;  // binades of one sum whose end is remembered from the previous sweep
+
+// guess (optional, ORD_MAX_GUESS entries, zero-initialised): where each binade ended in the previous sweep of the same
+// running sum -- theta moves little between EM iterations, so the search usually ends after one look around that place.
+// On the device cls must be 16-byte aligned (a chunk of classes is one vector load).
+LSQ_HD double ordered_sum(const uint8_t *cls, uint32_t n, const double *term, uint32_t stride, uint32_t C, const uint32_t *pre,
+                          uint32_t *guess = nullptr) {
     auto mag = [&](uint32_t c) { return fabs(term[c * stride]); };
     double s = 0.0;
-    uint32_t i = 0;
+    uint32_t i = 0, n_searches = 0;
     const uint32_t n_chunks = (n + ORD_CHUNK - 1u) / ORD_CHUNK;
     uint64_t inc[EXACT_MAX_CLS];
     while (i < n) {
@@ -1176,7 +1182,27 @@ LSQ_HD double ordered_sum(const uint8_t *cls, uint32_t n, const double *term, ui
         }
         uint64_t acc = 0;  // increments taken inside this binade, < rem
         bool crossed = false;
-        auto walk = [&](uint32_t end) {  // read by read up to `end`; stops before the read that would cross
+        // read by read up to `end` (at most the end of i's chunk); stops before the read that would cross
+        auto walk = [&](uint32_t end) {
+#ifdef __CUDA_ARCH__
+            // the chunk's 16 classes in one load, their increments fetched together, then the running test in registers
+            const uint32_t c0 = i & ~(ORD_CHUNK - 1u);
+            const uint4 v = *reinterpret_cast<const uint4 *>(cls + c0);  // the buffer is padded to a whole chunk
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            uint64_t d[ORD_CHUNK];
+#pragma unroll
+            for (uint32_t j = 0; j < ORD_CHUNK; ++j) d[j] = inc[(w[j >> 2] >> (8u * (j & 3u))) & (EXACT_MAX_CLS - 1u)];
+#pragma unroll
+            for (uint32_t j = 0; j < ORD_CHUNK; ++j) {
+                if (c0 + j < i || c0 + j >= end || crossed) continue;
+                if (d[j] >= rem - acc) {
+                    crossed = true;
+                } else {
+                    acc += d[j];
+                    ++i;
+                }
+            }
+#else
             while (i < end) {
                 const uint64_t d = inc[cls[i]];
                 if (d >= rem - acc) {
@@ -1186,6 +1212,7 @@ LSQ_HD double ordered_sum(const uint8_t *cls, uint32_t n, const double *term, ui
                 acc += d;
                 ++i;
             }
+#endif
         };
         walk(ord_min(n, (i / ORD_CHUNK + 1u) * ORD_CHUNK));  // to the end of the current chunk
         if (!crossed && i < n) {
@@ -1200,30 +1227,57 @@ LSQ_HD double ordered_sum(const uint8_t *cls, uint32_t n, const double *term, ui
                 }
                 return g < room ? g : room;
             };
-            uint32_t lo = j0, hi = n_chunks;  // span(lo) < room always; find the largest such boundary
-            if (span(hi) < room) {
-                lo = hi;
-            } else {
+            // invariant: span(lo) < room; hi_known: span(hi) >= room.  The answer is the largest boundary below room.
+            uint32_t lo = j0, hi = n_chunks;
+            bool hi_known = false;
+            const uint32_t gs = (guess != nullptr && n_searches < ORD_MAX_GUESS) ? guess[n_searches] : 0u;
 #ifdef __CUDA_ARCH__
-                // on the device a whole warp runs this function on the same arguments (everything above is uniform):
-                // the lanes probe 32 boundaries at once, so the search takes log32 instead of log2 round trips to L2
-                const uint32_t lane = threadIdx.x & 31u;
-                while (hi - lo > 1u) {
-                    const uint32_t step = (hi - lo + 31u) / 32u;
-                    const bool below = span(ord_min(hi, lo + (lane + 1u) * step)) < room;  // true for a prefix of the lanes
-                    const uint32_t nb = (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, below));
-                    const uint32_t nlo = ord_min(hi, lo + nb * step), nhi = ord_min(hi, lo + (nb + 1u) * step);
-                    lo = nlo;
-                    hi = nhi;
-                }
-#else
-                while (hi - lo > 1u) {
-                    const uint32_t mid = lo + (hi - lo) / 2u;
-                    if (span(mid) < room) lo = mid;
-                    else hi = mid;
-                }
-#endif
+            // on the device a whole warp runs this function on the same arguments (everything above is uniform): the
+            // lanes probe 32 boundaries at once -- first a window around the previous sweep's answer, then 32 evenly
+            // spaced ones per round -- so the search takes one or two round trips to L2 instead of log2(n / 16)
+            const uint32_t lane = threadIdx.x & 31u;
+            auto clampb = [&](uint32_t b) { return b <= lo ? lo + 1u : (b > hi ? hi : b); };
+            bool window = gs > lo && gs <= hi;
+            while (lo < hi && !(hi_known && hi - lo == 1u)) {
+                const uint32_t step = (hi - lo + 31u) / 32u;
+                const uint32_t first = gs > lo + 8u ? gs - 8u : lo + 1u;
+                const uint32_t mine = window ? clampb(first + lane) : ord_min(hi, lo + (lane + 1u) * step);
+                const bool below = span(mine) < room;  // true for a prefix of the lanes: the boundaries do not decrease
+                const uint32_t nb = (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, below));
+                const uint32_t b_last_below = __shfl_sync(0xFFFFFFFFu, mine, nb ? (int)nb - 1 : 0);
+                const uint32_t b_first_above = __shfl_sync(0xFFFFFFFFu, mine, nb < 32u ? (int)nb : 31);
+                if (nb) lo = b_last_below;
+                if (nb < 32u) {
+                    hi = b_first_above;
+                    hi_known = true;
+                }  // nb == 32: lo is now lane 31's boundary -- hi itself in an evenly spaced round, which ends the search
+                window = false;
             }
+#else
+            if (gs > lo && gs <= hi) {  // the previous sweep's answer and its successor first
+                if (span(gs) < room) {
+                    lo = gs;
+                    if (gs < hi && !(span(gs + 1u) < room)) {
+                        hi = gs + 1u;
+                        hi_known = true;
+                    }
+                } else {
+                    hi = gs;
+                    hi_known = true;
+                }
+            }
+            if (!hi_known) {
+                if (span(hi) < room) lo = hi;
+                else hi_known = true;
+            }
+            while (hi - lo > 1u) {
+                const uint32_t mid = lo + (hi - lo) / 2u;
+                if (span(mid) < room) lo = mid;
+                else hi = mid;
+            }
+#endif
+            if (guess != nullptr && n_searches < ORD_MAX_GUESS) guess[n_searches] = lo;
+            ++n_searches;
             acc += span(lo);
             i = ord_min(n, lo * ORD_CHUNK);
             if (i < n) walk(ord_min(n, (lo + 1u) * ORD_CHUNK));  // the crossing read is in this chunk

@@ -597,37 +597,66 @@ __global__ void __launch_bounds__(SCAN_BLOCK, 4) lsq_route_kernel(const __grid_c
             else cs[k] = r < g1 ? __ldcs(P.read_cs + r) : 0u;
             base[k] = o;
             o += rn[k];
-            unsigned long long m = 0ull;
+        }
+        // owner mask of block `at` of read k, stage by stage so that the four reads' lookups are in flight together
+        auto owners_of = [&](const int2 b, const uint32_t c, const Probe q, const uint2 e) -> uint32_t {
+            const uint32_t p = piece_of(P, b, c, q, e);
+            // a piece without candidate events (no PIECE_CAND) has no stab entry, hence no owner: no need to look at its record
+            return p == PIECE_NONE ? 0u : (uint32_t)__ldg(R.owner + p);  // at most ROUTE_MAX_RANKS = 16 ranks
+        };
+        {
+            int2 b[SCAN_ITEMS];
+            uint32_t c[SCAN_ITEMS];
+            Probe q[SCAN_ITEMS];
+            uint2 e[SCAN_ITEMS];
+#pragma unroll
+            for (int k = 0; k < SCAN_ITEMS; ++k) {
+                b[k] = rn[k] ? load_block(P, base[k]) : make_int2(0, 0);
+                c[k] = ((rn[k] && (cs[k] & 0x80000000u)) ? __ldg(P.blk_cs + base[k]) : cs[k]) & 0xFFFFu;
+            }
+#pragma unroll
+            for (int k = 0; k < SCAN_ITEMS; ++k) q[k] = probe_of(P, b[k], __ldg(P.file_meta + c[k]));
+#pragma unroll
+            for (int k = 0; k < SCAN_ITEMS; ++k) e[k] = (rn[k] && q[k].how == 1u) ? __ldg(P.T.bp_bkt + q[k].slot) : make_uint2(0u, 0u);
+#pragma unroll
+            for (int k = 0; k < SCAN_ITEMS; ++k) mask[k] = rn[k] ? owners_of(b[k], c[k], q[k], e[k]) : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k)  // the later blocks of spliced reads, one at a time
 #pragma unroll 1
-            for (uint32_t j = 0; j < rn[k]; ++j) {
+            for (uint32_t j = 1; j < rn[k]; ++j) {
                 const int2 b = load_block(P, base[k] + j);
                 const uint32_t c = ((cs[k] & 0x80000000u) ? __ldg(P.blk_cs + base[k] + j) : cs[k]) & 0xFFFFu;
                 const Probe q = probe_of(P, b, __ldg(P.file_meta + c));
                 const uint2 e = q.how == 1u ? __ldg(P.T.bp_bkt + q.slot) : make_uint2(0u, 0u);
-                const uint32_t p = piece_of(P, b, c, q, e);
-                if (p != PIECE_NONE && (__ldg(&pinfo[p].sigw) & PIECE_CAND)) m |= __ldg(R.owner + p);
+                mask[k] |= owners_of(b, c, q, e);
             }
-            mask[k] = (uint32_t)m;  // at most ROUTE_MAX_RANKS = 16 ranks
-        }
         uint32_t present = mask[0] | mask[1] | mask[2] | mask[3];
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) present |= __shfl_xor_sync(0xFFFFFFFFu, present, d);
         if (present == 0u) continue;  // warp-uniform
-        // what I send to destination d: reads << 32 | blocks
-        auto my_load = [&](uint32_t d) {
-            unsigned long long v = 0ull;
+        // what I send to destination d, as one half of a 64-bit word: reads << 20 | blocks (a group holds at most 128 reads
+        // and 32 640 blocks), so ONE warp scan serves two destinations and both passes use its result
+        auto my_half = [&](uint32_t d) {
+            uint32_t v = 0u;
 #pragma unroll
             for (int k = 0; k < SCAN_ITEMS; ++k)
-                if ((mask[k] >> d) & 1u) v += (1ull << 32) | (unsigned long long)rn[k];
+                if ((mask[k] >> d) & 1u) v += (1u << 20) | rn[k];
             return v;
         };
+        auto widen = [](uint32_t half) { return ((unsigned long long)(half >> 20) << 32) | (unsigned long long)(half & 0xFFFFFu); };
         // ---- pass 1: the group's totals per destination; lane d reserves destination d ----------------
+        unsigned long long excl[ROUTE_MAX_RANKS / 2];  // my exclusive prefixes, two destinations per word
         unsigned long long my_total = 0ull;
-#pragma unroll 1
-        for (uint32_t pm = present; pm; pm &= pm - 1u) {
-            const uint32_t d = (uint32_t)__ffs((int)pm) - 1u;
-            const unsigned long long tot = __shfl_sync(0xFFFFFFFFu, warp_incl_scan64(my_load(d), lane), 31);
-            if (lane == d) my_total = tot;
+#pragma unroll
+        for (int w = 0; w < (int)ROUTE_MAX_RANKS / 2; ++w) {
+            excl[w] = 0ull;
+            if ((uint32_t)(2 * w) >= R.n_ranks || !((present >> (2 * w)) & 3u)) continue;  // warp-uniform
+            const unsigned long long v = (unsigned long long)my_half(2 * w) | ((unsigned long long)my_half(2 * w + 1) << 32);
+            const unsigned long long incl = warp_incl_scan64(v, lane);
+            excl[w] = incl - v;
+            const unsigned long long tot = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            if ((lane >> 1) == (uint32_t)w) my_total = widen((lane & 1u) ? (uint32_t)(tot >> 32) : (uint32_t)tot);
         }
         unsigned long long my_rsv = 0ull;
         if (my_total) my_rsv = atomicAdd(R.cursor + lane, my_total);
@@ -635,9 +664,13 @@ __global__ void __launch_bounds__(SCAN_BLOCK, 4) lsq_route_kernel(const __grid_c
 #pragma unroll 1
         for (uint32_t pm = present; pm; pm &= pm - 1u) {
             const uint32_t d = (uint32_t)__ffs((int)pm) - 1u;
-            const unsigned long long v = my_load(d);
-            const unsigned long long at = __shfl_sync(0xFFFFFFFFu, my_rsv, (int)d) + warp_incl_scan64(v, lane) - v;
-            if (v == 0ull) continue;
+            unsigned long long ew = 0ull;
+#pragma unroll
+            for (int w = 0; w < (int)ROUTE_MAX_RANKS / 2; ++w)
+                if ((d >> 1) == (uint32_t)w) ew = excl[w];
+            const unsigned long long at = __shfl_sync(0xFFFFFFFFu, my_rsv, (int)d) + widen((d & 1u) ? (uint32_t)(ew >> 32) : (uint32_t)ew);
+            const uint32_t v = my_half(d);
+            if (v == 0u) continue;
             const RouteBox &B = R.box[d];
             size_t ri = (size_t)(at >> 32), bi = (size_t)(at & 0xFFFFFFFFull);
 #pragma unroll
@@ -1634,12 +1667,19 @@ struct ExactParams {
     uint32_t *pre;            // per event: class counts ahead of every ORD_CHUNK reads (ordered_sum), rows of EXACT_MAX_CLS
     const uint64_t *pre_off;  // [n_flag] first row of the event in pre
     uint32_t presorted;       // the records were sorted and classified by grid-wide launches (large events)
+    uint32_t scalar_sums;     // LSQ_EXACT_SCALAR_SUMS: every lane runs ordered_sum by itself (the form the CPU tests check)
     unsigned long long *ctab; // per event EXACT_CTAB u64: class keys (form mask | read set << 56) in order of discovery, then an overflow flag
     uint32_t sort_k, sort_j;  // lsq_exact_sort_kernel: the step of the bitonic network (j = 0: first step of merge k)
     uint64_t total;           // records of all events
 };
 
 constexpr int EXACT_BLOCK = 256;
+
+// Where the class bytes of flagged event fi start in ExactParams::cls: 16-byte aligned (ordered_sum loads a chunk of 16
+// classes at once) with room for a whole last chunk.
+__device__ __forceinline__ uint64_t exact_cls_offset(uint64_t seg_off_fi, uint32_t fi) {
+    return ((seg_off_fi + 15ull) & ~15ull) + 32ull * fi;
+}
 
 __device__ __forceinline__ void exact_cmpxchg(ExactRec *rec, uint32_t i, uint32_t l) {
     const ExactRec a = rec[i], b = rec[l];
@@ -1694,11 +1734,139 @@ __global__ void __launch_bounds__(256) lsq_exact_classify_kernel(const __grid_co
         unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(tab + q);
         if (cur == 0ull) cur = atomicCAS(tab + q, 0ull, key);
         if (cur == 0ull || cur == key) {
-            X.cls[g] = (uint8_t)q;
+            X.cls[exact_cls_offset(o, lo) + (g - o)] = (uint8_t)q;
             return;
         }
     }
     tab[EXACT_MAX_CLS] = 1ull;  // more classes than the table holds
+}
+
+// ordered_sum (lsq_device_fn.cuh) with the work of a binade spread over the lanes of a warp -- same algorithm, same
+// result: the increments of the classes are computed by the lanes in parallel (into s_inc, 64 entries of this warp), a
+// chunk's 16 reads are taken with one warp scan instead of 16 dependent steps, the boundary search probes 32 places at
+// once.  All lanes call it with the same arguments and get the same value.  cls must be 16-byte aligned.
+__device__ double ordered_sum_warp(const uint8_t *cls, uint32_t n, const double *term, uint32_t stride, uint32_t C,
+                                   const uint32_t *pre, uint32_t *guess, unsigned long long *s_inc) {
+    const uint32_t lane = threadIdx.x & 31u;
+    auto mag = [&](uint32_t c) { return fabs(term[c * stride]); };
+    double s = 0.0;
+    uint32_t i = 0, n_searches = 0;
+    const uint32_t n_chunks = (n + ORD_CHUNK - 1u) / ORD_CHUNK;
+    while (i < n) {
+        if (s == 0.0) {  // 0 + t is exact
+            s = mag(cls[i]);
+            ++i;
+            continue;
+        }
+        int e;
+        (void)frexp(s, &e);
+        const uint64_t S = (uint64_t)ldexp(s, 53 - e);
+        const uint64_t rem = (1ull << 53) - S;
+        bool tie = false;
+        __syncwarp();
+        for (uint32_t c = lane; c < C; c += 32u) {
+            const double sc = ldexp(mag(c), 53 - e);
+            uint64_t v;
+            if (!(sc < 9007199254740992.0)) {
+                v = rem;
+            } else {
+                const double q = floor(sc), r = sc - q;
+                v = (uint64_t)q + (r > 0.5 ? 1ull : 0ull);
+                if (r == 0.5) tie = true;
+                if (v > rem) v = rem;
+            }
+            s_inc[c] = v;
+        }
+        tie = __any_sync(0xFFFFFFFFu, tie);
+        __syncwarp();
+        const double top = ldexp(1.0, e);
+        if (tie || e < -900) {
+            while (i < n && s < top) {
+                s = lsq_add(s, mag(cls[i]));
+                ++i;
+            }
+            continue;
+        }
+        uint64_t acc = 0;
+        bool crossed = false;
+        // the reads [i, end) of i's chunk: lane j < 16 takes position c0 + j; stops before the read that would cross
+        auto walk = [&](uint32_t end) {
+            const uint32_t c0 = i & ~(ORD_CHUNK - 1u), pos = c0 + (lane & (ORD_CHUNK - 1u));
+            const bool valid = lane < ORD_CHUNK && pos >= i && pos < end;
+            const unsigned long long d = valid ? s_inc[cls[pos]] : 0ull;
+            unsigned long long incl = d;
+#pragma unroll
+            for (uint32_t sft = 1; sft < ORD_CHUNK; sft <<= 1) {
+                const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, incl, sft);
+                if (lane >= sft) incl += t;
+            }
+            const uint32_t over = __ballot_sync(0xFFFFFFFFu, valid && incl >= rem - acc);
+            if (over) {
+                const int lc = __ffs((int)over) - 1;
+                acc += __shfl_sync(0xFFFFFFFFu, incl - d, lc);
+                i = c0 + (uint32_t)lc;
+                crossed = true;
+            } else {
+                acc += __shfl_sync(0xFFFFFFFFu, incl, (int)ORD_CHUNK - 1);
+                i = end;
+            }
+        };
+        walk(min(n, (i / ORD_CHUNK + 1u) * ORD_CHUNK));
+        if (!crossed && i < n) {
+            const uint32_t j0 = i / ORD_CHUNK;
+            const uint64_t room = rem - acc;
+            auto span = [&](uint32_t j) {
+                uint64_t g = 0;
+                for (uint32_t c = 0; c < C && g < room; ++c) {
+                    const uint32_t cnt = __ldg(pre + (size_t)j * C + c) - __ldg(pre + (size_t)j0 * C + c);
+                    if (cnt) g += ord_sat_mul(s_inc[c], cnt, room);
+                }
+                return g < room ? g : room;
+            };
+            uint32_t lo = j0, hi = n_chunks;
+            bool hi_known = false;
+            const uint32_t gs = (guess != nullptr && n_searches < ORD_MAX_GUESS) ? guess[n_searches] : 0u;
+            auto clampb = [&](uint32_t b) { return b <= lo ? lo + 1u : (b > hi ? hi : b); };
+            bool window = gs > lo && gs <= hi;
+            while (lo < hi && !(hi_known && hi - lo == 1u)) {
+                const uint32_t step = (hi - lo + 31u) / 32u;
+                const uint32_t first = gs > lo + 8u ? gs - 8u : lo + 1u;
+                const uint32_t mine = window ? clampb(first + lane) : min(hi, lo + (lane + 1u) * step);
+                const bool below = span(mine) < room;
+                const uint32_t nb = (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, below));
+                const uint32_t b_last_below = __shfl_sync(0xFFFFFFFFu, mine, nb ? (int)nb - 1 : 0);
+                const uint32_t b_first_above = __shfl_sync(0xFFFFFFFFu, mine, nb < 32u ? (int)nb : 31);
+                if (nb) lo = b_last_below;
+                if (nb < 32u) {
+                    hi = b_first_above;
+                    hi_known = true;
+                }
+                window = false;
+            }
+            __syncwarp();
+            if (guess != nullptr && n_searches < ORD_MAX_GUESS && lane == 0u) guess[n_searches] = lo;
+            ++n_searches;
+            // span(lo), the lanes sharing the classes
+            {
+                unsigned long long g = 0;
+                for (uint32_t c = lane; c < C; c += 32u) {
+                    const uint32_t cnt = __ldg(pre + (size_t)lo * C + c) - __ldg(pre + (size_t)j0 * C + c);
+                    g += (unsigned long long)cnt * s_inc[c];  // below room in total: no overflow
+                }
+#pragma unroll
+                for (int sft = 16; sft > 0; sft >>= 1) g += __shfl_xor_sync(0xFFFFFFFFu, g, sft);
+                acc += g;
+            }
+            i = min(n, lo * ORD_CHUNK);
+            if (i < n) walk(min(n, (lo + 1u) * ORD_CHUNK));
+        }
+        s = ldexp((double)(S + acc), e - 53);
+        if (crossed) {
+            s = lsq_add(s, mag(cls[i]));
+            ++i;
+        }
+    }
+    return s;
 }
 
 // One block per flagged event (they are few): sort the event's records into the reference's read order, replay the
@@ -1713,13 +1881,16 @@ __global__ void __launch_bounds__(EXACT_BLOCK) lsq_exact_kernel(const __grid_con
     __shared__ uint64_t s_cmask[EXACT_MAX_CLS];
     __shared__ uint32_t s_cset[EXACT_MAX_CLS];
     __shared__ uint32_t s_C, s_tab;
+    __shared__ uint32_t s_guess[EXACT_BLOCK / 32][ORD_MAX_GUESS];  // ordered_sum: binade ends of the previous sweep, per running sum
+    __shared__ unsigned long long s_inc[EXACT_BLOCK / 32][EXACT_MAX_CLS];  // ordered_sum_warp: increments of the classes
     const uint32_t fi = blockIdx.x, t = threadIdx.x, lane = t & 31u;
+    for (uint32_t i = t; i < (EXACT_BLOCK / 32) * ORD_MAX_GUESS; i += EXACT_BLOCK) (&s_guess[0][0])[i] = 0u;
     if (fi >= X.n_flag) return;
     const uint32_t x = X.flag_list[fi];
     const EvHdr h = P.T.hdr[x];
     const uint32_t K = h.K, E = P.T.E;
     ExactRec *rec = X.rec + X.seg_off[fi];
-    uint8_t *cls = X.cls + X.seg_off[fi];
+    uint8_t *cls = X.cls + exact_cls_offset(X.seg_off[fi], fi);
     const uint32_t n = min((uint32_t)(X.seg_off[fi + 1] - X.seg_off[fi]), X.seg_cur[fi]);
     double n_total = 0.0, sum_supports = 0.0;
     for (uint32_t m = 0; m < P.M; ++m) {
@@ -1865,7 +2036,8 @@ __global__ void __launch_bounds__(EXACT_BLOCK) lsq_exact_kernel(const __grid_con
                     fin = fin && (v - v == 0.0);
                 }
                 if (fast_sums && fin && !(pos && neg)) {
-                    acc = ordered_sum(cls, n, tb, W, C, pre);
+                    uint32_t *const gs = a < (uint32_t)(EXACT_BLOCK / 32) ? s_guess[a] : nullptr;
+                    acc = X.scalar_sums ? ordered_sum(cls, n, tb, W, C, pre, gs) : ordered_sum_warp(cls, n, tb, W, C, pre, gs, s_inc[t >> 5]);
                     if (neg && acc != 0.0) acc = -acc;
                 } else {
                     uint32_t i = 0;

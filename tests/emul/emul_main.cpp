@@ -188,10 +188,22 @@ static int ordered_sum_selftest(unsigned seed) {
     }
     double seq = 0.0;
     for (uint32_t i = 0; i < n; ++i) seq = seq + fabs(term[(size_t)cls[i] * stride]);
-    const double fast = lsq::ordered_sum(cls.data(), n, term.data(), stride, C, pre.data());
+    std::vector<uint32_t> guess(lsq::ORD_MAX_GUESS, 0);
+    const double fast = lsq::ordered_sum(cls.data(), n, term.data(), stride, C, pre.data(), (seed & 2) ? guess.data() : nullptr);
     if (memcmp(&seq, &fast, 8) != 0) {
         fprintf(stderr, "ordered_sum selftest: seed %u C %u n %u style %d: %.17g != %.17g\n", seed, C, n, style, fast, seq);
         return 1;
+    }
+    // the next sweep of an EM: slightly different terms, the remembered binade ends of this one (right, nearly right or stale)
+    for (int sweep = 0; sweep < 3; ++sweep) {
+        for (uint32_t c = 0; c < C; ++c) term[(size_t)c * stride] *= 1.0 + (double)((int)(rng() % 2001) - 1000) * (sweep == 2 ? 1e-3 : 1e-9);
+        double seq2 = 0.0;
+        for (uint32_t i = 0; i < n; ++i) seq2 = seq2 + fabs(term[(size_t)cls[i] * stride]);
+        const double fast2 = lsq::ordered_sum(cls.data(), n, term.data(), stride, C, pre.data(), guess.data());
+        if (memcmp(&seq2, &fast2, 8) != 0) {
+            fprintf(stderr, "ordered_sum selftest (remembered ends): seed %u sweep %d: %.17g != %.17g\n", seed, sweep, fast2, seq2);
+            return 1;
+        }
     }
     return 0;
 }

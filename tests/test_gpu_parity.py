@@ -106,6 +106,16 @@ def test_large_fragile_events_match_reference_golden(api, tmp_path):
         ctx.solve([s["total_read_bases"] for s in case["sets"]])
         sol = ctx.get_solve()
         assert ctx.timings()["exact_events"] >= 1, case["name"]
+        # the warp-cooperative running sums (default) and the one-lane form that the CPU selftest checks give the same bits
+        os.environ["LSQ_EXACT_SCALAR_SUMS"] = "1"
+        try:
+            ctx.solve([s["total_read_bases"] for s in case["sets"]])
+            sol_scalar = ctx.get_solve()
+        finally:
+            del os.environ["LSQ_EXACT_SCALAR_SUMS"]
+        for key in ("theta", "loglik", "rpkm"):
+            assert np.array_equal(sol[key].view(np.uint64), sol_scalar[key].view(np.uint64)), (case["name"], key)
+        assert np.array_equal(sol["iters"], sol_scalar["iters"]), case["name"]
         ct, st = format_tables(api, ann, M, cnt, sol, 17)
         assert tables_match(case["expect"]["count17"], ct, False) is None, case["name"]
         bad = tables_match(case["expect"]["solve17"], st, True)
