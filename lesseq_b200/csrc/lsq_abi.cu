@@ -990,6 +990,7 @@ static int exact_replay(lsq_ctx *c, const lsq::SolveParams &P, uint32_t n_flag) 
     X.ctab = reinterpret_cast<unsigned long long *>(c->d_exact_rec.as<uint8_t>() + o_ctab);
     X.total = seg_off[n_flag];
     X.scalar_sums = getenv("LSQ_EXACT_SCALAR_SUMS") ? 1u : 0u;
+    X.debug = timing ? 1u : 0u;
     X.presorted = n_max > 8192 ? 1u : 0u;  // one block sorts a short event by itself; long ones take the whole device
     if (X.presorted) {
         const unsigned grid = (unsigned)((X.total + 255) / 256);

@@ -1151,17 +1151,20 @@ LSQ_HD double ordered_sum(const uint8_t *cls, uint32_t n, const double *term, ui
     const uint32_t n_chunks = (n + ORD_CHUNK - 1u) / ORD_CHUNK;
     uint64_t inc[EXACT_MAX_CLS];
     while (i < n) {
-        if (s == 0.0) {  // 0 + t is exact
-            s = mag(cls[i]);
-            ++i;
-            continue;
-        }
-        int e;  // s = m 2^e, 0.5 <= m < 1: the binade is [2^(e-1), 2^e), u = 2^(e-53)
-        (void)frexp(s, &e);
-        uint64_t S = (uint64_t)ldexp(s, 53 - e);
-        const uint64_t rem = (1ull << 53) - S;  // the sum leaves the binade when the increments reach rem
+        // While s is 0 every zero term leaves it 0 and the first other term is taken exactly (0 + t): the same search with
+        // "increment 1 for a class whose term is not zero" and room for none finds that read (a form whose theta has
+        // gone to 0 has nothing but zero terms: no read is visited at all).
+        const bool zero_mode = s == 0.0;
+        int e = 0;  // s = m 2^e, 0.5 <= m < 1: the binade is [2^(e-1), 2^e), u = 2^(e-53)
+        if (!zero_mode) (void)frexp(s, &e);
+        uint64_t S = zero_mode ? 0ull : (uint64_t)ldexp(s, 53 - e);
+        const uint64_t rem = zero_mode ? 1ull : (1ull << 53) - S;  // the sum leaves the binade when the increments reach rem
         bool tie = false;
         for (uint32_t c = 0; c < C; ++c) {
+            if (zero_mode) {
+                inc[c] = mag(c) != 0.0 ? 1ull : 0ull;
+                continue;
+            }
             const double sc = ldexp(mag(c), 53 - e);  // t / u, exact (or underflows towards 0: far below 1/2)
             if (!(sc < 9007199254740992.0)) {
                 inc[c] = rem;  // t alone leaves the binade
@@ -1173,7 +1176,7 @@ LSQ_HD double ordered_sum(const uint8_t *cls, uint32_t n, const double *term, ui
             }
         }
         const double top = ldexp(1.0, e);
-        if (tie || e < -900) {  // one by one until the binade is left (also near the subnormal range, where u is not 2^(e-53))
+        if (!zero_mode && (tie || e < -900)) {  // one by one until the binade is left (also near the subnormal range, where u is not 2^(e-53))
             while (i < n && s < top) {
                 s = lsq_add(s, mag(cls[i]));
                 ++i;
@@ -1282,7 +1285,7 @@ LSQ_HD double ordered_sum(const uint8_t *cls, uint32_t n, const double *term, ui
             i = ord_min(n, lo * ORD_CHUNK);
             if (i < n) walk(ord_min(n, (lo + 1u) * ORD_CHUNK));  // the crossing read is in this chunk
         }
-        s = ldexp((double)(S + acc), e - 53);  // exact: S + acc < 2^53
+        if (!zero_mode) s = ldexp((double)(S + acc), e - 53);  // exact: S + acc < 2^53
         if (crossed) {
             s = lsq_add(s, mag(cls[i]));
             ++i;

@@ -1668,6 +1668,7 @@ struct ExactParams {
     const uint64_t *pre_off;  // [n_flag] first row of the event in pre
     uint32_t presorted;       // the records were sorted and classified by grid-wide launches (large events)
     uint32_t scalar_sums;     // LSQ_EXACT_SCALAR_SUMS: every lane runs ordered_sum by itself (the form the CPU tests check)
+    uint32_t debug;           // LSQ_EXACT_TIMING: one line per event from the kernel
     unsigned long long *ctab; // per event EXACT_CTAB u64: class keys (form mask | read set << 56) in order of discovery, then an overflow flag
     uint32_t sort_k, sort_j;  // lsq_exact_sort_kernel: the step of the bitonic network (j = 0: first step of merge k)
     uint64_t total;           // records of all events
@@ -1753,21 +1754,19 @@ __device__ double ordered_sum_warp(const uint8_t *cls, uint32_t n, const double 
     uint32_t i = 0, n_searches = 0;
     const uint32_t n_chunks = (n + ORD_CHUNK - 1u) / ORD_CHUNK;
     while (i < n) {
-        if (s == 0.0) {  // 0 + t is exact
-            s = mag(cls[i]);
-            ++i;
-            continue;
-        }
-        int e;
-        (void)frexp(s, &e);
-        const uint64_t S = (uint64_t)ldexp(s, 53 - e);
-        const uint64_t rem = (1ull << 53) - S;
+        const bool zero_mode = s == 0.0;  // skip to the first read whose term is not zero (see ordered_sum)
+        int e = 0;
+        if (!zero_mode) (void)frexp(s, &e);
+        const uint64_t S = zero_mode ? 0ull : (uint64_t)ldexp(s, 53 - e);
+        const uint64_t rem = zero_mode ? 1ull : (1ull << 53) - S;
         bool tie = false;
         __syncwarp();
         for (uint32_t c = lane; c < C; c += 32u) {
-            const double sc = ldexp(mag(c), 53 - e);
+            const double sc = zero_mode ? 0.0 : ldexp(mag(c), 53 - e);
             uint64_t v;
-            if (!(sc < 9007199254740992.0)) {
+            if (zero_mode) {
+                v = mag(c) != 0.0 ? 1ull : 0ull;
+            } else if (!(sc < 9007199254740992.0)) {
                 v = rem;
             } else {
                 const double q = floor(sc), r = sc - q;
@@ -1780,7 +1779,7 @@ __device__ double ordered_sum_warp(const uint8_t *cls, uint32_t n, const double 
         tie = __any_sync(0xFFFFFFFFu, tie);
         __syncwarp();
         const double top = ldexp(1.0, e);
-        if (tie || e < -900) {
+        if (!zero_mode && (tie || e < -900)) {
             while (i < n && s < top) {
                 s = lsq_add(s, mag(cls[i]));
                 ++i;
@@ -1860,7 +1859,7 @@ __device__ double ordered_sum_warp(const uint8_t *cls, uint32_t n, const double 
             i = min(n, lo * ORD_CHUNK);
             if (i < n) walk(min(n, (lo + 1u) * ORD_CHUNK));
         }
-        s = ldexp((double)(S + acc), e - 53);
+        if (!zero_mode) s = ldexp((double)(S + acc), e - 53);
         if (crossed) {
             s = lsq_add(s, mag(cls[i]));
             ++i;
@@ -2035,6 +2034,8 @@ __global__ void __launch_bounds__(EXACT_BLOCK) lsq_exact_kernel(const __grid_con
                     neg = neg || v < 0.0;
                     fin = fin && (v - v == 0.0);
                 }
+                if (X.debug && lane == 0u && !(fast_sums && fin && !(pos && neg)) && fast_sums)
+                    printf("[exact] event %u sum %u of %u: read-by-read sweep (finite %d, positive %d, negative %d)\n", fi, a, W, (int)fin, (int)pos, (int)neg);
                 if (fast_sums && fin && !(pos && neg)) {
                     uint32_t *const gs = a < (uint32_t)(EXACT_BLOCK / 32) ? s_guess[a] : nullptr;
                     acc = X.scalar_sums ? ordered_sum(cls, n, tb, W, C, pre, gs) : ordered_sum_warp(cls, n, tb, W, C, pre, gs, s_inc[t >> 5]);
@@ -2078,6 +2079,7 @@ __global__ void __launch_bounds__(EXACT_BLOCK) lsq_exact_kernel(const __grid_con
         P.theta[h.out_form + t] = th;
         P.rpkm[h.out_form + t] = r;
     }
+    if (t == 0u && X.debug) printf("[exact] event %u: %u reads, %u forms, %u classes, tabulated %u, %u iterations\n", fi, n, K, s_C, s_tab, iters);
     if (t == 0u) {
         P.loglik[h.out_ev] = ll;
         P.ll_per_read[h.out_ev] = (sum_supports > 1E-5) ? __ddiv_rn(ll, sum_supports) : 0.0;

@@ -170,6 +170,10 @@ static int ordered_sum_selftest(unsigned seed) {
         else t = (double)(1 + rng() % 1000) / (double)(1 + rng() % 1000);
         term[(size_t)c * stride] = (seed & 1) ? -t : t;
     }
+    if (seed % 11 == 0)  // a form whose theta went to 0: nothing but zero terms
+        for (uint32_t c = 0; c < C; ++c) term[(size_t)c * stride] = 0.0;
+    if (seed % 11 == 1)  // ... or all but one class
+        for (uint32_t c = 1; c < C; ++c) term[(size_t)c * stride] = (seed & 1) ? -0.0 : 0.0;
     std::vector<uint8_t> cls(n);
     uint32_t run = 0, cur = 0;
     for (uint32_t i = 0; i < n; ++i) {
