@@ -71,6 +71,23 @@ def workload_config(args, world):
     return cfg, R, n, genes
 
 
+def multi_gpu_config(cfg, args, world, n):
+    """BASELINE config 3 for world > 1: ONE read set of fixed size (1 B reads) over all ranks; rank r holds reads
+    [r * total / world, (r + 1) * total / world) of it, whatever events they hit.  Returns (config, reads per GPU,
+    total reads); both arms of the bench print this config."""
+    if world <= 1:
+        return cfg, n, n
+    total_reads = args.reads_total or (args.reads * world if args.reads else 1_000_000_000)
+    n = total_reads // world
+    total_reads = n * world
+    cfg["workload"] = cfg["workload"].replace("C2:", "C3 (C2 genome, one read set of %d reads over %d GPUs):" % (total_reads, world))
+    cfg["reads_total"] = total_reads
+    cfg["reads_per_gpu"] = n
+    cfg["sharding"] = ("gene-rank ranges x%d (events), covered regions of the whole range; every rank holds 1/%d of the read "
+                       "set, buckets it per owning rank on the device and exchanges the buckets over NCCL" % (world, world))
+    return cfg, n, total_reads
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons sampled every 200 ms while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -245,6 +262,7 @@ def run_reference(args):
         return
     world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     cfg, R, n, genes = workload_config(args, world)
+    cfg, n, _ = multi_gpu_config(cfg, args, world, n)  # the same config line as the GPU arm at this N
     tmp = tempfile.mkdtemp(prefix="lsq_ref_")
     try:
         A, R, fp, mp, rp, trb = write_sample(args, tmp)
@@ -263,7 +281,7 @@ def run_reference(args):
                   % (args.sample_reads, n_events, procs))
         line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "i64+f64", "data": "synthetic", "config": cfg,
+                "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "i64+f64", "data": "synthetic", "config": cfg,
                 "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": kind, "sample": sample},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "events_per_sec": n_events / (ms / 1000.0), "gpu_launches": 0}
@@ -309,19 +327,7 @@ def run_ours(args):
     from lesseq_b200 import api, multi, synth
 
     cfg, R, n, genes = workload_config(args, world)
-    if world > 1:
-        # BASELINE config 3: ONE read set of fixed size (1 B reads) over all ranks; rank r holds reads
-        # [r * total / world, (r + 1) * total / world) of it, whatever events they hit
-        total_reads = args.reads_total or (args.reads * world if args.reads else 1_000_000_000)
-        n = total_reads // world
-        total_reads = n * world
-        cfg["workload"] = cfg["workload"].replace("C2:", "C3 (C2 genome, one read set of %d reads over %d GPUs):" % (total_reads, world))
-        cfg["reads_total"] = total_reads
-        cfg["reads_per_gpu"] = n
-        cfg["sharding"] = ("gene-rank ranges x%d (events), covered regions of the whole range; every rank holds 1/%d of the read "
-                           "set, buckets it per owning rank on the device and exchanges the buckets over NCCL" % (world, world))
-    else:
-        total_reads = n
+    cfg, n, total_reads = multi_gpu_config(cfg, args, world, n)
     tmp = tempfile.mkdtemp(prefix="lsq_bench_")
     A, _, _ = synth.make_config(args.workload, n_genes=args.genes)
     fp, mp = os.path.join(tmp, "ev.interval"), os.path.join(tmp, "ev.map")
