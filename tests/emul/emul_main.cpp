@@ -562,12 +562,13 @@ int main(int argc, char **argv) {
                     ll_old = ll;
                 }
                 const bool fragile = em_stop_is_fragile(near, ll, n_total) &&
-                                     !em_result_is_order_free(K, n_total, iters, 0xFFFFFFFFu,
+                                     (getenv("LSQ_EMUL_NO_CERT") != nullptr ||  // test hook: replay what the certificate would clear
+                                      !em_result_is_order_free(K, n_total, iters, 0xFFFFFFFFu,
                                                               [&](auto f) {
                                                                   for (uint32_t m = 0; m < M; ++m)
                                                                       for (auto &kv : hist[m][x]) f(m, (uint64_t)kv.first, (double)kv.second);
                                                               },
-                                                              [&](uint32_t m, uint32_t k) { return Gm[m][h.form_off + k]; });
+                                                              [&](uint32_t m, uint32_t k) { return Gm[m][h.form_off + k]; }));
                 if (fragile && getenv("LSQ_EMUL_STATS"))
                     fprintf(stderr, "emul: fragile event K %u reads %.0f near %.3g ll %.17g iters %u\n", K, n_total, near, ll, iters);
                 if (fragile && !getenv("LSQ_EMUL_NO_EXACT")) {

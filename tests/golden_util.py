@@ -24,7 +24,7 @@ def materialise(case, d):
 
 
 def all_cases():
-    return load("seed.json") + load("fuzz.json") + load("weird.json") + load("em_fragile.json")
+    return load("seed.json") + load("fuzz.json") + load("weird.json") + load("em_fragile.json") + load("em_orderfree.json")
 
 
 def materialise_formats(case, d):

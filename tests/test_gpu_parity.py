@@ -25,7 +25,8 @@ def api():
 
 
 SEED_CASES = golden_util.load("seed.json")
-FUZZ_CASES = golden_util.load("fuzz.json") + golden_util.load("weird.json") + golden_util.load("em_fragile.json")
+FUZZ_CASES = (golden_util.load("fuzz.json") + golden_util.load("weird.json") + golden_util.load("em_fragile.json") +
+              golden_util.load("em_orderfree.json"))
 
 
 @pytest.mark.parametrize("case", SEED_CASES, ids=[c["name"] for c in SEED_CASES])

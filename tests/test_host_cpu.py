@@ -326,6 +326,23 @@ def test_large_fragile_events_replayed_on_cpu_match_reference(emul_bin, tmp_path
         assert p.returncode == 0 and not _close(case["expect"]["solve17"], p.stdout, True), case["name"]
 
 
+def test_order_free_stops_are_certified_not_replayed(emul_bin, tmp_path):
+    """tests/golden/em_orderfree.json (reference binary outputs): forms no longer than a read drive theta to a vertex (or
+    leave it uniform) with a log-likelihood of exactly 0 -- flagged by value (the stop test divides by zero), cleared by
+    em_result_is_order_free.  Same tables with the certificate, with a replay instead of it, and with neither."""
+    for case in golden_util.load("em_orderfree.json"):
+        d = tmp_path / case["name"]
+        d.mkdir()
+        ca, sa = golden_util.materialise(case, str(d))
+        flagged = {}
+        for tag, extra in (("certified", {}), ("replayed", {"LSQ_EMUL_NO_CERT": "1"}), ("neither", {"LSQ_EMUL_NO_EXACT": "1"})):
+            env = dict(os.environ, LSQ_PRECISION="17", LSQ_EMUL_STATS="1", **extra)
+            p = subprocess.run([emul_bin, "solve"] + [str(a) for a in sa], env=env, capture_output=True, text=True)
+            assert p.returncode == 0 and _close(case["expect"]["solve17"], p.stdout, True), (case["name"], tag)
+            flagged[tag] = sum(1 for line in p.stderr.splitlines() if "fragile event" in line)
+        assert flagged["certified"] == 0 and flagged["replayed"] >= 3, (case["name"], flagged)
+
+
 def test_compact_wire_format_is_lossless(tmp_path):
     """lsqh_reads_compact: blk_cnt / read_cs8 / blk_start + blk_len expand to the wide arrays."""
     import ctypes as C
