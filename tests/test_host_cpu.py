@@ -343,6 +343,24 @@ def test_order_free_stops_are_certified_not_replayed(emul_bin, tmp_path):
         assert flagged["certified"] == 0 and flagged["replayed"] >= 3, (case["name"], flagged)
 
 
+def test_ctypes_mirrors_have_the_layout_of_the_c_header(tmp_path):
+    """lesseq_b200/_lib.py mirrors the structs of include/lesseq_b200.h by hand: same size and same offset of the last
+    member, checked against what the C compiler lays out (a field added on one side only would shift everything)."""
+    from lesseq_b200 import _lib
+    pairs = [("lsq_event_tables", _lib.EventTables), ("lsq_packed_reads", _lib.PackedReads), ("lsq_count_out", _lib.CountOut),
+             ("lsq_solve_out", _lib.SolveOut), ("lsq_timings", _lib.Timings), ("lsq_shard_stats", _lib.ShardStats),
+             ("lsq_device_results", _lib.DeviceResults)]
+    src = tmp_path / "layout.c"
+    body = "".join('    printf("%s %%zu %%zu\\n", sizeof(%s), offsetof(%s, %s));\n' % (c, c, c, t._fields_[-1][0]) for c, t in pairs)
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "lesseq_b200.h"\nint main(void) {\n' + body + "    return 0;\n}\n")
+    exe = tmp_path / "layout"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["gcc", "-I", os.path.join(root, "include"), "-o", str(exe), str(src)], check=True)
+    out = dict((ln.split()[0], (int(ln.split()[1]), int(ln.split()[2]))) for ln in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for c, t in pairs:
+        assert out[c] == (C.sizeof(t), getattr(t, t._fields_[-1][0]).offset), (c, out[c], C.sizeof(t))
+
+
 def test_compact_wire_format_is_lossless(tmp_path):
     """lsqh_reads_compact: blk_cnt / read_cs8 / blk_start + blk_len expand to the wide arrays."""
     import ctypes as C
