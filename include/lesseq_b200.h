@@ -163,7 +163,8 @@ typedef struct lsq_solve_out {
 typedef struct lsq_timings {
     float clear_ms, scan_ms, expand_ms, general_ms, finalize_ms, solve_ms;
     uint32_t launches;     /* kernels launched by the last lsq_count + lsq_solve */
-    uint32_t exact_events; /* events whose EM was replayed read by read in the reference's order (fragile stop rule) */
+    uint32_t exact_events; /* events whose EM was replayed read by read in the reference's order: their stop test fell
+                              inside summation-order noise and the run could not be certified order-free */
     uint64_t reads_in, blocks_in;   /* summed over read sets */
     uint64_t reads_single;          /* reads tallied by a single-block signature */
     uint64_t reads_pair;            /* reads tallied by a two-block signature */
@@ -208,7 +209,10 @@ int lsq_set_classes(lsq_ctx *ctx, uint32_t m, uint32_t read_type, uint64_t read_
                     const uint64_t *cls_off /*[E+1]*/, const uint64_t *cls_mask,
                     const uint64_t *cls_cnt, const uint64_t *bases /*[E]*/);
 
-/* EM + RPKM + log-likelihood (solve.cpp:796-826).  total_read_bases[m] is the CLI value. */
+/* EM + RPKM + log-likelihood (solve.cpp:796-826) + standard errors.  total_read_bases[m] is the CLI value.
+ * Theta, RPKM and log-likelihood agree with the reference within 1e-9 relative and the EM runs the reference's number
+ * of iterations for every event: where the stop test is decided inside summation-order noise the event is either
+ * certified order-free or replayed read by read in the reference's own order (one host round trip; lsq_timings). */
 int lsq_solve(lsq_ctx *ctx, const double *total_read_bases, uint32_t n_methods);
 int lsq_get_solve(lsq_ctx *ctx, lsq_solve_out *out);
 
