@@ -499,6 +499,99 @@ static int load_mrf(ReadSet &rs, std::map<std::string, IntervalList> &covered) {
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Standard errors (dump only; no reference program evaluates fim.h, so there is no reference output to pin this
+// to: it restates the reference's FORMULAS so that the product's standard errors have a checker that is not its own).
+// ---------------------------------------------------------------------------------------------
+
+// FIM::ofim, common/fim.h:322-367, summed over the event's valid reads: per read the (K-1)x(K-1) matrix
+// (v_p - v_K)(v_q - v_K) / s^2 with v_k = G_k [read compatible with form k] and s = sum_k theta_k v_k over the
+// terms with v_k > 0 and theta_k > 0; evaluated, like the reference, in the log domain with a sign matrix.
+static bool observed_information(size_t K, const std::vector<Matrix> &mats, const std::vector<double> &theta, Matrix &I) {
+    I.assign(K - 1, std::vector<double>(K - 1, 0.0));
+    for (size_t m = 0; m < mats.size(); ++m)
+        for (size_t i = 0; i < mats[m].size(); ++i) {
+            const std::vector<double> &v = mats[m][i];
+            double sum = 0;
+            for (size_t k = 0; k < K; ++k)
+                if (v[k] > 0 && theta[k] > 0) sum += theta[k] * v[k];
+            if (!(sum > 0)) return false;  // the reference asserts sum > 0
+            const double log_prod = log(sum) + log(sum);
+            for (size_t p = 0; p + 1 < K; ++p)
+                for (size_t q = 0; q + 1 < K; ++q) {
+                    double t = (v[p] - v[K - 1]) * (v[q] - v[K - 1]);
+                    if (t != 0) {
+                        const int sign = t > 0 ? 1 : -1;
+                        if (t < 0) t = -t;
+                        I[p][q] += sign * exp(log(t) - log_prod);
+                    }
+                }
+        }
+    return true;
+}
+
+// linalg::invert_matrix, common/linalg.h:28-71 = gsl_linalg_LU_decomp + gsl_linalg_LU_invert (GSL 1.12): LU with
+// partial pivoting (largest magnitude in the column), then the inverse column by column from the unit vectors.
+static bool lu_invert(const Matrix &A, Matrix &inv) {
+    const size_t n = A.size();
+    Matrix lu = A;
+    std::vector<size_t> perm(n);
+    for (size_t i = 0; i < n; ++i) perm[i] = i;
+    for (size_t j = 0; j + 1 < n || (j < n && n == 1); ++j) {
+        size_t piv = j;
+        double best = fabs(lu[j][j]);
+        for (size_t i = j + 1; i < n; ++i)
+            if (fabs(lu[i][j]) > best) {
+                best = fabs(lu[i][j]);
+                piv = i;
+            }
+        if (piv != j) {
+            std::swap(lu[j], lu[piv]);
+            std::swap(perm[j], perm[piv]);
+        }
+        if (lu[j][j] != 0.0)
+            for (size_t i = j + 1; i < n; ++i) {
+                const double f = lu[i][j] / lu[j][j];
+                lu[i][j] = f;
+                for (size_t c = j + 1; c < n; ++c) lu[i][c] -= f * lu[j][c];
+            }
+        if (n == 1) break;
+    }
+    for (size_t i = 0; i < n; ++i)
+        if (lu[i][i] == 0.0) return false;  // singular
+    inv.assign(n, std::vector<double>(n, 0.0));
+    for (size_t c = 0; c < n; ++c) {  // solve L U x = P e_c
+        std::vector<double> x(n, 0.0);
+        for (size_t i = 0; i < n; ++i) x[i] = perm[i] == c ? 1.0 : 0.0;
+        for (size_t i = 0; i < n; ++i)
+            for (size_t k = 0; k < i; ++k) x[i] -= lu[i][k] * x[k];
+        for (size_t ii = n; ii-- > 0;) {
+            for (size_t k = ii + 1; k < n; ++k) x[ii] -= lu[ii][k] * x[k];
+            x[ii] /= lu[ii][ii];
+        }
+        for (size_t i = 0; i < n; ++i) inv[i][c] = x[i];
+    }
+    return true;
+}
+
+// The variance decomposition of FIM::estimate_mle_variance_by_inv (fim.h:75-93: the sum of all entries of the inverse
+// plus its trace = var(theta_{K-1}) + sum_p var(theta_p)), form by form: se_p = sqrt(inv(p,p)), se_{K-1} = sqrt(sum of
+// all entries).  Returns false where the reference's own code would fail (no reads, s = 0, singular information).
+static bool standard_errors(size_t K, const std::vector<Matrix> &mats, const std::vector<double> &theta, std::vector<double> &se) {
+    se.assign(K, 0.0);
+    if (K == 1) return true;
+    if (mats.empty()) return false;
+    Matrix I, inv;
+    if (!observed_information(K, mats, theta, I) || !lu_invert(I, inv)) return false;
+    double total = 0;
+    for (size_t p = 0; p + 1 < K; ++p) {
+        for (size_t q = 0; q + 1 < K; ++q) total += inv[p][q];
+        se[p] = sqrt(inv[p][p]);
+    }
+    se[K - 1] = sqrt(total);
+    return true;
+}
+
 static int run(bool solve_mode, int argc, char **argv) {
     int group = solve_mode ? 5 : 4;
     if (argc < 10 + group) return fail("Usage error");  // argc < 14 / 15 incl. program name
@@ -723,6 +816,19 @@ static int run(bool solve_mode, int argc, char **argv) {
                 else std::cout << "\t" << 0 << std::endl;
             }
             if (dump) fprintf(dump, "E\t%s\titers\t%lu\n", ev.gname.c_str(), iters);
+            if (dump)  // G records: G_k = 1 / ARS_k per read set, as the S records below use it
+                for (size_t m = 0; m < M; ++m) {
+                    const bool sr = sets[m].type == "SHORT_READ";
+                    for (size_t k = 0; k < K; ++k) {
+                        const unsigned long a = ars_total_length(ev, k, sr, sets[m].read_length);
+                        fprintf(dump, "G\t%s\t%zu\t%zu\t%.17g\n", ev.gname.c_str(), m, k, a ? 1.0 / (double)a : 0.0);
+                    }
+                }
+            if (dump) {  // S records: standard errors from the observed information at the estimate (see standard_errors)
+                std::vector<double> se;
+                const bool ok = standard_errors(K, mats, theta, se);
+                for (size_t k = 0; k < K; ++k) fprintf(dump, "S\t%s\t%zu\t%.17g\n", ev.gname.c_str(), k, ok ? se[k] : NAN);
+            }
         }
         if (dump) {
             for (size_t m = 0; m < M; ++m) {
