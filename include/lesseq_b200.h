@@ -261,7 +261,9 @@ typedef struct lsq_shard_stats {
 /* Buckets read set m_src of `full` (this rank's slice, declared with lsq_set_reads; first_line = line number of
  * its first read in the whole file, 1 for the first slice) per destination rank, exchanges the buckets and
  * declares what arrives as read set m_dst of `shard` (device resident, with the reads' global line numbers).
- * Collective: every rank of the communicator must call it. */
+ * Collective: every rank of the communicator must call it.  Limits: what a rank receives must satisfy
+ * blocks + 2 * reads < 2^32 (LSQ_ERR_RANGE otherwise), and 128 consecutive reads of a slice may hold at most 2^20
+ * blocks in total (always true for the compact layout, whose reads have fewer than 256 blocks). */
 int lsq_shard_reads(lsq_ctx *full, uint32_t m_src, lsq_ctx *shard, uint32_t m_dst, lsq_comm *comm, uint64_t first_line,
                     lsq_shard_stats *stats /* may be NULL */);
 /* Gathers the per-event / per-form results of all shards on `root` in gene-rank order (one NCCL send/recv group;
