@@ -228,7 +228,14 @@ def cli_e2e(args, tmp, torch):
             if rc != 0:
                 raise RuntimeError("bin/%s failed: %s" % (prog, err[-300:]))
             best = dt
-            marks[prog] = {ln.split()[1]: float(ln.split()[2]) for ln in err.splitlines() if ln.startswith("[timing]")}
+            marks[prog] = {}
+            for ln in err.splitlines():  # "[timing] <milestone> <ms since start>"
+                f = ln.split()
+                if len(f) >= 3 and f[0] == "[timing]":
+                    try:
+                        marks[prog]["_".join(f[1:-1])] = float(f[-1])
+                    except ValueError:
+                        pass
         walls[prog] = best
         rows[prog] = out.count("\n")
     ref = {}

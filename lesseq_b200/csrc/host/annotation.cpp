@@ -15,6 +15,7 @@
 //     selected events (count.cpp:244) -- the read load filter.
 #include "annotation.hpp"
 
+#include <chrono>
 #include <algorithm>
 #include <climits>
 #include <cstdio>
@@ -269,6 +270,11 @@ int load_annotation(const char *forms_path, const char *map_path, uint64_t begin
 int load_annotation_fmt(const char *forms_format, const char *forms_path, const char *map_format, const char *map_path,
                         uint64_t begin, uint64_t end, uint64_t shard_begin, uint64_t shard_end, lsqh_annotation &A) {
     const std::string ffmt = forms_format ? forms_format : "", mfmt = map_format ? map_format : "";
+    const bool timing = getenv("LSQ_CLI_TIMING") != nullptr;  // milestones of the loader on stderr
+    const auto t0 = std::chrono::steady_clock::now();
+    auto mark = [&](const char *what) {
+        if (timing) fprintf(stderr, "[timing] annotation_%s %.1f\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    };
     // An EMPTY file passes the reference's `assert(ifs.is_open() && !ifs.eof())` (eof is only set by a read): it
     // simply yields no rows -- no forms, or no genes and therefore no output (verified against bin/count, bin/solve).
     FileLines ff(forms_path);
@@ -290,8 +296,10 @@ int load_annotation_fmt(const char *forms_format, const char *forms_path, const 
         set_error("Unknown file format error: " + ffmt);
         return LSQ_ERR_FORMAT;
     }
+    mark("forms_parsed");
     std::unordered_map<std::string, size_t> name2row;  // later duplicates win (count.cpp:176-179)
     for (size_t i = 0; i < rows.size(); ++i) name2row[rows[i].name] = i;
+    mark("forms_indexed");
 
     FileLines mf(map_path);
     if (!mf.ok) {
@@ -327,6 +335,7 @@ int load_annotation_fmt(const char *forms_format, const char *forms_path, const 
         }
     });
 
+    mark("map_parsed");
     std::vector<const std::pair<const std::string, std::vector<long> > *> selected;
     {
         uint64_t rank = 0;
@@ -421,6 +430,7 @@ int load_annotation_fmt(const char *forms_format, const char *forms_path, const 
         }
         A.ev_form_off.push_back((uint32_t)A.form_name.size());
     }
+    mark("events_built");
     if (covered.size() < A.chroms.names.size()) covered.resize(A.chroms.names.size());
     A.cov_off.push_back(0);
     for (auto &c : covered) {
