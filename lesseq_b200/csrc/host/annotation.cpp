@@ -16,6 +16,8 @@
 #include "annotation.hpp"
 
 #include <chrono>
+#include <atomic>
+#include <thread>
 #include <algorithm>
 #include <climits>
 #include <cstdio>
@@ -113,15 +115,36 @@ struct FileLines {  // '\n'-terminated lines only
     }
     template <class F>
     void each(F fn) const {
-        size_t i = 0;
-        while (i < buf.size()) {
+        each_range(0, buf.size(), fn);
+    }
+    // the lines that START in [from, to) (from is a line start)
+    template <class F>
+    void each_range(size_t from, size_t to, F fn) const {
+        size_t i = from;
+        while (i < to) {
             size_t j = buf.find('\n', i);
             if (j == std::string::npos) break;  // unterminated last line: dropped
             fn(buf.data() + i, j - i);
             i = j + 1;
         }
     }
+    // n + 1 line starts that cut the buffer into n pieces of about equal size
+    std::vector<size_t> cut(size_t n) const {
+        std::vector<size_t> c(n + 1, buf.size());
+        c[0] = 0;
+        for (size_t k = 1; k < n; ++k) {
+            size_t j = buf.find('\n', std::max(c[k - 1], buf.size() * k / n));
+            c[k] = j == std::string::npos ? buf.size() : j + 1;
+        }
+        return c;
+    }
 };
+
+unsigned host_threads() {
+    unsigned t = std::thread::hardware_concurrency();
+    if (const char *e = getenv("LSQ_THREADS")) t = (unsigned)std::max(1, atoi(e));
+    return std::max(1u, std::min(t, 64u));
+}
 
 inline bool is_ws(char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\v' || c == '\f' || c == '\n'; }
 
@@ -166,7 +189,13 @@ namespace {
 // cdsStart cdsEnd): one form per line, name chrom strand txStart txEnd [cdsStart cdsEnd] exonCount starts ends.
 // A column that does not parse as a number ends the row as `istream >>` does: the fields after it stay empty.
 void read_gene_txt(const FileLines &ff, bool with_cds, std::vector<FormRow> &rows) {
-    ff.each([&](const char *s, size_t n) {
+    // the lines are independent: every thread parses a stretch of the file, the rows are joined in file order
+    const unsigned T = ff.buf.size() < (1u << 20) ? 1u : host_threads();
+    const std::vector<size_t> cuts = ff.cut(T);
+    std::vector<std::vector<FormRow> > part(T);
+    auto work = [&](unsigned t) {
+        std::vector<FormRow> &rows = part[t];
+        ff.each_range(cuts[t], cuts[t + 1], [&](const char *s, size_t n) {
         Tokens tk(s, n);
         FormRow r;
         std::string t, cnt, es, ee;
@@ -179,7 +208,17 @@ void read_gene_txt(const FileLines &ff, bool with_cds, std::vector<FormRow> &row
             if (tk.next(ee)) split_exon_list(ee, r.ends);
         }
         rows.push_back(std::move(r));
-    });
+        });
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < T; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th) x.join();
+    size_t total = 0;
+    for (auto &p : part) total += p.size();
+    rows.reserve(rows.size() + total);
+    for (auto &p : part)
+        for (auto &r : p) rows.push_back(std::move(r));
 }
 
 // The GFF-like formats give one exon per line; the exons of a form are merged with interval_list semantics
@@ -348,7 +387,10 @@ int load_annotation_fmt(const char *forms_format, const char *forms_path, const 
     shard_end = std::min<uint64_t>(shard_end, selected.size());
     shard_begin = std::min(shard_begin, shard_end);
 
-    std::vector<IntervalSet> covered;  // by chromosome id
+    // covered regions by chromosome id: add_interval depends on the ORDER of the adds (it merges an adjacent interval only
+    // when the later one is appended), but the chromosomes are independent -- the adds are recorded in event order and
+    // replayed per chromosome, the chromosomes side by side
+    std::vector<std::vector<std::pair<long, long> > > cov_adds;
     A.ev_seg_off.push_back(0);
     A.ev_form_off.push_back(0);
     A.ev_name_off.push_back(0);
@@ -370,7 +412,7 @@ int load_annotation_fmt(const char *forms_format, const char *forms_path, const 
                 return LSQ_ERR_ARG;
             }
             uint32_t cid = A.chroms.intern(r.chrom);
-            if (covered.size() <= cid) covered.resize(cid + 1);
+            if (cov_adds.size() <= cid) cov_adds.resize(cid + 1);
             for (uint64_t i = 0; i < r.exon_count; ++i) {
                 long s = r.starts[i], e = r.ends[i];
                 if (s > e) {
@@ -381,7 +423,7 @@ int load_annotation_fmt(const char *forms_format, const char *forms_path, const 
                     set_error("form " + r.name + ": coordinate outside int32");
                     return LSQ_ERR_RANGE;
                 }
-                covered[cid].add(s, e);
+                cov_adds[cid].push_back(std::make_pair(s, e));
                 if (in_shard) insert_exon(segs, s, e);
                 if (s < e) {
                     gs = std::min(gs, s);
@@ -431,7 +473,20 @@ int load_annotation_fmt(const char *forms_format, const char *forms_path, const 
         A.ev_form_off.push_back((uint32_t)A.form_name.size());
     }
     mark("events_built");
-    if (covered.size() < A.chroms.names.size()) covered.resize(A.chroms.names.size());
+    std::vector<IntervalSet> covered(std::max(cov_adds.size(), A.chroms.names.size()));
+    {
+        std::atomic<size_t> next(0);
+        auto work = [&]() {
+            for (size_t c = next++; c < cov_adds.size(); c = next++)
+                for (auto &iv : cov_adds[c]) covered[c].add(iv.first, iv.second);
+        };
+        const unsigned T = std::min<size_t>(host_threads(), std::max<size_t>(cov_adds.size(), 1));
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < T; ++t) th.emplace_back(work);
+        work();
+        for (auto &x : th) x.join();
+    }
+    mark("covered_regions");
     A.cov_off.push_back(0);
     for (auto &c : covered) {
         for (size_t i = 0; i < c.starts.size(); ++i) {

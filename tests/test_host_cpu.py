@@ -361,6 +361,39 @@ def test_ctypes_mirrors_have_the_layout_of_the_c_header(tmp_path):
         assert out[c] == (C.sizeof(t), getattr(t, t._fields_[-1][0]).offset), (c, out[c], C.sizeof(t))
 
 
+def test_annotation_loader_is_thread_count_independent(tmp_path):
+    """lsqh_annotation_load parses the forms file in stretches and replays the covered-region adds chromosome by
+    chromosome on several threads (annotation.cpp): one thread and eight give identical tables -- the rows keep
+    file order and every chromosome sees its adds in event order (interval_list add_interval is order-dependent)."""
+    from lesseq_b200 import api, synth
+    A, _, _ = synth.make_config("C2", n_genes=4000)
+    fp, mp = str(tmp_path / "ev.interval"), str(tmp_path / "ev.map")
+    A.write(fp, mp)
+    assert os.path.getsize(fp) > (1 << 20)  # large enough for the parallel parse
+
+    def load(threads):
+        os.environ["LSQ_THREADS"] = str(threads)
+        try:
+            a = api.Annotation(fp, mp)
+        finally:
+            del os.environ["LSQ_THREADS"]
+        t = a.tables
+        arrays = {"ev_chrom": t.n_events, "ev_strand": t.n_events, "ev_gs": t.n_events, "ev_ge": t.n_events,
+                  "ev_seg_off": t.n_events + 1, "ev_form_off": t.n_events + 1, "seg_start": t.n_segments, "seg_end": t.n_segments,
+                  "form_seg_off": t.n_forms + 1, "cov_off": t.n_chroms + 1}
+        out = {k: a.array(k, n) for k, n in arrays.items()}
+        out["form_seg_idx"] = a.array("form_seg_idx", int(out["form_seg_off"][-1]))
+        out["cov_start"] = a.array("cov_start", int(out["cov_off"][-1]))
+        out["cov_end"] = a.array("cov_end", int(out["cov_off"][-1]))
+        return out, a.event_names(), a.form_names(), a.form_lengths()
+
+    one, eight = load(1), load(8)
+    assert one[1] == eight[1] and one[2] == eight[2] and np.array_equal(one[3], eight[3])
+    assert one[0]["ev_gs"].size > 10000 and one[0]["cov_start"].size > 10000
+    for k in one[0]:
+        assert np.array_equal(one[0][k], eight[0][k]), k
+
+
 def test_compact_wire_format_is_lossless(tmp_path):
     """lsqh_reads_compact: blk_cnt / read_cs8 / blk_start + blk_len expand to the wide arrays."""
     import ctypes as C
