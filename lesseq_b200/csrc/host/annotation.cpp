@@ -337,6 +337,7 @@ int load_annotation_fmt(const char *forms_format, const char *forms_path, const 
     }
     mark("forms_parsed");
     std::unordered_map<std::string, size_t> name2row;  // later duplicates win (count.cpp:176-179)
+    name2row.reserve(rows.size() * 2);
     for (size_t i = 0; i < rows.size(); ++i) name2row[rows[i].name] = i;
     mark("forms_indexed");
 
