@@ -352,12 +352,16 @@ int load_annotation_fmt(const char *forms_format, const char *forms_path, const 
     }
     const bool wb_map = mfmt == "WORMBASE_GENE2ISOFORMS";  // `gene form;form;...` (solve.cpp:318-329)
     std::map<std::string, std::vector<long> > ev2rows;  // std::map: bytewise lexicographic order
+    std::pair<const std::string, std::vector<long> > *last = nullptr;  // the rows of one event usually follow each other
+    std::string g, f;
     mf.each([&](const char *s, size_t n) {
         Tokens tk(s, n);
-        std::string g, f;
+        g.clear();
+        f.clear();
         tk.next(g);
         tk.next(f);
-        std::vector<long> &dst = ev2rows[g];
+        if (last == nullptr || last->first != g) last = &*ev2rows.emplace(g, std::vector<long>()).first;
+        std::vector<long> &dst = last->second;
         auto push = [&](const std::string &name) {
             auto it = name2row.find(name);
             dst.push_back(it == name2row.end() ? -1 : (long)it->second);
