@@ -3,6 +3,8 @@
 // into the sorted internal arrays the kernels read: event headers, segments, form masks /
 // prefix counts, tie-break data, class-slot layout and the stab arrangement.
 #pragma once
+#include <atomic>
+#include <thread>
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -218,6 +220,7 @@ inline int build_host_tables(const lsq_event_tables *t, HostTables &H, std::stri
     form_seg_off.assign(1, 0);
     std::string tie_pool;
     uint64_t slot_total = 0;
+    std::vector<uint32_t> member;  // scratch of the loop below
     for (uint32_t ie = 0; ie < E; ++ie) {
         const uint32_t e = order[ie];
         lsq::EvHdr &h = hdr[ie];
@@ -263,7 +266,7 @@ inline int build_host_tables(const lsq_event_tables *t, HostTables &H, std::stri
         for (uint32_t k = 0; k < K; ++k) {
             const uint32_t a = t->form_seg_off[f0 + k], b = t->form_seg_off[f0 + k + 1];
             uint64_t mask = 0, len = 0;
-            std::vector<uint32_t> member(S + 1, 0);
+            member.assign(S + 1, 0);
             uint32_t prev = 0;
             for (uint32_t q = a; q < b; ++q) {
                 uint32_t si = t->form_seg_idx[q];
@@ -320,17 +323,33 @@ inline int build_host_tables(const lsq_event_tables *t, HostTables &H, std::stri
     stab.clear();
     bp_pos.clear();
     {
-        uint32_t ie = 0;
-        for (uint32_t ch = 0; ch < t->n_chroms; ++ch) {
-            bp_chrom_off[ch] = (uint32_t)bp_pos.size();
-            uint32_t first = ie;
-            while (ie < E && t->ev_chrom[order[ie]] == ch) ++ie;
+        // the chromosomes are independent: each builds its pieces and stab lists into its own buffers (several threads),
+        // then the buffers are joined in chromosome order
+        std::vector<uint32_t> ch_first(t->n_chroms + 1, E);
+        {
+            uint32_t ie = 0;
+            for (uint32_t ch = 0; ch < t->n_chroms; ++ch) {
+                ch_first[ch] = ie;
+                while (ie < E && t->ev_chrom[order[ie]] == ch) ++ie;
+            }
+            ch_first[t->n_chroms] = ie;
+            if (ie != E) return tfail(err, LSQ_ERR_ARG, "event chromosome ids must be < n_chroms");
+        }
+        struct ChromPart {
             std::vector<int32_t> bps;
+            std::vector<StabEntry> stab;
+            std::vector<uint32_t> end;  // entries of pieces 0..p, per piece
+        };
+        std::vector<ChromPart> part(t->n_chroms);
+        auto build_chrom = [&](uint32_t ch) {
+            ChromPart &P = part[ch];
+            const uint32_t first = ch_first[ch], last = ch_first[ch + 1];
+            std::vector<int32_t> &bps = P.bps;
             for (uint32_t q = t->cov_off[ch]; q < t->cov_off[ch + 1]; ++q) {
                 bps.push_back(t->cov_start[q]);
                 bps.push_back(t->cov_end[q]);
             }
-            for (uint32_t q = first; q < ie; ++q) {
+            for (uint32_t q = first; q < last; ++q) {
                 bps.push_back(hdr[q].gs);
                 bps.push_back(hdr[q].ge + 1);
                 for (uint32_t j = 0; j < hdr[q].S; ++j) {
@@ -340,9 +359,25 @@ inline int build_host_tables(const lsq_event_tables *t, HostTables &H, std::stri
             }
             std::sort(bps.begin(), bps.end());
             bps.erase(std::unique(bps.begin(), bps.end()), bps.end());
-            std::vector<std::vector<StabEntry> > lists(bps.size());
-            uint64_t total = 0;
-            for (uint32_t q = first; q < ie; ++q) {
+            // the entries of a piece in the order (event, segment) they are met: count, offsets, fill
+            std::vector<uint32_t> cnt(bps.size() + 1, 0);
+            std::vector<std::pair<uint32_t, uint32_t> > range;  // piece range of every non-empty segment, in that order
+            for (uint32_t q = first; q < last; ++q) {
+                const EvHdr &h = hdr[q];
+                const int2 *sg = seg.data() + h.seg_off;
+                for (uint32_t j = 0; j < h.S; ++j) {
+                    if (!(sg[j].x < sg[j].y)) continue;
+                    const uint32_t a = (uint32_t)(std::lower_bound(bps.begin(), bps.end(), sg[j].x) - bps.begin());
+                    const uint32_t b = (uint32_t)(std::lower_bound(bps.begin() + a, bps.end(), sg[j].y) - bps.begin());
+                    range.push_back(std::make_pair(a, b));
+                    for (uint32_t p = a; p < b; ++p) cnt[p + 1]++;
+                }
+            }
+            for (size_t p = 0; p < bps.size(); ++p) cnt[p + 1] += cnt[p];
+            P.stab.resize(cnt[bps.size()]);
+            std::vector<uint32_t> cur(cnt.begin(), cnt.end() - 1);
+            size_t ri = 0;
+            for (uint32_t q = first; q < last; ++q) {
                 const EvHdr &h = hdr[q];
                 const int2 *sg = seg.data() + h.seg_off;
                 for (uint32_t j = 0; j < h.S; ++j) {
@@ -350,26 +385,40 @@ inline int build_host_tables(const lsq_event_tables *t, HostTables &H, std::stri
                     StabEntry en;
                     en.x = q;
                     en.meta = j & 0xFFFFu;
-                    size_t a = std::lower_bound(bps.begin(), bps.end(), sg[j].x) - bps.begin();
-                    size_t b = std::lower_bound(bps.begin(), bps.end(), sg[j].y) - bps.begin();
-                    for (size_t p = a; p < b; ++p) {
+                    const std::pair<uint32_t, uint32_t> r = range[ri++];
+                    for (uint32_t p = r.first; p < r.second; ++p) {
                         StabEntry e2 = en;
                         if (bps[p] == h.gs) e2.meta |= SE_AT_GS;
-                        lists[p].push_back(e2);
+                        P.stab[cur[p]++] = e2;
                     }
-                    total += b - a;
-                    if (stab.size() + total > 0x3FFFFFFFull)
-                        return tfail(err, LSQ_ERR_RANGE, "stab lists exceed 2^30 entries (too many nested events)");
                 }
             }
-            for (size_t p = 0; p < bps.size(); ++p) {
-                bp_pos.push_back(bps[p]);
-                stab.insert(stab.end(), lists[p].begin(), lists[p].end());
-                stab_off.push_back((uint32_t)stab.size());
-            }
+            P.end.assign(cnt.begin() + 1, cnt.end());
+        };
+        {
+            std::atomic<uint32_t> next(0);
+            auto work = [&]() {
+                for (uint32_t ch = next++; ch < t->n_chroms; ch = next++) build_chrom(ch);
+            };
+            unsigned T = std::thread::hardware_concurrency();
+            if (const char *e = getenv("LSQ_THREADS")) T = (unsigned)std::max(1, atoi(e));
+            T = std::max(1u, std::min(T, std::min(64u, std::max(t->n_chroms, 1u))));
+            std::vector<std::thread> th;
+            for (unsigned i = 1; i < T; ++i) th.emplace_back(work);
+            work();
+            for (auto &x : th) x.join();
+        }
+        for (uint32_t ch = 0; ch < t->n_chroms; ++ch) {
+            const ChromPart &P = part[ch];
+            bp_chrom_off[ch] = (uint32_t)bp_pos.size();
+            if (stab.size() + P.stab.size() > 0x3FFFFFFFull)
+                return tfail(err, LSQ_ERR_RANGE, "stab lists exceed 2^30 entries (too many nested events)");
+            const size_t stab0 = stab.size();
+            bp_pos.insert(bp_pos.end(), P.bps.begin(), P.bps.end());
+            stab.insert(stab.end(), P.stab.begin(), P.stab.end());
+            for (size_t p = 0; p < P.end.size(); ++p) stab_off.push_back((uint32_t)(stab0 + P.end[p]));
         }
         bp_chrom_off[t->n_chroms] = (uint32_t)bp_pos.size();
-        if (ie != E) return tfail(err, LSQ_ERR_ARG, "event chromosome ids must be < n_chroms");
     }
     H.cov_off.assign(t->cov_off, t->cov_off + t->n_chroms + 1);
     H.cov_start.assign(t->cov_start, t->cov_start + H.cov_off.back());
@@ -383,6 +432,7 @@ inline int build_host_tables(const lsq_event_tables *t, HostTables &H, std::stri
     H.pinfo.assign(H.bp_pos.size() + 1, PieceInfo());  // one sentinel: clamped candidate loads stay in bounds
     H.sig_cut.clear();
     H.sig_piece.clear();
+    std::vector<int32_t> cuts;  // scratch of the loop below
     for (uint32_t ch = 0; ch < t->n_chroms; ++ch) {
         const int32_t *cs = H.cov_start.data() + H.cov_off[ch], *ce = H.cov_end.data() + H.cov_off[ch];
         const size_t nc = H.cov_off[ch + 1] - H.cov_off[ch];
@@ -395,7 +445,7 @@ inline int build_host_tables(const lsq_event_tables *t, HostTables &H, std::stri
             pi.cutw = 0;
             if (H.stab_off[p + 1] == H.stab_off[p]) continue;
             // cut list: the segment ends of every entry's chain of abutting segments (lsq_types.cuh: PieceInfo)
-            std::vector<int32_t> cuts;
+            cuts.clear();
             bool tie = false;
             for (uint32_t q = H.stab_off[p]; q < H.stab_off[p + 1]; ++q) {
                 const StabEntry &en = H.stab[q];

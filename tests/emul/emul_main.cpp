@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <map>
+#include <chrono>
 #include <random>
 #include <string>
 #include <vector>
@@ -321,7 +322,10 @@ int main(int argc, char **argv) {
     lsq_event_tables t = tables_of(ann);
     HostTables H;
     std::string err;
+    const auto tb0 = std::chrono::steady_clock::now();
     rc = build_host_tables(&t, H, err);
+    if (getenv("LSQ_CLI_TIMING"))
+        fprintf(stderr, "[timing] emul_host_tables_ms %.1f\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tb0).count());
     if (rc) {
         fprintf(stderr, "emul: %s\n", err.c_str());
         return 1;
